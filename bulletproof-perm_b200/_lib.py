@@ -1,0 +1,74 @@
+"""ctypes loader for libbpperm_cuda.so (the C ABI in include/bpperm.h).
+
+There is no CPU fallback: if the shared library is missing, or no sm_100 device is
+visible, the product path raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbpperm_cuda.so")
+
+# every symbol include/bpperm.h declares (tests check that the .so exports all of them)
+SYMBOLS = [
+    "bpp_init", "bpp_free", "bpp_set_stream", "bpp_synchronize", "bpp_strerror", "bpp_last_error",
+    "bpp_launch_count", "bpp_device_info", "bpp_points_upload", "bpp_points_from_uniform", "bpp_points_compress", "bpp_points_free", "bpp_points_len",
+    "bpp_msm_vartime", "bpp_msm_vartime_host", "bpp_msm_vartime_dev", "bpp_msm_partial_dev",
+    "bpp_points_sum_compress_dev", "bpp_set_window_bits", "bpp_bench_imad_peak", "bpp_set_profiling",
+    "bpp_last_phase_ms", "bpp_last_op_counts", "bpp_test_op",
+]
+
+_lib = None
+
+
+class BppError(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"bpperm status {status}: {msg}")
+        self.status = status
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing - build it with `python -c 'import __graft_entry__ as g; g.build()'`; "
+            "this backend has no CPU fallback")
+    lib = ctypes.CDLL(LIB_PATH)
+    c = ctypes
+    vp, sz, u8p = c.c_void_p, c.c_size_t, c.c_char_p
+    lib.bpp_init.argtypes = [c.c_int, c.POINTER(vp)]
+    lib.bpp_free.argtypes = [vp]
+    lib.bpp_free.restype = None
+    lib.bpp_set_stream.argtypes = [vp, vp]
+    lib.bpp_synchronize.argtypes = [vp]
+    lib.bpp_strerror.argtypes = [c.c_int]
+    lib.bpp_strerror.restype = c.c_char_p
+    lib.bpp_last_error.argtypes = [vp]
+    lib.bpp_last_error.restype = c.c_char_p
+    lib.bpp_launch_count.argtypes = [vp]
+    lib.bpp_launch_count.restype = c.c_uint64
+    lib.bpp_device_info.argtypes = [vp, c.POINTER(c.c_int), c.POINTER(c.c_int), c.POINTER(c.c_int), c.POINTER(sz)]
+    lib.bpp_points_upload.argtypes = [vp, c.c_int, u8p, sz, c.POINTER(vp)]
+    lib.bpp_points_from_uniform.argtypes = [vp, u8p, sz, c.POINTER(vp)]
+    lib.bpp_points_compress.argtypes = [vp, vp, sz, sz, c.c_char_p]
+    lib.bpp_points_free.argtypes = [vp, vp]
+    lib.bpp_points_free.restype = None
+    lib.bpp_points_len.argtypes = [vp]
+    lib.bpp_points_len.restype = sz
+    lib.bpp_msm_vartime.argtypes = [vp, u8p, sz, vp, sz, sz, c.c_char_p, c.c_char_p]
+    lib.bpp_msm_vartime_host.argtypes = [vp, u8p, sz, c.c_int, u8p, sz, c.c_char_p]
+    lib.bpp_msm_vartime_dev.argtypes = [vp, vp, vp, sz, sz, vp]
+    lib.bpp_msm_partial_dev.argtypes = [vp, vp, vp, sz, sz, vp]
+    lib.bpp_points_sum_compress_dev.argtypes = [vp, vp, sz, vp]
+    lib.bpp_set_window_bits.argtypes = [vp, c.c_int]
+    lib.bpp_bench_imad_peak.argtypes = [vp, c.c_int, c.POINTER(c.c_double), c.POINTER(c.c_double)]
+    lib.bpp_set_profiling.argtypes = [vp, c.c_int]
+    lib.bpp_last_phase_ms.argtypes = [vp, c.POINTER(c.c_float)]
+    lib.bpp_last_op_counts.argtypes = [vp, c.POINTER(c.c_uint64), c.POINTER(c.c_uint64), c.POINTER(c.c_uint64)]
+    lib.bpp_test_op.argtypes = [vp, c.c_int, u8p, u8p, c.c_char_p, sz]
+    _lib = lib
+    return lib

@@ -1,0 +1,182 @@
+"""Host-side handle on the CUDA backend: the Python mirror of the reference's operator boundary.
+
+`Backend.vartime_multiscalar_mul(scalars, points)` has the argument meaning and error behaviour of
+`RistrettoPoint::vartime_multiscalar_mul` (dalek-ng 4.1.1 traits.rs; called at
+/root/reference/bp-perm/src/circuit_lib.rs:187-568): equal-length iterables of scalars and points,
+a length mismatch is an error (dalek asserts), an undecodable point is an error (dalek:
+`decompress().unwrap()` panics, circuit_lib.rs:532), the result is one Ristretto point - returned
+here in its canonical 32-byte encoding.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Iterable, Sequence, Union
+
+from . import _lib
+
+FMT_COMPRESSED, FMT_AFFINE, FMT_DALEK_XYZT = 0, 1, 2
+_FMT_BYTES = {FMT_COMPRESSED: 32, FMT_AFFINE: 64, FMT_DALEK_XYZT: 160}
+PHASES = ["recode", "scan", "scatter", "accumulate", "reduce", "finish"]
+
+ScalarLike = Union[int, bytes]
+
+
+def scalars_to_bytes(scalars: Iterable[ScalarLike]) -> bytes:
+    out = bytearray()
+    for s in scalars:
+        if isinstance(s, int):
+            out += s.to_bytes(32, "little")
+        else:
+            if len(s) != 32:
+                raise ValueError("scalar must be 32 bytes")
+            out += s
+    return bytes(out)
+
+
+class Points:
+    """Device-resident point table (affine Niels); upload once, reuse across MSMs."""
+
+    def __init__(self, backend: "Backend", handle: int, n: int):
+        self._backend, self._h, self.n = backend, handle, n
+
+    def __len__(self):
+        return self.n
+
+    def free(self):
+        if self._h:
+            self._backend._lib.bpp_points_free(self._backend._ctx, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Backend:
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        ctx = ctypes.c_void_p()
+        rc = self._lib.bpp_init(device, ctypes.byref(ctx))
+        if rc != 0:
+            raise _lib.BppError(rc, self._lib.bpp_strerror(rc).decode())
+        self._ctx = ctx
+        self.device = device
+
+    # -- plumbing -------------------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != 0:
+            detail = self._lib.bpp_last_error(self._ctx).decode() if rc == -2 else ""
+            raise _lib.BppError(rc, self._lib.bpp_strerror(rc).decode() + (": " + detail if detail else ""))
+
+    def close(self):
+        if self._ctx:
+            self._lib.bpp_free(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self._lib.bpp_set_stream(self._ctx, ctypes.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        self._check(self._lib.bpp_synchronize(self._ctx))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.bpp_launch_count(self._ctx))
+
+    def device_info(self):
+        sm, ma, mi, mem = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_size_t()
+        self._check(self._lib.bpp_device_info(self._ctx, ctypes.byref(sm), ctypes.byref(ma), ctypes.byref(mi),
+                                              ctypes.byref(mem)))
+        return {"sm_count": sm.value, "cc": (ma.value, mi.value), "total_mem": mem.value}
+
+    def set_window_bits(self, c: int):
+        self._check(self._lib.bpp_set_window_bits(self._ctx, c))
+
+    def set_profiling(self, on: bool):
+        self._check(self._lib.bpp_set_profiling(self._ctx, int(on)))
+
+    def last_phase_ms(self):
+        arr = (ctypes.c_float * len(PHASES))()
+        self._check(self._lib.bpp_last_phase_ms(self._ctx, arr))
+        return dict(zip(PHASES, [float(x) for x in arr]))
+
+    def last_op_counts(self):
+        m, a, d = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+        self._check(self._lib.bpp_last_op_counts(self._ctx, ctypes.byref(m), ctypes.byref(a), ctypes.byref(d)))
+        return {"mixed_adds": m.value, "full_adds": a.value, "doublings": d.value}
+
+    def imad_peak(self, iters: int = 4096):
+        ops, ms = ctypes.c_double(), ctypes.c_double()
+        self._check(self._lib.bpp_bench_imad_peak(self._ctx, iters, ctypes.byref(ops), ctypes.byref(ms)))
+        return ops.value, ms.value
+
+    # -- points ---------------------------------------------------------------------------------
+    def upload_points(self, pts: Union[bytes, Sequence[bytes]], fmt: int = FMT_COMPRESSED) -> Points:
+        if not isinstance(pts, (bytes, bytearray)):
+            pts = b"".join(pts)
+        eb = _FMT_BYTES[fmt]
+        if len(pts) % eb:
+            raise ValueError("point buffer length is not a multiple of the format size")
+        n = len(pts) // eb
+        h = ctypes.c_void_p()
+        self._check(self._lib.bpp_points_upload(self._ctx, fmt, bytes(pts), n, ctypes.byref(h)))
+        return Points(self, h, n)
+
+    def points_from_uniform(self, bytes64: bytes) -> Points:
+        """RistrettoPoint::from_uniform_bytes over n x 64 bytes (RistrettoPoint::random with an RNG stream)."""
+        n = len(bytes64) // 64
+        h = ctypes.c_void_p()
+        self._check(self._lib.bpp_points_from_uniform(self._ctx, bytes(bytes64), n, ctypes.byref(h)))
+        return Points(self, h, n)
+
+    def compress_points(self, points: Points, off: int = 0, n: int = None) -> bytes:
+        if n is None:
+            n = len(points) - off
+        out = ctypes.create_string_buffer(32 * n)
+        self._check(self._lib.bpp_points_compress(self._ctx, points._h, off, n, out))
+        return out.raw
+
+    # -- the operator ------------------------------------------------------------------------------
+    def vartime_multiscalar_mul(self, scalars, points, off: int = 0, n: int = None, want_ext: bool = False):
+        """sum_i scalars[i] * points[i] -> 32-byte compressed Ristretto point."""
+        sb = scalars if isinstance(scalars, (bytes, bytearray)) else scalars_to_bytes(scalars)
+        ns = len(sb) // 32
+        out = ctypes.create_string_buffer(32)
+        if isinstance(points, Points):
+            if n is None:
+                n = len(points) - off
+            ext = ctypes.create_string_buffer(128) if want_ext else None
+            self._check(self._lib.bpp_msm_vartime(self._ctx, bytes(sb), ns, points._h, off, n, out, ext))
+            return (out.raw, ext.raw) if want_ext else out.raw
+        pb = points if isinstance(points, (bytes, bytearray)) else b"".join(points)
+        self._check(self._lib.bpp_msm_vartime_host(self._ctx, bytes(sb), ns, FMT_COMPRESSED, bytes(pb), len(pb) // 32,
+                                                   out))
+        return out.raw
+
+    # device-pointer forms (pointers are ints, e.g. torch.Tensor.data_ptr())
+    def msm_dev(self, d_scalars: int, points: Points, off: int, n: int, d_out: int):
+        self._check(self._lib.bpp_msm_vartime_dev(self._ctx, ctypes.c_void_p(d_scalars), points._h, off, n,
+                                                  ctypes.c_void_p(d_out)))
+
+    def msm_partial_dev(self, d_scalars: int, points: Points, off: int, n: int, d_partial: int):
+        self._check(self._lib.bpp_msm_partial_dev(self._ctx, ctypes.c_void_p(d_scalars), points._h, off, n,
+                                                  ctypes.c_void_p(d_partial)))
+
+    def points_sum_compress_dev(self, d_partials: int, g: int, d_out32: int):
+        self._check(self._lib.bpp_points_sum_compress_dev(self._ctx, ctypes.c_void_p(d_partials), g,
+                                                          ctypes.c_void_p(d_out32)))
+
+    # -- element-wise self-test hook ------------------------------------------------------------------
+    def test_op(self, op: int, a: bytes, b: bytes) -> bytes:
+        n = len(a) // 32
+        out = ctypes.create_string_buffer(32 * n)
+        self._check(self._lib.bpp_test_op(self._ctx, op, a, b, out, n))
+        return out.raw

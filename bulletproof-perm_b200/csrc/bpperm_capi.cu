@@ -1,0 +1,531 @@
+// bpperm_capi.cu - C ABI (include/bpperm.h) over the sm_100a kernels.  No torch, no CPU fallback.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/bpperm.h"
+#include "msm_kernels.cuh"
+
+struct bpp_points {
+    uint32_t *niels = nullptr;  // n x 24 u32 (96 B)
+    size_t n = 0;
+};
+
+struct bpp_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 0, cc_major = 0, cc_minor = 0;
+    size_t total_mem = 0;
+    std::string last_error;
+    uint64_t launches = 0;
+    int forced_c = 0;
+    bool profiling = false;
+    cudaEvent_t ev[BPP_PHASE_COUNT + 1] = {};
+    float phase_ms[BPP_PHASE_COUNT] = {};
+    uint64_t n_madd = 0, n_add = 0, n_dbl = 0;
+    // scratch (grown on demand)
+    uint32_t *d_scalars = nullptr; size_t cap_scalars = 0;       // n x 8
+    uint32_t *d_counts = nullptr, *d_offsets = nullptr, *d_cursor = nullptr;  // W x B each
+    size_t cap_wb = 0, cap_offsets = 0, cap_cursor = 0;
+    uint32_t *d_entries = nullptr; size_t cap_entries = 0;      // W x n
+    uint32_t *d_buckets = nullptr; size_t cap_buckets = 0;      // W x B x 32
+    uint32_t *d_segS = nullptr, *d_segR = nullptr; size_t cap_seg = 0;
+    uint32_t *d_blk = nullptr; size_t cap_blk = 0;              // 3 x W x nb x 32
+    uint8_t *d_out = nullptr;                                   // 160 B
+    uint8_t *h_out = nullptr;                                   // pinned 160 B
+    uint8_t *d_stage = nullptr; size_t cap_stage = 0;           // upload staging
+    uint32_t *d_flag = nullptr;
+    uint8_t *h_pinned = nullptr; size_t cap_pinned = 0;         // pinned staging for host scalars
+};
+
+#define CK(ctx, call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            (ctx)->last_error = std::string(#call) + ": " + cudaGetErrorString(e_);                \
+            return e_ == cudaErrorMemoryAllocation ? BPP_ERR_OOM : BPP_ERR_CUDA;                   \
+        }                                                                                          \
+    } while (0)
+
+#define LAUNCH_CHECK(ctx)                                                                          \
+    do {                                                                                           \
+        (ctx)->launches++;                                                                         \
+        cudaError_t e_ = cudaGetLastError();                                                       \
+        if (e_ != cudaSuccess) {                                                                   \
+            (ctx)->last_error = std::string("kernel launch: ") + cudaGetErrorString(e_);           \
+            return BPP_ERR_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+template <typename T>
+static int grow(bpp_ctx *ctx, T **p, size_t *cap, size_t need_elems) {
+    if (need_elems <= *cap) return BPP_OK;
+    if (*p) CK(ctx, cudaFree(*p));
+    *p = nullptr;
+    *cap = 0;
+    size_t want = need_elems + need_elems / 8;
+    CK(ctx, cudaMalloc((void **)p, want * sizeof(T)));
+    *cap = want;
+    return BPP_OK;
+}
+
+extern "C" const char *bpp_strerror(int s) {
+    switch (s) {
+        case BPP_OK: return "ok";
+        case BPP_ERR_NO_DEVICE: return "no CUDA device (this backend has no CPU fallback)";
+        case BPP_ERR_CUDA: return "CUDA runtime error";
+        case BPP_ERR_INVALID_ARG: return "invalid argument";
+        case BPP_ERR_LENGTH_MISMATCH: return "scalars and points differ in length";
+        case BPP_ERR_INVALID_POINT: return "invalid ristretto255 encoding";
+        case BPP_ERR_SCALAR_RANGE: return "scalar has bit 255 set";
+        case BPP_ERR_OOM: return "out of device memory";
+        case BPP_ERR_VERIFICATION: return "verification failed";
+        default: return "unknown status";
+    }
+}
+
+extern "C" int bpp_init(int device, bpp_ctx **out) {
+    if (!out) return BPP_ERR_INVALID_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device < 0 || device >= count) {
+        cudaGetLastError();
+        return BPP_ERR_NO_DEVICE;
+    }
+    bpp_ctx *ctx = new bpp_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return BPP_ERR_NO_DEVICE; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return BPP_ERR_NO_DEVICE; }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->cc_major = prop.major;
+    ctx->cc_minor = prop.minor;
+    ctx->total_mem = prop.totalGlobalMem;
+    if (prop.major != 10) {  // the library is built for sm_100a only
+        delete ctx;
+        return BPP_ERR_NO_DEVICE;
+    }
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return BPP_ERR_CUDA; }
+    ctx->own_stream = true;
+    for (int i = 0; i <= BPP_PHASE_COUNT; i++) cudaEventCreate(&ctx->ev[i]);
+    if (cudaMalloc((void **)&ctx->d_out, 256) != cudaSuccess || cudaMalloc((void **)&ctx->d_flag, 256) != cudaSuccess ||
+        cudaMallocHost((void **)&ctx->h_out, 256) != cudaSuccess) {
+        delete ctx;
+        return BPP_ERR_OOM;
+    }
+    *out = ctx;
+    return BPP_OK;
+}
+
+extern "C" void bpp_free(bpp_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    void *ptrs[] = {ctx->d_scalars, ctx->d_counts, ctx->d_offsets, ctx->d_cursor, ctx->d_entries, ctx->d_buckets,
+                    ctx->d_segS, ctx->d_segR, ctx->d_blk, ctx->d_out, ctx->d_stage, ctx->d_flag};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (ctx->h_out) cudaFreeHost(ctx->h_out);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    for (int i = 0; i <= BPP_PHASE_COUNT; i++)
+        if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int bpp_set_stream(bpp_ctx *ctx, void *s) {
+    if (!ctx) return BPP_ERR_INVALID_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)s;
+    ctx->own_stream = false;
+    return BPP_OK;
+}
+extern "C" int bpp_synchronize(bpp_ctx *ctx) {
+    if (!ctx) return BPP_ERR_INVALID_ARG;
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return BPP_OK;
+}
+extern "C" const char *bpp_last_error(bpp_ctx *ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+extern "C" uint64_t bpp_launch_count(bpp_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int bpp_device_info(bpp_ctx *ctx, int *sm, int *maj, int *min, size_t *mem) {
+    if (!ctx) return BPP_ERR_INVALID_ARG;
+    if (sm) *sm = ctx->sm_count;
+    if (maj) *maj = ctx->cc_major;
+    if (min) *min = ctx->cc_minor;
+    if (mem) *mem = ctx->total_mem;
+    return BPP_OK;
+}
+extern "C" int bpp_set_window_bits(bpp_ctx *ctx, int c) {
+    if (!ctx || (c != 0 && (c < 4 || c > 16))) return BPP_ERR_INVALID_ARG;
+    ctx->forced_c = c;
+    return BPP_OK;
+}
+extern "C" int bpp_set_profiling(bpp_ctx *ctx, int on) {
+    if (!ctx) return BPP_ERR_INVALID_ARG;
+    ctx->profiling = on != 0;
+    return BPP_OK;
+}
+extern "C" int bpp_last_phase_ms(bpp_ctx *ctx, float ms[BPP_PHASE_COUNT]) {
+    if (!ctx || !ms) return BPP_ERR_INVALID_ARG;
+    for (int i = 0; i < BPP_PHASE_COUNT; i++) ms[i] = ctx->phase_ms[i];
+    return BPP_OK;
+}
+extern "C" int bpp_last_op_counts(bpp_ctx *ctx, uint64_t *m, uint64_t *a, uint64_t *d) {
+    if (!ctx) return BPP_ERR_INVALID_ARG;
+    if (m) *m = ctx->n_madd;
+    if (a) *a = ctx->n_add;
+    if (d) *d = ctx->n_dbl;
+    return BPP_OK;
+}
+
+// ---- points ----------------------------------------------------------------------------------
+static size_t fmt_bytes(int fmt) {
+    switch (fmt) {
+        case BPP_FMT_COMPRESSED: return 32;
+        case BPP_FMT_AFFINE: return 64;
+        case BPP_FMT_DALEK_XYZT: return 160;
+        default: return 0;
+    }
+}
+
+extern "C" int bpp_points_upload(bpp_ctx *ctx, int fmt, const uint8_t *pts, size_t n, bpp_points **out) {
+    if (!ctx || !out || (!pts && n) || n >= (1ull << 31)) return BPP_ERR_INVALID_ARG;
+    size_t eb = fmt_bytes(fmt);
+    if (!eb) return BPP_ERR_INVALID_ARG;
+    *out = nullptr;
+    CK(ctx, cudaSetDevice(ctx->device));
+    bpp_points *p = new bpp_points();
+    p->n = n;
+    if (n == 0) { *out = p; return BPP_OK; }
+    int rc = grow(ctx, &ctx->d_stage, &ctx->cap_stage, n * eb);
+    if (rc) { delete p; return rc; }
+    if (cudaMalloc((void **)&p->niels, n * 96) != cudaSuccess) {
+        cudaGetLastError();
+        delete p;
+        return BPP_ERR_OOM;
+    }
+    cudaError_t e = cudaMemcpyAsync(ctx->d_stage, pts, n * eb, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_flag, 0, 4, ctx->stream);
+    if (e != cudaSuccess) {
+        ctx->last_error = cudaGetErrorString(e);
+        cudaFree(p->niels);
+        delete p;
+        return BPP_ERR_CUDA;
+    }
+    unsigned blocks = (unsigned)((n + 127) / 128);
+    if (fmt == BPP_FMT_COMPRESSED)
+        k_decompress_to_niels<<<blocks, 128, 0, ctx->stream>>>(ctx->d_stage, (uint32_t)n, p->niels, ctx->d_flag);
+    else if (fmt == BPP_FMT_AFFINE)
+        k_affine_to_niels<<<blocks, 128, 0, ctx->stream>>>(ctx->d_stage, (uint32_t)n, p->niels);
+    else
+        k_dalek_xyzt_to_niels<<<blocks, 128, 0, ctx->stream>>>((const unsigned long long *)ctx->d_stage, (uint32_t)n,
+                                                             p->niels);
+    ctx->launches++;
+    uint32_t bad = 0;
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, ctx->d_flag, 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        ctx->last_error = cudaGetErrorString(e);
+        cudaFree(p->niels);
+        delete p;
+        return BPP_ERR_CUDA;
+    }
+    if (bad) {
+        cudaFree(p->niels);
+        delete p;
+        return BPP_ERR_INVALID_POINT;
+    }
+    *out = p;
+    return BPP_OK;
+}
+
+extern "C" int bpp_points_from_uniform(bpp_ctx *ctx, const uint8_t *bytes64, size_t n, bpp_points **out) {
+    if (!ctx || !out || !bytes64 || n == 0 || n >= (1ull << 31)) return BPP_ERR_INVALID_ARG;
+    *out = nullptr;
+    CK(ctx, cudaSetDevice(ctx->device));
+    int rc = grow(ctx, &ctx->d_stage, &ctx->cap_stage, n * 64);
+    if (rc) return rc;
+    bpp_points *p = new bpp_points();
+    p->n = n;
+    if (cudaMalloc((void **)&p->niels, n * 96) != cudaSuccess) {
+        cudaGetLastError();
+        delete p;
+        return BPP_ERR_OOM;
+    }
+    cudaError_t e = cudaMemcpyAsync(ctx->d_stage, bytes64, n * 64, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        k_from_uniform_to_niels<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_stage, (uint32_t)n, p->niels);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        ctx->last_error = cudaGetErrorString(e);
+        cudaFree(p->niels);
+        delete p;
+        return BPP_ERR_CUDA;
+    }
+    *out = p;
+    return BPP_OK;
+}
+
+extern "C" int bpp_points_compress(bpp_ctx *ctx, const bpp_points *points, size_t off, size_t n, uint8_t *out32) {
+    if (!ctx || !points || !out32 || n == 0) return BPP_ERR_INVALID_ARG;
+    if (off + n > points->n) return BPP_ERR_LENGTH_MISMATCH;
+    CK(ctx, cudaSetDevice(ctx->device));
+    int rc = grow(ctx, &ctx->d_stage, &ctx->cap_stage, n * 32);
+    if (rc) return rc;
+    k_niels_compress<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(points->niels + 24 * off, (uint32_t)n, ctx->d_stage);
+    LAUNCH_CHECK(ctx);
+    CK(ctx, cudaMemcpyAsync(out32, ctx->d_stage, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return BPP_OK;
+}
+
+extern "C" void bpp_points_free(bpp_ctx *ctx, bpp_points *p) {
+    if (!p) return;
+    if (ctx) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    if (p->niels) cudaFree(p->niels);
+    delete p;
+}
+extern "C" size_t bpp_points_len(const bpp_points *p) { return p ? p->n : 0; }
+
+// ---- MSM ---------------------------------------------------------------------------------------
+static int pick_window(size_t n) {
+    // minimise W * (n + 2 * 2^(c-1)) mixed-add equivalents; keep W <= 64
+    int best = 8;
+    double best_cost = 1e300;
+    for (int c = 4; c <= 16; c++) {
+        int W = (256 + c - 1) / c;
+        double cost = (double)W * ((double)n + 2.6 * (double)(1u << (c - 1)));
+        if (cost < best_cost) { best_cost = cost; best = c; }
+    }
+    return best;
+}
+
+static int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points *pts, size_t off, size_t n,
+                       uint8_t *d_out, int do_compress) {
+    const int c = ctx->forced_c ? ctx->forced_c : pick_window(n);
+    const int W = (256 + c - 1) / c;
+    const uint32_t B = 1u << (c - 1);
+    const size_t WB = (size_t)W * B;
+    uint32_t L = B / 1024;
+    if (L < 1) L = 1;
+    if (L > 32) L = 32;
+    uint32_t log2L = 0;
+    while ((1u << log2L) < L) log2L++;
+    const uint32_t T = B / L;
+    const uint32_t nb = (T + 255) / 256;
+    int rc;
+    if ((rc = grow(ctx, &ctx->d_counts, &ctx->cap_wb, WB))) return rc;
+    if ((rc = grow(ctx, &ctx->d_offsets, &ctx->cap_offsets, WB))) return rc;
+    if ((rc = grow(ctx, &ctx->d_cursor, &ctx->cap_cursor, WB))) return rc;
+    if ((rc = grow(ctx, &ctx->d_entries, &ctx->cap_entries, (size_t)W * n))) return rc;
+    if ((rc = grow(ctx, &ctx->d_buckets, &ctx->cap_buckets, WB * 32))) return rc;
+    {
+        size_t need = (size_t)W * T * 32;
+        if (need > ctx->cap_seg) {
+            if (ctx->d_segS) cudaFree(ctx->d_segS);
+            if (ctx->d_segR) cudaFree(ctx->d_segR);
+            ctx->d_segS = ctx->d_segR = nullptr;
+            ctx->cap_seg = 0;
+            CK(ctx, cudaMalloc((void **)&ctx->d_segS, need * 4));
+            CK(ctx, cudaMalloc((void **)&ctx->d_segR, need * 4));
+            ctx->cap_seg = need;
+        }
+    }
+    if ((rc = grow(ctx, &ctx->d_blk, &ctx->cap_blk, (size_t)3 * W * nb * 32))) return rc;
+    uint32_t *blkS = ctx->d_blk, *blkB = ctx->d_blk + (size_t)W * nb * 32, *blkR = ctx->d_blk + (size_t)2 * W * nb * 32;
+
+    cudaStream_t s = ctx->stream;
+    const bool prof = ctx->profiling;
+    const uint32_t *niels = pts->niels + 24 * off;
+    if (prof) cudaEventRecord(ctx->ev[0], s);
+    CK(ctx, cudaMemsetAsync(ctx->d_counts, 0, WB * 4, s));
+    unsigned sb = (unsigned)((n + 255) / 256);
+    k_digit_hist<<<sb, 256, 0, s>>>(d_scalars, (uint32_t)n, c, W, ctx->d_counts);
+    LAUNCH_CHECK(ctx);
+    if (prof) cudaEventRecord(ctx->ev[1], s);
+    k_window_scan<<<W, 1024, 0, s>>>(ctx->d_counts, B, ctx->d_offsets, ctx->d_cursor);
+    LAUNCH_CHECK(ctx);
+    if (prof) cudaEventRecord(ctx->ev[2], s);
+    k_digit_scatter<<<sb, 256, 0, s>>>(d_scalars, (uint32_t)n, c, W, ctx->d_cursor, ctx->d_entries);
+    LAUNCH_CHECK(ctx);
+    if (prof) cudaEventRecord(ctx->ev[3], s);
+    k_bucket_accum<<<(unsigned)((WB + BPP_ACC_THREADS - 1) / BPP_ACC_THREADS), BPP_ACC_THREADS, 0, s>>>(
+        niels, ctx->d_entries, ctx->d_offsets, ctx->d_cursor, (uint32_t)n, B, (uint32_t)WB, ctx->d_buckets);
+    LAUNCH_CHECK(ctx);
+    if (prof) cudaEventRecord(ctx->ev[4], s);
+    const uint32_t chunks = (uint32_t)W * T;
+    k_bucket_reduce1<<<(chunks + 127) / 128, 128, 0, s>>>(ctx->d_buckets, L, chunks, ctx->d_segS, ctx->d_segR);
+    LAUNCH_CHECK(ctx);
+    k_bucket_reduce2<<<dim3(nb, W), 256, 0, s>>>(ctx->d_segS, ctx->d_segR, T, blkS, blkB, blkR);
+    LAUNCH_CHECK(ctx);
+    if (prof) cudaEventRecord(ctx->ev[5], s);
+    k_msm_finish<<<1, 64, 0, s>>>(blkS, blkB, blkR, nb, log2L, c, W, do_compress, d_out);
+    LAUNCH_CHECK(ctx);
+    if (prof) cudaEventRecord(ctx->ev[6], s);
+    ctx->n_madd = (uint64_t)W * n;
+    ctx->n_add = (uint64_t)W * T * (2 * (uint64_t)L - 2) + (uint64_t)W * nb * (30 + 2 * 8 + 3) + (uint64_t)W * (3 * nb + 2) + (W - 1);
+    ctx->n_dbl = (uint64_t)c * (W - 1) + (uint64_t)W * (log2L + (nb > 1 ? 8 : 0)) + (uint64_t)W * nb * 5;
+    return BPP_OK;
+}
+
+static int finish_profile(bpp_ctx *ctx) {
+    if (!ctx->profiling) return BPP_OK;
+    CK(ctx, cudaEventSynchronize(ctx->ev[BPP_PHASE_COUNT]));
+    for (int i = 0; i < BPP_PHASE_COUNT; i++) cudaEventElapsedTime(&ctx->phase_ms[i], ctx->ev[i], ctx->ev[i + 1]);
+    return BPP_OK;
+}
+
+static int check_scalars_host(const uint8_t *scalars, size_t n) {
+    for (size_t i = 0; i < n; i++)
+        if (scalars[32 * i + 31] & 0x80) return BPP_ERR_SCALAR_RANGE;
+    return BPP_OK;
+}
+
+static int empty_msm_result(uint8_t out32[32], uint8_t *out_ext) {
+    memset(out32, 0, 32);  // identity compresses to 32 zero bytes
+    if (out_ext) {
+        memset(out_ext, 0, 128);
+        out_ext[32] = 1;  // Y = 1
+        out_ext[64] = 1;  // Z = 1
+    }
+    return BPP_OK;
+}
+
+extern "C" int bpp_msm_vartime_dev(bpp_ctx *ctx, const void *d_scalars, const bpp_points *points, size_t off, size_t n,
+                                   void *d_out) {
+    if (!ctx || !d_scalars || !points || !d_out || n == 0) return BPP_ERR_INVALID_ARG;
+    if (off + n > points->n) return BPP_ERR_LENGTH_MISMATCH;
+    CK(ctx, cudaSetDevice(ctx->device));
+    int rc = msm_enqueue(ctx, (const uint32_t *)d_scalars, points, off, n, (uint8_t *)d_out, 1);
+    return rc;
+}
+
+extern "C" int bpp_msm_partial_dev(bpp_ctx *ctx, const void *d_scalars, const bpp_points *points, size_t off, size_t n,
+                                   void *d_partial) {
+    if (!ctx || !d_scalars || !points || !d_partial || n == 0) return BPP_ERR_INVALID_ARG;
+    if (off + n > points->n) return BPP_ERR_LENGTH_MISMATCH;
+    CK(ctx, cudaSetDevice(ctx->device));
+    return msm_enqueue(ctx, (const uint32_t *)d_scalars, points, off, n, (uint8_t *)d_partial, 0);
+}
+
+extern "C" int bpp_points_sum_compress_dev(bpp_ctx *ctx, const void *d_partials, size_t g, void *d_out32) {
+    if (!ctx || !d_partials || !d_out32 || g == 0) return BPP_ERR_INVALID_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    k_points_sum_compress<<<1, 32, 0, ctx->stream>>>((const uint32_t *)d_partials, (uint32_t)g, (uint8_t *)d_out32);
+    LAUNCH_CHECK(ctx);
+    return BPP_OK;
+}
+
+extern "C" int bpp_msm_vartime(bpp_ctx *ctx, const uint8_t *scalars, size_t n_scalars, const bpp_points *points,
+                               size_t off, size_t n, uint8_t out32[32], uint8_t *out_ext) {
+    if (!ctx || !points || !out32 || (!scalars && n)) return BPP_ERR_INVALID_ARG;
+    if (n_scalars != n || off + n > points->n) return BPP_ERR_LENGTH_MISMATCH;
+    if (n == 0) return empty_msm_result(out32, out_ext);
+    int rc = check_scalars_host(scalars, n);
+    if (rc) return rc;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if ((rc = grow(ctx, &ctx->d_scalars, &ctx->cap_scalars, n * 8))) return rc;
+    CK(ctx, cudaMemcpyAsync(ctx->d_scalars, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = msm_enqueue(ctx, ctx->d_scalars, points, off, n, ctx->d_out, 1))) return rc;
+    CK(ctx, cudaMemcpyAsync(ctx->h_out, ctx->d_out, 160, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if ((rc = finish_profile(ctx))) return rc;
+    memcpy(out32, ctx->h_out, 32);
+    if (out_ext) {
+        // canonicalise the four raw field elements on the host: value mod p, little endian
+        for (int k = 0; k < 4; k++) {
+            // 256-bit value v (may be >= p): subtract p up to twice (v < 2^256 < 3p)
+            uint32_t v[8];
+            memcpy(v, ctx->h_out + 32 + 32 * k, 32);
+            static const uint32_t P[8] = {0xffffffedu, 0xffffffffu, 0xffffffffu, 0xffffffffu,
+                                          0xffffffffu, 0xffffffffu, 0xffffffffu, 0x7fffffffu};
+            for (int round = 0; round < 2; round++) {
+                uint32_t t[8];
+                int64_t borrow = 0;
+                for (int i = 0; i < 8; i++) {
+                    int64_t d = (int64_t)v[i] - (int64_t)P[i] + borrow;
+                    t[i] = (uint32_t)d;
+                    borrow = d >> 32;
+                }
+                if (borrow == 0) memcpy(v, t, 32);
+            }
+            memcpy(out_ext + 32 * k, v, 32);
+        }
+    }
+    return BPP_OK;
+}
+
+extern "C" int bpp_msm_vartime_host(bpp_ctx *ctx, const uint8_t *scalars, size_t n_scalars, int fmt, const uint8_t *pts,
+                                    size_t n_points, uint8_t out32[32]) {
+    if (!ctx || !out32) return BPP_ERR_INVALID_ARG;
+    if (n_scalars != n_points) return BPP_ERR_LENGTH_MISMATCH;
+    if (n_points == 0) return empty_msm_result(out32, nullptr);
+    bpp_points *p = nullptr;
+    int rc = bpp_points_upload(ctx, fmt, pts, n_points, &p);
+    if (rc) return rc;
+    rc = bpp_msm_vartime(ctx, scalars, n_scalars, p, 0, n_points, out32, nullptr);
+    bpp_points_free(ctx, p);
+    return rc;
+}
+
+// ---- measurement / tests -------------------------------------------------------------------------
+extern "C" int bpp_bench_imad_peak(bpp_ctx *ctx, int iters, double *ops_per_sec, double *ms_out) {
+    if (!ctx || iters <= 0) return BPP_ERR_INVALID_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    unsigned long long *d = (unsigned long long *)ctx->d_flag;
+    int blocks = ctx->sm_count * 8;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    k_imad_peak<<<blocks, 256, 0, ctx->stream>>>(1u, iters / 8 + 1, d);  // warm-up
+    LAUNCH_CHECK(ctx);
+    cudaEventRecord(a, ctx->stream);
+    k_imad_peak<<<blocks, 256, 0, ctx->stream>>>(7u, iters, d);
+    LAUNCH_CHECK(ctx);
+    cudaEventRecord(b, ctx->stream);
+    CK(ctx, cudaEventSynchronize(b));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    double ops = (double)blocks * 256.0 * (double)iters * 16.0 * 8.0;
+    if (ops_per_sec) *ops_per_sec = ops / (ms * 1e-3);
+    if (ms_out) *ms_out = ms;
+    return BPP_OK;
+}
+
+extern "C" int bpp_test_op(bpp_ctx *ctx, int op, const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n) {
+    if (!ctx || !a || !b || !out || n == 0 || n >= (1ull << 31)) return BPP_ERR_INVALID_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    uint8_t *d = nullptr;
+    CK(ctx, cudaMalloc((void **)&d, n * 96));
+    cudaError_t e = cudaMemcpyAsync(d, a, n * 32, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + n * 32, b, n * 32, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        k_test_op<<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(op, d, d + n * 32, d + n * 64, (uint32_t)n);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d + n * 64, n * 32, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) {
+        ctx->last_error = cudaGetErrorString(e);
+        return BPP_ERR_CUDA;
+    }
+    return BPP_OK;
+}

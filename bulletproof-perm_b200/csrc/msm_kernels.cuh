@@ -1,0 +1,533 @@
+// msm_kernels.cuh - GPU Pippenger for Ristretto255 on sm_100a.
+//
+// Replaces dalek-ng 4.1.1 `backend::serial::scalar_mul::{straus,pippenger}` behind
+// `RistrettoPoint::vartime_multiscalar_mul` (reference call sites: circuit_lib.rs:187,202,216,
+// 363-407,498-568).  The group result is algorithm independent and the Ristretto encoding is
+// canonical, so the bytes equal dalek's for every input.
+//
+// Pipeline (N points, window c bits, W = ceil(256/c) windows, B = 2^(c-1) buckets per window):
+//   k_digit_hist      signed-window recode, per-(window,bucket) histogram (atomics)
+//   k_window_scan     exclusive scan of each window's histogram -> bucket offsets
+//   k_digit_scatter   counting-sort scatter of (point index | sign) into bucket order
+//   k_bucket_accum    one thread per bucket: mixed adds (extended += affine Niels, 7M)
+//   k_bucket_reduce1  running sums over chunks of L buckets -> (S, R) per chunk
+//   k_bucket_reduce2  warp-shuffle suffix scans over 256 chunks -> (S, B, R) per block
+//   k_msm_finish      per-window totals, Horner over windows (c doublings each), compress
+#pragma once
+#include "ge25519.cuh"
+
+#define BPP_ACC_THREADS 128
+
+// ---- signed-window recoding ---------------------------------------------------------------
+// Digits d_w in [-(2^(c-1)-1), 2^(c-1)] with sum d_w 2^(cw) = s, for s < 2^255.
+// (dalek Scalar::to_radix_2w uses the same carry scheme for w <= 8.)
+FE_INLINE uint32_t sc_window(const uint32_t s[8], int bit, int c) {
+    int limb = bit >> 5, sh = bit & 31;
+    if (limb >= 8) return 0;
+    uint64_t v = s[limb];
+    if (limb + 1 < 8) v |= (uint64_t)s[limb + 1] << 32;
+    return (uint32_t)(v >> sh) & ((1u << c) - 1u);
+}
+
+__global__ void k_digit_hist(const uint32_t *__restrict__ scalars, uint32_t n, int c, int W,
+                             uint32_t *__restrict__ counts) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s[8];
+    const uint4 *p = reinterpret_cast<const uint4 *>(scalars + 8 * (size_t)i);
+    uint4 lo = __ldg(p), hi = __ldg(p + 1);
+    s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w; s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
+    const uint32_t half = 1u << (c - 1);
+    uint32_t carry = 0;
+    for (int w = 0; w < W; w++) {
+        uint32_t raw = sc_window(s, w * c, c) + carry;
+        carry = raw > half ? 1u : 0u;
+        uint32_t mag = carry ? (1u << c) - raw : raw;
+        if (mag) atomicAdd(&counts[(size_t)w * half + (mag - 1)], 1u);
+    }
+}
+
+// one block (1024 threads) per window: exclusive scan of B counts
+__global__ void __launch_bounds__(1024) k_window_scan(const uint32_t *__restrict__ counts, uint32_t B,
+                                                      uint32_t *__restrict__ offsets,
+                                                      uint32_t *__restrict__ cursor) {
+    __shared__ uint32_t warp_sums[32];
+    const uint32_t w = blockIdx.x;
+    const uint32_t per = (B + 1023) / 1024;
+    const uint32_t base = threadIdx.x * per;
+    const uint32_t *cw = counts + (size_t)w * B;
+    uint32_t local = 0;
+    for (uint32_t k = 0; k < per; k++)
+        if (base + k < B) local += cw[base + k];
+    // block exclusive scan of `local`
+    uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t incl = local;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (uint32_t)d) incl += o;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t v = warp_sums[lane];
+        uint32_t iv = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t o = __shfl_up_sync(0xffffffffu, iv, d);
+            if (lane >= (uint32_t)d) iv += o;
+        }
+        warp_sums[lane] = iv - v;
+    }
+    __syncthreads();
+    uint32_t run = warp_sums[wid] + incl - local;
+    for (uint32_t k = 0; k < per; k++)
+        if (base + k < B) {
+            offsets[(size_t)w * B + base + k] = run;
+            cursor[(size_t)w * B + base + k] = run;
+            run += cw[base + k];
+        }
+}
+
+__global__ void k_digit_scatter(const uint32_t *__restrict__ scalars, uint32_t n, int c, int W,
+                                uint32_t *__restrict__ cursor, uint32_t *__restrict__ entries) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s[8];
+    const uint4 *p = reinterpret_cast<const uint4 *>(scalars + 8 * (size_t)i);
+    uint4 lo = __ldg(p), hi = __ldg(p + 1);
+    s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w; s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
+    const uint32_t half = 1u << (c - 1);
+    uint32_t carry = 0;
+    for (int w = 0; w < W; w++) {
+        uint32_t raw = sc_window(s, w * c, c) + carry;
+        carry = raw > half ? 1u : 0u;
+        uint32_t mag = carry ? (1u << c) - raw : raw;
+        if (mag) {
+            uint32_t pos = atomicAdd(&cursor[(size_t)w * half + (mag - 1)], 1u);
+            entries[(size_t)w * n + pos] = i | (carry << 31);
+        }
+    }
+}
+
+// ---- bucket accumulation: the dominant kernel ------------------------------------------------
+// One thread per (window, bucket).  entries are grouped by bucket; `niels` is the static point
+// table (96 B per point, read through the read-only path; 2^20 points = 96 MiB, L2 resident).
+__global__ void __launch_bounds__(BPP_ACC_THREADS) k_bucket_accum(
+    const uint32_t *__restrict__ niels, const uint32_t *__restrict__ entries,
+    const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ ends, uint32_t n, uint32_t B,
+    uint32_t total_buckets, uint32_t *__restrict__ buckets) {
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total_buckets) return;
+    uint32_t w = g / B;
+    uint32_t beg = offsets[g], end = ends[g];
+    const uint32_t *ew = entries + (size_t)w * n;
+    ge_ext acc;
+    ge_identity(acc);
+#pragma unroll 1
+    for (uint32_t e = beg; e < end; e++) {
+        uint32_t idx = ew[e];
+        ge_niels q;
+        ge_niels_load(q, niels + 24 * (size_t)(idx & 0x7fffffffu));
+        ge_madd(acc, acc, q, (idx >> 31) != 0);
+    }
+    ge_store(buckets + 32 * (size_t)g, acc);
+}
+
+// ---- bucket reduction ---------------------------------------------------------------------------
+// Window total = sum_j (j+1) * bucket_j.  Chunk t covers buckets [tL, tL+L):
+//   S_t = sum bucket, R_t = sum (k+1) * bucket_{tL+k}   (running-sum trick, 2L-2 adds)
+// so that total = sum_t R_t + L * sum_t t * S_t.
+__global__ void __launch_bounds__(128) k_bucket_reduce1(const uint32_t *__restrict__ buckets, uint32_t L,
+                                                        uint32_t total_chunks, uint32_t *__restrict__ segS,
+                                                        uint32_t *__restrict__ segR) {
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total_chunks) return;
+    const uint32_t *b = buckets + 32 * (size_t)g * L;
+    ge_ext run, acc, t;
+    ge_load(run, b + 32 * (size_t)(L - 1));
+    acc = run;
+#pragma unroll 1
+    for (int k = (int)L - 2; k >= 0; k--) {
+        ge_load(t, b + 32 * (size_t)k);
+        ge_add(run, run, t);
+        ge_add(acc, acc, run);
+    }
+    ge_store(segS + 32 * (size_t)g, run);
+    ge_store(segR + 32 * (size_t)g, acc);
+}
+
+FE_INLINE void ge_shfl_down(ge_ext &r, const ge_ext &a, int d) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        r.X.v[i] = __shfl_down_sync(0xffffffffu, a.X.v[i], d);
+        r.Y.v[i] = __shfl_down_sync(0xffffffffu, a.Y.v[i], d);
+        r.Z.v[i] = __shfl_down_sync(0xffffffffu, a.Z.v[i], d);
+        r.T.v[i] = __shfl_down_sync(0xffffffffu, a.T.v[i], d);
+    }
+}
+FE_INLINE void ge_select(ge_ext &r, const ge_ext &a, bool take) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        if (take) {
+            r.X.v[i] = a.X.v[i]; r.Y.v[i] = a.Y.v[i]; r.Z.v[i] = a.Z.v[i]; r.T.v[i] = a.T.v[i];
+        }
+    }
+}
+
+// Warp-level: given per-lane point S, returns in every lane  A0 = sum_lanes S  (valid in lane 0)
+// and Wt = sum_lanes lane * S (valid in lane 0).  Suffix scan + plain reduction: 10 adds deep.
+__device__ __noinline__ void warp_weighted_sum(ge_ext &sum, ge_ext &wsum, const ge_ext &S) {
+    const uint32_t lane = threadIdx.x & 31;
+    ge_ext a = S, o, t;
+#pragma unroll 1
+    for (int d = 1; d < 32; d <<= 1) {  // inclusive suffix scan: a_lane = sum_{j >= lane} S_j
+        ge_shfl_down(o, a, d);
+        ge_add(t, a, o);
+        ge_select(a, t, lane + d < 32);
+    }
+    sum = a;  // lane 0 holds the warp total
+    // sum_lanes lane*S_lane = sum_{j=1..31} suffix_j
+    ge_ext b = a;
+    if (lane == 0) ge_identity(b);
+#pragma unroll 1
+    for (int d = 16; d >= 1; d >>= 1) {
+        ge_shfl_down(o, b, d);
+        ge_add(t, b, o);
+        ge_select(b, t, lane < (uint32_t)d);
+    }
+    wsum = b;
+}
+__device__ __noinline__ void warp_plain_sum(ge_ext &sum, const ge_ext &S) {
+    const uint32_t lane = threadIdx.x & 31;
+    ge_ext b = S, o, t;
+#pragma unroll 1
+    for (int d = 16; d >= 1; d >>= 1) {
+        ge_shfl_down(o, b, d);
+        ge_add(t, b, o);
+        ge_select(b, t, lane < (uint32_t)d);
+    }
+    sum = b;
+}
+
+// grid (nb, W), 256 threads.  Block handles chunks t in [256*blk, 256*blk+256) of window w
+// (identity beyond T).  Output per block: S = sum S_t, Bw = sum (t - 256 blk) S_t, R = sum R_t.
+__global__ void __launch_bounds__(256) k_bucket_reduce2(const uint32_t *__restrict__ segS,
+                                                        const uint32_t *__restrict__ segR, uint32_t T,
+                                                        uint32_t *__restrict__ blkS, uint32_t *__restrict__ blkB,
+                                                        uint32_t *__restrict__ blkR) {
+    __shared__ __align__(16) uint32_t sh[3][8][32];
+    const uint32_t w = blockIdx.y, blk = blockIdx.x, nb = gridDim.x;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t t = blk * 256 + threadIdx.x;
+    ge_ext S, R;
+    if (t < T) {
+        ge_load(S, segS + 32 * ((size_t)w * T + t));
+        ge_load(R, segR + 32 * ((size_t)w * T + t));
+    } else {
+        ge_identity(S);
+        ge_identity(R);
+    }
+    ge_ext ws, wb, wr;
+    warp_weighted_sum(ws, wb, S);
+    warp_plain_sum(wr, R);
+    if (lane == 0) {
+        ge_store(&sh[0][wid][0], ws);
+        ge_store(&sh[1][wid][0], wb);
+        ge_store(&sh[2][wid][0], wr);
+    }
+    __syncthreads();
+    if (wid == 0) {
+        if (lane < 8) {
+            ge_load(S, &sh[0][lane][0]);
+            ge_load(wb, &sh[1][lane][0]);
+            ge_load(R, &sh[2][lane][0]);
+        } else {
+            ge_identity(S);
+            ge_identity(wb);
+            ge_identity(R);
+        }
+        ge_ext bs, bx, by, br;
+        warp_weighted_sum(bs, bx, S);   // bs = sum_v Sw_v, bx = sum_v v*Sw_v
+        warp_plain_sum(by, wb);         // sum_v Bw_v
+        warp_plain_sum(br, R);
+        if (lane == 0) {
+#pragma unroll 1
+            for (int i = 0; i < 5; i++) ge_double(bx, bx);  // 32 * bx
+            ge_add(by, by, bx);
+            size_t o = 32 * ((size_t)w * nb + blk);
+            ge_store(blkS + o, bs);
+            ge_store(blkB + o, by);
+            ge_store(blkR + o, br);
+        }
+    }
+}
+
+// Single block of 64 threads: thread w < W folds window w's block triples into the window total
+//   total_w = sum_b R_b + L * sum_b (B_b + 256 b S_b)
+// then thread 0 combines windows (Horner, c doublings per window).  With `do_compress` the
+// 32-byte encoding goes to out[0..32) and the raw extended point to out[32..160); otherwise the
+// raw extended point goes to out[0..128).
+__global__ void __launch_bounds__(64) k_msm_finish(const uint32_t *__restrict__ blkS,
+                                                   const uint32_t *__restrict__ blkB,
+                                                   const uint32_t *__restrict__ blkR, uint32_t nb, uint32_t log2L,
+                                                   int c, int W, int do_compress, uint8_t *__restrict__ out) {
+    __shared__ __align__(16) uint32_t sh[64][32];
+    const uint32_t w = threadIdx.x;
+    if ((int)w < W) {
+        ge_ext x, y, r, t;
+        ge_identity(x);  // x = sum_b b * S_b via running sum from the top
+        ge_identity(y);
+        ge_identity(r);
+        ge_ext run;
+        ge_identity(run);
+#pragma unroll 1
+        for (int b = (int)nb - 1; b >= 0; b--) {
+            size_t o = 32 * ((size_t)w * nb + b);
+            ge_load(t, blkB + o);
+            ge_add(y, y, t);
+            ge_load(t, blkR + o);
+            ge_add(r, r, t);
+            if (b >= 1) {
+                ge_load(t, blkS + o);
+                ge_add(run, run, t);
+                ge_add(x, x, run);
+            }
+        }
+        if (nb > 1) {
+#pragma unroll 1
+            for (int i = 0; i < 8; i++) ge_double(x, x);  // 256 * x
+            ge_add(y, y, x);
+        }
+#pragma unroll 1
+        for (uint32_t i = 0; i < log2L; i++) ge_double(y, y);
+        ge_add(r, r, y);
+        ge_store(&sh[w][0], r);
+    }
+    __syncthreads();
+    if (w == 0) {
+        ge_ext acc, t;
+        ge_load(acc, &sh[W - 1][0]);
+#pragma unroll 1
+        for (int k = W - 2; k >= 0; k--) {
+#pragma unroll 1
+            for (int i = 0; i < c; i++) ge_double(acc, acc);
+            ge_load(t, &sh[k][0]);
+            ge_add(acc, acc, t);
+        }
+        if (do_compress) {
+            ge_compress(out, acc);
+            ge_store(reinterpret_cast<uint32_t *>(out + 32), acc);
+        } else {
+            ge_store(reinterpret_cast<uint32_t *>(out), acc);
+        }
+    }
+}
+
+// sum of g extended points (raw limbs, 128 B each) -> compress
+__global__ void __launch_bounds__(32) k_points_sum_compress(const uint32_t *__restrict__ parts, uint32_t g,
+                                                            uint8_t *__restrict__ out32) {
+    if (threadIdx.x != 0) return;
+    ge_ext acc, t;
+    ge_load(acc, parts);
+#pragma unroll 1
+    for (uint32_t i = 1; i < g; i++) {
+        ge_load(t, parts + 32 * (size_t)i);
+        ge_add(acc, acc, t);
+    }
+    ge_compress(out32, acc);
+}
+
+// ---- point ingestion ----------------------------------------------------------------------------
+__global__ void k_decompress_to_niels(const uint8_t *__restrict__ in, uint32_t n, uint32_t *__restrict__ niels,
+                                      uint32_t *__restrict__ n_invalid) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe x, y;
+    bool ok = ge_decompress(x, y, in + 32 * (size_t)i);
+    if (!ok) {
+        atomicAdd(n_invalid, 1u);
+        fe_set0(x);
+        fe_set1(y);
+    }
+    ge_niels q;
+    ge_affine_to_niels(q, x, y);
+    ge_niels_store(niels + 24 * (size_t)i, q);
+}
+
+__global__ void k_affine_to_niels(const uint8_t *__restrict__ in, uint32_t n, uint32_t *__restrict__ niels) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe x, y;
+    fe_frombytes(x, in + 64 * (size_t)i);
+    fe_frombytes(y, in + 64 * (size_t)i + 32);
+    ge_niels q;
+    ge_affine_to_niels(q, x, y);
+    ge_niels_store(niels + 24 * (size_t)i, q);
+}
+
+// dalek FieldElement51: 5 x u64 limbs radix 2^51 (limbs may exceed 51 bits by a few bits)
+FE_INLINE void fe_from_radix51(fe &r, const unsigned long long *l) {
+    // value = sum l_i 2^(51 i); accumulate into 9 x 32-bit limbs, then fold
+    unsigned long long acc[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) acc[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        int bit = 51 * i, limb = bit >> 5, sh = bit & 31;
+        unsigned long long lo = l[i] << sh;                      // low 64 bits of l_i << sh
+        unsigned long long hi = sh ? (l[i] >> (64 - sh)) : 0ull;  // overflow bits
+        acc[limb] += lo & 0xffffffffull;
+        acc[limb + 1] += lo >> 32;
+        if (limb + 2 < 9) acc[limb + 2] += hi;
+    }
+    uint32_t t[16];
+    unsigned long long carry = 0;
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        carry += acc[i];
+        t[i] = (uint32_t)carry;
+        carry >>= 32;
+    }
+    t[9] = (uint32_t)carry;
+#pragma unroll
+    for (int i = 10; i < 16; i++) t[i] = 0;
+    fe_reduce16(r, t);
+}
+
+__global__ void k_dalek_xyzt_to_niels(const unsigned long long *__restrict__ in, uint32_t n,
+                                      uint32_t *__restrict__ niels) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long *p = in + 20 * (size_t)i;
+    unsigned long long l[5];
+    fe X, Y, Z, zi, x, y;
+#pragma unroll
+    for (int k = 0; k < 5; k++) l[k] = p[k];
+    fe_from_radix51(X, l);
+#pragma unroll
+    for (int k = 0; k < 5; k++) l[k] = p[5 + k];
+    fe_from_radix51(Y, l);
+#pragma unroll
+    for (int k = 0; k < 5; k++) l[k] = p[10 + k];
+    fe_from_radix51(Z, l);
+    fe_invert(zi, Z);
+    fe_mul_noinline(x, X, zi);
+    fe_mul_noinline(y, Y, zi);
+    ge_niels q;
+    ge_affine_to_niels(q, x, y);
+    ge_niels_store(niels + 24 * (size_t)i, q);
+}
+
+// RistrettoPoint::from_uniform_bytes / ::random (lib.rs:165-166,179-180): 64 uniform bytes -> point
+__global__ void k_from_uniform_to_niels(const uint8_t *__restrict__ in, uint32_t n, uint32_t *__restrict__ niels) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ge_ext p;
+    ge_from_uniform(p, in + 64 * (size_t)i);
+    fe zi, x, y;
+    fe_invert(zi, p.Z);
+    fe_mul_noinline(x, p.X, zi);
+    fe_mul_noinline(y, p.Y, zi);
+    ge_niels q;
+    ge_affine_to_niels(q, x, y);
+    ge_niels_store(niels + 24 * (size_t)i, q);
+}
+
+// Niels table -> compressed encodings (x = (yp - ym)/2, y = (yp + ym)/2; the common factor 2 is
+// projective: (X, Y, Z, T) = (2x*2, 2y*2, 4, 2x*2y) = (2(yp-ym), 2(yp+ym), 4, (yp-ym)(yp+ym)))
+__global__ void k_niels_compress(const uint32_t *__restrict__ niels, uint32_t n, uint8_t *__restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ge_niels q;
+    ge_niels_load(q, niels + 24 * (size_t)i);
+    fe x2, y2;
+    fe_sub(x2, q.yp, q.ym);
+    fe_add(y2, q.yp, q.ym);
+    ge_ext p;
+    fe_dbl(p.X, x2);
+    fe_dbl(p.Y, y2);
+    fe_set0(p.Z);
+    p.Z.v[0] = 4;
+    fe_mul_noinline(p.T, x2, y2);
+    ge_compress(out + 32 * (size_t)i, p);
+}
+
+// ---- IMAD.WIDE.U32 peak microbenchmark ---------------------------------------------------------
+// 8 independent 64-bit accumulate chains per thread: acc_k = a_k * b + acc_k.
+__global__ void __launch_bounds__(256) k_imad_peak(uint32_t seed, int iters, unsigned long long *out) {
+    uint32_t a0 = seed + threadIdx.x, a1 = a0 * 3u + 1u, a2 = a0 * 5u + 2u, a3 = a0 * 7u + 3u;
+    uint32_t a4 = a0 * 11u + 4u, a5 = a0 * 13u + 5u, a6 = a0 * 17u + 6u, a7 = a0 * 19u + 7u;
+    uint32_t b = blockIdx.x * 2654435761u + 12345u;
+    unsigned long long c0 = 1, c1 = 2, c2 = 3, c3 = 4, c4 = 5, c5 = 6, c6 = 7, c7 = 8;
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c0) : "r"(a0), "r"(b));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c1) : "r"(a1), "r"(b));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c2) : "r"(a2), "r"(b));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c3) : "r"(a3), "r"(b));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c4) : "r"(a4), "r"(b));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c5) : "r"(a5), "r"(b));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c6) : "r"(a6), "r"(b));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c7) : "r"(a7), "r"(b));
+        }
+    }
+    unsigned long long r = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
+    if (r == 0x1234567812345678ull) out[0] = r;  // never true in practice; keeps the chains alive
+}
+
+// ---- element-wise test kernels -------------------------------------------------------------------
+__global__ void k_test_op(int op, const uint8_t *__restrict__ a, const uint8_t *__restrict__ b,
+                          uint8_t *__restrict__ out, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t *pa = a + 32 * (size_t)i, *pb = b + 32 * (size_t)i;
+    uint8_t *po = out + 32 * (size_t)i;
+    if (op <= 4) {
+        fe x, y, r;
+        fe_frombytes(x, pa);
+        fe_frombytes(y, pb);
+        switch (op) {
+            case 0: fe_mul(r, x, y); break;
+            case 1: fe_add(r, x, y); break;
+            case 2: fe_sub(r, x, y); break;
+            case 3: fe_invert(r, x); break;
+            default: fe_copy(r, x); break;
+        }
+        fe_tobytes(po, r);
+        return;
+    }
+    ge_ext P, Q, Rr;
+    fe x, y;
+    bool ok = ge_decompress(x, y, pa);
+    P.X = x; P.Y = y; fe_set1(P.Z); fe_mul(P.T, x, y);
+    if (!ok) {
+        for (int k = 0; k < 32; k++) po[k] = 0xff;
+        return;
+    }
+    if (op == 5) {
+        ok = ge_decompress(x, y, pb);
+        Q.X = x; Q.Y = y; fe_set1(Q.Z); fe_mul(Q.T, x, y);
+        if (!ok) {
+            for (int k = 0; k < 32; k++) po[k] = 0xff;
+            return;
+        }
+        ge_add(Rr, P, Q);
+    } else if (op == 6) {
+        ge_double(Rr, P);
+    } else if (op == 7) {
+        Rr = P;
+    } else {  // scalar mult: b is a 32-byte scalar, plain double-and-add via Niels
+        ge_niels q;
+        ge_affine_to_niels(q, P.X, P.Y);
+        ge_identity(Rr);
+#pragma unroll 1
+        for (int bit = 255; bit >= 0; bit--) {
+            ge_double(Rr, Rr);
+            if ((pb[bit >> 3] >> (bit & 7)) & 1) ge_madd(Rr, Rr, q, false);
+        }
+    }
+    ge_compress(po, Rr);
+}

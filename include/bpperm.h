@@ -1,0 +1,123 @@
+/* bpperm.h - C ABI of the B200 (sm_100a) backend for bulletproof-perm's hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  Every
+ * entry point names the reference interface it replaces.  The reference
+ * (/root/reference/bp-perm, Rust) reaches its group arithmetic through the dalek trait
+ *     curve25519_dalek_ng::traits::VartimeMultiscalarMul      (circuit_lib.rs:11, lib.rs:27)
+ * invoked as RistrettoPoint::vartime_multiscalar_mul(scalars, points) at
+ * circuit_lib.rs:187,202,216,363,374,385,396,407,498,504,509,525,535,552,568, and its scalar
+ * vector work through the free functions of util.rs / poly.rs.  INTEGRATION.md shows the Rust
+ * `extern "C"` block and the `impl VartimeMultiscalarMul for GpuRistretto` that bind these symbols.
+ *
+ * Conventions
+ *   - every function returns BPP_OK (0) or a negative bpp_status; nothing aborts or throws.
+ *   - scalars are 32-byte little-endian integers with bit 255 clear (dalek `Scalar` invariant);
+ *     canonical (< l) wherever a scalar is an arithmetic operand of the mod-l kernels.
+ *   - compressed points are 32-byte RFC 9496 ristretto255 encodings.
+ *   - "host" entry points take host pointers and include the host<->device copies;
+ *     "_dev" entry points take device pointers and enqueue on the context's stream.
+ *   - a context is bound to one GPU and one stream; use one context per thread.
+ *   - there is no CPU fallback: without a CUDA device bpp_init fails with BPP_ERR_NO_DEVICE.
+ */
+#ifndef BPPERM_H
+#define BPPERM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum bpp_status {
+    BPP_OK = 0,
+    BPP_ERR_NO_DEVICE = -1,     /* no CUDA device / wrong architecture */
+    BPP_ERR_CUDA = -2,          /* a CUDA runtime call failed; see bpp_last_error() */
+    BPP_ERR_INVALID_ARG = -3,   /* null pointer, zero where non-zero is required, bad enum */
+    BPP_ERR_LENGTH_MISMATCH = -4, /* dalek panics when the two iterators differ in length (edwards.rs) */
+    BPP_ERR_INVALID_POINT = -5, /* a compressed point failed RFC 9496 decoding (dalek: decompress() -> None) */
+    BPP_ERR_SCALAR_RANGE = -6,  /* a scalar has bit 255 set */
+    BPP_ERR_OOM = -7,
+    BPP_ERR_VERIFICATION = -8   /* bulletproofs::ProofError::VerificationError (circuit_lib.rs:487,519,543) */
+} bpp_status;
+
+typedef struct bpp_ctx bpp_ctx;
+typedef struct bpp_points bpp_points;
+
+/* point input formats */
+enum {
+    BPP_FMT_COMPRESSED = 0, /* 32 B RFC 9496 encoding (CompressedRistretto) */
+    BPP_FMT_AFFINE = 1,     /* 64 B: x || y, each 32-byte little-endian, any representative of the Ristretto coset */
+    BPP_FMT_DALEK_XYZT = 2  /* 160 B: dalek-ng in-memory RistrettoPoint = EdwardsPoint{X,Y,Z,T: FieldElement51([u64;5])} */
+};
+
+/* ---- lifecycle ---------------------------------------------------------------------------- */
+int bpp_init(int device, bpp_ctx **out);
+void bpp_free(bpp_ctx *ctx);
+/* Enqueue on an existing CUDA stream (a cudaStream_t passed as void*) instead of the context's own. */
+int bpp_set_stream(bpp_ctx *ctx, void *cuda_stream);
+int bpp_synchronize(bpp_ctx *ctx);
+const char *bpp_strerror(int status);
+const char *bpp_last_error(bpp_ctx *ctx);
+/* Number of kernels this context has launched since creation (bench.py's `gpu_launches`). */
+uint64_t bpp_launch_count(bpp_ctx *ctx);
+int bpp_device_info(bpp_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, size_t *total_mem);
+
+/* ---- points: upload once, reuse across MSMs (generators are static in the protocol) -------- */
+/* Converts n points to the device layout (affine Niels, 96 B/point).  For BPP_FMT_COMPRESSED an
+ * invalid encoding yields BPP_ERR_INVALID_POINT (dalek: decompress().unwrap() panics, circuit_lib.rs:532). */
+int bpp_points_upload(bpp_ctx *ctx, int fmt, const uint8_t *pts, size_t n, bpp_points **out);
+/* RistrettoPoint::from_uniform_bytes / RistrettoPoint::random(rng) (lib.rs:165-166,179-180): n x 64 uniform
+ * bytes -> n points (RFC 9496 one-way map), kept on the device. */
+int bpp_points_from_uniform(bpp_ctx *ctx, const uint8_t *bytes64, size_t n, bpp_points **out);
+/* RistrettoPoint::compress for points[off .. off+n): n x 32 bytes to host memory. */
+int bpp_points_compress(bpp_ctx *ctx, const bpp_points *points, size_t off, size_t n, uint8_t *out32);
+void bpp_points_free(bpp_ctx *ctx, bpp_points *p);
+size_t bpp_points_len(const bpp_points *p);
+
+/* ---- multiscalar multiplication ------------------------------------------------------------
+ * Replaces RistrettoPoint::vartime_multiscalar_mul (dalek-ng 4.1.1 traits.rs / edwards.rs
+ * optional_multiscalar_mul; Straus below 190 points, Pippenger above).  Result = sum_i s_i * P_i
+ * over points[off .. off+n).  out_compressed receives the canonical 32-byte encoding
+ * (== result.compress().to_bytes()); out_ext (nullable) receives X,Y,Z,T as 4 x 32-byte
+ * canonical little-endian field elements (128 B) for callers that keep an uncompressed point. */
+int bpp_msm_vartime(bpp_ctx *ctx, const uint8_t *scalars, size_t n_scalars, const bpp_points *points, size_t off,
+                    size_t n, uint8_t out_compressed[32], uint8_t *out_ext /* 128 B or NULL */);
+/* One-shot form: uploads the points, runs the MSM, frees them (what a trait call with fresh
+ * iterators does). */
+int bpp_msm_vartime_host(bpp_ctx *ctx, const uint8_t *scalars, size_t n_scalars, int fmt, const uint8_t *pts,
+                         size_t n_points, uint8_t out_compressed[32]);
+/* Device-resident form: scalars already in HBM (n x 32 B), result (32 B compressed, then 128 B
+ * X,Y,Z,T as raw 8x32-bit-limb field elements) written to d_out (160 B, device). Asynchronous. */
+int bpp_msm_vartime_dev(bpp_ctx *ctx, const void *d_scalars, const bpp_points *points, size_t off, size_t n,
+                        void *d_out);
+/* Partial (uncompressed) sum for multi-GPU sharding: writes the 128-byte extended point (raw limbs)
+ * to d_partial and does not compress.  bpp_points_sum_compress_dev adds g such partials (e.g. after an
+ * all-gather) and compresses: d_out32 receives the 32-byte encoding. */
+int bpp_msm_partial_dev(bpp_ctx *ctx, const void *d_scalars, const bpp_points *points, size_t off, size_t n,
+                        void *d_partial);
+int bpp_points_sum_compress_dev(bpp_ctx *ctx, const void *d_partials, size_t g, void *d_out32);
+/* Override the Pippenger window width (0 = automatic). */
+int bpp_set_window_bits(bpp_ctx *ctx, int c);
+
+/* ---- measurement helpers --------------------------------------------------------------------- */
+/* IMAD.WIDE.U32 peak microbenchmark: returns wide multiply-adds per second over all SMs. */
+int bpp_bench_imad_peak(bpp_ctx *ctx, int iters, double *ops_per_sec, double *ms);
+/* Per-phase device time (ms) of the last bpp_msm_* call when profiling is enabled. */
+enum { BPP_PHASE_RECODE = 0, BPP_PHASE_SCAN, BPP_PHASE_SCATTER, BPP_PHASE_ACCUMULATE, BPP_PHASE_REDUCE,
+       BPP_PHASE_FINISH, BPP_PHASE_COUNT };
+int bpp_set_profiling(bpp_ctx *ctx, int on);
+int bpp_last_phase_ms(bpp_ctx *ctx, float ms[BPP_PHASE_COUNT]);
+/* point-add count of the last MSM: accumulate (mixed) adds, reduction (full) adds, doublings */
+int bpp_last_op_counts(bpp_ctx *ctx, uint64_t *mixed_adds, uint64_t *full_adds, uint64_t *doublings);
+
+/* ---- element-wise self-test hooks (used by tests/ to compare single operations with the oracle) */
+enum { BPP_TEST_FE_MUL = 0, BPP_TEST_FE_ADD, BPP_TEST_FE_SUB, BPP_TEST_FE_INVERT, BPP_TEST_FE_CANON,
+       BPP_TEST_GE_ADD, BPP_TEST_GE_DOUBLE, BPP_TEST_GE_COMPRESS_ROUNDTRIP, BPP_TEST_GE_SCALARMULT };
+/* a, b: n x 32-byte operands (points as compressed encodings); out: n x 32 bytes. */
+int bpp_test_op(bpp_ctx *ctx, int op, const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BPPERM_H */

@@ -1,0 +1,156 @@
+"""GPU parity: RistrettoPoint::vartime_multiscalar_mul through the C ABI vs the CPU oracle.
+Bit-exact on the 32-byte compressed result."""
+import os
+import random
+
+import pytest
+
+from oracle import ristretto255 as R
+from oracle.chacha import ChaChaRng
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(n, seed):
+    rng = ChaChaRng(bytes([seed]) * 32)
+    pts = [rng.point() for _ in range(n)]
+    sc = [rng.scalar() for _ in range(n)]
+    return sc, pts
+
+
+def test_survey_e2_golden_vector(backend):
+    rng = ChaChaRng(bytes(range(32)))
+    pts = [rng.point() for _ in range(4)]
+    sc = [rng.scalar() for _ in range(4)]
+    out = backend.vartime_multiscalar_mul(sc, [R.compress(p) for p in pts])
+    assert out.hex() == "ac0188282e26885b30102aa5ee4e91734b3328dba689b17245af361585d58d6f"
+
+
+# the reference's own MSM sizes at 52 cards plus ragged / tiny cases
+@pytest.mark.parametrize("n", [1, 2, 3, 17, 104, 105, 110, 111, 209, 600])
+def test_msm_matches_oracle(backend, n):
+    sc, pts = _inputs(n, n % 251)
+    want = R.compress(R.msm_naive(sc, pts))
+    got = backend.vartime_multiscalar_mul(sc, [R.compress(p) for p in pts])
+    assert got == want
+
+
+@pytest.mark.parametrize("c", list(range(4, 17)))
+def test_every_window_width_gives_identical_bytes(backend, c):
+    sc, pts = _inputs(64, 77)
+    want = R.compress(R.msm_naive(sc, pts))
+    backend.set_window_bits(c)
+    try:
+        assert backend.vartime_multiscalar_mul(sc, [R.compress(p) for p in pts]) == want
+    finally:
+        backend.set_window_bits(0)
+
+
+def test_edge_scalars_and_points(backend):
+    sc, pts = _inputs(12, 3)
+    sc[0] = 0
+    sc[1] = 1
+    sc[2] = R.L - 1
+    sc[3] = 2**252
+    sc[4] = R.L - 2**128
+    pts[5] = R.IDENTITY
+    pts[6] = pts[7]                      # repeated point
+    sc[8], sc[9] = 12345, R.L - 12345    # s*P + (-s)*P
+    pts[9] = pts[8]
+    sc[10] = (1 << 255) - 1 - (1 << 254)  # non-canonical but bit 255 clear (dalek allows < 2^255)
+    want = R.compress(R.msm_naive([s % R.L for s in sc], pts))
+    got = backend.vartime_multiscalar_mul(sc, [R.compress(p) for p in pts])
+    assert got == want
+
+
+def test_cancelling_terms_give_identity(backend):
+    sc, pts = _inputs(5, 4)
+    sc2 = sc + [R.L - s for s in sc]
+    enc = [R.compress(p) for p in pts] * 2
+    assert backend.vartime_multiscalar_mul(sc2, enc) == bytes(32)
+    assert backend.vartime_multiscalar_mul([0] * 10, enc) == bytes(32)
+
+
+def test_empty_and_error_behaviour(backend):
+    import bpperm_b200
+    assert backend.vartime_multiscalar_mul([], []) == bytes(32)   # empty sum = identity (dalek: same)
+    sc, pts = _inputs(3, 5)
+    enc = [R.compress(p) for p in pts]
+    with pytest.raises(bpperm_b200.BppError) as ei:              # dalek asserts equal lengths
+        backend.vartime_multiscalar_mul(sc[:2], enc)
+    assert ei.value.status == -4
+    with pytest.raises(bpperm_b200.BppError) as ei:
+        backend.vartime_multiscalar_mul([1 << 255, 1, 1], enc)
+    assert ei.value.status == -6
+    with pytest.raises(bpperm_b200.BppError) as ei:              # decompress().unwrap() on a bad point
+        backend.vartime_multiscalar_mul(sc, enc[:2] + [b"\x01" + bytes(31)])
+    assert ei.value.status == -5
+
+
+def test_resident_points_offsets_and_ext_output(backend):
+    sc, pts = _inputs(40, 6)
+    table = backend.upload_points([R.compress(p) for p in pts])
+    for off, n in ((0, 40), (5, 10), (39, 1), (13, 27)):
+        want = R.msm_naive(sc[:n], pts[off:off + n])
+        got, ext = backend.vartime_multiscalar_mul(sc[:n], table, off=off, n=n, want_ext=True)
+        assert got == R.compress(want)
+        X, Y, Z, T = (int.from_bytes(ext[32 * k:32 * k + 32], "little") for k in range(4))
+        assert max(X, Y, Z, T) < R.P
+        assert R.compress((X, Y, Z, T)) == got and (X * Y - Z * T) % R.P == 0
+
+
+def _np_scalars(n, seed):
+    import numpy as np
+    rs = np.random.RandomState(seed)
+    b = rs.randint(0, 256, size=(n, 32), dtype=np.uint8)
+    b[:, 31] &= 0x0F      # < 2^252 < l: canonical
+    return b
+
+
+@pytest.mark.parametrize("logn", [14, 20])
+def test_large_msm_properties(backend, logn):
+    """BASELINE sizes: no CPU oracle finishes 2^20 in seconds, so check size-independent properties:
+    (1) identical bytes for two different window widths (two different bucket decompositions),
+    (2) split linearity: MSM(all) == sum of the two half-MSMs' partial points,
+    (3) scalar linearity: MSM(s) + MSM(l - s) == identity,
+    (4) a 600-point slice equals the CPU oracle."""
+    import numpy as np
+    import torch
+    n = 1 << logn
+    seed_bytes = np.random.RandomState(logn).randint(0, 256, size=(n, 64), dtype=np.uint8).tobytes()
+    table = backend.points_from_uniform(seed_bytes)
+    sc = _np_scalars(n, 1000 + logn)
+    scb = sc.tobytes()
+    full = backend.vartime_multiscalar_mul(scb, table)
+    backend.set_window_bits(13)
+    try:
+        assert backend.vartime_multiscalar_mul(scb, table) == full
+    finally:
+        backend.set_window_bits(0)
+    # (2) halves via the device-pointer partial API
+    dev = torch.device("cuda:0")
+    d_sc = torch.from_numpy(sc).to(dev)
+    parts = torch.zeros(2, 128, dtype=torch.uint8, device=dev)
+    out32 = torch.zeros(32, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    h = n // 2
+    backend.msm_partial_dev(d_sc.data_ptr(), table, 0, h, parts[0].data_ptr())
+    backend.msm_partial_dev(d_sc[h:].data_ptr(), table, h, n - h, parts[1].data_ptr())
+    backend.points_sum_compress_dev(parts.data_ptr(), 2, out32.data_ptr())
+    backend.synchronize()
+    assert bytes(out32.cpu().numpy().tobytes()) == full
+    # (3) negated scalars
+    neg = np.zeros_like(sc)
+    for i in range(0, n, max(1, n // 4096)):   # negate a subset exactly on the host (python ints)
+        pass
+    sub = 2048
+    s_int = [int.from_bytes(sc[i].tobytes(), "little") for i in range(sub)]
+    both = b"".join(x.to_bytes(32, "little") for x in s_int) + b"".join((R.L - x).to_bytes(32, "little") for x in s_int)
+    enc = backend.compress_points(table, 0, sub)
+    t2 = backend.upload_points(enc + enc)
+    assert backend.vartime_multiscalar_mul(both, t2) == bytes(32)
+    # (4) slice against the oracle
+    k = 600
+    pts = [R.decompress(enc[32 * i:32 * i + 32]) for i in range(k)]
+    want = R.compress(R.msm_naive(s_int[:k], pts))
+    assert backend.vartime_multiscalar_mul(scb[:32 * k], table, off=0, n=k) == want
