@@ -24,7 +24,7 @@ struct bpp_ctx {
     std::string last_error;
     uint64_t launches = 0;
     int forced_c = 0;
-    bool profiling = false;
+    bool profiling = false, events_pending = false;
     cudaEvent_t ev[BPP_PHASE_COUNT + 1] = {};
     float phase_ms[BPP_PHASE_COUNT] = {};
     uint64_t n_madd = 0, n_add = 0, n_dbl = 0;
@@ -33,6 +33,9 @@ struct bpp_ctx {
     uint32_t *d_counts = nullptr, *d_offsets = nullptr, *d_cursor = nullptr;  // W x B each
     size_t cap_wb = 0, cap_offsets = 0, cap_cursor = 0;
     uint32_t *d_entries = nullptr; size_t cap_entries = 0;      // W x n
+    uint16_t *d_ebkt = nullptr; size_t cap_ebkt = 0;            // W x n bucket ids
+    uint32_t *d_partials = nullptr; size_t cap_partials = 0;    // 2 x tiles x 32
+    uint32_t *d_long = nullptr; size_t cap_long = 0;            // hot-bucket queue (+ counter at [0] of d_flag+1)
     uint32_t *d_buckets = nullptr; size_t cap_buckets = 0;      // W x B x 32
     uint32_t *d_segS = nullptr, *d_segR = nullptr; size_t cap_seg = 0;
     uint32_t *d_blk = nullptr; size_t cap_blk = 0;              // 3 x W x nb x 32
@@ -127,7 +130,8 @@ extern "C" void bpp_free(bpp_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     void *ptrs[] = {ctx->d_scalars, ctx->d_counts, ctx->d_offsets, ctx->d_cursor, ctx->d_entries, ctx->d_buckets,
-                    ctx->d_segS, ctx->d_segR, ctx->d_blk, ctx->d_out, ctx->d_stage, ctx->d_flag};
+                    ctx->d_segS, ctx->d_segR, ctx->d_blk, ctx->d_out, ctx->d_stage, ctx->d_flag,
+                    ctx->d_ebkt, ctx->d_partials, ctx->d_long};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
@@ -174,6 +178,11 @@ extern "C" int bpp_set_profiling(bpp_ctx *ctx, int on) {
 }
 extern "C" int bpp_last_phase_ms(bpp_ctx *ctx, float ms[BPP_PHASE_COUNT]) {
     if (!ctx || !ms) return BPP_ERR_INVALID_ARG;
+    if (ctx->profiling && ctx->events_pending) {  // the events of the last MSM were recorded on the stream
+        CK(ctx, cudaEventSynchronize(ctx->ev[BPP_PHASE_COUNT]));
+        for (int i = 0; i < BPP_PHASE_COUNT; i++) cudaEventElapsedTime(&ctx->phase_ms[i], ctx->ev[i], ctx->ev[i + 1]);
+        ctx->events_pending = false;
+    }
     for (int i = 0; i < BPP_PHASE_COUNT; i++) ms[i] = ctx->phase_ms[i];
     return BPP_OK;
 }
@@ -332,6 +341,12 @@ static int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points
     if ((rc = grow(ctx, &ctx->d_offsets, &ctx->cap_offsets, WB))) return rc;
     if ((rc = grow(ctx, &ctx->d_cursor, &ctx->cap_cursor, WB))) return rc;
     if ((rc = grow(ctx, &ctx->d_entries, &ctx->cap_entries, (size_t)W * n))) return rc;
+    if ((rc = grow(ctx, &ctx->d_ebkt, &ctx->cap_ebkt, (size_t)W * n))) return rc;
+    const uint32_t tpw = (uint32_t)((n + BPP_TILE - 1) / BPP_TILE);
+    const size_t total_tiles = (size_t)W * tpw;
+    if ((rc = grow(ctx, &ctx->d_partials, &ctx->cap_partials, total_tiles * 2 * 32))) return rc;
+    if ((rc = grow(ctx, &ctx->d_long, &ctx->cap_long, total_tiles / BPP_LONG_SPAN + 16))) return rc;
+    uint32_t *d_nlong = ctx->d_flag + 8;
     if ((rc = grow(ctx, &ctx->d_buckets, &ctx->cap_buckets, WB * 32))) return rc;
     {
         size_t need = (size_t)W * T * 32;
@@ -353,6 +368,7 @@ static int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points
     const uint32_t *niels = pts->niels + 24 * off;
     if (prof) cudaEventRecord(ctx->ev[0], s);
     CK(ctx, cudaMemsetAsync(ctx->d_counts, 0, WB * 4, s));
+    CK(ctx, cudaMemsetAsync(d_nlong, 0, 4, s));
     unsigned sb = (unsigned)((n + 255) / 256);
     k_digit_hist<<<sb, 256, 0, s>>>(d_scalars, (uint32_t)n, c, W, ctx->d_counts);
     LAUNCH_CHECK(ctx);
@@ -360,13 +376,20 @@ static int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points
     k_window_scan<<<W, 1024, 0, s>>>(ctx->d_counts, B, ctx->d_offsets, ctx->d_cursor);
     LAUNCH_CHECK(ctx);
     if (prof) cudaEventRecord(ctx->ev[2], s);
-    k_digit_scatter<<<sb, 256, 0, s>>>(d_scalars, (uint32_t)n, c, W, ctx->d_cursor, ctx->d_entries);
+    k_digit_scatter<<<sb, 256, 0, s>>>(d_scalars, (uint32_t)n, c, W, ctx->d_cursor, ctx->d_entries, ctx->d_ebkt);
     LAUNCH_CHECK(ctx);
     if (prof) cudaEventRecord(ctx->ev[3], s);
-    k_bucket_accum<<<(unsigned)((WB + BPP_ACC_THREADS - 1) / BPP_ACC_THREADS), BPP_ACC_THREADS, 0, s>>>(
-        niels, ctx->d_entries, ctx->d_offsets, ctx->d_cursor, (uint32_t)n, B, (uint32_t)WB, ctx->d_buckets);
+    k_bucket_accum<<<(unsigned)((total_tiles + BPP_ACC_THREADS - 1) / BPP_ACC_THREADS), BPP_ACC_THREADS, 0, s>>>(
+        niels, ctx->d_entries, ctx->d_ebkt, ctx->d_offsets, ctx->d_cursor, (uint32_t)n, B, tpw, (uint32_t)total_tiles,
+        ctx->d_buckets, ctx->d_partials);
     LAUNCH_CHECK(ctx);
     if (prof) cudaEventRecord(ctx->ev[4], s);
+    k_bucket_fixup<<<(unsigned)((WB + 127) / 128), 128, 0, s>>>(ctx->d_offsets, ctx->d_cursor, B, tpw, (uint32_t)WB,
+                                                               ctx->d_partials, ctx->d_buckets, ctx->d_long, d_nlong);
+    LAUNCH_CHECK(ctx);
+    k_bucket_fixup_long<<<ctx->sm_count * 2, 128, 0, s>>>(ctx->d_offsets, ctx->d_cursor, B, tpw, ctx->d_partials,
+                                                         ctx->d_buckets, ctx->d_long, d_nlong);
+    LAUNCH_CHECK(ctx);
     const uint32_t chunks = (uint32_t)W * T;
     k_bucket_reduce1<<<(chunks + 127) / 128, 128, 0, s>>>(ctx->d_buckets, L, chunks, ctx->d_segS, ctx->d_segR);
     LAUNCH_CHECK(ctx);
@@ -375,19 +398,14 @@ static int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points
     if (prof) cudaEventRecord(ctx->ev[5], s);
     k_msm_finish<<<1, 64, 0, s>>>(blkS, blkB, blkR, nb, log2L, c, W, do_compress, d_out);
     LAUNCH_CHECK(ctx);
-    if (prof) cudaEventRecord(ctx->ev[6], s);
+    if (prof) { cudaEventRecord(ctx->ev[6], s); ctx->events_pending = true; }
     ctx->n_madd = (uint64_t)W * n;
-    ctx->n_add = (uint64_t)W * T * (2 * (uint64_t)L - 2) + (uint64_t)W * nb * (30 + 2 * 8 + 3) + (uint64_t)W * (3 * nb + 2) + (W - 1);
+    ctx->n_add = (uint64_t)W * (B < tpw ? B : tpw) /* fix-up of buckets cut by tile boundaries (upper bound) */ +
+                 (uint64_t)W * T * (2 * (uint64_t)L - 2) + (uint64_t)W * nb * (30 + 2 * 8 + 3) + (uint64_t)W * (3 * nb + 2) + (W - 1);
     ctx->n_dbl = (uint64_t)c * (W - 1) + (uint64_t)W * (log2L + (nb > 1 ? 8 : 0)) + (uint64_t)W * nb * 5;
     return BPP_OK;
 }
 
-static int finish_profile(bpp_ctx *ctx) {
-    if (!ctx->profiling) return BPP_OK;
-    CK(ctx, cudaEventSynchronize(ctx->ev[BPP_PHASE_COUNT]));
-    for (int i = 0; i < BPP_PHASE_COUNT; i++) cudaEventElapsedTime(&ctx->phase_ms[i], ctx->ev[i], ctx->ev[i + 1]);
-    return BPP_OK;
-}
 
 static int check_scalars_host(const uint8_t *scalars, size_t n) {
     for (size_t i = 0; i < n; i++)
@@ -443,7 +461,6 @@ extern "C" int bpp_msm_vartime(bpp_ctx *ctx, const uint8_t *scalars, size_t n_sc
     if ((rc = msm_enqueue(ctx, ctx->d_scalars, points, off, n, ctx->d_out, 1))) return rc;
     CK(ctx, cudaMemcpyAsync(ctx->h_out, ctx->d_out, 160, cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
-    if ((rc = finish_profile(ctx))) return rc;
     memcpy(out32, ctx->h_out, 32);
     if (out_ext) {
         // canonicalise the four raw field elements on the host: value mod p, little endian

@@ -9,7 +9,8 @@
 //   k_digit_hist      signed-window recode, per-(window,bucket) histogram (atomics)
 //   k_window_scan     exclusive scan of each window's histogram -> bucket offsets
 //   k_digit_scatter   counting-sort scatter of (point index | sign) into bucket order
-//   k_bucket_accum    one thread per bucket: mixed adds (extended += affine Niels, 7M)
+//   k_bucket_accum    one thread per tile of 32 sorted entries: mixed adds (extended += affine Niels, 7M)
+//   k_bucket_fixup    stitches buckets cut by tile boundaries (+ k_bucket_fixup_long for hot buckets)
 //   k_bucket_reduce1  running sums over chunks of L buckets -> (S, R) per chunk
 //   k_bucket_reduce2  warp-shuffle suffix scans over 256 chunks -> (S, B, R) per block
 //   k_msm_finish      per-window totals, Horner over windows (c doublings each), compress
@@ -90,7 +91,8 @@ __global__ void __launch_bounds__(1024) k_window_scan(const uint32_t *__restrict
 }
 
 __global__ void k_digit_scatter(const uint32_t *__restrict__ scalars, uint32_t n, int c, int W,
-                                uint32_t *__restrict__ cursor, uint32_t *__restrict__ entries) {
+                                uint32_t *__restrict__ cursor, uint32_t *__restrict__ entries,
+                                uint16_t *__restrict__ ebkt) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t s[8];
@@ -106,32 +108,151 @@ __global__ void k_digit_scatter(const uint32_t *__restrict__ scalars, uint32_t n
         if (mag) {
             uint32_t pos = atomicAdd(&cursor[(size_t)w * half + (mag - 1)], 1u);
             entries[(size_t)w * n + pos] = i | (carry << 31);
+            ebkt[(size_t)w * n + pos] = (uint16_t)(mag - 1);
         }
     }
 }
 
 // ---- bucket accumulation: the dominant kernel ------------------------------------------------
-// One thread per (window, bucket).  entries are grouped by bucket; `niels` is the static point
-// table (96 B per point, read through the read-only path; 2^20 points = 96 MiB, L2 resident).
+// The bucket-sorted entry list of each window is cut into tiles of BPP_TILE entries; one thread
+// owns one tile, so every thread performs the same number of mixed adds (extended += affine
+// Niels, 7M) whatever the bucket sizes are: no warp divergence from Poisson bucket sizes and no
+// serialisation on hot buckets (repeated / small scalars).  A bucket that lies inside one tile is
+// written directly; a bucket cut by a tile boundary leaves partial sums (at most two per tile:
+// `head` = the run touching the tile start, `tail` = the run touching the tile end) that
+// k_bucket_fixup adds up.  `niels` is the static point table (96 B per point, read-only path).
+#define BPP_TILE 32
+
+FE_INLINE void bucket_flush(const ge_ext &acc, uint32_t w, uint32_t b, uint32_t rs, uint32_t re, uint32_t e0,
+                            uint32_t B, size_t tile, const uint32_t *__restrict__ offsets,
+                            const uint32_t *__restrict__ ends, uint32_t *__restrict__ buckets,
+                            uint32_t *__restrict__ partials) {
+    size_t g = (size_t)w * B + b;
+    bool complete = (offsets[g] == rs) && (ends[g] == re);
+    uint32_t *dst = complete ? buckets + 32 * g : partials + 32 * (2 * tile + (rs == e0 ? 0 : 1));
+    ge_store(dst, acc);
+}
+
 __global__ void __launch_bounds__(BPP_ACC_THREADS) k_bucket_accum(
-    const uint32_t *__restrict__ niels, const uint32_t *__restrict__ entries,
+    const uint32_t *__restrict__ niels, const uint32_t *__restrict__ entries, const uint16_t *__restrict__ ebkt,
     const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ ends, uint32_t n, uint32_t B,
-    uint32_t total_buckets, uint32_t *__restrict__ buckets) {
-    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= total_buckets) return;
-    uint32_t w = g / B;
-    uint32_t beg = offsets[g], end = ends[g];
+    uint32_t tiles_per_window, uint32_t total_tiles, uint32_t *__restrict__ buckets,
+    uint32_t *__restrict__ partials) {
+    uint32_t tile = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= total_tiles) return;
+    const uint32_t w = tile / tiles_per_window, t = tile - w * tiles_per_window;
+    const uint32_t cnt = ends[(size_t)w * B + (B - 1)];  // entries in this window
+    const uint32_t e0 = t * BPP_TILE;
+    if (e0 >= cnt) return;
+    const uint32_t e1 = min(e0 + BPP_TILE, cnt);
     const uint32_t *ew = entries + (size_t)w * n;
+    const uint16_t *bw = ebkt + (size_t)w * n;
     ge_ext acc;
     ge_identity(acc);
+    uint32_t idx = ew[e0];
+    uint32_t cur = bw[e0], run_start = e0;
+    ge_niels q;
+    ge_niels_load(q, niels + 24 * (size_t)(idx & 0x7fffffffu));
 #pragma unroll 1
-    for (uint32_t e = beg; e < end; e++) {
-        uint32_t idx = ew[e];
-        ge_niels q;
-        ge_niels_load(q, niels + 24 * (size_t)(idx & 0x7fffffffu));
+    for (uint32_t e = e0; e < e1; e++) {
+        // software pipeline: fetch the next entry's point while this one is being added
+        uint32_t idx_n = idx, b_n = cur;
+        ge_niels qn = q;
+        if (e + 1 < e1) {
+            idx_n = ew[e + 1];
+            b_n = bw[e + 1];
+            ge_niels_load(qn, niels + 24 * (size_t)(idx_n & 0x7fffffffu));
+        }
         ge_madd(acc, acc, q, (idx >> 31) != 0);
+        if (e + 1 == e1 || b_n != cur) {
+            bucket_flush(acc, w, cur, run_start, e + 1, e0, B, tile, offsets, ends, buckets, partials);
+            ge_identity(acc);
+            cur = b_n;
+            run_start = e + 1;
+        }
+        idx = idx_n;
+        q = qn;
+    }
+}
+
+// One thread per (window, bucket): empty buckets become the identity; buckets cut by tile
+// boundaries are assembled from their partial sums.  Buckets spanning more than BPP_LONG_SPAN
+// tiles (hot buckets) are queued for k_bucket_fixup_long.
+#define BPP_LONG_SPAN 24
+__global__ void __launch_bounds__(128) k_bucket_fixup(const uint32_t *__restrict__ offsets,
+                                                      const uint32_t *__restrict__ ends, uint32_t B,
+                                                      uint32_t tiles_per_window, uint32_t total_buckets,
+                                                      const uint32_t *__restrict__ partials,
+                                                      uint32_t *__restrict__ buckets, uint32_t *__restrict__ long_list,
+                                                      uint32_t *__restrict__ n_long) {
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total_buckets) return;
+    const uint32_t beg = offsets[g], end = ends[g];
+    if (beg == end) {
+        ge_ext id;
+        ge_identity(id);
+        ge_store(buckets + 32 * (size_t)g, id);
+        return;
+    }
+    const uint32_t first = beg / BPP_TILE, last = (end - 1) / BPP_TILE;
+    if (first == last) return;  // complete inside one tile: already written
+    if (last - first > BPP_LONG_SPAN) {
+        long_list[atomicAdd(n_long, 1u)] = g;
+        return;
+    }
+    const size_t tbase = (size_t)(g / B) * tiles_per_window;
+    ge_ext acc, t;
+    ge_load(acc, partials + 32 * (2 * (tbase + first) + (beg > first * BPP_TILE ? 1 : 0)));
+#pragma unroll 1
+    for (uint32_t k = first + 1; k <= last; k++) {
+        ge_load(t, partials + 32 * (2 * (tbase + k)));
+        ge_add(acc, acc, t);
     }
     ge_store(buckets + 32 * (size_t)g, acc);
+}
+
+// One block (128 threads) per hot bucket: strided partial sums, then a shared-memory tree.
+__global__ void __launch_bounds__(128) k_bucket_fixup_long(const uint32_t *__restrict__ offsets,
+                                                           const uint32_t *__restrict__ ends, uint32_t B,
+                                                           uint32_t tiles_per_window,
+                                                           const uint32_t *__restrict__ partials,
+                                                           uint32_t *__restrict__ buckets,
+                                                           const uint32_t *__restrict__ long_list,
+                                                           const uint32_t *__restrict__ n_long) {
+    __shared__ __align__(16) uint32_t sh[128][32];
+    const uint32_t nl = *n_long;
+    for (uint32_t i = blockIdx.x; i < nl; i += gridDim.x) {
+        const uint32_t g = long_list[i];
+        const uint32_t beg = offsets[g], end = ends[g];
+        const uint32_t first = beg / BPP_TILE, last = (end - 1) / BPP_TILE;
+        const size_t tbase = (size_t)(g / B) * tiles_per_window;
+        ge_ext acc, t;
+        ge_identity(acc);
+#pragma unroll 1
+        for (uint32_t k = first + 1 + threadIdx.x; k <= last; k += 128) {
+            ge_load(t, partials + 32 * (2 * (tbase + k)));
+            ge_add(acc, acc, t);
+        }
+        ge_store(&sh[threadIdx.x][0], acc);
+        __syncthreads();
+#pragma unroll 1
+        for (uint32_t d = 64; d >= 1; d >>= 1) {
+            if (threadIdx.x < d) {
+                ge_load(acc, &sh[threadIdx.x][0]);
+                ge_load(t, &sh[threadIdx.x + d][0]);
+                ge_add(acc, acc, t);
+                ge_store(&sh[threadIdx.x][0], acc);
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            ge_load(acc, &sh[0][0]);
+            ge_load(t, partials + 32 * (2 * (tbase + first) + (beg > first * BPP_TILE ? 1 : 0)));
+            ge_add(acc, acc, t);
+            ge_store(buckets + 32 * (size_t)g, acc);
+        }
+        __syncthreads();
+    }
 }
 
 // ---- bucket reduction ---------------------------------------------------------------------------

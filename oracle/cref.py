@@ -1,0 +1,97 @@
+"""ctypes wrapper for oracle/c/dalek_ref.c (C restatement of the dalek-ng 4.1.1 serial backend).
+
+TEST INFRASTRUCTURE (see oracle/__init__.py): fast checker for sizes the Python oracle cannot
+reach, and the timed CPU baseline.  Points cross this API as opaque 160-byte blobs
+(the in-memory layout of dalek's RistrettoPoint: 4 x FieldElement51).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libbpperm_oracle.so")
+_lib = None
+PT = 160
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "c", "dalek_ref.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", os.path.join(_HERE, "c"), "-B"], stdout=subprocess.DEVNULL)
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        l = ctypes.CDLL(_SO)
+        c = ctypes
+        l.orc_point_size.restype = c.c_int
+        l.orc_decompress.argtypes = [c.c_char_p, c.c_size_t, c.c_char_p]
+        l.orc_compress.argtypes = [c.c_char_p, c.c_size_t, c.c_char_p]
+        l.orc_compress.restype = None
+        l.orc_from_uniform.argtypes = [c.c_char_p, c.c_size_t, c.c_char_p]
+        l.orc_from_uniform.restype = None
+        l.orc_point_add.argtypes = [c.c_char_p, c.c_char_p, c.c_char_p]
+        l.orc_point_add.restype = None
+        l.orc_msm_vartime.argtypes = [c.c_char_p, c.c_char_p, c.c_size_t, c.c_char_p]
+        l.orc_msm_vartime.restype = None
+        l.orc_msm_forced.argtypes = [c.c_int, c.c_char_p, c.c_char_p, c.c_size_t, c.c_char_p]
+        l.orc_msm_forced.restype = None
+        l.orc_scalar_mul.argtypes = [c.c_char_p, c.c_char_p, c.c_char_p]
+        l.orc_scalar_mul.restype = None
+        l.orc_msm_vartime_mt.argtypes = [c.c_char_p, c.c_char_p, c.c_size_t, c.c_int, c.c_char_p]
+        l.orc_msm_vartime_mt.restype = None
+        assert l.orc_point_size() == PT
+        _lib = l
+    return _lib
+
+
+def decompress(enc: bytes) -> bytes:
+    n = len(enc) // 32
+    out = ctypes.create_string_buffer(PT * n)
+    rc = lib().orc_decompress(enc, n, out)
+    if rc != 0:
+        raise ValueError("invalid ristretto255 encoding")
+    return out.raw
+
+
+def compress(pts: bytes) -> bytes:
+    n = len(pts) // PT
+    out = ctypes.create_string_buffer(32 * n)
+    lib().orc_compress(pts, n, out)
+    return out.raw
+
+
+def from_uniform(b64: bytes) -> bytes:
+    n = len(b64) // 64
+    out = ctypes.create_string_buffer(PT * n)
+    lib().orc_from_uniform(b64, n, out)
+    return out.raw
+
+
+def msm(scalars: bytes, pts: bytes, threads: int = 1, forced: int = -1) -> bytes:
+    """vartime_multiscalar_mul with dalek's dispatch -> 32-byte compressed result."""
+    n = len(pts) // PT
+    assert len(scalars) == 32 * n
+    out = ctypes.create_string_buffer(PT)
+    if forced >= 0:
+        lib().orc_msm_forced(forced, scalars, pts, n, out)
+    elif threads > 1:
+        lib().orc_msm_vartime_mt(scalars, pts, n, threads, out)
+    else:
+        lib().orc_msm_vartime(scalars, pts, n, out)
+    return compress(out.raw)
+
+
+def msm_raw(scalars: bytes, pts: bytes, threads: int = 1) -> bytes:
+    n = len(pts) // PT
+    out = ctypes.create_string_buffer(PT)
+    if threads > 1:
+        lib().orc_msm_vartime_mt(scalars, pts, n, threads, out)
+    else:
+        lib().orc_msm_vartime(scalars, pts, n, out)
+    return out.raw
