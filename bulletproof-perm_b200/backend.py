@@ -118,6 +118,11 @@ class Backend:
         self._check(self._lib.bpp_bench_imad_peak(self._ctx, iters, ctypes.byref(ops), ctypes.byref(ms)))
         return ops.value, ms.value
 
+    def pipe_probe(self, mode: int, iters: int = 2048) -> float:
+        ops = ctypes.c_double()
+        self._check(self._lib.bpp_bench_pipe_probe(self._ctx, mode, iters, ctypes.byref(ops)))
+        return ops.value
+
     # -- points ---------------------------------------------------------------------------------
     def upload_points(self, pts: Union[bytes, Sequence[bytes]], fmt: int = FMT_COMPRESSED) -> Points:
         if not isinstance(pts, (bytes, bytearray)):

@@ -525,6 +525,32 @@ extern "C" int bpp_bench_imad_peak(bpp_ctx *ctx, int iters, double *ops_per_sec,
     return BPP_OK;
 }
 
+// mode 0: plain IMAD.WIDE.U32 (64-bit accumulate); 1: carry-chained IMAD.WIDE.U32; 2: 32-bit IMAD; 3: IADD3.X chains
+extern "C" int bpp_bench_pipe_probe(bpp_ctx *ctx, int mode, int iters, double *ops_per_sec) {
+    if (!ctx || iters <= 0 || mode < 0 || mode > 3 || !ops_per_sec) return BPP_ERR_INVALID_ARG;
+    if (mode == 0) return bpp_bench_imad_peak(ctx, iters, ops_per_sec, nullptr);
+    CK(ctx, cudaSetDevice(ctx->device));
+    unsigned long long *d = (unsigned long long *)ctx->d_flag;
+    int blocks = ctx->sm_count * 8;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    k_pipe_probe<<<blocks, 256, 0, ctx->stream>>>(mode, 1u, iters / 8 + 1, d);
+    LAUNCH_CHECK(ctx);
+    cudaEventRecord(a, ctx->stream);
+    k_pipe_probe<<<blocks, 256, 0, ctx->stream>>>(mode, 7u, iters, d);
+    LAUNCH_CHECK(ctx);
+    cudaEventRecord(b, ctx->stream);
+    CK(ctx, cudaEventSynchronize(b));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    double per_u = mode == 1 ? 8.0 : 16.0;
+    *ops_per_sec = (double)blocks * 256.0 * (double)iters * 8.0 * per_u / (ms * 1e-3);
+    return BPP_OK;
+}
+
 extern "C" int bpp_test_op(bpp_ctx *ctx, int op, const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n) {
     if (!ctx || !a || !b || !out || n == 0 || n >= (1ull << 31)) return BPP_ERR_INVALID_ARG;
     CK(ctx, cudaSetDevice(ctx->device));

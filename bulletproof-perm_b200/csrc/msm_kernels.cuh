@@ -599,6 +599,52 @@ __global__ void __launch_bounds__(256) k_imad_peak(uint32_t seed, int iters, uns
     if (r == 0x1234567812345678ull) out[0] = r;  // never true in practice; keeps the chains alive
 }
 
+// Variants of the same microbenchmark for the instruction forms the multiplier can be built from:
+//   mode 1: carry chains (mad.lo.cc/madc.hi.cc pairs -> IMAD.WIDE.U32 with carry-out / .X carry-in)
+//   mode 2: 32-bit IMAD lo (mad.lo.u32)          mode 3: IADD3 carry chains (add.cc/addc)
+__global__ void __launch_bounds__(256) k_pipe_probe(int mode, uint32_t seed, int iters, unsigned long long *out) {
+    uint32_t a0 = seed + threadIdx.x, a1 = a0 * 3u + 1u, a2 = a0 * 5u + 2u, a3 = a0 * 7u + 3u;
+    uint32_t b = blockIdx.x * 2654435761u + 12345u;
+    uint32_t c0 = 1, c1 = 2, c2 = 3, c3 = 4, c4 = 5, c5 = 6, c6 = 7, c7 = 8, c8 = 0;
+    uint32_t d0 = 9, d1 = 10, d2 = 11, d3 = 12, d4 = 13, d5 = 14, d6 = 15, d7 = 16, d8 = 0;
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            if (mode == 1) {  // 2 independent chains of 4 wide multiply-adds each (8 per u)
+                fe_mad4(c0, c1, c2, c3, c4, c5, c6, c7, c8, a0, a1, a2, a3, b);
+                fe_mad4(d0, d1, d2, d3, d4, d5, d6, d7, d8, a1, a2, a3, a0, b);
+            } else if (mode == 2) {  // 16 independent 32-bit multiply-adds per u
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c0) : "r"(a0), "r"(b));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c1) : "r"(a1), "r"(b));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c2) : "r"(a2), "r"(b));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c3) : "r"(a3), "r"(b));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c4) : "r"(a0), "r"(b));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c5) : "r"(a1), "r"(b));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c6) : "r"(a2), "r"(b));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c7) : "r"(a3), "r"(b));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(d0) : "r"(a0), "r"(b));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(d1) : "r"(a1), "r"(b));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(d2) : "r"(a2), "r"(b));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(d3) : "r"(a3), "r"(b));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(d4) : "r"(a0), "r"(b));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(d5) : "r"(a1), "r"(b));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(d6) : "r"(a2), "r"(b));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(d7) : "r"(a3), "r"(b));
+            } else {  // 2 independent add-with-carry chains of 8 (16 adds per u)
+                asm volatile("add.cc.u32 %0,%0,%8; addc.cc.u32 %1,%1,%8; addc.cc.u32 %2,%2,%8; addc.cc.u32 %3,%3,%8;"
+                             "addc.cc.u32 %4,%4,%8; addc.cc.u32 %5,%5,%8; addc.cc.u32 %6,%6,%8; addc.u32 %7,%7,%8;"
+                             : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3), "+r"(c4), "+r"(c5), "+r"(c6), "+r"(c7) : "r"(b));
+                asm volatile("add.cc.u32 %0,%0,%8; addc.cc.u32 %1,%1,%8; addc.cc.u32 %2,%2,%8; addc.cc.u32 %3,%3,%8;"
+                             "addc.cc.u32 %4,%4,%8; addc.cc.u32 %5,%5,%8; addc.cc.u32 %6,%6,%8; addc.u32 %7,%7,%8;"
+                             : "+r"(d0), "+r"(d1), "+r"(d2), "+r"(d3), "+r"(d4), "+r"(d5), "+r"(d6), "+r"(d7) : "r"(a0));
+            }
+        }
+    }
+    uint32_t r = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7 ^ c8 ^ d0 ^ d1 ^ d2 ^ d3 ^ d4 ^ d5 ^ d6 ^ d7 ^ d8;
+    if (r == 0x12345678u && iters < 0) out[0] = r;
+}
+
 // ---- element-wise test kernels -------------------------------------------------------------------
 __global__ void k_test_op(int op, const uint8_t *__restrict__ a, const uint8_t *__restrict__ b,
                           uint8_t *__restrict__ out, uint32_t n) {

@@ -103,6 +103,9 @@ int bpp_set_window_bits(bpp_ctx *ctx, int c);
 /* ---- measurement helpers --------------------------------------------------------------------- */
 /* IMAD.WIDE.U32 peak microbenchmark: returns wide multiply-adds per second over all SMs. */
 int bpp_bench_imad_peak(bpp_ctx *ctx, int iters, double *ops_per_sec, double *ms);
+/* Same harness for the other instruction forms a multiplier can be built from.  mode 0: plain IMAD.WIDE.U32
+ * with a 64-bit addend; 1: carry-chained IMAD.WIDE.U32 (mad.lo.cc/madc.hi.cc); 2: 32-bit IMAD; 3: IADD3.X chains. */
+int bpp_bench_pipe_probe(bpp_ctx *ctx, int mode, int iters, double *ops_per_sec);
 /* Per-phase device time (ms) of the last bpp_msm_* call when profiling is enabled. */
 enum { BPP_PHASE_RECODE = 0, BPP_PHASE_SCAN, BPP_PHASE_SCATTER, BPP_PHASE_ACCUMULATE, BPP_PHASE_REDUCE,
        BPP_PHASE_FINISH, BPP_PHASE_COUNT };
