@@ -18,6 +18,9 @@ SYMBOLS = [
     "bpp_msm_vartime", "bpp_msm_vartime_host", "bpp_msm_vartime_dev", "bpp_msm_partial_dev",
     "bpp_points_sum_compress_dev", "bpp_set_window_bits", "bpp_bench_imad_peak", "bpp_bench_pipe_probe", "bpp_set_profiling",
     "bpp_last_phase_ms", "bpp_last_op_counts", "bpp_test_op",
+    "bpp_inner_product", "bpp_hadamard_V", "bpp_vm_mult", "bpp_mv_mult", "bpp_exp_iter", "bpp_scalar_powers",
+    "bpp_scalar_exp", "bpp_scalar_invert", "bpp_scalar_from_wide", "bpp_scalar_reduce",
+    "bpp_vecpoly3_special_inner_product", "bpp_vecpoly3_eval", "bpp_poly6_eval",
 ]
 
 _lib = None
@@ -71,5 +74,18 @@ def load() -> ctypes.CDLL:
     lib.bpp_last_phase_ms.argtypes = [vp, c.POINTER(c.c_float)]
     lib.bpp_last_op_counts.argtypes = [vp, c.POINTER(c.c_uint64), c.POINTER(c.c_uint64), c.POINTER(c.c_uint64)]
     lib.bpp_test_op.argtypes = [vp, c.c_int, u8p, u8p, c.c_char_p, sz]
+    lib.bpp_inner_product.argtypes = [vp, u8p, sz, u8p, sz, c.c_char_p]
+    lib.bpp_hadamard_V.argtypes = [vp, u8p, sz, u8p, sz, c.c_char_p]
+    lib.bpp_vm_mult.argtypes = [vp, u8p, sz, u8p, sz, sz, c.c_char_p]
+    lib.bpp_mv_mult.argtypes = [vp, u8p, sz, sz, u8p, sz, c.c_char_p]
+    lib.bpp_exp_iter.argtypes = [vp, u8p, sz, c.c_char_p]
+    lib.bpp_scalar_powers.argtypes = [vp, u8p, sz, sz, c.c_char_p]
+    lib.bpp_scalar_exp.argtypes = [vp, u8p, c.c_uint32, c.c_char_p]
+    lib.bpp_scalar_invert.argtypes = [vp, u8p, sz, c.c_char_p]
+    lib.bpp_scalar_from_wide.argtypes = [vp, u8p, sz, c.c_char_p]
+    lib.bpp_scalar_reduce.argtypes = [vp, u8p, sz, c.c_char_p]
+    lib.bpp_vecpoly3_special_inner_product.argtypes = [vp, u8p, u8p, sz, c.c_char_p]
+    lib.bpp_vecpoly3_eval.argtypes = [vp, u8p, sz, u8p, c.c_char_p]
+    lib.bpp_poly6_eval.argtypes = [vp, u8p, u8p, c.c_char_p]
     _lib = lib
     return lib

@@ -44,6 +44,7 @@ struct bpp_ctx {
     uint8_t *d_stage = nullptr; size_t cap_stage = 0;           // upload staging
     uint32_t *d_flag = nullptr;
     uint8_t *h_pinned = nullptr; size_t cap_pinned = 0;         // pinned staging for host scalars
+    uint8_t *d_vec = nullptr; size_t cap_vec = 0;               // arena of the scalar-vector operators
 };
 
 #define CK(ctx, call)                                                                              \
@@ -131,7 +132,7 @@ extern "C" void bpp_free(bpp_ctx *ctx) {
     cudaDeviceSynchronize();
     void *ptrs[] = {ctx->d_scalars, ctx->d_counts, ctx->d_offsets, ctx->d_cursor, ctx->d_entries, ctx->d_buckets,
                     ctx->d_segS, ctx->d_segR, ctx->d_blk, ctx->d_out, ctx->d_stage, ctx->d_flag,
-                    ctx->d_ebkt, ctx->d_partials, ctx->d_long};
+                    ctx->d_ebkt, ctx->d_partials, ctx->d_long, ctx->d_vec};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
@@ -572,3 +573,5 @@ extern "C" int bpp_test_op(bpp_ctx *ctx, int op, const uint8_t *a, const uint8_t
     }
     return BPP_OK;
 }
+
+#include "vec_capi.cuh"

@@ -1,0 +1,208 @@
+// sc25519.cuh - scalar arithmetic mod l = 2^252 + 27742317777372353535851937790883648493 (sm_100a).
+//
+// Replaces curve25519-dalek-ng 4.1.1 `Scalar` / `Scalar52` (backend/serial/u64/scalar.rs) under the
+// reference's scalar-vector operators: util.rs:6-94 (hadamard_V, vm_mult, mv_mult, exp_iter,
+// scalar_exp, inner_product), poly.rs:14-76, circuit_lib.rs:269-291,313-356,441-462 and
+// `Scalar::from_bytes_mod_order_wide` (transcript_protocol.rs:62-67).
+//
+// Representation: 8 x 32-bit limbs, canonical (< l) in memory - the same bytes dalek keeps.
+// Multiplication is Montgomery with R = 2^256: mont(a, b) = a*b/R.  sc_mul() of two standard-form
+// values is mont(mont(a, b), R^2); chains may stay in Montgomery form (sc_to_mont/sc_from_mont).
+// Every result is fully reduced, so any evaluation order gives identical bytes.
+#pragma once
+#include <stdint.h>
+
+#define SC_INLINE __device__ __forceinline__
+
+struct sc {
+    uint32_t v[8];
+};
+
+__device__ __constant__ const uint32_t SC_L[8] = {0x5cf5d3edu, 0x5812631au, 0xa2f79cd6u, 0x14def9deu,
+                                                  0x00000000u, 0x00000000u, 0x00000000u, 0x10000000u};
+// R mod l, R^2 mod l (R = 2^256), -l^{-1} mod 2^32
+__device__ __constant__ const uint32_t SC_R[8] = {0x8d98951du, 0xd6ec3174u, 0x737dcf70u, 0xc6ef5bf4u,
+                                                  0xfffffffeu, 0xffffffffu, 0xffffffffu, 0x0fffffffu};
+__device__ __constant__ const uint32_t SC_R2[8] = {0x449c0f01u, 0xa40611e3u, 0x68859347u, 0xd00e1ba7u,
+                                                   0x17f5be65u, 0xceec73d2u, 0x7c309a3du, 0x0399411bu};
+#define SC_NPRIME 0x12547e1bu
+
+SC_INLINE void sc_set0(sc &r) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = 0;
+}
+SC_INLINE void sc_set_u32(sc &r, uint32_t x) {
+    sc_set0(r);
+    r.v[0] = x;
+}
+SC_INLINE void sc_const(sc &r, const uint32_t *c) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = c[i];
+}
+SC_INLINE void sc_load(sc &r, const uint32_t *p) {  // 16-byte aligned
+    uint4 lo = *reinterpret_cast<const uint4 *>(p);
+    uint4 hi = *reinterpret_cast<const uint4 *>(p + 4);
+    r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w;
+    r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
+}
+SC_INLINE void sc_store(uint32_t *p, const sc &a) {
+    *reinterpret_cast<uint4 *>(p) = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);
+    *reinterpret_cast<uint4 *>(p + 4) = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
+}
+SC_INLINE bool sc_is_zero(const sc &a) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) o |= a.v[i];
+    return o == 0;
+}
+SC_INLINE bool sc_eq(const sc &a, const sc &b) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) o |= a.v[i] ^ b.v[i];
+    return o == 0;
+}
+
+// r = a - l if a >= l else a      (a < 2l)
+SC_INLINE void sc_cond_sub_l(sc &r, const uint32_t a[8], uint32_t top /* bit 256 of a */) {
+    uint32_t d[8];
+    long long borrow = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        long long t = (long long)a[i] - (long long)SC_L[i] + borrow;
+        d[i] = (uint32_t)t;
+        borrow = t >> 32;
+    }
+    bool ge = (top != 0) || (borrow == 0);
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = ge ? d[i] : a[i];
+}
+
+SC_INLINE void sc_add(sc &r, const sc &a, const sc &b) {  // canonical inputs
+    uint32_t s[8];
+    unsigned long long c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        c += (unsigned long long)a.v[i] + b.v[i];
+        s[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    sc_cond_sub_l(r, s, (uint32_t)c);
+}
+SC_INLINE void sc_sub(sc &r, const sc &a, const sc &b) {  // canonical inputs
+    uint32_t d[8];
+    long long borrow = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        long long t = (long long)a.v[i] - (long long)b.v[i] + borrow;
+        d[i] = (uint32_t)t;
+        borrow = t >> 32;
+    }
+    // add l back if negative
+    unsigned long long c = 0;
+    uint32_t mask = borrow ? 0xffffffffu : 0u;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        c += (unsigned long long)d[i] + (SC_L[i] & mask);
+        r.v[i] = (uint32_t)c;
+        c >>= 32;
+    }
+}
+SC_INLINE void sc_neg(sc &r, const sc &a) {
+    sc z;
+    sc_set0(z);
+    sc_sub(r, z, a);
+}
+
+// Montgomery product: r = a * b / 2^256 mod l.  Needs a * b < l * 2^256 (one operand < l suffices).
+SC_INLINE void sc_mont(sc &r, const sc &a, const sc &b) {
+    uint32_t t[17];
+#pragma unroll
+    for (int i = 0; i < 17; i++) t[i] = 0;
+    // schoolbook product, operand scanning with 64-bit temporaries (a*b + t + carry never overflows)
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        unsigned long long carry = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            unsigned long long v = (unsigned long long)a.v[j] * b.v[i] + t[i + j] + carry;
+            t[i + j] = (uint32_t)v;
+            carry = v >> 32;
+        }
+        t[i + 8] = (uint32_t)carry;
+    }
+    // Montgomery reduction; l has non-zero limbs only at 0..3 and 7
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint32_t m = t[i] * SC_NPRIME;
+        unsigned long long carry = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            unsigned long long v = (unsigned long long)m * SC_L[j] + t[i + j] + carry;
+            t[i + j] = (uint32_t)v;
+            carry = v >> 32;
+        }
+#pragma unroll
+        for (int k = i + 8; k < 17; k++) {
+            carry += t[k];
+            t[k] = (uint32_t)carry;
+            carry >>= 32;
+        }
+    }
+    sc_cond_sub_l(r, t + 8, t[16]);
+}
+
+SC_INLINE void sc_to_mont(sc &r, const sc &a) {
+    sc k;
+    sc_const(k, SC_R2);
+    sc_mont(r, a, k);
+}
+SC_INLINE void sc_from_mont(sc &r, const sc &a) {
+    sc one;
+    sc_set_u32(one, 1);
+    sc_mont(r, a, one);
+}
+// standard-form product a * b mod l
+SC_INLINE void sc_mul(sc &r, const sc &a, const sc &b) {
+    sc t, k;
+    sc_mont(t, a, b);
+    sc_const(k, SC_R2);
+    sc_mont(r, t, k);
+}
+__device__ __noinline__ void sc_mul_noinline(sc &r, const sc &a, const sc &b) { sc_mul(r, a, b); }
+__device__ __noinline__ void sc_mont_noinline(sc &r, const sc &a, const sc &b) { sc_mont(r, a, b); }
+
+// Scalar::from_bytes_mod_order_wide: 512-bit little-endian value mod l
+SC_INLINE void sc_from_wide(sc &r, const uint32_t w[16]) {
+    sc lo, hi, k, a, b;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        lo.v[i] = w[i];
+        hi.v[i] = w[8 + i];
+    }
+    sc_const(k, SC_R);
+    sc_mont(a, lo, k);   // lo * R / R = lo mod l
+    sc_const(k, SC_R2);
+    sc_mont(b, hi, k);   // hi * R^2 / R = hi * 2^256 mod l
+    sc_add(r, a, b);
+}
+// any 256-bit value -> canonical (Scalar::from_bytes_mod_order)
+SC_INLINE void sc_reduce256(sc &r, const sc &a) {
+    sc k;
+    sc_const(k, SC_R);
+    sc_mont(r, a, k);
+}
+
+// r = a^(l-2) mod l (standard form in and out); 0 -> 0.  Scalar::invert (circuit_lib.rs:273-275).
+__device__ __noinline__ void sc_invert(sc &r, const sc &a) {
+    // l - 2, little-endian limbs
+    const uint32_t e[8] = {0x5cf5d3ebu, 0x5812631au, 0xa2f79cd6u, 0x14def9deu, 0u, 0u, 0u, 0x10000000u};
+    sc am, acc;
+    sc_to_mont(am, a);
+    sc_const(acc, SC_R);  // 1 in Montgomery form
+#pragma unroll 1
+    for (int bit = 252; bit >= 0; bit--) {
+        sc_mont_noinline(acc, acc, acc);
+        if ((e[bit >> 5] >> (bit & 31)) & 1u) sc_mont_noinline(acc, acc, am);
+    }
+    sc_from_mont(r, acc);
+}

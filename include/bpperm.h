@@ -100,6 +100,38 @@ int bpp_points_sum_compress_dev(bpp_ctx *ctx, const void *d_partials, size_t g, 
 /* Override the Pippenger window width (0 = automatic). */
 int bpp_set_window_bits(bpp_ctx *ctx, int c);
 
+/* ---- scalar-vector operators mod l: the reference's util.rs / poly.rs -------------------------------
+ * All vectors are arrays of 32-byte little-endian canonical scalars in host memory.  Where the Rust
+ * function panics on a dimension mismatch (util.rs:9-11,26-28,44-46,86-88) the call returns
+ * BPP_ERR_LENGTH_MISMATCH. */
+/* util.rs:84-94  inner_product(a, b) */
+int bpp_inner_product(bpp_ctx *ctx, const uint8_t *a, size_t len_a, const uint8_t *b, size_t len_b, uint8_t out[32]);
+/* util.rs:6-20  hadamard_V(a, b) */
+int bpp_hadamard_V(bpp_ctx *ctx, const uint8_t *a, size_t len_a, const uint8_t *b, size_t len_b, uint8_t *out);
+/* util.rs:22-38  vm_mult(a, b): out[i] = <a, b[i]>; b is rows x cols row-major, a has cols entries */
+int bpp_vm_mult(bpp_ctx *ctx, const uint8_t *a, size_t len_a, const uint8_t *b, size_t rows, size_t cols, uint8_t *out);
+/* util.rs:40-56  mv_mult(a, b): out[j] = sum_i a[i][j] * b[i]; a is rows x cols, b has rows entries */
+int bpp_mv_mult(bpp_ctx *ctx, const uint8_t *a, size_t rows, size_t cols, const uint8_t *b, size_t len_b, uint8_t *out);
+/* util.rs:63-65,139-157  exp_iter(x).take(count), exactly as coded: x^F(i) = x, x, x^2, x^3, x^5, ... */
+int bpp_exp_iter(bpp_ctx *ctx, const uint8_t x[32], size_t count, uint8_t *out);
+/* the standard powers x^first, x^(first+1), ... (what exp_iter is meant to produce; used by the IPA mode) */
+int bpp_scalar_powers(bpp_ctx *ctx, const uint8_t x[32], size_t first, size_t count, uint8_t *out);
+/* util.rs:67-82  scalar_exp(x, pow) */
+int bpp_scalar_exp(bpp_ctx *ctx, const uint8_t x[32], uint32_t pow, uint8_t out[32]);
+/* circuit_lib.rs:273-275  y_n.iter().map(|k| k.invert()) */
+int bpp_scalar_invert(bpp_ctx *ctx, const uint8_t *a, size_t n, uint8_t *out);
+/* transcript_protocol.rs:62-67 / Scalar::random: Scalar::from_bytes_mod_order_wide over n x 64 bytes */
+int bpp_scalar_from_wide(bpp_ctx *ctx, const uint8_t *in64, size_t n, uint8_t *out);
+/* traits.rs:7-17  reduce_scalars: Scalar::reduce over n x 32 bytes */
+int bpp_scalar_reduce(bpp_ctx *ctx, const uint8_t *in32, size_t n, uint8_t *out);
+/* poly.rs:39-55  VecPoly3::special_inner_product(lhs, rhs) -> Poly6 {t1..t6}; lhs/rhs are 4 x n */
+int bpp_vecpoly3_special_inner_product(bpp_ctx *ctx, const uint8_t *lhs, const uint8_t *rhs, size_t n,
+                                       uint8_t out_t1_t6[192]);
+/* poly.rs:57-76  VecPoly3::eval / eval_ref */
+int bpp_vecpoly3_eval(bpp_ctx *ctx, const uint8_t *coeffs, size_t n, const uint8_t x[32], uint8_t *out);
+/* poly.rs:14-18  Poly6::eval */
+int bpp_poly6_eval(bpp_ctx *ctx, const uint8_t t1_t6[192], const uint8_t x[32], uint8_t out[32]);
+
 /* ---- measurement helpers --------------------------------------------------------------------- */
 /* IMAD.WIDE.U32 peak microbenchmark: returns wide multiply-adds per second over all SMs. */
 int bpp_bench_imad_peak(bpp_ctx *ctx, int iters, double *ops_per_sec, double *ms);
