@@ -21,6 +21,10 @@ SYMBOLS = [
     "bpp_inner_product", "bpp_hadamard_V", "bpp_vm_mult", "bpp_mv_mult", "bpp_exp_iter", "bpp_scalar_powers",
     "bpp_scalar_exp", "bpp_scalar_invert", "bpp_scalar_from_wide", "bpp_scalar_reduce",
     "bpp_vecpoly3_special_inner_product", "bpp_vecpoly3_eval", "bpp_poly6_eval",
+    "bpp_circuit_create", "bpp_circuit_free", "bpp_gens_create", "bpp_gens_free", "bpp_acproof_proof_len",
+    "bpp_acproof_prove_batch", "bpp_acproof_verify_batch", "bpp_acp_batch_create", "bpp_acp_batch_free",
+    "bpp_acp_batch_upload_witness", "bpp_acp_batch_commit", "bpp_acp_batch_prove", "bpp_acp_batch_download_proofs",
+    "bpp_acp_batch_upload_proofs", "bpp_acp_batch_verify", "bpp_acp_batch_download_accept",
 ]
 
 _lib = None
@@ -87,5 +91,26 @@ def load() -> ctypes.CDLL:
     lib.bpp_vecpoly3_special_inner_product.argtypes = [vp, u8p, u8p, sz, c.c_char_p]
     lib.bpp_vecpoly3_eval.argtypes = [vp, u8p, sz, u8p, c.c_char_p]
     lib.bpp_poly6_eval.argtypes = [vp, u8p, u8p, c.c_char_p]
+    u32p = c.POINTER(c.c_uint32)
+    lib.bpp_circuit_create.argtypes = [vp, sz, sz, sz, u32p, u32p, u32p, u8p, u8p, c.POINTER(vp)]
+    lib.bpp_circuit_free.argtypes = [vp, vp]
+    lib.bpp_circuit_free.restype = None
+    lib.bpp_gens_create.argtypes = [vp, u8p, u8p, u8p, u8p, sz, c.c_int, c.POINTER(vp)]
+    lib.bpp_gens_free.argtypes = [vp, vp]
+    lib.bpp_gens_free.restype = None
+    lib.bpp_acproof_proof_len.argtypes = [sz]
+    lib.bpp_acproof_proof_len.restype = sz
+    lib.bpp_acproof_prove_batch.argtypes = [vp, vp, vp, c.c_int, sz, u8p, u8p, u8p, u8p, u8p, u8p, sz, c.c_char_p]
+    lib.bpp_acproof_verify_batch.argtypes = [vp, vp, vp, c.c_int, sz, u8p, u8p, u8p, sz, u8p, c.c_char_p]
+    lib.bpp_acp_batch_create.argtypes = [vp, vp, vp, c.c_int, sz, u8p, sz, c.POINTER(vp)]
+    lib.bpp_acp_batch_free.argtypes = [vp]
+    lib.bpp_acp_batch_free.restype = None
+    lib.bpp_acp_batch_upload_witness.argtypes = [vp, u8p, u8p, u8p, u8p, u8p]
+    lib.bpp_acp_batch_commit.argtypes = [vp, u8p, c.c_char_p]
+    lib.bpp_acp_batch_prove.argtypes = [vp]
+    lib.bpp_acp_batch_download_proofs.argtypes = [vp, c.c_char_p]
+    lib.bpp_acp_batch_upload_proofs.argtypes = [vp, u8p, u8p]
+    lib.bpp_acp_batch_verify.argtypes = [vp, u8p]
+    lib.bpp_acp_batch_download_accept.argtypes = [vp, c.c_char_p]
     _lib = lib
     return lib

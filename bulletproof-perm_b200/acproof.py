@@ -1,0 +1,142 @@
+"""Host-side mirror of the reference's ACProof module (circuit_lib.rs) on the CUDA backend.
+
+`Circuit` + `Generators` are ACEssentials (circuit_lib.rs:58-74); a `Batch` carries `count` ACProver
+states (a_L, a_R, a_O, gamma: circuit_lib.rs:76-81) through the reference's seven steps at once.
+Scalars are ints or 32-byte little-endian bytes; points are 32-byte compressed encodings.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Sequence
+
+from .backend import Backend, scalars_to_bytes
+
+MODE_REFERENCE, MODE_REFERENCE_FIXED = 0, 1
+_MODES = {"reference": 0, "reference-fixed": 1, 0: 0, 1: 1}
+
+
+def _sc32(x) -> bytes:
+    return x.to_bytes(32, "little") if isinstance(x, int) else bytes(x)
+
+
+class Circuit:
+    """W_L, W_R, W_O (n x Q), W_V (m x Q) as (wire, constraint, coeff) triples and c (Q)."""
+
+    def __init__(self, backend: Backend, n: int, Q: int, m: int, WL, WR, WO, WV, c_vec):
+        self.be, self.n, self.Q, self.m = backend, n, Q, m
+        mats = [list(WL), list(WR), list(WO), list(WV)]
+        nnz = (ctypes.c_uint32 * 4)(*[len(t) for t in mats])
+        flat = [t for mat in mats for t in mat]
+        N = max(len(flat), 1)
+        wire = (ctypes.c_uint32 * N)(*[t[0] for t in flat])
+        cons = (ctypes.c_uint32 * N)(*[t[1] for t in flat])
+        coeff = b"".join(_sc32(t[2]) for t in flat) or bytes(32)
+        if len(c_vec) != Q:
+            raise ValueError("c_vec must have Q entries")
+        h = ctypes.c_void_p()
+        backend._check(backend._lib.bpp_circuit_create(backend._ctx, n, Q, m, nnz, wire, cons, coeff,
+                                                        scalars_to_bytes(c_vec), ctypes.byref(h)))
+        self._h = h
+
+    @classmethod
+    def from_dense(cls, backend, W_L, W_R, W_O, W_V, c_vec):
+        """From the reference's dense matrices (rows = wires, columns = constraints)."""
+        def trip(M):
+            return [(i, q, v) for i, row in enumerate(M) for q, v in enumerate(row) if v]
+        return cls(backend, len(W_L), len(W_L[0]), len(W_V), trip(W_L), trip(W_R), trip(W_O), trip(W_V), c_vec)
+
+    def free(self):
+        if self._h:
+            self.be._lib.bpp_circuit_free(self.be._ctx, self._h)
+            self._h = None
+
+
+class Generators:
+    """g_base, h_base, G_vec, H_vec + their fixed-base window tables on the device."""
+
+    def __init__(self, backend: Backend, g: bytes, h: bytes, G: Sequence[bytes], H: Sequence[bytes], window_bits: int = 0):
+        if len(G) != len(H):
+            raise ValueError("G_vec and H_vec must have the same length (circuit_lib.rs:154)")
+        self.be, self.n = backend, len(G)
+        hnd = ctypes.c_void_p()
+        backend._check(backend._lib.bpp_gens_create(backend._ctx, g, h, b"".join(G), b"".join(H), len(G), window_bits,
+                                                     ctypes.byref(hnd)))
+        self._h = hnd
+
+    def free(self):
+        if self._h:
+            self.be._lib.bpp_gens_free(self.be._ctx, self._h)
+            self._h = None
+
+
+def proof_len(n: int) -> int:
+    return 32 * (11 + 2 * n)
+
+
+class Batch:
+    """`count` proofs in lock-step; buffers stay on the device between calls."""
+
+    def __init__(self, backend: Backend, circuit: Circuit, gens: Generators, count: int, mode="reference-fixed",
+                 label: bytes = b"test"):
+        self.be, self.cir, self.gens, self.count, self.mode = backend, circuit, gens, count, _MODES[mode]
+        h = ctypes.c_void_p()
+        backend._check(backend._lib.bpp_acp_batch_create(backend._ctx, circuit._h, gens._h, self.mode, count, label,
+                                                          len(label), ctypes.byref(h)))
+        self._h = h
+        self.proof_len = proof_len(circuit.n)
+
+    def upload_witness(self, aL: bytes, aR: bytes, aO: bytes, gamma: bytes, seeds: bytes):
+        n, m, B = self.cir.n, self.cir.m, self.count
+        if not (len(aL) == len(aR) == len(aO) == 32 * n * B and len(gamma) == 32 * m * B and len(seeds) == 32 * B):
+            raise ValueError("witness shape mismatch (circuit_lib.rs:160-167 assert_eq!)")
+        self.be._check(self.be._lib.bpp_acp_batch_upload_witness(self._h, aL, aR, aO, gamma, seeds))
+
+    def commit(self, v: bytes, want: bool = True) -> bytes:
+        out = ctypes.create_string_buffer(32 * self.cir.m * self.count) if want else None
+        self.be._check(self.be._lib.bpp_acp_batch_commit(self._h, v, out))
+        return out.raw if want else b""
+
+    def prove(self):
+        self.be._check(self.be._lib.bpp_acp_batch_prove(self._h))
+
+    def download_proofs(self) -> bytes:
+        out = ctypes.create_string_buffer(self.proof_len * self.count)
+        self.be._check(self.be._lib.bpp_acp_batch_download_proofs(self._h, out))
+        return out.raw
+
+    def upload_proofs(self, proofs: bytes, V: bytes = None):
+        self.be._check(self.be._lib.bpp_acp_batch_upload_proofs(self._h, proofs, V))
+
+    def verify(self, verifier_seed: bytes = bytes(32)):
+        self.be._check(self.be._lib.bpp_acp_batch_verify(self._h, verifier_seed))
+
+    def download_accept(self) -> bytes:
+        out = ctypes.create_string_buffer(self.count)
+        self.be._check(self.be._lib.bpp_acp_batch_download_accept(self._h, out))
+        return out.raw
+
+    def free(self):
+        if self._h:
+            self.be._lib.bpp_acp_batch_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def prove_batch(backend, circuit, gens, aL, aR, aO, gamma, seeds, count, mode="reference-fixed", label=b"test") -> bytes:
+    out = ctypes.create_string_buffer(proof_len(circuit.n) * count)
+    backend._check(backend._lib.bpp_acproof_prove_batch(backend._ctx, circuit._h, gens._h, _MODES[mode], count, aL, aR, aO,
+                                                         gamma, seeds, label, len(label), out))
+    return out.raw
+
+
+def verify_batch(backend, circuit, gens, proofs, V, count, mode="reference-fixed", label=b"test",
+                 verifier_seed=bytes(32)) -> bytes:
+    out = ctypes.create_string_buffer(count)
+    backend._check(backend._lib.bpp_acproof_verify_batch(backend._ctx, circuit._h, gens._h, _MODES[mode], count, proofs, V,
+                                                          label, len(label), verifier_seed, out))
+    return out.raw

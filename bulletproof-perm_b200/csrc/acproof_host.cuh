@@ -1,0 +1,580 @@
+// acproof_host.cuh - host driver + C ABI of the batched shuffle prover / verifier.
+// Included by bpperm_capi.cu.  The driver re-expresses the seven-step state machine of
+// /root/reference/bp-perm/src/circuit_lib.rs (call order lib.rs:219-231) for B proofs in lock-step:
+// one kernel launch per protocol step for the whole batch, Fiat-Shamir transcripts on host threads.
+#pragma once
+#include <thread>
+
+#include "acproof_kernels.cuh"
+#include "host_merlin.hpp"
+
+struct bpp_circuit {
+    uint32_t n = 0, Q = 0, m = 0, rows = 0, nnz = 0;
+    uint32_t *d_rowptr = nullptr, *d_col = nullptr, *d_coeff = nullptr;
+    uint8_t *d_kind = nullptr;
+};
+
+struct bpp_gens {
+    uint32_t n = 0, n_gens = 0;  // gens order: g, h, G[0..n), H[0..n)
+    int c = 8, Wn = 32;
+    uint32_t *d_niels = nullptr, *d_table = nullptr;
+    fb_consts kc;
+};
+
+struct bpp_acp_batch {
+    bpp_ctx *ctx = nullptr;
+    const bpp_circuit *cir = nullptr;
+    const bpp_gens *gens = nullptr;
+    int mode = 1;
+    uint32_t B = 0, proof_len = 0;
+    acp_layout lay;
+    std::vector<uint8_t> label;
+    uint32_t *d_blk = nullptr, *d_seeds = nullptr, *d_wide = nullptr, *d_ext8 = nullptr, *d_dyn = nullptr,
+             *d_wsum = nullptr, *d_stat = nullptr, *d_bad = nullptr, *d_vext = nullptr, *d_vseed = nullptr;
+    uint8_t *d_pts8 = nullptr, *d_proofs = nullptr, *d_V = nullptr, *d_accept = nullptr;
+    uint8_t *h_pts8 = nullptr, *h_wide = nullptr, *h_proofs = nullptr;  // pinned
+    std::vector<bpp_host::Transcript> tr;
+};
+
+static acp_layout acp_make_layout(uint32_t n, uint32_t Q, uint32_t m) {
+    acp_layout L;
+    uint32_t o = 0;
+    auto take = [&](uint32_t cnt) { uint32_t r = o; o += cnt; return r; };
+    L.n = n; L.Q = Q; L.m = m;
+    L.aL = take(n); L.aR = take(n); L.aO = take(n); L.gamma = take(m);
+    L.alpha = take(1); L.beta = take(1); L.ro = take(1); L.sl = take(n); L.sr = take(n); L.tau = take(5);
+    L.y = take(1); L.z = take(1); L.x = take(1); L.w = take(1);
+    L.yn = take(n); L.yninv = take(n); L.zq = take(Q);
+    L.zWL = take(n); L.zWR = take(n); L.zWO = take(n); L.zWV = take(m); L.zc = take(1);
+    L.lin = take(n); L.l1 = take(n); L.r0 = take(n); L.r1 = take(n); L.r3 = take(n);
+    L.dots = take(12); L.sigma = L.dots + 9;
+    L.tc = take(6); L.tsel = take(5);
+    L.l = take(n); L.r = take(n); L.that = take(1); L.taux = take(1); L.mu = take(1);
+    L.vg = take(1); L.vh = take(1); L.vG = take(n); L.vH = take(n); L.vd = take(m + 8);
+    L.stride = (o + 3) & ~3u;
+    return L;
+}
+
+// ---- circuit --------------------------------------------------------------------------------------
+// Weights arrive as (wire, constraint, coefficient) triples of the four matrices concatenated in the
+// order W_L, W_R, W_O, W_V - the sparse form of the reference's dense n x Q / m x Q matrices
+// (ACEssentials, circuit_lib.rs:58-74; shapes SURVEY A.1) - plus the dense constant vector c (Q).
+extern "C" int bpp_circuit_create(bpp_ctx *ctx, size_t n, size_t Q, size_t m, const uint32_t nnz[4], const uint32_t *wire,
+                                  const uint32_t *constraint, const uint8_t *coeff, const uint8_t *c_vec,
+                                  bpp_circuit **out) {
+    if (!ctx || !out || !nnz || n == 0 || Q == 0 || m == 0 || !c_vec) return BPP_ERR_INVALID_ARG;
+    *out = nullptr;
+    CK(ctx, cudaSetDevice(ctx->device));
+    const uint32_t rows = (uint32_t)(3 * n + m + 1);
+    const uint32_t row_base[4] = {0, (uint32_t)n, (uint32_t)(2 * n), (uint32_t)(3 * n)};
+    const uint32_t row_cnt[4] = {(uint32_t)n, (uint32_t)n, (uint32_t)n, (uint32_t)m};
+    size_t total = 0;
+    for (int k = 0; k < 4; k++) total += nnz[k];
+    if (total && (!wire || !constraint || !coeff)) return BPP_ERR_INVALID_ARG;
+    static const uint8_t ONE[32] = {1};
+    static const uint8_t MINUS_ONE[32] = {0xec, 0xd3, 0xf5, 0x5c, 0x1a, 0x63, 0x12, 0x58, 0xd6, 0x9c, 0xf7, 0xa2, 0xde, 0xf9, 0xde, 0x14,
+                                          0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0x10};
+    std::vector<uint32_t> rowptr(rows + 1, 0);
+    size_t e = 0;
+    for (int k = 0; k < 4; k++)
+        for (uint32_t i = 0; i < nnz[k]; i++, e++) {
+            if (wire[e] >= row_cnt[k] || constraint[e] >= Q) return BPP_ERR_INVALID_ARG;
+            rowptr[row_base[k] + wire[e] + 1]++;
+        }
+    size_t c_nnz = 0;
+    for (size_t q = 0; q < Q; q++) {
+        bool nz = false;
+        for (int b = 0; b < 32; b++) nz |= c_vec[32 * q + b] != 0;
+        if (nz) c_nnz++;
+    }
+    rowptr[rows] = (uint32_t)c_nnz;
+    for (uint32_t r = 0; r < rows; r++) rowptr[r + 1] += rowptr[r];
+    const size_t all = total + c_nnz;
+    std::vector<uint32_t> col(all ? all : 1), cf((all ? all : 1) * 8, 0), fill(rowptr.begin(), rowptr.end() - 1);
+    std::vector<uint8_t> kind(all ? all : 1);
+    auto put = [&](uint32_t row, uint32_t q, const uint8_t *v) {
+        uint32_t pos = fill[row]++;
+        col[pos] = q;
+        kind[pos] = memcmp(v, ONE, 32) == 0 ? 1 : memcmp(v, MINUS_ONE, 32) == 0 ? 2 : 0;
+        memcpy(&cf[8 * (size_t)pos], v, 32);
+    };
+    e = 0;
+    for (int k = 0; k < 4; k++)
+        for (uint32_t i = 0; i < nnz[k]; i++, e++) put(row_base[k] + wire[e], constraint[e], coeff + 32 * e);
+    for (size_t q = 0; q < Q; q++) {
+        bool nz = false;
+        for (int b = 0; b < 32; b++) nz |= c_vec[32 * q + b] != 0;
+        if (nz) put(rows - 1, (uint32_t)q, c_vec + 32 * q);
+    }
+    bpp_circuit *c = new bpp_circuit();
+    c->n = (uint32_t)n; c->Q = (uint32_t)Q; c->m = (uint32_t)m; c->rows = rows; c->nnz = (uint32_t)all;
+    cudaError_t err = cudaMalloc((void **)&c->d_rowptr, (rows + 1) * 4);
+    if (err == cudaSuccess) err = cudaMalloc((void **)&c->d_col, col.size() * 4);
+    if (err == cudaSuccess) err = cudaMalloc((void **)&c->d_coeff, cf.size() * 4);
+    if (err == cudaSuccess) err = cudaMalloc((void **)&c->d_kind, kind.size());
+    if (err == cudaSuccess) err = cudaMemcpy(c->d_rowptr, rowptr.data(), (rows + 1) * 4, cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) err = cudaMemcpy(c->d_col, col.data(), col.size() * 4, cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) err = cudaMemcpy(c->d_coeff, cf.data(), cf.size() * 4, cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) err = cudaMemcpy(c->d_kind, kind.data(), kind.size(), cudaMemcpyHostToDevice);
+    if (err != cudaSuccess) {
+        ctx->last_error = cudaGetErrorString(err);
+        delete c;
+        return BPP_ERR_CUDA;
+    }
+    *out = c;
+    return BPP_OK;
+}
+extern "C" void bpp_circuit_free(bpp_ctx *ctx, bpp_circuit *c) {
+    if (!c) return;
+    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    cudaFree(c->d_rowptr); cudaFree(c->d_col); cudaFree(c->d_coeff); cudaFree(c->d_kind);
+    delete c;
+}
+
+// ---- generators + fixed-base tables ---------------------------------------------------------------
+// g_base, h_base, G_vec, H_vec of ACEssentials (circuit_lib.rs:58-65) as compressed points.
+extern "C" int bpp_gens_create(bpp_ctx *ctx, const uint8_t g[32], const uint8_t h[32], const uint8_t *G, const uint8_t *H,
+                               size_t n, int window_bits, bpp_gens **out) {
+    if (!ctx || !out || !g || !h || !G || !H || n == 0) return BPP_ERR_INVALID_ARG;
+    if (window_bits == 0) window_bits = 8;
+    if (window_bits < 4 || window_bits > 16) return BPP_ERR_INVALID_ARG;
+    *out = nullptr;
+    std::vector<uint8_t> all(32 * (2 * n + 2));
+    memcpy(&all[0], g, 32);
+    memcpy(&all[32], h, 32);
+    memcpy(&all[64], G, 32 * n);
+    memcpy(&all[64 + 32 * n], H, 32 * n);
+    bpp_points *pts = nullptr;
+    int rc = bpp_points_upload(ctx, BPP_FMT_COMPRESSED, all.data(), 2 * n + 2, &pts);
+    if (rc) return rc;
+    bpp_gens *gs = new bpp_gens();
+    gs->n = (uint32_t)n;
+    gs->n_gens = (uint32_t)(2 * n + 2);
+    gs->c = window_bits;
+    gs->Wn = (256 + window_bits - 1) / window_bits;
+    gs->d_niels = pts->niels;
+    pts->niels = nullptr;
+    bpp_points_free(ctx, pts);
+    // K = sum_{w < Wn-1} 2^(c w + c - 1)
+    memset(&gs->kc, 0, sizeof(gs->kc));
+    for (int w = 0; w < gs->Wn - 1; w++) {
+        int bit = gs->c * w + gs->c - 1;
+        gs->kc.K[bit >> 5] |= 1u << (bit & 31);
+    }
+    const size_t half = (size_t)1 << (gs->c - 1);
+    const size_t entries = (size_t)gs->n_gens * gs->Wn * half;
+    if (cudaMalloc((void **)&gs->d_table, entries * 96) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(gs->d_niels);
+        delete gs;
+        return BPP_ERR_OOM;
+    }
+    const uint32_t threads = gs->n_gens * gs->Wn;
+    k_fb_build<<<(threads + 63) / 64, 64, 0, ctx->stream>>>(gs->d_niels, gs->n_gens, gs->c, gs->Wn, gs->d_table);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        ctx->last_error = cudaGetErrorString(e);
+        cudaFree(gs->d_niels);
+        cudaFree(gs->d_table);
+        delete gs;
+        return BPP_ERR_CUDA;
+    }
+    *out = gs;
+    return BPP_OK;
+}
+extern "C" void bpp_gens_free(bpp_ctx *ctx, bpp_gens *g) {
+    if (!g) return;
+    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    cudaFree(g->d_niels);
+    cudaFree(g->d_table);
+    delete g;
+}
+
+// ---- batch object ----------------------------------------------------------------------------------
+extern "C" size_t bpp_acproof_proof_len(size_t n) { return 32 * (11 + 2 * n); }
+
+extern "C" void bpp_acp_batch_free(bpp_acp_batch *b) {
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
+    void *dev[] = {b->d_blk, b->d_seeds, b->d_wide, b->d_ext8, b->d_dyn, b->d_wsum, b->d_stat, b->d_bad, b->d_vext, b->d_vseed,
+                   b->d_pts8, b->d_proofs, b->d_V, b->d_accept};
+    for (void *p : dev)
+        if (p) cudaFree(p);
+    if (b->h_pts8) cudaFreeHost(b->h_pts8);
+    if (b->h_wide) cudaFreeHost(b->h_wide);
+    if (b->h_proofs) cudaFreeHost(b->h_proofs);
+    delete b;
+}
+
+// mode 0 = "reference" (bit-for-bit what circuit_lib.rs does, defects included; verification never
+// accepts), mode 1 = "reference-fixed" (SURVEY A.3).  label = the Transcript::new label (lib.rs:172: b"test").
+extern "C" int bpp_acp_batch_create(bpp_ctx *ctx, const bpp_circuit *cir, const bpp_gens *gens, int mode, size_t count,
+                                    const uint8_t *label, size_t label_len, bpp_acp_batch **out) {
+    if (!ctx || !cir || !gens || !out || count == 0 || count > (1u << 24) || (mode != 0 && mode != 1) ||
+        (!label && label_len))
+        return BPP_ERR_INVALID_ARG;
+    if (gens->n != cir->n) return BPP_ERR_LENGTH_MISMATCH;  // circuit_lib.rs:154-160 assert_eq!
+    *out = nullptr;
+    CK(ctx, cudaSetDevice(ctx->device));
+    bpp_acp_batch *b = new bpp_acp_batch();
+    b->ctx = ctx; b->cir = cir; b->gens = gens; b->mode = mode; b->B = (uint32_t)count;
+    b->lay = acp_make_layout(cir->n, cir->Q, cir->m);
+    b->proof_len = (uint32_t)bpp_acproof_proof_len(cir->n);
+    b->label.assign(label, label + label_len);
+    const size_t B = count, per = cir->m + 8;
+    cudaError_t e = cudaMalloc((void **)&b->d_blk, B * b->lay.stride * 32);
+    if (e == cudaSuccess) e = cudaMemsetAsync(b->d_blk, 0, B * b->lay.stride * 32, ctx->stream);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_seeds, B * 32);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_wide, B * 3 * 64);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_ext8, B * 8 * 128);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_dyn, B * per * 96);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_wsum, B * DYN_W * 128);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_stat, B * 128);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_bad, B * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_vseed, 64);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_pts8, B * 8 * 32);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_proofs, B * b->proof_len);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_V, B * cir->m * 32);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_vext, B * cir->m * 128);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_accept, B);
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&b->h_pts8, B * 8 * 32);
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&b->h_wide, B * 3 * 64);
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&b->h_proofs, B * b->proof_len);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_dyn_window_sums, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_W * 8 * 128);
+    if (e != cudaSuccess) {
+        ctx->last_error = cudaGetErrorString(e);
+        bool oom = e == cudaErrorMemoryAllocation;
+        cudaGetLastError();
+        bpp_acp_batch_free(b);
+        return oom ? BPP_ERR_OOM : BPP_ERR_CUDA;
+    }
+    *out = b;
+    return BPP_OK;
+}
+
+template <typename F>
+static void acp_parallel_for(uint32_t n, F fn) {
+    unsigned T = std::thread::hardware_concurrency();
+    if (T == 0) T = 4;
+    if (T > 32) T = 32;
+    if (n < 64 || T == 1) { for (uint32_t i = 0; i < n; i++) fn(i); return; }
+    std::vector<std::thread> th;
+    uint32_t per = (n + T - 1) / T;
+    for (unsigned t = 0; t < T; t++) {
+        uint32_t lo = t * per, hi = lo + per < n ? lo + per : n;
+        if (lo >= hi) break;
+        th.emplace_back([=]() { for (uint32_t i = lo; i < hi; i++) fn(i); });
+    }
+    for (auto &x : th) x.join();
+}
+
+static fb_shape acp_shape(uint32_t outs) {
+    fb_shape s;
+    memset(&s, 0, sizeof(s));
+    s.outs = outs;
+    return s;
+}
+static void acp_seg(fb_shape &s, uint32_t off, uint32_t ostride, uint32_t gen, uint32_t cnt) {
+    s.sc_off[s.nseg] = off; s.sc_ostride[s.nseg] = ostride; s.gen[s.nseg] = gen; s.cnt[s.nseg] = cnt;
+    s.nseg++;
+}
+// launches the fixed-base MSM; results land in dst[(p * pitch + o)] (raw extended points)
+static int acp_fb(bpp_acp_batch *b, const fb_shape &sh, uint32_t *dst, uint32_t pitch) {
+    bpp_ctx *ctx = b->ctx;
+    fb_shape s = sh;
+    s.outs = pitch;  // k_fb_msm addresses out_ext + 32 * (p * outs + o)
+    k_fb_msm<<<dim3(b->B, sh.outs), FB_THREADS, 0, ctx->stream>>>(b->d_blk, b->lay, s, b->gens->d_table, b->gens->c,
+                                                                  b->gens->Wn, b->gens->kc, dst);
+    LAUNCH_CHECK(ctx);
+    return BPP_OK;
+}
+
+__global__ void __launch_bounds__(128) k_compress_strided(const uint32_t *__restrict__ ext, uint32_t pitch, uint32_t first,
+                                                          uint32_t cnt, uint32_t B, uint8_t *__restrict__ out32) {
+    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= B * cnt) return;
+    uint32_t p = id / cnt, k = first + (id - p * cnt);
+    ge_ext pt;
+    ge_load(pt, ext + 32 * ((size_t)p * pitch + k));
+    ge_compress(out32 + 32 * ((size_t)p * pitch + k), pt);
+}
+
+// per-proof verifier weights: Scalar::random from ChaCha20(verifier_seed), block p (mode 1); 0 in mode 0
+__global__ void k_acp_weights(const uint32_t *__restrict__ seed8, acp_layout lay, uint32_t B, int mode,
+                              uint32_t *__restrict__ blk) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    sc r;
+    sc_set0(r);
+    if (mode != 0) {
+        uint32_t s[16], x[16];
+        s[0] = 0x61707865u; s[1] = 0x3320646eu; s[2] = 0x79622d32u; s[3] = 0x6b206574u;
+        for (int i = 0; i < 8; i++) s[4 + i] = seed8[i];
+        s[12] = p; s[13] = 0; s[14] = 0; s[15] = 0;
+        for (int i = 0; i < 16; i++) x[i] = s[i];
+        for (int rd = 0; rd < 10; rd++) {
+            CHACHA_QR(x[0], x[4], x[8], x[12]) CHACHA_QR(x[1], x[5], x[9], x[13])
+            CHACHA_QR(x[2], x[6], x[10], x[14]) CHACHA_QR(x[3], x[7], x[11], x[15])
+            CHACHA_QR(x[0], x[5], x[10], x[15]) CHACHA_QR(x[1], x[6], x[11], x[12])
+            CHACHA_QR(x[2], x[7], x[8], x[13]) CHACHA_QR(x[3], x[4], x[9], x[14])
+        }
+        for (int i = 0; i < 16; i++) x[i] += s[i];
+        sc_from_wide(r, x);
+    }
+    sc_store(ACP_PTR(blk, lay, p, lay.w), r);
+}
+
+// witness: a_L, a_R, a_O (count x n), gamma (count x m), prover RNG seeds (count x 32)
+extern "C" int bpp_acp_batch_upload_witness(bpp_acp_batch *b, const uint8_t *aL, const uint8_t *aR, const uint8_t *aO,
+                                            const uint8_t *gamma, const uint8_t *seeds) {
+    if (!b || !aL || !aR || !aO || !gamma || !seeds) return BPP_ERR_INVALID_ARG;
+    bpp_ctx *ctx = b->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    const size_t pitch = (size_t)b->lay.stride * 32, n32 = (size_t)b->lay.n * 32, m32 = (size_t)b->lay.m * 32;
+    uint8_t *base = (uint8_t *)b->d_blk;
+    CK(ctx, cudaMemcpy2DAsync(base + 32 * (size_t)b->lay.aL, pitch, aL, n32, n32, b->B, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaMemcpy2DAsync(base + 32 * (size_t)b->lay.aR, pitch, aR, n32, n32, b->B, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaMemcpy2DAsync(base + 32 * (size_t)b->lay.aO, pitch, aO, n32, n32, b->B, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaMemcpy2DAsync(base + 32 * (size_t)b->lay.gamma, pitch, gamma, m32, m32, b->B, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(b->d_seeds, seeds, (size_t)b->B * 32, cudaMemcpyHostToDevice, ctx->stream));
+    return BPP_OK;
+}
+
+// commit_variables (weights.rs:58-61): V_j = v_j * g + gamma_j * h for the uploaded gamma; the compressed
+// commitments are returned (count x m x 32) and also stay resident as this batch's V.
+extern "C" int bpp_acp_batch_commit(bpp_acp_batch *b, const uint8_t *v, uint8_t *V_out) {
+    if (!b || !v) return BPP_ERR_INVALID_ARG;
+    bpp_ctx *ctx = b->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    const acp_layout &L = b->lay;
+    // v is staged in the (not yet used) zWV..; use vd area? keep it simple: stage into the l/r area (2n >= m)
+    if (2 * L.n < L.m) return BPP_ERR_INVALID_ARG;
+    const size_t pitch = (size_t)L.stride * 32, m32 = (size_t)L.m * 32;
+    CK(ctx, cudaMemcpy2DAsync((uint8_t *)b->d_blk + 32 * (size_t)L.l, pitch, v, m32, m32, b->B, cudaMemcpyHostToDevice, ctx->stream));
+    fb_shape sh = acp_shape(L.m);
+    acp_seg(sh, L.l, 1, 0, 1);
+    acp_seg(sh, L.gamma, 1, 1, 1);
+    int rc = acp_fb(b, sh, b->d_vext, L.m);
+    if (rc) return rc;
+    k_compress_strided<<<(b->B * L.m + 127) / 128, 128, 0, ctx->stream>>>(b->d_vext, L.m, 0, L.m, b->B, b->d_V);
+    LAUNCH_CHECK(ctx);
+    if (V_out) CK(ctx, cudaMemcpyAsync(V_out, b->d_V, (size_t)b->B * L.m * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return BPP_OK;
+}
+
+static int acp_put_challenges(bpp_acp_batch *b, uint32_t off, uint32_t per) {
+    bpp_ctx *ctx = b->ctx;
+    CK(ctx, cudaMemcpyAsync(b->d_wide, b->h_wide, (size_t)b->B * per * 64, cudaMemcpyHostToDevice, ctx->stream));
+    k_acp_put_wide<<<(b->B * per + 127) / 128, 128, 0, ctx->stream>>>(b->d_wide, b->lay, off, per, b->B, b->d_blk);
+    LAUNCH_CHECK(ctx);
+    return BPP_OK;
+}
+
+static int acp_challenge_dependent_scalars(bpp_acp_batch *b) {
+    bpp_ctx *ctx = b->ctx;
+    const acp_layout &L = b->lay;
+    k_acp_pow<<<(b->B + 63) / 64, 64, 0, ctx->stream>>>(L, b->B, b->d_blk);
+    LAUNCH_CHECK(ctx);
+    acp_csr W{b->cir->d_rowptr, b->cir->d_col, b->cir->d_kind, b->cir->d_coeff, b->cir->rows};
+    k_acp_csr<<<dim3((W.rows + 127) / 128, b->B), 128, 0, ctx->stream>>>(W, L, b->d_blk);
+    LAUNCH_CHECK(ctx);
+    k_acp_vec1<<<dim3((L.n + 127) / 128, b->B), 128, 0, ctx->stream>>>(L, b->d_blk);
+    LAUNCH_CHECK(ctx);
+    return BPP_OK;
+}
+
+// Prover: witness resident -> proofs resident (b->d_proofs).  Steps and labels follow lib.rs:219-228.
+extern "C" int bpp_acp_batch_prove(bpp_acp_batch *b) {
+    if (!b) return BPP_ERR_INVALID_ARG;
+    bpp_ctx *ctx = b->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    const acp_layout &L = b->lay;
+    const uint32_t B = b->B, n = L.n;
+    cudaStream_t s = ctx->stream;
+    int rc;
+    // create(): randomness alpha,beta,ro,s_l,s_r (+ the five tau drawn later from the same stream)
+    const uint32_t nrand = 3 + 2 * n + 5;
+    k_acp_rng<<<dim3((nrand + 127) / 128, B), 128, 0, s>>>(b->d_seeds, L, nrand, b->d_blk);
+    LAUNCH_CHECK(ctx);
+    {   // A_I = alpha*h + <a_L,G> + <a_R,H>; A_O = beta*h + <a_O,G>; S = ro*h + <s_l,G> + <s_r,H>
+        fb_shape sh = acp_shape(1);
+        acp_seg(sh, L.alpha, 0, 1, 1); acp_seg(sh, L.aL, 0, 2, n); acp_seg(sh, L.aR, 0, 2 + n, n);
+        if ((rc = acp_fb(b, sh, b->d_ext8 + 0, 8))) return rc;
+        sh = acp_shape(1);
+        acp_seg(sh, L.beta, 0, 1, 1); acp_seg(sh, L.aO, 0, 2, n);
+        if ((rc = acp_fb(b, sh, b->d_ext8 + 32, 8))) return rc;
+        sh = acp_shape(1);
+        acp_seg(sh, L.ro, 0, 1, 1); acp_seg(sh, L.sl, 0, 2, n); acp_seg(sh, L.sr, 0, 2 + n, n);
+        if ((rc = acp_fb(b, sh, b->d_ext8 + 64, 8))) return rc;
+    }
+    k_compress_strided<<<(B * 3 + 127) / 128, 128, 0, s>>>(b->d_ext8, 8, 0, 3, B, b->d_pts8);
+    LAUNCH_CHECK(ctx);
+    CK(ctx, cudaMemcpyAsync(b->h_pts8, b->d_pts8, (size_t)B * 256, cudaMemcpyDeviceToHost, s));
+    CK(ctx, cudaStreamSynchronize(s));
+    // transcripts: dom-sep, A_I, A_O, S -> y, z
+    b->tr.clear();
+    b->tr.reserve(B);
+    for (uint32_t p = 0; p < B; p++) b->tr.emplace_back(b->label.data(), b->label.size());
+    acp_parallel_for(B, [&](uint32_t p) {
+        bpp_host::Transcript &t = b->tr[p];
+        const uint8_t *pt = b->h_pts8 + 256 * (size_t)p;
+        t.arithmetic_domain_sep(n);
+        t.append_point("A_I", pt);
+        t.append_point("A_O", pt + 32);
+        t.append_point("S", pt + 64);
+        t.challenge_wide("y", b->h_wide + 128 * (size_t)p);
+        t.challenge_wide("z", b->h_wide + 128 * (size_t)p + 64);
+    });
+    if ((rc = acp_put_challenges(b, L.y, 2))) return rc;
+    if ((rc = acp_challenge_dependent_scalars(b))) return rc;
+    k_acp_dots<<<dim3(10, B), 128, 0, s>>>(L, 0, b->d_blk);
+    LAUNCH_CHECK(ctx);
+    k_acp_tcoef<<<(B + 63) / 64, 64, 0, s>>>(L, B, b->mode, b->d_blk);
+    LAUNCH_CHECK(ctx);
+    {   // T_i = t_i*g + tau_i*h for i in (1,3,4,5,6)
+        fb_shape sh = acp_shape(5);
+        acp_seg(sh, L.tsel, 1, 0, 1); acp_seg(sh, L.tau, 1, 1, 1);
+        if ((rc = acp_fb(b, sh, b->d_ext8 + 96, 8))) return rc;
+    }
+    k_compress_strided<<<(B * 5 + 127) / 128, 128, 0, s>>>(b->d_ext8, 8, 3, 5, B, b->d_pts8);
+    LAUNCH_CHECK(ctx);
+    CK(ctx, cudaMemcpyAsync(b->h_pts8, b->d_pts8, (size_t)B * 256, cudaMemcpyDeviceToHost, s));
+    CK(ctx, cudaStreamSynchronize(s));
+    const int mode = b->mode;
+    acp_parallel_for(B, [&](uint32_t p) {
+        bpp_host::Transcript &t = b->tr[p];
+        const uint8_t *pt = b->h_pts8 + 256 * (size_t)p + 96;
+        t.append_point("T1", pt);
+        t.append_point("T3", pt + 32);
+        t.append_point("T4", mode == 0 ? pt + 32 : pt + 64);  // circuit_lib.rs:391 appends T_3 under "T4"
+        t.append_point("T5", pt + 96);
+        t.append_point("T6", pt + 128);
+        t.challenge_wide("x", b->h_wide + 64 * (size_t)p);
+    });
+    if ((rc = acp_put_challenges(b, L.x, 1))) return rc;
+    k_acp_final<<<dim3((n + 127) / 128, B), 128, 0, s>>>(L, b->d_blk);
+    LAUNCH_CHECK(ctx);
+    k_acp_dots<<<dim3(2, B), 128, 0, s>>>(L, 10, b->d_blk);
+    LAUNCH_CHECK(ctx);
+    k_acp_final2<<<(B + 63) / 64, 64, 0, s>>>(L, B, b->mode, b->d_blk);
+    LAUNCH_CHECK(ctx);
+    k_acp_pack<<<dim3((b->proof_len / 32 + 127) / 128, B), 128, 0, s>>>(L, B, b->d_pts8, b->d_blk, b->d_proofs, b->proof_len);
+    LAUNCH_CHECK(ctx);
+    return BPP_OK;
+}
+
+extern "C" int bpp_acp_batch_download_proofs(bpp_acp_batch *b, uint8_t *proofs_out) {
+    if (!b || !proofs_out) return BPP_ERR_INVALID_ARG;
+    bpp_ctx *ctx = b->ctx;
+    CK(ctx, cudaMemcpyAsync(proofs_out, b->d_proofs, (size_t)b->B * b->proof_len, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return BPP_OK;
+}
+
+// proofs (count x proof_len) and commitments V (count x m x 32, compressed); V may be NULL to keep the
+// resident commitments of bpp_acp_batch_commit
+extern "C" int bpp_acp_batch_upload_proofs(bpp_acp_batch *b, const uint8_t *proofs, const uint8_t *V) {
+    if (!b || !proofs) return BPP_ERR_INVALID_ARG;
+    bpp_ctx *ctx = b->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaMemcpyAsync(b->d_proofs, proofs, (size_t)b->B * b->proof_len, cudaMemcpyHostToDevice, ctx->stream));
+    if (V) CK(ctx, cudaMemcpyAsync(b->d_V, V, (size_t)b->B * b->lay.m * 32, cudaMemcpyHostToDevice, ctx->stream));
+    return BPP_OK;
+}
+
+// Verifier: proofs + V resident -> accept bytes resident.  Replays the transcript (A_I,A_O,S -> y,z;
+// T's -> x), recomputes the challenge-dependent scalars and evaluates the checks of
+// circuit_lib.rs:518 (t == <l,r>), :541 and (mode 1) :577-582 as one MSM per proof.
+extern "C" int bpp_acp_batch_verify(bpp_acp_batch *b, const uint8_t verifier_seed[32]) {
+    if (!b || !verifier_seed) return BPP_ERR_INVALID_ARG;
+    bpp_ctx *ctx = b->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    const acp_layout &L = b->lay;
+    const uint32_t B = b->B, n = L.n, m = L.m, per = m + 8;
+    cudaStream_t s = ctx->stream;
+    int rc;
+    k_acp_unpack<<<dim3((b->proof_len / 32 + 127) / 128, B), 128, 0, s>>>(L, B, b->d_proofs, b->proof_len, b->d_blk, b->d_pts8);
+    LAUNCH_CHECK(ctx);
+    CK(ctx, cudaMemcpyAsync(b->h_pts8, b->d_pts8, (size_t)B * 256, cudaMemcpyDeviceToHost, s));
+    CK(ctx, cudaMemcpyAsync(b->d_vseed, verifier_seed, 32, cudaMemcpyHostToDevice, s));
+    CK(ctx, cudaStreamSynchronize(s));
+    const int mode = b->mode;
+    const std::vector<uint8_t> &label = b->label;
+    acp_parallel_for(B, [&](uint32_t p) {
+        bpp_host::Transcript t(label.data(), label.size());
+        const uint8_t *pt = b->h_pts8 + 256 * (size_t)p;
+        t.arithmetic_domain_sep(n);
+        t.append_point("A_I", pt);
+        t.append_point("A_O", pt + 32);
+        t.append_point("S", pt + 64);
+        t.challenge_wide("y", b->h_wide + 192 * (size_t)p);
+        t.challenge_wide("z", b->h_wide + 192 * (size_t)p + 64);
+        t.append_point("T1", pt + 96);
+        t.append_point("T3", pt + 128);
+        t.append_point("T4", mode == 0 ? pt + 128 : pt + 160);
+        t.append_point("T5", pt + 192);
+        t.append_point("T6", pt + 224);
+        t.challenge_wide("x", b->h_wide + 192 * (size_t)p + 128);
+    });
+    if ((rc = acp_put_challenges(b, L.y, 3))) return rc;
+    k_acp_weights<<<(B + 127) / 128, 128, 0, s>>>(b->d_vseed, L, B, mode, b->d_blk);
+    LAUNCH_CHECK(ctx);
+    if ((rc = acp_challenge_dependent_scalars(b))) return rc;
+    k_acp_dots<<<dim3(2, B), 128, 0, s>>>(L, 9, b->d_blk);  // sigma, <l, r>
+    LAUNCH_CHECK(ctx);
+    CK(ctx, cudaMemsetAsync(b->d_bad, 0, (size_t)B * 4, s));
+    k_acp_decompress<<<(B * per + 127) / 128, 128, 0, s>>>(b->d_V, b->d_pts8, m, B, b->d_dyn, b->d_bad);
+    LAUNCH_CHECK(ctx);
+    k_acp_vscal<<<dim3((n + m + 1 + 127) / 128, B), 128, 0, s>>>(L, b->d_blk);
+    LAUNCH_CHECK(ctx);
+    {
+        fb_shape sh = acp_shape(1);
+        acp_seg(sh, L.vg, 0, 0, 2 * n + 2);
+        if ((rc = acp_fb(b, sh, b->d_stat, 1))) return rc;
+    }
+    k_dyn_window_sums<<<B, DYN_W, DYN_W * 8 * 128, s>>>(b->d_blk, L, b->d_dyn, per, b->d_wsum);
+    LAUNCH_CHECK(ctx);
+    k_dyn_horner_accept<<<(B + 63) / 64, 64, 0, s>>>(L, B, b->d_blk, b->d_wsum, b->d_stat, b->d_bad, b->d_accept);
+    LAUNCH_CHECK(ctx);
+    return BPP_OK;
+}
+
+extern "C" int bpp_acp_batch_download_accept(bpp_acp_batch *b, uint8_t *accept) {
+    if (!b || !accept) return BPP_ERR_INVALID_ARG;
+    bpp_ctx *ctx = b->ctx;
+    CK(ctx, cudaMemcpyAsync(accept, b->d_accept, b->B, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return BPP_OK;
+}
+
+// ---- one-call host forms (what a drop-in for create..blinding_values / verify binds) -------------------
+extern "C" int bpp_acproof_prove_batch(bpp_ctx *ctx, const bpp_circuit *cir, const bpp_gens *gens, int mode, size_t count,
+                                       const uint8_t *aL, const uint8_t *aR, const uint8_t *aO, const uint8_t *gamma,
+                                       const uint8_t *seeds, const uint8_t *label, size_t label_len, uint8_t *proofs_out) {
+    bpp_acp_batch *b = nullptr;
+    int rc = bpp_acp_batch_create(ctx, cir, gens, mode, count, label, label_len, &b);
+    if (rc) return rc;
+    rc = bpp_acp_batch_upload_witness(b, aL, aR, aO, gamma, seeds);
+    if (!rc) rc = bpp_acp_batch_prove(b);
+    if (!rc) rc = bpp_acp_batch_download_proofs(b, proofs_out);
+    bpp_acp_batch_free(b);
+    return rc;
+}
+
+extern "C" int bpp_acproof_verify_batch(bpp_ctx *ctx, const bpp_circuit *cir, const bpp_gens *gens, int mode, size_t count,
+                                        const uint8_t *proofs, const uint8_t *V, const uint8_t *label, size_t label_len,
+                                        const uint8_t verifier_seed[32], uint8_t *accept) {
+    if (!V) return BPP_ERR_INVALID_ARG;
+    bpp_acp_batch *b = nullptr;
+    int rc = bpp_acp_batch_create(ctx, cir, gens, mode, count, label, label_len, &b);
+    if (rc) return rc;
+    rc = bpp_acp_batch_upload_proofs(b, proofs, V);
+    if (!rc) rc = bpp_acp_batch_verify(b, verifier_seed);
+    if (!rc) rc = bpp_acp_batch_download_accept(b, accept);
+    bpp_acp_batch_free(b);
+    return rc;
+}

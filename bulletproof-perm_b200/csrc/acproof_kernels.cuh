@@ -1,0 +1,675 @@
+// acproof_kernels.cuh - batched arithmetic-circuit (shuffle) prover / verifier kernels for sm_100a.
+//
+// Re-expresses the arithmetic of /root/reference/bp-perm/src/circuit_lib.rs for a batch of B
+// independent proofs that share one circuit and one set of generators:
+//   create                  :139-253   A_I, A_O, S commitments          -> k_acp_rng, k_fb_msm, k_compress_batch
+//   compute_per_challenges  :256-302   y^n, y^-n, z^Q, z*W, l_in, sigma -> k_acp_pow, k_acp_csr, k_acp_vec1, k_acp_dots
+//   commit_Ts               :304-423   l(X), r(X), t(X), T_i            -> k_acp_vec1, k_acp_dots, k_acp_tcoef, k_fb_msm
+//   blinding_values         :434-476   l, r, t, tau_x, mu               -> k_acp_final, k_acp_dots2, k_acp_final2
+//   verify                  :478-585   the three checks, fused into one MSM per proof
+//                                      -> k_acp_vscal, k_fb_msm, k_dyn_window_sums, k_dyn_horner_accept
+// Each proof owns one block of scalars in HBM (layout below); a kernel touches element (proof, i) from
+// one thread, so all loads are 32-byte contiguous per thread and coalesced across the warp.
+#pragma once
+#include "ge25519.cuh"
+#include "vec_kernels.cuh"
+
+struct acp_layout {
+    uint32_t n, Q, m, stride;  // stride: scalars per proof
+    uint32_t aL, aR, aO, gamma;                    // witness (uploaded)
+    uint32_t alpha, beta, ro, sl, sr, tau;         // prover randomness, RNG draw order (contiguous)
+    uint32_t y, z, x, w;                           // challenges, verifier weight
+    uint32_t yn, yninv, zq;                        // exp_iter outputs and inverses
+    uint32_t zWL, zWR, zWO, zWV, zc;               // z*W_L, z*W_R, z*W_O (n each), z*W_V (m), <z_q,c> (contiguous)
+    uint32_t lin, l1, r0, r1, r3;                  // vector polynomial coefficients
+    uint32_t dots;                                 // 12 block-reduced dot products
+    uint32_t tc, tsel, sigma;                      // t1..t6, the five committed values, delta(y,z)
+    uint32_t l, r, that, taux, mu;                 // proof scalars
+    uint32_t vg, vh, vG, vH, vd;                   // verifier MSM scalars: static (contiguous g,h,G,H), dynamic (m+8)
+};
+
+#define ACP_PTR(base, lay, p, off) ((base) + 8 * ((size_t)(p) * (lay).stride + (off)))
+
+// ---- RNG: ChaCha20 keystream block j of the proof's stream -> Scalar::random -----------------------
+// rand_chacha::ChaCha20Rng::from_seed(seed): key = seed, 64-bit block counter, zero nonce; each
+// Scalar::random consumes exactly one 64-byte block (circuit_lib.rs:180-182,213-214,361-404).
+SC_INLINE uint32_t rotl32(uint32_t v, int n) { return (v << n) | (v >> (32 - n)); }
+#define CHACHA_QR(a, b, c, d) \
+    a += b; d = rotl32(d ^ a, 16); c += d; b = rotl32(b ^ c, 12); a += b; d = rotl32(d ^ a, 8); c += d; b = rotl32(b ^ c, 7);
+
+__global__ void k_acp_rng(const uint32_t *__restrict__ seeds /* B x 8 */, acp_layout lay, uint32_t count,
+                          uint32_t *__restrict__ blk) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
+    if (j >= count) return;
+    uint32_t s[16], x[16];
+    s[0] = 0x61707865u; s[1] = 0x3320646eu; s[2] = 0x79622d32u; s[3] = 0x6b206574u;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s[4 + i] = seeds[8 * (size_t)p + i];
+    s[12] = j; s[13] = 0; s[14] = 0; s[15] = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) x[i] = s[i];
+#pragma unroll 1
+    for (int r = 0; r < 10; r++) {
+        CHACHA_QR(x[0], x[4], x[8], x[12]) CHACHA_QR(x[1], x[5], x[9], x[13])
+        CHACHA_QR(x[2], x[6], x[10], x[14]) CHACHA_QR(x[3], x[7], x[11], x[15])
+        CHACHA_QR(x[0], x[5], x[10], x[15]) CHACHA_QR(x[1], x[6], x[11], x[12])
+        CHACHA_QR(x[2], x[7], x[8], x[13]) CHACHA_QR(x[3], x[4], x[9], x[14])
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i++) x[i] += s[i];
+    sc r;
+    sc_from_wide(r, x);
+    sc_store(ACP_PTR(blk, lay, p, lay.alpha + j), r);
+}
+
+// wide challenge bytes (64 B each, from the host transcripts) -> scalars at a layout offset
+__global__ void k_acp_put_wide(const uint32_t *__restrict__ wide /* B x per x 16 */, acp_layout lay, uint32_t off,
+                               uint32_t per, uint32_t B, uint32_t *__restrict__ blk) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * per) return;
+    uint32_t p = i / per, k = i - p * per;
+    uint32_t w[16];
+#pragma unroll
+    for (int t = 0; t < 16; t++) w[t] = wide[16 * (size_t)i + t];
+    sc r;
+    sc_from_wide(r, w);
+    sc_store(ACP_PTR(blk, lay, p, off + k), r);
+}
+
+// ---- fixed-base tables ---------------------------------------------------------------------------
+// table[((gen * Wn + w) * half + (j - 1))] = j * 2^(c w) * P_gen as affine Niels (96 B).
+// Thread per (gen, window): 2^(c w) P by doublings, then j = 1..half by repeated addition, each
+// entry normalised with its own inversion (one-time cost at generator upload).
+__global__ void __launch_bounds__(64) k_fb_build(const uint32_t *__restrict__ gens_niels, uint32_t n_gens, int c,
+                                                 int Wn, uint32_t *__restrict__ table) {
+    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n_gens * (uint32_t)Wn) return;
+    const uint32_t gen = id / Wn, w = id - gen * Wn;
+    const uint32_t half = 1u << (c - 1);
+    ge_niels q;
+    ge_niels_load(q, gens_niels + 24 * (size_t)gen);
+    ge_ext base, run;
+    ge_identity(base);
+    ge_madd(base, base, q, false);
+#pragma unroll 1
+    for (uint32_t i = 0; i < w * (uint32_t)c; i++) ge_double_noinline(base, base);
+    run = base;
+    uint32_t *dst = table + 24 * ((size_t)id * half);
+#pragma unroll 1
+    for (uint32_t j = 1; j <= half; j++) {
+        fe zi, x, y;
+        fe_invert(zi, run.Z);
+        fe_mul_noinline(x, run.X, zi);
+        fe_mul_noinline(y, run.Y, zi);
+        ge_niels e;
+        ge_affine_to_niels(e, x, y);
+        ge_niels_store(dst + 24 * (size_t)(j - 1), e);
+        if (j < half) ge_add_noinline(run, run, base);
+    }
+}
+
+// ---- batched fixed-base MSM ----------------------------------------------------------------------
+// One block per output point.  The MSM's terms are up to 4 segments of (scalar range in the proof
+// block) x (generator range); every term costs Wn table look-ups + mixed adds, no doublings and no
+// buckets.  Signed digits without a carry chain: s' = s + sum_{w < Wn-1} half*2^(cw), digit_w =
+// window_w(s') - half (top window unsigned), so any (term, window) can be evaluated independently.
+struct fb_shape {
+    uint32_t nseg;
+    uint32_t sc_off[4];      // scalar offset of the segment inside the proof block
+    uint32_t sc_ostride[4];  // added per output index (blockIdx.y)
+    uint32_t gen[4];         // first generator of the segment
+    uint32_t cnt[4];
+    uint32_t outs;           // outputs per proof (gridDim.y)
+};
+struct fb_consts {
+    uint32_t K[8];  // sum_{w < Wn-1} half * 2^(c w)
+};
+#define FB_THREADS 128
+#define FB_GROUP 4  // windows handled per work item
+
+__global__ void __launch_bounds__(FB_THREADS) k_fb_msm(const uint32_t *__restrict__ blk, acp_layout lay, fb_shape sh,
+                                                       const uint32_t *__restrict__ table, int c, int Wn, fb_consts kc,
+                                                       uint32_t *__restrict__ out_ext /* [p][outs] x 32 */) {
+    __shared__ __align__(16) uint32_t red[FB_THREADS][32];
+    const uint32_t p = blockIdx.x, o = blockIdx.y;
+    const uint32_t half = 1u << (c - 1), mask = (1u << c) - 1u;
+    const uint32_t groups = (Wn + FB_GROUP - 1) / FB_GROUP;
+    uint32_t total_terms = 0;
+    for (uint32_t s = 0; s < sh.nseg; s++) total_terms += sh.cnt[s];
+    const uint32_t items = total_terms * groups;
+    ge_ext acc;
+    ge_identity(acc);
+#pragma unroll 1
+    for (uint32_t it = threadIdx.x; it < items; it += FB_THREADS) {
+        uint32_t term = it / groups, grp = it - term * groups;
+        uint32_t seg = 0, k = term;
+        while (seg + 1 < sh.nseg && k >= sh.cnt[seg]) { k -= sh.cnt[seg]; seg++; }
+        const uint32_t *sp = ACP_PTR(blk, lay, p, sh.sc_off[seg] + o * sh.sc_ostride[seg] + k);
+        const uint32_t gen = sh.gen[seg] + k;
+        // s' = s + K
+        uint32_t s[9];
+        {
+            uint4 lo = *reinterpret_cast<const uint4 *>(sp), hi = *reinterpret_cast<const uint4 *>(sp + 4);
+            s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w; s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
+            s[8] = 0;
+            unsigned long long carry = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                carry += (unsigned long long)s[i] + kc.K[i];
+                s[i] = (uint32_t)carry;
+                carry >>= 32;
+            }
+            s[8] = (uint32_t)carry;
+        }
+#pragma unroll 1
+        for (uint32_t w = grp * FB_GROUP; w < min((uint32_t)Wn, (grp + 1) * FB_GROUP); w++) {
+            int bit = c * (int)w, limb = bit >> 5, shf = bit & 31;
+            unsigned long long v = s[limb];
+            if (limb + 1 < 9) v |= (unsigned long long)s[limb + 1] << 32;
+            uint32_t u = (uint32_t)(v >> shf) & mask;
+            int d = (w + 1 == (uint32_t)Wn) ? (int)u : (int)u - (int)half;
+            if (d == 0) continue;
+            uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+            ge_niels q;
+            ge_niels_load(q, table + 24 * (((size_t)gen * Wn + w) * half + (mag - 1)));
+            ge_madd(acc, acc, q, d < 0);
+        }
+    }
+    // block tree reduction
+    ge_store(&red[threadIdx.x][0], acc);
+    __syncthreads();
+#pragma unroll 1
+    for (uint32_t dstep = FB_THREADS / 2; dstep >= 1; dstep >>= 1) {
+        if (threadIdx.x < dstep) {
+            ge_ext a, b;
+            ge_load(a, &red[threadIdx.x][0]);
+            ge_load(b, &red[threadIdx.x + dstep][0]);
+            ge_add(a, a, b);
+            ge_store(&red[threadIdx.x][0], a);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 32) {
+        uint32_t *dst = out_ext + 32 * ((size_t)p * sh.outs + o);
+        dst[threadIdx.x] = red[0][threadIdx.x];
+    }
+}
+
+// thread per point: ext (raw limbs) -> 32-byte encoding
+__global__ void __launch_bounds__(128) k_compress_batch(const uint32_t *__restrict__ ext, uint32_t n,
+                                                        uint8_t *__restrict__ out32) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ge_ext p;
+    ge_load(p, ext + 32 * (size_t)i);
+    ge_compress(out32 + 32 * (size_t)i, p);
+}
+
+// ---- per-challenge scalars -------------------------------------------------------------------------
+// Thread per proof: y_n = exp_iter(y) (n), z_q = exp_iter(z) (Q) with the reference's Fibonacci
+// recurrence (util.rs:139-157), y_n_inv by Montgomery's trick (one inversion instead of the reference's
+// n: circuit_lib.rs:273-275; identical results).  All chains stay in Montgomery form.
+__global__ void __launch_bounds__(64) k_acp_pow(acp_layout lay, uint32_t B, uint32_t *__restrict__ blk) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    sc one_m;
+    sc_const(one_m, SC_R);
+    for (int which = 0; which < 2; which++) {
+        const uint32_t cnt = which ? lay.Q : lay.n;
+        uint32_t *dst = ACP_PTR(blk, lay, p, which ? lay.zq : lay.yn);
+        sc base = one_m, nxt, ret, s;
+        sc_load(nxt, ACP_PTR(blk, lay, p, which ? lay.z : lay.y));
+        sc_to_mont(nxt, nxt);
+#pragma unroll 1
+        for (uint32_t i = 0; i < cnt; i++) {
+            ret = nxt;
+            sc_mont_noinline(nxt, nxt, base);
+            base = ret;
+            sc_from_mont(s, ret);
+            sc_store(dst + 8 * (size_t)i, s);
+        }
+    }
+    // batch inversion of y_n -> y_n_inv (prefix products kept in the output array)
+    uint32_t *yn = ACP_PTR(blk, lay, p, lay.yn), *yi = ACP_PTR(blk, lay, p, lay.yninv);
+    sc acc = one_m, v;
+    bool any_zero = false;
+#pragma unroll 1
+    for (uint32_t i = 0; i < lay.n; i++) {
+        sc_store(yi + 8 * (size_t)i, acc);  // prefix product of elements < i (Montgomery form)
+        sc_load(v, yn + 8 * (size_t)i);
+        any_zero = any_zero || sc_is_zero(v);
+        sc_to_mont(v, v);
+        sc_mont_noinline(acc, acc, v);
+    }
+    if (any_zero) {  // only when y = 0: dalek's invert(0) = 0
+        sc z;
+        sc_set0(z);
+        for (uint32_t i = 0; i < lay.n; i++) sc_store(yi + 8 * (size_t)i, z);
+        return;
+    }
+    sc inv;
+    sc_from_mont(v, acc);
+    sc_invert(inv, v);
+    sc_to_mont(inv, inv);  // Montgomery form of (prod all)^-1
+#pragma unroll 1
+    for (int i = (int)lay.n - 1; i >= 0; i--) {
+        sc pre, r, e;
+        sc_load(pre, yi + 8 * (size_t)i);
+        sc_mont_noinline(r, inv, pre);     // inverse of element i (Montgomery form)
+        sc_load(e, yn + 8 * (size_t)i);
+        sc_to_mont(e, e);
+        sc_mont_noinline(inv, inv, e);
+        sc_from_mont(r, r);
+        sc_store(yi + 8 * (size_t)i, r);
+    }
+}
+
+// CSR weights.  Row r of the concatenation [W_L (n) | W_R (n) | W_O (n) | W_V (m) | c (1)] holds
+// (constraint q, coefficient) pairs; out[r] = sum coeff * z_q[q]  (vm_mult(z_q, W) of util.rs:22-38
+// without the dense zero entries; <z_q, c> for the last row).  kind: 1 = +1, 2 = -1, 0 = general.
+struct acp_csr {
+    const uint32_t *rowptr;   // rows + 1
+    const uint32_t *col;      // nnz
+    const uint8_t *kind;      // nnz
+    const uint32_t *coeff;    // nnz x 8 (used when kind == 0)
+    uint32_t rows;
+};
+__global__ void __launch_bounds__(128) k_acp_csr(acp_csr W, acp_layout lay, uint32_t *__restrict__ blk) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
+    if (r >= W.rows) return;
+    const uint32_t *zq = ACP_PTR(blk, lay, p, lay.zq);
+    sc acc, z, t, cf;
+    sc_set0(acc);
+    for (uint32_t e = W.rowptr[r]; e < W.rowptr[r + 1]; e++) {
+        sc_load(z, zq + 8 * (size_t)W.col[e]);
+        uint8_t k = W.kind[e];
+        if (k == 1) sc_add(acc, acc, z);
+        else if (k == 2) sc_sub(acc, acc, z);
+        else {
+            sc_load(cf, W.coeff + 8 * (size_t)e);
+            sc_mul(t, cf, z);
+            sc_add(acc, acc, t);
+        }
+    }
+    sc_store(ACP_PTR(blk, lay, p, lay.zWL + r), acc);
+}
+
+// thread per (proof, i < n): l_in, l1, r0, r1, r3 (circuit_lib.rs:286,313-339)
+__global__ void __launch_bounds__(128) k_acp_vec1(acp_layout lay, uint32_t *__restrict__ blk) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
+    if (i >= lay.n) return;
+    sc yn, yi, zwl, zwr, zwo, al, ar, srv, lin, t;
+    sc_load(yn, ACP_PTR(blk, lay, p, lay.yn + i));
+    sc_load(yi, ACP_PTR(blk, lay, p, lay.yninv + i));
+    sc_load(zwl, ACP_PTR(blk, lay, p, lay.zWL + i));
+    sc_load(zwr, ACP_PTR(blk, lay, p, lay.zWR + i));
+    sc_load(zwo, ACP_PTR(blk, lay, p, lay.zWO + i));
+    sc_load(al, ACP_PTR(blk, lay, p, lay.aL + i));
+    sc_load(ar, ACP_PTR(blk, lay, p, lay.aR + i));
+    sc_load(srv, ACP_PTR(blk, lay, p, lay.sr + i));
+    sc_mul(lin, yi, zwr);
+    sc_store(ACP_PTR(blk, lay, p, lay.lin + i), lin);
+    sc_add(t, al, lin);
+    sc_store(ACP_PTR(blk, lay, p, lay.l1 + i), t);
+    sc_sub(t, zwo, yn);
+    sc_store(ACP_PTR(blk, lay, p, lay.r0 + i), t);
+    sc_mul(t, yn, ar);
+    sc_add(t, t, zwl);
+    sc_store(ACP_PTR(blk, lay, p, lay.r1 + i), t);
+    sc_mul(t, yn, srv);
+    sc_store(ACP_PTR(blk, lay, p, lay.r3 + i), t);
+}
+
+// block per (proof, k): dots[k] = <u_k, v_k> over n (k < 10) - the nine products of
+// VecPoly3::special_inner_product (poly.rs:39-55; l2 = a_O, l3 = s_l) and sigma = <l_in, z*W_L> (:291).
+// second stage (k = 10, 11): t_hat = <l, r> (n) and <z*W_V, gamma> (m) for blinding_values (:444,452).
+__global__ void __launch_bounds__(128) k_acp_dots(acp_layout lay, uint32_t first, uint32_t *__restrict__ blk) {
+    __shared__ __align__(16) uint32_t sh[32 * 8];
+    const uint32_t k = first + blockIdx.x, p = blockIdx.y;
+    uint32_t ua, vb, len = lay.n;
+    switch (k) {
+        case 0: ua = lay.l1; vb = lay.r0; break;
+        case 1: ua = lay.l1; vb = lay.r1; break;
+        case 2: ua = lay.aO; vb = lay.r0; break;
+        case 3: ua = lay.aO; vb = lay.r1; break;
+        case 4: ua = lay.sl; vb = lay.r0; break;
+        case 5: ua = lay.l1; vb = lay.r3; break;
+        case 6: ua = lay.sl; vb = lay.r1; break;
+        case 7: ua = lay.aO; vb = lay.r3; break;
+        case 8: ua = lay.sl; vb = lay.r3; break;
+        case 9: ua = lay.lin; vb = lay.zWL; break;
+        case 10: ua = lay.l; vb = lay.r; break;
+        default: ua = lay.zWV; vb = lay.gamma; len = lay.m; break;
+    }
+    sc acc, tot, r2;
+    dot_partial(acc, ACP_PTR(blk, lay, p, ua), 1, ACP_PTR(blk, lay, p, vb), 1, len);
+    block_sum_sc(tot, acc, sh);
+    if (threadIdx.x == 0) {
+        sc_const(r2, SC_R2);
+        sc_mont(tot, tot, r2);
+        sc_store(ACP_PTR(blk, lay, p, lay.dots + k), tot);
+    }
+}
+
+// thread per proof: t1..t6, sigma, and the five values committed in T_1,T_3,T_4,T_5,T_6:
+// mode 0 ("reference", circuit_lib.rs:362-406): t(X) evaluated at the integers 1,3,4,5,6;
+// mode 1 ("reference-fixed"): the coefficients t_1,t_3,t_4,t_5,t_6.
+__global__ void __launch_bounds__(64) k_acp_tcoef(acp_layout lay, uint32_t B, int mode, uint32_t *__restrict__ blk) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    sc d[10], t[6];
+    for (int k = 0; k < 10; k++) sc_load(d[k], ACP_PTR(blk, lay, p, lay.dots + k));
+    t[0] = d[0];
+    sc_add(t[1], d[1], d[2]);
+    sc_add(t[2], d[3], d[4]);
+    sc_add(t[3], d[5], d[6]);
+    t[4] = d[7];
+    t[5] = d[8];
+    for (int k = 0; k < 6; k++) sc_store(ACP_PTR(blk, lay, p, lay.tc + k), t[k]);
+    sc_store(ACP_PTR(blk, lay, p, lay.sigma), d[9]);
+    const int deg[5] = {1, 3, 4, 5, 6};
+    for (int k = 0; k < 5; k++) {
+        sc v;
+        if (mode == 0) {  // Poly6::eval(deg)
+            sc xx, acc;
+            sc_set_u32(xx, (uint32_t)deg[k]);
+            acc = t[5];
+            for (int j = 4; j >= 0; j--) {
+                sc_mul_noinline(acc, xx, acc);
+                sc_add(acc, acc, t[j]);
+            }
+            sc_mul_noinline(v, xx, acc);
+        } else {
+            v = t[deg[k] - 1];
+        }
+        sc_store(ACP_PTR(blk, lay, p, lay.tsel + k), v);
+    }
+}
+
+// thread per (proof, i): l = l(x), r = r(x)  (poly.rs:67-76 with l0 = 0, r2 = 0)
+__global__ void __launch_bounds__(128) k_acp_final(acp_layout lay, uint32_t *__restrict__ blk) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
+    if (i >= lay.n) return;
+    sc x, a, b, c, t;
+    sc_load(x, ACP_PTR(blk, lay, p, lay.x));
+    sc_load(a, ACP_PTR(blk, lay, p, lay.l1 + i));
+    sc_load(b, ACP_PTR(blk, lay, p, lay.aO + i));
+    sc_load(c, ACP_PTR(blk, lay, p, lay.sl + i));
+    sc_mul(t, x, c);
+    sc_add(t, t, b);
+    sc_mul(t, x, t);
+    sc_add(t, t, a);
+    sc_mul(t, x, t);
+    sc_store(ACP_PTR(blk, lay, p, lay.l + i), t);
+    sc_load(a, ACP_PTR(blk, lay, p, lay.r0 + i));
+    sc_load(b, ACP_PTR(blk, lay, p, lay.r1 + i));
+    sc_load(c, ACP_PTR(blk, lay, p, lay.r3 + i));
+    sc_mul(t, x, c);        // x*r3
+    sc_mul(t, x, t);        // x^2*r3 (+ r2 = 0)
+    sc_add(t, t, b);
+    sc_mul(t, x, t);
+    sc_add(t, t, a);
+    sc_store(ACP_PTR(blk, lay, p, lay.r + i), t);
+}
+
+// thread per proof: t_hat, tau_x, mu (circuit_lib.rs:444-462).  mode 0 adds the x^2<z_q, W_V gamma> term
+// five times like the reference (:452-456), mode 1 once.
+__global__ void __launch_bounds__(64) k_acp_final2(acp_layout lay, uint32_t B, int mode, uint32_t *__restrict__ blk) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    sc x, xp[7], t, acc, wvg, v;
+    sc_load(x, ACP_PTR(blk, lay, p, lay.x));
+    sc_set_u32(xp[0], 1);
+    for (int k = 1; k <= 6; k++) sc_mul_noinline(xp[k], xp[k - 1], x);
+    sc_load(v, ACP_PTR(blk, lay, p, lay.dots + 10));
+    sc_store(ACP_PTR(blk, lay, p, lay.that), v);
+    sc_load(wvg, ACP_PTR(blk, lay, p, lay.dots + 11));
+    sc_mul_noinline(wvg, wvg, xp[2]);
+    const int deg[5] = {1, 3, 4, 5, 6};
+    sc_set0(acc);
+    for (int k = 0; k < 5; k++) {
+        sc_load(v, ACP_PTR(blk, lay, p, lay.tau + k));
+        sc_mul_noinline(t, v, xp[deg[k]]);
+        sc_add(acc, acc, t);
+        if (mode == 0) sc_add(acc, acc, wvg);
+    }
+    if (mode != 0) sc_add(acc, acc, wvg);
+    sc_store(ACP_PTR(blk, lay, p, lay.taux), acc);
+    sc_set0(acc);
+    for (int k = 0; k < 3; k++) {  // mu = alpha x + beta x^2 + ro x^3 (alpha, beta, ro contiguous)
+        sc_load(v, ACP_PTR(blk, lay, p, lay.alpha + k));
+        sc_mul_noinline(t, v, xp[k + 1]);
+        sc_add(acc, acc, t);
+    }
+    sc_store(ACP_PTR(blk, lay, p, lay.mu), acc);
+}
+
+// ---- proof (de)serialisation: A_I,A_O,S,T1,T3,T4,T5,T6 | tau_x, mu, t | l[n] | r[n] ------------------
+__global__ void k_acp_pack(acp_layout lay, uint32_t B, const uint8_t *__restrict__ pts8 /* B x 8 x 32 */,
+                           const uint32_t *__restrict__ blk, uint8_t *__restrict__ out, uint32_t proof_len) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;  // i: 32-byte word of the proof
+    const uint32_t words = proof_len / 32;
+    if (i >= words) return;
+    uint4 lo, hi;
+    if (i < 8) {
+        const uint4 *s = reinterpret_cast<const uint4 *>(pts8 + 32 * ((size_t)p * 8 + i));
+        lo = s[0]; hi = s[1];
+    } else {
+        uint32_t off = i == 8 ? lay.taux : i == 9 ? lay.mu : i == 10 ? lay.that
+                     : i < 11 + lay.n ? lay.l + (i - 11) : lay.r + (i - 11 - lay.n);
+        const uint4 *s = reinterpret_cast<const uint4 *>(ACP_PTR(blk, lay, p, off));
+        lo = s[0]; hi = s[1];
+    }
+    uint4 *d = reinterpret_cast<uint4 *>(out + (size_t)p * proof_len + 32 * (size_t)i);
+    d[0] = lo; d[1] = hi;
+}
+// proofs -> scalars into the proof block (reduced mod l: a non-canonical scalar is taken mod l, as
+// dalek's arithmetic would) and the 8 compressed points into pts8
+__global__ void k_acp_unpack(acp_layout lay, uint32_t B, const uint8_t *__restrict__ proofs, uint32_t proof_len,
+                             uint32_t *__restrict__ blk, uint8_t *__restrict__ pts8) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
+    const uint32_t words = proof_len / 32;
+    if (i >= words) return;
+    const uint4 *s = reinterpret_cast<const uint4 *>(proofs + (size_t)p * proof_len + 32 * (size_t)i);
+    uint4 lo = s[0], hi = s[1];
+    if (i < 8) {
+        uint4 *d = reinterpret_cast<uint4 *>(pts8 + 32 * ((size_t)p * 8 + i));
+        d[0] = lo; d[1] = hi;
+        return;
+    }
+    uint32_t off = i == 8 ? lay.taux : i == 9 ? lay.mu : i == 10 ? lay.that
+                 : i < 11 + lay.n ? lay.l + (i - 11) : lay.r + (i - 11 - lay.n);
+    sc v;
+    v.v[0] = lo.x; v.v[1] = lo.y; v.v[2] = lo.z; v.v[3] = lo.w; v.v[4] = hi.x; v.v[5] = hi.y; v.v[6] = hi.z; v.v[7] = hi.w;
+    sc_reduce256(v, v);
+    sc_store(ACP_PTR(blk, lay, p, off), v);
+}
+
+// ---- verifier ------------------------------------------------------------------------------------------
+// Scalars of the fused check, w = per-proof verifier weight (w = 0 in "reference" mode,
+// where only checks 1 and 2 are live: circuit_lib.rs:518,541,577-582):
+//   g: t - x^2(<z_q,c> + sigma)        h: tau_x - w mu
+//   G_i: w (x l_in_i - l_i)            H_i: w y_n_inv_i (x zWL_i + zWO_i - y_n_i - r_i)
+//   V_j: -x^2 zWV_j     T_1,T_3..T_6: -x, -x^3 .. -x^6     A_I, A_O, S: w x, w x^2, w x^3
+// accept <=> t == <l, r>  and  the MSM over these scalars is the identity.
+__global__ void __launch_bounds__(128) k_acp_vscal(acp_layout lay, uint32_t *__restrict__ blk) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
+    const uint32_t tot = lay.n + lay.m + 1;
+    if (i >= tot) return;
+    sc x, w, t, u, v;
+    sc_load(x, ACP_PTR(blk, lay, p, lay.x));
+    sc_load(w, ACP_PTR(blk, lay, p, lay.w));
+    if (i < lay.n) {
+        sc lin, l, yi, zwl, zwo, yn, r;
+        sc_load(lin, ACP_PTR(blk, lay, p, lay.lin + i));
+        sc_load(l, ACP_PTR(blk, lay, p, lay.l + i));
+        sc_mul(t, x, lin);
+        sc_sub(t, t, l);
+        sc_mul(t, w, t);
+        sc_store(ACP_PTR(blk, lay, p, lay.vG + i), t);
+        sc_load(yi, ACP_PTR(blk, lay, p, lay.yninv + i));
+        sc_load(zwl, ACP_PTR(blk, lay, p, lay.zWL + i));
+        sc_load(zwo, ACP_PTR(blk, lay, p, lay.zWO + i));
+        sc_load(yn, ACP_PTR(blk, lay, p, lay.yn + i));
+        sc_load(r, ACP_PTR(blk, lay, p, lay.r + i));
+        sc_mul(t, x, zwl);
+        sc_add(t, t, zwo);
+        sc_sub(t, t, yn);
+        sc_sub(t, t, r);
+        sc_mul(t, yi, t);
+        sc_mul(t, w, t);
+        sc_store(ACP_PTR(blk, lay, p, lay.vH + i), t);
+    } else if (i < lay.n + lay.m) {
+        const uint32_t j = i - lay.n;
+        sc_load(u, ACP_PTR(blk, lay, p, lay.zWV + j));
+        sc_mul(t, x, x);
+        sc_mul(t, t, u);
+        sc_neg(t, t);
+        sc_store(ACP_PTR(blk, lay, p, lay.vd + j), t);
+    } else {
+        sc xp[7];
+        sc_set_u32(xp[0], 1);
+        for (int k = 1; k <= 6; k++) sc_mul_noinline(xp[k], xp[k - 1], x);
+        // g
+        sc_load(u, ACP_PTR(blk, lay, p, lay.zc));
+        sc_load(v, ACP_PTR(blk, lay, p, lay.sigma));
+        sc_add(u, u, v);
+        sc_mul_noinline(u, u, xp[2]);
+        sc_load(v, ACP_PTR(blk, lay, p, lay.that));
+        sc_sub(t, v, u);
+        sc_store(ACP_PTR(blk, lay, p, lay.vg), t);
+        // h
+        sc_load(u, ACP_PTR(blk, lay, p, lay.mu));
+        sc_mul_noinline(u, u, w);
+        sc_load(v, ACP_PTR(blk, lay, p, lay.taux));
+        sc_sub(t, v, u);
+        sc_store(ACP_PTR(blk, lay, p, lay.vh), t);
+        const int deg[5] = {1, 3, 4, 5, 6};
+        for (int k = 0; k < 5; k++) {
+            sc_neg(t, xp[deg[k]]);
+            sc_store(ACP_PTR(blk, lay, p, lay.vd + lay.m + k), t);
+        }
+        for (int k = 0; k < 3; k++) {
+            sc_mul_noinline(t, w, xp[k + 1]);
+            sc_store(ACP_PTR(blk, lay, p, lay.vd + lay.m + 5 + k), t);
+        }
+    }
+}
+
+// thread per point: compressed -> affine Niels; invalid encodings flag the proof (dalek: decompress() is
+// None; the reference unwraps and panics, circuit_lib.rs:532 - here the proof is rejected).
+__global__ void __launch_bounds__(128) k_acp_decompress(const uint8_t *__restrict__ V /* B x m x 32 */,
+                                                        const uint8_t *__restrict__ pts8 /* B x 8 x 32 */, uint32_t m,
+                                                        uint32_t B, uint32_t *__restrict__ dyn /* B x (m+8) x 24 */,
+                                                        uint32_t *__restrict__ bad /* B */) {
+    const uint32_t per = m + 8;
+    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= B * per) return;
+    const uint32_t p = id / per, k = id - p * per;
+    const uint8_t *src = k < m ? V + 32 * ((size_t)p * m + k) : pts8 + 32 * ((size_t)p * 8 + (k < m + 5 ? 3 + (k - m) : k - m - 5));
+    fe x, y;
+    bool ok = ge_decompress(x, y, src);
+    if (!ok) {
+        atomicOr(&bad[p], 1u);
+        fe_set0(x);
+        fe_set1(y);
+    }
+    ge_niels q;
+    ge_affine_to_niels(q, x, y);
+    ge_niels_store(dyn + 24 * (size_t)id, q);
+}
+
+// Dynamic-point MSM, phase 1.  Block per proof, one thread per 4-bit signed window (64 windows):
+// each thread walks the proof's m+8 points and adds them into its 8 buckets (shared memory), then
+// folds the buckets with the running-sum trick into the window sum.
+#define DYN_C 4
+#define DYN_W 64
+FE_INLINE void dyn_bucket_store(uint4 *bk4, uint32_t b, uint32_t w, const ge_ext &a) {
+    const fe *f[4] = {&a.X, &a.Y, &a.Z, &a.T};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        bk4[((b * 8 + 2 * k) * DYN_W) + w] = make_uint4(f[k]->v[0], f[k]->v[1], f[k]->v[2], f[k]->v[3]);
+        bk4[((b * 8 + 2 * k + 1) * DYN_W) + w] = make_uint4(f[k]->v[4], f[k]->v[5], f[k]->v[6], f[k]->v[7]);
+    }
+}
+FE_INLINE void dyn_bucket_load(ge_ext &a, const uint4 *bk4, uint32_t b, uint32_t w) {
+    fe *f[4] = {&a.X, &a.Y, &a.Z, &a.T};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint4 lo = bk4[((b * 8 + 2 * k) * DYN_W) + w], hi = bk4[((b * 8 + 2 * k + 1) * DYN_W) + w];
+        f[k]->v[0] = lo.x; f[k]->v[1] = lo.y; f[k]->v[2] = lo.z; f[k]->v[3] = lo.w;
+        f[k]->v[4] = hi.x; f[k]->v[5] = hi.y; f[k]->v[6] = hi.z; f[k]->v[7] = hi.w;
+    }
+}
+__global__ void __launch_bounds__(DYN_W) k_dyn_window_sums(const uint32_t *__restrict__ blk, acp_layout lay,
+                                                           const uint32_t *__restrict__ dyn, uint32_t per,
+                                                           uint32_t *__restrict__ wsum /* B x 64 x 32 */) {
+    extern __shared__ uint4 bk4[];  // [bucket 8][quad 8][thread DYN_W]: conflict-free 16-byte accesses
+    const uint32_t p = blockIdx.x, w = threadIdx.x;
+    ge_ext id;
+    ge_identity(id);
+    for (int b = 0; b < 8; b++) dyn_bucket_store(bk4, b, w, id);
+    const uint32_t *scal = ACP_PTR(blk, lay, p, lay.vd);
+    const uint32_t *pts = dyn + 24 * (size_t)p * per;
+    // digit w of s' = s + 0x0888...8 (carry-free signed recoding, top window unsigned)
+#pragma unroll 1
+    for (uint32_t k = 0; k < per; k++) {
+        uint32_t s[9];
+        unsigned long long carry = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            uint32_t kl = (i == 7) ? 0x08888888u : 0x88888888u;
+            carry += (unsigned long long)scal[8 * (size_t)k + i] + kl;
+            s[i] = (uint32_t)carry;
+            carry >>= 32;
+        }
+        s[8] = (uint32_t)carry;
+        uint32_t u = (s[w >> 3] >> ((w & 7) * 4)) & 15u;
+        if (w == DYN_W - 1) u += s[8] << 4;  // cannot happen for s < 2^255 (kept for safety)
+        int d = (w == DYN_W - 1) ? (int)u : (int)u - 8;
+        if (d == 0) continue;
+        uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+        ge_niels q;
+        ge_niels_load(q, pts + 24 * (size_t)k);
+        ge_ext a;
+        dyn_bucket_load(a, bk4, mag - 1, w);
+        ge_madd(a, a, q, d < 0);
+        dyn_bucket_store(bk4, mag - 1, w, a);
+    }
+    ge_ext run, acc, t;
+    dyn_bucket_load(run, bk4, 7, w);
+    acc = run;
+#pragma unroll 1
+    for (int b = 6; b >= 0; b--) {
+        dyn_bucket_load(t, bk4, b, w);
+        ge_add(run, run, t);
+        ge_add(acc, acc, run);
+    }
+    ge_store(wsum + 32 * ((size_t)p * DYN_W + w), acc);
+}
+
+// phase 2.  Thread per proof: Horner over the 64 window sums (4 doublings each), add the fixed-base
+// part, test for the identity and fold in the scalar check t == <l, r>.
+__global__ void __launch_bounds__(64) k_dyn_horner_accept(acp_layout lay, uint32_t B, const uint32_t *__restrict__ blk,
+                                                          const uint32_t *__restrict__ wsum,
+                                                          const uint32_t *__restrict__ stat_ext /* B x 32 */,
+                                                          const uint32_t *__restrict__ bad, uint8_t *__restrict__ accept) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    ge_ext acc, t;
+    ge_load(acc, wsum + 32 * ((size_t)p * DYN_W + DYN_W - 1));
+#pragma unroll 1
+    for (int w = DYN_W - 2; w >= 0; w--) {
+#pragma unroll 1
+        for (int i = 0; i < DYN_C; i++) ge_double(acc, acc);
+        ge_load(t, wsum + 32 * ((size_t)p * DYN_W + w));
+        ge_add(acc, acc, t);
+    }
+    ge_load(t, stat_ext + 32 * (size_t)p);
+    ge_add(acc, acc, t);
+    bool ident = fe_is_zero(acc.X) || fe_is_zero(acc.Y);  // the Ristretto identity coset
+    sc that, lr;
+    sc_load(that, ACP_PTR(blk, lay, p, lay.that));
+    sc_load(lr, ACP_PTR(blk, lay, p, lay.dots + 10));
+    accept[p] = (ident && sc_eq(that, lr) && bad[p] == 0) ? 1 : 0;
+}

@@ -575,3 +575,4 @@ extern "C" int bpp_test_op(bpp_ctx *ctx, int op, const uint8_t *a, const uint8_t
 }
 
 #include "vec_capi.cuh"
+#include "acproof_host.cuh"

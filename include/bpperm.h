@@ -132,6 +132,57 @@ int bpp_vecpoly3_eval(bpp_ctx *ctx, const uint8_t *coeffs, size_t n, const uint8
 /* poly.rs:14-18  Poly6::eval */
 int bpp_poly6_eval(bpp_ctx *ctx, const uint8_t t1_t6[192], const uint8_t x[32], uint8_t out[32]);
 
+/* ---- the arithmetic-circuit (shuffle) proof, batched ------------------------------------------------
+ * Replaces the group/scalar arithmetic of ACProof::ArithmeticCircuitProof (circuit_lib.rs:133-585) for
+ * `count` independent proofs that share one circuit and one generator set, driven in the reference's
+ * call order (lib.rs:219-231): create -> challenge_wit_and_const -> compute_per_challenges -> commit_Ts
+ * -> random_chall_x -> blinding_values -> verify.  Merlin transcripts (transcript_protocol.rs) run on
+ * host threads inside the library; the prover's RNG is a ChaCha20 stream per proof (seed = 32 bytes ==
+ * rand_chacha::ChaCha20Rng::from_seed), drawn in the reference's order alpha, beta, ro, s_l[], s_r[],
+ * tau_1, tau_3, tau_4, tau_5, tau_6 (circuit_lib.rs:180-182,213-214,361-404).
+ *   mode 0 "reference"        what the reference code computes, defects included; its
+ *                             verifier rejects every proof (circuit_lib.rs:541-544), so does this one.
+ *   mode 1 "reference-fixed"  defects 2-5 corrected: an accepting protocol with l, r in the clear.
+ * Proof bytes (the reference defines no serialisation): A_I | A_O | S | T_1 | T_3 | T_4 | T_5 | T_6 |
+ * tau_x | mu | t | l[0..n) | r[0..n), 32 bytes each. */
+typedef struct bpp_circuit bpp_circuit;
+typedef struct bpp_gens bpp_gens;
+typedef struct bpp_acp_batch bpp_acp_batch;
+/* Sparse form of ACEssentials' W_L, W_R, W_O (n x Q) and W_V (m x Q) (circuit_lib.rs:66-70): triples
+ * (wire, constraint, coefficient), the four matrices concatenated in that order with nnz[4] counts;
+ * c_vec is the dense constant vector (Q x 32).  Constraint q: W_L a_L + W_R a_R + W_O a_O = W_V v + c. */
+int bpp_circuit_create(bpp_ctx *ctx, size_t n, size_t Q, size_t m, const uint32_t nnz[4], const uint32_t *wire,
+                       const uint32_t *constraint, const uint8_t *coeff, const uint8_t *c_vec, bpp_circuit **out);
+void bpp_circuit_free(bpp_ctx *ctx, bpp_circuit *c);
+/* g_base, h_base, G_vec[n], H_vec[n] (circuit_lib.rs:59-65) as compressed points; builds the fixed-base
+ * window tables (window_bits 4..16, 0 = default 8) used by every commitment of the protocol. */
+int bpp_gens_create(bpp_ctx *ctx, const uint8_t g[32], const uint8_t h[32], const uint8_t *G, const uint8_t *H, size_t n,
+                    int window_bits, bpp_gens **out);
+void bpp_gens_free(bpp_ctx *ctx, bpp_gens *g);
+size_t bpp_acproof_proof_len(size_t n);
+/* One-call host forms: host buffers in, host buffers out (all copies included). */
+int bpp_acproof_prove_batch(bpp_ctx *ctx, const bpp_circuit *cir, const bpp_gens *gens, int mode, size_t count,
+                            const uint8_t *aL, const uint8_t *aR, const uint8_t *aO /* count x n x 32 */,
+                            const uint8_t *gamma /* count x m x 32 */, const uint8_t *seeds /* count x 32 */,
+                            const uint8_t *label, size_t label_len, uint8_t *proofs_out /* count x proof_len */);
+int bpp_acproof_verify_batch(bpp_ctx *ctx, const bpp_circuit *cir, const bpp_gens *gens, int mode, size_t count,
+                             const uint8_t *proofs, const uint8_t *V /* count x m x 32 compressed */,
+                             const uint8_t *label, size_t label_len, const uint8_t verifier_seed[32],
+                             uint8_t *accept /* count bytes: 1 = Ok(()), 0 = Err(VerificationError) */);
+/* Staged forms (device-resident batches; used for the resident-input timing and by long-lived provers). */
+int bpp_acp_batch_create(bpp_ctx *ctx, const bpp_circuit *cir, const bpp_gens *gens, int mode, size_t count,
+                         const uint8_t *label, size_t label_len, bpp_acp_batch **out);
+void bpp_acp_batch_free(bpp_acp_batch *b);
+int bpp_acp_batch_upload_witness(bpp_acp_batch *b, const uint8_t *aL, const uint8_t *aR, const uint8_t *aO,
+                                 const uint8_t *gamma, const uint8_t *seeds);
+/* commit_variables (weights.rs:58-61): V_j = v_j*g + gamma_j*h with the uploaded gamma; V_out nullable. */
+int bpp_acp_batch_commit(bpp_acp_batch *b, const uint8_t *v /* count x m x 32 */, uint8_t *V_out);
+int bpp_acp_batch_prove(bpp_acp_batch *b);
+int bpp_acp_batch_download_proofs(bpp_acp_batch *b, uint8_t *proofs_out);
+int bpp_acp_batch_upload_proofs(bpp_acp_batch *b, const uint8_t *proofs, const uint8_t *V /* nullable */);
+int bpp_acp_batch_verify(bpp_acp_batch *b, const uint8_t verifier_seed[32]);
+int bpp_acp_batch_download_accept(bpp_acp_batch *b, uint8_t *accept);
+
 /* ---- measurement helpers --------------------------------------------------------------------- */
 /* IMAD.WIDE.U32 peak microbenchmark: returns wide multiply-adds per second over all SMs. */
 int bpp_bench_imad_peak(bpp_ctx *ctx, int iters, double *ops_per_sec, double *ms);
