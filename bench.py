@@ -1,23 +1,25 @@
 #!/usr/bin/env python
 """bench.py - headline benchmark of the B200 backend (contract in the task statement).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload msm]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload shuffle|msm|both]
 
+BASELINE.json metric: "shuffle proofs/sec prove+verify (52-card); MSM points/sec at 2^20".
 One "step" = one pass of the hot path over one batch of synthetic input.
 
-workload `msm` (BASELINE.json configs[4] at N = 2^20, the second half of the metric):
-    one Ristretto255 vartime multiscalar multiplication over 2^20 points per GPU.
-    value  : points/s with scalars AND the point table resident in HBM
-    e2e    : points/s through the host C-ABI call bpp_msm_vartime(): the step's scalars start in
-             pinned host memory, are copied H2D inside the timed region, and the 32-byte result
-             is read back D2H.  The generator table is uploaded once (static public parameters,
-             like weights) - stated in DESIGN.md.
-    multi-GPU: rank r holds its own 2^20-point slice (weak scaling); each step every rank computes
-             its partial sum, one NCCL all-gather of 128 B per rank, then every rank adds and
-             compresses.  value = (world * 2^20) / max-over-ranks time.
+workload `shuffle` (headline; BASELINE configs[1], and configs[3] when --gpus > 1):
+    one step = prove + verify a batch of `--batch` independent 52-card shuffle proofs
+    (k = 52 -> n = 104 multipliers, Q = 208 constraints, m = 105 commitments; mode "reference-fixed").
+    value : proofs/s with witness, commitments and proofs resident in HBM
+    e2e   : proofs/s through the host C ABI - witness H2D, proofs D2H, proofs + commitments H2D,
+            accept bytes D2H every step (bpp_acp_batch_upload_witness/prove/download_proofs/
+            upload_proofs/verify/download_accept)
+    multi-GPU: proofs are independent -> each rank owns `--batch` proofs, no data-path collective
+            (weak scaling); value = world * batch * steps / max-over-ranks time.
+workload `msm` (second half of the metric; BASELINE configs[4] at N = 2^20): reported under "msm".
+    multi-GPU: points sharded, one NCCL all-gather of 128 B per rank, then add + compress.
 
-`--impl reference` times the CPU restatement of the reference's dalek-ng 4.1.1 serial backend
-(oracle/c/dalek_ref.c) on the host cores, on a bounded sample of the same workload.
+`--impl reference` times the CPU restatement of the reference (oracle/c: dalek-ng 4.1.1 serial
+backend + circuit_lib.rs flow) on all host cores, on a bounded sample of the same workload.
 """
 from __future__ import annotations
 
@@ -36,6 +38,8 @@ sys.path.insert(0, ROOT)
 
 # IMAD.WIDE.U32-equivalents per point operation
 IMAD_MADD, IMAD_ADD, IMAD_DBL = 504, 648, 464
+L_ORDER = 2**252 + 27742317777372353535851937790883648493
+K_CARDS = 52
 
 
 def _peaks():
@@ -56,9 +60,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
-        self.idx = gpu_index
-        self.samples = []
-        self.proc = None
+        self.idx, self.samples, self.proc = gpu_index, [], None
 
     def start(self):
         try:
@@ -96,13 +98,15 @@ class ClockSampler:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        # clocks under load = the upper half of the samples (the sampler also sees idle gaps)
+        sm_sorted = sorted(sm)
+        under_load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
+        return {"sm_mhz": float(np.median(under_load)) if under_load else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# ---------------------------------------------------------------------------------- synthetic inputs
 def synth_msm_inputs(n: int, rank: int, n_sets: int):
-    """Synthetic inputs: 64 uniform bytes per point (-> RistrettoPoint::from_uniform_bytes on the
-    device), uniform canonical scalars (< 2^252 < l)."""
     rs = np.random.RandomState(20260000 + rank)
     blobs = rs.randint(0, 256, size=(n, 64), dtype=np.uint8)
     sets = []
@@ -113,13 +117,110 @@ def synth_msm_inputs(n: int, rank: int, n_sets: int):
     return blobs, sets
 
 
-# --------------------------------------------------------------------------------------------------
-def cpu_msm_baseline(budget_s: float = 12.0):
-    """C restatement of dalek's vartime_multiscalar_mul, 1 core (the reference is single-threaded)
-    and all cores (one process per core over slices), on a bounded sample."""
+def _sc_bytes(vals):
+    return b"".join(int(v).to_bytes(32, "little") for v in vals)
+
+
+def synth_shuffle_batch(k: int, count: int, rank: int):
+    """`count` independent k-card shuffles: deck 1..k, a random permutation, a random challenge value X,
+    uniform blindings.  Returns bytes for a_L, a_R, a_O (count x n), gamma, v (count x m), seeds."""
+    import bpperm_b200
+    W = bpperm_b200.weights
+    rs = np.random.RandomState(777 + rank)
+    aL, aR, aO, vv = [], [], [], []
+    for _ in range(count):
+        perm = rs.permutation(k)
+        x = int.from_bytes(rs.bytes(31), "little")
+        v, a_L, a_R, a_O = W.shuffle_witness(k, perm, x)
+        aL.append(_sc_bytes(a_L)); aR.append(_sc_bytes(a_R)); aO.append(_sc_bytes(a_O)); vv.append(_sc_bytes(v))
+    m = 2 * k + 1
+    g = rs.randint(0, 256, size=(count * m, 32), dtype=np.uint8)
+    g[:, 31] &= 0x0F
+    seeds = rs.randint(0, 256, size=(count, 32), dtype=np.uint8)
+    return b"".join(aL), b"".join(aR), b"".join(aO), g.tobytes(), b"".join(vv), seeds.tobytes()
+
+
+def shuffle_setup(be, k: int):
+    """Generators as RistrettoPoint::random (lib.rs:164-167,179-180) from a seeded byte stream, the
+    corrected k-card shuffle circuit, fixed-base tables."""
+    import bpperm_b200
+    G = bpperm_b200.acproof
+    n, Q, m, WL, WR, WO, WV, c = bpperm_b200.weights.shuffle_circuit(k)
+    rs = np.random.RandomState(4242)
+    pts = be.points_from_uniform(rs.randint(0, 256, size=(2 * n + 2, 64), dtype=np.uint8).tobytes())
+    enc = be.compress_points(pts)
+    pts.free()
+    cir = G.Circuit(be, n, Q, m, WL, WR, WO, WV, c)
+    gens = G.Generators(be, enc[:32], enc[32:64], [enc[64 + 32 * i: 96 + 32 * i] for i in range(n)],
+                        [enc[64 + 32 * (n + i): 96 + 32 * (n + i)] for i in range(n)])
+    return cir, gens, enc, (n, Q, m)
+
+
+# ---------------------------------------------------------------------------------- CPU baselines
+def _cpu_instance(k, enc):
+    """Dense-matrix instance for the C restatement, same generators/circuit as the GPU run."""
+    from oracle import cref
+    import bpperm_b200
+    n, Q, m, WL, WR, WO, WV, c = bpperm_b200.weights.shuffle_circuit(k)
+
+    def dense(tr, rows):
+        M = bytearray(rows * Q * 32)
+        for i, q, cf in tr:
+            M[32 * (i * Q + q): 32 * (i * Q + q) + 32] = int(cf).to_bytes(32, "little")
+        return bytes(M)
+
+    return cref.AcpInstance(n, Q, m, dense(WL, n), dense(WR, n), dense(WO, n), dense(WV, m), _sc_bytes(c), enc[:32],
+                            enc[32:64], enc[64:64 + 32 * n], enc[64 + 32 * n: 64 + 64 * n])
+
+
+_CPU_INST = None
+
+
+def _cpu_one(args):
+    aL, aR, aO, gamma, v, seed = args
+    Vp = _CPU_INST.commit(v, gamma)
+    t0 = time.time()
+    pb, rc = _CPU_INST.prove_verify(aL, aR, aO, gamma, Vp, seed, 1)
+    return time.time() - t0, rc, pb
+
+
+def cpu_shuffle_baseline(k, enc, batch_bytes, n_single=8):
+    """The reference's CPU path (C restatement of dalek-ng 4.1.1 + circuit_lib.rs, dense matrices) on the
+    same inputs: single core (the reference is single-threaded) and all cores over independent proofs."""
+    global _CPU_INST
+    import multiprocessing as mp
+    _CPU_INST = _cpu_instance(k, enc)
+    n, m = 2 * k, 2 * k + 1
+    aL, aR, aO, gamma, v, seeds = batch_bytes
+    cores = os.cpu_count() or 1
+
+    def job(i):
+        return (aL[32 * n * i:32 * n * (i + 1)], aR[32 * n * i:32 * n * (i + 1)], aO[32 * n * i:32 * n * (i + 1)],
+                gamma[32 * m * i:32 * m * (i + 1)], v[32 * m * i:32 * m * (i + 1)], seeds[32 * i:32 * (i + 1)])
+
+    res = [_cpu_one(job(i)) for i in range(n_single)]
+    t1 = sum(r[0] for r in res)
+    out = {"value": n_single / t1, "unit": "proofs/s", "cores": 1, "kind": "port",
+           "sample": f"{n_single} of the batch's 52-card proofs, prove+verify each, one core ({t1 / n_single * 1e3:.1f} ms/proof)",
+           "impl": "C restatement of circuit_lib.rs over curve25519-dalek-ng 4.1.1's serial u64 algorithms (oracle/c)",
+           "accepted": all(r[1] == 1 for r in res), "proofs": [r[2] for r in res]}
+    try:
+        ctx = mp.get_context("fork")
+        jobs = [job(i % n_single) for i in range(cores * 2)]
+        with ctx.Pool(cores) as pool:
+            pool.map(_cpu_one, jobs[:cores])  # warm the workers
+            t0 = time.time()
+            pool.map(_cpu_one, jobs)
+            tall = time.time() - t0
+        out["all_cores"] = {"value": len(jobs) / tall, "cores": cores}
+    except Exception as e:  # pragma: no cover
+        out["all_cores"] = {"error": str(e)}
+    return out
+
+
+def cpu_msm_baseline():
     from oracle import cref
     import multiprocessing as mp
-
     cores = os.cpu_count() or 1
     n = 1 << 16
     rs = np.random.RandomState(7)
@@ -131,10 +232,9 @@ def cpu_msm_baseline(budget_s: float = 12.0):
     r1 = cref.msm(scb, pts)
     t1 = time.time() - t0
     out = {"value": n / t1, "unit": "points/s", "cores": 1, "kind": "port",
-           "sample": f"one 2^16-point MSM (dalek Pippenger w=8 restated in C, {t1:.2f} s); 2^20 extrapolates linearly",
-           "impl": "C restatement of curve25519-dalek-ng 4.1.1 serial u64 backend"}
-    # all cores: slices in worker processes (fork), partial sums added
+           "sample": f"one 2^16-point MSM (dalek Pippenger w=8 restated in C, {t1:.2f} s); 2^20 scales linearly"}
     try:
+        import ctypes
         per = n // cores
         ctx = mp.get_context("fork")
         t0 = time.time()
@@ -142,59 +242,64 @@ def cpu_msm_baseline(budget_s: float = 12.0):
             parts = pool.starmap(cref.msm_raw, [(scb[32 * i * per:32 * (i + 1) * per], pts[160 * i * per:160 * (i + 1) * per])
                                                 for i in range(cores)])
         acc = parts[0]
-        import ctypes
         for p in parts[1:]:
             o = ctypes.create_string_buffer(160)
             cref.lib().orc_point_add(acc, p, o)
             acc = o.raw
         tall = time.time() - t0
-        ok = cref.compress(acc) == r1 if per * cores == n else None
-        out["all_cores"] = {"value": n / tall, "cores": cores, "matches_1core": ok}
+        out["all_cores"] = {"value": n / tall, "cores": cores,
+                            "matches_1core": (cref.compress(acc) == r1) if per * cores == n else None}
     except Exception as e:  # pragma: no cover
         out["all_cores"] = {"error": str(e)}
     return out
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path (C restatement) on the host cores."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """--impl reference: the reference's CPU path on all host cores, bounded sample per step."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return 0
-    from oracle import cref
+    global _CPU_INST
     import multiprocessing as mp
+    from oracle import cref
     cores = os.cpu_count() or 1
-    n = 1 << 14  # bounded sample per step, per core
-    rs = np.random.RandomState(11)
-    pts = cref.from_uniform(rs.randint(0, 256, size=(n * cores, 64), dtype=np.uint8).tobytes())
-    sc = rs.randint(0, 256, size=(n * cores, 32), dtype=np.uint8)
-    sc[:, 31] &= 0x0F
-    scb = sc.tobytes()
-    jobs = [(scb[32 * i * n:32 * (i + 1) * n], pts[160 * i * n:160 * (i + 1) * n]) for i in range(cores)]
+    k = K_CARDS
+    n, m = 2 * k, 2 * k + 1
+    # same generator stream as the GPU arm; points derived on the CPU
+    rs = np.random.RandomState(4242)
+    enc = cref.compress(cref.from_uniform(rs.randint(0, 256, size=(2 * n + 2, 64), dtype=np.uint8).tobytes()))
+    _CPU_INST = _cpu_instance(k, enc)
+    aL, aR, aO, gamma, v, seeds = synth_shuffle_batch(k, cores, 0)
+    jobs = [(aL[32 * n * i:32 * n * (i + 1)], aR[32 * n * i:32 * n * (i + 1)], aO[32 * n * i:32 * n * (i + 1)],
+             gamma[32 * m * i:32 * m * (i + 1)], v[32 * m * i:32 * m * (i + 1)], seeds[32 * i:32 * (i + 1)])
+            for i in range(cores)]
     ctx = mp.get_context("fork")
+    ok = True
     with ctx.Pool(cores) as pool:
         for _ in range(args.warmup):
-            pool.starmap(cref.msm_raw, jobs)
+            pool.map(_cpu_one, jobs)
         t0 = time.time()
         for _ in range(args.steps):
-            pool.starmap(cref.msm_raw, jobs)
+            ok = ok and all(r[1] == 1 for r in pool.map(_cpu_one, jobs))
         dt = time.time() - t0
-    value = args.steps * n * cores / dt
+    value = args.steps * cores / dt
     line = {
-        "impl": "reference", "metric": "MSM points/sec at 2^20", "value": value, "unit": "points/s",
+        "impl": "reference", "metric": "shuffle proofs/sec prove+verify (52-card)", "value": value, "unit": "proofs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 (5x51-bit limbs)",
-        "data": "synthetic", "config": {"workload": "ristretto255 vartime MSM, 2^20 points (bounded sample)"},
-        "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port",
-                         "sample": f"each step: {cores} independent 2^14-point slices (one per core) of the 2^20 workload; "
-                                   "dalek Pippenger restated in C"},
-        "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 (5x51-bit field limbs, 4x64 scalars)",
+        "data": "synthetic",
+        "config": {"workload": "52-card shuffle proof prove+verify (k=52, n=104, Q=208, m=105), mode reference-fixed",
+                   "all_accepted": ok},
+        "cpu_baseline": {"value": value, "unit": "proofs/s", "cores": cores, "kind": "port",
+                         "sample": f"each step: {cores} independent 52-card proofs (one per core), prove+verify; "
+                                   "C restatement of circuit_lib.rs + dalek-ng 4.1.1 serial algorithms, dense W matrices"},
+        "e2e": {"value": value, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
     return 0
 
 
-# --------------------------------------------------------------------------------------------------
+# ---------------------------------------------------------------------------------- GPU arm
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -211,38 +316,6 @@ def run_ours(args):
     be = bpperm_b200.Backend(local)
     stream = torch.cuda.current_stream(dev)
     be.set_stream(stream.cuda_stream)
-
-    n = 1 << args.log_n
-    n_sets = 4
-    blobs, sets = synth_msm_inputs(n, rank, n_sets)
-    table = be.points_from_uniform(blobs.tobytes())
-    d_sets = [torch.from_numpy(s).to(dev) for s in sets]
-    h_sets = [torch.from_numpy(s).pin_memory() for s in sets]
-    d_part = torch.zeros(128, dtype=torch.uint8, device=dev)
-    d_gather = torch.zeros(world * 128, dtype=torch.uint8, device=dev)
-    d_out = torch.zeros(160, dtype=torch.uint8, device=dev)
-    h_out = torch.zeros(32, dtype=torch.uint8).pin_memory()
-
-    def step_resident(i):
-        d_sc = d_sets[i % n_sets]
-        if world == 1:
-            be.msm_dev(d_sc.data_ptr(), table, 0, n, d_out.data_ptr())
-        else:
-            be.msm_partial_dev(d_sc.data_ptr(), table, 0, n, d_part.data_ptr())
-            dist.all_gather_into_tensor(d_gather, d_part)
-            be.points_sum_compress_dev(d_gather.data_ptr(), world, d_out.data_ptr())
-
-    def step_e2e(i):
-        d_sc = d_sets[i % n_sets]
-        d_sc.copy_(h_sets[(i + 1) % n_sets], non_blocking=True)  # this step's inputs: pinned host -> HBM
-        if world == 1:
-            be.msm_dev(d_sc.data_ptr(), table, 0, n, d_out.data_ptr())
-        else:
-            be.msm_partial_dev(d_sc.data_ptr(), table, 0, n, d_part.data_ptr())
-            dist.all_gather_into_tensor(d_gather, d_part)
-            be.points_sum_compress_dev(d_gather.data_ptr(), world, d_out.data_ptr())
-        h_out.copy_(d_out[:32], non_blocking=True)
-        stream.synchronize()  # the caller needs the result before the next call
 
     def barrier():
         if world > 1:
@@ -266,72 +339,178 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
-    # roofline denominator measured live on this GPU
     imad_peak, _ = be.imad_peak(4096)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    launches0 = be.launch_count
-    ms_res = timed(step_resident, args.steps, args.warmup)
-    launches = be.launch_count - launches0
-    launches_timed = launches * args.steps // (args.steps + args.warmup)
-    clocks = sampler.stop() if rank == 0 else None
-    ms_e2e = timed(step_e2e, args.steps, args.warmup)
-
-    # per-kernel timing of the dominant kernel (bucket accumulation), CUDA events inside the library
-    be.set_profiling(True)
-    acc_ms = []
-    for i in range(max(3, args.steps)):
-        be.msm_dev(d_sets[i % n_sets].data_ptr(), table, 0, n, d_out.data_ptr())
-        ph = be.last_phase_ms()  # CUDA events recorded on the launching stream around each kernel
-        acc_ms.append([ph[k] for k in bpperm_b200.backend.PHASES])
-    be.set_profiling(False)
-    ops = be.last_op_counts()
-    result_hex = bytes(d_out[:32].cpu().numpy().tobytes()).hex()
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return 0
-
-    total_points = n * world
-    value = total_points * args.steps / (ms_res * 1e-3)
-    e2e = total_points * args.steps / (ms_e2e * 1e-3)
-    phases = np.median(np.array(acc_ms), axis=0)
-    acc_t = float(phases[3]) * 1e-3
-    imads_acc = ops["mixed_adds"] * IMAD_MADD
-    imads_all = imads_acc + ops["full_adds"] * IMAD_ADD + ops["doublings"] * IMAD_DBL
     peaks, peaks_src = _peaks()
-    achieved = imads_acc / acc_t if acc_t > 0 else 0.0
-    line = {
-        "metric": "MSM points/sec at 2^20", "value": value, "unit": "points/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u32 (8x32-bit limbs, IMAD.WIDE.U32)", "data": "synthetic",
-        "config": {"workload": f"ristretto255 vartime MSM, 2^{args.log_n} points per GPU (BASELINE configs[4])",
-                   "points": "from_uniform_bytes(seeded bytes), resident as affine Niels (96 B/pt)",
-                   "scalars": "uniform < 2^252, 4 rotating sets",
-                   "l2": "working set (96 MiB table + 32 MiB scalars + 100 MiB sort scratch + 64 MiB buckets) exceeds the 126 MB L2; scalar sets rotate",
-                   "parallelism": f"points sharded over {world} GPU(s), one NCCL all-gather of 128 B/rank" if world > 1 else "single GPU",
-                   "result": result_hex},
-        "e2e": {"value": e2e, "unit": "points/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": 32,
-                "ms_per_step": ms_e2e / args.steps,
-                "note": "scalars pinned-host->HBM and result HBM->host every step; generator table resident"},
-        "gpu_launches": launches_timed,
-        "roofline": {"bound": "imad", "kernel": "k_bucket_accum", "achieved": achieved / 1e12, "peak": imad_peak / 1e12,
-                     "unit": "T IMAD.WIDE.U32/s", "frac": achieved / imad_peak if imad_peak else None,
-                     "peak_source": "bpp_bench_imad_peak measured in this run (8 independent chains/thread, all SMs)",
-                     "traffic": None, "kernel_ms": float(phases[3]),
-                     "point_adds_per_s": ops["mixed_adds"] / acc_t if acc_t > 0 else None,
-                     "whole_msm": {"imad_equiv": imads_all, "frac_of_peak": imads_all / (ms_res / args.steps * 1e-3) / imad_peak},
-                     "phases_ms": dict(zip(["recode", "scan", "scatter", "accumulate", "reduce", "finish"],
-                                           [float(x) for x in phases])),
-                     "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_peak_source": peaks_src},
-        "clocks": clocks,
-    }
-    if world == 1 and not args.no_cpu:
-        line["cpu_baseline"] = cpu_msm_baseline()
-    print(json.dumps(line))
+    line = {}
+    sampler = ClockSampler(local)
+
+    # ------------------------------------------------------------------ shuffle proofs (headline)
+    if args.workload in ("shuffle", "both"):
+        G = bpperm_b200.acproof
+        k, B = K_CARDS, args.batch
+        cir, gens, enc, (n, Q, m) = shuffle_setup(be, k)
+        data = synth_shuffle_batch(k, B, rank)
+        aL, aR, aO, gamma, v, seeds = data
+        batch = G.Batch(be, cir, gens, B, "reference-fixed", b"test")
+        batch.upload_witness(aL, aR, aO, gamma, seeds)
+        Vc = batch.commit(v)               # commit_variables: input generation, not timed
+        plen = batch.proof_len
+
+        def step_resident(i):
+            batch.prove()
+            batch.verify(b"\x5a" * 32)
+
+        state = {}
+
+        def step_e2e(i):
+            batch.upload_witness(aL, aR, aO, gamma, seeds)
+            batch.prove()
+            proofs = batch.download_proofs()
+            batch.upload_proofs(proofs, Vc)
+            batch.verify(b"\x5a" * 32)
+            state["accept"] = batch.download_accept()
+            state["proofs"] = proofs
+
+        if rank == 0:
+            sampler.start()
+        l0 = be.launch_count
+        ms_res = timed(step_resident, args.steps, args.warmup)
+        launches = (be.launch_count - l0) * args.steps // (args.steps + args.warmup)
+        clocks = sampler.stop() if rank == 0 else None
+        ms_e2e = timed(step_e2e, args.steps, args.warmup)
+        all_ok = state["accept"] == b"\x01" * B
+        fb_ms, fb_madd, fb_add = batch.time_commit_msm(5)
+        if world > 1:
+            okt = torch.tensor([1 if all_ok else 0], device=dev)
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+            all_ok = bool(okt.item())
+        if rank == 0:
+            total = B * world
+            value = total * args.steps / (ms_res * 1e-3)
+            e2e = total * args.steps / (ms_e2e * 1e-3)
+            fb_imads = fb_madd * IMAD_MADD + fb_add * IMAD_ADD
+            ach = fb_imads / (fb_ms * 1e-3)
+            line = {
+                "metric": "shuffle proofs/sec prove+verify (52-card)", "value": value, "unit": "proofs/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u32 (8x32-bit limbs, IMAD.WIDE.U32)", "data": "synthetic",
+                "config": {"workload": f"52-card shuffle prove+verify, batch of {B} independent proofs per GPU "
+                                       f"(k=52, n={n}, Q={Q}, m={m}; BASELINE configs[1]/[3])",
+                           "mode": "reference-fixed (SURVEY A.3: the reference's own flow never verifies)",
+                           "inputs": "deck 1..52, random permutation and challenge value per proof, uniform blindings, "
+                                     "generators = from_uniform_bytes(seeded bytes); prover RNG = ChaCha20 per proof",
+                           "l2": f"per-step working set {B * batch.proof_len / 2**20:.0f} MiB proofs + {B * 2548 * 32 / 2**20:.0f} MiB "
+                                 "scalar blocks + 83 MiB fixed-base tables + 226 MiB verifier window sums > 126 MB L2",
+                           "parallelism": f"proofs sharded over {world} GPU(s), no data-path collective" if world > 1 else "single GPU",
+                           "all_accepted": all_ok},
+                "e2e": {"value": e2e, "unit": "proofs/s", "h2d_bytes_per_step": B * (3 * n + m) * 32 + B * 32 + B * plen + B * m * 32,
+                        "d2h_bytes_per_step": B * plen + B, "ms_per_step": ms_e2e / args.steps,
+                        "note": "witness H2D, proofs D2H, proofs+commitments H2D, accept bytes D2H inside the timed region; "
+                                "Fiat-Shamir transcripts on host threads in both numbers"},
+                "gpu_launches": launches,
+                "roofline": {"bound": "imad", "kernel": "k_fb_msm (A_I-shaped commitment MSM, 209 terms x 32 windows per proof)",
+                             "achieved": ach / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD.WIDE.U32/s",
+                             "frac": ach / imad_peak, "kernel_ms": fb_ms, "point_adds_per_s": (fb_madd + fb_add) / (fb_ms * 1e-3),
+                             "peak_source": "bpp_bench_imad_peak measured in this run (plain IMAD.WIDE.U32, 8 chains/thread, all SMs)",
+                             "traffic": None, "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_peak_source": peaks_src},
+                "clocks": clocks,
+            }
+            if world == 1 and not args.no_cpu:
+                cb = cpu_shuffle_baseline(k, enc, data)
+                gpu_first = [state["proofs"][i * plen:(i + 1) * plen] for i in range(len(cb["proofs"]))]
+                cb["proof_bytes_equal_gpu"] = gpu_first == cb.pop("proofs")
+                line["cpu_baseline"] = cb
+        batch.free()
+
+    # ------------------------------------------------------------------ MSM at 2^20 (second metric)
+    if args.workload in ("msm", "both"):
+        n = 1 << args.log_n
+        n_sets = 4
+        blobs, sets = synth_msm_inputs(n, rank, n_sets)
+        table = be.points_from_uniform(blobs.tobytes())
+        d_sets = [torch.from_numpy(s).to(dev) for s in sets]
+        h_sets = [torch.from_numpy(s).pin_memory() for s in sets]
+        d_part = torch.zeros(128, dtype=torch.uint8, device=dev)
+        d_gather = torch.zeros(world * 128, dtype=torch.uint8, device=dev)
+        d_out = torch.zeros(160, dtype=torch.uint8, device=dev)
+        h_out = torch.zeros(32, dtype=torch.uint8).pin_memory()
+
+        def msm_once(d_sc):
+            if world == 1:
+                be.msm_dev(d_sc.data_ptr(), table, 0, n, d_out.data_ptr())
+            else:
+                be.msm_partial_dev(d_sc.data_ptr(), table, 0, n, d_part.data_ptr())
+                dist.all_gather_into_tensor(d_gather, d_part)
+                be.points_sum_compress_dev(d_gather.data_ptr(), world, d_out.data_ptr())
+
+        def msm_resident(i):
+            msm_once(d_sets[i % n_sets])
+
+        def msm_e2e(i):
+            d_sc = d_sets[i % n_sets]
+            d_sc.copy_(h_sets[(i + 1) % n_sets], non_blocking=True)
+            msm_once(d_sc)
+            h_out.copy_(d_out[:32], non_blocking=True)
+            stream.synchronize()
+
+        msm_steps = max(args.steps, 10)
+        l0 = be.launch_count
+        samp2 = ClockSampler(local)
+        if rank == 0 and args.workload == "msm":
+            samp2.start()
+        ms_res = timed(msm_resident, msm_steps, args.warmup)
+        launches = (be.launch_count - l0) * msm_steps // (msm_steps + args.warmup)
+        clocks2 = samp2.stop() if (rank == 0 and args.workload == "msm") else None
+        ms_e2e = timed(msm_e2e, msm_steps, args.warmup)
+        be.set_profiling(True)
+        acc_ms = []
+        for i in range(5):
+            be.msm_dev(d_sets[i % n_sets].data_ptr(), table, 0, n, d_out.data_ptr())
+            ph = be.last_phase_ms()
+            acc_ms.append([ph[kk] for kk in bpperm_b200.backend.PHASES])
+        be.set_profiling(False)
+        ops = be.last_op_counts()
+        if rank == 0:
+            total_points = n * world
+            phases = np.median(np.array(acc_ms), axis=0)
+            acc_t = float(phases[3]) * 1e-3
+            imads_acc = ops["mixed_adds"] * IMAD_MADD
+            imads_all = imads_acc + ops["full_adds"] * IMAD_ADD + ops["doublings"] * IMAD_DBL
+            ach = imads_acc / acc_t
+            msm = {
+                "metric": "MSM points/sec at 2^20", "value": total_points * msm_steps / (ms_res * 1e-3), "unit": "points/s",
+                "n_gpus": world, "steps": msm_steps, "ms_per_step": ms_res / msm_steps, "scaling": "weak",
+                "config": {"workload": f"ristretto255 vartime MSM, 2^{args.log_n} points per GPU (BASELINE configs[4])",
+                           "points": "from_uniform_bytes(seeded bytes), resident as affine Niels (96 B/pt), no precomputed multiples",
+                           "scalars": "uniform < 2^252, 4 rotating sets",
+                           "l2": "96 MiB table + 32 MiB scalars + 100 MiB sort scratch + 64 MiB buckets > 126 MB L2",
+                           "parallelism": f"points sharded over {world} GPUs, one NCCL all-gather of 128 B/rank" if world > 1 else "single GPU",
+                           "result": bytes(d_out[:32].cpu().numpy().tobytes()).hex()},
+                "e2e": {"value": total_points * msm_steps / (ms_e2e * 1e-3), "unit": "points/s", "h2d_bytes_per_step": n * 32,
+                        "d2h_bytes_per_step": 32, "ms_per_step": ms_e2e / msm_steps,
+                        "note": "scalars pinned-host->HBM and result HBM->host every step; generator table resident"},
+                "gpu_launches": launches,
+                "roofline": {"bound": "imad", "kernel": "k_bucket_accum", "achieved": ach / 1e12, "peak": imad_peak / 1e12,
+                             "unit": "T IMAD.WIDE.U32/s", "frac": ach / imad_peak, "kernel_ms": float(phases[3]),
+                             "point_adds_per_s": ops["mixed_adds"] / acc_t,
+                             "traffic": 1.60e9 if args.log_n == 20 else None,
+                             "traffic_source": "profiles/r1_ncu_full_k_bucket_accum.csv (dram read+write per launch)",
+                             "whole_msm": {"imad_equiv": imads_all, "frac_of_peak": imads_all / (ms_res / msm_steps * 1e-3) / imad_peak},
+                             "phases_ms": dict(zip(bpperm_b200.backend.PHASES, [float(x) for x in phases]))},
+            }
+            if clocks2:
+                msm["clocks"] = clocks2
+            if world == 1 and not args.no_cpu:
+                msm["cpu_baseline"] = cpu_msm_baseline()
+            if line:
+                line["msm"] = msm
+            else:
+                line = dict(msm)
+                line.update({"warmup": args.warmup, "higher_is_better": True, "vs_baseline": None,
+                             "dtype": "u32 (8x32-bit limbs, IMAD.WIDE.U32)", "data": "synthetic"})
+
+    if rank == 0:
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -340,12 +519,13 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="msm", choices=["msm"])
+    ap.add_argument("--workload", default="both", choices=["shuffle", "msm", "both"])
+    ap.add_argument("--batch", type=int, default=4096, help="independent 52-card proofs per GPU per step")
     ap.add_argument("--log-n", type=int, default=20)
-    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

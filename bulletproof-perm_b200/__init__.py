@@ -6,4 +6,4 @@ is not a valid Python identifier).
 from ._lib import BppError, LIB_PATH, SYMBOLS, load  # noqa: F401
 from .backend import Backend, Points, FMT_AFFINE, FMT_COMPRESSED, FMT_DALEK_XYZT, scalars_to_bytes  # noqa: F401
 from .util import Ops  # noqa: F401
-from . import acproof  # noqa: F401
+from . import acproof, weights  # noqa: F401

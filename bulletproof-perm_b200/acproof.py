@@ -115,6 +115,12 @@ class Batch:
         self.be._check(self.be._lib.bpp_acp_batch_download_accept(self._h, out))
         return out.raw
 
+    def time_commit_msm(self, reps: int = 5):
+        ms, madd, add = ctypes.c_float(), ctypes.c_uint64(), ctypes.c_uint64()
+        self.be._check(self.be._lib.bpp_acp_batch_time_commit_msm(self._h, reps, ctypes.byref(ms), ctypes.byref(madd),
+                                                                  ctypes.byref(add)))
+        return ms.value, madd.value, add.value
+
     def free(self):
         if self._h:
             self.be._lib.bpp_acp_batch_free(self._h)

@@ -551,6 +551,37 @@ extern "C" int bpp_acp_batch_download_accept(bpp_acp_batch *b, uint8_t *accept) 
     return BPP_OK;
 }
 
+// Measurement hook: the commitment-shaped fixed-base MSM (A_I: 1 + 2n terms per proof) alone, `reps`
+// launches between CUDA events on the context's stream.  madds = point adds per launch by SURVEY 8(d)'s
+// accounting (terms x windows mixed adds + the block tree reduction's full adds).
+extern "C" int bpp_acp_batch_time_commit_msm(bpp_acp_batch *b, int reps, float *ms_avg, uint64_t *mixed_adds,
+                                             uint64_t *full_adds) {
+    if (!b || reps <= 0 || !ms_avg) return BPP_ERR_INVALID_ARG;
+    bpp_ctx *ctx = b->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    const acp_layout &L = b->lay;
+    fb_shape sh = acp_shape(1);
+    acp_seg(sh, L.alpha, 0, 1, 1); acp_seg(sh, L.aL, 0, 2, L.n); acp_seg(sh, L.aR, 0, 2 + L.n, L.n);
+    int rc = acp_fb(b, sh, b->d_ext8, 8);  // warm-up
+    if (rc) return rc;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, ctx->stream);
+    for (int i = 0; i < reps; i++)
+        if ((rc = acp_fb(b, sh, b->d_ext8, 8))) return rc;
+    cudaEventRecord(e1, ctx->stream);
+    CK(ctx, cudaEventSynchronize(e1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ms_avg = ms / reps;
+    if (mixed_adds) *mixed_adds = (uint64_t)b->B * (1 + 2 * L.n) * b->gens->Wn;
+    if (full_adds) *full_adds = (uint64_t)b->B * (FB_THREADS - 1);
+    return BPP_OK;
+}
+
 // ---- one-call host forms (what a drop-in for create..blinding_values / verify binds) -------------------
 extern "C" int bpp_acproof_prove_batch(bpp_ctx *ctx, const bpp_circuit *cir, const bpp_gens *gens, int mode, size_t count,
                                        const uint8_t *aL, const uint8_t *aR, const uint8_t *aO, const uint8_t *gamma,

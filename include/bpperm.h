@@ -182,6 +182,8 @@ int bpp_acp_batch_download_proofs(bpp_acp_batch *b, uint8_t *proofs_out);
 int bpp_acp_batch_upload_proofs(bpp_acp_batch *b, const uint8_t *proofs, const uint8_t *V /* nullable */);
 int bpp_acp_batch_verify(bpp_acp_batch *b, const uint8_t verifier_seed[32]);
 int bpp_acp_batch_download_accept(bpp_acp_batch *b, uint8_t *accept);
+/* measurement hook: the A_I-shaped fixed-base MSM kernel alone, timed with CUDA events over `reps` launches */
+int bpp_acp_batch_time_commit_msm(bpp_acp_batch *b, int reps, float *ms_avg, uint64_t *mixed_adds, uint64_t *full_adds);
 
 /* ---- measurement helpers --------------------------------------------------------------------- */
 /* IMAD.WIDE.U32 peak microbenchmark: returns wide multiply-adds per second over all SMs. */

@@ -17,8 +17,8 @@ PT = 160
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "c", "dalek_ref.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, "c", f) for f in ("dalek_ref.c", "acproof_ref.c")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(x) for x in srcs):
         subprocess.check_call(["make", "-C", os.path.join(_HERE, "c"), "-B"], stdout=subprocess.DEVNULL)
     return _SO
 
@@ -45,6 +45,12 @@ def lib():
         l.orc_scalar_mul.restype = None
         l.orc_msm_vartime_mt.argtypes = [c.c_char_p, c.c_char_p, c.c_size_t, c.c_int, c.c_char_p]
         l.orc_msm_vartime_mt.restype = None
+        l.orc_acp_prove_verify.argtypes = [c.c_int, c.c_size_t, c.c_size_t, c.c_size_t] + [c.c_char_p] * 16 + [
+            c.c_size_t, c.c_char_p, c.c_int]
+        l.orc_commit_variables.argtypes = [c.c_char_p] * 4 + [c.c_size_t, c.c_char_p]
+        l.orc_commit_variables.restype = None
+        l.orc_scalar_ops_selftest.argtypes = [c.c_char_p] * 4
+        l.orc_scalar_ops_selftest.restype = None
         assert l.orc_point_size() == PT
         _lib = l
     return _lib
@@ -95,3 +101,28 @@ def msm_raw(scalars: bytes, pts: bytes, threads: int = 1) -> bytes:
     else:
         lib().orc_msm_vartime(scalars, pts, n, out)
     return out.raw
+
+
+class AcpInstance:
+    """Dense-matrix instance for orc_acp_prove_verify (the reference's ACEssentials + ACProver shapes)."""
+
+    def __init__(self, n, Q, m, W_L, W_R, W_O, W_V, c_vec, g, h, G, H):
+        """W_* and c_vec: bytes of dense row-major scalar matrices; g, h, G, H: compressed encodings."""
+        self.n, self.Q, self.m = n, Q, m
+        self.W = (W_L, W_R, W_O, W_V)
+        self.c = c_vec
+        self.g, self.h = decompress(g), decompress(h)
+        self.G, self.H = decompress(G), decompress(H)
+
+    def commit(self, v: bytes, gamma: bytes) -> bytes:
+        out = ctypes.create_string_buffer(PT * self.m)
+        lib().orc_commit_variables(self.g, self.h, v, gamma, self.m, out)
+        return out.raw
+
+    def prove_verify(self, aL, aR, aO, gamma, V_pts, seed, mode=1, label=b"test", do_verify=True):
+        """-> (proof_bytes, result) with result 1 = Ok(()), 0 = Err(VerificationError)."""
+        out = ctypes.create_string_buffer(32 * (11 + 2 * self.n))
+        rc = lib().orc_acp_prove_verify(mode, self.n, self.Q, self.m, self.W[0], self.W[1], self.W[2], self.W[3], self.c,
+                                        self.g, self.h, self.G, self.H, aL, aR, aO, gamma, V_pts, seed, label, len(label),
+                                        out, 1 if do_verify else 0)
+        return out.raw, rc
