@@ -430,18 +430,12 @@ def run_ours(args):
         table = be.points_from_uniform(blobs.tobytes())
         d_sets = [torch.from_numpy(s).to(dev) for s in sets]
         h_sets = [torch.from_numpy(s).pin_memory() for s in sets]
-        d_part = torch.zeros(128, dtype=torch.uint8, device=dev)
-        d_gather = torch.zeros(world * 128, dtype=torch.uint8, device=dev)
-        d_out = torch.zeros(160, dtype=torch.uint8, device=dev)
+        smsm = bpperm_b200.parallel.ShardedMsm(be, table, world, dev)
+        d_out = smsm.d_out
         h_out = torch.zeros(32, dtype=torch.uint8).pin_memory()
 
         def msm_once(d_sc):
-            if world == 1:
-                be.msm_dev(d_sc.data_ptr(), table, 0, n, d_out.data_ptr())
-            else:
-                be.msm_partial_dev(d_sc.data_ptr(), table, 0, n, d_part.data_ptr())
-                dist.all_gather_into_tensor(d_gather, d_part)
-                be.points_sum_compress_dev(d_gather.data_ptr(), world, d_out.data_ptr())
+            smsm.run(d_sc)
 
         def msm_resident(i):
             msm_once(d_sets[i % n_sets])

@@ -1,0 +1,53 @@
+"""Multi-GPU plumbing (one process per GPU, torch.distributed): only what SURVEY 8(e) shards.
+
+* proofs are independent units  -> contiguous slices per rank, no data-path collective; accept bytes can be
+  gathered with `gather_bytes` when one rank needs all decisions;
+* a large MSM shards its points  -> every rank reduces its slice to one extended point (128 B), a single
+  all-gather of those partials, then every rank adds them and compresses.
+The collective payloads are tiny (128 B per rank): latency, not bandwidth, is what matters.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, world: int, rank: int):
+    """Contiguous split of n units over `world` ranks: (offset, count); the first n % world ranks get one more."""
+    base, rem = divmod(n, world)
+    cnt = base + (1 if rank < rem else 0)
+    off = rank * base + min(rank, rem)
+    return off, cnt
+
+
+def gather_bytes(local: torch.Tensor, world: int) -> torch.Tensor:
+    """All-gather a fixed-size uint8 tensor; result is [world * len(local)] in rank order."""
+    if world == 1:
+        return local.clone()
+    out = torch.empty(world * local.numel(), dtype=torch.uint8, device=local.device)
+    dist.all_gather_into_tensor(out, local.contiguous())
+    return out
+
+
+class ShardedMsm:
+    """MSM over a point set sharded across ranks.  `table` holds this rank's slice on its GPU."""
+
+    PARTIAL_BYTES = 128
+
+    def __init__(self, backend, table, world: int, device):
+        self.be, self.table, self.world = backend, table, world
+        self.d_part = torch.zeros(self.PARTIAL_BYTES, dtype=torch.uint8, device=device)
+        self.d_all = torch.zeros(world * self.PARTIAL_BYTES, dtype=torch.uint8, device=device)
+        self.d_out = torch.zeros(160, dtype=torch.uint8, device=device)
+
+    def run(self, d_scalars: torch.Tensor) -> torch.Tensor:
+        """d_scalars: this rank's scalars (n_local x 32, uint8, on the GPU).  Returns the device buffer whose
+        first 32 bytes are the compressed result (identical on every rank)."""
+        n = len(self.table)
+        if self.world == 1:
+            self.be.msm_dev(d_scalars.data_ptr(), self.table, 0, n, self.d_out.data_ptr())
+            return self.d_out
+        self.be.msm_partial_dev(d_scalars.data_ptr(), self.table, 0, n, self.d_part.data_ptr())
+        dist.all_gather_into_tensor(self.d_all, self.d_part)
+        self.be.points_sum_compress_dev(self.d_all.data_ptr(), self.world, self.d_out.data_ptr())
+        return self.d_out
