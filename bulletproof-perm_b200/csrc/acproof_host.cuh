@@ -243,7 +243,6 @@ extern "C" int bpp_acp_batch_create(bpp_ctx *ctx, const bpp_circuit *cir, const 
     if (e == cudaSuccess) e = cudaMallocHost((void **)&b->h_pts8, B * 8 * 32);
     if (e == cudaSuccess) e = cudaMallocHost((void **)&b->h_wide, B * 3 * 64);
     if (e == cudaSuccess) e = cudaMallocHost((void **)&b->h_proofs, B * b->proof_len);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_dyn_window_sums, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_W * 8 * 128);
     if (e != cudaSuccess) {
         ctx->last_error = cudaGetErrorString(e);
         bool oom = e == cudaErrorMemoryAllocation;
@@ -377,7 +376,7 @@ static int acp_put_challenges(bpp_acp_batch *b, uint32_t off, uint32_t per) {
 static int acp_challenge_dependent_scalars(bpp_acp_batch *b) {
     bpp_ctx *ctx = b->ctx;
     const acp_layout &L = b->lay;
-    k_acp_pow<<<(b->B + 63) / 64, 64, 0, ctx->stream>>>(L, b->B, b->d_blk);
+    k_acp_pow<<<(b->B + 31) / 32, 64, 0, ctx->stream>>>(L, b->B, b->d_blk);
     LAUNCH_CHECK(ctx);
     acp_csr W{b->cir->d_rowptr, b->cir->d_col, b->cir->d_kind, b->cir->d_coeff, b->cir->rows};
     k_acp_csr<<<dim3((W.rows + 127) / 128, b->B), 128, 0, ctx->stream>>>(W, L, b->d_blk);
@@ -416,13 +415,14 @@ extern "C" int bpp_acp_batch_prove(bpp_acp_batch *b) {
     CK(ctx, cudaMemcpyAsync(b->h_pts8, b->d_pts8, (size_t)B * 256, cudaMemcpyDeviceToHost, s));
     CK(ctx, cudaStreamSynchronize(s));
     // transcripts: dom-sep, A_I, A_O, S -> y, z
-    b->tr.clear();
-    b->tr.reserve(B);
-    for (uint32_t p = 0; p < B; p++) b->tr.emplace_back(b->label.data(), b->label.size());
+    {   // Transcript::new(label) + arithmetic_domain_sep(n) are identical for every proof: hash once, copy
+        bpp_host::Transcript proto(b->label.data(), b->label.size());
+        proto.arithmetic_domain_sep(n);
+        b->tr.assign(B, proto);
+    }
     acp_parallel_for(B, [&](uint32_t p) {
         bpp_host::Transcript &t = b->tr[p];
         const uint8_t *pt = b->h_pts8 + 256 * (size_t)p;
-        t.arithmetic_domain_sep(n);
         t.append_point("A_I", pt);
         t.append_point("A_O", pt + 32);
         t.append_point("S", pt + 64);
@@ -503,11 +503,11 @@ extern "C" int bpp_acp_batch_verify(bpp_acp_batch *b, const uint8_t verifier_see
     CK(ctx, cudaMemcpyAsync(b->d_vseed, verifier_seed, 32, cudaMemcpyHostToDevice, s));
     CK(ctx, cudaStreamSynchronize(s));
     const int mode = b->mode;
-    const std::vector<uint8_t> &label = b->label;
+    bpp_host::Transcript proto(b->label.data(), b->label.size());
+    proto.arithmetic_domain_sep(n);
     acp_parallel_for(B, [&](uint32_t p) {
-        bpp_host::Transcript t(label.data(), label.size());
+        bpp_host::Transcript t = proto;
         const uint8_t *pt = b->h_pts8 + 256 * (size_t)p;
-        t.arithmetic_domain_sep(n);
         t.append_point("A_I", pt);
         t.append_point("A_O", pt + 32);
         t.append_point("S", pt + 64);
@@ -536,7 +536,7 @@ extern "C" int bpp_acp_batch_verify(bpp_acp_batch *b, const uint8_t verifier_see
         acp_seg(sh, L.vg, 0, 0, 2 * n + 2);
         if ((rc = acp_fb(b, sh, b->d_stat, 1))) return rc;
     }
-    k_dyn_window_sums<<<B, DYN_W, DYN_W * 8 * 128, s>>>(b->d_blk, L, b->d_dyn, per, b->d_wsum);
+    k_dyn_window_sums<<<B, DYN_W, 0, s>>>(b->d_blk, L, b->d_dyn, per, b->d_wsum);
     LAUNCH_CHECK(ctx);
     k_dyn_horner_accept<<<(B + 63) / 64, 64, 0, s>>>(L, B, b->d_blk, b->d_wsum, b->d_stat, b->d_bad, b->d_accept);
     LAUNCH_CHECK(ctx);

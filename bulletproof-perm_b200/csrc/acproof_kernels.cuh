@@ -210,11 +210,13 @@ __global__ void __launch_bounds__(128) k_compress_batch(const uint32_t *__restri
 // recurrence (util.rs:139-157), y_n_inv by Montgomery's trick (one inversion instead of the reference's
 // n: circuit_lib.rs:273-275; identical results).  All chains stay in Montgomery form.
 __global__ void __launch_bounds__(64) k_acp_pow(acp_layout lay, uint32_t B, uint32_t *__restrict__ blk) {
-    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    // block = 2 warps over the same 32 proofs: warp 0 runs the y chain + inversion, warp 1 the (longer) z chain
+    const uint32_t p = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int which = threadIdx.x >> 5;
     if (p >= B) return;
     sc one_m;
     sc_const(one_m, SC_R);
-    for (int which = 0; which < 2; which++) {
+    {
         const uint32_t cnt = which ? lay.Q : lay.n;
         uint32_t *dst = ACP_PTR(blk, lay, p, which ? lay.zq : lay.yn);
         sc base = one_m, nxt, ret, s;
@@ -229,6 +231,7 @@ __global__ void __launch_bounds__(64) k_acp_pow(acp_layout lay, uint32_t B, uint
             sc_store(dst + 8 * (size_t)i, s);
         }
     }
+    if (which) return;
     // batch inversion of y_n -> y_n_inv (prefix products kept in the output array)
     uint32_t *yn = ACP_PTR(blk, lay, p, lay.yn), *yi = ACP_PTR(blk, lay, p, lay.yninv);
     sc acc = one_m, v;
@@ -604,11 +607,11 @@ FE_INLINE void dyn_bucket_load(ge_ext &a, const uint4 *bk4, uint32_t b, uint32_t
 __global__ void __launch_bounds__(DYN_W) k_dyn_window_sums(const uint32_t *__restrict__ blk, acp_layout lay,
                                                            const uint32_t *__restrict__ dyn, uint32_t per,
                                                            uint32_t *__restrict__ wsum /* B x 64 x 32 */) {
-    extern __shared__ uint4 bk4[];  // [bucket 8][quad 8][thread DYN_W]: conflict-free 16-byte accesses
+    // 8 buckets per thread in local memory (per-thread interleaved, L1-resident): no shared-memory
+    // occupancy limit, 128 B load + store per mixed add
+    ge_ext bkt[8];
     const uint32_t p = blockIdx.x, w = threadIdx.x;
-    ge_ext id;
-    ge_identity(id);
-    for (int b = 0; b < 8; b++) dyn_bucket_store(bk4, b, w, id);
+    for (int b = 0; b < 8; b++) ge_identity(bkt[b]);
     const uint32_t *scal = ACP_PTR(blk, lay, p, lay.vd);
     const uint32_t *pts = dyn + 24 * (size_t)p * per;
     // digit w of s' = s + 0x0888...8 (carry-free signed recoding, top window unsigned)
@@ -631,17 +634,16 @@ __global__ void __launch_bounds__(DYN_W) k_dyn_window_sums(const uint32_t *__res
         uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
         ge_niels q;
         ge_niels_load(q, pts + 24 * (size_t)k);
-        ge_ext a;
-        dyn_bucket_load(a, bk4, mag - 1, w);
+        ge_ext a = bkt[mag - 1];
         ge_madd(a, a, q, d < 0);
-        dyn_bucket_store(bk4, mag - 1, w, a);
+        bkt[mag - 1] = a;
     }
     ge_ext run, acc, t;
-    dyn_bucket_load(run, bk4, 7, w);
+    run = bkt[7];
     acc = run;
 #pragma unroll 1
     for (int b = 6; b >= 0; b--) {
-        dyn_bucket_load(t, bk4, b, w);
+        t = bkt[b];
         ge_add(run, run, t);
         ge_add(acc, acc, run);
     }
