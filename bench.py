@@ -339,7 +339,19 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
-    imad_peak, _ = be.imad_peak(4096)
+    # Roofline denominator: the IMAD.WIDE.U32 issue limit (32 lanes/clk/SM = one warp instruction per 4 clocks
+    # per sub-partition, confirmed by ncu: fmaheavy cycles per IMAD.WIDE = 4.0) at the maximum SM clock.  The
+    # microbenchmarks measured in this run are reported next to it.
+    imad_peak = be.imad_pipe_limit()
+    imad_probes = {"imad_wide_plain": max(be.pipe_probe(0, 2048) for _ in range(2)),
+                   "imad_wide_carry_chained": max(be.pipe_probe(1, 2048) for _ in range(2)),
+                   "imad_32": max(be.pipe_probe(2, 2048) for _ in range(2)),
+                   "fe_mul_chain_x72": max(be.pipe_probe(4, 512) for _ in range(2)),
+                   "ge_madd_chain_x504": max(be.pipe_probe(5, 256) for _ in range(2))}
+    imad_probes = {k: v / 1e12 for k, v in imad_probes.items()}
+    peak_src = ("IMAD.WIDE.U32 pipe limit = SMs x 32 lanes/clk x max SM clock (4-cycle issue per warp instruction per "
+                "sub-partition; ncu fmaheavy cycles per IMAD.WIDE = 4.0, profiles/r1_imad_rate.md); microbenchmarks of "
+                "this run in imad_probes (T ops/s)")
     peaks, peaks_src = _peaks()
     line = {}
     sampler = ClockSampler(local)
@@ -411,7 +423,7 @@ def run_ours(args):
                 "roofline": {"bound": "imad", "kernel": "k_fb_msm (A_I-shaped commitment MSM, 209 terms x 32 windows per proof)",
                              "achieved": ach / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD.WIDE.U32/s",
                              "frac": ach / imad_peak, "kernel_ms": fb_ms, "point_adds_per_s": (fb_madd + fb_add) / (fb_ms * 1e-3),
-                             "peak_source": "bpp_bench_imad_peak measured in this run (plain IMAD.WIDE.U32, 8 chains/thread, all SMs)",
+                             "peak_source": peak_src, "imad_probes": imad_probes,
                              "traffic": None, "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_peak_source": peaks_src},
                 "clocks": clocks,
             }
@@ -486,7 +498,7 @@ def run_ours(args):
                 "gpu_launches": launches,
                 "roofline": {"bound": "imad", "kernel": "k_bucket_accum", "achieved": ach / 1e12, "peak": imad_peak / 1e12,
                              "unit": "T IMAD.WIDE.U32/s", "frac": ach / imad_peak, "kernel_ms": float(phases[3]),
-                             "point_adds_per_s": ops["mixed_adds"] / acc_t,
+                             "point_adds_per_s": ops["mixed_adds"] / acc_t, "peak_source": peak_src,
                              "traffic": 1.60e9 if args.log_n == 20 else None,
                              "traffic_source": "profiles/r1_ncu_full_k_bucket_accum.csv (dram read+write per launch)",
                              "whole_msm": {"imad_equiv": imads_all, "frac_of_peak": imads_all / (ms_res / msm_steps * 1e-3) / imad_peak},

@@ -95,7 +95,15 @@ class Backend:
         sm, ma, mi, mem = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_size_t()
         self._check(self._lib.bpp_device_info(self._ctx, ctypes.byref(sm), ctypes.byref(ma), ctypes.byref(mi),
                                               ctypes.byref(mem)))
-        return {"sm_count": sm.value, "cc": (ma.value, mi.value), "total_mem": mem.value}
+        return {"sm_count": sm.value, "cc": (ma.value, mi.value), "total_mem": mem.value,
+                "clock_khz": int(self._lib.bpp_device_clock_khz(self._ctx))}
+
+    def imad_pipe_limit(self) -> float:
+        """IMAD.WIDE.U32 issue limit in ops/s: one warp instruction per 4 clocks per SM sub-partition
+        (= 32 lanes/clk/SM; ncu: fmaheavy cycles per IMAD.WIDE = 4.0, profiles/r1_imad_rate.md) at the
+        maximum SM clock.  The roofline denominator for every IMAD-bound kernel."""
+        info = self.device_info()
+        return info["sm_count"] * 32.0 * info["clock_khz"] * 1e3
 
     def set_window_bits(self, c: int):
         self._check(self._lib.bpp_set_window_bits(self._ctx, c))

@@ -167,6 +167,12 @@ extern "C" int bpp_device_info(bpp_ctx *ctx, int *sm, int *maj, int *min, size_t
     if (mem) *mem = ctx->total_mem;
     return BPP_OK;
 }
+extern "C" int bpp_device_clock_khz(bpp_ctx *ctx) {
+    if (!ctx) return 0;
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
+    return khz;
+}
 extern "C" int bpp_set_window_bits(bpp_ctx *ctx, int c) {
     if (!ctx || (c != 0 && (c < 4 || c > 16))) return BPP_ERR_INVALID_ARG;
     ctx->forced_c = c;
@@ -526,9 +532,10 @@ extern "C" int bpp_bench_imad_peak(bpp_ctx *ctx, int iters, double *ops_per_sec,
     return BPP_OK;
 }
 
-// mode 0: plain IMAD.WIDE.U32 (64-bit accumulate); 1: carry-chained IMAD.WIDE.U32; 2: 32-bit IMAD; 3: IADD3.X chains
+// mode 0: plain IMAD.WIDE.U32 (64-bit accumulate); 1: carry-chained IMAD.WIDE.U32; 2: 32-bit IMAD; 3: IADD3.X chains;
+// 4: fe_mul chains (counted as 72 IMAD.WIDE each); 5: ge_madd chains (504 each)
 extern "C" int bpp_bench_pipe_probe(bpp_ctx *ctx, int mode, int iters, double *ops_per_sec) {
-    if (!ctx || iters <= 0 || mode < 0 || mode > 3 || !ops_per_sec) return BPP_ERR_INVALID_ARG;
+    if (!ctx || iters <= 0 || mode < 0 || mode > 5 || !ops_per_sec) return BPP_ERR_INVALID_ARG;
     if (mode == 0) return bpp_bench_imad_peak(ctx, iters, ops_per_sec, nullptr);
     CK(ctx, cudaSetDevice(ctx->device));
     unsigned long long *d = (unsigned long long *)ctx->d_flag;
@@ -547,8 +554,8 @@ extern "C" int bpp_bench_pipe_probe(bpp_ctx *ctx, int mode, int iters, double *o
     cudaEventElapsedTime(&ms, a, b);
     cudaEventDestroy(a);
     cudaEventDestroy(b);
-    double per_u = mode == 1 ? 8.0 : 16.0;
-    *ops_per_sec = (double)blocks * 256.0 * (double)iters * 8.0 * per_u / (ms * 1e-3);
+    double per_iter = mode == 1 ? 64.0 : mode == 4 ? 144.0 : mode == 5 ? 504.0 : 128.0;
+    *ops_per_sec = (double)blocks * 256.0 * (double)iters * per_iter / (ms * 1e-3);
     return BPP_OK;
 }
 

@@ -574,75 +574,114 @@ __global__ void k_niels_compress(const uint32_t *__restrict__ niels, uint32_t n,
     ge_compress(out + 32 * (size_t)i, p);
 }
 
-// ---- IMAD.WIDE.U32 peak microbenchmark ---------------------------------------------------------
-// 8 independent 64-bit accumulate chains per thread: acc_k = a_k * b + acc_k.
+// ---- integer-pipe microbenchmarks --------------------------------------------------------------
+// Every multiply takes one operand from ANOTHER chain's previous result, so ptxas can neither hoist
+// the product out of the loop nor strength-reduce repeated accumulation into adds (an earlier version
+// with loop-invariant operands was rewritten by ptxas into one IMAD.WIDE + IADD3 pairs and measured the
+// alu pipe instead; the SASS of these kernels is checked in tests/test_cabi.py::test_probe_sass).
+//   mode 0: plain IMAD.WIDE.U32 with 64-bit addend       (8 chains/thread, 128 per loop trip)
+//   mode 1: carry-chained IMAD.WIDE.U32 (mad.lo.cc/madc.hi.cc pairs: the saturated multiplier's form)
+//   mode 2: 32-bit IMAD                                   mode 3: IADD3 carry chains
+//   mode 4: fe_mul chains (2 per thread; 72 IMAD.WIDE-equivalents each)
+//   mode 5: ge_madd chains (1 per thread; 504 IMAD.WIDE-equivalents each)
 __global__ void __launch_bounds__(256) k_imad_peak(uint32_t seed, int iters, unsigned long long *out) {
-    uint32_t a0 = seed + threadIdx.x, a1 = a0 * 3u + 1u, a2 = a0 * 5u + 2u, a3 = a0 * 7u + 3u;
-    uint32_t a4 = a0 * 11u + 4u, a5 = a0 * 13u + 5u, a6 = a0 * 17u + 6u, a7 = a0 * 19u + 7u;
-    uint32_t b = blockIdx.x * 2654435761u + 12345u;
-    unsigned long long c0 = 1, c1 = 2, c2 = 3, c3 = 4, c4 = 5, c5 = 6, c6 = 7, c7 = 8;
+    uint32_t a[16], b[8];
+    unsigned long long c[8];
+#pragma unroll
+    for (int u = 0; u < 16; u++) a[u] = (seed + threadIdx.x) * (2u * u + 3u) + u;
+#pragma unroll
+    for (int k = 0; k < 8; k++) c[k] = blockIdx.x + k + 1;
 #pragma unroll 1
     for (int it = 0; it < iters; it++) {
 #pragma unroll
-        for (int u = 0; u < 16; u++) {
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c0) : "r"(a0), "r"(b));
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c1) : "r"(a1), "r"(b));
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c2) : "r"(a2), "r"(b));
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c3) : "r"(a3), "r"(b));
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c4) : "r"(a4), "r"(b));
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c5) : "r"(a5), "r"(b));
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c6) : "r"(a6), "r"(b));
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c7) : "r"(a7), "r"(b));
-        }
+        for (int k = 0; k < 8; k++) b[k] = (uint32_t)(c[(k + 1) & 7] >> 7) | 1u;  // data dependent, once per trip
+#pragma unroll
+        for (int u = 0; u < 16; u++)
+#pragma unroll
+            for (int k = 0; k < 8; k++) c[k] += (unsigned long long)a[u] * b[k];  // IMAD.WIDE.U32 Rc, Ra, Rb, Rc
     }
-    unsigned long long r = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
-    if (r == 0x1234567812345678ull) out[0] = r;  // never true in practice; keeps the chains alive
+    unsigned long long r = c[0] ^ c[1] ^ c[2] ^ c[3] ^ c[4] ^ c[5] ^ c[6] ^ c[7];
+    if (r == 0x1234567812345678ull) out[0] = r;  // practically never; keeps the chains alive
 }
 
-// Variants of the same microbenchmark for the instruction forms the multiplier can be built from:
-//   mode 1: carry chains (mad.lo.cc/madc.hi.cc pairs -> IMAD.WIDE.U32 with carry-out / .X carry-in)
-//   mode 2: 32-bit IMAD lo (mad.lo.u32)          mode 3: IADD3 carry chains (add.cc/addc)
 __global__ void __launch_bounds__(256) k_pipe_probe(int mode, uint32_t seed, int iters, unsigned long long *out) {
     uint32_t a0 = seed + threadIdx.x, a1 = a0 * 3u + 1u, a2 = a0 * 5u + 2u, a3 = a0 * 7u + 3u;
-    uint32_t b = blockIdx.x * 2654435761u + 12345u;
-    uint32_t c0 = 1, c1 = 2, c2 = 3, c3 = 4, c4 = 5, c5 = 6, c6 = 7, c7 = 8, c8 = 0;
+    uint32_t c0 = 1 + blockIdx.x, c1 = 2, c2 = 3, c3 = 4, c4 = 5, c5 = 6, c6 = 7, c7 = 8, c8 = 0;
     uint32_t d0 = 9, d1 = 10, d2 = 11, d3 = 12, d4 = 13, d5 = 14, d6 = 15, d7 = 16, d8 = 0;
+    if (mode == 1) {
 #pragma unroll 1
-    for (int it = 0; it < iters; it++) {
+        for (int it = 0; it < iters; it++) {
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-            if (mode == 1) {  // 2 independent chains of 4 wide multiply-adds each (8 per u)
-                fe_mad4(c0, c1, c2, c3, c4, c5, c6, c7, c8, a0, a1, a2, a3, b);
-                fe_mad4(d0, d1, d2, d3, d4, d5, d6, d7, d8, a1, a2, a3, a0, b);
-            } else if (mode == 2) {  // 16 independent 32-bit multiply-adds per u
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c0) : "r"(a0), "r"(b));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c1) : "r"(a1), "r"(b));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c2) : "r"(a2), "r"(b));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c3) : "r"(a3), "r"(b));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c4) : "r"(a0), "r"(b));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c5) : "r"(a1), "r"(b));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c6) : "r"(a2), "r"(b));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c7) : "r"(a3), "r"(b));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(d0) : "r"(a0), "r"(b));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(d1) : "r"(a1), "r"(b));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(d2) : "r"(a2), "r"(b));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(d3) : "r"(a3), "r"(b));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(d4) : "r"(a0), "r"(b));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(d5) : "r"(a1), "r"(b));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(d6) : "r"(a2), "r"(b));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(d7) : "r"(a3), "r"(b));
-            } else {  // 2 independent add-with-carry chains of 8 (16 adds per u)
-                asm volatile("add.cc.u32 %0,%0,%8; addc.cc.u32 %1,%1,%8; addc.cc.u32 %2,%2,%8; addc.cc.u32 %3,%3,%8;"
-                             "addc.cc.u32 %4,%4,%8; addc.cc.u32 %5,%5,%8; addc.cc.u32 %6,%6,%8; addc.u32 %7,%7,%8;"
-                             : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3), "+r"(c4), "+r"(c5), "+r"(c6), "+r"(c7) : "r"(b));
-                asm volatile("add.cc.u32 %0,%0,%8; addc.cc.u32 %1,%1,%8; addc.cc.u32 %2,%2,%8; addc.cc.u32 %3,%3,%8;"
-                             "addc.cc.u32 %4,%4,%8; addc.cc.u32 %5,%5,%8; addc.cc.u32 %6,%6,%8; addc.u32 %7,%7,%8;"
-                             : "+r"(d0), "+r"(d1), "+r"(d2), "+r"(d3), "+r"(d4), "+r"(d5), "+r"(d6), "+r"(d7) : "r"(a0));
+            for (int u = 0; u < 8; u++) {  // 2 chains of 4 carry-linked wide multiply-adds (8 per u)
+                fe_mad4(c0, c1, c2, c3, c4, c5, c6, c7, c8, a0, a1, a2, a3, d0 ^ d7);
+                fe_mad4(d0, d1, d2, d3, d4, d5, d6, d7, d8, a1, a2, a3, a0, c0 ^ c7);
             }
         }
+    } else if (mode == 2) {
+#pragma unroll 1
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {  // 16 32-bit multiply-adds per u, multiplier from the other half
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c0) : "r"(a0), "r"(d0));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c1) : "r"(a1), "r"(d1));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c2) : "r"(a2), "r"(d2));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c3) : "r"(a3), "r"(d3));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c4) : "r"(a0), "r"(d4));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c5) : "r"(a1), "r"(d5));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c6) : "r"(a2), "r"(d6));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c7) : "r"(a3), "r"(d7));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(d0) : "r"(a0), "r"(c0));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(d1) : "r"(a1), "r"(c1));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(d2) : "r"(a2), "r"(c2));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(d3) : "r"(a3), "r"(c3));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(d4) : "r"(a0), "r"(c4));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(d5) : "r"(a1), "r"(c5));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(d6) : "r"(a2), "r"(c6));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(d7) : "r"(a3), "r"(c7));
+            }
+        }
+    } else if (mode == 3) {
+#pragma unroll 1
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {  // 2 add-with-carry chains of 8 (16 adds per u), cross-fed
+                asm volatile("add.cc.u32 %0,%0,%8; addc.cc.u32 %1,%1,%8; addc.cc.u32 %2,%2,%8; addc.cc.u32 %3,%3,%8;"
+                             "addc.cc.u32 %4,%4,%8; addc.cc.u32 %5,%5,%8; addc.cc.u32 %6,%6,%8; addc.u32 %7,%7,%8;"
+                             : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3), "+r"(c4), "+r"(c5), "+r"(c6), "+r"(c7) : "r"(d7));
+                asm volatile("add.cc.u32 %0,%0,%8; addc.cc.u32 %1,%1,%8; addc.cc.u32 %2,%2,%8; addc.cc.u32 %3,%3,%8;"
+                             "addc.cc.u32 %4,%4,%8; addc.cc.u32 %5,%5,%8; addc.cc.u32 %6,%6,%8; addc.u32 %7,%7,%8;"
+                             : "+r"(d0), "+r"(d1), "+r"(d2), "+r"(d3), "+r"(d4), "+r"(d5), "+r"(d6), "+r"(d7) : "r"(c7));
+            }
+        }
+    } else if (mode == 4) {
+        fe x, y;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            x.v[i] = a0 * (2u * i + 1u) + c0;
+            y.v[i] = a1 * (2u * i + 3u) + i;
+        }
+#pragma unroll 1
+        for (int it = 0; it < iters; it++) {  // 2 multiplications per trip
+            fe_mul(x, x, y);
+            fe_mul(y, y, x);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) c1 ^= x.v[i] ^ y.v[i];
+    } else {
+        ge_ext p;
+        ge_niels q;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            p.X.v[i] = a0 + i; p.Y.v[i] = a1 + c0 + i; p.Z.v[i] = a2 + i; p.T.v[i] = a3 + i;
+            q.yp.v[i] = a0 * 3u + i; q.ym.v[i] = a1 * 5u + i; q.t2d.v[i] = a2 * 7u + i;
+        }
+#pragma unroll 1
+        for (int it = 0; it < iters; it++) ge_madd(p, p, q, (it & 1) != 0);
+#pragma unroll
+        for (int i = 0; i < 8; i++) c1 ^= p.X.v[i] ^ p.Y.v[i] ^ p.Z.v[i] ^ p.T.v[i];
     }
     uint32_t r = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7 ^ c8 ^ d0 ^ d1 ^ d2 ^ d3 ^ d4 ^ d5 ^ d6 ^ d7 ^ d8;
-    if (r == 0x12345678u && iters < 0) out[0] = r;
+    if (r == 0x12345678u) out[0] = r;  // practically never; keeps every chain alive
 }
 
 // ---- element-wise test kernels -------------------------------------------------------------------

@@ -62,6 +62,8 @@ const char *bpp_last_error(bpp_ctx *ctx);
 /* Number of kernels this context has launched since creation (bench.py's `gpu_launches`). */
 uint64_t bpp_launch_count(bpp_ctx *ctx);
 int bpp_device_info(bpp_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, size_t *total_mem);
+/* Maximum SM clock in kHz (cudaDevAttrClockRate); the IMAD.WIDE pipe limit is sm_count * 32 lanes * this. */
+int bpp_device_clock_khz(bpp_ctx *ctx);
 
 /* ---- points: upload once, reuse across MSMs (generators are static in the protocol) -------- */
 /* Converts n points to the device layout (affine Niels, 96 B/point).  For BPP_FMT_COMPRESSED an
@@ -189,7 +191,9 @@ int bpp_acp_batch_time_commit_msm(bpp_acp_batch *b, int reps, float *ms_avg, uin
 /* IMAD.WIDE.U32 peak microbenchmark: returns wide multiply-adds per second over all SMs. */
 int bpp_bench_imad_peak(bpp_ctx *ctx, int iters, double *ops_per_sec, double *ms);
 /* Same harness for the other instruction forms a multiplier can be built from.  mode 0: plain IMAD.WIDE.U32
- * with a 64-bit addend; 1: carry-chained IMAD.WIDE.U32 (mad.lo.cc/madc.hi.cc); 2: 32-bit IMAD; 3: IADD3.X chains. */
+ * with a 64-bit addend; 1: carry-chained IMAD.WIDE.U32 (mad.lo.cc/madc.hi.cc); 2: 32-bit IMAD; 3: IADD3.X chains;
+ * 4: dependent field multiplications (reported as 72 wide multiply-adds each); 5: dependent mixed point adds (504 each).
+ * Every multiply has a data-dependent operand so the assembler cannot strength-reduce the loop. */
 int bpp_bench_pipe_probe(bpp_ctx *ctx, int mode, int iters, double *ops_per_sec);
 /* Per-phase device time (ms) of the last bpp_msm_* call when profiling is enabled. */
 enum { BPP_PHASE_RECODE = 0, BPP_PHASE_SCAN, BPP_PHASE_SCATTER, BPP_PHASE_ACCUMULATE, BPP_PHASE_REDUCE,
