@@ -11,8 +11,8 @@ from typing import Sequence
 
 from .backend import Backend, scalars_to_bytes
 
-MODE_REFERENCE, MODE_REFERENCE_FIXED = 0, 1
-_MODES = {"reference": 0, "reference-fixed": 1, 0: 0, 1: 1}
+MODE_REFERENCE, MODE_REFERENCE_FIXED, MODE_FIXED = 0, 1, 2
+_MODES = {"reference": 0, "reference-fixed": 1, "fixed": 2, 0: 0, 1: 1, 2: 2}
 
 
 def _sc32(x) -> bytes:
@@ -69,7 +69,18 @@ class Generators:
             self._h = None
 
 
-def proof_len(n: int) -> int:
+def next_pow2(n: int) -> int:
+    p = 1
+    while p < n:
+        p *= 2
+    return p
+
+
+def proof_len(n: int, mode="reference-fixed") -> int:
+    """Bytes per proof: modes "reference"/"reference-fixed" carry l and r in the clear (circuit_lib.rs:464-468),
+    "fixed" replaces them by the inner-product proof (2 lg n' points + 2 scalars)."""
+    if _MODES[mode] == 2:
+        return 32 * (13 + 2 * (next_pow2(n).bit_length() - 1))
     return 32 * (11 + 2 * n)
 
 
@@ -83,7 +94,7 @@ class Batch:
         backend._check(backend._lib.bpp_acp_batch_create(backend._ctx, circuit._h, gens._h, self.mode, count, label,
                                                           len(label), ctypes.byref(h)))
         self._h = h
-        self.proof_len = proof_len(circuit.n)
+        self.proof_len = proof_len(circuit.n, self.mode)
 
     def upload_witness(self, aL: bytes, aR: bytes, aO: bytes, gamma: bytes, seeds: bytes):
         n, m, B = self.cir.n, self.cir.m, self.count
@@ -134,7 +145,7 @@ class Batch:
 
 
 def prove_batch(backend, circuit, gens, aL, aR, aO, gamma, seeds, count, mode="reference-fixed", label=b"test") -> bytes:
-    out = ctypes.create_string_buffer(proof_len(circuit.n) * count)
+    out = ctypes.create_string_buffer(proof_len(circuit.n, mode) * count)
     backend._check(backend._lib.bpp_acproof_prove_batch(backend._ctx, circuit._h, gens._h, _MODES[mode], count, aL, aR, aO,
                                                          gamma, seeds, label, len(label), out))
     return out.raw

@@ -6,6 +6,7 @@
 #include <thread>
 
 #include "acproof_kernels.cuh"
+#include "ipa_kernels.cuh"
 #include "host_merlin.hpp"
 
 struct bpp_circuit {
@@ -33,24 +34,36 @@ struct bpp_acp_batch {
              *d_wsum = nullptr, *d_stat = nullptr, *d_bad = nullptr, *d_vext = nullptr, *d_vseed = nullptr;
     uint8_t *d_pts8 = nullptr, *d_proofs = nullptr, *d_V = nullptr, *d_accept = nullptr;
     uint8_t *h_pts8 = nullptr, *h_wide = nullptr, *h_proofs = nullptr;  // pinned
+    // `fixed` mode: L_j/R_j encodings (B x 2 lg x 32), the three transcript scalars (B x 3 x 32), fb split scratch
+    uint8_t *d_lr = nullptr, *h_lr = nullptr, *h_tx3 = nullptr;
+    uint32_t *d_tx3 = nullptr, *d_lrext = nullptr, *d_part = nullptr;
+    uint32_t fb_splits = 1;
     std::vector<bpp_host::Transcript> tr;
 };
 
-static acp_layout acp_make_layout(uint32_t n, uint32_t Q, uint32_t m) {
+static uint32_t acp_next_pow2(uint32_t n) { uint32_t p = 1; while (p < n) p <<= 1; return p; }
+static uint32_t acp_log2(uint32_t p) { uint32_t l = 0; while ((1u << l) < p) l++; return l; }
+
+static acp_layout acp_make_layout(uint32_t n_, uint32_t Q, uint32_t m, int mode) {
     acp_layout L;
     uint32_t o = 0;
     auto take = [&](uint32_t cnt) { uint32_t r = o; o += cnt; return r; };
-    L.n = n; L.Q = Q; L.m = m;
+    L.n = n_; L.Q = Q; L.m = m;
+    L.np = mode == 2 ? acp_next_pow2(n_) : n_;
+    L.lg = mode == 2 ? acp_log2(L.np) : 0;
+    const uint32_t n = L.n, np = L.np;   // only y^n, y^-n, l, r and the verifier's G/H scalars have the padded length
     L.aL = take(n); L.aR = take(n); L.aO = take(n); L.gamma = take(m);
     L.alpha = take(1); L.beta = take(1); L.ro = take(1); L.sl = take(n); L.sr = take(n); L.tau = take(5);
     L.y = take(1); L.z = take(1); L.x = take(1); L.w = take(1);
-    L.yn = take(n); L.yninv = take(n); L.zq = take(Q);
+    L.yn = take(np); L.yninv = take(np); L.zq = take(Q);
     L.zWL = take(n); L.zWR = take(n); L.zWO = take(n); L.zWV = take(m); L.zc = take(1);
     L.lin = take(n); L.l1 = take(n); L.r0 = take(n); L.r1 = take(n); L.r3 = take(n);
     L.dots = take(12); L.sigma = L.dots + 9;
     L.tc = take(6); L.tsel = take(5);
-    L.l = take(n); L.r = take(n); L.that = take(1); L.taux = take(1); L.mu = take(1);
-    L.vg = take(1); L.vh = take(1); L.vG = take(n); L.vH = take(n); L.vd = take(m + 8);
+    L.l = take(np); L.r = take(np); L.that = take(1); L.taux = take(1); L.mu = take(1);
+    L.vg = take(1); L.vh = take(1); L.vG = take(np); L.vH = take(np); L.vd = take(m + 8 + 2 * L.lg);
+    L.wq = take(1); L.u = take(L.lg); L.uinv = take(L.lg); L.cl = take(2); L.pa = take(1); L.pb = take(1);
+    L.ptab = take(mode == 2 ? 3 * IPA_MAX_LG : 0);
     L.stride = (o + 3) & ~3u;
     return L;
 }
@@ -194,41 +207,64 @@ extern "C" void bpp_gens_free(bpp_ctx *ctx, bpp_gens *g) {
 
 // ---- batch object ----------------------------------------------------------------------------------
 extern "C" size_t bpp_acproof_proof_len(size_t n) { return 32 * (11 + 2 * n); }
+// mode 2 (`fixed`): 8 points | t_hat, tau_x, mu | (L_j, R_j) x lg | a, b
+extern "C" size_t bpp_acproof_proof_len_mode(size_t n, int mode) {
+    if (mode != 2) return bpp_acproof_proof_len(n);
+    return 32 * (13 + 2 * (size_t)acp_log2(acp_next_pow2((uint32_t)n)));
+}
 
 extern "C" void bpp_acp_batch_free(bpp_acp_batch *b) {
     if (!b) return;
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
     void *dev[] = {b->d_blk, b->d_seeds, b->d_wide, b->d_ext8, b->d_dyn, b->d_wsum, b->d_stat, b->d_bad, b->d_vext, b->d_vseed,
-                   b->d_pts8, b->d_proofs, b->d_V, b->d_accept};
+                   b->d_pts8, b->d_proofs, b->d_V, b->d_accept, b->d_lr, b->d_tx3, b->d_lrext, b->d_part};
     for (void *p : dev)
         if (p) cudaFree(p);
     if (b->h_pts8) cudaFreeHost(b->h_pts8);
     if (b->h_wide) cudaFreeHost(b->h_wide);
     if (b->h_proofs) cudaFreeHost(b->h_proofs);
+    if (b->h_lr) cudaFreeHost(b->h_lr);
+    if (b->h_tx3) cudaFreeHost(b->h_tx3);
     delete b;
 }
 
 // mode 0 = "reference" (bit-for-bit what circuit_lib.rs does, defects included; verification never
-// accepts), mode 1 = "reference-fixed" (SURVEY A.3).  label = the Transcript::new label (lib.rs:172: b"test").
+// accepts), mode 1 = "reference-fixed" (SURVEY A.3), mode 2 = "fixed" (standard powers + inner-product argument,
+// ipa_kernels.cuh; needs next_pow2(n) generators).  label = the Transcript::new label (lib.rs:172: b"test").
 extern "C" int bpp_acp_batch_create(bpp_ctx *ctx, const bpp_circuit *cir, const bpp_gens *gens, int mode, size_t count,
                                     const uint8_t *label, size_t label_len, bpp_acp_batch **out) {
-    if (!ctx || !cir || !gens || !out || count == 0 || count > (1u << 24) || (mode != 0 && mode != 1) ||
+    if (!ctx || !cir || !gens || !out || count == 0 || count > (1u << 24) || mode < 0 || mode > 2 ||
         (!label && label_len))
         return BPP_ERR_INVALID_ARG;
-    if (gens->n != cir->n) return BPP_ERR_LENGTH_MISMATCH;  // circuit_lib.rs:154-160 assert_eq!
+    if (gens->n != (mode == 2 ? acp_next_pow2(cir->n) : cir->n)) return BPP_ERR_LENGTH_MISMATCH;  // circuit_lib.rs:154-160 assert_eq!
+    if (mode == 2 && acp_log2(acp_next_pow2(cir->n)) > IPA_MAX_LG) return BPP_ERR_INVALID_ARG;
     *out = nullptr;
     CK(ctx, cudaSetDevice(ctx->device));
     bpp_acp_batch *b = new bpp_acp_batch();
     b->ctx = ctx; b->cir = cir; b->gens = gens; b->mode = mode; b->B = (uint32_t)count;
-    b->lay = acp_make_layout(cir->n, cir->Q, cir->m);
-    b->proof_len = (uint32_t)bpp_acproof_proof_len(cir->n);
+    b->lay = acp_make_layout(cir->n, cir->Q, cir->m, mode);
+    b->proof_len = (uint32_t)bpp_acproof_proof_len_mode(cir->n, mode);
     b->label.assign(label, label + label_len);
-    const size_t B = count, per = cir->m + 8;
+    const size_t B = count, lg = b->lay.lg, per = cir->m + 8 + 2 * lg, nch = 4 + lg;
+    {   // small batches of large circuits: split each fixed-base MSM over several blocks (k_fb_sum_splits adds them)
+        const size_t terms = 2 * (size_t)b->lay.np + 2, want = 4 * (size_t)ctx->sm_count;
+        size_t sp = B >= want ? 1 : (want + B - 1) / B;
+        const size_t max_sp = (terms * 8 + FB_THREADS - 1) / FB_THREADS;   // at least one work item per thread
+        if (sp > max_sp) sp = max_sp;
+        if (sp > 256) sp = 256;
+        b->fb_splits = (uint32_t)(sp ? sp : 1);
+    }
     cudaError_t e = cudaMalloc((void **)&b->d_blk, B * b->lay.stride * 32);
     if (e == cudaSuccess) e = cudaMemsetAsync(b->d_blk, 0, B * b->lay.stride * 32, ctx->stream);
     if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_seeds, B * 32);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_wide, B * 3 * 64);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_wide, B * nch * 64);
+    if (e == cudaSuccess && b->fb_splits > 1) e = cudaMalloc((void **)&b->d_part, B * 8 * b->fb_splits * 128);
+    if (e == cudaSuccess && lg) e = cudaMalloc((void **)&b->d_lr, B * 2 * lg * 32);
+    if (e == cudaSuccess && lg) e = cudaMalloc((void **)&b->d_lrext, B * 2 * lg * 128);
+    if (e == cudaSuccess && lg) e = cudaMalloc((void **)&b->d_tx3, B * 3 * 32);
+    if (e == cudaSuccess && lg) e = cudaMallocHost((void **)&b->h_lr, B * 2 * lg * 32);
+    if (e == cudaSuccess && lg) e = cudaMallocHost((void **)&b->h_tx3, B * 3 * 32);
     if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_ext8, B * 8 * 128);
     if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_dyn, B * per * 96);
     if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_wsum, B * DYN_W * 128);
@@ -241,7 +277,7 @@ extern "C" int bpp_acp_batch_create(bpp_ctx *ctx, const bpp_circuit *cir, const 
     if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_vext, B * cir->m * 128);
     if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_accept, B);
     if (e == cudaSuccess) e = cudaMallocHost((void **)&b->h_pts8, B * 8 * 32);
-    if (e == cudaSuccess) e = cudaMallocHost((void **)&b->h_wide, B * 3 * 64);
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&b->h_wide, B * nch * 64);
     if (e == cudaSuccess) e = cudaMallocHost((void **)&b->h_proofs, B * b->proof_len);
     if (e != cudaSuccess) {
         ctx->last_error = cudaGetErrorString(e);
@@ -285,6 +321,22 @@ static int acp_fb(bpp_acp_batch *b, const fb_shape &sh, uint32_t *dst, uint32_t 
     bpp_ctx *ctx = b->ctx;
     fb_shape s = sh;
     s.outs = pitch;  // k_fb_msm addresses out_ext + 32 * (p * outs + o)
+    // few (proof, output) pairs: split the terms of each MSM over several blocks so the launch fills the GPU
+    uint32_t terms = 0;
+    for (uint32_t k = 0; k < sh.nseg; k++) terms += sh.cnt[k];
+    const uint64_t blocks = (uint64_t)b->B * sh.outs, want = 4ull * ctx->sm_count;
+    const uint64_t items = (uint64_t)terms * ((b->gens->Wn + FB_GROUP - 1) / FB_GROUP);
+    uint64_t sp = blocks >= want ? 1 : (want + blocks - 1) / blocks;
+    if (sp > (items + FB_THREADS - 1) / FB_THREADS) sp = (items + FB_THREADS - 1) / FB_THREADS;
+    if (sp > b->fb_splits || sh.outs > 8) sp = sh.outs > 8 ? 1 : b->fb_splits;
+    if (sp > 1) {
+        k_fb_msm<<<dim3(b->B, sh.outs, (uint32_t)sp), FB_THREADS, 0, ctx->stream>>>(b->d_blk, b->lay, s, b->gens->d_table,
+                                                                                   b->gens->c, b->gens->Wn, b->gens->kc, b->d_part);
+        LAUNCH_CHECK(ctx);
+        k_fb_sum_splits<<<dim3(b->B, sh.outs), 32, 0, ctx->stream>>>(b->d_part, sh.outs, (uint32_t)sp, pitch, dst);
+        LAUNCH_CHECK(ctx);
+        return BPP_OK;
+    }
     k_fb_msm<<<dim3(b->B, sh.outs), FB_THREADS, 0, ctx->stream>>>(b->d_blk, b->lay, s, b->gens->d_table, b->gens->c,
                                                                   b->gens->Wn, b->gens->kc, dst);
     LAUNCH_CHECK(ctx);
@@ -376,12 +428,77 @@ static int acp_put_challenges(bpp_acp_batch *b, uint32_t off, uint32_t per) {
 static int acp_challenge_dependent_scalars(bpp_acp_batch *b) {
     bpp_ctx *ctx = b->ctx;
     const acp_layout &L = b->lay;
-    k_acp_pow<<<(b->B + 31) / 32, 64, 0, ctx->stream>>>(L, b->B, b->d_blk);
-    LAUNCH_CHECK(ctx);
+    if (b->mode == 2) {   // standard powers y^i, y^-i (i < n'), z^(q+1)
+        k_pow_table<<<(b->B + 63) / 64, 64, 0, ctx->stream>>>(L, b->B, b->d_blk);
+        LAUNCH_CHECK(ctx);
+        k_pow_fill<<<dim3((2 * L.np + L.Q + 127) / 128, b->B), 128, 0, ctx->stream>>>(L, b->d_blk);
+        LAUNCH_CHECK(ctx);
+    } else {
+        k_acp_pow<<<(b->B + 31) / 32, 64, 0, ctx->stream>>>(L, b->B, b->d_blk);
+        LAUNCH_CHECK(ctx);
+    }
     acp_csr W{b->cir->d_rowptr, b->cir->d_col, b->cir->d_kind, b->cir->d_coeff, b->cir->rows};
     k_acp_csr<<<dim3((W.rows + 127) / 128, b->B), 128, 0, ctx->stream>>>(W, L, b->d_blk);
     LAUNCH_CHECK(ctx);
     k_acp_vec1<<<dim3((L.n + 127) / 128, b->B), 128, 0, ctx->stream>>>(L, b->d_blk);
+    LAUNCH_CHECK(ctx);
+    return BPP_OK;
+}
+
+// `fixed` mode tail of the prover (oracle/ipa.py prove(), bulletproofs inner_product_proof.rs create()):
+// append t_x, t_x_blinding, e_blinding -> w; lg rounds of (L_j, R_j) -> u_j with a, b folded in place.
+static int acp_prove_ipa(bpp_acp_batch *b) {
+    bpp_ctx *ctx = b->ctx;
+    const acp_layout &L = b->lay;
+    const uint32_t B = b->B, np = L.np, lg = L.lg;
+    cudaStream_t s = ctx->stream;
+    int rc;
+    // t_hat, tau_x, mu are contiguous in the proof block
+    CK(ctx, cudaMemcpy2DAsync(b->h_tx3, 96, (const uint8_t *)b->d_blk + 32 * (size_t)L.that, (size_t)L.stride * 32, 96, B,
+                              cudaMemcpyDeviceToHost, s));
+    CK(ctx, cudaStreamSynchronize(s));
+    acp_parallel_for(B, [&](uint32_t p) {
+        bpp_host::Transcript &t = b->tr[p];
+        const uint8_t *sc3 = b->h_tx3 + 96 * (size_t)p;
+        t.append_scalar("t_x", sc3);
+        t.append_scalar("t_x_blinding", sc3 + 32);
+        t.append_scalar("e_blinding", sc3 + 64);
+        t.challenge_wide("w", b->h_wide + 64 * (size_t)p);
+        t.append_message("dom-sep", (const uint8_t *)"ipp v1", 6);
+        t.append_u64("n", np);
+    });
+    if ((rc = acp_put_challenges(b, L.wq, 1))) return rc;
+    const uint32_t gH = 2 + b->gens->n;
+    for (uint32_t j = 0; j < lg; j++) {
+        const uint32_t nj = np >> j, h = nj >> 1;
+        k_ipa_dots<<<dim3(2, B), 128, 0, s>>>(L, h, b->d_blk);
+        LAUNCH_CHECK(ctx);
+        k_ipa_prep<<<dim3((np + 127) / 128, B), 128, 0, s>>>(L, j, b->d_blk);
+        LAUNCH_CHECK(ctx);
+        fb_shape sh = acp_shape(2);
+        sh.sel_period = nj;
+        acp_seg(sh, L.vG, 0, 2, np);  sh.sel[0] = 1;    // <a_L s, G_R> for L, <a_R s, G_L> for R
+        acp_seg(sh, L.vH, 0, gH, np); sh.sel[1] = 2;    // <b_R s^-1 y^-n, H_L> for L, <b_L .., H_R> for R
+        acp_seg(sh, L.cl, 1, 0, 1);   sh.sel[2] = 0;    // c_L Q, c_R Q with Q = w g
+        if ((rc = acp_fb(b, sh, b->d_lrext + 32 * 2 * (size_t)j, 2 * lg))) return rc;
+        k_compress_strided<<<(2 * B + 127) / 128, 128, 0, s>>>(b->d_lrext, 2 * lg, 2 * j, 2, B, b->d_lr);
+        LAUNCH_CHECK(ctx);
+        CK(ctx, cudaMemcpy2DAsync(b->h_pts8, 64, b->d_lr + 64 * (size_t)j, 64 * (size_t)lg, 64, B, cudaMemcpyDeviceToHost, s));
+        CK(ctx, cudaStreamSynchronize(s));
+        acp_parallel_for(B, [&](uint32_t p) {
+            bpp_host::Transcript &t = b->tr[p];
+            t.append_point("L", b->h_pts8 + 64 * (size_t)p);
+            t.append_point("R", b->h_pts8 + 64 * (size_t)p + 32);
+            t.challenge_wide("u", b->h_wide + 64 * (size_t)p);
+        });
+        if ((rc = acp_put_challenges(b, L.u + j, 1))) return rc;
+        k_ipa_uinv<<<(B + 63) / 64, 64, 0, s>>>(L, B, j, b->d_blk);
+        LAUNCH_CHECK(ctx);
+        k_ipa_fold<<<dim3((h + 127) / 128, B), 128, 0, s>>>(L, j, b->d_blk);
+        LAUNCH_CHECK(ctx);
+    }
+    k_acp_pack_fixed<<<dim3((b->proof_len / 32 + 127) / 128, B), 128, 0, s>>>(L, b->d_pts8, b->d_lr, b->d_blk, b->d_proofs,
+                                                                             b->proof_len);
     LAUNCH_CHECK(ctx);
     return BPP_OK;
 }
@@ -401,13 +518,14 @@ extern "C" int bpp_acp_batch_prove(bpp_acp_batch *b) {
     LAUNCH_CHECK(ctx);
     {   // A_I = alpha*h + <a_L,G> + <a_R,H>; A_O = beta*h + <a_O,G>; S = ro*h + <s_l,G> + <s_r,H>
         fb_shape sh = acp_shape(1);
-        acp_seg(sh, L.alpha, 0, 1, 1); acp_seg(sh, L.aL, 0, 2, n); acp_seg(sh, L.aR, 0, 2 + n, n);
+        const uint32_t gH = 2 + b->gens->n;   // first H generator (gens order g, h, G[..], H[..])
+        acp_seg(sh, L.alpha, 0, 1, 1); acp_seg(sh, L.aL, 0, 2, n); acp_seg(sh, L.aR, 0, gH, n);
         if ((rc = acp_fb(b, sh, b->d_ext8 + 0, 8))) return rc;
         sh = acp_shape(1);
         acp_seg(sh, L.beta, 0, 1, 1); acp_seg(sh, L.aO, 0, 2, n);
         if ((rc = acp_fb(b, sh, b->d_ext8 + 32, 8))) return rc;
         sh = acp_shape(1);
-        acp_seg(sh, L.ro, 0, 1, 1); acp_seg(sh, L.sl, 0, 2, n); acp_seg(sh, L.sr, 0, 2 + n, n);
+        acp_seg(sh, L.ro, 0, 1, 1); acp_seg(sh, L.sl, 0, 2, n); acp_seg(sh, L.sr, 0, gH, n);
         if ((rc = acp_fb(b, sh, b->d_ext8 + 64, 8))) return rc;
     }
     k_compress_strided<<<(B * 3 + 127) / 128, 128, 0, s>>>(b->d_ext8, 8, 0, 3, B, b->d_pts8);
@@ -456,12 +574,13 @@ extern "C" int bpp_acp_batch_prove(bpp_acp_batch *b) {
         t.challenge_wide("x", b->h_wide + 64 * (size_t)p);
     });
     if ((rc = acp_put_challenges(b, L.x, 1))) return rc;
-    k_acp_final<<<dim3((n + 127) / 128, B), 128, 0, s>>>(L, b->d_blk);
+    k_acp_final<<<dim3((L.np + 127) / 128, B), 128, 0, s>>>(L, b->d_blk);
     LAUNCH_CHECK(ctx);
     k_acp_dots<<<dim3(2, B), 128, 0, s>>>(L, 10, b->d_blk);
     LAUNCH_CHECK(ctx);
     k_acp_final2<<<(B + 63) / 64, 64, 0, s>>>(L, B, b->mode, b->d_blk);
     LAUNCH_CHECK(ctx);
+    if (b->mode == 2) return acp_prove_ipa(b);
     k_acp_pack<<<dim3((b->proof_len / 32 + 127) / 128, B), 128, 0, s>>>(L, B, b->d_pts8, b->d_blk, b->d_proofs, b->proof_len);
     LAUNCH_CHECK(ctx);
     return BPP_OK;
@@ -486,6 +605,82 @@ extern "C" int bpp_acp_batch_upload_proofs(bpp_acp_batch *b, const uint8_t *proo
     return BPP_OK;
 }
 
+// `fixed` mode verifier (oracle/ipa.py verify()): replays the transcript including the inner-product rounds,
+// then evaluates rho * check 2 + check 3 with the inner-product verification substituted for <l,G> + <r,h'>
+// as ONE MSM per proof (2 n' + 2 fixed-base terms, m + 8 + 2 lg decompressed points) that must be the identity.
+static int acp_verify_fixed(bpp_acp_batch *b, const uint8_t verifier_seed[32]) {
+    bpp_ctx *ctx = b->ctx;
+    const acp_layout &L = b->lay;
+    const uint32_t B = b->B, n = L.n, np = L.np, m = L.m, lg = L.lg, per = m + 8 + 2 * lg, nch = 4 + lg;
+    cudaStream_t s = ctx->stream;
+    int rc;
+    k_acp_unpack_fixed<<<dim3((b->proof_len / 32 + 127) / 128, B), 128, 0, s>>>(L, b->d_proofs, b->proof_len, b->d_blk, b->d_pts8,
+                                                                               b->d_lr, b->d_tx3);
+    LAUNCH_CHECK(ctx);
+    CK(ctx, cudaMemcpyAsync(b->h_pts8, b->d_pts8, (size_t)B * 256, cudaMemcpyDeviceToHost, s));
+    CK(ctx, cudaMemcpyAsync(b->h_tx3, b->d_tx3, (size_t)B * 96, cudaMemcpyDeviceToHost, s));
+    CK(ctx, cudaMemcpyAsync(b->h_lr, b->d_lr, (size_t)B * 64 * lg, cudaMemcpyDeviceToHost, s));
+    CK(ctx, cudaMemcpyAsync(b->d_vseed, verifier_seed, 32, cudaMemcpyHostToDevice, s));
+    CK(ctx, cudaStreamSynchronize(s));
+    bpp_host::Transcript proto(b->label.data(), b->label.size());
+    proto.arithmetic_domain_sep(n);
+    acp_parallel_for(B, [&](uint32_t p) {
+        bpp_host::Transcript t = proto;
+        const uint8_t *pt = b->h_pts8 + 256 * (size_t)p, *sc3 = b->h_tx3 + 96 * (size_t)p, *lr = b->h_lr + 64 * (size_t)lg * p;
+        uint8_t *wide = b->h_wide + 64 * (size_t)nch * p;
+        t.append_point("A_I", pt);
+        t.append_point("A_O", pt + 32);
+        t.append_point("S", pt + 64);
+        t.challenge_wide("y", wide);
+        t.challenge_wide("z", wide + 64);
+        t.append_point("T1", pt + 96);
+        t.append_point("T3", pt + 128);
+        t.append_point("T4", pt + 160);
+        t.append_point("T5", pt + 192);
+        t.append_point("T6", pt + 224);
+        t.challenge_wide("x", wide + 128);
+        t.append_scalar("t_x", sc3);
+        t.append_scalar("t_x_blinding", sc3 + 32);
+        t.append_scalar("e_blinding", sc3 + 64);
+        t.challenge_wide("w", wide + 192);
+        t.append_message("dom-sep", (const uint8_t *)"ipp v1", 6);
+        t.append_u64("n", np);
+        for (uint32_t j = 0; j < lg; j++) {   // an identity encoding is rejected on the device (k_acp_decompress_lr)
+            t.append_point("L", lr + 64 * (size_t)j);
+            t.append_point("R", lr + 64 * (size_t)j + 32);
+            t.challenge_wide("u", wide + 256 + 64 * (size_t)j);
+        }
+    });
+    // challenges land at y, z, x, (w = verifier weight, overwritten below), then wq and u_j are placed explicitly
+    CK(ctx, cudaMemcpyAsync(b->d_wide, b->h_wide, (size_t)B * nch * 64, cudaMemcpyHostToDevice, s));
+    k_acp_put_wide_strided<<<(B * nch + 127) / 128, 128, 0, s>>>(b->d_wide, L, nch, B, b->d_blk);
+    LAUNCH_CHECK(ctx);
+    k_acp_weights<<<(B + 127) / 128, 128, 0, s>>>(b->d_vseed, L, B, 1, b->d_blk);
+    LAUNCH_CHECK(ctx);
+    if ((rc = acp_challenge_dependent_scalars(b))) return rc;
+    k_acp_dots<<<dim3(1, B), 128, 0, s>>>(L, 9, b->d_blk);   // sigma
+    LAUNCH_CHECK(ctx);
+    k_ipa_vprep<<<(B + 63) / 64, 64, 0, s>>>(L, B, b->d_blk);
+    LAUNCH_CHECK(ctx);
+    CK(ctx, cudaMemsetAsync(b->d_bad, 0, (size_t)B * 4, s));
+    k_acp_decompress<<<(B * (m + 8) + 127) / 128, 128, 0, s>>>(b->d_V, b->d_pts8, m, B, per, b->d_dyn, b->d_bad);
+    LAUNCH_CHECK(ctx);
+    k_acp_decompress_lr<<<(B * 2 * lg + 127) / 128, 128, 0, s>>>(b->d_lr, m, lg, B, b->d_dyn, b->d_bad);
+    LAUNCH_CHECK(ctx);
+    k_acp_vscal_fixed<<<dim3((np + m + 1 + 127) / 128, B), 128, 0, s>>>(L, b->d_blk);
+    LAUNCH_CHECK(ctx);
+    {
+        fb_shape sh = acp_shape(1);
+        acp_seg(sh, L.vg, 0, 0, 2 * np + 2);
+        if ((rc = acp_fb(b, sh, b->d_stat, 1))) return rc;
+    }
+    k_dyn_window_sums<<<B, DYN_W, 0, s>>>(b->d_blk, L, b->d_dyn, per, b->d_wsum);
+    LAUNCH_CHECK(ctx);
+    k_dyn_horner_accept<<<(B + 63) / 64, 64, 0, s>>>(L, B, b->d_blk, b->d_wsum, b->d_stat, b->d_bad, 0, b->d_accept);
+    LAUNCH_CHECK(ctx);
+    return BPP_OK;
+}
+
 // Verifier: proofs + V resident -> accept bytes resident.  Replays the transcript (A_I,A_O,S -> y,z;
 // T's -> x), recomputes the challenge-dependent scalars and evaluates the checks of
 // circuit_lib.rs:518 (t == <l,r>), :541 and (mode 1) :577-582 as one MSM per proof.
@@ -493,6 +688,7 @@ extern "C" int bpp_acp_batch_verify(bpp_acp_batch *b, const uint8_t verifier_see
     if (!b || !verifier_seed) return BPP_ERR_INVALID_ARG;
     bpp_ctx *ctx = b->ctx;
     CK(ctx, cudaSetDevice(ctx->device));
+    if (b->mode == 2) return acp_verify_fixed(b, verifier_seed);
     const acp_layout &L = b->lay;
     const uint32_t B = b->B, n = L.n, m = L.m, per = m + 8;
     cudaStream_t s = ctx->stream;
@@ -527,7 +723,7 @@ extern "C" int bpp_acp_batch_verify(bpp_acp_batch *b, const uint8_t verifier_see
     k_acp_dots<<<dim3(2, B), 128, 0, s>>>(L, 9, b->d_blk);  // sigma, <l, r>
     LAUNCH_CHECK(ctx);
     CK(ctx, cudaMemsetAsync(b->d_bad, 0, (size_t)B * 4, s));
-    k_acp_decompress<<<(B * per + 127) / 128, 128, 0, s>>>(b->d_V, b->d_pts8, m, B, b->d_dyn, b->d_bad);
+    k_acp_decompress<<<(B * per + 127) / 128, 128, 0, s>>>(b->d_V, b->d_pts8, m, B, per, b->d_dyn, b->d_bad);
     LAUNCH_CHECK(ctx);
     k_acp_vscal<<<dim3((n + m + 1 + 127) / 128, B), 128, 0, s>>>(L, b->d_blk);
     LAUNCH_CHECK(ctx);
@@ -538,7 +734,7 @@ extern "C" int bpp_acp_batch_verify(bpp_acp_batch *b, const uint8_t verifier_see
     }
     k_dyn_window_sums<<<B, DYN_W, 0, s>>>(b->d_blk, L, b->d_dyn, per, b->d_wsum);
     LAUNCH_CHECK(ctx);
-    k_dyn_horner_accept<<<(B + 63) / 64, 64, 0, s>>>(L, B, b->d_blk, b->d_wsum, b->d_stat, b->d_bad, b->d_accept);
+    k_dyn_horner_accept<<<(B + 63) / 64, 64, 0, s>>>(L, B, b->d_blk, b->d_wsum, b->d_stat, b->d_bad, 1, b->d_accept);
     LAUNCH_CHECK(ctx);
     return BPP_OK;
 }
@@ -561,7 +757,7 @@ extern "C" int bpp_acp_batch_time_commit_msm(bpp_acp_batch *b, int reps, float *
     CK(ctx, cudaSetDevice(ctx->device));
     const acp_layout &L = b->lay;
     fb_shape sh = acp_shape(1);
-    acp_seg(sh, L.alpha, 0, 1, 1); acp_seg(sh, L.aL, 0, 2, L.n); acp_seg(sh, L.aR, 0, 2 + L.n, L.n);
+    acp_seg(sh, L.alpha, 0, 1, 1); acp_seg(sh, L.aL, 0, 2, L.n); acp_seg(sh, L.aR, 0, 2 + b->gens->n, L.n);
     int rc = acp_fb(b, sh, b->d_ext8, 8);  // warm-up
     if (rc) return rc;
     cudaEvent_t e0, e1;

@@ -16,6 +16,8 @@
 
 struct acp_layout {
     uint32_t n, Q, m, stride;  // stride: scalars per proof
+    uint32_t np, lg;           // `fixed` mode: n padded to a power of two and its log2 (np = n, lg = 0 otherwise);
+                               // yn, yninv, l, r, vG, vH hold np entries, vd holds m + 8 + 2 lg
     uint32_t aL, aR, aO, gamma;                    // witness (uploaded)
     uint32_t alpha, beta, ro, sl, sr, tau;         // prover randomness, RNG draw order (contiguous)
     uint32_t y, z, x, w;                           // challenges, verifier weight
@@ -26,6 +28,8 @@ struct acp_layout {
     uint32_t tc, tsel, sigma;                      // t1..t6, the five committed values, delta(y,z)
     uint32_t l, r, that, taux, mu;                 // proof scalars
     uint32_t vg, vh, vG, vH, vd;                   // verifier MSM scalars: static (contiguous g,h,G,H), dynamic (m+8)
+    uint32_t wq, u, uinv, cl, pa, pb, ptab;        // `fixed` mode: challenge w, u_j / u_j^-1 (lg each), w*c_L, w*c_R,
+                                                   // the proof's a and b, 3 x IPA_MAX_LG squarings for the power tables
 };
 
 #define ACP_PTR(base, lay, p, off) ((base) + 8 * ((size_t)(p) * (lay).stride + (off)))
@@ -120,6 +124,8 @@ struct fb_shape {
     uint32_t gen[4];         // first generator of the segment
     uint32_t cnt[4];
     uint32_t outs;           // outputs per proof (gridDim.y)
+    uint32_t sel_period;     // 0 = off.  IPA rounds (ipa_kernels.cuh): term k of a segment belongs to output 0 (L) or
+    uint32_t sel[4];         // 1 (R) by the half of its period it lies in: sel 1 = upper half -> L, 2 = lower half -> L
 };
 struct fb_consts {
     uint32_t K[8];  // sum_{w < Wn-1} half * 2^(c w)
@@ -140,10 +146,14 @@ __global__ void __launch_bounds__(FB_THREADS) k_fb_msm(const uint32_t *__restric
     ge_ext acc;
     ge_identity(acc);
 #pragma unroll 1
-    for (uint32_t it = threadIdx.x; it < items; it += FB_THREADS) {
+    for (uint32_t it = blockIdx.z * FB_THREADS + threadIdx.x; it < items; it += FB_THREADS * gridDim.z) {
         uint32_t term = it / groups, grp = it - term * groups;
         uint32_t seg = 0, k = term;
         while (seg + 1 < sh.nseg && k >= sh.cnt[seg]) { k -= sh.cnt[seg]; seg++; }
+        if (sh.sel_period && sh.sel[seg]) {
+            const bool upper = (k & (sh.sel_period - 1)) >= (sh.sel_period >> 1);
+            if ((upper == (o == 0)) != (sh.sel[seg] == 1)) continue;
+        }
         const uint32_t *sp = ACP_PTR(blk, lay, p, sh.sc_off[seg] + o * sh.sc_ostride[seg] + k);
         const uint32_t gen = sh.gen[seg] + k;
         // s' = s + K
@@ -189,10 +199,37 @@ __global__ void __launch_bounds__(FB_THREADS) k_fb_msm(const uint32_t *__restric
         }
         __syncthreads();
     }
-    if (threadIdx.x < 32) {
-        uint32_t *dst = out_ext + 32 * ((size_t)p * sh.outs + o);
+    if (threadIdx.x < 32) {  // gridDim.z > 1: partial sums, [p][o][z], added up by k_fb_sum_splits
+        uint32_t *dst = gridDim.z == 1 ? out_ext + 32 * ((size_t)p * sh.outs + o)
+                                       : out_ext + 32 * (((size_t)p * gridDim.y + o) * gridDim.z + blockIdx.z);
         dst[threadIdx.x] = red[0][threadIdx.x];
     }
+}
+// warp per output: sum of `splits` partial points -> dst[p * pitch + o]
+__global__ void __launch_bounds__(32) k_fb_sum_splits(const uint32_t *__restrict__ part, uint32_t outs, uint32_t splits,
+                                                      uint32_t pitch, uint32_t *__restrict__ dst) {
+    const uint32_t p = blockIdx.x, o = blockIdx.y, lane = threadIdx.x;
+    const uint32_t *src = part + 32 * ((size_t)p * outs + o) * splits;
+    ge_ext acc, t;
+    ge_identity(acc);
+#pragma unroll 1
+    for (uint32_t z = lane; z < splits; z += 32) {
+        ge_load(t, src + 32 * (size_t)z);
+        ge_add(acc, acc, t);
+    }
+#pragma unroll 1
+    for (int d = 16; d >= 1; d >>= 1) {
+        ge_ext o2;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            o2.X.v[i] = __shfl_down_sync(0xffffffffu, acc.X.v[i], d);
+            o2.Y.v[i] = __shfl_down_sync(0xffffffffu, acc.Y.v[i], d);
+            o2.Z.v[i] = __shfl_down_sync(0xffffffffu, acc.Z.v[i], d);
+            o2.T.v[i] = __shfl_down_sync(0xffffffffu, acc.T.v[i], d);
+        }
+        ge_add_noinline(acc, acc, o2);
+    }
+    if (lane == 0) ge_store(dst + 32 * ((size_t)p * pitch + o), acc);
 }
 
 // thread per point: ext (raw limbs) -> 32-byte encoding
@@ -341,7 +378,7 @@ __global__ void __launch_bounds__(128) k_acp_dots(acp_layout lay, uint32_t first
         case 7: ua = lay.aO; vb = lay.r3; break;
         case 8: ua = lay.sl; vb = lay.r3; break;
         case 9: ua = lay.lin; vb = lay.zWL; break;
-        case 10: ua = lay.l; vb = lay.r; break;
+        case 10: ua = lay.l; vb = lay.r; len = lay.np; break;
         default: ua = lay.zWV; vb = lay.gamma; len = lay.m; break;
     }
     sc acc, tot, r2;
@@ -392,8 +429,16 @@ __global__ void __launch_bounds__(64) k_acp_tcoef(acp_layout lay, uint32_t B, in
 // thread per (proof, i): l = l(x), r = r(x)  (poly.rs:67-76 with l0 = 0, r2 = 0)
 __global__ void __launch_bounds__(128) k_acp_final(acp_layout lay, uint32_t *__restrict__ blk) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
-    if (i >= lay.n) return;
+    if (i >= lay.np) return;
     sc x, a, b, c, t;
+    if (i >= lay.n) {  // `fixed` mode padding (as dalek pads): l = 0, r = -y^i
+        sc_set0(t);
+        sc_store(ACP_PTR(blk, lay, p, lay.l + i), t);
+        sc_load(a, ACP_PTR(blk, lay, p, lay.yn + i));
+        sc_neg(t, a);
+        sc_store(ACP_PTR(blk, lay, p, lay.r + i), t);
+        return;
+    }
     sc_load(x, ACP_PTR(blk, lay, p, lay.x));
     sc_load(a, ACP_PTR(blk, lay, p, lay.l1 + i));
     sc_load(b, ACP_PTR(blk, lay, p, lay.aO + i));
@@ -563,7 +608,8 @@ __global__ void __launch_bounds__(128) k_acp_vscal(acp_layout lay, uint32_t *__r
 // None; the reference unwraps and panics, circuit_lib.rs:532 - here the proof is rejected).
 __global__ void __launch_bounds__(128) k_acp_decompress(const uint8_t *__restrict__ V /* B x m x 32 */,
                                                         const uint8_t *__restrict__ pts8 /* B x 8 x 32 */, uint32_t m,
-                                                        uint32_t B, uint32_t *__restrict__ dyn /* B x (m+8) x 24 */,
+                                                        uint32_t B, uint32_t pitch /* points per proof in dyn */,
+                                                        uint32_t *__restrict__ dyn /* B x pitch x 24 */,
                                                         uint32_t *__restrict__ bad /* B */) {
     const uint32_t per = m + 8;
     uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
@@ -579,7 +625,7 @@ __global__ void __launch_bounds__(128) k_acp_decompress(const uint8_t *__restric
     }
     ge_niels q;
     ge_affine_to_niels(q, x, y);
-    ge_niels_store(dyn + 24 * (size_t)id, q);
+    ge_niels_store(dyn + 24 * ((size_t)p * pitch + k), q);
 }
 
 // Dynamic-point MSM, phase 1.  Block per proof, one thread per 4-bit signed window (64 windows):
@@ -655,7 +701,8 @@ __global__ void __launch_bounds__(DYN_W) k_dyn_window_sums(const uint32_t *__res
 __global__ void __launch_bounds__(64) k_dyn_horner_accept(acp_layout lay, uint32_t B, const uint32_t *__restrict__ blk,
                                                           const uint32_t *__restrict__ wsum,
                                                           const uint32_t *__restrict__ stat_ext /* B x 32 */,
-                                                          const uint32_t *__restrict__ bad, uint8_t *__restrict__ accept) {
+                                                          const uint32_t *__restrict__ bad, int check_t,
+                                                          uint8_t *__restrict__ accept) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= B) return;
     ge_ext acc, t;
@@ -673,5 +720,5 @@ __global__ void __launch_bounds__(64) k_dyn_horner_accept(acp_layout lay, uint32
     sc that, lr;
     sc_load(that, ACP_PTR(blk, lay, p, lay.that));
     sc_load(lr, ACP_PTR(blk, lay, p, lay.dots + 10));
-    accept[p] = (ident && sc_eq(that, lr) && bad[p] == 0) ? 1 : 0;
+    accept[p] = (ident && (!check_t || sc_eq(that, lr)) && bad[p] == 0) ? 1 : 0;
 }

@@ -1,0 +1,341 @@
+// ipa_kernels.cuh - `fixed` protocol mode: standard powers and the inner-product argument, batched.
+//
+// SURVEY section 8 row a16 / north_star item (2): bulletproofs 4.0.0 `InnerProductProof::create`
+// (inner_product_proof.rs; Cargo.lock:47-50, un-vendored) - absent from the reference, which sends l and r
+// in the clear (circuit_lib.rs:464-468).  Restated in oracle/ipa.py and oracle/c/acproof_ref.c.
+//
+// Formulation ("fold the scalars, not the points"): the folded generators of round j are
+//   G^(j)[i] = sum_t s_t G[i + t n_j],   H^(j)[i] = sum_t s_t^-1 y^-(i + t n_j) H[i + t n_j],
+//   n_j = n' / 2^j,  s_t = prod_{k<j} u_k^(+-1)  (+ iff bit j-1-k of t is set),
+// so L_j and R_j are MSMs over the ORIGINAL generators with scalars a[i^h] s_t (G side) and
+// b[i^h] s_t^-1 y^-g (H side), h = n_j / 2: they run through the same fixed-base tables as the
+// commitments (k_fb_msm) and no generator is ever folded.  a and b fold in place in the proof block.
+#pragma once
+#include "acproof_kernels.cuh"
+
+#define IPA_MAX_LG 20
+
+// ---- standard powers ---------------------------------------------------------------------------------
+// Thread per proof: squarings y^(2^k), (y^-1)^(2^k), z^(2^k) (Montgomery form) into the proof block.
+__global__ void __launch_bounds__(64) k_pow_table(acp_layout lay, uint32_t B, uint32_t *__restrict__ blk) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    sc y, z, yi;
+    sc_load(y, ACP_PTR(blk, lay, p, lay.y));
+    sc_load(z, ACP_PTR(blk, lay, p, lay.z));
+    sc_invert(yi, y);
+    sc_to_mont(y, y);
+    sc_to_mont(yi, yi);
+    sc_to_mont(z, z);
+#pragma unroll 1
+    for (uint32_t k = 0; k < IPA_MAX_LG; k++) {
+        sc_store(ACP_PTR(blk, lay, p, lay.ptab + k), y);
+        sc_store(ACP_PTR(blk, lay, p, lay.ptab + IPA_MAX_LG + k), yi);
+        sc_store(ACP_PTR(blk, lay, p, lay.ptab + 2 * IPA_MAX_LG + k), z);
+        sc_mont_noinline(y, y, y);
+        sc_mont_noinline(yi, yi, yi);
+        sc_mont_noinline(z, z, z);
+    }
+}
+// Thread per (proof, j): y_n[i] = y^i, y_n_inv[i] = y^-i (i < n'), z_q[q] = z^(q+1) (q < Q) as products of the
+// squarings selected by the exponent's bits (<= lg multiplications each, no serial chain over n).
+__global__ void __launch_bounds__(128) k_pow_fill(acp_layout lay, uint32_t *__restrict__ blk) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
+    const uint32_t total = 2 * lay.np + lay.Q;
+    if (j >= total) return;
+    uint32_t which, e, dst;
+    if (j < lay.np) { which = 0; e = j; dst = lay.yn + j; }
+    else if (j < 2 * lay.np) { which = 1; e = j - lay.np; dst = lay.yninv + e; }
+    else { which = 2; e = j - 2 * lay.np + 1; dst = lay.zq + (e - 1); }
+    sc acc, t;
+    sc_const(acc, SC_R);
+    const uint32_t *tab = ACP_PTR(blk, lay, p, lay.ptab + which * IPA_MAX_LG);
+#pragma unroll 1
+    for (uint32_t k = 0; e; k++, e >>= 1)
+        if (e & 1u) {
+            sc_load(t, tab + 8 * (size_t)k);
+            sc_mont_noinline(acc, acc, t);
+        }
+    sc_from_mont(acc, acc);
+    sc_store(ACP_PTR(blk, lay, p, dst), acc);
+}
+
+// ---- prover rounds -----------------------------------------------------------------------------------
+// block per (proof, which): cl[0] = w <a_L, b_R>, cl[1] = w <a_R, b_L> over the current halves (the Q = w*g term)
+__global__ void __launch_bounds__(128) k_ipa_dots(acp_layout lay, uint32_t h, uint32_t *__restrict__ blk) {
+    __shared__ __align__(16) uint32_t sh[32 * 8];
+    const uint32_t which = blockIdx.x, p = blockIdx.y;
+    const uint32_t *a = ACP_PTR(blk, lay, p, lay.l + (which ? h : 0));
+    const uint32_t *b = ACP_PTR(blk, lay, p, lay.r + (which ? 0 : h));
+    sc acc, tot, w;
+    dot_partial(acc, a, 1, b, 1, h);
+    block_sum_sc(tot, acc, sh);
+    if (threadIdx.x == 0) {
+        sc r2;
+        sc_const(r2, SC_R2);
+        sc_mont(tot, tot, r2);
+        sc_load(w, ACP_PTR(blk, lay, p, lay.wq));
+        sc_mul(tot, tot, w);
+        sc_store(ACP_PTR(blk, lay, p, lay.cl + which), tot);
+    }
+}
+// s_t (or its inverse) for the first `rounds` challenges: prod_k (bit (rounds-1-k) of t ? u_k : u_k^-1)
+SC_INLINE void ipa_s_mont(sc &s, sc &sinv, const uint32_t *__restrict__ u, const uint32_t *__restrict__ ui, uint32_t rounds,
+                          uint32_t t) {
+    sc a, b;
+    sc_const(s, SC_R);
+    sinv = s;
+#pragma unroll 1
+    for (uint32_t k = 0; k < rounds; k++) {
+        sc_load(a, u + 8 * (size_t)k);      // Montgomery form
+        sc_load(b, ui + 8 * (size_t)k);
+        const bool bit = (t >> (rounds - 1 - k)) & 1u;
+        sc_mont_noinline(s, s, bit ? a : b);
+        sc_mont_noinline(sinv, sinv, bit ? b : a);
+    }
+}
+// thread per (proof, g < n'): the round's MSM scalars over the original generators
+__global__ void __launch_bounds__(128) k_ipa_prep(acp_layout lay, uint32_t round, uint32_t *__restrict__ blk) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
+    if (g >= lay.np) return;
+    const uint32_t nj = lay.np >> round, h = nj >> 1;
+    const uint32_t i = g & (nj - 1), t = g >> (lay.lg - round), ip = i ^ h;
+    sc s, sinv, a, b, yi, r;
+    ipa_s_mont(s, sinv, ACP_PTR(blk, lay, p, lay.u), ACP_PTR(blk, lay, p, lay.uinv), round, t);
+    sc_load(a, ACP_PTR(blk, lay, p, lay.l + ip));
+    sc_load(b, ACP_PTR(blk, lay, p, lay.r + ip));
+    sc_load(yi, ACP_PTR(blk, lay, p, lay.yninv + g));
+    sc_mont(r, a, s);                       // a * s_t (s in Montgomery form -> standard result)
+    sc_store(ACP_PTR(blk, lay, p, lay.vG + g), r);
+    sc_mont(r, b, sinv);
+    sc_mul(r, r, yi);
+    sc_store(ACP_PTR(blk, lay, p, lay.vH + g), r);
+}
+// thread per proof: u_round^-1; both kept in Montgomery form at u[round], uinv[round]
+__global__ void __launch_bounds__(64) k_ipa_uinv(acp_layout lay, uint32_t B, uint32_t round, uint32_t *__restrict__ blk) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    sc u, ui;
+    sc_load(u, ACP_PTR(blk, lay, p, lay.u + round));   // standard form (k_acp_put_wide)
+    sc_invert(ui, u);
+    sc_to_mont(u, u);
+    sc_to_mont(ui, ui);
+    sc_store(ACP_PTR(blk, lay, p, lay.u + round), u);
+    sc_store(ACP_PTR(blk, lay, p, lay.uinv + round), ui);
+}
+// thread per (proof, i < h): a[i] = a[i] u + u^-1 a[h+i],  b[i] = b[i] u^-1 + u b[h+i]   (in place)
+__global__ void __launch_bounds__(128) k_ipa_fold(acp_layout lay, uint32_t round, uint32_t *__restrict__ blk) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
+    const uint32_t h = lay.np >> (round + 1);
+    if (i >= h) return;
+    sc u, ui, lo, hi, t1, t2;
+    sc_load(u, ACP_PTR(blk, lay, p, lay.u + round));
+    sc_load(ui, ACP_PTR(blk, lay, p, lay.uinv + round));
+    sc_load(lo, ACP_PTR(blk, lay, p, lay.l + i));
+    sc_load(hi, ACP_PTR(blk, lay, p, lay.l + h + i));
+    sc_mont(t1, lo, u);
+    sc_mont(t2, hi, ui);
+    sc_add(t1, t1, t2);
+    sc_store(ACP_PTR(blk, lay, p, lay.l + i), t1);
+    sc_load(lo, ACP_PTR(blk, lay, p, lay.r + i));
+    sc_load(hi, ACP_PTR(blk, lay, p, lay.r + h + i));
+    sc_mont(t1, lo, ui);
+    sc_mont(t2, hi, u);
+    sc_add(t1, t1, t2);
+    sc_store(ACP_PTR(blk, lay, p, lay.r + i), t1);
+}
+
+// ---- proof (de)serialisation, `fixed` mode: 8 points | t_hat, tau_x, mu | (L_j, R_j) x lg | a, b -----------
+__global__ void k_acp_pack_fixed(acp_layout lay, const uint8_t *__restrict__ pts8, const uint8_t *__restrict__ lr,
+                                 const uint32_t *__restrict__ blk, uint8_t *__restrict__ out, uint32_t proof_len) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
+    const uint32_t words = proof_len / 32;
+    if (i >= words) return;
+    const uint4 *s;
+    if (i < 8) s = reinterpret_cast<const uint4 *>(pts8 + 32 * ((size_t)p * 8 + i));
+    else if (i < 11) s = reinterpret_cast<const uint4 *>(ACP_PTR(blk, lay, p, i == 8 ? lay.that : i == 9 ? lay.taux : lay.mu));
+    else if (i < 11 + 2 * lay.lg) s = reinterpret_cast<const uint4 *>(lr + 32 * ((size_t)p * 2 * lay.lg + (i - 11)));
+    else s = reinterpret_cast<const uint4 *>(ACP_PTR(blk, lay, p, i == 11 + 2 * lay.lg ? lay.l : lay.r));
+    uint4 *d = reinterpret_cast<uint4 *>(out + (size_t)p * proof_len + 32 * (size_t)i);
+    d[0] = s[0];
+    d[1] = s[1];
+}
+// scalars are taken mod l (dalek arithmetic on a non-canonical scalar would do the same); the three transcript
+// scalars are also written, reduced, to tx3 for the host
+__global__ void k_acp_unpack_fixed(acp_layout lay, const uint8_t *__restrict__ proofs, uint32_t proof_len,
+                                   uint32_t *__restrict__ blk, uint8_t *__restrict__ pts8, uint8_t *__restrict__ lr,
+                                   uint32_t *__restrict__ tx3) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
+    const uint32_t words = proof_len / 32;
+    if (i >= words) return;
+    const uint4 *s = reinterpret_cast<const uint4 *>(proofs + (size_t)p * proof_len + 32 * (size_t)i);
+    uint4 lo = s[0], hi = s[1];
+    if (i < 8 || (i >= 11 && i < 11 + 2 * lay.lg)) {
+        uint4 *d = i < 8 ? reinterpret_cast<uint4 *>(pts8 + 32 * ((size_t)p * 8 + i))
+                         : reinterpret_cast<uint4 *>(lr + 32 * ((size_t)p * 2 * lay.lg + (i - 11)));
+        d[0] = lo;
+        d[1] = hi;
+        return;
+    }
+    sc v;
+    v.v[0] = lo.x; v.v[1] = lo.y; v.v[2] = lo.z; v.v[3] = lo.w; v.v[4] = hi.x; v.v[5] = hi.y; v.v[6] = hi.z; v.v[7] = hi.w;
+    sc_reduce256(v, v);
+    uint32_t off = i == 8 ? lay.that : i == 9 ? lay.taux : i == 10 ? lay.mu : i == 11 + 2 * lay.lg ? lay.pa : lay.pb;
+    sc_store(ACP_PTR(blk, lay, p, off), v);
+    if (i < 11) sc_store(tx3 + 8 * ((size_t)p * 3 + (i - 8)), v);
+}
+
+// ---- verifier ------------------------------------------------------------------------------------------------
+// the verifier's 4 + lg wide challenges per proof (y, z, x, w, u_0..) -> y, z, x, wq, u[j]
+__global__ void k_acp_put_wide_strided(const uint32_t *__restrict__ wide, acp_layout lay, uint32_t nch, uint32_t B,
+                                       uint32_t *__restrict__ blk) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * nch) return;
+    uint32_t p = i / nch, k = i - p * nch;
+    uint32_t w[16];
+#pragma unroll
+    for (int t = 0; t < 16; t++) w[t] = wide[16 * (size_t)i + t];
+    sc r;
+    sc_from_wide(r, w);
+    const uint32_t off = k == 0 ? lay.y : k == 1 ? lay.z : k == 2 ? lay.x : k == 3 ? lay.wq : lay.u + (k - 4);
+    sc_store(ACP_PTR(blk, lay, p, off), r);
+}
+// thread per proof: u_j^-1 for all rounds with one inversion; u, uinv in Montgomery form; usq, uinvsq standard
+__global__ void __launch_bounds__(64) k_ipa_vprep(acp_layout lay, uint32_t B, uint32_t *__restrict__ blk) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    uint32_t *u = ACP_PTR(blk, lay, p, lay.u), *ui = ACP_PTR(blk, lay, p, lay.uinv);
+    sc acc, v, inv;
+    sc_const(acc, SC_R);
+    bool zero = false;
+#pragma unroll 1
+    for (uint32_t k = 0; k < lay.lg; k++) {     // prefix products (Montgomery) in uinv
+        sc_store(ui + 8 * (size_t)k, acc);
+        sc_load(v, u + 8 * (size_t)k);
+        zero = zero || sc_is_zero(v);
+        sc_to_mont(v, v);
+        sc_store(u + 8 * (size_t)k, v);
+        sc_mont_noinline(acc, acc, v);
+    }
+    sc_from_mont(v, acc);
+    sc_invert(inv, v);
+    sc_to_mont(inv, inv);
+#pragma unroll 1
+    for (int k = (int)lay.lg - 1; k >= 0; k--) {
+        sc pre, r, e, sq;
+        sc_load(pre, ui + 8 * (size_t)k);
+        sc_mont_noinline(r, inv, pre);          // u_k^-1 (Montgomery)
+        sc_load(e, u + 8 * (size_t)k);
+        sc_mont_noinline(inv, inv, e);
+        if (zero) sc_set0(r);                   // only if some u_k = 0: dalek's invert(0) = 0
+        sc_store(ui + 8 * (size_t)k, r);
+        sc_mont_noinline(sq, e, e);
+        sc_from_mont(sq, sq);
+        sc_store(ACP_PTR(blk, lay, p, lay.vd + lay.m + 8 + 2 * k), sq);          // L_k: u_k^2
+        sc_mont_noinline(sq, r, r);
+        sc_from_mont(sq, sq);
+        sc_store(ACP_PTR(blk, lay, p, lay.vd + lay.m + 8 + 2 * k + 1), sq);      // R_k: u_k^-2
+    }
+}
+// Scalars of the fused check (`fixed` layout; rho = per-proof verifier weight on check 2):
+//   g: rho (t - x^2(<z_q,c> + sigma)) + w (t - a b)          h: rho tau_x - mu
+//   G_i: x l_in_i - a s_i                                     H_i: y^-i (x zWL_i + zWO_i - y^i - b s_i^-1)
+//   V_j: -rho x^2 zWV_j   T_1,T_3..T_6: -rho x^deg   A_I, A_O, S: x, x^2, x^3   L_k: u_k^2   R_k: u_k^-2
+__global__ void __launch_bounds__(128) k_acp_vscal_fixed(acp_layout lay, uint32_t *__restrict__ blk) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
+    const uint32_t tot = lay.np + lay.m + 1;
+    if (i >= tot) return;
+    sc x, rho, t, u, v;
+    sc_load(x, ACP_PTR(blk, lay, p, lay.x));
+    sc_load(rho, ACP_PTR(blk, lay, p, lay.w));
+    if (i < lay.np) {
+        sc s, sinv, pa, pb, yi, yn;
+        ipa_s_mont(s, sinv, ACP_PTR(blk, lay, p, lay.u), ACP_PTR(blk, lay, p, lay.uinv), lay.lg, i);
+        sc_load(pa, ACP_PTR(blk, lay, p, lay.pa));
+        sc_load(pb, ACP_PTR(blk, lay, p, lay.pb));
+        sc_load(yi, ACP_PTR(blk, lay, p, lay.yninv + i));
+        sc_load(yn, ACP_PTR(blk, lay, p, lay.yn + i));
+        sc_mont(u, pa, s);                       // a s_i
+        sc_set0(t);
+        if (i < lay.n) {
+            sc_load(v, ACP_PTR(blk, lay, p, lay.lin + i));
+            sc_mul(t, x, v);
+        }
+        sc_sub(t, t, u);
+        sc_store(ACP_PTR(blk, lay, p, lay.vG + i), t);
+        sc_mont(u, pb, sinv);                    // b / s_i
+        sc_set0(t);
+        if (i < lay.n) {
+            sc zwl, zwo;
+            sc_load(zwl, ACP_PTR(blk, lay, p, lay.zWL + i));
+            sc_load(zwo, ACP_PTR(blk, lay, p, lay.zWO + i));
+            sc_mul(t, x, zwl);
+            sc_add(t, t, zwo);
+        }
+        sc_sub(t, t, yn);
+        sc_sub(t, t, u);
+        sc_mul(t, yi, t);
+        sc_store(ACP_PTR(blk, lay, p, lay.vH + i), t);
+    } else if (i < lay.np + lay.m) {
+        const uint32_t j = i - lay.np;
+        sc_load(u, ACP_PTR(blk, lay, p, lay.zWV + j));
+        sc_mul(t, x, x);
+        sc_mul(t, t, u);
+        sc_mul(t, t, rho);
+        sc_neg(t, t);
+        sc_store(ACP_PTR(blk, lay, p, lay.vd + j), t);
+    } else {
+        sc xp[7], wq, pa, pb, that;
+        sc_set_u32(xp[0], 1);
+        for (int k = 1; k <= 6; k++) sc_mul_noinline(xp[k], xp[k - 1], x);
+        sc_load(that, ACP_PTR(blk, lay, p, lay.that));
+        sc_load(u, ACP_PTR(blk, lay, p, lay.zc));
+        sc_load(v, ACP_PTR(blk, lay, p, lay.sigma));
+        sc_add(u, u, v);
+        sc_mul_noinline(u, u, xp[2]);
+        sc_sub(t, that, u);
+        sc_mul_noinline(t, t, rho);              // rho (t - x^2(zc + sigma))
+        sc_load(wq, ACP_PTR(blk, lay, p, lay.wq));
+        sc_load(pa, ACP_PTR(blk, lay, p, lay.pa));
+        sc_load(pb, ACP_PTR(blk, lay, p, lay.pb));
+        sc_mul_noinline(u, pa, pb);
+        sc_sub(u, that, u);
+        sc_mul_noinline(u, u, wq);               // w (t - a b)
+        sc_add(t, t, u);
+        sc_store(ACP_PTR(blk, lay, p, lay.vg), t);
+        sc_load(u, ACP_PTR(blk, lay, p, lay.taux));
+        sc_mul_noinline(u, u, rho);
+        sc_load(v, ACP_PTR(blk, lay, p, lay.mu));
+        sc_sub(t, u, v);
+        sc_store(ACP_PTR(blk, lay, p, lay.vh), t);
+        const int deg[5] = {1, 3, 4, 5, 6};
+        for (int k = 0; k < 5; k++) {
+            sc_mul_noinline(t, rho, xp[deg[k]]);
+            sc_neg(t, t);
+            sc_store(ACP_PTR(blk, lay, p, lay.vd + lay.m + k), t);
+        }
+        for (int k = 0; k < 3; k++) sc_store(ACP_PTR(blk, lay, p, lay.vd + lay.m + 5 + k), xp[k + 1]);
+    }
+}
+// extra dynamic points of `fixed` mode: L_k, R_k (an identity encoding is rejected like
+// validate_and_append_point, an invalid one like decompress() = None)
+__global__ void __launch_bounds__(128) k_acp_decompress_lr(const uint8_t *__restrict__ lr, uint32_t m, uint32_t lg, uint32_t B,
+                                                           uint32_t *__restrict__ dyn, uint32_t *__restrict__ bad) {
+    const uint32_t per = m + 8 + 2 * lg;
+    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= B * 2 * lg) return;
+    const uint32_t p = id / (2 * lg), k = id - p * 2 * lg;
+    const uint8_t *src = lr + 32 * (size_t)id;
+    uint32_t any = 0;
+    for (int b = 0; b < 32; b++) any |= src[b];
+    fe x, y;
+    bool ok = ge_decompress(x, y, src) && any != 0;
+    if (!ok) {
+        atomicOr(&bad[p], 1u);
+        fe_set0(x);
+        fe_set1(y);
+    }
+    ge_niels q;
+    ge_affine_to_niels(q, x, y);
+    ge_niels_store(dyn + 24 * ((size_t)p * per + m + 8 + k), q);
+}

@@ -145,6 +145,12 @@ int bpp_poly6_eval(bpp_ctx *ctx, const uint8_t t1_t6[192], const uint8_t x[32], 
  *   mode 0 "reference"        what the reference code computes, defects included; its
  *                             verifier rejects every proof (circuit_lib.rs:541-544), so does this one.
  *   mode 1 "reference-fixed"  defects 2-5 corrected: an accepting protocol with l, r in the clear.
+ *   mode 2 "fixed"            + standard powers y^i, z^q and l, r replaced by an inner-product proof: bulletproofs
+ *                             4.0.0 InnerProductProof::create / verification_scalars (Cargo.lock:47-50; absent from
+ *                             the reference) with dalek's R1CS glue (t_x, t_x_blinding, e_blinding,
+ *                             w, Q = w*g, H_factors = y^-n, padding to n' = next_pow2(n)).  Needs n' generators
+ *                             in bpp_gens_create.  Proof bytes: the same 8 points | t | tau_x | mu |
+ *                             L_0 | R_0 | .. | L_{lg n'-1} | R_{lg n'-1} | a | b.
  * Proof bytes (the reference defines no serialisation): A_I | A_O | S | T_1 | T_3 | T_4 | T_5 | T_6 |
  * tau_x | mu | t | l[0..n) | r[0..n), 32 bytes each. */
 typedef struct bpp_circuit bpp_circuit;
@@ -161,7 +167,8 @@ void bpp_circuit_free(bpp_ctx *ctx, bpp_circuit *c);
 int bpp_gens_create(bpp_ctx *ctx, const uint8_t g[32], const uint8_t h[32], const uint8_t *G, const uint8_t *H, size_t n,
                     int window_bits, bpp_gens **out);
 void bpp_gens_free(bpp_ctx *ctx, bpp_gens *g);
-size_t bpp_acproof_proof_len(size_t n);
+size_t bpp_acproof_proof_len(size_t n);                  /* modes 0 and 1: 32 * (11 + 2n) */
+size_t bpp_acproof_proof_len_mode(size_t n, int mode);    /* mode 2: 32 * (13 + 2 lg n') */
 /* One-call host forms: host buffers in, host buffers out (all copies included). */
 int bpp_acproof_prove_batch(bpp_ctx *ctx, const bpp_circuit *cir, const bpp_gens *gens, int mode, size_t count,
                             const uint8_t *aL, const uint8_t *aR, const uint8_t *aO /* count x n x 32 */,

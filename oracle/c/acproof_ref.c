@@ -489,3 +489,243 @@ void orc_scalar_ops_selftest(const u8 *a32, const u8 *b32, const u8 *w64, u8 *ou
     sc_invert(&r, &a); sc_tobytes(out + 96, &r);
     sc_from_wide(&r, w64); sc_tobytes(out + 128, &r);
 }
+
+/* ------------------------------------------------------------------ `fixed` mode (IPA) ---------- */
+/* Restatement of bulletproofs 4.0.0 inner_product_proof.rs (create / verification_scalars / verify)
+ * and of the R1CS glue around it, as described in oracle/ipa.py (the reference has no IPA; PARITY
+ * UNPINNED, this file == oracle/ipa.py == the CUDA path).  The prover folds the generators explicitly
+ * with 2-term vartime MSMs exactly like dalek; weights come as sparse (wire, constraint, coeff)
+ * triples for W_L|W_R|W_O|W_V so that the 4096-card deck fits in memory. */
+static size_t next_pow2_sz(size_t n) { size_t p = 1; while (p < n) p <<= 1; return p; }
+static void v_std_powers(sc *out, const sc *x, size_t count, const sc *first) {
+    sc cur = *first;
+    for (size_t i = 0; i < count; i++) { out[i] = cur; sc_mul(&cur, &cur, x); }
+}
+/* out[wire] += coeff * z_q[constraint] over one matrix's triples */
+static void v_sparse_vm(sc *out, size_t rows, const sc *z_q, const u32 *wire, const u32 *cons, const sc *coeff, size_t nnz) {
+    memset(out, 0, rows * sizeof(sc));
+    for (size_t e = 0; e < nnz; e++) { sc t; sc_mul(&t, &coeff[e], &z_q[cons[e]]); sc_add(&out[wire[e]], &out[wire[e]], &t); }
+}
+static int is_zero32(const u8 *b) { u8 o = 0; for (int i = 0; i < 32; i++) o |= b[i]; return o == 0; }
+static void sc_from_bytes_mod_order(sc *r, const u8 *b) { u8 w[64] = {0}; memcpy(w, b, 32); sc_from_wide(r, w); }
+
+size_t orc_acp_fixed_proof_len(size_t n) {
+    size_t np = next_pow2_sz(n), lg = 0; while (((size_t)1 << lg) < np) lg++;
+    return 32 * (13 + 2 * lg);
+}
+
+/* G_pts, H_pts: next_pow2(n) generators each.  Returns 1 accept / 0 reject (or 1 when !do_verify). */
+int orc_acp_fixed_prove_verify(size_t n, size_t Q, size_t m, const u32 nnz[4], const u32 *wire, const u32 *cons,
+                               const u8 *coeffb, const u8 *cb, const u8 *g_pt, const u8 *h_pt, const u8 *G_pts,
+                               const u8 *H_pts, const u8 *aLb, const u8 *aRb, const u8 *aOb, const u8 *gammab,
+                               const u8 *V_pts, const u8 *seed32, const u8 *label, size_t label_len, u8 *proof,
+                               int do_prove, int do_verify) {
+    orc_init();
+    const size_t np = next_pow2_sz(n);
+    size_t lg = 0; while (((size_t)1 << lg) < np) lg++;
+    const sc *coeff = (const sc *)coeffb, *cv = (const sc *)cb;
+    const sc *a_L = (const sc *)aLb, *a_R = (const sc *)aRb, *a_O = (const sc *)aOb, *gamma = (const sc *)gammab;
+    const ge_ext *g = (const ge_ext *)g_pt, *h = (const ge_ext *)h_pt, *G = (const ge_ext *)G_pts, *H = (const ge_ext *)H_pts;
+    const ge_ext *V = (const ge_ext *)V_pts;
+    const u32 *wr[4], *cn[4]; const sc *cf[4]; size_t off = 0;
+    for (int k = 0; k < 4; k++) { wr[k] = wire + off; cn[k] = cons + off; cf[k] = coeff + off; off += nnz[k]; }
+    const size_t big = 2 * np + m + 2 * lg + 16;
+    sc *sv = malloc(big * sizeof(sc)); ge_ext *pv = malloc(big * sizeof(ge_ext));
+    sc *y_n = malloc(np * sizeof(sc)), *y_n_inv = malloc(np * sizeof(sc)), *z_q = malloc(Q * sizeof(sc));
+    sc *zWL = malloc(n * sizeof(sc)), *zWR = malloc(n * sizeof(sc)), *zWO = malloc(n * sizeof(sc)), *zWV = malloc(m * sizeof(sc));
+    sc *l_in = malloc(n * sizeof(sc));
+    const sc one = {{1, 0, 0, 0}};
+    static const int DEG[5] = {1, 3, 4, 5, 6};
+    static const char *TL[5] = {"T1", "T3", "T4", "T5", "T6"};
+    u8 *po = proof;
+    int result = 1;
+    if (do_prove) {
+        rng_t rng; memcpy(rng.key, seed32, 32); rng.ctr = 0;
+        strobe tr; tr_new(&tr, label, label_len);
+        { u8 nb[8]; for (int i = 0; i < 8; i++) nb[i] = (u8)((u64)n >> (8 * i)); tr_append(&tr, "dom-sep", (const u8 *)"acp v1", 6); tr_append(&tr, "n", nb, 8); }
+        sc alpha, beta, ro; rng_scalar(&rng, &alpha); rng_scalar(&rng, &beta); rng_scalar(&rng, &ro);
+        ge_ext A_I, A_O, S;
+        sv[0] = alpha; pv[0] = *h; memcpy(sv + 1, a_L, n * 32); memcpy(pv + 1, G, n * sizeof(ge_ext));
+        memcpy(sv + 1 + n, a_R, n * 32); memcpy(pv + 1 + n, H, n * sizeof(ge_ext));
+        msm_sc(&A_I, sv, pv, 1 + 2 * n);
+        sv[0] = beta; memcpy(sv + 1, a_O, n * 32);
+        msm_sc(&A_O, sv, pv, 1 + n);
+        sc *s_l = malloc(n * sizeof(sc)), *s_r = malloc(n * sizeof(sc));
+        for (size_t i = 0; i < n; i++) rng_scalar(&rng, &s_l[i]);
+        for (size_t i = 0; i < n; i++) rng_scalar(&rng, &s_r[i]);
+        sv[0] = ro; memcpy(sv + 1, s_l, n * 32); memcpy(sv + 1 + n, s_r, n * 32);
+        msm_sc(&S, sv, pv, 1 + 2 * n);
+        ristretto_compress(po, &A_I); ristretto_compress(po + 32, &A_O); ristretto_compress(po + 64, &S);
+        tr_append(&tr, "A_I", po, 32); tr_append(&tr, "A_O", po + 32, 32); tr_append(&tr, "S", po + 64, 32);
+        sc y, z, y_inv; tr_challenge_scalar(&tr, "y", &y); tr_challenge_scalar(&tr, "z", &z);
+        sc_invert(&y_inv, &y);
+        v_std_powers(y_n, &y, np, &one); v_std_powers(y_n_inv, &y_inv, np, &one); v_std_powers(z_q, &z, Q, &z);
+        v_sparse_vm(zWL, n, z_q, wr[0], cn[0], cf[0], nnz[0]);
+        v_sparse_vm(zWR, n, z_q, wr[1], cn[1], cf[1], nnz[1]);
+        v_sparse_vm(zWO, n, z_q, wr[2], cn[2], cf[2], nnz[2]);
+        v_sparse_vm(zWV, m, z_q, wr[3], cn[3], cf[3], nnz[3]);
+        v_hadamard(l_in, y_n_inv, zWR, n);
+        sc *l1 = malloc(n * sizeof(sc)), *r0 = malloc(n * sizeof(sc)), *r1 = malloc(n * sizeof(sc)), *r3 = malloc(n * sizeof(sc));
+        for (size_t i = 0; i < n; i++) {
+            sc t;
+            sc_add(&l1[i], &a_L[i], &l_in[i]);
+            sc_sub(&r0[i], &zWO[i], &y_n[i]);
+            sc_mul(&t, &y_n[i], &a_R[i]); sc_add(&r1[i], &t, &zWL[i]);
+            sc_mul(&r3[i], &y_n[i], &s_r[i]);
+        }
+        sc t6[6], d1, d2;
+        v_inner_product(&t6[0], l1, r0, n);
+        v_inner_product(&d1, l1, r1, n); v_inner_product(&d2, a_O, r0, n); sc_add(&t6[1], &d1, &d2);
+        v_inner_product(&d1, a_O, r1, n); v_inner_product(&d2, s_l, r0, n); sc_add(&t6[2], &d1, &d2);
+        v_inner_product(&d1, l1, r3, n); v_inner_product(&d2, s_l, r1, n); sc_add(&t6[3], &d1, &d2);
+        v_inner_product(&t6[4], a_O, r3, n);
+        v_inner_product(&t6[5], s_l, r3, n);
+        sc taus[5];
+        for (int k = 0; k < 5; k++) {
+            rng_scalar(&rng, &taus[k]);
+            sv[0] = t6[DEG[k] - 1]; sv[1] = taus[k]; pv[0] = *g; pv[1] = *h;
+            ge_ext T; msm_sc(&T, sv, pv, 2);
+            ristretto_compress(po + 96 + 32 * k, &T);
+            tr_append(&tr, TL[k], po + 96 + 32 * k, 32);
+        }
+        sc x; tr_challenge_scalar(&tr, "x", &x);
+        sc *a = calloc(np, sizeof(sc)), *b = malloc(np * sizeof(sc)), *zero = calloc(n, sizeof(sc));
+        v_poly3_eval(a, zero, l1, a_O, s_l, &x, n);
+        v_poly3_eval(b, r0, r1, zero, r3, &x, n);
+        for (size_t i = n; i < np; i++) sc_neg(&b[i], &y_n[i]);
+        sc that; v_inner_product(&that, a, b, np);
+        sc tau_x, xx, term, wvg;
+        sc_mul(&xx, &x, &x);
+        v_inner_product(&wvg, zWV, gamma, m);     /* <z_q, W_V gamma> = <z W_V, gamma> */
+        sc_mul(&tau_x, &xx, &wvg);
+        for (int k = 0; k < 5; k++) { sc xp; v_scalar_exp(&xp, &x, DEG[k]); sc_mul(&term, &taus[k], &xp); sc_add(&tau_x, &tau_x, &term); }
+        sc mu, xp3; sc_mul(&xp3, &xx, &x);
+        sc_mul(&mu, &alpha, &x); sc_mul(&term, &beta, &xx); sc_add(&mu, &mu, &term); sc_mul(&term, &ro, &xp3); sc_add(&mu, &mu, &term);
+        tr_append_scalar(&tr, "t_x", &that); tr_append_scalar(&tr, "t_x_blinding", &tau_x); tr_append_scalar(&tr, "e_blinding", &mu);
+        sc_tobytes(po + 256, &that); sc_tobytes(po + 288, &tau_x); sc_tobytes(po + 320, &mu);
+        sc w; tr_challenge_scalar(&tr, "w", &w);
+        ge_ext Qp; sv[0] = w; pv[0] = *g; msm_sc(&Qp, sv, pv, 1);
+        /* InnerProductProof::create with G_factors = 1, H_factors = y^-n */
+        { u8 nb[8]; for (int i = 0; i < 8; i++) nb[i] = (u8)((u64)np >> (8 * i)); tr_append(&tr, "dom-sep", (const u8 *)"ipp v1", 6); tr_append(&tr, "n", nb, 8); }
+        ge_ext *Gf = malloc(np * sizeof(ge_ext)), *Hf = malloc(np * sizeof(ge_ext));
+        memcpy(Gf, G, np * sizeof(ge_ext)); memcpy(Hf, H, np * sizeof(ge_ext));
+        size_t cur = np, round = 0;
+        while (cur != 1) {
+            cur /= 2;
+            const int first = round == 0;
+            sc c_L, c_R;
+            v_inner_product(&c_L, a, b + cur, cur); v_inner_product(&c_R, a + cur, b, cur);
+            /* L = <a_L o gf_R, G_R> + <b_R o hf_L, H_L> + c_L Q */
+            for (size_t i = 0; i < cur; i++) {
+                sv[i] = a[i]; pv[i] = Gf[cur + i];
+                if (first) sc_mul(&sv[cur + i], &b[cur + i], &y_n_inv[i]); else sv[cur + i] = b[cur + i];
+                pv[cur + i] = Hf[i];
+            }
+            sv[2 * cur] = c_L; pv[2 * cur] = Qp;
+            ge_ext Lp, Rp; msm_sc(&Lp, sv, pv, 2 * cur + 1);
+            for (size_t i = 0; i < cur; i++) {
+                sv[i] = a[cur + i]; pv[i] = Gf[i];
+                if (first) sc_mul(&sv[cur + i], &b[i], &y_n_inv[cur + i]); else sv[cur + i] = b[i];
+                pv[cur + i] = Hf[cur + i];
+            }
+            sv[2 * cur] = c_R;
+            msm_sc(&Rp, sv, pv, 2 * cur + 1);
+            u8 *lr = po + 352 + 64 * round;
+            ristretto_compress(lr, &Lp); ristretto_compress(lr + 32, &Rp);
+            tr_append(&tr, "L", lr, 32); tr_append(&tr, "R", lr + 32, 32);
+            sc u, u_inv; tr_challenge_scalar(&tr, "u", &u); sc_invert(&u_inv, &u);
+            for (size_t i = 0; i < cur; i++) {
+                sc t1, t2;
+                sc_mul(&t1, &a[i], &u); sc_mul(&t2, &u_inv, &a[cur + i]); sc_add(&a[i], &t1, &t2);
+                sc_mul(&t1, &b[i], &u_inv); sc_mul(&t2, &u, &b[cur + i]); sc_add(&b[i], &t1, &t2);
+                sc s2[2]; ge_ext p2[2];
+                s2[0] = u_inv; s2[1] = u; p2[0] = Gf[i]; p2[1] = Gf[cur + i];
+                msm_sc(&Gf[i], s2, p2, 2);
+                if (first) { sc_mul(&s2[0], &u, &y_n_inv[i]); sc_mul(&s2[1], &u_inv, &y_n_inv[cur + i]); }
+                else { s2[0] = u; s2[1] = u_inv; }
+                p2[0] = Hf[i]; p2[1] = Hf[cur + i];
+                msm_sc(&Hf[i], s2, p2, 2);
+            }
+            round++;
+        }
+        sc_tobytes(po + 352 + 64 * lg, &a[0]); sc_tobytes(po + 384 + 64 * lg, &b[0]);
+        free(s_l); free(s_r); free(l1); free(r0); free(r1); free(r3); free(a); free(b); free(zero); free(Gf); free(Hf);
+    }
+    if (do_verify) {
+        ge_ext pts8[8], *Lp = malloc((lg + 1) * sizeof(ge_ext)), *Rp = malloc((lg + 1) * sizeof(ge_ext));
+        for (int k = 0; k < 8 && result == 1; k++) if (!ristretto_decompress(&pts8[k], po + 32 * k)) result = 0;
+        sc that, tau_x, mu, pa, pb;
+        sc_from_bytes_mod_order(&that, po + 256); sc_from_bytes_mod_order(&tau_x, po + 288); sc_from_bytes_mod_order(&mu, po + 320);
+        sc_from_bytes_mod_order(&pa, po + 352 + 64 * lg); sc_from_bytes_mod_order(&pb, po + 384 + 64 * lg);
+        strobe tr; tr_new(&tr, label, label_len);
+        { u8 nb[8]; for (int i = 0; i < 8; i++) nb[i] = (u8)((u64)n >> (8 * i)); tr_append(&tr, "dom-sep", (const u8 *)"acp v1", 6); tr_append(&tr, "n", nb, 8); }
+        tr_append(&tr, "A_I", po, 32); tr_append(&tr, "A_O", po + 32, 32); tr_append(&tr, "S", po + 64, 32);
+        sc y, z, x, w, y_inv; tr_challenge_scalar(&tr, "y", &y); tr_challenge_scalar(&tr, "z", &z);
+        for (int k = 0; k < 5; k++) tr_append(&tr, TL[k], po + 96 + 32 * k, 32);
+        tr_challenge_scalar(&tr, "x", &x);
+        tr_append_scalar(&tr, "t_x", &that); tr_append_scalar(&tr, "t_x_blinding", &tau_x); tr_append_scalar(&tr, "e_blinding", &mu);
+        tr_challenge_scalar(&tr, "w", &w);
+        { u8 nb[8]; for (int i = 0; i < 8; i++) nb[i] = (u8)((u64)np >> (8 * i)); tr_append(&tr, "dom-sep", (const u8 *)"ipp v1", 6); tr_append(&tr, "n", nb, 8); }
+        sc *u_sq = malloc((lg + 1) * sizeof(sc)), *u_inv_sq = malloc((lg + 1) * sizeof(sc)), *s = malloc(np * sizeof(sc));
+        sc allinv = one;
+        for (size_t j = 0; j < lg; j++) {
+            const u8 *lr = po + 352 + 64 * j;
+            if (is_zero32(lr) || is_zero32(lr + 32)) result = 0;           /* validate_and_append_point */
+            if (result == 1 && (!ristretto_decompress(&Lp[j], lr) || !ristretto_decompress(&Rp[j], lr + 32))) result = 0;
+            tr_append(&tr, "L", lr, 32); tr_append(&tr, "R", lr + 32, 32);
+            sc u, ui; tr_challenge_scalar(&tr, "u", &u); sc_invert(&ui, &u);
+            sc_mul(&u_sq[j], &u, &u); sc_mul(&u_inv_sq[j], &ui, &ui); sc_mul(&allinv, &allinv, &ui);
+        }
+        if (result == 1) {
+            s[0] = allinv;
+            for (size_t i = 1; i < np; i++) {
+                size_t lg_i = 0; while (((size_t)2 << lg_i) <= i) lg_i++;
+                sc_mul(&s[i], &s[i - ((size_t)1 << lg_i)], &u_sq[(lg - 1) - lg_i]);
+            }
+            sc_invert(&y_inv, &y);
+            v_std_powers(y_n, &y, np, &one); v_std_powers(y_n_inv, &y_inv, np, &one); v_std_powers(z_q, &z, Q, &z);
+            v_sparse_vm(zWL, n, z_q, wr[0], cn[0], cf[0], nnz[0]);
+            v_sparse_vm(zWR, n, z_q, wr[1], cn[1], cf[1], nnz[1]);
+            v_sparse_vm(zWO, n, z_q, wr[2], cn[2], cf[2], nnz[2]);
+            v_sparse_vm(zWV, m, z_q, wr[3], cn[3], cf[3], nnz[3]);
+            v_hadamard(l_in, y_n_inv, zWR, n);
+            sc sigma, zc, xx, g_exp; v_inner_product(&sigma, l_in, zWL, n);
+            sc_mul(&xx, &x, &x);
+            v_inner_product(&zc, z_q, cv, Q); sc_add(&zc, &zc, &sigma); sc_mul(&g_exp, &xx, &zc);
+            /* check 2 */
+            sv[0] = g_exp; pv[0] = *g;
+            for (size_t j = 0; j < m; j++) { sc_mul(&sv[1 + j], &xx, &zWV[j]); pv[1 + j] = V[j]; }
+            for (int k = 0; k < 5; k++) { v_scalar_exp(&sv[1 + m + k], &x, DEG[k]); pv[1 + m + k] = pts8[3 + k]; }
+            ge_ext cand, lhs; msm_sc(&cand, sv, pv, 1 + m + 5);
+            sv[0] = that; sv[1] = tau_x; pv[0] = *g; pv[1] = *h; msm_sc(&lhs, sv, pv, 2);
+            if (!ge_ristretto_eq(&lhs, &cand)) result = 0;
+        }
+        if (result == 1) {
+            /* check 3 + InnerProductProof::verify: P + t_hat Q == a<s,G> + b<s^-1 o y^-n,H> + ab Q - sum u^2 L - sum u^-2 R */
+            sc xx, xxx, t; sc_mul(&xx, &x, &x); sc_mul(&xxx, &xx, &x);
+            size_t o = 0;
+            sv[o] = x; pv[o++] = pts8[0]; sv[o] = xx; pv[o++] = pts8[1]; sv[o] = xxx; pv[o++] = pts8[2];
+            sc_neg(&sv[o], &mu); pv[o++] = *h;
+            for (size_t i = 0; i < n; i++) { sc_mul(&sv[o], &x, &l_in[i]); pv[o++] = G[i]; }
+            for (size_t i = 0; i < np; i++) {
+                sc inner = {{0, 0, 0, 0}};
+                if (i < n) { sc_mul(&inner, &x, &zWL[i]); sc_add(&inner, &inner, &zWO[i]); }
+                sc_sub(&inner, &inner, &y_n[i]);
+                sc_mul(&sv[o], &y_n_inv[i], &inner); pv[o++] = H[i];
+            }
+            sc_mul(&sv[o], &that, &w); pv[o++] = *g;       /* t_hat Q, Q = w g */
+            ge_ext P; msm_sc(&P, sv, pv, o);
+            o = 0;
+            for (size_t i = 0; i < np; i++) { sc_mul(&sv[o], &pa, &s[i]); pv[o++] = G[i]; }
+            for (size_t i = 0; i < np; i++) { sc_mul(&t, &pb, &s[np - 1 - i]); sc_mul(&sv[o], &t, &y_n_inv[i]); pv[o++] = H[i]; }
+            sc_mul(&t, &pa, &pb); sc_mul(&sv[o], &t, &w); pv[o++] = *g;
+            for (size_t j = 0; j < lg; j++) { sc_neg(&sv[o], &u_sq[j]); pv[o++] = Lp[j]; }
+            for (size_t j = 0; j < lg; j++) { sc_neg(&sv[o], &u_inv_sq[j]); pv[o++] = Rp[j]; }
+            ge_ext rhs; msm_sc(&rhs, sv, pv, o);
+            if (!ge_ristretto_eq(&P, &rhs)) result = 0;
+        }
+        free(Lp); free(Rp); free(u_sq); free(u_inv_sq); free(s);
+    }
+    free(sv); free(pv); free(y_n); free(y_n_inv); free(z_q); free(zWL); free(zWR); free(zWO); free(zWV); free(l_in);
+    return result;
+}

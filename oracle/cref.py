@@ -47,6 +47,10 @@ def lib():
         l.orc_msm_vartime_mt.restype = None
         l.orc_acp_prove_verify.argtypes = [c.c_int, c.c_size_t, c.c_size_t, c.c_size_t] + [c.c_char_p] * 16 + [
             c.c_size_t, c.c_char_p, c.c_int]
+        l.orc_acp_fixed_proof_len.argtypes = [c.c_size_t]
+        l.orc_acp_fixed_proof_len.restype = c.c_size_t
+        l.orc_acp_fixed_prove_verify.argtypes = [c.c_size_t, c.c_size_t, c.c_size_t, c.c_char_p, c.c_char_p, c.c_char_p] + [
+            c.c_char_p] * 12 + [c.c_char_p, c.c_size_t, c.c_char_p, c.c_int, c.c_int]
         l.orc_commit_variables.argtypes = [c.c_char_p] * 4 + [c.c_size_t, c.c_char_p]
         l.orc_commit_variables.restype = None
         l.orc_scalar_ops_selftest.argtypes = [c.c_char_p] * 4
@@ -126,3 +130,49 @@ class AcpInstance:
                                         self.g, self.h, self.G, self.H, aL, aR, aO, gamma, V_pts, seed, label, len(label),
                                         out, 1 if do_verify else 0)
         return out.raw, rc
+
+
+class AcpFixedInstance:
+    """Sparse-weight instance for orc_acp_fixed_prove_verify (`fixed` mode: standard powers + IPA,
+    oracle/ipa.py).  W_* are lists of (wire, constraint, coeff) triples; G, H hold next_pow2(n) generators."""
+
+    def __init__(self, n, Q, m, WL, WR, WO, WV, c_vec: bytes, g, h, G, H):
+        import struct
+        self.n, self.Q, self.m = n, Q, m
+        mats = (WL, WR, WO, WV)
+        self.nnz = struct.pack("<4I", *[len(x) for x in mats])
+        self.wire = b"".join(struct.pack("<I", t[0]) for M in mats for t in M)
+        self.cons = b"".join(struct.pack("<I", t[1]) for M in mats for t in M)
+        self.coeff = b"".join(int(t[2]).to_bytes(32, "little") for M in mats for t in M)
+        self.c = c_vec
+        self.g, self.h = decompress(g), decompress(h)
+        self.G, self.H = decompress(G), decompress(H)
+        self.proof_len = lib().orc_acp_fixed_proof_len(n)
+
+    @classmethod
+    def from_core(cls, core):
+        """From an oracle.ipa.make_instance() core dict (points as oracle.ristretto255 tuples)."""
+        from . import ristretto255 as R
+        WL, WR, WO, WV = core["sparse"]
+        return cls(core["n"], core["Q"], core["m"], WL, WR, WO, WV, b"".join(R.sc_bytes(s) for s in core["c_vec"]),
+                   R.compress(core["g_base"]), R.compress(core["h_base"]),
+                   b"".join(R.compress(p) for p in core["G_vec"]), b"".join(R.compress(p) for p in core["H_vec"]))
+
+    def commit(self, v: bytes, gamma: bytes) -> bytes:
+        out = ctypes.create_string_buffer(PT * self.m)
+        lib().orc_commit_variables(self.g, self.h, v, gamma, self.m, out)
+        return out.raw
+
+    def _call(self, aL, aR, aO, gamma, V_pts, seed, label, buf, do_prove, do_verify):
+        return lib().orc_acp_fixed_prove_verify(self.n, self.Q, self.m, self.nnz, self.wire, self.cons, self.coeff, self.c,
+                                                self.g, self.h, self.G, self.H, aL, aR, aO, gamma, V_pts, seed, label,
+                                                len(label), buf, do_prove, do_verify)
+
+    def prove(self, aL, aR, aO, gamma, seed, label=b"test") -> bytes:
+        buf = ctypes.create_string_buffer(self.proof_len)
+        self._call(aL, aR, aO, gamma, None, seed, label, buf, 1, 0)
+        return buf.raw
+
+    def verify(self, proof: bytes, V_pts: bytes, label=b"test") -> bool:
+        buf = ctypes.create_string_buffer(proof, len(proof))
+        return self._call(None, None, None, None, V_pts, None, label, buf, 0, 1) == 1

@@ -1,0 +1,109 @@
+"""GPU parity for the `fixed` protocol mode (inner-product argument): proof bytes and
+accept/reject decisions against oracle/ipa.py (Python) and oracle/c (C restatement that folds the generators
+explicitly like bulletproofs 4.0.0, while the CUDA path folds the scalars)."""
+import pytest
+
+from oracle import cref, ipa, ristretto255 as R
+from oracle.chacha import ChaChaRng
+
+pytestmark = pytest.mark.gpu
+L = R.L
+
+
+def _sb(v):
+    return b"".join(R.sc_bytes(s) for s in v)
+
+
+def _setup(backend, k, seed, window_bits=0):
+    from bpperm_b200 import acproof as G
+    rng = ChaChaRng(bytes([seed]) * 32)
+    core, prover, V = ipa.make_instance(k, rng, dense_weights=k <= 16)
+    WL, WR, WO, WV = core["sparse"]
+    cir = G.Circuit(backend, core["n"], core["Q"], core["m"], WL, WR, WO, WV, core["c_vec"])
+    gens = G.Generators(backend, R.compress(core["g_base"]), R.compress(core["h_base"]),
+                        [R.compress(p) for p in core["G_vec"]], [R.compress(p) for p in core["H_vec"]], window_bits)
+    return core, prover, V, cir, gens, cref.AcpFixedInstance.from_core(core)
+
+
+@pytest.mark.parametrize("k", [2, 3, 5, 8])
+def test_small_decks_fixed_mode_bytes_and_decisions(backend, k):
+    from bpperm_b200 import acproof as G
+    core, prover, V, cir, gens, inst = _setup(backend, k, 60 + k)
+    seeds = [bytes([i + 1]) * 32 for i in range(3)]
+    B = len(seeds)
+    n = core["n"]
+    proofs = G.prove_batch(backend, cir, gens, _sb(prover["a_L"]) * B, _sb(prover["a_R"]) * B, _sb(prover["a_O"]) * B,
+                           _sb(prover["gamma"]) * B, b"".join(seeds), B, "fixed")
+    plen = G.proof_len(n, "fixed")
+    assert plen == ipa.proof_len(n) and len(proofs) == B * plen
+    Vc = b"".join(R.compress(p) for p in V)
+    for i, sd in enumerate(seeds):
+        pb, _ = ipa.prove(core, prover, ChaChaRng(sd))
+        assert proofs[i * plen:(i + 1) * plen] == pb, (k, i)
+        assert ipa.verify(core, V, pb)
+    assert list(G.verify_batch(backend, cir, gens, proofs, Vc * B, B, "fixed")) == [1] * B
+
+
+def test_52_card_fixed_mode_proof_is_byte_identical_to_the_c_restatement(backend):
+    """BASELINE configs[1] in `fixed` mode: k = 52 -> n = 104 padded to 128, 7 rounds, 864-byte proofs."""
+    from bpperm_b200 import acproof as G
+    core, prover, V, cir, gens, inst = _setup(backend, 52, 53)
+    seeds = [b"\x77" * 32, b"\x78" * 32, b"\x79" * 32]
+    B = len(seeds)
+    proofs = G.prove_batch(backend, cir, gens, _sb(prover["a_L"]) * B, _sb(prover["a_R"]) * B, _sb(prover["a_O"]) * B,
+                           _sb(prover["gamma"]) * B, b"".join(seeds), B, "fixed")
+    plen = G.proof_len(104, "fixed")
+    assert plen == 864
+    Vp = inst.commit(_sb(prover["v"]), _sb(prover["gamma"]))
+    for i, sd in enumerate(seeds):
+        want = inst.prove(_sb(prover["a_L"]), _sb(prover["a_R"]), _sb(prover["a_O"]), _sb(prover["gamma"]), sd)
+        assert proofs[i * plen:(i + 1) * plen] == want
+        assert inst.verify(want, Vp)
+    Vc = cref.compress(Vp)
+    assert list(G.verify_batch(backend, cir, gens, proofs, Vc * B, B, "fixed")) == [1] * B
+
+
+def test_fixed_mode_tampering_matches_the_oracle_decision_per_proof(backend):
+    from bpperm_b200 import acproof as G
+    core, prover, V, cir, gens, inst = _setup(backend, 6, 15)
+    n, m = core["n"], core["m"]
+    plen = G.proof_len(n, "fixed")
+    words = plen // 32
+    B = words + 3
+    seeds = b"".join(bytes([50 + i]) * 32 for i in range(B))
+    proofs = bytearray(G.prove_batch(backend, cir, gens, _sb(prover["a_L"]) * B, _sb(prover["a_R"]) * B, _sb(prover["a_O"]) * B,
+                                     _sb(prover["gamma"]) * B, seeds, B, "fixed"))
+    Vp = inst.commit(_sb(prover["v"]), _sb(prover["gamma"]))
+    Vc = bytearray(cref.compress(Vp) * B)
+    assert list(G.verify_batch(backend, cir, gens, bytes(proofs), bytes(Vc), B, "fixed")) == [1] * B
+    for f in range(words):                   # proof f: one bit flipped in field f
+        proofs[f * plen + 32 * f + 5] ^= 0x04
+    proofs[words * plen + 32 * 11: words * plen + 32 * 12] = bytes(32)                                  # identity L_0
+    proofs[(words + 1) * plen + 32 * 12: (words + 1) * plen + 32 * 13] = R.compress(R.pt_mul(9, R.BASEPOINT))  # wrong R_0
+    Vc[(words + 2) * 32 * m: (words + 2) * 32 * m + 32] = R.compress(R.pt_mul(5, R.BASEPOINT))          # wrong V_0
+    acc = list(G.verify_batch(backend, cir, gens, bytes(proofs), bytes(Vc), B, "fixed"))
+    want = []
+    for i in range(B):
+        Vi = cref.decompress(bytes(Vc[i * 32 * m:(i + 1) * 32 * m]))
+        want.append(1 if inst.verify(bytes(proofs[i * plen:(i + 1) * plen]), Vi) else 0)
+    assert acc == want
+    assert sum(acc) <= 1     # a flipped high bit of a scalar field may stay the same value mod l; everything else rejects
+
+
+@pytest.mark.parametrize("k,window_bits", [(200, 8), (100, 6)])
+def test_larger_deck_single_proof_uses_split_msm_and_matches_c(backend, k, window_bits):
+    """One proof of a 200-card deck (n = 400 -> 512, 9 rounds): the (proof, output) grid is tiny, so every
+    fixed-base MSM is split over several blocks; bytes must not change."""
+    from bpperm_b200 import acproof as G
+    core, prover, V, cir, gens, inst = _setup(backend, k, 77, window_bits)
+    sd = b"\x42" * 32
+    proof = G.prove_batch(backend, cir, gens, _sb(prover["a_L"]), _sb(prover["a_R"]), _sb(prover["a_O"]), _sb(prover["gamma"]),
+                          sd, 1, "fixed")
+    want = inst.prove(_sb(prover["a_L"]), _sb(prover["a_R"]), _sb(prover["a_O"]), _sb(prover["gamma"]), sd)
+    assert proof == want
+    Vp = inst.commit(_sb(prover["v"]), _sb(prover["gamma"]))
+    assert inst.verify(want, Vp)
+    assert list(G.verify_batch(backend, cir, gens, proof, cref.compress(Vp), 1, "fixed")) == [1]
+    # the same circuit in the other modes still needs exactly n generators
+    with pytest.raises(Exception):
+        G.Batch(backend, cir, gens, 1, "reference-fixed")
