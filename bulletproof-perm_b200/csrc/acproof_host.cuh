@@ -445,7 +445,7 @@ static int acp_challenge_dependent_scalars(bpp_acp_batch *b) {
     return BPP_OK;
 }
 
-// `fixed` mode tail of the prover (oracle/ipa.py prove(), bulletproofs inner_product_proof.rs create()):
+// `fixed` mode tail of the prover (bulletproofs 4.0.0 inner_product_proof.rs create() behind dalek's R1CS glue):
 // append t_x, t_x_blinding, e_blinding -> w; lg rounds of (L_j, R_j) -> u_j with a, b folded in place.
 static int acp_prove_ipa(bpp_acp_batch *b) {
     bpp_ctx *ctx = b->ctx;
@@ -605,7 +605,7 @@ extern "C" int bpp_acp_batch_upload_proofs(bpp_acp_batch *b, const uint8_t *proo
     return BPP_OK;
 }
 
-// `fixed` mode verifier (oracle/ipa.py verify()): replays the transcript including the inner-product rounds,
+// `fixed` mode verifier (bulletproofs 4.0.0 verification_scalars + the mega-check of dalek's R1CS verifier): replays the transcript including the inner-product rounds,
 // then evaluates rho * check 2 + check 3 with the inner-product verification substituted for <l,G> + <r,h'>
 // as ONE MSM per proof (2 n' + 2 fixed-base terms, m + 8 + 2 lg decompressed points) that must be the identity.
 static int acp_verify_fixed(bpp_acp_batch *b, const uint8_t verifier_seed[32]) {

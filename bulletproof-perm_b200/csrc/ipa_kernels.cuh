@@ -2,7 +2,7 @@
 //
 // SURVEY section 8 row a16 / north_star item (2): bulletproofs 4.0.0 `InnerProductProof::create`
 // (inner_product_proof.rs; Cargo.lock:47-50, un-vendored) - absent from the reference, which sends l and r
-// in the clear (circuit_lib.rs:464-468).  Restated in oracle/ipa.py and oracle/c/acproof_ref.c.
+// in the clear (circuit_lib.rs:464-468).  The CPU restatements the tests compare with live in the test tree.
 //
 // Formulation ("fold the scalars, not the points"): the folded generators of round j are
 //   G^(j)[i] = sum_t s_t G[i + t n_j],   H^(j)[i] = sum_t s_t^-1 y^-(i + t n_j) H[i + t n_j],
