@@ -336,13 +336,24 @@ static int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points
     const int W = (256 + c - 1) / c;
     const uint32_t B = 1u << (c - 1);
     const size_t WB = (size_t)W * B;
-    uint32_t L = B / 1024;
-    if (L < 1) L = 1;
-    if (L > 32) L = 32;
-    uint32_t log2L = 0;
-    while ((1u << log2L) < L) log2L++;
-    const uint32_t T = B / L;
-    const uint32_t nb = (T + 255) / 256;
+    // reduction plan: thread-serial merges of 8 nodes while more than 1024 nodes per window remain,
+    // then warp merges of 32 down to one root node per window
+    struct level { int warp; uint32_t L, T_in, T_out, loglen; };
+    level plan[8];
+    int n_levels = 0;
+    uint32_t T = B, loglen = 0;
+    size_t node_elems = 0;  // u32 elements of node storage (S and A each), ping-pong halves
+    while (T > 1) {
+        level lv;
+        if (T > 1024) { lv.warp = 0; lv.L = 8; lv.T_out = T / 8; }
+        else { lv.warp = 1; lv.L = 32; lv.T_out = (T + 31) / 32; }
+        lv.T_in = T;
+        lv.loglen = loglen;
+        plan[n_levels++] = lv;
+        if ((size_t)W * lv.T_out * 32 > node_elems) node_elems = (size_t)W * lv.T_out * 32;
+        T = lv.T_out;
+        loglen += lv.warp ? 5 : 3;
+    }
     int rc;
     if ((rc = grow(ctx, &ctx->d_counts, &ctx->cap_wb, WB))) return rc;
     if ((rc = grow(ctx, &ctx->d_offsets, &ctx->cap_offsets, WB))) return rc;
@@ -355,8 +366,8 @@ static int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points
     if ((rc = grow(ctx, &ctx->d_long, &ctx->cap_long, total_tiles / BPP_LONG_SPAN + 16))) return rc;
     uint32_t *d_nlong = ctx->d_flag + 8;
     if ((rc = grow(ctx, &ctx->d_buckets, &ctx->cap_buckets, WB * 32))) return rc;
-    {
-        size_t need = (size_t)W * T * 32;
+    if (node_elems) {
+        size_t need = 2 * node_elems;  // two ping-pong buffers in each of segS / segR
         if (need > ctx->cap_seg) {
             if (ctx->d_segS) cudaFree(ctx->d_segS);
             if (ctx->d_segR) cudaFree(ctx->d_segR);
@@ -367,8 +378,6 @@ static int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points
             ctx->cap_seg = need;
         }
     }
-    if ((rc = grow(ctx, &ctx->d_blk, &ctx->cap_blk, (size_t)3 * W * nb * 32))) return rc;
-    uint32_t *blkS = ctx->d_blk, *blkB = ctx->d_blk + (size_t)W * nb * 32, *blkR = ctx->d_blk + (size_t)2 * W * nb * 32;
 
     cudaStream_t s = ctx->stream;
     const bool prof = ctx->profiling;
@@ -397,19 +406,33 @@ static int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points
     k_bucket_fixup_long<<<ctx->sm_count * 2, 128, 0, s>>>(ctx->d_offsets, ctx->d_cursor, B, tpw, ctx->d_partials,
                                                          ctx->d_buckets, ctx->d_long, d_nlong);
     LAUNCH_CHECK(ctx);
-    const uint32_t chunks = (uint32_t)W * T;
-    k_bucket_reduce1<<<(chunks + 127) / 128, 128, 0, s>>>(ctx->d_buckets, L, chunks, ctx->d_segS, ctx->d_segR);
-    LAUNCH_CHECK(ctx);
-    k_bucket_reduce2<<<dim3(nb, W), 256, 0, s>>>(ctx->d_segS, ctx->d_segR, T, blkS, blkB, blkR);
-    LAUNCH_CHECK(ctx);
+    const uint32_t *curS = ctx->d_buckets, *curA = nullptr;
+    uint64_t red_add = 0, red_dbl = 0;
+    for (int i = 0; i < n_levels; i++) {
+        const level &lv = plan[i];
+        uint32_t *oS = ctx->d_segS + (i & 1) * node_elems, *oA = ctx->d_segR + (i & 1) * node_elems;
+        if (!lv.warp) {
+            uint32_t n_out = (uint32_t)W * lv.T_out;
+            k_node_merge_serial<<<(n_out + 127) / 128, 128, 0, s>>>(curS, curA, lv.L, lv.loglen, n_out, oS, oA);
+            red_add += (uint64_t)n_out * (2 * lv.L - 3 + (curA ? lv.L : 0));
+            red_dbl += (uint64_t)n_out * lv.loglen;
+        } else {
+            k_node_merge_warp<<<dim3((lv.T_out + 3) / 4, W), 128, 0, s>>>(curS, curA, lv.T_in, lv.loglen, lv.T_out, oS, oA);
+            red_add += (uint64_t)W * lv.T_out * (2 * (uint64_t)lv.T_in / lv.T_out + 1);  // useful additions
+            red_dbl += (uint64_t)W * lv.T_out * lv.loglen;
+        }
+        LAUNCH_CHECK(ctx);
+        curS = oS;
+        curA = oA;
+    }
     if (prof) cudaEventRecord(ctx->ev[5], s);
-    k_msm_finish<<<1, 64, 0, s>>>(blkS, blkB, blkR, nb, log2L, c, W, do_compress, d_out);
+    k_msm_finish<<<1, 32, 0, s>>>(curS, curA, c, W, do_compress, d_out);
     LAUNCH_CHECK(ctx);
     if (prof) { cudaEventRecord(ctx->ev[6], s); ctx->events_pending = true; }
     ctx->n_madd = (uint64_t)W * n;
     ctx->n_add = (uint64_t)W * (B < tpw ? B : tpw) /* fix-up of buckets cut by tile boundaries (upper bound) */ +
-                 (uint64_t)W * T * (2 * (uint64_t)L - 2) + (uint64_t)W * nb * (30 + 2 * 8 + 3) + (uint64_t)W * (3 * nb + 2) + (W - 1);
-    ctx->n_dbl = (uint64_t)c * (W - 1) + (uint64_t)W * (log2L + (nb > 1 ? 8 : 0)) + (uint64_t)W * nb * 5;
+                 red_add + 2 * (uint64_t)W;
+    ctx->n_dbl = (uint64_t)c * (W - 1) + red_dbl;
     return BPP_OK;
 }
 

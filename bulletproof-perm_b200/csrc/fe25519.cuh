@@ -55,7 +55,7 @@ FE_INLINE void fe_mad4(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, u
         "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
         "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
         "addc.u32 %8, %8, 0;"
-        : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3), "+r"(c4), "+r"(c5), "+r"(c6), "+r"(c7), "+r"(c8)
+        : "+&r"(c0), "+&r"(c1), "+&r"(c2), "+&r"(c3), "+&r"(c4), "+&r"(c5), "+&r"(c6), "+&r"(c7), "+&r"(c8)
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
 }
 // same, when the carry out of limb 7 is known to be zero
@@ -70,7 +70,7 @@ FE_INLINE void fe_mad4_nc(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3
         "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
         "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
         "madc.hi.u32 %7, %11, %12, %7;"
-        : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3), "+r"(c4), "+r"(c5), "+r"(c6), "+r"(c7)
+        : "+&r"(c0), "+&r"(c1), "+&r"(c2), "+&r"(c3), "+&r"(c4), "+&r"(c5), "+&r"(c6), "+&r"(c7)
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
 }
 
@@ -91,7 +91,7 @@ FE_INLINE void fe_reduce16(fe &r, const uint32_t *t /*16 limbs*/) {
         "addc.cc.u32 %5, %5, %13;\n\t"
         "addc.cc.u32 %6, %6, %14;\n\t"
         "addc.u32 %7, %7, %15;"
-        : "+r"(e1), "+r"(e2), "+r"(e3), "+r"(e4), "+r"(e5), "+r"(e6), "+r"(e7), "+r"(e8)
+        : "+&r"(e1), "+&r"(e2), "+&r"(e3), "+&r"(e4), "+&r"(e5), "+&r"(e6), "+&r"(e7), "+&r"(e8)
         : "r"(o0), "r"(o1), "r"(o2), "r"(o3), "r"(o4), "r"(o5), "r"(o6), "r"(o7));
     // e8 < 2^7: fold 38*e8 into limb 0 and ripple; a final carry (value wrapped past 2^256,
     // so the remainder is < 38*e8) is folded once more without further ripple.
@@ -105,7 +105,7 @@ FE_INLINE void fe_reduce16(fe &r, const uint32_t *t /*16 limbs*/) {
         "addc.cc.u32 %6, %6, 0;\n\t"
         "addc.cc.u32 %7, %7, 0;\n\t"
         "addc.u32 %8, 0, 0;"
-        : "+r"(e0), "+r"(e1), "+r"(e2), "+r"(e3), "+r"(e4), "+r"(e5), "+r"(e6), "+r"(e7), "=r"(c)
+        : "+&r"(e0), "+&r"(e1), "+&r"(e2), "+&r"(e3), "+&r"(e4), "+&r"(e5), "+&r"(e6), "+&r"(e7), "=&r"(c)
         : "r"(f));
     e0 += c * 38u;
     r.v[0] = e0; r.v[1] = e1; r.v[2] = e2; r.v[3] = e3;
@@ -154,8 +154,8 @@ FE_INLINE void fe_mul(fe &r, const fe &a, const fe &b) {
         "addc.cc.u32 %12, %27, %42;\n\t"
         "addc.cc.u32 %13, %28, %43;\n\t"
         "addc.u32 %14, %29, %44;"
-        : "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(t[8]),
-          "=r"(t[9]), "=r"(t[10]), "=r"(t[11]), "=r"(t[12]), "=r"(t[13]), "=r"(t[14]), "=r"(t[15])
+        : "=&r"(t[1]), "=&r"(t[2]), "=&r"(t[3]), "=&r"(t[4]), "=&r"(t[5]), "=&r"(t[6]), "=&r"(t[7]), "=&r"(t[8]),
+          "=&r"(t[9]), "=&r"(t[10]), "=&r"(t[11]), "=&r"(t[12]), "=&r"(t[13]), "=&r"(t[14]), "=&r"(t[15])
         : "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]), "r"(ev[8]),
           "r"(ev[9]), "r"(ev[10]), "r"(ev[11]), "r"(ev[12]), "r"(ev[13]), "r"(ev[14]), "r"(ev[15]),
           "r"(od[0]), "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(od[7]),
@@ -163,7 +163,109 @@ FE_INLINE void fe_mul(fe &r, const fe &a, const fe &b) {
     fe_reduce16(r, t);
 }
 
-FE_INLINE void fe_sqr(fe &r, const fe &a) { fe_mul(r, a, a); }
+// shorter carry chains of the same form: c[0..2k) += (x0..x(k-1)) * y, carry out added into ct
+FE_INLINE void fe_mad3(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, uint32_t &c4, uint32_t &c5,
+                       uint32_t &ct, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t y) {
+    asm("mad.lo.cc.u32 %0, %7, %10, %0;\n\t"
+        "madc.hi.cc.u32 %1, %7, %10, %1;\n\t"
+        "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"
+        "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+        "madc.lo.cc.u32 %4, %9, %10, %4;\n\t"
+        "madc.hi.cc.u32 %5, %9, %10, %5;\n\t"
+        "addc.u32 %6, %6, 0;"
+        : "+&r"(c0), "+&r"(c1), "+&r"(c2), "+&r"(c3), "+&r"(c4), "+&r"(c5), "+&r"(ct)
+        : "r"(x0), "r"(x1), "r"(x2), "r"(y));
+}
+FE_INLINE void fe_mad2(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, uint32_t &ct, uint32_t x0,
+                       uint32_t x1, uint32_t y) {
+    asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\t"
+        "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+        "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"
+        "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
+        "addc.u32 %4, %4, 0;"
+        : "+&r"(c0), "+&r"(c1), "+&r"(c2), "+&r"(c3), "+&r"(ct)
+        : "r"(x0), "r"(x1), "r"(y));
+}
+FE_INLINE void fe_mad1(uint32_t &c0, uint32_t &c1, uint32_t &ct, uint32_t x0, uint32_t y) {
+    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+        "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+        "addc.u32 %2, %2, 0;"
+        : "+&r"(c0), "+&r"(c1), "+&r"(ct)
+        : "r"(x0), "r"(y));
+}
+
+// r = a^2.  28 off-diagonal products (each counted twice by one left shift of their sum) + 8 squares
+// + 8 for the fold: 44 wide multiply-adds instead of 72.  Same even/odd accumulator layout as fe_mul;
+// every chain's carry-out lands on a limb that so far holds only earlier carries, so it cannot wrap.
+FE_INLINE void fe_sqr(fe &r, const fe &a) {
+    uint32_t ev[16], od[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) { ev[i] = 0; od[i] = 0; }
+    const uint32_t a0 = a.v[0], a1 = a.v[1], a2 = a.v[2], a3 = a.v[3], a4 = a.v[4], a5 = a.v[5], a6 = a.v[6],
+                   a7 = a.v[7];
+    fe_mad4(od[0], od[1], od[2], od[3], od[4], od[5], od[6], od[7], od[8], a1, a3, a5, a7, a0);
+    fe_mad3(ev[2], ev[3], ev[4], ev[5], ev[6], ev[7], ev[8], a2, a4, a6, a0);
+    fe_mad3(od[2], od[3], od[4], od[5], od[6], od[7], od[8], a2, a4, a6, a1);
+    fe_mad3(ev[4], ev[5], ev[6], ev[7], ev[8], ev[9], ev[10], a3, a5, a7, a1);
+    fe_mad3(od[4], od[5], od[6], od[7], od[8], od[9], od[10], a3, a5, a7, a2);
+    fe_mad2(ev[6], ev[7], ev[8], ev[9], ev[10], a4, a6, a2);
+    fe_mad2(od[6], od[7], od[8], od[9], od[10], a4, a6, a3);
+    fe_mad2(ev[8], ev[9], ev[10], ev[11], ev[12], a5, a7, a3);
+    fe_mad2(od[8], od[9], od[10], od[11], od[12], a5, a7, a4);
+    fe_mad1(ev[10], ev[11], ev[12], a6, a4);
+    fe_mad1(od[10], od[11], od[12], a6, a5);
+    fe_mad1(ev[12], ev[13], ev[14], a7, a5);
+    fe_mad1(od[12], od[13], od[14], a7, a6);
+    // s = ev + (od << 32): the off-diagonal sum, < 2^511
+    uint32_t s[16];
+    s[0] = ev[0];
+    asm("add.cc.u32 %0, %15, %30;\n\t"
+        "addc.cc.u32 %1, %16, %31;\n\t"
+        "addc.cc.u32 %2, %17, %32;\n\t"
+        "addc.cc.u32 %3, %18, %33;\n\t"
+        "addc.cc.u32 %4, %19, %34;\n\t"
+        "addc.cc.u32 %5, %20, %35;\n\t"
+        "addc.cc.u32 %6, %21, %36;\n\t"
+        "addc.cc.u32 %7, %22, %37;\n\t"
+        "addc.cc.u32 %8, %23, %38;\n\t"
+        "addc.cc.u32 %9, %24, %39;\n\t"
+        "addc.cc.u32 %10, %25, %40;\n\t"
+        "addc.cc.u32 %11, %26, %41;\n\t"
+        "addc.cc.u32 %12, %27, %42;\n\t"
+        "addc.cc.u32 %13, %28, %43;\n\t"
+        "addc.u32 %14, %29, %44;"
+        : "=&r"(s[1]), "=&r"(s[2]), "=&r"(s[3]), "=&r"(s[4]), "=&r"(s[5]), "=&r"(s[6]), "=&r"(s[7]), "=&r"(s[8]),
+          "=&r"(s[9]), "=&r"(s[10]), "=&r"(s[11]), "=&r"(s[12]), "=&r"(s[13]), "=&r"(s[14]), "=&r"(s[15])
+        : "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]), "r"(ev[8]),
+          "r"(ev[9]), "r"(ev[10]), "r"(ev[11]), "r"(ev[12]), "r"(ev[13]), "r"(ev[14]), "r"(ev[15]),
+          "r"(od[0]), "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(od[7]),
+          "r"(od[8]), "r"(od[9]), "r"(od[10]), "r"(od[11]), "r"(od[12]), "r"(od[13]), "r"(od[14]));
+    // t = 2 s + sum a_i^2 2^(64 i)
+    uint32_t t[16];
+#pragma unroll
+    for (int k = 15; k >= 1; k--) t[k] = __funnelshift_l(s[k - 1], s[k], 1);
+    t[0] = s[0] << 1;
+    asm("mad.lo.cc.u32 %0, %16, %16, %0;\n\t"
+        "madc.hi.cc.u32 %1, %16, %16, %1;\n\t"
+        "madc.lo.cc.u32 %2, %17, %17, %2;\n\t"
+        "madc.hi.cc.u32 %3, %17, %17, %3;\n\t"
+        "madc.lo.cc.u32 %4, %18, %18, %4;\n\t"
+        "madc.hi.cc.u32 %5, %18, %18, %5;\n\t"
+        "madc.lo.cc.u32 %6, %19, %19, %6;\n\t"
+        "madc.hi.cc.u32 %7, %19, %19, %7;\n\t"
+        "madc.lo.cc.u32 %8, %20, %20, %8;\n\t"
+        "madc.hi.cc.u32 %9, %20, %20, %9;\n\t"
+        "madc.lo.cc.u32 %10, %21, %21, %10;\n\t"
+        "madc.hi.cc.u32 %11, %21, %21, %11;\n\t"
+        "madc.lo.cc.u32 %12, %22, %22, %12;\n\t"
+        "madc.hi.cc.u32 %13, %22, %22, %13;\n\t"
+        "madc.lo.cc.u32 %14, %23, %23, %14;\n\t"
+        "madc.hi.u32 %15, %23, %23, %15;"
+        : "+&r"(t[0]), "+&r"(t[1]), "+&r"(t[2]), "+&r"(t[3]), "+&r"(t[4]), "+&r"(t[5]), "+&r"(t[6]), "+&r"(t[7]),
+          "+&r"(t[8]), "+&r"(t[9]), "+&r"(t[10]), "+&r"(t[11]), "+&r"(t[12]), "+&r"(t[13]), "+&r"(t[14]), "+&r"(t[15])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(a5), "r"(a6), "r"(a7));
+    fe_reduce16(r, t);
+}
 
 // r = a + b  (inputs < 2^256, output < 2^256)
 FE_INLINE void fe_add(fe &r, const fe &a, const fe &b) {
@@ -177,8 +279,8 @@ FE_INLINE void fe_add(fe &r, const fe &a, const fe &b) {
         "addc.cc.u32 %6, %15, %23;\n\t"
         "addc.cc.u32 %7, %16, %24;\n\t"
         "addc.u32 %8, 0, 0;"
-        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
-          "=r"(r.v[7]), "=r"(c)
+        : "=&r"(r.v[0]), "=&r"(r.v[1]), "=&r"(r.v[2]), "=&r"(r.v[3]), "=&r"(r.v[4]), "=&r"(r.v[5]), "=&r"(r.v[6]),
+          "=&r"(r.v[7]), "=&r"(c)
         : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]),
           "r"(a.v[7]), "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]),
           "r"(b.v[6]), "r"(b.v[7]));
@@ -196,8 +298,8 @@ FE_INLINE void fe_add(fe &r, const fe &a, const fe &b) {
             "addc.cc.u32 %5, %5, 0;\n\t"
             "addc.cc.u32 %6, %6, 0;\n\t"
             "addc.u32 %7, 0, 0;"
-            : "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]), "+r"(r.v[7]),
-              "=r"(c2));
+            : "+&r"(r.v[1]), "+&r"(r.v[2]), "+&r"(r.v[3]), "+&r"(r.v[4]), "+&r"(r.v[5]), "+&r"(r.v[6]), "+&r"(r.v[7]),
+              "=&r"(c2));
         r.v[0] += c2 * 38u;  // second wrap leaves limbs 1..7 zero and limb 0 < 38: cannot carry
     }
 }
@@ -214,8 +316,8 @@ FE_INLINE void fe_sub(fe &r, const fe &a, const fe &b) {
         "subc.cc.u32 %6, %15, %23;\n\t"
         "subc.cc.u32 %7, %16, %24;\n\t"
         "subc.u32 %8, 0, 0;"
-        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
-          "=r"(r.v[7]), "=r"(bw)
+        : "=&r"(r.v[0]), "=&r"(r.v[1]), "=&r"(r.v[2]), "=&r"(r.v[3]), "=&r"(r.v[4]), "=&r"(r.v[5]), "=&r"(r.v[6]),
+          "=&r"(r.v[7]), "=&r"(bw)
         : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]),
           "r"(a.v[7]), "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]),
           "r"(b.v[6]), "r"(b.v[7]));
@@ -233,8 +335,8 @@ FE_INLINE void fe_sub(fe &r, const fe &a, const fe &b) {
             "subc.cc.u32 %5, %5, 0;\n\t"
             "subc.cc.u32 %6, %6, 0;\n\t"
             "subc.u32 %7, 0, 0;"
-            : "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]), "+r"(r.v[7]),
-              "=r"(b2));
+            : "+&r"(r.v[1]), "+&r"(r.v[2]), "+&r"(r.v[3]), "+&r"(r.v[4]), "+&r"(r.v[5]), "+&r"(r.v[6]), "+&r"(r.v[7]),
+              "=&r"(b2));
         r.v[0] -= b2 & 38u;  // second wrap leaves the value >= 2^256-76: cannot borrow
     }
 }
@@ -267,7 +369,7 @@ FE_INLINE void fe_canon(fe &r, const fe &a) {
             "addc.cc.u32 %5, %5, 0;\n\t"
             "addc.cc.u32 %6, %6, 0;\n\t"
             "addc.u32 %7, %7, 0;"
-            : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7])
+            : "+&r"(v[0]), "+&r"(v[1]), "+&r"(v[2]), "+&r"(v[3]), "+&r"(v[4]), "+&r"(v[5]), "+&r"(v[6]), "+&r"(v[7])
             : "r"(f));
     }
     // now v < 2^255; subtract p iff v >= p, i.e. iff v + 19 has bit 255 set
@@ -280,7 +382,7 @@ FE_INLINE void fe_canon(fe &r, const fe &a) {
         "addc.cc.u32 %5, %13, 0;\n\t"
         "addc.cc.u32 %6, %14, 0;\n\t"
         "addc.u32 %7, %15, 0;"
-        : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+        : "=&r"(w[0]), "=&r"(w[1]), "=&r"(w[2]), "=&r"(w[3]), "=&r"(w[4]), "=&r"(w[5]), "=&r"(w[6]), "=&r"(w[7])
         : "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]));
     bool ge = (w[7] >> 31) != 0;
     w[7] &= 0x7fffffffu;
@@ -338,7 +440,7 @@ __device__ __noinline__ void fe_sqr_n(fe &r, const fe &a, int n) {
     fe t;
     fe_copy(t, a);
 #pragma unroll 1
-    for (int i = 0; i < n; i++) fe_mul(t, t, t);
+    for (int i = 0; i < n; i++) fe_sqr(t, t);
     fe_copy(r, t);
 }
 __device__ __noinline__ void fe_mul_noinline(fe &r, const fe &a, const fe &b) { fe_mul(r, a, b); }

@@ -118,6 +118,25 @@ FE_INLINE void ge_double(ge_ext &r, const ge_ext &p) {
     fe_mul(r.T, e, h);
 }
 
+// r = 2p without the T coordinate (r.T is left unspecified): for runs of doublings, where only the
+// last one before an addition needs T.  4 squarings + 3 multiplications.
+FE_INLINE void ge_double_p2(ge_ext &r, const ge_ext &p) {
+    fe a, b, c, e, f, g, h, t;
+    fe_sqr(a, p.X);
+    fe_sqr(b, p.Y);
+    fe_sqr(c, p.Z);
+    fe_dbl(c, c);
+    fe_add(h, a, b);
+    fe_add(t, p.X, p.Y);
+    fe_sqr(t, t);
+    fe_sub(e, h, t);
+    fe_sub(g, a, b);
+    fe_add(f, c, g);
+    fe_mul(r.X, e, f);
+    fe_mul(r.Y, g, h);
+    fe_mul(r.Z, f, g);
+}
+
 __device__ __noinline__ void ge_add_noinline(ge_ext &r, const ge_ext &p, const ge_ext &q) { ge_add(r, p, q); }
 __device__ __noinline__ void ge_double_noinline(ge_ext &r, const ge_ext &p) { ge_double(r, p); }
 

@@ -11,9 +11,9 @@
 //   k_digit_scatter   counting-sort scatter of (point index | sign) into bucket order
 //   k_bucket_accum    one thread per tile of 32 sorted entries: mixed adds (extended += affine Niels, 7M)
 //   k_bucket_fixup    stitches buckets cut by tile boundaries (+ k_bucket_fixup_long for hot buckets)
-//   k_bucket_reduce1  running sums over chunks of L buckets -> (S, R) per chunk
-//   k_bucket_reduce2  warp-shuffle suffix scans over 256 chunks -> (S, B, R) per block
-//   k_msm_finish      per-window totals, Horner over windows (c doublings each), compress
+//   k_node_merge_*    bucket running sums as a tree of (S, A) nodes: thread-serial merges of 8 while
+//                     the GPU is full, warp-shuffle merges of 32 after that
+//   k_msm_finish      last merge per window, Horner over windows (c doublings each), compress
 #pragma once
 #include "ge25519.cuh"
 
@@ -58,8 +58,17 @@ __global__ void __launch_bounds__(1024) k_window_scan(const uint32_t *__restrict
     const uint32_t base = threadIdx.x * per;
     const uint32_t *cw = counts + (size_t)w * B;
     uint32_t local = 0;
-    for (uint32_t k = 0; k < per; k++)
-        if (base + k < B) local += cw[base + k];
+    const bool vec = (per & 3u) == 0;  // B >= 4096: whole uint4 groups per thread
+    if (vec) {
+        const uint4 *cv = reinterpret_cast<const uint4 *>(cw + base);
+        for (uint32_t k = 0; k < per / 4; k++) {
+            uint4 v = cv[k];
+            local += v.x + v.y + v.z + v.w;
+        }
+    } else {
+        for (uint32_t k = 0; k < per; k++)
+            if (base + k < B) local += cw[base + k];
+    }
     // block exclusive scan of `local`
     uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t incl = local;
@@ -82,12 +91,28 @@ __global__ void __launch_bounds__(1024) k_window_scan(const uint32_t *__restrict
     }
     __syncthreads();
     uint32_t run = warp_sums[wid] + incl - local;
-    for (uint32_t k = 0; k < per; k++)
-        if (base + k < B) {
-            offsets[(size_t)w * B + base + k] = run;
-            cursor[(size_t)w * B + base + k] = run;
-            run += cw[base + k];
+    if (vec) {
+        const uint4 *cv = reinterpret_cast<const uint4 *>(cw + base);
+        uint4 *ov = reinterpret_cast<uint4 *>(offsets + (size_t)w * B + base);
+        uint4 *uv = reinterpret_cast<uint4 *>(cursor + (size_t)w * B + base);
+        for (uint32_t k = 0; k < per / 4; k++) {
+            uint4 v = cv[k], o;
+            o.x = run;
+            o.y = o.x + v.x;
+            o.z = o.y + v.y;
+            o.w = o.z + v.z;
+            run = o.w + v.w;
+            ov[k] = o;
+            uv[k] = o;
         }
+    } else {
+        for (uint32_t k = 0; k < per; k++)
+            if (base + k < B) {
+                offsets[(size_t)w * B + base + k] = run;
+                cursor[(size_t)w * B + base + k] = run;
+                run += cw[base + k];
+            }
+    }
 }
 
 __global__ void k_digit_scatter(const uint32_t *__restrict__ scalars, uint32_t n, int c, int W,
@@ -256,26 +281,49 @@ __global__ void __launch_bounds__(128) k_bucket_fixup_long(const uint32_t *__res
 }
 
 // ---- bucket reduction ---------------------------------------------------------------------------
-// Window total = sum_j (j+1) * bucket_j.  Chunk t covers buckets [tL, tL+L):
-//   S_t = sum bucket, R_t = sum (k+1) * bucket_{tL+k}   (running-sum trick, 2L-2 adds)
-// so that total = sum_t R_t + L * sum_t t * S_t.
-__global__ void __launch_bounds__(128) k_bucket_reduce1(const uint32_t *__restrict__ buckets, uint32_t L,
-                                                        uint32_t total_chunks, uint32_t *__restrict__ segS,
-                                                        uint32_t *__restrict__ segR) {
+// Window total = sum_b (b+1) * bucket_b.  The reduction works on NODES: a node covers a contiguous
+// range [lo, lo+len) of one window's buckets and carries
+//     S = sum bucket_b,          A = sum (b - lo) * bucket_b         (b in the range)
+// so that total = A_root + S_root.  Merging L adjacent nodes of equal length len:
+//     S' = sum_k S_k,            A' = sum_k A_k + len * sum_k k * S_k
+// (sum_k k*S_k by the running-sum trick, len = 2^loglen by doublings).  A bucket is a node with
+// len = 1 and A = 0.  Two kernels: a thread-serial merge of L nodes (used while there are enough
+// nodes to fill the GPU) and a warp-shuffle merge of 32 nodes (short dependency chains for the
+// few nodes left); k_msm_finish merges the last <= 32 nodes of every window and combines windows.
+__global__ void __launch_bounds__(128) k_node_merge_serial(const uint32_t *__restrict__ inS,
+                                                           const uint32_t *__restrict__ inA, uint32_t L,
+                                                           uint32_t loglen, uint32_t n_out,
+                                                           uint32_t *__restrict__ outS, uint32_t *__restrict__ outA) {
     uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= total_chunks) return;
-    const uint32_t *b = buckets + 32 * (size_t)g * L;
+    if (g >= n_out) return;
+    const uint32_t *ps = inS + 32 * (size_t)g * L;
     ge_ext run, acc, t;
-    ge_load(run, b + 32 * (size_t)(L - 1));
-    acc = run;
+    ge_load(run, ps + 32 * (size_t)(L - 1));
+    acc = run;  // after the loop: acc = sum_k k * S_k, run = sum_k S_k
 #pragma unroll 1
-    for (int k = (int)L - 2; k >= 0; k--) {
-        ge_load(t, b + 32 * (size_t)k);
+    for (int k = (int)L - 2; k >= 1; k--) {
+        ge_load(t, ps + 32 * (size_t)k);
         ge_add(run, run, t);
         ge_add(acc, acc, run);
     }
-    ge_store(segS + 32 * (size_t)g, run);
-    ge_store(segR + 32 * (size_t)g, acc);
+    if (L > 1) {
+        ge_load(t, ps);
+        ge_add(run, run, t);
+    } else {
+        ge_identity(acc);
+    }
+#pragma unroll 1
+    for (uint32_t i = 0; i < loglen; i++) ge_double(acc, acc);
+    if (inA) {
+        const uint32_t *pa = inA + 32 * (size_t)g * L;
+#pragma unroll 1
+        for (uint32_t k = 0; k < L; k++) {
+            ge_load(t, pa + 32 * (size_t)k);
+            ge_add(acc, acc, t);
+        }
+    }
+    ge_store(outS + 32 * (size_t)g, run);
+    ge_store(outA + 32 * (size_t)g, acc);
 }
 
 FE_INLINE void ge_shfl_down(ge_ext &r, const ge_ext &a, int d) {
@@ -296,146 +344,169 @@ FE_INLINE void ge_select(ge_ext &r, const ge_ext &a, bool take) {
     }
 }
 
-// Warp-level: given per-lane point S, returns in every lane  A0 = sum_lanes S  (valid in lane 0)
-// and Wt = sum_lanes lane * S (valid in lane 0).  Suffix scan + plain reduction: 10 adds deep.
-__device__ __noinline__ void warp_weighted_sum(ge_ext &sum, ge_ext &wsum, const ge_ext &S) {
+// Warp merge of 32 nodes (one per lane; identity for missing lanes).  On return lane 0 holds
+// S' in `S` and A' in `A`.  15 additions deep.
+__device__ __noinline__ void warp_node_merge(ge_ext &S, ge_ext &A, uint32_t loglen) {
     const uint32_t lane = threadIdx.x & 31;
-    ge_ext a = S, o, t;
+    ge_ext o, t;
 #pragma unroll 1
-    for (int d = 1; d < 32; d <<= 1) {  // inclusive suffix scan: a_lane = sum_{j >= lane} S_j
-        ge_shfl_down(o, a, d);
-        ge_add(t, a, o);
-        ge_select(a, t, lane + d < 32);
+    for (int d = 1; d < 32; d <<= 1) {  // inclusive suffix scan: S_lane = sum_{j >= lane} S_j
+        ge_shfl_down(o, S, d);
+        ge_add(t, S, o);
+        ge_select(S, t, lane + d < 32);
     }
-    sum = a;  // lane 0 holds the warp total
-    // sum_lanes lane*S_lane = sum_{j=1..31} suffix_j
-    ge_ext b = a;
+    // sum_k k * S_k = sum_{j = 1..31} suffix_j; the plain sum of A rides along in the same tree
+    ge_ext b = S;
     if (lane == 0) ge_identity(b);
 #pragma unroll 1
     for (int d = 16; d >= 1; d >>= 1) {
         ge_shfl_down(o, b, d);
         ge_add(t, b, o);
         ge_select(b, t, lane < (uint32_t)d);
+        ge_shfl_down(o, A, d);
+        ge_add(t, A, o);
+        ge_select(A, t, lane < (uint32_t)d);
     }
-    wsum = b;
-}
-__device__ __noinline__ void warp_plain_sum(ge_ext &sum, const ge_ext &S) {
-    const uint32_t lane = threadIdx.x & 31;
-    ge_ext b = S, o, t;
 #pragma unroll 1
-    for (int d = 16; d >= 1; d >>= 1) {
-        ge_shfl_down(o, b, d);
-        ge_add(t, b, o);
-        ge_select(b, t, lane < (uint32_t)d);
-    }
-    sum = b;
+    for (uint32_t i = 0; i < loglen; i++) ge_double(b, b);
+    ge_add(A, A, b);
 }
 
-// grid (nb, W), 256 threads.  Block handles chunks t in [256*blk, 256*blk+256) of window w
-// (identity beyond T).  Output per block: S = sum S_t, Bw = sum (t - 256 blk) S_t, R = sum R_t.
-__global__ void __launch_bounds__(256) k_bucket_reduce2(const uint32_t *__restrict__ segS,
-                                                        const uint32_t *__restrict__ segR, uint32_t T,
-                                                        uint32_t *__restrict__ blkS, uint32_t *__restrict__ blkB,
-                                                        uint32_t *__restrict__ blkR) {
-    __shared__ __align__(16) uint32_t sh[3][8][32];
-    const uint32_t w = blockIdx.y, blk = blockIdx.x, nb = gridDim.x;
-    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const uint32_t t = blk * 256 + threadIdx.x;
-    ge_ext S, R;
+// grid (ceil(T/32) warps per window, W); 128 threads = 4 warps per block.
+__global__ void __launch_bounds__(128) k_node_merge_warp(const uint32_t *__restrict__ inS,
+                                                         const uint32_t *__restrict__ inA, uint32_t T,
+                                                         uint32_t loglen, uint32_t T_out,
+                                                         uint32_t *__restrict__ outS, uint32_t *__restrict__ outA) {
+    const uint32_t w = blockIdx.y, lane = threadIdx.x & 31;
+    const uint32_t g = blockIdx.x * 4 + (threadIdx.x >> 5);  // output node within the window
+    if (g >= T_out) return;
+    const uint32_t t = g * 32 + lane;
+    ge_ext S, A;
+    ge_identity(S);
+    ge_identity(A);
     if (t < T) {
-        ge_load(S, segS + 32 * ((size_t)w * T + t));
-        ge_load(R, segR + 32 * ((size_t)w * T + t));
-    } else {
-        ge_identity(S);
-        ge_identity(R);
+        ge_load(S, inS + 32 * ((size_t)w * T + t));
+        if (inA) ge_load(A, inA + 32 * ((size_t)w * T + t));
     }
-    ge_ext ws, wb, wr;
-    warp_weighted_sum(ws, wb, S);
-    warp_plain_sum(wr, R);
+    warp_node_merge(S, A, loglen);
     if (lane == 0) {
-        ge_store(&sh[0][wid][0], ws);
-        ge_store(&sh[1][wid][0], wb);
-        ge_store(&sh[2][wid][0], wr);
-    }
-    __syncthreads();
-    if (wid == 0) {
-        if (lane < 8) {
-            ge_load(S, &sh[0][lane][0]);
-            ge_load(wb, &sh[1][lane][0]);
-            ge_load(R, &sh[2][lane][0]);
-        } else {
-            ge_identity(S);
-            ge_identity(wb);
-            ge_identity(R);
-        }
-        ge_ext bs, bx, by, br;
-        warp_weighted_sum(bs, bx, S);   // bs = sum_v Sw_v, bx = sum_v v*Sw_v
-        warp_plain_sum(by, wb);         // sum_v Bw_v
-        warp_plain_sum(br, R);
-        if (lane == 0) {
-#pragma unroll 1
-            for (int i = 0; i < 5; i++) ge_double(bx, bx);  // 32 * bx
-            ge_add(by, by, bx);
-            size_t o = 32 * ((size_t)w * nb + blk);
-            ge_store(blkS + o, bs);
-            ge_store(blkB + o, by);
-            ge_store(blkR + o, br);
-        }
+        ge_store(outS + 32 * ((size_t)w * T_out + g), S);
+        ge_store(outA + 32 * ((size_t)w * T_out + g), A);
     }
 }
 
-// Single block of 64 threads: thread w < W folds window w's block triples into the window total
-//   total_w = sum_b R_b + L * sum_b (B_b + 256 b S_b)
-// then thread 0 combines windows (Horner, c doublings per window).  With `do_compress` the
-// 32-byte encoding goes to out[0..32) and the raw extended point to out[32..160); otherwise the
-// raw extended point goes to out[0..128).
-__global__ void __launch_bounds__(64) k_msm_finish(const uint32_t *__restrict__ blkS,
-                                                   const uint32_t *__restrict__ blkB,
-                                                   const uint32_t *__restrict__ blkR, uint32_t nb, uint32_t log2L,
-                                                   int c, int W, int do_compress, uint8_t *__restrict__ out) {
+// ---- final combination: lane-parallel point arithmetic -------------------------------------------
+// The Horner combination of the window totals is one dependent chain of c*(W-1) doublings: nothing
+// to parallelise across points, and a warp instruction costs the same for 1 or 32 active lanes.  So
+// the four independent field multiplications of each half of a point operation run in four LANES
+// of one warp ("quad" form: lane k holds coordinate k of (X, Y, Z, T)); a doubling costs one
+// squaring + one multiplication of warp time instead of 4 + 4.
+FE_INLINE void fe_shfl(fe &r, const fe &a, int src) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = __shfl_sync(0xffffffffu, a.v[i], src);
+}
+FE_INLINE void fe_pick(fe &r, const fe &a, const fe &b, bool take_a) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = take_a ? a.v[i] : b.v[i];
+}
+// second half shared by doubling and addition: lane0 E*F, lane1 G*H, lane2 F*G, lane3 E*H
+FE_INLINE void quad_finish(fe &v, const fe &E, const fe &F, const fe &G, const fe &H, uint32_t lane) {
+    fe p, q, t;
+    fe_pick(t, G, F, lane == 1);
+    fe_pick(p, E, t, lane == 0 || lane == 3);
+    fe_pick(t, G, H, lane == 2);
+    fe_pick(q, F, t, lane == 0);
+    fe_mul(v, p, q);
+}
+__device__ __noinline__ void quad_double(fe &v, uint32_t lane) {
+    fe x, y, s, in, sq, A, B, Zs, D, E, F, G, H;
+    fe_shfl(x, v, 0);
+    fe_shfl(y, v, 1);
+    fe_add(s, x, y);
+    fe_pick(in, s, v, lane == 3);
+    fe_sqr(sq, in);
+    fe_shfl(A, sq, 0);
+    fe_shfl(B, sq, 1);
+    fe_shfl(Zs, sq, 2);
+    fe_shfl(D, sq, 3);
+    fe_add(H, A, B);
+    fe_sub(E, H, D);
+    fe_sub(G, A, B);
+    fe_dbl(Zs, Zs);
+    fe_add(F, Zs, G);
+    quad_finish(v, E, F, G, H, lane);
+}
+// v += the point cached at c (8 limbs each of Y+X, Y-X, Z, 2d*T; same address in every lane)
+__device__ __noinline__ void quad_add_cached(fe &v, const uint32_t *c, uint32_t lane) {
+    fe x, y, z, t, p, q, m, a, b, cc, d, E, F, G, H;
+    fe_shfl(x, v, 0);
+    fe_shfl(y, v, 1);
+    fe_shfl(z, v, 2);
+    fe_shfl(t, v, 3);
+    fe_sub(a, y, x);
+    fe_add(b, y, x);
+    fe_pick(p, a, b, lane == 0);
+    fe_pick(q, t, z, lane == 2);
+    fe_pick(p, p, q, lane < 2);
+    fe_load(q, c + 8 * (lane == 0 ? 1 : lane == 1 ? 0 : lane == 2 ? 3 : 2));
+    fe_mul(m, p, q);
+    fe_shfl(a, m, 0);
+    fe_shfl(b, m, 1);
+    fe_shfl(cc, m, 2);
+    fe_shfl(d, m, 3);
+    fe_dbl(d, d);
+    fe_sub(E, b, a);
+    fe_add(H, b, a);
+    fe_sub(F, d, cc);
+    fe_add(G, d, cc);
+    quad_finish(v, E, F, G, H, lane);
+}
+
+// One warp.  Lane w < W adds window w's root node (A + S = window total) and caches it; then the
+// warp runs Horner over the windows in quad form (c doublings + 1 addition per window) and lane 0
+// compresses.  With `do_compress` the 32-byte encoding goes to out[0..32) and the raw extended
+// point to out[32..160); otherwise the raw extended point goes to out[0..128).
+__global__ void __launch_bounds__(32) k_msm_finish(const uint32_t *__restrict__ inS,
+                                                   const uint32_t *__restrict__ inA, int c, int W,
+                                                   int do_compress, uint8_t *__restrict__ out) {
     __shared__ __align__(16) uint32_t sh[64][32];
-    const uint32_t w = threadIdx.x;
-    if ((int)w < W) {
-        ge_ext x, y, r, t;
-        ge_identity(x);  // x = sum_b b * S_b via running sum from the top
-        ge_identity(y);
-        ge_identity(r);
-        ge_ext run;
-        ge_identity(run);
-#pragma unroll 1
-        for (int b = (int)nb - 1; b >= 0; b--) {
-            size_t o = 32 * ((size_t)w * nb + b);
-            ge_load(t, blkB + o);
-            ge_add(y, y, t);
-            ge_load(t, blkR + o);
-            ge_add(r, r, t);
-            if (b >= 1) {
-                ge_load(t, blkS + o);
-                ge_add(run, run, t);
-                ge_add(x, x, run);
-            }
+    const uint32_t lane = threadIdx.x;
+    for (uint32_t w = lane; w < (uint32_t)W; w += 32) {
+        ge_ext S, A;
+        ge_load(S, inS + 32 * (size_t)w);
+        if (inA) {
+            ge_load(A, inA + 32 * (size_t)w);
+            ge_add(S, S, A);
         }
-        if (nb > 1) {
-#pragma unroll 1
-            for (int i = 0; i < 8; i++) ge_double(x, x);  // 256 * x
-            ge_add(y, y, x);
-        }
-#pragma unroll 1
-        for (uint32_t i = 0; i < log2L; i++) ge_double(y, y);
-        ge_add(r, r, y);
-        ge_store(&sh[w][0], r);
+        fe yp, ym, t2d, d2;
+        fe_add(yp, S.Y, S.X);
+        fe_sub(ym, S.Y, S.X);
+        fe_const(d2, GE_D2);
+        fe_mul(t2d, S.T, d2);
+        fe_store(&sh[w][0], yp);
+        fe_store(&sh[w][8], ym);
+        fe_store(&sh[w][16], S.Z);
+        fe_store(&sh[w][24], t2d);
     }
-    __syncthreads();
-    if (w == 0) {
-        ge_ext acc, t;
-        ge_load(acc, &sh[W - 1][0]);
+    __syncwarp();
+    // acc = identity in quad form: (0, 1, 1, 0)
+    fe v;
+    fe_set0(v);
+    v.v[0] = (lane == 1 || lane == 2) ? 1u : 0u;
 #pragma unroll 1
-        for (int k = W - 2; k >= 0; k--) {
+    for (int k = W - 1; k >= 0; k--) {
+        quad_add_cached(v, &sh[k][0], lane);
+        if (k > 0) {
 #pragma unroll 1
-            for (int i = 0; i < c; i++) ge_double(acc, acc);
-            ge_load(t, &sh[k][0]);
-            ge_add(acc, acc, t);
+            for (int i = 0; i < c; i++) quad_double(v, lane);
         }
+    }
+    ge_ext acc;
+    fe_shfl(acc.X, v, 0);
+    fe_shfl(acc.Y, v, 1);
+    fe_shfl(acc.Z, v, 2);
+    fe_shfl(acc.T, v, 3);
+    if (lane == 0) {
         if (do_compress) {
             ge_compress(out, acc);
             ge_store(reinterpret_cast<uint32_t *>(out + 32), acc);
@@ -622,22 +693,22 @@ __global__ void __launch_bounds__(256) k_pipe_probe(int mode, uint32_t seed, int
         for (int it = 0; it < iters; it++) {
 #pragma unroll
             for (int u = 0; u < 8; u++) {  // 16 32-bit multiply-adds per u, multiplier from the other half
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c0) : "r"(a0), "r"(d0));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c1) : "r"(a1), "r"(d1));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c2) : "r"(a2), "r"(d2));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c3) : "r"(a3), "r"(d3));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c4) : "r"(a0), "r"(d4));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c5) : "r"(a1), "r"(d5));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c6) : "r"(a2), "r"(d6));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c7) : "r"(a3), "r"(d7));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(d0) : "r"(a0), "r"(c0));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(d1) : "r"(a1), "r"(c1));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(d2) : "r"(a2), "r"(c2));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(d3) : "r"(a3), "r"(c3));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(d4) : "r"(a0), "r"(c4));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(d5) : "r"(a1), "r"(c5));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(d6) : "r"(a2), "r"(c6));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(d7) : "r"(a3), "r"(c7));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+&r"(c0) : "r"(a0), "r"(d0));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+&r"(c1) : "r"(a1), "r"(d1));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+&r"(c2) : "r"(a2), "r"(d2));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+&r"(c3) : "r"(a3), "r"(d3));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+&r"(c4) : "r"(a0), "r"(d4));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+&r"(c5) : "r"(a1), "r"(d5));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+&r"(c6) : "r"(a2), "r"(d6));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+&r"(c7) : "r"(a3), "r"(d7));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+&r"(d0) : "r"(a0), "r"(c0));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+&r"(d1) : "r"(a1), "r"(c1));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+&r"(d2) : "r"(a2), "r"(c2));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+&r"(d3) : "r"(a3), "r"(c3));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+&r"(d4) : "r"(a0), "r"(c4));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+&r"(d5) : "r"(a1), "r"(c5));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+&r"(d6) : "r"(a2), "r"(c6));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+&r"(d7) : "r"(a3), "r"(c7));
             }
         }
     } else if (mode == 3) {
@@ -647,10 +718,10 @@ __global__ void __launch_bounds__(256) k_pipe_probe(int mode, uint32_t seed, int
             for (int u = 0; u < 8; u++) {  // 2 add-with-carry chains of 8 (16 adds per u), cross-fed
                 asm volatile("add.cc.u32 %0,%0,%8; addc.cc.u32 %1,%1,%8; addc.cc.u32 %2,%2,%8; addc.cc.u32 %3,%3,%8;"
                              "addc.cc.u32 %4,%4,%8; addc.cc.u32 %5,%5,%8; addc.cc.u32 %6,%6,%8; addc.u32 %7,%7,%8;"
-                             : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3), "+r"(c4), "+r"(c5), "+r"(c6), "+r"(c7) : "r"(d7));
+                             : "+&r"(c0), "+&r"(c1), "+&r"(c2), "+&r"(c3), "+&r"(c4), "+&r"(c5), "+&r"(c6), "+&r"(c7) : "r"(d7));
                 asm volatile("add.cc.u32 %0,%0,%8; addc.cc.u32 %1,%1,%8; addc.cc.u32 %2,%2,%8; addc.cc.u32 %3,%3,%8;"
                              "addc.cc.u32 %4,%4,%8; addc.cc.u32 %5,%5,%8; addc.cc.u32 %6,%6,%8; addc.u32 %7,%7,%8;"
-                             : "+r"(d0), "+r"(d1), "+r"(d2), "+r"(d3), "+r"(d4), "+r"(d5), "+r"(d6), "+r"(d7) : "r"(c7));
+                             : "+&r"(d0), "+&r"(d1), "+&r"(d2), "+&r"(d3), "+&r"(d4), "+&r"(d5), "+&r"(d6), "+&r"(d7) : "r"(c7));
             }
         }
     } else if (mode == 4) {
@@ -691,7 +762,7 @@ __global__ void k_test_op(int op, const uint8_t *__restrict__ a, const uint8_t *
     if (i >= n) return;
     const uint8_t *pa = a + 32 * (size_t)i, *pb = b + 32 * (size_t)i;
     uint8_t *po = out + 32 * (size_t)i;
-    if (op <= 4) {
+    if (op <= 4 || op == 9) {
         fe x, y, r;
         fe_frombytes(x, pa);
         fe_frombytes(y, pb);
@@ -700,6 +771,7 @@ __global__ void k_test_op(int op, const uint8_t *__restrict__ a, const uint8_t *
             case 1: fe_add(r, x, y); break;
             case 2: fe_sub(r, x, y); break;
             case 3: fe_invert(r, x); break;
+            case 9: fe_sqr(r, x); break;
             default: fe_copy(r, x); break;
         }
         fe_tobytes(po, r);
@@ -709,6 +781,7 @@ __global__ void k_test_op(int op, const uint8_t *__restrict__ a, const uint8_t *
     fe x, y;
     bool ok = ge_decompress(x, y, pa);
     P.X = x; P.Y = y; fe_set1(P.Z); fe_mul(P.T, x, y);
+    P.Z.v[0] += n >> 31;  // 0 at run time; keeps Z out of ptxas' uniform datapath (see k_test_uniform_sqr)
     if (!ok) {
         for (int k = 0; k < 32; k++) po[k] = 0xff;
         return;
@@ -722,6 +795,9 @@ __global__ void k_test_op(int op, const uint8_t *__restrict__ a, const uint8_t *
         }
         ge_add(Rr, P, Q);
     } else if (op == 6) {
+        ge_double(Rr, P);
+    } else if (op == 10) {  // doubling with a compile-time Z = 1 (uniform-datapath code)
+        fe_set1(P.Z);
         ge_double(Rr, P);
     } else if (op == 7) {
         Rr = P;

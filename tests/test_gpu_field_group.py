@@ -10,7 +10,7 @@ from oracle.chacha import ChaChaRng
 pytestmark = pytest.mark.gpu
 
 P = R.P
-FE_MUL, FE_ADD, FE_SUB, FE_INVERT, FE_CANON, GE_ADD, GE_DOUBLE, GE_ROUNDTRIP, GE_SCALARMULT = range(9)
+FE_MUL, FE_ADD, FE_SUB, FE_INVERT, FE_CANON, GE_ADD, GE_DOUBLE, GE_ROUNDTRIP, GE_SCALARMULT, FE_SQR, GE_DOUBLE_Z1 = range(11)
 
 
 def _le(x):
@@ -46,6 +46,19 @@ def test_field_invert(backend):
         assert out[32 * i:32 * i + 32] == _le(pow(x % P, P - 2, P))
 
 
+def test_field_square(backend):
+    """dedicated squaring (28 doubled off-diagonal products + 8 squares) against x*x, edge limbs included"""
+    rnd = random.Random(1234)
+    xs = _edge_values() + [rnd.getrandbits(256) for _ in range(2000)]
+    for _ in range(1000):  # limbs drawn from {0, 1, 2^31, 2^32-2, 2^32-1, random}: worst cases for the carry chains
+        xs.append(sum(rnd.choice([0, 1, 0x80000000, 0xFFFFFFFE, 0xFFFFFFFF, rnd.getrandbits(32)]) << (32 * i)
+                      for i in range(8)))
+    a = b"".join(_le(x) for x in xs)
+    out = backend.test_op(FE_SQR, a, a)
+    for i, x in enumerate(xs):
+        assert out[32 * i:32 * i + 32] == _le(x * x % P), hex(x)
+
+
 def _points(n, seed):
     rng = ChaChaRng(bytes([seed]) * 32)
     return [rng.point() for _ in range(n)]
@@ -59,10 +72,12 @@ def test_point_add_double_roundtrip(backend):
     out = backend.test_op(GE_ADD, a, b)
     out2 = backend.test_op(GE_DOUBLE, a, b)
     out3 = backend.test_op(GE_ROUNDTRIP, a, b)
+    out4 = backend.test_op(GE_DOUBLE_Z1, a, b)
     for i, (p, q) in enumerate(zip(pts, qs)):
         assert out[32 * i:32 * i + 32] == R.compress(R.pt_add(p, q))
         assert out2[32 * i:32 * i + 32] == R.compress(R.pt_double(p))
         assert out3[32 * i:32 * i + 32] == R.compress(p)
+        assert out4[32 * i:32 * i + 32] == R.compress(R.pt_double(p))
 
 
 def test_point_plus_negative_is_identity(backend):
