@@ -25,7 +25,7 @@ SYMBOLS = [
     "bpp_acproof_prove_batch", "bpp_acproof_verify_batch", "bpp_acp_batch_create", "bpp_acp_batch_free",
     "bpp_acp_batch_upload_witness", "bpp_acp_batch_commit", "bpp_acp_batch_prove", "bpp_acp_batch_download_proofs",
     "bpp_acp_batch_upload_proofs", "bpp_acp_batch_verify", "bpp_acp_batch_download_accept",
-    "bpp_acp_batch_time_commit_msm",
+    "bpp_acp_batch_time_commit_msm", "bpp_acp_batch_set_host_transcripts", "bpp_transcript_script",
 ]
 
 _lib = None
@@ -109,13 +109,16 @@ def load() -> ctypes.CDLL:
     lib.bpp_acp_batch_create.argtypes = [vp, vp, vp, c.c_int, sz, u8p, sz, c.POINTER(vp)]
     lib.bpp_acp_batch_free.argtypes = [vp]
     lib.bpp_acp_batch_free.restype = None
-    lib.bpp_acp_batch_upload_witness.argtypes = [vp, u8p, u8p, u8p, u8p, u8p]
-    lib.bpp_acp_batch_commit.argtypes = [vp, u8p, c.c_char_p]
+    # host buffers as void*: bytes objects or raw addresses of pinned memory
+    lib.bpp_acp_batch_upload_witness.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.bpp_acp_batch_commit.argtypes = [vp, vp, vp]
     lib.bpp_acp_batch_prove.argtypes = [vp]
-    lib.bpp_acp_batch_download_proofs.argtypes = [vp, c.c_char_p]
-    lib.bpp_acp_batch_upload_proofs.argtypes = [vp, u8p, u8p]
+    lib.bpp_acp_batch_download_proofs.argtypes = [vp, vp]
+    lib.bpp_acp_batch_upload_proofs.argtypes = [vp, vp, vp]
     lib.bpp_acp_batch_verify.argtypes = [vp, u8p]
-    lib.bpp_acp_batch_download_accept.argtypes = [vp, c.c_char_p]
+    lib.bpp_acp_batch_download_accept.argtypes = [vp, vp]
+    lib.bpp_acp_batch_set_host_transcripts.argtypes = [vp, c.c_int]
+    lib.bpp_transcript_script.argtypes = [vp, u8p, sz, c.c_char_p, sz]
     lib.bpp_acp_batch_time_commit_msm.argtypes = [vp, c.c_int, c.POINTER(c.c_float), c.POINTER(c.c_uint64),
                                                   c.POINTER(c.c_uint64)]
     _lib = lib

@@ -107,8 +107,25 @@ class Batch:
         self.be._check(self.be._lib.bpp_acp_batch_commit(self._h, v, out))
         return out.raw if want else b""
 
+    def set_host_transcripts(self, on: bool):
+        """Fiat-Shamir on host threads (True) instead of one device thread per proof (default)."""
+        self.be._check(self.be._lib.bpp_acp_batch_set_host_transcripts(self._h, 1 if on else 0))
+
     def prove(self):
         self.be._check(self.be._lib.bpp_acp_batch_prove(self._h))
+
+    # raw-address forms for callers that own pinned host buffers (addresses as ints)
+    def upload_witness_ptr(self, aL: int, aR: int, aO: int, gamma: int, seeds: int):
+        self.be._check(self.be._lib.bpp_acp_batch_upload_witness(self._h, aL, aR, aO, gamma, seeds))
+
+    def download_proofs_ptr(self, dst: int):
+        self.be._check(self.be._lib.bpp_acp_batch_download_proofs(self._h, dst))
+
+    def upload_proofs_ptr(self, proofs: int, V: int = None):
+        self.be._check(self.be._lib.bpp_acp_batch_upload_proofs(self._h, proofs, V))
+
+    def download_accept_ptr(self, dst: int):
+        self.be._check(self.be._lib.bpp_acp_batch_download_accept(self._h, dst))
 
     def download_proofs(self) -> bytes:
         out = ctypes.create_string_buffer(self.proof_len * self.count)
@@ -157,3 +174,19 @@ def verify_batch(backend, circuit, gens, proofs, V, count, mode="reference-fixed
     backend._check(backend._lib.bpp_acproof_verify_batch(backend._ctx, circuit._h, gens._h, _MODES[mode], count, proofs, V,
                                                           label, len(label), verifier_seed, out))
     return out.raw
+
+
+def transcript_script(backend, records) -> bytes:
+    """Run a merlin::Transcript on the device.  records: ("append", label, message) or ("challenge", label, n);
+    the first record must be ("append", b"dom-sep", protocol_label) == Transcript::new(protocol_label).
+    Returns the concatenated challenge bytes."""
+    script, out_len = b"", 0
+    for op, label, arg in records:
+        if op == "append":
+            script += bytes([0, len(label)]) + label + len(arg).to_bytes(4, "little") + arg
+        else:
+            script += bytes([1, len(label)]) + label + int(arg).to_bytes(4, "little")
+            out_len += int(arg)
+    out = ctypes.create_string_buffer(max(out_len, 1))
+    backend._check(backend._lib.bpp_transcript_script(backend._ctx, script, len(script), out, out_len))
+    return out.raw[:out_len]

@@ -7,6 +7,7 @@
 
 #include "acproof_kernels.cuh"
 #include "ipa_kernels.cuh"
+#include "transcript_kernels.cuh"
 #include "host_merlin.hpp"
 
 struct bpp_circuit {
@@ -38,6 +39,11 @@ struct bpp_acp_batch {
     uint8_t *d_lr = nullptr, *h_lr = nullptr, *h_tx3 = nullptr;
     uint32_t *d_tx3 = nullptr, *d_lrext = nullptr, *d_part = nullptr;
     uint32_t fb_splits = 1;
+    // Fiat-Shamir: per-proof Merlin states on the device (default; no host round trip between kernels) or on
+    // host threads (host_transcripts: the same bytes, kept as the cross-check and for hosts that want the
+    // transcript in their own process)
+    bool host_transcripts = false;
+    uint64_t *d_tr = nullptr, *d_proto = nullptr;
     std::vector<bpp_host::Transcript> tr;
 };
 
@@ -218,7 +224,7 @@ extern "C" void bpp_acp_batch_free(bpp_acp_batch *b) {
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
     void *dev[] = {b->d_blk, b->d_seeds, b->d_wide, b->d_ext8, b->d_dyn, b->d_wsum, b->d_stat, b->d_bad, b->d_vext, b->d_vseed,
-                   b->d_pts8, b->d_proofs, b->d_V, b->d_accept, b->d_lr, b->d_tx3, b->d_lrext, b->d_part};
+                   b->d_pts8, b->d_proofs, b->d_V, b->d_accept, b->d_lr, b->d_tx3, b->d_lrext, b->d_part, b->d_tr, b->d_proto};
     for (void *p : dev)
         if (p) cudaFree(p);
     if (b->h_pts8) cudaFreeHost(b->h_pts8);
@@ -258,6 +264,16 @@ extern "C" int bpp_acp_batch_create(bpp_ctx *ctx, const bpp_circuit *cir, const 
     cudaError_t e = cudaMalloc((void **)&b->d_blk, B * b->lay.stride * 32);
     if (e == cudaSuccess) e = cudaMemsetAsync(b->d_blk, 0, B * b->lay.stride * 32, ctx->stream);
     if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_seeds, B * 32);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_tr, B * MERLIN_STATE_WORDS * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_proto, MERLIN_STATE_WORDS * 8);
+    if (e == cudaSuccess) {   // Transcript::new(label) + arithmetic_domain_sep(n): identical for every proof, hashed once
+        bpp_host::Transcript proto(b->label.data(), b->label.size());
+        proto.arithmetic_domain_sep(cir->n);
+        uint64_t st[MERLIN_STATE_WORDS];
+        proto.export_state(st);
+        e = cudaMemcpyAsync(b->d_proto, st, sizeof(st), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    }
     if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_wide, B * nch * 64);
     if (e == cudaSuccess && b->fb_splits > 1) e = cudaMalloc((void **)&b->d_part, B * 8 * b->fb_splits * 128);
     if (e == cudaSuccess && lg) e = cudaMalloc((void **)&b->d_lr, B * 2 * lg * 32);
@@ -287,6 +303,14 @@ extern "C" int bpp_acp_batch_create(bpp_ctx *ctx, const bpp_circuit *cir, const 
         return oom ? BPP_ERR_OOM : BPP_ERR_CUDA;
     }
     *out = b;
+    return BPP_OK;
+}
+
+// Fiat-Shamir location: 0 (default) = per-proof Merlin transcripts on the device, 1 = on host threads.
+// Both produce the same challenges; proofs and decisions are identical (tests/test_gpu_acproof.py).
+extern "C" int bpp_acp_batch_set_host_transcripts(bpp_acp_batch *b, int on) {
+    if (!b) return BPP_ERR_INVALID_ARG;
+    b->host_transcripts = on != 0;
     return BPP_OK;
 }
 
@@ -453,21 +477,26 @@ static int acp_prove_ipa(bpp_acp_batch *b) {
     const uint32_t B = b->B, np = L.np, lg = L.lg;
     cudaStream_t s = ctx->stream;
     int rc;
-    // t_hat, tau_x, mu are contiguous in the proof block
-    CK(ctx, cudaMemcpy2DAsync(b->h_tx3, 96, (const uint8_t *)b->d_blk + 32 * (size_t)L.that, (size_t)L.stride * 32, 96, B,
-                              cudaMemcpyDeviceToHost, s));
-    CK(ctx, cudaStreamSynchronize(s));
-    acp_parallel_for(B, [&](uint32_t p) {
-        bpp_host::Transcript &t = b->tr[p];
-        const uint8_t *sc3 = b->h_tx3 + 96 * (size_t)p;
-        t.append_scalar("t_x", sc3);
-        t.append_scalar("t_x_blinding", sc3 + 32);
-        t.append_scalar("e_blinding", sc3 + 64);
-        t.challenge_wide("w", b->h_wide + 64 * (size_t)p);
-        t.append_message("dom-sep", (const uint8_t *)"ipp v1", 6);
-        t.append_u64("n", np);
-    });
-    if ((rc = acp_put_challenges(b, L.wq, 1))) return rc;
+    if (!b->host_transcripts) {
+        k_tr_prove_w<<<(B + TR_THREADS - 1) / TR_THREADS, TR_THREADS, 0, s>>>(L, B, b->d_tr, b->d_blk);
+        LAUNCH_CHECK(ctx);
+    } else {
+        // t_hat, tau_x, mu are contiguous in the proof block
+        CK(ctx, cudaMemcpy2DAsync(b->h_tx3, 96, (const uint8_t *)b->d_blk + 32 * (size_t)L.that, (size_t)L.stride * 32, 96, B,
+                                  cudaMemcpyDeviceToHost, s));
+        CK(ctx, cudaStreamSynchronize(s));
+        acp_parallel_for(B, [&](uint32_t p) {
+            bpp_host::Transcript &t = b->tr[p];
+            const uint8_t *sc3 = b->h_tx3 + 96 * (size_t)p;
+            t.append_scalar("t_x", sc3);
+            t.append_scalar("t_x_blinding", sc3 + 32);
+            t.append_scalar("e_blinding", sc3 + 64);
+            t.challenge_wide("w", b->h_wide + 64 * (size_t)p);
+            t.append_message("dom-sep", (const uint8_t *)"ipp v1", 6);
+            t.append_u64("n", np);
+        });
+        if ((rc = acp_put_challenges(b, L.wq, 1))) return rc;
+    }
     const uint32_t gH = 2 + b->gens->n;
     for (uint32_t j = 0; j < lg; j++) {
         const uint32_t nj = np >> j, h = nj >> 1;
@@ -483,15 +512,20 @@ static int acp_prove_ipa(bpp_acp_batch *b) {
         if ((rc = acp_fb(b, sh, b->d_lrext + 32 * 2 * (size_t)j, 2 * lg))) return rc;
         k_compress_strided<<<(2 * B + 127) / 128, 128, 0, s>>>(b->d_lrext, 2 * lg, 2 * j, 2, B, b->d_lr);
         LAUNCH_CHECK(ctx);
-        CK(ctx, cudaMemcpy2DAsync(b->h_pts8, 64, b->d_lr + 64 * (size_t)j, 64 * (size_t)lg, 64, B, cudaMemcpyDeviceToHost, s));
-        CK(ctx, cudaStreamSynchronize(s));
-        acp_parallel_for(B, [&](uint32_t p) {
-            bpp_host::Transcript &t = b->tr[p];
-            t.append_point("L", b->h_pts8 + 64 * (size_t)p);
-            t.append_point("R", b->h_pts8 + 64 * (size_t)p + 32);
-            t.challenge_wide("u", b->h_wide + 64 * (size_t)p);
-        });
-        if ((rc = acp_put_challenges(b, L.u + j, 1))) return rc;
+        if (!b->host_transcripts) {
+            k_tr_prove_u<<<(B + TR_THREADS - 1) / TR_THREADS, TR_THREADS, 0, s>>>(b->d_lr, L, B, j, b->d_tr, b->d_blk);
+            LAUNCH_CHECK(ctx);
+        } else {
+            CK(ctx, cudaMemcpy2DAsync(b->h_pts8, 64, b->d_lr + 64 * (size_t)j, 64 * (size_t)lg, 64, B, cudaMemcpyDeviceToHost, s));
+            CK(ctx, cudaStreamSynchronize(s));
+            acp_parallel_for(B, [&](uint32_t p) {
+                bpp_host::Transcript &t = b->tr[p];
+                t.append_point("L", b->h_pts8 + 64 * (size_t)p);
+                t.append_point("R", b->h_pts8 + 64 * (size_t)p + 32);
+                t.challenge_wide("u", b->h_wide + 64 * (size_t)p);
+            });
+            if ((rc = acp_put_challenges(b, L.u + j, 1))) return rc;
+        }
         k_ipa_uinv<<<(B + 63) / 64, 64, 0, s>>>(L, B, j, b->d_blk);
         LAUNCH_CHECK(ctx);
         k_ipa_fold<<<dim3((h + 127) / 128, B), 128, 0, s>>>(L, j, b->d_blk);
@@ -530,24 +564,29 @@ extern "C" int bpp_acp_batch_prove(bpp_acp_batch *b) {
     }
     k_compress_strided<<<(B * 3 + 127) / 128, 128, 0, s>>>(b->d_ext8, 8, 0, 3, B, b->d_pts8);
     LAUNCH_CHECK(ctx);
-    CK(ctx, cudaMemcpyAsync(b->h_pts8, b->d_pts8, (size_t)B * 256, cudaMemcpyDeviceToHost, s));
-    CK(ctx, cudaStreamSynchronize(s));
     // transcripts: dom-sep, A_I, A_O, S -> y, z
-    {   // Transcript::new(label) + arithmetic_domain_sep(n) are identical for every proof: hash once, copy
-        bpp_host::Transcript proto(b->label.data(), b->label.size());
-        proto.arithmetic_domain_sep(n);
-        b->tr.assign(B, proto);
+    if (!b->host_transcripts) {
+        k_tr_prove_yz<<<(B + TR_THREADS - 1) / TR_THREADS, TR_THREADS, 0, s>>>(b->d_proto, b->d_pts8, L, B, b->d_tr, b->d_blk);
+        LAUNCH_CHECK(ctx);
+    } else {
+        CK(ctx, cudaMemcpyAsync(b->h_pts8, b->d_pts8, (size_t)B * 256, cudaMemcpyDeviceToHost, s));
+        CK(ctx, cudaStreamSynchronize(s));
+        {   // Transcript::new(label) + arithmetic_domain_sep(n) are identical for every proof: hash once, copy
+            bpp_host::Transcript proto(b->label.data(), b->label.size());
+            proto.arithmetic_domain_sep(n);
+            b->tr.assign(B, proto);
+        }
+        acp_parallel_for(B, [&](uint32_t p) {
+            bpp_host::Transcript &t = b->tr[p];
+            const uint8_t *pt = b->h_pts8 + 256 * (size_t)p;
+            t.append_point("A_I", pt);
+            t.append_point("A_O", pt + 32);
+            t.append_point("S", pt + 64);
+            t.challenge_wide("y", b->h_wide + 128 * (size_t)p);
+            t.challenge_wide("z", b->h_wide + 128 * (size_t)p + 64);
+        });
+        if ((rc = acp_put_challenges(b, L.y, 2))) return rc;
     }
-    acp_parallel_for(B, [&](uint32_t p) {
-        bpp_host::Transcript &t = b->tr[p];
-        const uint8_t *pt = b->h_pts8 + 256 * (size_t)p;
-        t.append_point("A_I", pt);
-        t.append_point("A_O", pt + 32);
-        t.append_point("S", pt + 64);
-        t.challenge_wide("y", b->h_wide + 128 * (size_t)p);
-        t.challenge_wide("z", b->h_wide + 128 * (size_t)p + 64);
-    });
-    if ((rc = acp_put_challenges(b, L.y, 2))) return rc;
     if ((rc = acp_challenge_dependent_scalars(b))) return rc;
     k_acp_dots<<<dim3(10, B), 128, 0, s>>>(L, 0, b->d_blk);
     LAUNCH_CHECK(ctx);
@@ -560,20 +599,25 @@ extern "C" int bpp_acp_batch_prove(bpp_acp_batch *b) {
     }
     k_compress_strided<<<(B * 5 + 127) / 128, 128, 0, s>>>(b->d_ext8, 8, 3, 5, B, b->d_pts8);
     LAUNCH_CHECK(ctx);
-    CK(ctx, cudaMemcpyAsync(b->h_pts8, b->d_pts8, (size_t)B * 256, cudaMemcpyDeviceToHost, s));
-    CK(ctx, cudaStreamSynchronize(s));
     const int mode = b->mode;
-    acp_parallel_for(B, [&](uint32_t p) {
-        bpp_host::Transcript &t = b->tr[p];
-        const uint8_t *pt = b->h_pts8 + 256 * (size_t)p + 96;
-        t.append_point("T1", pt);
-        t.append_point("T3", pt + 32);
-        t.append_point("T4", mode == 0 ? pt + 32 : pt + 64);  // circuit_lib.rs:391 appends T_3 under "T4"
-        t.append_point("T5", pt + 96);
-        t.append_point("T6", pt + 128);
-        t.challenge_wide("x", b->h_wide + 64 * (size_t)p);
-    });
-    if ((rc = acp_put_challenges(b, L.x, 1))) return rc;
+    if (!b->host_transcripts) {
+        k_tr_prove_x<<<(B + TR_THREADS - 1) / TR_THREADS, TR_THREADS, 0, s>>>(b->d_pts8, L, B, mode, b->d_tr, b->d_blk);
+        LAUNCH_CHECK(ctx);
+    } else {
+        CK(ctx, cudaMemcpyAsync(b->h_pts8, b->d_pts8, (size_t)B * 256, cudaMemcpyDeviceToHost, s));
+        CK(ctx, cudaStreamSynchronize(s));
+        acp_parallel_for(B, [&](uint32_t p) {
+            bpp_host::Transcript &t = b->tr[p];
+            const uint8_t *pt = b->h_pts8 + 256 * (size_t)p + 96;
+            t.append_point("T1", pt);
+            t.append_point("T3", pt + 32);
+            t.append_point("T4", mode == 0 ? pt + 32 : pt + 64);  // circuit_lib.rs:391 appends T_3 under "T4"
+            t.append_point("T5", pt + 96);
+            t.append_point("T6", pt + 128);
+            t.challenge_wide("x", b->h_wide + 64 * (size_t)p);
+        });
+        if ((rc = acp_put_challenges(b, L.x, 1))) return rc;
+    }
     k_acp_final<<<dim3((L.np + 127) / 128, B), 128, 0, s>>>(L, b->d_blk);
     LAUNCH_CHECK(ctx);
     k_acp_dots<<<dim3(2, B), 128, 0, s>>>(L, 10, b->d_blk);
@@ -617,44 +661,50 @@ static int acp_verify_fixed(bpp_acp_batch *b, const uint8_t verifier_seed[32]) {
     k_acp_unpack_fixed<<<dim3((b->proof_len / 32 + 127) / 128, B), 128, 0, s>>>(L, b->d_proofs, b->proof_len, b->d_blk, b->d_pts8,
                                                                                b->d_lr, b->d_tx3);
     LAUNCH_CHECK(ctx);
-    CK(ctx, cudaMemcpyAsync(b->h_pts8, b->d_pts8, (size_t)B * 256, cudaMemcpyDeviceToHost, s));
-    CK(ctx, cudaMemcpyAsync(b->h_tx3, b->d_tx3, (size_t)B * 96, cudaMemcpyDeviceToHost, s));
-    CK(ctx, cudaMemcpyAsync(b->h_lr, b->d_lr, (size_t)B * 64 * lg, cudaMemcpyDeviceToHost, s));
     CK(ctx, cudaMemcpyAsync(b->d_vseed, verifier_seed, 32, cudaMemcpyHostToDevice, s));
-    CK(ctx, cudaStreamSynchronize(s));
-    bpp_host::Transcript proto(b->label.data(), b->label.size());
-    proto.arithmetic_domain_sep(n);
-    acp_parallel_for(B, [&](uint32_t p) {
-        bpp_host::Transcript t = proto;
-        const uint8_t *pt = b->h_pts8 + 256 * (size_t)p, *sc3 = b->h_tx3 + 96 * (size_t)p, *lr = b->h_lr + 64 * (size_t)lg * p;
-        uint8_t *wide = b->h_wide + 64 * (size_t)nch * p;
-        t.append_point("A_I", pt);
-        t.append_point("A_O", pt + 32);
-        t.append_point("S", pt + 64);
-        t.challenge_wide("y", wide);
-        t.challenge_wide("z", wide + 64);
-        t.append_point("T1", pt + 96);
-        t.append_point("T3", pt + 128);
-        t.append_point("T4", pt + 160);
-        t.append_point("T5", pt + 192);
-        t.append_point("T6", pt + 224);
-        t.challenge_wide("x", wide + 128);
-        t.append_scalar("t_x", sc3);
-        t.append_scalar("t_x_blinding", sc3 + 32);
-        t.append_scalar("e_blinding", sc3 + 64);
-        t.challenge_wide("w", wide + 192);
-        t.append_message("dom-sep", (const uint8_t *)"ipp v1", 6);
-        t.append_u64("n", np);
-        for (uint32_t j = 0; j < lg; j++) {   // an identity encoding is rejected on the device (k_acp_decompress_lr)
-            t.append_point("L", lr + 64 * (size_t)j);
-            t.append_point("R", lr + 64 * (size_t)j + 32);
-            t.challenge_wide("u", wide + 256 + 64 * (size_t)j);
-        }
-    });
-    // challenges land at y, z, x, (w = verifier weight, overwritten below), then wq and u_j are placed explicitly
-    CK(ctx, cudaMemcpyAsync(b->d_wide, b->h_wide, (size_t)B * nch * 64, cudaMemcpyHostToDevice, s));
-    k_acp_put_wide_strided<<<(B * nch + 127) / 128, 128, 0, s>>>(b->d_wide, L, nch, B, b->d_blk);
-    LAUNCH_CHECK(ctx);
+    if (!b->host_transcripts) {
+        k_tr_verify<<<(B + TR_THREADS - 1) / TR_THREADS, TR_THREADS, 0, s>>>(b->d_proto, b->d_pts8, (const uint8_t *)b->d_tx3, b->d_lr,
+                                                                             L, B, 2, b->d_blk);
+        LAUNCH_CHECK(ctx);
+    } else {
+        CK(ctx, cudaMemcpyAsync(b->h_pts8, b->d_pts8, (size_t)B * 256, cudaMemcpyDeviceToHost, s));
+        CK(ctx, cudaMemcpyAsync(b->h_tx3, b->d_tx3, (size_t)B * 96, cudaMemcpyDeviceToHost, s));
+        CK(ctx, cudaMemcpyAsync(b->h_lr, b->d_lr, (size_t)B * 64 * lg, cudaMemcpyDeviceToHost, s));
+        CK(ctx, cudaStreamSynchronize(s));
+        bpp_host::Transcript proto(b->label.data(), b->label.size());
+        proto.arithmetic_domain_sep(n);
+        acp_parallel_for(B, [&](uint32_t p) {
+            bpp_host::Transcript t = proto;
+            const uint8_t *pt = b->h_pts8 + 256 * (size_t)p, *sc3 = b->h_tx3 + 96 * (size_t)p, *lr = b->h_lr + 64 * (size_t)lg * p;
+            uint8_t *wide = b->h_wide + 64 * (size_t)nch * p;
+            t.append_point("A_I", pt);
+            t.append_point("A_O", pt + 32);
+            t.append_point("S", pt + 64);
+            t.challenge_wide("y", wide);
+            t.challenge_wide("z", wide + 64);
+            t.append_point("T1", pt + 96);
+            t.append_point("T3", pt + 128);
+            t.append_point("T4", pt + 160);
+            t.append_point("T5", pt + 192);
+            t.append_point("T6", pt + 224);
+            t.challenge_wide("x", wide + 128);
+            t.append_scalar("t_x", sc3);
+            t.append_scalar("t_x_blinding", sc3 + 32);
+            t.append_scalar("e_blinding", sc3 + 64);
+            t.challenge_wide("w", wide + 192);
+            t.append_message("dom-sep", (const uint8_t *)"ipp v1", 6);
+            t.append_u64("n", np);
+            for (uint32_t j = 0; j < lg; j++) {   // an identity encoding is rejected on the device (k_acp_decompress_lr)
+                t.append_point("L", lr + 64 * (size_t)j);
+                t.append_point("R", lr + 64 * (size_t)j + 32);
+                t.challenge_wide("u", wide + 256 + 64 * (size_t)j);
+            }
+        });
+        // challenges land at y, z, x, (w = verifier weight, overwritten below), then wq and u_j are placed explicitly
+        CK(ctx, cudaMemcpyAsync(b->d_wide, b->h_wide, (size_t)B * nch * 64, cudaMemcpyHostToDevice, s));
+        k_acp_put_wide_strided<<<(B * nch + 127) / 128, 128, 0, s>>>(b->d_wide, L, nch, B, b->d_blk);
+        LAUNCH_CHECK(ctx);
+    }
     k_acp_weights<<<(B + 127) / 128, 128, 0, s>>>(b->d_vseed, L, B, 1, b->d_blk);
     LAUNCH_CHECK(ctx);
     if ((rc = acp_challenge_dependent_scalars(b))) return rc;
@@ -695,28 +745,34 @@ extern "C" int bpp_acp_batch_verify(bpp_acp_batch *b, const uint8_t verifier_see
     int rc;
     k_acp_unpack<<<dim3((b->proof_len / 32 + 127) / 128, B), 128, 0, s>>>(L, B, b->d_proofs, b->proof_len, b->d_blk, b->d_pts8);
     LAUNCH_CHECK(ctx);
-    CK(ctx, cudaMemcpyAsync(b->h_pts8, b->d_pts8, (size_t)B * 256, cudaMemcpyDeviceToHost, s));
     CK(ctx, cudaMemcpyAsync(b->d_vseed, verifier_seed, 32, cudaMemcpyHostToDevice, s));
-    CK(ctx, cudaStreamSynchronize(s));
     const int mode = b->mode;
-    bpp_host::Transcript proto(b->label.data(), b->label.size());
-    proto.arithmetic_domain_sep(n);
-    acp_parallel_for(B, [&](uint32_t p) {
-        bpp_host::Transcript t = proto;
-        const uint8_t *pt = b->h_pts8 + 256 * (size_t)p;
-        t.append_point("A_I", pt);
-        t.append_point("A_O", pt + 32);
-        t.append_point("S", pt + 64);
-        t.challenge_wide("y", b->h_wide + 192 * (size_t)p);
-        t.challenge_wide("z", b->h_wide + 192 * (size_t)p + 64);
-        t.append_point("T1", pt + 96);
-        t.append_point("T3", pt + 128);
-        t.append_point("T4", mode == 0 ? pt + 128 : pt + 160);
-        t.append_point("T5", pt + 192);
-        t.append_point("T6", pt + 224);
-        t.challenge_wide("x", b->h_wide + 192 * (size_t)p + 128);
-    });
-    if ((rc = acp_put_challenges(b, L.y, 3))) return rc;
+    if (!b->host_transcripts) {
+        k_tr_verify<<<(B + TR_THREADS - 1) / TR_THREADS, TR_THREADS, 0, s>>>(b->d_proto, b->d_pts8, nullptr, nullptr, L, B, mode,
+                                                                             b->d_blk);
+        LAUNCH_CHECK(ctx);
+    } else {
+        CK(ctx, cudaMemcpyAsync(b->h_pts8, b->d_pts8, (size_t)B * 256, cudaMemcpyDeviceToHost, s));
+        CK(ctx, cudaStreamSynchronize(s));
+        bpp_host::Transcript proto(b->label.data(), b->label.size());
+        proto.arithmetic_domain_sep(n);
+        acp_parallel_for(B, [&](uint32_t p) {
+            bpp_host::Transcript t = proto;
+            const uint8_t *pt = b->h_pts8 + 256 * (size_t)p;
+            t.append_point("A_I", pt);
+            t.append_point("A_O", pt + 32);
+            t.append_point("S", pt + 64);
+            t.challenge_wide("y", b->h_wide + 192 * (size_t)p);
+            t.challenge_wide("z", b->h_wide + 192 * (size_t)p + 64);
+            t.append_point("T1", pt + 96);
+            t.append_point("T3", pt + 128);
+            t.append_point("T4", mode == 0 ? pt + 128 : pt + 160);
+            t.append_point("T5", pt + 192);
+            t.append_point("T6", pt + 224);
+            t.challenge_wide("x", b->h_wide + 192 * (size_t)p + 128);
+        });
+        if ((rc = acp_put_challenges(b, L.y, 3))) return rc;
+    }
     k_acp_weights<<<(B + 127) / 128, 128, 0, s>>>(b->d_vseed, L, B, mode, b->d_blk);
     LAUNCH_CHECK(ctx);
     if ((rc = acp_challenge_dependent_scalars(b))) return rc;
@@ -804,4 +860,26 @@ extern "C" int bpp_acproof_verify_batch(bpp_ctx *ctx, const bpp_circuit *cir, co
     if (!rc) rc = bpp_acp_batch_download_accept(b, accept);
     bpp_acp_batch_free(b);
     return rc;
+}
+
+// ---- scripted device transcript (test hook) -----------------------------------------------------------
+extern "C" int bpp_transcript_script(bpp_ctx *ctx, const uint8_t *script, size_t len, uint8_t *out, size_t out_len) {
+    if (!ctx || !script || len == 0 || len > (1u << 24) || (!out && out_len)) return BPP_ERR_INVALID_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    uint8_t *d = nullptr;
+    CK(ctx, cudaMalloc((void **)&d, len + out_len + 64));
+    cudaError_t e = cudaMemcpyAsync(d, script, len, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        k_tr_script<<<1, 32, 0, ctx->stream>>>(d, (uint32_t)len, d + len);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess && out_len) e = cudaMemcpyAsync(out, d + len, out_len, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) {
+        ctx->last_error = cudaGetErrorString(e);
+        return BPP_ERR_CUDA;
+    }
+    return BPP_OK;
 }

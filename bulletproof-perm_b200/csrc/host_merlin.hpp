@@ -54,6 +54,11 @@ class Strobe128 {
     void meta_ad(const uint8_t *d, size_t n, bool more) { begin_op(kM | kA, more); absorb(d, n); }
     void ad(const uint8_t *d, size_t n, bool more) { begin_op(kA, more); absorb(d, n); }
     void prf(uint8_t *out, size_t n, bool more) { begin_op(kI | kA | kC, more); squeeze(out, n); }
+    // 25 little-endian lanes + pos | pos_begin << 8 | cur_flags << 16: the layout merlin_dev.cuh loads
+    void export_state(uint64_t out[26]) const {
+        memcpy(out, st_, 200);
+        out[25] = (uint64_t)pos_ | ((uint64_t)pos_begin_ << 8) | ((uint64_t)cur_flags_ << 16);
+    }
 
   private:
     static const int kR = 166;
@@ -136,6 +141,7 @@ class Transcript {
     // challenge_scalar (:62-67) squeezes 64 bytes; the wide reduction mod l runs on the device
     // (k_scalar_from_wide) or through reduce_wide() below for single values.
     void challenge_wide(const char *label, uint8_t out64[64]) { challenge_bytes(label, out64, 64); }
+    void export_state(uint64_t out[26]) const { strobe_.export_state(out); }
 
   private:
     Strobe128 strobe_;

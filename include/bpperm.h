@@ -138,8 +138,10 @@ int bpp_poly6_eval(bpp_ctx *ctx, const uint8_t t1_t6[192], const uint8_t x[32], 
  * Replaces the group/scalar arithmetic of ACProof::ArithmeticCircuitProof (circuit_lib.rs:133-585) for
  * `count` independent proofs that share one circuit and one generator set, driven in the reference's
  * call order (lib.rs:219-231): create -> challenge_wit_and_const -> compute_per_challenges -> commit_Ts
- * -> random_chall_x -> blinding_values -> verify.  Merlin transcripts (transcript_protocol.rs) run on
- * host threads inside the library; the prover's RNG is a ChaCha20 stream per proof (seed = 32 bytes ==
+ * -> random_chall_x -> blinding_values -> verify.  Merlin transcripts (transcript_protocol.rs) run one
+ * device thread per proof between the protocol's kernels (no host round trip; the common prefix
+ * Transcript::new(label) + domain separator is hashed once on the host), or on host threads when
+ * bpp_acp_batch_set_host_transcripts(b, 1) is set - same bytes either way; the prover's RNG is a ChaCha20 stream per proof (seed = 32 bytes ==
  * rand_chacha::ChaCha20Rng::from_seed), drawn in the reference's order alpha, beta, ro, s_l[], s_r[],
  * tau_1, tau_3, tau_4, tau_5, tau_6 (circuit_lib.rs:180-182,213-214,361-404).
  *   mode 0 "reference"        what the reference code computes, defects included; its
@@ -191,6 +193,13 @@ int bpp_acp_batch_download_proofs(bpp_acp_batch *b, uint8_t *proofs_out);
 int bpp_acp_batch_upload_proofs(bpp_acp_batch *b, const uint8_t *proofs, const uint8_t *V /* nullable */);
 int bpp_acp_batch_verify(bpp_acp_batch *b, const uint8_t verifier_seed[32]);
 int bpp_acp_batch_download_accept(bpp_acp_batch *b, uint8_t *accept);
+/* Fiat-Shamir location: 0 (default) per-proof Merlin transcripts on the device, 1 on host threads. */
+int bpp_acp_batch_set_host_transcripts(bpp_acp_batch *b, int on);
+/* merlin::Transcript on the device, scripted (test hook for the Merlin KAT and framing edge cases): records
+ * op (1 B: 0 append_message, 1 challenge_bytes) | label_len (1 B) | label | n (4 B LE) | message (op 0);
+ * the transcript is Transcript::new(first record's message) when the first record is labelled "dom-sep";
+ * challenge outputs are concatenated into out (out_len = sum of the challenge lengths). */
+int bpp_transcript_script(bpp_ctx *ctx, const uint8_t *script, size_t len, uint8_t *out, size_t out_len);
 /* measurement hook: the A_I-shaped fixed-base MSM kernel alone, timed with CUDA events over `reps` launches */
 int bpp_acp_batch_time_commit_msm(bpp_acp_batch *b, int reps, float *ms_avg, uint64_t *mixed_adds, uint64_t *full_adds);
 
@@ -212,7 +221,8 @@ int bpp_last_op_counts(bpp_ctx *ctx, uint64_t *mixed_adds, uint64_t *full_adds, 
 
 /* ---- element-wise self-test hooks (used by tests/ to compare single operations with the oracle) */
 enum { BPP_TEST_FE_MUL = 0, BPP_TEST_FE_ADD, BPP_TEST_FE_SUB, BPP_TEST_FE_INVERT, BPP_TEST_FE_CANON,
-       BPP_TEST_GE_ADD, BPP_TEST_GE_DOUBLE, BPP_TEST_GE_COMPRESS_ROUNDTRIP, BPP_TEST_GE_SCALARMULT };
+       BPP_TEST_GE_ADD, BPP_TEST_GE_DOUBLE, BPP_TEST_GE_COMPRESS_ROUNDTRIP, BPP_TEST_GE_SCALARMULT,
+       BPP_TEST_FE_SQR, BPP_TEST_GE_DOUBLE_Z1 /* doubling with a compile-time Z = 1 */ };
 /* a, b: n x 32-byte operands (points as compressed encodings); out: n x 32 bytes. */
 int bpp_test_op(bpp_ctx *ctx, int op, const uint8_t *a, const uint8_t *b, uint8_t *out, size_t n);
 
