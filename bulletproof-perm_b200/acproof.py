@@ -37,6 +37,7 @@ class Circuit:
         backend._check(backend._lib.bpp_circuit_create(backend._ctx, n, Q, m, nnz, wire, cons, coeff,
                                                         scalars_to_bytes(c_vec), ctypes.byref(h)))
         self._h = h
+        backend._adopt(self)
 
     @classmethod
     def from_dense(cls, backend, W_L, W_R, W_O, W_V, c_vec):
@@ -46,9 +47,9 @@ class Circuit:
         return cls(backend, len(W_L), len(W_L[0]), len(W_V), trip(W_L), trip(W_R), trip(W_O), trip(W_V), c_vec)
 
     def free(self):
-        if self._h:
+        if self._h and self.be._ctx:
             self.be._lib.bpp_circuit_free(self.be._ctx, self._h)
-            self._h = None
+        self._h = None
 
 
 class Generators:
@@ -62,11 +63,12 @@ class Generators:
         backend._check(backend._lib.bpp_gens_create(backend._ctx, g, h, b"".join(G), b"".join(H), len(G), window_bits,
                                                      ctypes.byref(hnd)))
         self._h = hnd
+        backend._adopt(self)
 
     def free(self):
-        if self._h:
+        if self._h and self.be._ctx:
             self.be._lib.bpp_gens_free(self.be._ctx, self._h)
-            self._h = None
+        self._h = None
 
 
 def next_pow2(n: int) -> int:
@@ -94,6 +96,7 @@ class Batch:
         backend._check(backend._lib.bpp_acp_batch_create(backend._ctx, circuit._h, gens._h, self.mode, count, label,
                                                           len(label), ctypes.byref(h)))
         self._h = h
+        backend._adopt(self)
         self.proof_len = proof_len(circuit.n, self.mode)
 
     def upload_witness(self, aL: bytes, aR: bytes, aO: bytes, gamma: bytes, seeds: bytes):
@@ -110,6 +113,10 @@ class Batch:
     def set_host_transcripts(self, on: bool):
         """Fiat-Shamir on host threads (True) instead of one device thread per proof (default)."""
         self.be._check(self.be._lib.bpp_acp_batch_set_host_transcripts(self._h, 1 if on else 0))
+
+    def set_batch_rlc(self, on: bool):
+        """Verify with one random-linear-combination MSM over the batch first (default) or per proof only."""
+        self.be._check(self.be._lib.bpp_acp_batch_set_batch_rlc(self._h, 1 if on else 0))
 
     def prove(self):
         self.be._check(self.be._lib.bpp_acp_batch_prove(self._h))
@@ -150,9 +157,9 @@ class Batch:
         return ms.value, madd.value, add.value
 
     def free(self):
-        if self._h:
+        if self._h and self.be._ctx:
             self.be._lib.bpp_acp_batch_free(self._h)
-            self._h = None
+        self._h = None
 
     def __del__(self):
         try:

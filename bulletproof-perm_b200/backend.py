@@ -10,6 +10,7 @@ here in its canonical 32-byte encoding.
 from __future__ import annotations
 
 import ctypes
+import weakref
 from typing import Iterable, Sequence, Union
 
 from . import _lib
@@ -38,14 +39,15 @@ class Points:
 
     def __init__(self, backend: "Backend", handle: int, n: int):
         self._backend, self._h, self.n = backend, handle, n
+        backend._adopt(self)
 
     def __len__(self):
         return self.n
 
     def free(self):
-        if self._h:
+        if self._h and self._backend._ctx:
             self._backend._lib.bpp_points_free(self._backend._ctx, self._h)
-            self._h = None
+        self._h = None
 
     def __del__(self):
         try:
@@ -63,6 +65,10 @@ class Backend:
             raise _lib.BppError(rc, self._lib.bpp_strerror(rc).decode())
         self._ctx = ctx
         self.device = device
+        self._children = weakref.WeakSet()   # device objects created on this context: freed before it
+
+    def _adopt(self, child):
+        self._children.add(child)
 
     # -- plumbing -------------------------------------------------------------------------------
     def _check(self, rc: int):
@@ -72,6 +78,11 @@ class Backend:
 
     def close(self):
         if self._ctx:
+            for child in list(self._children):
+                try:
+                    child.free()
+                except Exception:
+                    pass
             self._lib.bpp_free(self._ctx)
             self._ctx = None
 

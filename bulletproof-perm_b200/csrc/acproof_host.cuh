@@ -44,6 +44,12 @@ struct bpp_acp_batch {
     // transcript in their own process)
     bool host_transcripts = false;
     uint64_t *d_tr = nullptr, *d_proto = nullptr;
+    // batch verification by random linear combination (k_rlc_*): scalars of the one MSM over the batch's
+    // dynamic points + the shared generators (appended to d_dyn), its compressed result, the fall-back flag
+    bool batch_rlc = true;
+    uint32_t *d_rlc_sc = nullptr, *d_rlc_flag = nullptr;
+    uint8_t *d_rlc_out = nullptr;
+    uint32_t *h_rlc_flag = nullptr;
     std::vector<bpp_host::Transcript> tr;
 };
 
@@ -70,6 +76,7 @@ static acp_layout acp_make_layout(uint32_t n_, uint32_t Q, uint32_t m, int mode)
     L.vg = take(1); L.vh = take(1); L.vG = take(np); L.vH = take(np); L.vd = take(m + 8 + 2 * L.lg);
     L.wq = take(1); L.u = take(L.lg); L.uinv = take(L.lg); L.cl = take(2); L.pa = take(1); L.pb = take(1);
     L.ptab = take(mode == 2 ? 3 * IPA_MAX_LG : 0);
+    L.rho = take(1);
     L.stride = (o + 3) & ~3u;
     return L;
 }
@@ -224,7 +231,7 @@ extern "C" void bpp_acp_batch_free(bpp_acp_batch *b) {
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
     void *dev[] = {b->d_blk, b->d_seeds, b->d_wide, b->d_ext8, b->d_dyn, b->d_wsum, b->d_stat, b->d_bad, b->d_vext, b->d_vseed,
-                   b->d_pts8, b->d_proofs, b->d_V, b->d_accept, b->d_lr, b->d_tx3, b->d_lrext, b->d_part, b->d_tr, b->d_proto};
+                   b->d_pts8, b->d_proofs, b->d_V, b->d_accept, b->d_lr, b->d_tx3, b->d_lrext, b->d_part, b->d_tr, b->d_proto, b->d_rlc_sc, b->d_rlc_flag, b->d_rlc_out};
     for (void *p : dev)
         if (p) cudaFree(p);
     if (b->h_pts8) cudaFreeHost(b->h_pts8);
@@ -232,6 +239,7 @@ extern "C" void bpp_acp_batch_free(bpp_acp_batch *b) {
     if (b->h_proofs) cudaFreeHost(b->h_proofs);
     if (b->h_lr) cudaFreeHost(b->h_lr);
     if (b->h_tx3) cudaFreeHost(b->h_tx3);
+    if (b->h_rlc_flag) cudaFreeHost(b->h_rlc_flag);
     delete b;
 }
 
@@ -282,7 +290,13 @@ extern "C" int bpp_acp_batch_create(bpp_ctx *ctx, const bpp_circuit *cir, const 
     if (e == cudaSuccess && lg) e = cudaMallocHost((void **)&b->h_lr, B * 2 * lg * 32);
     if (e == cudaSuccess && lg) e = cudaMallocHost((void **)&b->h_tx3, B * 3 * 32);
     if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_ext8, B * 8 * 128);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_dyn, B * per * 96);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_dyn, (B * per + gens->n_gens) * 96);   // + the shared generators (RLC batch MSM)
+    if (e == cudaSuccess) e = cudaMemcpyAsync(b->d_dyn + 24 * B * per, gens->d_niels, (size_t)gens->n_gens * 96, cudaMemcpyDeviceToDevice,
+                                              ctx->stream);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_rlc_sc, (B * per + gens->n_gens) * 32);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_rlc_flag, 64);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_rlc_out, 256);
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&b->h_rlc_flag, 64);
     if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_wsum, B * DYN_W * 128);
     if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_stat, B * 128);
     if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_bad, B * 4);
@@ -303,6 +317,14 @@ extern "C" int bpp_acp_batch_create(bpp_ctx *ctx, const bpp_circuit *cir, const 
         return oom ? BPP_ERR_OOM : BPP_ERR_CUDA;
     }
     *out = b;
+    return BPP_OK;
+}
+
+// Verification strategy: 1 (default) = one random-linear-combination MSM over the whole batch first, per-proof
+// kernels only if it fails (some proof is invalid); 0 = always per proof.  Decisions are identical.
+extern "C" int bpp_acp_batch_set_batch_rlc(bpp_acp_batch *b, int on) {
+    if (!b) return BPP_ERR_INVALID_ARG;
+    b->batch_rlc = on != 0;
     return BPP_OK;
 }
 
@@ -649,6 +671,37 @@ extern "C" int bpp_acp_batch_upload_proofs(bpp_acp_batch *b, const uint8_t *proo
     return BPP_OK;
 }
 
+static int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points *pts, size_t off, size_t n, uint8_t *d_out,
+                       int do_compress);
+
+// One MSM over the batch (see k_rlc_weights).  *decided = true when every proof's accept byte is final.
+static int acp_verify_rlc(bpp_acp_batch *b, uint32_t per, int check_t, bool *decided) {
+    bpp_ctx *ctx = b->ctx;
+    const acp_layout &L = b->lay;
+    const uint32_t B = b->B, nstat = b->gens->n_gens;
+    cudaStream_t s = ctx->stream;
+    *decided = false;
+    const size_t N = (size_t)B * per + nstat;
+    k_rlc_weights<<<(B + 127) / 128, 128, 0, s>>>(b->d_vseed, L, B, check_t, b->d_bad, L.rho, b->d_blk);
+    LAUNCH_CHECK(ctx);
+    k_rlc_dyn_scalars<<<dim3((per + 127) / 128, B), 128, 0, s>>>(L, per, B, L.rho, b->d_blk, b->d_rlc_sc);
+    LAUNCH_CHECK(ctx);
+    k_rlc_stat_scalars<<<nstat, 128, 0, s>>>(L, nstat, B, L.rho, b->d_blk, b->d_rlc_sc + 8 * (size_t)B * per);
+    LAUNCH_CHECK(ctx);
+    bpp_points view;
+    view.niels = b->d_dyn;
+    view.n = N;
+    int rc = msm_enqueue(ctx, b->d_rlc_sc, &view, 0, N, b->d_rlc_out, 1);
+    view.niels = nullptr;
+    if (rc) return rc;
+    k_rlc_accept<<<(B + 127) / 128, 128, 0, s>>>(b->d_rlc_out, L, B, L.rho, b->d_blk, b->d_accept, b->d_rlc_flag);
+    LAUNCH_CHECK(ctx);
+    CK(ctx, cudaMemcpyAsync(b->h_rlc_flag, b->d_rlc_flag, 4, cudaMemcpyDeviceToHost, s));
+    CK(ctx, cudaStreamSynchronize(s));
+    *decided = b->h_rlc_flag[0] == 0;
+    return BPP_OK;
+}
+
 // `fixed` mode verifier (bulletproofs 4.0.0 verification_scalars + the mega-check of dalek's R1CS verifier): replays the transcript including the inner-product rounds,
 // then evaluates rho * check 2 + check 3 with the inner-product verification substituted for <l,G> + <r,h'>
 // as ONE MSM per proof (2 n' + 2 fixed-base terms, m + 8 + 2 lg decompressed points) that must be the identity.
@@ -719,6 +772,11 @@ static int acp_verify_fixed(bpp_acp_batch *b, const uint8_t verifier_seed[32]) {
     LAUNCH_CHECK(ctx);
     k_acp_vscal_fixed<<<dim3((np + m + 1 + 127) / 128, B), 128, 0, s>>>(L, b->d_blk);
     LAUNCH_CHECK(ctx);
+    if (b->batch_rlc && B >= 8) {
+        bool decided = false;
+        if ((rc = acp_verify_rlc(b, per, 0, &decided))) return rc;
+        if (decided) return BPP_OK;
+    }
     {
         fb_shape sh = acp_shape(1);
         acp_seg(sh, L.vg, 0, 0, 2 * np + 2);
@@ -783,6 +841,11 @@ extern "C" int bpp_acp_batch_verify(bpp_acp_batch *b, const uint8_t verifier_see
     LAUNCH_CHECK(ctx);
     k_acp_vscal<<<dim3((n + m + 1 + 127) / 128, B), 128, 0, s>>>(L, b->d_blk);
     LAUNCH_CHECK(ctx);
+    if (b->batch_rlc && mode != 0 && B >= 8) {   // `reference` mode never accepts: nothing to gain from the combined check
+        bool decided = false;
+        if ((rc = acp_verify_rlc(b, per, 1, &decided))) return rc;
+        if (decided) return BPP_OK;
+    }
     {
         fb_shape sh = acp_shape(1);
         acp_seg(sh, L.vg, 0, 0, 2 * n + 2);

@@ -28,6 +28,7 @@ struct acp_layout {
     uint32_t tc, tsel, sigma;                      // t1..t6, the five committed values, delta(y,z)
     uint32_t l, r, that, taux, mu;                 // proof scalars
     uint32_t vg, vh, vG, vH, vd;                   // verifier MSM scalars: static (contiguous g,h,G,H), dynamic (m+8)
+    uint32_t rho;                                  // batch verification weight (k_rlc_weights)
     uint32_t wq, u, uinv, cl, pa, pb, ptab;        // `fixed` mode: challenge w, u_j / u_j^-1 (lg each), w*c_L, w*c_R,
                                                    // the proof's a and b, 3 x IPA_MAX_LG squarings for the power tables
 };
@@ -721,4 +722,99 @@ __global__ void __launch_bounds__(64) k_dyn_horner_accept(acp_layout lay, uint32
     sc_load(that, ACP_PTR(blk, lay, p, lay.that));
     sc_load(lr, ACP_PTR(blk, lay, p, lay.dots + 10));
     accept[p] = (ident && (!check_t || sc_eq(that, lr)) && bad[p] == 0) ? 1 : 0;
+}
+
+// ---- batch verification by random linear combination ---------------------------------------------------
+// Every proof's check is "one MSM is the identity" (k_acp_vscal / k_acp_vscal_fixed give its scalars).  With
+// independent verifier weights rho_p, sum_p rho_p * MSM_p is ONE Pippenger MSM over the batch's
+// B x per decompressed points plus the shared generators (whose scalars add up across proofs): c = 16
+// windows instead of per-proof 4-bit windows, i.e. 16 mixed adds per point instead of ~64.  It is the
+// identity for an all-valid batch and, for any invalid proof, a non-identity except with probability
+// ~2^-252; on failure the caller falls back to the per-proof kernels, so per-proof decisions are unchanged.
+// rho_p = Scalar::random from the verifier's ChaCha20 stream (key = verifier seed, block p, stream word 1);
+// proofs that already failed a cheap check (bad encoding, t != <l, r>) get rho_p = 0 and are rejected here.
+__global__ void k_rlc_weights(const uint32_t *__restrict__ seed8, acp_layout lay, uint32_t B, int check_t,
+                              const uint32_t *__restrict__ bad, uint32_t rho_off, uint32_t *__restrict__ blk) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    uint32_t s[16], x[16];
+    s[0] = 0x61707865u; s[1] = 0x3320646eu; s[2] = 0x79622d32u; s[3] = 0x6b206574u;
+    for (int i = 0; i < 8; i++) s[4 + i] = seed8[i];
+    s[12] = p; s[13] = 0; s[14] = 1; s[15] = 0;
+    for (int i = 0; i < 16; i++) x[i] = s[i];
+#pragma unroll 1
+    for (int rd = 0; rd < 10; rd++) {
+        CHACHA_QR(x[0], x[4], x[8], x[12]) CHACHA_QR(x[1], x[5], x[9], x[13])
+        CHACHA_QR(x[2], x[6], x[10], x[14]) CHACHA_QR(x[3], x[7], x[11], x[15])
+        CHACHA_QR(x[0], x[5], x[10], x[15]) CHACHA_QR(x[1], x[6], x[11], x[12])
+        CHACHA_QR(x[2], x[7], x[8], x[13]) CHACHA_QR(x[3], x[4], x[9], x[14])
+    }
+    for (int i = 0; i < 16; i++) x[i] += s[i];
+    sc r;
+    sc_from_wide(r, x);
+    bool ok = bad[p] == 0;
+    if (check_t) {
+        sc that, lr;
+        sc_load(that, ACP_PTR(blk, lay, p, lay.that));
+        sc_load(lr, ACP_PTR(blk, lay, p, lay.dots + 10));
+        ok = ok && sc_eq(that, lr);
+    }
+    if (!ok) sc_set0(r);
+    sc_store(ACP_PTR(blk, lay, p, rho_off), r);
+}
+// out[p * per + k] = rho_p * vd_p[k]
+__global__ void __launch_bounds__(128) k_rlc_dyn_scalars(acp_layout lay, uint32_t per, uint32_t B, uint32_t rho_off,
+                                                         const uint32_t *__restrict__ blk, uint32_t *__restrict__ out) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
+    if (k >= per) return;
+    sc rho, v;
+    sc_load(rho, ACP_PTR(blk, lay, p, rho_off));
+    sc_load(v, ACP_PTR(blk, lay, p, lay.vd + k));
+    sc_mul(v, v, rho);
+    sc_store(out + 8 * ((size_t)p * per + k), v);
+}
+// out[i] = sum_p rho_p * vstat_p[i] for the nstat shared generators (g, h, G[], H[]); block per generator
+__global__ void __launch_bounds__(128) k_rlc_stat_scalars(acp_layout lay, uint32_t nstat, uint32_t B, uint32_t rho_off,
+                                                          const uint32_t *__restrict__ blk, uint32_t *__restrict__ out) {
+    __shared__ __align__(16) uint32_t red[128][8];
+    const uint32_t i = blockIdx.x;
+    sc acc, rho, v, rr;
+    sc_set0(acc);
+    sc_const(rr, SC_R2);
+    for (uint32_t p = threadIdx.x; p < B; p += 128) {
+        sc_load(rho, ACP_PTR(blk, lay, p, rho_off));
+        sc_load(v, ACP_PTR(blk, lay, p, lay.vg + i));
+        sc_mont(v, v, rho);      // rho * v / R; the factor R is restored once after the reduction
+        sc_add(acc, acc, v);
+    }
+    sc_store(&red[threadIdx.x][0], acc);
+    __syncthreads();
+    for (uint32_t d = 64; d >= 1; d >>= 1) {
+        if (threadIdx.x < d) {
+            sc a, b2;
+            sc_load(a, &red[threadIdx.x][0]);
+            sc_load(b2, &red[threadIdx.x + d][0]);
+            sc_add(a, a, b2);
+            sc_store(&red[threadIdx.x][0], a);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        sc_load(acc, &red[0][0]);
+        sc_mont(acc, acc, rr);
+        sc_store(out + 8 * (size_t)i, acc);
+    }
+}
+// enc32 = compressed result of the batch MSM: all-zero bytes <=> identity.  accept[p] = identity and rho_p != 0;
+// flag[0] = 1 when the combination is not the identity (caller falls back to per-proof verification).
+__global__ void k_rlc_accept(const uint8_t *__restrict__ enc32, acp_layout lay, uint32_t B, uint32_t rho_off,
+                             const uint32_t *__restrict__ blk, uint8_t *__restrict__ accept, uint32_t *__restrict__ flag) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    uint32_t o = 0;
+    for (int i = 0; i < 32; i++) o |= enc32[i];
+    sc rho;
+    sc_load(rho, ACP_PTR(blk, lay, p, rho_off));
+    accept[p] = (o == 0 && !sc_is_zero(rho)) ? 1 : 0;
+    if (p == 0) flag[0] = o == 0 ? 0u : 1u;
 }

@@ -193,6 +193,11 @@ int bpp_acp_batch_download_proofs(bpp_acp_batch *b, uint8_t *proofs_out);
 int bpp_acp_batch_upload_proofs(bpp_acp_batch *b, const uint8_t *proofs, const uint8_t *V /* nullable */);
 int bpp_acp_batch_verify(bpp_acp_batch *b, const uint8_t verifier_seed[32]);
 int bpp_acp_batch_download_accept(bpp_acp_batch *b, uint8_t *accept);
+/* Verification strategy: 1 (default) = first ONE random-linear-combination MSM over the whole batch (weights from
+ * the verifier seed; Pippenger over count x (m + 8) decompressed points + the shared generators), the per-proof
+ * kernels only when it is not the identity, i.e. some proof is invalid; 0 = always per proof.  The accept bytes
+ * are the per-proof decisions either way. */
+int bpp_acp_batch_set_batch_rlc(bpp_acp_batch *b, int on);
 /* Fiat-Shamir location: 0 (default) per-proof Merlin transcripts on the device, 1 on host threads. */
 int bpp_acp_batch_set_host_transcripts(bpp_acp_batch *b, int on);
 /* merlin::Transcript on the device, scripted (test hook for the Merlin KAT and framing edge cases): records

@@ -88,3 +88,62 @@ def test_device_and_host_transcripts_agree(backend, mode):
     assert res[0][1] == res[1][1]
     want = [0 if (i == 3 or mode == "reference") else 1 for i in range(B)]
     assert list(res[0][1]) == want
+
+
+@pytest.mark.parametrize("mode", ["reference-fixed", "fixed"])
+def test_batch_rlc_verification_matches_per_proof_decisions(backend, mode):
+    """one random-linear-combination MSM over the batch (default) vs per-proof verification: same accept bytes
+    for an all-valid batch (combined check decides) and for batches with corrupted proofs (falls back)"""
+    from bpperm_b200 import acproof as G
+    k = 4
+    rng = ChaChaRng(bytes([91]) * 32)
+    if mode == "fixed":
+        from oracle import ipa
+        core, prover, V = ipa.make_instance(k, rng, dense_weights=True)
+    else:
+        core, prover, V = A.make_instance(k, rng)
+    n, m = core["n"], core["m"]
+    WL, WR, WO, WV = core["sparse"]
+    cir = G.Circuit(backend, n, core["Q"], m, WL, WR, WO, WV, core["c_vec"])
+    gens = G.Generators(backend, R.compress(core["g_base"]), R.compress(core["h_base"]),
+                        [R.compress(p) for p in core["G_vec"]], [R.compress(p) for p in core["H_vec"]])
+    B = 24
+    sb = lambda v: b"".join(R.sc_bytes(s) for s in v)
+    seeds = b"".join(bytes([i + 1]) * 32 for i in range(B))
+    Vc = b"".join(R.compress(p) for p in V) * B
+    batch = G.Batch(backend, cir, gens, B, mode, b"test")
+    batch.upload_witness(sb(prover["a_L"]) * B, sb(prover["a_R"]) * B, sb(prover["a_O"]) * B, sb(prover["gamma"]) * B, seeds)
+    batch.prove()
+    proofs = batch.download_proofs()
+    plen = batch.proof_len
+    other = R.compress(R.pt_double(R.BASEPOINT))
+
+    def decisions(pr, Vs, rlc):
+        batch.set_batch_rlc(rlc)
+        batch.upload_proofs(pr, Vs)
+        l0 = backend.launch_count
+        batch.verify(b"\x33" * 32)
+        return batch.download_accept(), backend.launch_count - l0
+
+    ok_rlc, n_rlc = decisions(proofs, Vc, True)
+    ok_pp, n_pp = decisions(proofs, Vc, False)
+    assert ok_rlc == ok_pp == b"\x01" * B
+    cases = []
+    for victim, off in ((0, 0), (5, 3 * 32), (B - 1, 8 * 32 + 5), (7, plen - 1)):    # A_I, T_1, a proof scalar, last byte
+        bad = bytearray(proofs)
+        if off % 32 == 0 and off < 256:
+            bad[victim * plen + off:victim * plen + off + 32] = other     # another valid point
+        else:
+            bad[victim * plen + off] ^= 1
+        cases.append((bytes(bad), Vc, victim, mode == "fixed" or off != plen - 1))
+    badV = bytearray(Vc)
+    badV[32 * (m * 9 + 2):32 * (m * 9 + 3)] = other                        # commitment 2 of proof 9
+    cases.append((proofs, bytes(badV), 9, True))
+    for pr, Vs, victim, needs_msm in cases:
+        a1, n1 = decisions(pr, Vs, True)
+        a0, _ = decisions(pr, Vs, False)
+        assert a1 == a0
+        assert list(a1) == [0 if i == victim else 1 for i in range(B)], victim
+        if needs_msm:   # (a flipped byte of r already fails t == <l, r>: weight 0, no fall-back needed)
+            assert n1 > n_rlc     # the combined check failed and the per-proof kernels ran
+    batch.free()
