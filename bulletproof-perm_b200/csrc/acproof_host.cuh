@@ -370,6 +370,14 @@ static int acp_fb(bpp_acp_batch *b, const fb_shape &sh, uint32_t *dst, uint32_t 
     // few (proof, output) pairs: split the terms of each MSM over several blocks so the launch fills the GPU
     uint32_t terms = 0;
     for (uint32_t k = 0; k < sh.nseg; k++) terms += sh.cnt[k];
+    if (!sh.sel_period && (uint64_t)terms * b->gens->Wn <= 64 && (uint64_t)b->B * sh.outs >= 32ull * ctx->sm_count) {
+        // few terms per output and plenty of outputs: a thread per output
+        const uint32_t total = b->B * sh.outs;
+        k_fb_msm_small<<<(total + 127) / 128, 128, 0, ctx->stream>>>(b->d_blk, b->lay, s, b->gens->d_table, b->gens->c, b->gens->Wn,
+                                                                    b->gens->kc, b->B, sh.outs, dst);
+        LAUNCH_CHECK(ctx);
+        return BPP_OK;
+    }
     const uint64_t blocks = (uint64_t)b->B * sh.outs, want = 4ull * ctx->sm_count;
     const uint64_t items = (uint64_t)terms * ((b->gens->Wn + FB_GROUP - 1) / FB_GROUP);
     uint64_t sp = blocks >= want ? 1 : (want + blocks - 1) / blocks;
@@ -480,7 +488,7 @@ static int acp_challenge_dependent_scalars(bpp_acp_batch *b) {
         k_pow_fill<<<dim3((2 * L.np + L.Q + 127) / 128, b->B), 128, 0, ctx->stream>>>(L, b->d_blk);
         LAUNCH_CHECK(ctx);
     } else {
-        k_acp_pow<<<(b->B + 31) / 32, 64, 0, ctx->stream>>>(L, b->B, b->d_blk);
+        k_acp_pow<<<(b->B + 31) / 32, ACP_POW_THREADS, 0, ctx->stream>>>(L, b->B, b->d_blk);
         LAUNCH_CHECK(ctx);
     }
     acp_csr W{b->cir->d_rowptr, b->cir->d_col, b->cir->d_kind, b->cir->d_coeff, b->cir->rows};

@@ -206,6 +206,51 @@ __global__ void __launch_bounds__(FB_THREADS) k_fb_msm(const uint32_t *__restric
         dst[threadIdx.x] = red[0][threadIdx.x];
     }
 }
+// Few-term shapes (T_i = t_i*g + tau_i*h, V_j = v_j*g + gamma_j*h: 2 terms): one THREAD per output point
+// walks its terms x windows serially - no block tree, no idle lanes.
+__global__ void __launch_bounds__(128) k_fb_msm_small(const uint32_t *__restrict__ blk, acp_layout lay, fb_shape sh,
+                                                      const uint32_t *__restrict__ table, int c, int Wn, fb_consts kc,
+                                                      uint32_t B, uint32_t outs /* per proof; sh.outs = pitch */,
+                                                      uint32_t *__restrict__ out_ext /* [p][pitch] x 32 */) {
+    const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= B * outs) return;
+    const uint32_t p = id / outs, o = id - p * outs;
+    const uint32_t half = 1u << (c - 1), mask = (1u << c) - 1u;
+    ge_ext acc;
+    ge_identity(acc);
+#pragma unroll 1
+    for (uint32_t seg = 0; seg < sh.nseg; seg++) {
+#pragma unroll 1
+        for (uint32_t k = 0; k < sh.cnt[seg]; k++) {
+            const uint32_t *sp = ACP_PTR(blk, lay, p, sh.sc_off[seg] + o * sh.sc_ostride[seg] + k);
+            const uint32_t gen = sh.gen[seg] + k;
+            uint32_t s[9];
+            unsigned long long carry = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                carry += (unsigned long long)sp[i] + kc.K[i];
+                s[i] = (uint32_t)carry;
+                carry >>= 32;
+            }
+            s[8] = (uint32_t)carry;
+#pragma unroll 1
+            for (uint32_t w = 0; w < (uint32_t)Wn; w++) {
+                int bit = c * (int)w, limb = bit >> 5, shf = bit & 31;
+                unsigned long long v = s[limb];
+                if (limb + 1 < 9) v |= (unsigned long long)s[limb + 1] << 32;
+                uint32_t u = (uint32_t)(v >> shf) & mask;
+                int d = (w + 1 == (uint32_t)Wn) ? (int)u : (int)u - (int)half;
+                if (d == 0) continue;
+                uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+                ge_niels q;
+                ge_niels_load(q, table + 24 * (((size_t)gen * Wn + w) * half + (mag - 1)));
+                ge_madd(acc, acc, q, d < 0);
+            }
+        }
+    }
+    ge_store(out_ext + 32 * ((size_t)p * sh.outs + o), acc);
+}
+
 // warp per output: sum of `splits` partial points -> dst[p * pitch + o]
 __global__ void __launch_bounds__(32) k_fb_sum_splits(const uint32_t *__restrict__ part, uint32_t outs, uint32_t splits,
                                                       uint32_t pitch, uint32_t *__restrict__ dst) {
@@ -244,64 +289,31 @@ __global__ void __launch_bounds__(128) k_compress_batch(const uint32_t *__restri
 }
 
 // ---- per-challenge scalars -------------------------------------------------------------------------
-// Thread per proof: y_n = exp_iter(y) (n), z_q = exp_iter(z) (Q) with the reference's Fibonacci
-// recurrence (util.rs:139-157), y_n_inv by Montgomery's trick (one inversion instead of the reference's
-// n: circuit_lib.rs:273-275; identical results).  All chains stay in Montgomery form.
-__global__ void __launch_bounds__(64) k_acp_pow(acp_layout lay, uint32_t B, uint32_t *__restrict__ blk) {
-    // block = 2 warps over the same 32 proofs: warp 0 runs the y chain + inversion, warp 1 the (longer) z chain
+// Three threads per proof (one per warp of the block): y_n = exp_iter(y) (n), z_q = exp_iter(z) (Q) with
+// the reference's Fibonacci recurrence (util.rs:139-157), and y_n_inv.  The reference inverts every
+// y_n[i] (circuit_lib.rs:273-275); since y_n[i] = y^F(i), its inverse is (y^-1)^F(i): ONE inversion, then
+// the same recurrence started from y^-1 - identical values (dalek's invert(0) = 0 also falls out: the
+// chain of 0 is 0).  All chains stay in Montgomery form.
+#define ACP_POW_THREADS 96
+__global__ void __launch_bounds__(ACP_POW_THREADS) k_acp_pow(acp_layout lay, uint32_t B, uint32_t *__restrict__ blk) {
     const uint32_t p = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int which = threadIdx.x >> 5;
+    const int which = threadIdx.x >> 5;   // 0: y chain, 1: z chain, 2: y^-1 chain
     if (p >= B) return;
     sc one_m;
     sc_const(one_m, SC_R);
-    {
-        const uint32_t cnt = which ? lay.Q : lay.n;
-        uint32_t *dst = ACP_PTR(blk, lay, p, which ? lay.zq : lay.yn);
-        sc base = one_m, nxt, ret, s;
-        sc_load(nxt, ACP_PTR(blk, lay, p, which ? lay.z : lay.y));
-        sc_to_mont(nxt, nxt);
+    const uint32_t cnt = which == 1 ? lay.Q : lay.n;
+    uint32_t *dst = ACP_PTR(blk, lay, p, which == 0 ? lay.yn : which == 1 ? lay.zq : lay.yninv);
+    sc base = one_m, nxt, ret, s;
+    sc_load(nxt, ACP_PTR(blk, lay, p, which == 1 ? lay.z : lay.y));
+    if (which == 2) sc_invert(nxt, nxt);
+    sc_to_mont(nxt, nxt);
 #pragma unroll 1
-        for (uint32_t i = 0; i < cnt; i++) {
-            ret = nxt;
-            sc_mont_noinline(nxt, nxt, base);
-            base = ret;
-            sc_from_mont(s, ret);
-            sc_store(dst + 8 * (size_t)i, s);
-        }
-    }
-    if (which) return;
-    // batch inversion of y_n -> y_n_inv (prefix products kept in the output array)
-    uint32_t *yn = ACP_PTR(blk, lay, p, lay.yn), *yi = ACP_PTR(blk, lay, p, lay.yninv);
-    sc acc = one_m, v;
-    bool any_zero = false;
-#pragma unroll 1
-    for (uint32_t i = 0; i < lay.n; i++) {
-        sc_store(yi + 8 * (size_t)i, acc);  // prefix product of elements < i (Montgomery form)
-        sc_load(v, yn + 8 * (size_t)i);
-        any_zero = any_zero || sc_is_zero(v);
-        sc_to_mont(v, v);
-        sc_mont_noinline(acc, acc, v);
-    }
-    if (any_zero) {  // only when y = 0: dalek's invert(0) = 0
-        sc z;
-        sc_set0(z);
-        for (uint32_t i = 0; i < lay.n; i++) sc_store(yi + 8 * (size_t)i, z);
-        return;
-    }
-    sc inv;
-    sc_from_mont(v, acc);
-    sc_invert(inv, v);
-    sc_to_mont(inv, inv);  // Montgomery form of (prod all)^-1
-#pragma unroll 1
-    for (int i = (int)lay.n - 1; i >= 0; i--) {
-        sc pre, r, e;
-        sc_load(pre, yi + 8 * (size_t)i);
-        sc_mont_noinline(r, inv, pre);     // inverse of element i (Montgomery form)
-        sc_load(e, yn + 8 * (size_t)i);
-        sc_to_mont(e, e);
-        sc_mont_noinline(inv, inv, e);
-        sc_from_mont(r, r);
-        sc_store(yi + 8 * (size_t)i, r);
+    for (uint32_t i = 0; i < cnt; i++) {
+        ret = nxt;
+        sc_mont_noinline(nxt, nxt, base);
+        base = ret;
+        sc_from_mont(s, ret);
+        sc_store(dst + 8 * (size_t)i, s);
     }
 }
 
