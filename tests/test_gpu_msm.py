@@ -154,3 +154,20 @@ def test_large_msm_properties(backend, logn):
     pts = [R.decompress(enc[32 * i:32 * i + 32]) for i in range(k)]
     want = R.compress(R.msm_naive(s_int[:k], pts))
     assert backend.vartime_multiscalar_mul(scb[:32 * k], table, off=0, n=k) == want
+
+
+@pytest.mark.parametrize("log_n", [10, 12, 14, 16])
+def test_sweep_inputs_match_oracle(backend, log_n):
+    """BASELINE configs[4]: the seeded inputs of tools/msm_sweep.py (seed 5000 + log2 N) against the C restatement
+    of dalek's vartime_multiscalar_mul; pins the `result` bytes recorded in profiles/*msm_sweep*.json."""
+    import numpy as np
+    from oracle import cref
+    n = 1 << log_n
+    rs = np.random.RandomState(5000 + log_n)
+    blobs = rs.randint(0, 256, size=(n, 64), dtype=np.uint8)
+    sc = rs.randint(0, 256, size=(n, 32), dtype=np.uint8)
+    sc[:, 31] &= 0x0F
+    table = backend.points_from_uniform(blobs.tobytes())
+    got = backend.vartime_multiscalar_mul(sc.tobytes(), table)
+    table.free()
+    assert got == cref.msm(sc.tobytes(), cref.from_uniform(blobs.tobytes()))
