@@ -780,7 +780,7 @@ static int acp_verify_fixed(bpp_acp_batch *b, const uint8_t verifier_seed[32]) {
     LAUNCH_CHECK(ctx);
     k_acp_vscal_fixed<<<dim3((np + m + 1 + 127) / 128, B), 128, 0, s>>>(L, b->d_blk);
     LAUNCH_CHECK(ctx);
-    if (b->batch_rlc && B >= 8) {
+    if (b->batch_rlc && (size_t)B * per >= 1024) {   // enough points for the bucket method to pay
         bool decided = false;
         if ((rc = acp_verify_rlc(b, per, 0, &decided))) return rc;
         if (decided) return BPP_OK;
@@ -849,7 +849,7 @@ extern "C" int bpp_acp_batch_verify(bpp_acp_batch *b, const uint8_t verifier_see
     LAUNCH_CHECK(ctx);
     k_acp_vscal<<<dim3((n + m + 1 + 127) / 128, B), 128, 0, s>>>(L, b->d_blk);
     LAUNCH_CHECK(ctx);
-    if (b->batch_rlc && mode != 0 && B >= 8) {   // `reference` mode never accepts: nothing to gain from the combined check
+    if (b->batch_rlc && mode != 0 && (size_t)B * per >= 1024) {   // `reference` mode never accepts: nothing to gain from the combined check
         bool decided = false;
         if ((rc = acp_verify_rlc(b, per, 1, &decided))) return rc;
         if (decided) return BPP_OK;

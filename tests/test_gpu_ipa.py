@@ -107,3 +107,46 @@ def test_larger_deck_single_proof_uses_split_msm_and_matches_c(backend, k, windo
     # the same circuit in the other modes still needs exactly n generators
     with pytest.raises(Exception):
         G.Batch(backend, cir, gens, 1, "reference-fixed")
+
+
+def _large_instance(k, seed):
+    """k-card instance with generators derived by the C oracle from seeded uniform bytes (the Python oracle's
+    elligator is too slow for 2^14 generators); same circuit / witness generators as the small cases."""
+    import numpy as np
+    from oracle import acproof as A
+    n, Q, m, WL, WR, WO, WV, c = A.shuffle_circuit(k)
+    npad = 1
+    while npad < n:
+        npad *= 2
+    rs = np.random.RandomState(seed)
+    enc = cref.compress(cref.from_uniform(rs.randint(0, 256, size=(2 * npad + 2, 64), dtype=np.uint8).tobytes()))
+    rng = ChaChaRng(bytes([seed & 0xFF]) * 32)
+    v, aL, aR, aO = A.shuffle_witness(k, rng)
+    gamma = [rng.scalar() for _ in range(m)]
+    g, h, Gb, Hb = enc[:32], enc[32:64], enc[64:64 + 32 * npad], enc[64 + 32 * npad:]
+    inst = cref.AcpFixedInstance(n, Q, m, WL, WR, WO, WV, _sb(c), g, h, Gb, Hb)
+    return (n, Q, m, npad, WL, WR, WO, WV, c), (g, h, Gb, Hb), (v, aL, aR, aO, gamma), inst
+
+
+def test_large_deck_4096_cards_single_proof_is_byte_identical(backend):
+    """BASELINE configs[2]: 4096 committed card values -> k = 4096, n = 8192 multipliers, 2^14 generators,
+    13 inner-product rounds, one proof on one GPU; bytes and decision against the C restatement."""
+    from bpperm_b200 import acproof as G
+    (n, Q, m, npad, WL, WR, WO, WV, c), (g, h, Gb, Hb), (v, aL, aR, aO, gamma), inst = _large_instance(4096, 99)
+    assert (n, npad, m) == (8192, 8192, 8193)
+    cir = G.Circuit(backend, n, Q, m, WL, WR, WO, WV, c)
+    gens = G.Generators(backend, g, h, [Gb[32 * i:32 * i + 32] for i in range(npad)], [Hb[32 * i:32 * i + 32] for i in range(npad)], 8)
+    sd = b"\x42" * 32
+    proof = G.prove_batch(backend, cir, gens, _sb(aL), _sb(aR), _sb(aO), _sb(gamma), sd, 1, "fixed")
+    assert len(proof) == 32 * (13 + 2 * 13)
+    want = inst.prove(_sb(aL), _sb(aR), _sb(aO), _sb(gamma), sd)
+    assert proof == want
+    Vp = inst.commit(_sb(v), _sb(gamma))
+    assert inst.verify(want, Vp)
+    Vc = cref.compress(Vp)
+    assert list(G.verify_batch(backend, cir, gens, proof, Vc, 1, "fixed")) == [1]
+    bad = bytearray(proof)
+    bad[32 * 20 + 3] ^= 2      # one of the L_j
+    assert list(G.verify_batch(backend, cir, gens, bytes(bad), Vc, 1, "fixed")) == [0]
+    gens.free()
+    cir.free()

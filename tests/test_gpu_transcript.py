@@ -107,7 +107,7 @@ def test_batch_rlc_verification_matches_per_proof_decisions(backend, mode):
     cir = G.Circuit(backend, n, core["Q"], m, WL, WR, WO, WV, core["c_vec"])
     gens = G.Generators(backend, R.compress(core["g_base"]), R.compress(core["h_base"]),
                         [R.compress(p) for p in core["G_vec"]], [R.compress(p) for p in core["H_vec"]])
-    B = 24
+    B = 64      # 64 x (m + 8) >= 1024 points: the combined check is active
     sb = lambda v: b"".join(R.sc_bytes(s) for s in v)
     seeds = b"".join(bytes([i + 1]) * 32 for i in range(B))
     Vc = b"".join(R.compress(p) for p in V) * B
