@@ -146,44 +146,70 @@ __global__ void __launch_bounds__(FB_THREADS) k_fb_msm(const uint32_t *__restric
     const uint32_t items = total_terms * groups;
     ge_ext acc;
     ge_identity(acc);
-#pragma unroll 1
-    for (uint32_t it = blockIdx.z * FB_THREADS + threadIdx.x; it < items; it += FB_THREADS * gridDim.z) {
-        uint32_t term = it / groups, grp = it - term * groups;
-        uint32_t seg = 0, k = term;
-        while (seg + 1 < sh.nseg && k >= sh.cnt[seg]) { k -= sh.cnt[seg]; seg++; }
-        if (sh.sel_period && sh.sel[seg]) {
-            const bool upper = (k & (sh.sel_period - 1)) >= (sh.sel_period >> 1);
-            if ((upper == (o == 0)) != (sh.sel[seg] == 1)) continue;
-        }
-        const uint32_t *sp = ACP_PTR(blk, lay, p, sh.sc_off[seg] + o * sh.sc_ostride[seg] + k);
-        const uint32_t gen = sh.gen[seg] + k;
-        // s' = s + K
-        uint32_t s[9];
-        {
-            uint4 lo = *reinterpret_cast<const uint4 *>(sp), hi = *reinterpret_cast<const uint4 *>(sp + 4);
-            s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w; s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
-            s[8] = 0;
-            unsigned long long carry = 0;
+    // Work items (term, group of FB_GROUP windows) are strided over the block; within this thread's items the
+    // non-zero digits form one stream of (table entry, sign) pairs.  The stream is software pipelined: the
+    // next entry's 96-byte gather (random access into a multi-GB table) is issued before the current mixed add.
+    const uint32_t stride = FB_THREADS * gridDim.z;
+    uint32_t it = blockIdx.z * FB_THREADS + threadIdx.x;
+    uint32_t w = 0, w_end = 0, gen = 0;
+    uint32_t s[9];
+    bool first = true;
+    auto advance = [&](const uint32_t *&ptr, bool &neg) -> bool {
+        for (;;) {
+            if (w >= w_end) {
+                if (!first) it += stride;
+                first = false;
+                if (it >= items) return false;
+                uint32_t term = it / groups, grp = it - term * groups;
+                uint32_t seg = 0, k = term;
+                while (seg + 1 < sh.nseg && k >= sh.cnt[seg]) { k -= sh.cnt[seg]; seg++; }
+                w = grp * FB_GROUP;
+                w_end = min((uint32_t)Wn, (grp + 1) * FB_GROUP);
+                if (sh.sel_period && sh.sel[seg]) {
+                    const bool upper = (k & (sh.sel_period - 1)) >= (sh.sel_period >> 1);
+                    if ((upper == (o == 0)) != (sh.sel[seg] == 1)) { w = w_end; continue; }
+                }
+                const uint32_t *sp = ACP_PTR(blk, lay, p, sh.sc_off[seg] + o * sh.sc_ostride[seg] + k);
+                gen = sh.gen[seg] + k;
+                uint4 lo = *reinterpret_cast<const uint4 *>(sp), hi = *reinterpret_cast<const uint4 *>(sp + 4);
+                s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w; s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
+                unsigned long long carry = 0;   // s' = s + K
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                carry += (unsigned long long)s[i] + kc.K[i];
-                s[i] = (uint32_t)carry;
-                carry >>= 32;
+                for (int i = 0; i < 8; i++) {
+                    carry += (unsigned long long)s[i] + kc.K[i];
+                    s[i] = (uint32_t)carry;
+                    carry >>= 32;
+                }
+                s[8] = (uint32_t)carry;
             }
-            s[8] = (uint32_t)carry;
-        }
-#pragma unroll 1
-        for (uint32_t w = grp * FB_GROUP; w < min((uint32_t)Wn, (grp + 1) * FB_GROUP); w++) {
-            int bit = c * (int)w, limb = bit >> 5, shf = bit & 31;
+            const uint32_t ww = w++;
+            int bit = c * (int)ww, limb = bit >> 5, shf = bit & 31;
             unsigned long long v = s[limb];
             if (limb + 1 < 9) v |= (unsigned long long)s[limb + 1] << 32;
             uint32_t u = (uint32_t)(v >> shf) & mask;
-            int d = (w + 1 == (uint32_t)Wn) ? (int)u : (int)u - (int)half;
+            int d = (ww + 1 == (uint32_t)Wn) ? (int)u : (int)u - (int)half;
             if (d == 0) continue;
             uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-            ge_niels q;
-            ge_niels_load(q, table + 24 * (((size_t)gen * Wn + w) * half + (mag - 1)));
-            ge_madd(acc, acc, q, d < 0);
+            ptr = table + 24 * (((size_t)gen * Wn + ww) * half + (mag - 1));
+            neg = d < 0;
+            return true;
+        }
+    };
+    {
+        const uint32_t *ptr = nullptr, *ptr_n = nullptr;
+        bool neg = false, neg_n = false;
+        bool ok = advance(ptr, neg);
+        ge_niels q, qn;
+        if (ok) ge_niels_load(q, ptr);
+#pragma unroll 1
+        while (ok) {
+            bool ok_n = advance(ptr_n, neg_n);
+            qn = q;
+            if (ok_n) ge_niels_load(qn, ptr_n);
+            ge_madd(acc, acc, q, neg);
+            q = qn;
+            neg = neg_n;
+            ok = ok_n;
         }
     }
     // block tree reduction

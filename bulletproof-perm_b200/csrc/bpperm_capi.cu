@@ -33,7 +33,6 @@ struct bpp_ctx {
     uint32_t *d_counts = nullptr, *d_offsets = nullptr, *d_cursor = nullptr;  // W x B each
     size_t cap_wb = 0, cap_offsets = 0, cap_cursor = 0;
     uint32_t *d_entries = nullptr; size_t cap_entries = 0;      // W x n
-    uint16_t *d_ebkt = nullptr; size_t cap_ebkt = 0;            // W x n bucket ids
     uint32_t *d_partials = nullptr; size_t cap_partials = 0;    // 2 x tiles x 32
     uint32_t *d_long = nullptr; size_t cap_long = 0;            // hot-bucket queue (+ counter at [0] of d_flag+1)
     uint32_t *d_buckets = nullptr; size_t cap_buckets = 0;      // W x B x 32
@@ -132,7 +131,7 @@ extern "C" void bpp_free(bpp_ctx *ctx) {
     cudaDeviceSynchronize();
     void *ptrs[] = {ctx->d_scalars, ctx->d_counts, ctx->d_offsets, ctx->d_cursor, ctx->d_entries, ctx->d_buckets,
                     ctx->d_segS, ctx->d_segR, ctx->d_blk, ctx->d_out, ctx->d_stage, ctx->d_flag,
-                    ctx->d_ebkt, ctx->d_partials, ctx->d_long, ctx->d_vec};
+                    ctx->d_partials, ctx->d_long, ctx->d_vec};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
@@ -359,7 +358,6 @@ static int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points
     if ((rc = grow(ctx, &ctx->d_offsets, &ctx->cap_offsets, WB))) return rc;
     if ((rc = grow(ctx, &ctx->d_cursor, &ctx->cap_cursor, WB))) return rc;
     if ((rc = grow(ctx, &ctx->d_entries, &ctx->cap_entries, (size_t)W * n))) return rc;
-    if ((rc = grow(ctx, &ctx->d_ebkt, &ctx->cap_ebkt, (size_t)W * n))) return rc;
     const uint32_t tpw = (uint32_t)((n + BPP_TILE - 1) / BPP_TILE);
     const size_t total_tiles = (size_t)W * tpw;
     if ((rc = grow(ctx, &ctx->d_partials, &ctx->cap_partials, total_tiles * 2 * 32))) return rc;
@@ -392,11 +390,11 @@ static int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points
     k_window_scan<<<W, 1024, 0, s>>>(ctx->d_counts, B, ctx->d_offsets, ctx->d_cursor);
     LAUNCH_CHECK(ctx);
     if (prof) cudaEventRecord(ctx->ev[2], s);
-    k_digit_scatter<<<sb, 256, 0, s>>>(d_scalars, (uint32_t)n, c, W, ctx->d_cursor, ctx->d_entries, ctx->d_ebkt);
+    k_digit_scatter<<<sb, 256, 0, s>>>(d_scalars, (uint32_t)n, c, W, ctx->d_cursor, ctx->d_entries);
     LAUNCH_CHECK(ctx);
     if (prof) cudaEventRecord(ctx->ev[3], s);
     k_bucket_accum<<<(unsigned)((total_tiles + BPP_ACC_THREADS - 1) / BPP_ACC_THREADS), BPP_ACC_THREADS, 0, s>>>(
-        niels, ctx->d_entries, ctx->d_ebkt, ctx->d_offsets, ctx->d_cursor, (uint32_t)n, B, tpw, (uint32_t)total_tiles,
+        niels, ctx->d_entries, ctx->d_offsets, ctx->d_cursor, (uint32_t)n, B, tpw, (uint32_t)total_tiles,
         ctx->d_buckets, ctx->d_partials);
     LAUNCH_CHECK(ctx);
     if (prof) cudaEventRecord(ctx->ev[4], s);

@@ -8,7 +8,8 @@
 // Pipeline (N points, window c bits, W = ceil(256/c) windows, B = 2^(c-1) buckets per window):
 //   k_digit_hist      signed-window recode, per-(window,bucket) histogram (atomics)
 //   k_window_scan     exclusive scan of each window's histogram -> bucket offsets
-//   k_digit_scatter   counting-sort scatter of (point index | sign) into bucket order
+//   k_digit_scatter   counting-sort scatter of (point index | sign) into bucket order (no bucket ids are stored:
+//                     the sorted order and the offsets determine them)
 //   k_bucket_accum    one thread per tile of 32 sorted entries: mixed adds (extended += affine Niels, 7M)
 //   k_bucket_fixup    stitches buckets cut by tile boundaries (+ k_bucket_fixup_long for hot buckets)
 //   k_node_merge_*    bucket running sums as a tree of (S, A) nodes: thread-serial merges of 8 while
@@ -116,8 +117,7 @@ __global__ void __launch_bounds__(1024) k_window_scan(const uint32_t *__restrict
 }
 
 __global__ void k_digit_scatter(const uint32_t *__restrict__ scalars, uint32_t n, int c, int W,
-                                uint32_t *__restrict__ cursor, uint32_t *__restrict__ entries,
-                                uint16_t *__restrict__ ebkt) {
+                                uint32_t *__restrict__ cursor, uint32_t *__restrict__ entries) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t s[8];
@@ -133,7 +133,6 @@ __global__ void k_digit_scatter(const uint32_t *__restrict__ scalars, uint32_t n
         if (mag) {
             uint32_t pos = atomicAdd(&cursor[(size_t)w * half + (mag - 1)], 1u);
             entries[(size_t)w * n + pos] = i | (carry << 31);
-            ebkt[(size_t)w * n + pos] = (uint16_t)(mag - 1);
         }
     }
 }
@@ -159,41 +158,52 @@ FE_INLINE void bucket_flush(const ge_ext &acc, uint32_t w, uint32_t b, uint32_t 
 }
 
 __global__ void __launch_bounds__(BPP_ACC_THREADS) k_bucket_accum(
-    const uint32_t *__restrict__ niels, const uint32_t *__restrict__ entries, const uint16_t *__restrict__ ebkt,
-    const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ ends, uint32_t n, uint32_t B,
-    uint32_t tiles_per_window, uint32_t total_tiles, uint32_t *__restrict__ buckets,
-    uint32_t *__restrict__ partials) {
+    const uint32_t *__restrict__ niels, const uint32_t *__restrict__ entries, const uint32_t *__restrict__ offsets,
+    const uint32_t *__restrict__ ends, uint32_t n, uint32_t B, uint32_t tiles_per_window, uint32_t total_tiles,
+    uint32_t *__restrict__ buckets, uint32_t *__restrict__ partials) {
     uint32_t tile = blockIdx.x * blockDim.x + threadIdx.x;
     if (tile >= total_tiles) return;
     const uint32_t w = tile / tiles_per_window, t = tile - w * tiles_per_window;
-    const uint32_t cnt = ends[(size_t)w * B + (B - 1)];  // entries in this window
+    const uint32_t *endw = ends + (size_t)w * B;
+    const uint32_t cnt = endw[B - 1];  // entries in this window
     const uint32_t e0 = t * BPP_TILE;
     if (e0 >= cnt) return;
     const uint32_t e1 = min(e0 + BPP_TILE, cnt);
     const uint32_t *ew = entries + (size_t)w * n;
-    const uint16_t *bw = ebkt + (size_t)w * n;
+    // bucket of entry e0 = the first bucket whose end offset lies beyond e0 (the entry list carries no
+    // bucket ids: the sorted order and the offsets determine them)
+    uint32_t lo = 0, hi = B - 1;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (endw[mid] > e0) hi = mid;
+        else lo = mid + 1;
+    }
+    uint32_t cur = lo, cur_end = endw[lo], run_start = e0;
     ge_ext acc;
     ge_identity(acc);
     uint32_t idx = ew[e0];
-    uint32_t cur = bw[e0], run_start = e0;
     ge_niels q;
     ge_niels_load(q, niels + 24 * (size_t)(idx & 0x7fffffffu));
 #pragma unroll 1
     for (uint32_t e = e0; e < e1; e++) {
         // software pipeline: fetch the next entry's point while this one is being added
-        uint32_t idx_n = idx, b_n = cur;
+        uint32_t idx_n = idx;
         ge_niels qn = q;
         if (e + 1 < e1) {
             idx_n = ew[e + 1];
-            b_n = bw[e + 1];
             ge_niels_load(qn, niels + 24 * (size_t)(idx_n & 0x7fffffffu));
         }
         ge_madd(acc, acc, q, (idx >> 31) != 0);
-        if (e + 1 == e1 || b_n != cur) {
+        if (e + 1 == e1 || e + 1 == cur_end) {
             bucket_flush(acc, w, cur, run_start, e + 1, e0, B, tile, offsets, ends, buckets, partials);
             ge_identity(acc);
-            cur = b_n;
             run_start = e + 1;
+            if (e + 1 < e1) {   // next non-empty bucket
+                do {
+                    cur++;
+                    cur_end = endw[cur];
+                } while (cur_end <= e + 1);
+            }
         }
         idx = idx_n;
         q = qn;
@@ -314,7 +324,7 @@ __global__ void __launch_bounds__(128) k_node_merge_serial(const uint32_t *__res
     }
 #pragma unroll 1
     for (uint32_t i = 0; i < loglen; i++) ge_double(acc, acc);
-    if (inA) {
+    if (inA) {   // (interleaving this independent chain with the one above was measured: slower, 212 registers)
         const uint32_t *pa = inA + 32 * (size_t)g * L;
 #pragma unroll 1
         for (uint32_t k = 0; k < L; k++) {
