@@ -10,6 +10,7 @@
 // values is mont(mont(a, b), R^2); chains may stay in Montgomery form (sc_to_mont/sc_from_mont).
 // Every result is fully reduced, so any evaluation order gives identical bytes.
 #pragma once
+#include "mp256.cuh"
 #include <stdint.h>
 
 #define SC_INLINE __device__ __forceinline__
@@ -114,41 +115,62 @@ SC_INLINE void sc_neg(sc &r, const sc &a) {
 }
 
 // Montgomery product: r = a * b / 2^256 mod l.  Needs a * b < l * 2^256 (one operand < l suffices).
+// t = a*b (64 wide multiply-adds, mp_mul8); q = t_lo * (-l^-1) mod 2^256; r = (t + q*l) / 2^256.  With
+// l = 2^252 + delta, q*l = q*delta (8 x 4 limbs) + (q << 252); the low half of t + q*l is 0 mod 2^256 by
+// construction and carries out exactly when t_lo != 0, so only the high half is assembled.  No word-serial
+// dependency (the classic per-limb m_i = t_i * n' loop is one chain of ~100 dependent steps).
+__device__ __constant__ const uint32_t SC_NP[8] = {0x12547e1bu, 0xd2b51da3u, 0xfdba84ffu, 0xb1a206f2u,
+                                                   0xffa36beau, 0x14e75438u, 0x6fe91836u, 0x9db6c6f2u};
 SC_INLINE void sc_mont(sc &r, const sc &a, const sc &b) {
-    uint32_t t[17];
+    uint32_t t[16], qf[16], u[12], np[8], dl[4];
+    mp_mul8<8>(t, a.v, b.v);
 #pragma unroll
-    for (int i = 0; i < 17; i++) t[i] = 0;
-    // schoolbook product, operand scanning with 64-bit temporaries (a*b + t + carry never overflows)
+    for (int i = 0; i < 8; i++) np[i] = SC_NP[i];
+    mp_mul8<8>(qf, t, np);            // q = low 8 limbs (the high half is dead code for the compiler)
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        unsigned long long carry = 0;
+    for (int i = 0; i < 4; i++) dl[i] = SC_L[i];
+    mp_mul8<4>(u, qf, dl);            // q * delta, 12 limbs
+    // h = high half of (q*delta + (q << 252)): limbs 8..15, with the carry out of limb 7
+    uint32_t w[9];                    // (q << 28) occupies limbs 7..15
+    w[0] = qf[0] << 28;
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            unsigned long long v = (unsigned long long)a.v[j] * b.v[i] + t[i + j] + carry;
-            t[i + j] = (uint32_t)v;
-            carry = v >> 32;
-        }
-        t[i + 8] = (uint32_t)carry;
-    }
-    // Montgomery reduction; l has non-zero limbs only at 0..3 and 7
+    for (int k = 1; k < 8; k++) w[k] = (qf[k] << 28) | (qf[k - 1] >> 4);
+    w[8] = qf[7] >> 4;
+    uint32_t nz = 0;
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        uint32_t m = t[i] * SC_NPRIME;
-        unsigned long long carry = 0;
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            unsigned long long v = (unsigned long long)m * SC_L[j] + t[i + j] + carry;
-            t[i + j] = (uint32_t)v;
-            carry = v >> 32;
-        }
-#pragma unroll
-        for (int k = i + 8; k < 17; k++) {
-            carry += t[k];
-            t[k] = (uint32_t)carry;
-            carry >>= 32;
-        }
-    }
-    sc_cond_sub_l(r, t + 8, t[16]);
+    for (int i = 0; i < 8; i++) nz |= t[i];
+    nz = nz ? 0xffffffffu : 0u;
+    uint32_t h[8], dummy;
+    asm("add.cc.u32 %8, %9, %10;\n\t"          // limb 7: only the carry matters
+        "addc.cc.u32 %0, %11, %15;\n\t"
+        "addc.cc.u32 %1, %12, %16;\n\t"
+        "addc.cc.u32 %2, %13, %17;\n\t"
+        "addc.cc.u32 %3, %14, %18;\n\t"
+        "addc.cc.u32 %4, %19, 0;\n\t"
+        "addc.cc.u32 %5, %20, 0;\n\t"
+        "addc.cc.u32 %6, %21, 0;\n\t"
+        "addc.u32 %7, %22, 0;"
+        : "=&r"(h[0]), "=&r"(h[1]), "=&r"(h[2]), "=&r"(h[3]), "=&r"(h[4]), "=&r"(h[5]), "=&r"(h[6]), "=&r"(h[7]),
+          "=&r"(dummy)
+        : "r"(u[7]), "r"(w[0]), "r"(u[8]), "r"(u[9]), "r"(u[10]), "r"(u[11]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+          "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "r"(w[8]));
+    // s = t_hi + h + (t_lo != 0): the carry-in is produced by nz + nz (0xffffffff + 0xffffffff carries)
+    uint32_t s8[8];
+    asm("add.cc.u32 %8, %9, %9;\n\t"
+        "addc.cc.u32 %0, %10, %18;\n\t"
+        "addc.cc.u32 %1, %11, %19;\n\t"
+        "addc.cc.u32 %2, %12, %20;\n\t"
+        "addc.cc.u32 %3, %13, %21;\n\t"
+        "addc.cc.u32 %4, %14, %22;\n\t"
+        "addc.cc.u32 %5, %15, %23;\n\t"
+        "addc.cc.u32 %6, %16, %24;\n\t"
+        "addc.u32 %7, %17, %25;"
+        : "=&r"(s8[0]), "=&r"(s8[1]), "=&r"(s8[2]), "=&r"(s8[3]), "=&r"(s8[4]), "=&r"(s8[5]), "=&r"(s8[6]),
+          "=&r"(s8[7]), "=&r"(dummy)
+        : "r"(nz), "r"(t[8]), "r"(t[9]), "r"(t[10]), "r"(t[11]), "r"(t[12]), "r"(t[13]), "r"(t[14]), "r"(t[15]),
+          "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]), "r"(h[4]), "r"(h[5]), "r"(h[6]), "r"(h[7]));
+    (void)dummy;
+    sc_cond_sub_l(r, s8, 0);          // s < 2l < 2^254
 }
 
 SC_INLINE void sc_to_mont(sc &r, const sc &a) {
