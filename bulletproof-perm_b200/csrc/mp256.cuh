@@ -147,3 +147,45 @@ FE_INLINE void mp_mul8(uint32_t *t, const uint32_t *a, const uint32_t *b) {
               "r"(od[8]), "r"(od[9]), "r"(od[10]));
     }
 }
+
+// q[0..8) = low 256 bits of a[0..8) * b[0..8): only the 36 products with i + j <= 7 (carries and high
+// halves that would land on limb 8 and above go to scratch limbs and are dropped).
+FE_INLINE void mp_mul8_lo(uint32_t *q, const uint32_t *a, const uint32_t *b) {
+    uint32_t ev[10], od[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) { ev[i] = 0; od[i] = 0; }
+    // b0: a0,a2,a4,a6 -> limbs 0,2,4,6;  a1,a3,a5,a7 -> limbs 1,3,5,7
+    fe_mad4(ev[0], ev[1], ev[2], ev[3], ev[4], ev[5], ev[6], ev[7], ev[8], a[0], a[2], a[4], a[6], b[0]);
+    fe_mad4(od[0], od[1], od[2], od[3], od[4], od[5], od[6], od[7], od[8], a[1], a[3], a[5], a[7], b[0]);
+    // b1: a1,a3,a5 -> limbs 2,4,6;  a0,a2,a4,a6 -> limbs 1,3,5,7
+    fe_mad3(ev[2], ev[3], ev[4], ev[5], ev[6], ev[7], ev[8], a[1], a[3], a[5], b[1]);
+    fe_mad4(od[0], od[1], od[2], od[3], od[4], od[5], od[6], od[7], od[8], a[0], a[2], a[4], a[6], b[1]);
+    // b2: a0,a2,a4 -> limbs 2,4,6;  a1,a3,a5 -> limbs 3,5,7
+    fe_mad3(ev[2], ev[3], ev[4], ev[5], ev[6], ev[7], ev[8], a[0], a[2], a[4], b[2]);
+    fe_mad3(od[2], od[3], od[4], od[5], od[6], od[7], od[8], a[1], a[3], a[5], b[2]);
+    // b3: a1,a3 -> limbs 4,6;  a0,a2,a4 -> limbs 3,5,7
+    fe_mad2(ev[4], ev[5], ev[6], ev[7], ev[8], a[1], a[3], b[3]);
+    fe_mad3(od[2], od[3], od[4], od[5], od[6], od[7], od[8], a[0], a[2], a[4], b[3]);
+    // b4: a0,a2 -> limbs 4,6;  a1,a3 -> limbs 5,7
+    fe_mad2(ev[4], ev[5], ev[6], ev[7], ev[8], a[0], a[2], b[4]);
+    fe_mad2(od[4], od[5], od[6], od[7], od[8], a[1], a[3], b[4]);
+    // b5: a1 -> limb 6;  a0,a2 -> limbs 5,7
+    fe_mad1(ev[6], ev[7], ev[8], a[1], b[5]);
+    fe_mad2(od[4], od[5], od[6], od[7], od[8], a[0], a[2], b[5]);
+    // b6: a0 -> limb 6;  a1 -> limb 7
+    fe_mad1(ev[6], ev[7], ev[8], a[0], b[6]);
+    fe_mad1(od[6], od[7], od[8], a[1], b[6]);
+    // b7: a0 -> limb 7
+    fe_mad1(od[6], od[7], od[8], a[0], b[7]);
+    q[0] = ev[0];
+    asm("add.cc.u32 %0, %7, %14;\n\t"
+        "addc.cc.u32 %1, %8, %15;\n\t"
+        "addc.cc.u32 %2, %9, %16;\n\t"
+        "addc.cc.u32 %3, %10, %17;\n\t"
+        "addc.cc.u32 %4, %11, %18;\n\t"
+        "addc.cc.u32 %5, %12, %19;\n\t"
+        "addc.u32 %6, %13, %20;"
+        : "=&r"(q[1]), "=&r"(q[2]), "=&r"(q[3]), "=&r"(q[4]), "=&r"(q[5]), "=&r"(q[6]), "=&r"(q[7])
+        : "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]),
+          "r"(od[0]), "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]));
+}

@@ -115,18 +115,19 @@ SC_INLINE void sc_neg(sc &r, const sc &a) {
 }
 
 // Montgomery product: r = a * b / 2^256 mod l.  Needs a * b < l * 2^256 (one operand < l suffices).
-// t = a*b (64 wide multiply-adds, mp_mul8); q = t_lo * (-l^-1) mod 2^256; r = (t + q*l) / 2^256.  With
+// t = a*b (64 wide multiply-adds, mp_mul8); q = t_lo * (-l^-1) mod 2^256 (36); r = (t + q*l) / 2^256.  With
 // l = 2^252 + delta, q*l = q*delta (8 x 4 limbs) + (q << 252); the low half of t + q*l is 0 mod 2^256 by
 // construction and carries out exactly when t_lo != 0, so only the high half is assembled.  No word-serial
 // dependency (the classic per-limb m_i = t_i * n' loop is one chain of ~100 dependent steps).
 __device__ __constant__ const uint32_t SC_NP[8] = {0x12547e1bu, 0xd2b51da3u, 0xfdba84ffu, 0xb1a206f2u,
                                                    0xffa36beau, 0x14e75438u, 0x6fe91836u, 0x9db6c6f2u};
+#pragma nv_diag_suppress 550   // `dummy` receives a limb whose carry-out is all that matters
 SC_INLINE void sc_mont(sc &r, const sc &a, const sc &b) {
-    uint32_t t[16], qf[16], u[12], np[8], dl[4];
+    uint32_t t[16], qf[8], u[12], np[8], dl[4];
     mp_mul8<8>(t, a.v, b.v);
 #pragma unroll
     for (int i = 0; i < 8; i++) np[i] = SC_NP[i];
-    mp_mul8<8>(qf, t, np);            // q = low 8 limbs (the high half is dead code for the compiler)
+    mp_mul8_lo(qf, t, np);            // q = t_lo * (-l^-1) mod 2^256: 36 products
 #pragma unroll
     for (int i = 0; i < 4; i++) dl[i] = SC_L[i];
     mp_mul8<4>(u, qf, dl);            // q * delta, 12 limbs
@@ -140,7 +141,7 @@ SC_INLINE void sc_mont(sc &r, const sc &a, const sc &b) {
 #pragma unroll
     for (int i = 0; i < 8; i++) nz |= t[i];
     nz = nz ? 0xffffffffu : 0u;
-    uint32_t h[8], dummy;
+    uint32_t h[8], dummy = 0;
     asm("add.cc.u32 %8, %9, %10;\n\t"          // limb 7: only the carry matters
         "addc.cc.u32 %0, %11, %15;\n\t"
         "addc.cc.u32 %1, %12, %16;\n\t"
@@ -169,9 +170,9 @@ SC_INLINE void sc_mont(sc &r, const sc &a, const sc &b) {
           "=&r"(s8[7]), "=&r"(dummy)
         : "r"(nz), "r"(t[8]), "r"(t[9]), "r"(t[10]), "r"(t[11]), "r"(t[12]), "r"(t[13]), "r"(t[14]), "r"(t[15]),
           "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]), "r"(h[4]), "r"(h[5]), "r"(h[6]), "r"(h[7]));
-    (void)dummy;
     sc_cond_sub_l(r, s8, 0);          // s < 2l < 2^254
 }
+#pragma nv_diag_default 550
 
 SC_INLINE void sc_to_mont(sc &r, const sc &a) {
     sc k;
