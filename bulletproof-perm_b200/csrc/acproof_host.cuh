@@ -44,6 +44,7 @@ struct bpp_acp_batch {
     // transcript in their own process)
     bool host_transcripts = false;
     uint64_t *d_tr = nullptr, *d_proto = nullptr;
+    uint32_t *d_wstage = nullptr;   // witness staging (contiguous upload), allocated on first use
     // batch verification by random linear combination (k_rlc_*): scalars of the one MSM over the batch's
     // dynamic points + the shared generators (appended to d_dyn), its compressed result, the fall-back flag
     bool batch_rlc = true;
@@ -231,7 +232,7 @@ extern "C" void bpp_acp_batch_free(bpp_acp_batch *b) {
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
     void *dev[] = {b->d_blk, b->d_seeds, b->d_wide, b->d_ext8, b->d_dyn, b->d_wsum, b->d_stat, b->d_bad, b->d_vext, b->d_vseed,
-                   b->d_pts8, b->d_proofs, b->d_V, b->d_accept, b->d_lr, b->d_tx3, b->d_lrext, b->d_part, b->d_tr, b->d_proto, b->d_rlc_sc, b->d_rlc_flag, b->d_rlc_out};
+                   b->d_pts8, b->d_proofs, b->d_V, b->d_accept, b->d_lr, b->d_tx3, b->d_lrext, b->d_part, b->d_tr, b->d_proto, b->d_rlc_sc, b->d_rlc_flag, b->d_rlc_out, b->d_wstage};
     for (void *p : dev)
         if (p) cudaFree(p);
     if (b->h_pts8) cudaFreeHost(b->h_pts8);
@@ -438,12 +439,20 @@ extern "C" int bpp_acp_batch_upload_witness(bpp_acp_batch *b, const uint8_t *aL,
     if (!b || !aL || !aR || !aO || !gamma || !seeds) return BPP_ERR_INVALID_ARG;
     bpp_ctx *ctx = b->ctx;
     CK(ctx, cudaSetDevice(ctx->device));
-    const size_t pitch = (size_t)b->lay.stride * 32, n32 = (size_t)b->lay.n * 32, m32 = (size_t)b->lay.m * 32;
-    uint8_t *base = (uint8_t *)b->d_blk;
-    CK(ctx, cudaMemcpy2DAsync(base + 32 * (size_t)b->lay.aL, pitch, aL, n32, n32, b->B, cudaMemcpyHostToDevice, ctx->stream));
-    CK(ctx, cudaMemcpy2DAsync(base + 32 * (size_t)b->lay.aR, pitch, aR, n32, n32, b->B, cudaMemcpyHostToDevice, ctx->stream));
-    CK(ctx, cudaMemcpy2DAsync(base + 32 * (size_t)b->lay.aO, pitch, aO, n32, n32, b->B, cudaMemcpyHostToDevice, ctx->stream));
-    CK(ctx, cudaMemcpy2DAsync(base + 32 * (size_t)b->lay.gamma, pitch, gamma, m32, m32, b->B, cudaMemcpyHostToDevice, ctx->stream));
+    // four contiguous copies at full link speed into a staging buffer, then one kernel places every scalar in
+    // its proof's block (a strided 2-D copy of 3 KB rows runs at a fraction of the link rate)
+    const size_t n32 = (size_t)b->lay.n * 32 * b->B, m32 = (size_t)b->lay.m * 32 * b->B;
+    if (!b->d_wstage) CK(ctx, cudaMalloc((void **)&b->d_wstage, 3 * n32 + m32));
+    uint8_t *st = (uint8_t *)b->d_wstage;
+    CK(ctx, cudaMemcpyAsync(st, aL, n32, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(st + n32, aR, n32, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(st + 2 * n32, aO, n32, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(st + 3 * n32, gamma, m32, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        const uint32_t per = 3 * b->lay.n + b->lay.m;
+        k_acp_place_witness<<<dim3((per + 127) / 128, b->B), 128, 0, ctx->stream>>>(b->d_wstage, b->lay, b->B, b->d_blk);
+        LAUNCH_CHECK(ctx);
+    }
     CK(ctx, cudaMemcpyAsync(b->d_seeds, seeds, (size_t)b->B * 32, cudaMemcpyHostToDevice, ctx->stream));
     return BPP_OK;
 }

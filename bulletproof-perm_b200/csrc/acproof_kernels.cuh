@@ -67,6 +67,21 @@ __global__ void k_acp_rng(const uint32_t *__restrict__ seeds /* B x 8 */, acp_la
     sc_store(ACP_PTR(blk, lay, p, lay.alpha + j), r);
 }
 
+// staged witness [a_L (B x n) | a_R (B x n) | a_O (B x n) | gamma (B x m)] -> the proofs' scalar blocks
+__global__ void __launch_bounds__(128) k_acp_place_witness(const uint32_t *__restrict__ st, acp_layout lay, uint32_t B,
+                                                           uint32_t *__restrict__ blk) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
+    const uint32_t n = lay.n, m = lay.m;
+    if (i >= 3 * n + m) return;
+    const uint32_t which = i < 3 * n ? i / n : 3, k = i - which * n;
+    const uint32_t *src = which < 3 ? st + 8 * (((size_t)which * B + p) * n + k) : st + 8 * ((size_t)3 * B * n + (size_t)p * m + k);
+    const uint32_t off = which == 0 ? lay.aL : which == 1 ? lay.aR : which == 2 ? lay.aO : lay.gamma;
+    uint4 lo = *reinterpret_cast<const uint4 *>(src), hi = *reinterpret_cast<const uint4 *>(src + 4);
+    uint32_t *dst = ACP_PTR(blk, lay, p, off + k);
+    *reinterpret_cast<uint4 *>(dst) = lo;
+    *reinterpret_cast<uint4 *>(dst + 4) = hi;
+}
+
 // wide challenge bytes (64 B each, from the host transcripts) -> scalars at a layout offset
 __global__ void k_acp_put_wide(const uint32_t *__restrict__ wide /* B x per x 16 */, acp_layout lay, uint32_t off,
                                uint32_t per, uint32_t B, uint32_t *__restrict__ blk) {
