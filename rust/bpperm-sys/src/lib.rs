@@ -1,0 +1,74 @@
+//! Raw bindings to include/bpperm.h (hand-written, bindgen-free).  Status codes: 0 = ok, negative = error
+//! (`bpp_strerror`).  Every pointer is caller-owned; the library never frees caller memory.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int};
+
+#[repr(C)] pub struct bpp_ctx { _p: [u8; 0] }
+#[repr(C)] pub struct bpp_points { _p: [u8; 0] }
+#[repr(C)] pub struct bpp_circuit { _p: [u8; 0] }
+#[repr(C)] pub struct bpp_gens { _p: [u8; 0] }
+#[repr(C)] pub struct bpp_acp_batch { _p: [u8; 0] }
+
+pub const BPP_OK: c_int = 0;
+pub const BPP_ERR_LENGTH_MISMATCH: c_int = -4;
+pub const BPP_FMT_COMPRESSED: c_int = 0; // 32 B RFC 9496 encodings
+pub const BPP_FMT_AFFINE: c_int = 1;     // 64 B (x, y) canonical little endian
+pub const BPP_FMT_DALEK_XYZT: c_int = 2; // 160 B EdwardsPoint { X, Y, Z, T: FieldElement51([u64; 5]) }
+pub const MODE_REFERENCE: c_int = 0;
+pub const MODE_REFERENCE_FIXED: c_int = 1;
+pub const MODE_FIXED: c_int = 2;
+
+extern "C" {
+    pub fn bpp_init(device: c_int, out: *mut *mut bpp_ctx) -> c_int;
+    pub fn bpp_free(ctx: *mut bpp_ctx);
+    pub fn bpp_strerror(status: c_int) -> *const c_char;
+    pub fn bpp_last_error(ctx: *mut bpp_ctx) -> *const c_char;
+    pub fn bpp_synchronize(ctx: *mut bpp_ctx) -> c_int;
+
+    pub fn bpp_points_upload(ctx: *mut bpp_ctx, fmt: c_int, pts: *const u8, n: usize, out: *mut *mut bpp_points) -> c_int;
+    pub fn bpp_points_free(ctx: *mut bpp_ctx, p: *mut bpp_points);
+    pub fn bpp_points_len(p: *const bpp_points) -> usize;
+    pub fn bpp_msm_vartime(ctx: *mut bpp_ctx, scalars: *const u8, n_scalars: usize, points: *const bpp_points, off: usize,
+                           n: usize, out_compressed: *mut u8, out_ext: *mut u8) -> c_int;
+    pub fn bpp_msm_vartime_host(ctx: *mut bpp_ctx, scalars: *const u8, n_scalars: usize, fmt: c_int, pts: *const u8,
+                                n_points: usize, out_compressed: *mut u8) -> c_int;
+
+    pub fn bpp_inner_product(ctx: *mut bpp_ctx, a: *const u8, la: usize, b: *const u8, lb: usize, out: *mut u8) -> c_int;
+    pub fn bpp_hadamard_V(ctx: *mut bpp_ctx, a: *const u8, la: usize, b: *const u8, lb: usize, out: *mut u8) -> c_int;
+    pub fn bpp_vm_mult(ctx: *mut bpp_ctx, a: *const u8, la: usize, b: *const u8, rows: usize, cols: usize, out: *mut u8) -> c_int;
+    pub fn bpp_mv_mult(ctx: *mut bpp_ctx, a: *const u8, rows: usize, cols: usize, b: *const u8, lb: usize, out: *mut u8) -> c_int;
+    pub fn bpp_exp_iter(ctx: *mut bpp_ctx, x: *const u8, count: usize, out: *mut u8) -> c_int;
+    pub fn bpp_scalar_exp(ctx: *mut bpp_ctx, x: *const u8, pow: u32, out: *mut u8) -> c_int;
+    pub fn bpp_scalar_invert(ctx: *mut bpp_ctx, a: *const u8, n: usize, out: *mut u8) -> c_int;
+    pub fn bpp_scalar_from_wide(ctx: *mut bpp_ctx, in64: *const u8, n: usize, out: *mut u8) -> c_int;
+    pub fn bpp_vecpoly3_special_inner_product(ctx: *mut bpp_ctx, lhs: *const u8, rhs: *const u8, n: usize, out: *mut u8) -> c_int;
+    pub fn bpp_vecpoly3_eval(ctx: *mut bpp_ctx, coeffs: *const u8, n: usize, x: *const u8, out: *mut u8) -> c_int;
+    pub fn bpp_poly6_eval(ctx: *mut bpp_ctx, t1_t6: *const u8, x: *const u8, out: *mut u8) -> c_int;
+
+    pub fn bpp_circuit_create(ctx: *mut bpp_ctx, n: usize, q: usize, m: usize, nnz: *const u32, wire: *const u32,
+                              constraint: *const u32, coeff: *const u8, c_vec: *const u8, out: *mut *mut bpp_circuit) -> c_int;
+    pub fn bpp_circuit_free(ctx: *mut bpp_ctx, c: *mut bpp_circuit);
+    pub fn bpp_gens_create(ctx: *mut bpp_ctx, g: *const u8, h: *const u8, g_vec: *const u8, h_vec: *const u8, n: usize,
+                           window_bits: c_int, out: *mut *mut bpp_gens) -> c_int;
+    pub fn bpp_gens_free(ctx: *mut bpp_ctx, g: *mut bpp_gens);
+    pub fn bpp_acproof_proof_len_mode(n: usize, mode: c_int) -> usize;
+    pub fn bpp_acproof_prove_batch(ctx: *mut bpp_ctx, cir: *const bpp_circuit, gens: *const bpp_gens, mode: c_int, count: usize,
+                                   a_l: *const u8, a_r: *const u8, a_o: *const u8, gamma: *const u8, seeds: *const u8,
+                                   label: *const u8, label_len: usize, proofs_out: *mut u8) -> c_int;
+    pub fn bpp_acproof_verify_batch(ctx: *mut bpp_ctx, cir: *const bpp_circuit, gens: *const bpp_gens, mode: c_int, count: usize,
+                                    proofs: *const u8, v: *const u8, label: *const u8, label_len: usize,
+                                    verifier_seed: *const u8, accept: *mut u8) -> c_int;
+    pub fn bpp_acp_batch_create(ctx: *mut bpp_ctx, cir: *const bpp_circuit, gens: *const bpp_gens, mode: c_int, count: usize,
+                                label: *const u8, label_len: usize, out: *mut *mut bpp_acp_batch) -> c_int;
+    pub fn bpp_acp_batch_free(b: *mut bpp_acp_batch);
+    pub fn bpp_acp_batch_upload_witness(b: *mut bpp_acp_batch, a_l: *const u8, a_r: *const u8, a_o: *const u8,
+                                        gamma: *const u8, seeds: *const u8) -> c_int;
+    pub fn bpp_acp_batch_commit(b: *mut bpp_acp_batch, v: *const u8, v_out: *mut u8) -> c_int;
+    pub fn bpp_acp_batch_prove(b: *mut bpp_acp_batch) -> c_int;
+    pub fn bpp_acp_batch_download_proofs(b: *mut bpp_acp_batch, proofs_out: *mut u8) -> c_int;
+    pub fn bpp_acp_batch_upload_proofs(b: *mut bpp_acp_batch, proofs: *const u8, v: *const u8) -> c_int;
+    pub fn bpp_acp_batch_verify(b: *mut bpp_acp_batch, verifier_seed: *const u8) -> c_int;
+    pub fn bpp_acp_batch_download_accept(b: *mut bpp_acp_batch, accept: *mut u8) -> c_int;
+    pub fn bpp_acp_batch_set_host_transcripts(b: *mut bpp_acp_batch, on: c_int) -> c_int;
+    pub fn bpp_acp_batch_set_batch_rlc(b: *mut bpp_acp_batch, on: c_int) -> c_int;
+}
