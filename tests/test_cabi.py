@@ -47,3 +47,32 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt, f
+
+
+def test_tools_and_bench_product_legs_do_not_import_the_oracle():
+    """tools/ are product-side utilities: only tests/, smoke() and bench.py's CPU-baseline legs may touch oracle/"""
+    tools = os.path.join(ROOT, "tools")
+    for f in os.listdir(tools):
+        if f.endswith(".py"):
+            txt = open(os.path.join(tools, f)).read()
+            assert "import oracle" not in txt and "from oracle" not in txt, f
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    ours = bench[bench.index("def run_ours"):bench.index("def main")]
+    # inside the GPU arm the oracle may only appear in the cpu_baseline calls
+    assert "from oracle" not in ours and "import oracle" not in ours
+
+
+def test_null_arguments_are_rejected_without_a_device():
+    """entry points validate their arguments before touching CUDA: BPP_ERR_INVALID_ARG (-3), never a crash"""
+    import ctypes
+    import bpperm_b200
+    lib = bpperm_b200.load()
+    assert lib.bpp_acp_batch_set_host_transcripts(None, 1) == -3
+    assert lib.bpp_acp_batch_set_batch_rlc(None, 0) == -3
+    assert lib.bpp_transcript_script(None, b"x", 1, None, 0) == -3
+    assert lib.bpp_acp_batch_prove(None) == -3
+    assert lib.bpp_acp_batch_verify(None, bytes(32)) == -3
+    assert lib.bpp_msm_vartime(None, b"", 0, None, 0, 0, None, None) == -3
+    assert lib.bpp_strerror(-3).decode() == "invalid argument"
+    assert lib.bpp_acproof_proof_len_mode(104, 2) == 32 * (13 + 2 * 7)
+    assert lib.bpp_acproof_proof_len_mode(104, 1) == 32 * (11 + 208)
