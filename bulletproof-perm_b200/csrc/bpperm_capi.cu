@@ -318,15 +318,15 @@ extern "C" size_t bpp_points_len(const bpp_points *p) { return p ? p->n : 0; }
 
 // ---- MSM ---------------------------------------------------------------------------------------
 static int pick_window(size_t n) {
-    // minimise W * (n + 2 * 2^(c-1)) mixed-add equivalents; keep W <= 64
-    int best = 8;
-    double best_cost = 1e300;
-    for (int c = 4; c <= 16; c++) {
-        int W = (256 + c - 1) / c;
-        double cost = (double)W * ((double)n + 2.6 * (double)(1u << (c - 1)));
-        if (cost < best_cost) { best_cost = cost; best = c; }
-    }
-    return best;
+    // Measured on B200 (tools/window_tune.py, 2^10..2^21 points, every c in 8..16): below ~2^17 points the MSM
+    // is bound by its dependent chains (node merges + c*(W-1) Horner doublings), which c = 11 keeps shortest
+    // once the buckets fit (c = 8 for tiny inputs); from there the accumulate's W*n mixed adds decide:
+    // c = 15 below ~2^20 points, c = 16 from there (equal at 2^20; 16 keeps W*n exact for 252-bit scalars).  (Odd widths win over their even neighbours because
+    // W = ceil(256/c) drops at 11, 13, 15.)
+    if (n <= 1500) return 8;
+    if (n <= 180000) return 11;
+    if (n < 1000000) return 15;
+    return 16;
 }
 
 static int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points *pts, size_t off, size_t n,
