@@ -45,6 +45,10 @@ struct bpp_acp_batch {
     bool host_transcripts = false;
     uint64_t *d_tr = nullptr, *d_proto = nullptr;
     uint32_t *d_wstage = nullptr;   // witness staging (contiguous upload), allocated on first use
+    // verifier fork: point decompression (IMAD-bound, fills the GPU) runs on `aux` beside the challenge-dependent
+    // scalar chain (Fiat-Shamir replay, Fibonacci power chains, CSR products: serial, low occupancy)
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // batch verification by random linear combination (k_rlc_*): scalars of the one MSM over the batch's
     // dynamic points + the shared generators (appended to d_dyn), its compressed result, the fall-back flag
     bool batch_rlc = true;
@@ -241,6 +245,9 @@ extern "C" void bpp_acp_batch_free(bpp_acp_batch *b) {
     if (b->h_lr) cudaFreeHost(b->h_lr);
     if (b->h_tx3) cudaFreeHost(b->h_tx3);
     if (b->h_rlc_flag) cudaFreeHost(b->h_rlc_flag);
+    if (b->aux) cudaStreamDestroy(b->aux);
+    if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+    if (b->ev_join) cudaEventDestroy(b->ev_join);
     delete b;
 }
 
@@ -273,6 +280,9 @@ extern "C" int bpp_acp_batch_create(bpp_ctx *ctx, const bpp_circuit *cir, const 
     cudaError_t e = cudaMalloc((void **)&b->d_blk, B * b->lay.stride * 32);
     if (e == cudaSuccess) e = cudaMemsetAsync(b->d_blk, 0, B * b->lay.stride * 32, ctx->stream);
     if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_seeds, B * 32);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->aux, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_tr, B * MERLIN_STATE_WORDS * 8);
     if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_proto, MERLIN_STATE_WORDS * 8);
     if (e == cudaSuccess) {   // Transcript::new(label) + arithmetic_domain_sep(n): identical for every proof, hashed once
@@ -498,6 +508,8 @@ static int acp_challenge_dependent_scalars(bpp_acp_batch *b) {
         LAUNCH_CHECK(ctx);
     } else {
         k_acp_pow<<<(b->B + 31) / 32, ACP_POW_THREADS, 0, ctx->stream>>>(L, b->B, b->d_blk);
+        LAUNCH_CHECK(ctx);
+        k_acp_pow_unmont<<<dim3((2 * L.n + L.Q + 127) / 128, b->B), 128, 0, ctx->stream>>>(L, b->d_blk);
         LAUNCH_CHECK(ctx);
     }
     acp_csr W{b->cir->d_rowptr, b->cir->d_col, b->cir->d_kind, b->cir->d_coeff, b->cir->rows};
@@ -731,6 +743,14 @@ static int acp_verify_fixed(bpp_acp_batch *b, const uint8_t verifier_seed[32]) {
     k_acp_unpack_fixed<<<dim3((b->proof_len / 32 + 127) / 128, B), 128, 0, s>>>(L, b->d_proofs, b->proof_len, b->d_blk, b->d_pts8,
                                                                                b->d_lr, b->d_tx3);
     LAUNCH_CHECK(ctx);
+    CK(ctx, cudaEventRecord(b->ev_fork, s));
+    CK(ctx, cudaStreamWaitEvent(b->aux, b->ev_fork, 0));
+    CK(ctx, cudaMemsetAsync(b->d_bad, 0, (size_t)B * 4, b->aux));
+    k_acp_decompress<<<(B * (m + 8) + 127) / 128, 128, 0, b->aux>>>(b->d_V, b->d_pts8, m, B, per, b->d_dyn, b->d_bad);
+    LAUNCH_CHECK(ctx);
+    k_acp_decompress_lr<<<(B * 2 * lg + 127) / 128, 128, 0, b->aux>>>(b->d_lr, m, lg, B, b->d_dyn, b->d_bad);
+    LAUNCH_CHECK(ctx);
+    CK(ctx, cudaEventRecord(b->ev_join, b->aux));
     CK(ctx, cudaMemcpyAsync(b->d_vseed, verifier_seed, 32, cudaMemcpyHostToDevice, s));
     if (!b->host_transcripts) {
         k_tr_verify<<<(B + TR_THREADS - 1) / TR_THREADS, TR_THREADS, 0, s>>>(b->d_proto, b->d_pts8, (const uint8_t *)b->d_tx3, b->d_lr,
@@ -782,13 +802,9 @@ static int acp_verify_fixed(bpp_acp_batch *b, const uint8_t verifier_seed[32]) {
     LAUNCH_CHECK(ctx);
     k_ipa_vprep<<<(B + 63) / 64, 64, 0, s>>>(L, B, b->d_blk);
     LAUNCH_CHECK(ctx);
-    CK(ctx, cudaMemsetAsync(b->d_bad, 0, (size_t)B * 4, s));
-    k_acp_decompress<<<(B * (m + 8) + 127) / 128, 128, 0, s>>>(b->d_V, b->d_pts8, m, B, per, b->d_dyn, b->d_bad);
-    LAUNCH_CHECK(ctx);
-    k_acp_decompress_lr<<<(B * 2 * lg + 127) / 128, 128, 0, s>>>(b->d_lr, m, lg, B, b->d_dyn, b->d_bad);
-    LAUNCH_CHECK(ctx);
     k_acp_vscal_fixed<<<dim3((np + m + 1 + 127) / 128, B), 128, 0, s>>>(L, b->d_blk);
     LAUNCH_CHECK(ctx);
+    CK(ctx, cudaStreamWaitEvent(s, b->ev_join, 0));   // decompressed points + bad flags (forked after the unpack)
     if (b->batch_rlc && (size_t)B * per >= 1024) {   // enough points for the bucket method to pay
         bool decided = false;
         if ((rc = acp_verify_rlc(b, per, 0, &decided))) return rc;
@@ -820,6 +836,12 @@ extern "C" int bpp_acp_batch_verify(bpp_acp_batch *b, const uint8_t verifier_see
     int rc;
     k_acp_unpack<<<dim3((b->proof_len / 32 + 127) / 128, B), 128, 0, s>>>(L, B, b->d_proofs, b->proof_len, b->d_blk, b->d_pts8);
     LAUNCH_CHECK(ctx);
+    CK(ctx, cudaEventRecord(b->ev_fork, s));
+    CK(ctx, cudaStreamWaitEvent(b->aux, b->ev_fork, 0));
+    CK(ctx, cudaMemsetAsync(b->d_bad, 0, (size_t)B * 4, b->aux));
+    k_acp_decompress<<<(B * per + 127) / 128, 128, 0, b->aux>>>(b->d_V, b->d_pts8, m, B, per, b->d_dyn, b->d_bad);
+    LAUNCH_CHECK(ctx);
+    CK(ctx, cudaEventRecord(b->ev_join, b->aux));
     CK(ctx, cudaMemcpyAsync(b->d_vseed, verifier_seed, 32, cudaMemcpyHostToDevice, s));
     const int mode = b->mode;
     if (!b->host_transcripts) {
@@ -853,11 +875,9 @@ extern "C" int bpp_acp_batch_verify(bpp_acp_batch *b, const uint8_t verifier_see
     if ((rc = acp_challenge_dependent_scalars(b))) return rc;
     k_acp_dots<<<dim3(2, B), 128, 0, s>>>(L, 9, b->d_blk);  // sigma, <l, r>
     LAUNCH_CHECK(ctx);
-    CK(ctx, cudaMemsetAsync(b->d_bad, 0, (size_t)B * 4, s));
-    k_acp_decompress<<<(B * per + 127) / 128, 128, 0, s>>>(b->d_V, b->d_pts8, m, B, per, b->d_dyn, b->d_bad);
-    LAUNCH_CHECK(ctx);
     k_acp_vscal<<<dim3((n + m + 1 + 127) / 128, B), 128, 0, s>>>(L, b->d_blk);
     LAUNCH_CHECK(ctx);
+    CK(ctx, cudaStreamWaitEvent(s, b->ev_join, 0));   // decompressed points + bad flags (forked after the unpack)
     if (b->batch_rlc && mode != 0 && (size_t)B * per >= 1024) {   // `reference` mode never accepts: nothing to gain from the combined check
         bool decided = false;
         if ((rc = acp_verify_rlc(b, per, 1, &decided))) return rc;

@@ -344,18 +344,29 @@ __global__ void __launch_bounds__(ACP_POW_THREADS) k_acp_pow(acp_layout lay, uin
     sc_const(one_m, SC_R);
     const uint32_t cnt = which == 1 ? lay.Q : lay.n;
     uint32_t *dst = ACP_PTR(blk, lay, p, which == 0 ? lay.yn : which == 1 ? lay.zq : lay.yninv);
-    sc base = one_m, nxt, ret, s;
+    sc base = one_m, nxt, ret;
     sc_load(nxt, ACP_PTR(blk, lay, p, which == 1 ? lay.z : lay.y));
     if (which == 2) sc_invert(nxt, nxt);
     sc_to_mont(nxt, nxt);
+    // the chain stores Montgomery-form values: one dependent multiplication per step; k_acp_pow_unmont converts
+    // the whole range afterwards with one thread per element
 #pragma unroll 1
     for (uint32_t i = 0; i < cnt; i++) {
         ret = nxt;
         sc_mont_noinline(nxt, nxt, base);
         base = ret;
-        sc_from_mont(s, ret);
-        sc_store(dst + 8 * (size_t)i, s);
+        sc_store(dst + 8 * (size_t)i, ret);
     }
+}
+// y_n | y_n_inv | z_q are contiguous in the proof block: Montgomery form -> standard form, in place
+__global__ void __launch_bounds__(128) k_acp_pow_unmont(acp_layout lay, uint32_t *__restrict__ blk) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
+    if (i >= 2 * lay.n + lay.Q) return;
+    uint32_t *ptr = ACP_PTR(blk, lay, p, lay.yn + i);
+    sc v;
+    sc_load(v, ptr);
+    sc_from_mont(v, v);
+    sc_store(ptr, v);
 }
 
 // CSR weights.  Row r of the concatenation [W_L (n) | W_R (n) | W_O (n) | W_V (m) | c (1)] holds
