@@ -52,6 +52,20 @@ def _peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
 
 
+def _ncu_traffic(name):
+    """dram read + write bytes per launch from a committed `ncu --set full` summary (profiles/<name>), or None."""
+    import csv
+    path = os.path.join(ROOT, "profiles", name)
+    if not os.path.exists(path):
+        return None
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = 0.0
+    for row in csv.reader(open(path)):
+        if len(row) >= 3 and row[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(row[2]) * mult.get(row[1], 1.0)
+    return tot or None
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons during the timed region."""
 
@@ -441,7 +455,10 @@ def run_ours(args):
                              "achieved": ach / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD.WIDE.U32/s",
                              "frac": ach / imad_peak, "kernel_ms": fb_ms, "point_adds_per_s": (fb_madd + fb_add) / (fb_ms * 1e-3),
                              "peak_source": peak_src, "imad_probes": imad_probes,
-                             "traffic": None, "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_peak_source": peaks_src},
+                             "traffic": _ncu_traffic("r1_ncu_full_k_fb_msm.csv"),
+                             "traffic_source": "profiles/r1_ncu_full_k_fb_msm.csv (dram read+write of one A_I-shaped launch; "
+                                               "algorithmic gathers = mixed adds x 96 B)",
+                             "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_peak_source": peaks_src},
                 "clocks": clocks,
             }
             if world == 1 and not args.no_cpu:
@@ -517,7 +534,7 @@ def run_ours(args):
                 "roofline": {"bound": "imad", "kernel": "k_bucket_accum", "achieved": ach / 1e12, "peak": imad_peak / 1e12,
                              "unit": "T IMAD.WIDE.U32/s", "frac": ach / imad_peak, "kernel_ms": float(phases[3]),
                              "point_adds_per_s": ops["mixed_adds"] / acc_t, "peak_source": peak_src,
-                             "traffic": 1.60e9 if args.log_n == 20 else None,
+                             "traffic": _ncu_traffic("r1_ncu_full_k_bucket_accum.csv") if args.log_n == 20 else None,
                              "traffic_source": "profiles/r1_ncu_full_k_bucket_accum.csv (dram read+write per launch)",
                              "whole_msm": {"imad_equiv": imads_all, "frac_of_peak": imads_all / (ms_res / msm_steps * 1e-3) / imad_peak},
                              "phases_ms": dict(zip(bpperm_b200.backend.PHASES, [float(x) for x in phases]))},

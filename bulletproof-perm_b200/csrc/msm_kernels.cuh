@@ -157,7 +157,7 @@ FE_INLINE void bucket_flush(const ge_ext &acc, uint32_t w, uint32_t b, uint32_t 
     ge_store(dst, acc);
 }
 
-__global__ void __launch_bounds__(BPP_ACC_THREADS) k_bucket_accum(
+__global__ void __launch_bounds__(BPP_ACC_THREADS, 4) k_bucket_accum(
     const uint32_t *__restrict__ niels, const uint32_t *__restrict__ entries, const uint32_t *__restrict__ offsets,
     const uint32_t *__restrict__ ends, uint32_t n, uint32_t B, uint32_t tiles_per_window, uint32_t total_tiles,
     uint32_t *__restrict__ buckets, uint32_t *__restrict__ partials) {
