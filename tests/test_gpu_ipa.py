@@ -150,3 +150,48 @@ def test_large_deck_4096_cards_single_proof_is_byte_identical(backend):
     assert list(G.verify_batch(backend, cir, gens, bytes(bad), Vc, 1, "fixed")) == [0]
     gens.free()
     cir.free()
+
+
+def test_batch_verification_with_one_percent_corrupted_proofs_matches_the_oracle_per_proof(backend):
+    """BASELINE configs[3] in miniature: a batch of 512 independent 52-card proofs, 6 of them (>1 %) corrupted in
+    different fields; the accept bytes must equal the C restatement's decision for every single proof, with the
+    combined batch check (which must fall back) and with strictly per-proof verification."""
+    from bpperm_b200 import acproof as G
+    core, prover, V, cir, gens, inst = _setup(backend, 52, 54, 8)
+    n, m = core["n"], core["m"]
+    B = 512
+    plen = G.proof_len(n, "fixed")
+    seeds = b"".join((1000 + i).to_bytes(4, "little") * 8 for i in range(B))
+    batch = G.Batch(backend, cir, gens, B, "fixed", b"test")
+    batch.upload_witness(_sb(prover["a_L"]) * B, _sb(prover["a_R"]) * B, _sb(prover["a_O"]) * B, _sb(prover["gamma"]) * B, seeds)
+    batch.prove()
+    good = batch.download_proofs()
+    Vp = inst.commit(_sb(prover["v"]), _sb(prover["gamma"]))
+    Vc1 = cref.compress(Vp)
+    # all valid: the combined check decides
+    batch.upload_proofs(good, Vc1 * B)
+    batch.verify(b"\x21" * 32)
+    assert batch.download_accept() == b"\x01" * B
+    proofs, Vc = bytearray(good), bytearray(Vc1 * B)
+    victims = {3: 0, 77: 5, 128: 8, 300: 11, 400: 12, 511: plen // 32 - 1}     # A_I, T_4, t, L_0, R_0, b
+    for p, f in victims.items():
+        if f in (0, 5, 11, 12):
+            proofs[p * plen + 32 * f: p * plen + 32 * f + 32] = R.compress(R.pt_mul(p + 2, R.BASEPOINT))
+        else:
+            s = (int.from_bytes(proofs[p * plen + 32 * f: p * plen + 32 * f + 32], "little") + 1) % L
+            proofs[p * plen + 32 * f: p * plen + 32 * f + 32] = R.sc_bytes(s)
+    Vc[32 * (m * 222 + 7): 32 * (m * 222 + 8)] = R.compress(R.pt_mul(3, R.BASEPOINT))              # commitment 7 of proof 222
+    want = []
+    for i in range(B):
+        if i in victims or i == 222 or i % 64 == 0:      # every corrupted proof + a sample of the valid ones
+            Vi = cref.decompress(bytes(Vc[i * 32 * m:(i + 1) * 32 * m]))
+            want.append(1 if inst.verify(bytes(proofs[i * plen:(i + 1) * plen]), Vi) else 0)
+        else:
+            want.append(1)
+    assert sum(want) == B - 7
+    for rlc in (True, False):
+        batch.set_batch_rlc(rlc)
+        batch.upload_proofs(bytes(proofs), bytes(Vc))
+        batch.verify(b"\x21" * 32)
+        assert list(batch.download_accept()) == want, rlc
+    batch.free()
