@@ -335,23 +335,25 @@ static int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points
     const int W = (256 + c - 1) / c;
     const uint32_t B = 1u << (c - 1);
     const size_t WB = (size_t)W * B;
-    // reduction plan: thread-serial merges of 8 nodes while more than 1024 nodes per window remain,
-    // then warp merges of 32 down to one root node per window
-    struct level { int warp; uint32_t L, T_in, T_out, loglen; };
-    level plan[8];
+    // reduction plan (msm_kernels.cuh): level 0 merges 8 buckets per THREAD (the GPU is full: 2^(c-1)*W buckets);
+    // after that few nodes are left and the work is a dependent chain, so a QUAD of lanes carries each node:
+    // quad-serial merges of 8 while more than 1024 nodes per window remain, then block merges of 32 down to one root
+    struct level { int kind; uint32_t L, T_in, T_out, loglen; };   // kind 0 thread-serial, 1 quad-serial, 2 quad block merge
+    level plan[10];
     int n_levels = 0;
     uint32_t T = B, loglen = 0;
     size_t node_elems = 0;  // u32 elements of node storage (S and A each), ping-pong halves
     while (T > 1) {
         level lv;
-        if (T > 1024) { lv.warp = 0; lv.L = 8; lv.T_out = T / 8; }
-        else { lv.warp = 1; lv.L = 32; lv.T_out = (T + 31) / 32; }
+        if (n_levels == 0 && T >= 64) { lv.kind = 0; lv.L = 8; lv.T_out = T / 8; }
+        else if (T > 1024) { lv.kind = 1; lv.L = 8; lv.T_out = T / 8; }
+        else { lv.kind = 2; lv.L = 32; lv.T_out = (T + 31) / 32; }
         lv.T_in = T;
         lv.loglen = loglen;
         plan[n_levels++] = lv;
         if ((size_t)W * lv.T_out * 32 > node_elems) node_elems = (size_t)W * lv.T_out * 32;
         T = lv.T_out;
-        loglen += lv.warp ? 5 : 3;
+        loglen += lv.kind == 2 ? 5 : 3;
     }
     int rc;
     if ((rc = grow(ctx, &ctx->d_counts, &ctx->cap_wb, WB))) return rc;
@@ -409,13 +411,17 @@ static int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points
     for (int i = 0; i < n_levels; i++) {
         const level &lv = plan[i];
         uint32_t *oS = ctx->d_segS + (i & 1) * node_elems, *oA = ctx->d_segR + (i & 1) * node_elems;
-        if (!lv.warp) {
-            uint32_t n_out = (uint32_t)W * lv.T_out;
+        const uint32_t n_out = (uint32_t)W * lv.T_out;
+        if (lv.kind == 0) {
             k_node_merge_serial<<<(n_out + 127) / 128, 128, 0, s>>>(curS, curA, lv.L, lv.loglen, n_out, oS, oA);
             red_add += (uint64_t)n_out * (2 * lv.L - 3 + (curA ? lv.L : 0));
             red_dbl += (uint64_t)n_out * lv.loglen;
+        } else if (lv.kind == 1) {
+            k_node_merge_quad_serial<<<(4 * n_out + 127) / 128, 128, 0, s>>>(curS, curA, lv.L, lv.loglen, n_out, oS, oA);
+            red_add += (uint64_t)n_out * (3 * lv.L - 3);
+            red_dbl += (uint64_t)n_out * lv.loglen;
         } else {
-            k_node_merge_warp<<<dim3((lv.T_out + 3) / 4, W), 128, 0, s>>>(curS, curA, lv.T_in, lv.loglen, lv.T_out, oS, oA);
+            k_node_merge_quad_block<<<dim3(lv.T_out, W), 128, 0, s>>>(curS, curA, lv.T_in, lv.loglen, lv.T_out, oS, oA);
             red_add += (uint64_t)W * lv.T_out * (2 * (uint64_t)lv.T_in / lv.T_out + 1);  // useful additions
             red_dbl += (uint64_t)W * lv.T_out * lv.loglen;
         }

@@ -336,140 +336,203 @@ __global__ void __launch_bounds__(128) k_node_merge_serial(const uint32_t *__res
     ge_store(outA + 32 * (size_t)g, acc);
 }
 
-FE_INLINE void ge_shfl_down(ge_ext &r, const ge_ext &a, int d) {
+// ---- lane-parallel ("quad") point arithmetic --------------------------------------------------------
+// Everything after the first merge level is a short dependent chain of point operations on few points:
+// nothing to parallelise across points, and a warp instruction costs the same for 1 or 32 active lanes.
+// So the four independent field multiplications of each stage of a point operation run in four LANES:
+// an aligned group of 4 lanes (a quad) holds one point, lane k of the quad holds coordinate k of
+// (X, Y, Z, T).  A doubling costs one squaring + one multiplication of warp time instead of 4 + 4, a full
+// addition three multiplications instead of nine; a warp carries 8 points.
+FE_INLINE void fe_shfl4(fe &r, const fe &a, int k) {   // coordinate k of this lane's quad
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        r.X.v[i] = __shfl_down_sync(0xffffffffu, a.X.v[i], d);
-        r.Y.v[i] = __shfl_down_sync(0xffffffffu, a.Y.v[i], d);
-        r.Z.v[i] = __shfl_down_sync(0xffffffffu, a.Z.v[i], d);
-        r.T.v[i] = __shfl_down_sync(0xffffffffu, a.T.v[i], d);
-    }
+    for (int i = 0; i < 8; i++) r.v[i] = __shfl_sync(0xffffffffu, a.v[i], k, 4);
 }
-FE_INLINE void ge_select(ge_ext &r, const ge_ext &a, bool take) {
+FE_INLINE void fe_shfl_xor1(fe &r, const fe &a) {      // swap within the lane pairs (0,1) and (2,3)
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        if (take) {
-            r.X.v[i] = a.X.v[i]; r.Y.v[i] = a.Y.v[i]; r.Z.v[i] = a.Z.v[i]; r.T.v[i] = a.T.v[i];
-        }
-    }
-}
-
-// Warp merge of 32 nodes (one per lane; identity for missing lanes).  On return lane 0 holds
-// S' in `S` and A' in `A`.  15 additions deep.
-__device__ __noinline__ void warp_node_merge(ge_ext &S, ge_ext &A, uint32_t loglen) {
-    const uint32_t lane = threadIdx.x & 31;
-    ge_ext o, t;
-#pragma unroll 1
-    for (int d = 1; d < 32; d <<= 1) {  // inclusive suffix scan: S_lane = sum_{j >= lane} S_j
-        ge_shfl_down(o, S, d);
-        ge_add(t, S, o);
-        ge_select(S, t, lane + d < 32);
-    }
-    // sum_k k * S_k = sum_{j = 1..31} suffix_j; the plain sum of A rides along in the same tree
-    ge_ext b = S;
-    if (lane == 0) ge_identity(b);
-#pragma unroll 1
-    for (int d = 16; d >= 1; d >>= 1) {
-        ge_shfl_down(o, b, d);
-        ge_add(t, b, o);
-        ge_select(b, t, lane < (uint32_t)d);
-        ge_shfl_down(o, A, d);
-        ge_add(t, A, o);
-        ge_select(A, t, lane < (uint32_t)d);
-    }
-#pragma unroll 1
-    for (uint32_t i = 0; i < loglen; i++) ge_double(b, b);
-    ge_add(A, A, b);
-}
-
-// grid (ceil(T/32) warps per window, W); 128 threads = 4 warps per block.
-__global__ void __launch_bounds__(128) k_node_merge_warp(const uint32_t *__restrict__ inS,
-                                                         const uint32_t *__restrict__ inA, uint32_t T,
-                                                         uint32_t loglen, uint32_t T_out,
-                                                         uint32_t *__restrict__ outS, uint32_t *__restrict__ outA) {
-    const uint32_t w = blockIdx.y, lane = threadIdx.x & 31;
-    const uint32_t g = blockIdx.x * 4 + (threadIdx.x >> 5);  // output node within the window
-    if (g >= T_out) return;
-    const uint32_t t = g * 32 + lane;
-    ge_ext S, A;
-    ge_identity(S);
-    ge_identity(A);
-    if (t < T) {
-        ge_load(S, inS + 32 * ((size_t)w * T + t));
-        if (inA) ge_load(A, inA + 32 * ((size_t)w * T + t));
-    }
-    warp_node_merge(S, A, loglen);
-    if (lane == 0) {
-        ge_store(outS + 32 * ((size_t)w * T_out + g), S);
-        ge_store(outA + 32 * ((size_t)w * T_out + g), A);
-    }
-}
-
-// ---- final combination: lane-parallel point arithmetic -------------------------------------------
-// The Horner combination of the window totals is one dependent chain of c*(W-1) doublings: nothing
-// to parallelise across points, and a warp instruction costs the same for 1 or 32 active lanes.  So
-// the four independent field multiplications of each half of a point operation run in four LANES
-// of one warp ("quad" form: lane k holds coordinate k of (X, Y, Z, T)); a doubling costs one
-// squaring + one multiplication of warp time instead of 4 + 4.
-FE_INLINE void fe_shfl(fe &r, const fe &a, int src) {
-#pragma unroll
-    for (int i = 0; i < 8; i++) r.v[i] = __shfl_sync(0xffffffffu, a.v[i], src);
+    for (int i = 0; i < 8; i++) r.v[i] = __shfl_xor_sync(0xffffffffu, a.v[i], 1);
 }
 FE_INLINE void fe_pick(fe &r, const fe &a, const fe &b, bool take_a) {
 #pragma unroll
     for (int i = 0; i < 8; i++) r.v[i] = take_a ? a.v[i] : b.v[i];
 }
-// second half shared by doubling and addition: lane0 E*F, lane1 G*H, lane2 F*G, lane3 E*H
-FE_INLINE void quad_finish(fe &v, const fe &E, const fe &F, const fe &G, const fe &H, uint32_t lane) {
+FE_INLINE void quad_identity(fe &v, uint32_t ql) {     // (0, 1, 1, 0)
+    fe_set0(v);
+    v.v[0] = (ql == 1 || ql == 2) ? 1u : 0u;
+}
+FE_INLINE void quad_load(fe &v, const uint32_t *node, uint32_t ql) { fe_load(v, node + 8 * ql); }
+FE_INLINE void quad_store(uint32_t *node, const fe &v, uint32_t ql) { fe_store(node + 8 * ql, v); }
+// last stage shared by doubling and addition: lane0 E*F, lane1 G*H, lane2 F*G, lane3 E*H
+FE_INLINE void quad_finish(fe &v, const fe &E, const fe &F, const fe &G, const fe &H, uint32_t ql) {
     fe p, q, t;
-    fe_pick(t, G, F, lane == 1);
-    fe_pick(p, E, t, lane == 0 || lane == 3);
-    fe_pick(t, G, H, lane == 2);
-    fe_pick(q, F, t, lane == 0);
+    fe_pick(t, G, F, ql == 1);
+    fe_pick(p, E, t, ql == 0 || ql == 3);
+    fe_pick(t, G, H, ql == 2);
+    fe_pick(q, F, t, ql == 0);
     fe_mul(v, p, q);
 }
-__device__ __noinline__ void quad_double(fe &v, uint32_t lane) {
+__device__ __noinline__ void quad_double(fe &v, uint32_t ql) {
     fe x, y, s, in, sq, A, B, Zs, D, E, F, G, H;
-    fe_shfl(x, v, 0);
-    fe_shfl(y, v, 1);
+    fe_shfl4(x, v, 0);
+    fe_shfl4(y, v, 1);
     fe_add(s, x, y);
-    fe_pick(in, s, v, lane == 3);
+    fe_pick(in, s, v, ql == 3);
     fe_sqr(sq, in);
-    fe_shfl(A, sq, 0);
-    fe_shfl(B, sq, 1);
-    fe_shfl(Zs, sq, 2);
-    fe_shfl(D, sq, 3);
+    fe_shfl4(A, sq, 0);
+    fe_shfl4(B, sq, 1);
+    fe_shfl4(Zs, sq, 2);
+    fe_shfl4(D, sq, 3);
     fe_add(H, A, B);
     fe_sub(E, H, D);
     fe_sub(G, A, B);
     fe_dbl(Zs, Zs);
     fe_add(F, Zs, G);
-    quad_finish(v, E, F, G, H, lane);
+    quad_finish(v, E, F, G, H, ql);
 }
-// v += the point cached at c (8 limbs each of Y+X, Y-X, Z, 2d*T; same address in every lane)
-__device__ __noinline__ void quad_add_cached(fe &v, const uint32_t *c, uint32_t lane) {
+// v += the point cached at c (8 limbs each of Y+X, Y-X, Z, 2d*T; same address in every lane): two stages
+__device__ __noinline__ void quad_add_cached(fe &v, const uint32_t *c, uint32_t ql) {
     fe x, y, z, t, p, q, m, a, b, cc, d, E, F, G, H;
-    fe_shfl(x, v, 0);
-    fe_shfl(y, v, 1);
-    fe_shfl(z, v, 2);
-    fe_shfl(t, v, 3);
+    fe_shfl4(x, v, 0);
+    fe_shfl4(y, v, 1);
+    fe_shfl4(z, v, 2);
+    fe_shfl4(t, v, 3);
     fe_sub(a, y, x);
     fe_add(b, y, x);
-    fe_pick(p, a, b, lane == 0);
-    fe_pick(q, t, z, lane == 2);
-    fe_pick(p, p, q, lane < 2);
-    fe_load(q, c + 8 * (lane == 0 ? 1 : lane == 1 ? 0 : lane == 2 ? 3 : 2));
+    fe_pick(p, a, b, ql == 0);
+    fe_pick(q, t, z, ql == 2);
+    fe_pick(p, p, q, ql < 2);
+    fe_load(q, c + 8 * (ql == 0 ? 1 : ql == 1 ? 0 : ql == 2 ? 3 : 2));
     fe_mul(m, p, q);
-    fe_shfl(a, m, 0);
-    fe_shfl(b, m, 1);
-    fe_shfl(cc, m, 2);
-    fe_shfl(d, m, 3);
+    fe_shfl4(a, m, 0);
+    fe_shfl4(b, m, 1);
+    fe_shfl4(cc, m, 2);
+    fe_shfl4(d, m, 3);
     fe_dbl(d, d);
     fe_sub(E, b, a);
     fe_add(H, b, a);
     fe_sub(F, d, cc);
     fe_add(G, d, cc);
-    quad_finish(v, E, F, G, H, lane);
+    quad_finish(v, E, F, G, H, ql);
+}
+// v += w, both in quad form: (Y1-X1)(Y2-X2) | (Y1+X1)(Y2+X2) | T1*T2 | Z1*Z2, then 2d*(T1*T2) in lane 2,
+// then the four products of the last stage.
+__device__ __noinline__ void quad_add(fe &v, const fe &w, uint32_t ql) {
+    fe x1, y1, x2, y2, p1, p2, a, b, m, k, cc, d, E, F, G, H;
+    fe_shfl4(x1, v, 0);
+    fe_shfl4(y1, v, 1);
+    fe_shfl4(x2, w, 0);
+    fe_shfl4(y2, w, 1);
+    fe_shfl_xor1(p1, v);    // lane 2 <- T1, lane 3 <- Z1
+    fe_shfl_xor1(p2, w);    // lane 2 <- T2, lane 3 <- Z2
+    fe_sub(a, y1, x1);
+    fe_sub(b, y2, x2);
+    fe_add(m, y1, x1);
+    fe_add(k, y2, x2);
+    fe_pick(a, a, m, ql == 0);
+    fe_pick(b, b, k, ql == 0);
+    fe_pick(a, a, p1, ql < 2);
+    fe_pick(b, b, p2, ql < 2);
+    fe_mul(m, a, b);
+    fe_const(k, GE_D2);
+    fe_set1(a);
+    fe_pick(k, k, a, ql == 2);
+    fe_mul(m, m, k);        // lane 2: 2d*T1*T2; the other lanes multiply by one
+    fe_shfl4(a, m, 0);
+    fe_shfl4(b, m, 1);
+    fe_shfl4(cc, m, 2);
+    fe_shfl4(d, m, 3);
+    fe_dbl(d, d);
+    fe_sub(E, b, a);
+    fe_add(H, b, a);
+    fe_sub(F, d, cc);
+    fe_add(G, d, cc);
+    quad_finish(v, E, F, G, H, ql);
+}
+
+// Quad-serial merge of L nodes into one (same arithmetic as k_node_merge_serial, one quad per output node).
+__global__ void __launch_bounds__(128) k_node_merge_quad_serial(const uint32_t *__restrict__ inS,
+                                                                const uint32_t *__restrict__ inA, uint32_t L,
+                                                                uint32_t loglen, uint32_t n_out,
+                                                                uint32_t *__restrict__ outS, uint32_t *__restrict__ outA) {
+    const uint32_t ql = threadIdx.x & 3;
+    uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const bool live = g < n_out;
+    if (!live) g = n_out - 1;   // whole quads stay in step for the shuffles; only live quads store
+    const uint32_t *ps = inS + 32 * (size_t)g * L, *pa = inA + 32 * (size_t)g * L;
+    fe run, acc, t;
+    quad_load(run, ps + 32 * (size_t)(L - 1), ql);
+    acc = run;
+#pragma unroll 1
+    for (int k = (int)L - 2; k >= 1; k--) {
+        quad_load(t, ps + 32 * (size_t)k, ql);
+        quad_add(run, t, ql);
+        quad_add(acc, run, ql);
+    }
+    quad_load(t, ps, ql);
+    quad_add(run, t, ql);
+#pragma unroll 1
+    for (uint32_t i = 0; i < loglen; i++) quad_double(acc, ql);
+#pragma unroll 1
+    for (uint32_t k = 0; k < L; k++) {
+        quad_load(t, pa + 32 * (size_t)k, ql);
+        quad_add(acc, t, ql);
+    }
+    if (live) {
+        quad_store(outS + 32 * (size_t)g, run, ql);
+        quad_store(outA + 32 * (size_t)g, acc, ql);
+    }
+}
+
+// Block merge of 32 nodes (one per quad, identity for missing ones): suffix scan of S (5 additions),
+// then sum_k k*S_k and sum_k A_k as two trees riding together (5 x 2), loglen doublings, one addition.
+// Partner values travel through shared memory (the 32 quads span 4 warps).  grid (T_out, W).
+__global__ void __launch_bounds__(128) k_node_merge_quad_block(const uint32_t *__restrict__ inS,
+                                                               const uint32_t *__restrict__ inA, uint32_t T,
+                                                               uint32_t loglen, uint32_t T_out,
+                                                               uint32_t *__restrict__ outS, uint32_t *__restrict__ outA) {
+    __shared__ __align__(16) uint32_t shS[32][32], shA[32][32];
+    const uint32_t w = blockIdx.y, g = blockIdx.x, quad = threadIdx.x >> 2, ql = threadIdx.x & 3;
+    const uint32_t t = g * 32 + quad;
+    fe S, A, o, oa, tmp;
+    quad_identity(S, ql);
+    quad_identity(A, ql);
+    if (t < T) {
+        quad_load(S, inS + 32 * ((size_t)w * T + t), ql);
+        if (inA) quad_load(A, inA + 32 * ((size_t)w * T + t), ql);
+    }
+#pragma unroll 1
+    for (uint32_t d = 1; d < 32; d <<= 1) {   // inclusive suffix scan: S_q = sum_{j >= q} S_j
+        quad_store(&shS[quad][0], S, ql);
+        __syncthreads();
+        quad_load(o, &shS[(quad + d) & 31][0], ql);
+        __syncthreads();
+        tmp = S;
+        quad_add(tmp, o, ql);
+        fe_pick(S, tmp, S, quad + d < 32);
+    }
+    fe b = S;   // sum_k k * S_k = sum_{j = 1..31} suffix_j
+    if (quad == 0) quad_identity(b, ql);
+#pragma unroll 1
+    for (uint32_t d = 16; d >= 1; d >>= 1) {
+        quad_store(&shS[quad][0], b, ql);
+        quad_store(&shA[quad][0], A, ql);
+        __syncthreads();
+        quad_load(o, &shS[(quad + d) & 31][0], ql);
+        quad_load(oa, &shA[(quad + d) & 31][0], ql);
+        __syncthreads();
+        tmp = b;
+        quad_add(tmp, o, ql);
+        fe_pick(b, tmp, b, quad < d);
+        tmp = A;
+        quad_add(tmp, oa, ql);
+        fe_pick(A, tmp, A, quad < d);
+    }
+#pragma unroll 1
+    for (uint32_t i = 0; i < loglen; i++) quad_double(b, ql);
+    quad_add(A, b, ql);
+    if (quad == 0) {
+        quad_store(outS + 32 * ((size_t)w * T_out + g), S, ql);
+        quad_store(outA + 32 * ((size_t)w * T_out + g), A, ql);
+    }
 }
 
 // One warp.  Lane w < W adds window w's root node (A + S = window total) and caches it; then the
@@ -499,23 +562,21 @@ __global__ void __launch_bounds__(32) k_msm_finish(const uint32_t *__restrict__ 
         fe_store(&sh[w][24], t2d);
     }
     __syncwarp();
-    // acc = identity in quad form: (0, 1, 1, 0)
     fe v;
-    fe_set0(v);
-    v.v[0] = (lane == 1 || lane == 2) ? 1u : 0u;
+    quad_identity(v, lane & 3);   // the warp's 8 quads all run the same chain; quad 0 is the one that is read
 #pragma unroll 1
     for (int k = W - 1; k >= 0; k--) {
-        quad_add_cached(v, &sh[k][0], lane);
+        quad_add_cached(v, &sh[k][0], lane & 3);
         if (k > 0) {
 #pragma unroll 1
-            for (int i = 0; i < c; i++) quad_double(v, lane);
+            for (int i = 0; i < c; i++) quad_double(v, lane & 3);
         }
     }
     ge_ext acc;
-    fe_shfl(acc.X, v, 0);
-    fe_shfl(acc.Y, v, 1);
-    fe_shfl(acc.Z, v, 2);
-    fe_shfl(acc.T, v, 3);
+    fe_shfl4(acc.X, v, 0);
+    fe_shfl4(acc.Y, v, 1);
+    fe_shfl4(acc.Z, v, 2);
+    fe_shfl4(acc.T, v, 3);
     if (lane == 0) {
         if (do_compress) {
             ge_compress(out, acc);
