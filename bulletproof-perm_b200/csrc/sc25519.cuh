@@ -215,17 +215,77 @@ SC_INLINE void sc_reduce256(sc &r, const sc &a) {
     sc_mont(r, a, k);
 }
 
-// r = a^(l-2) mod l (standard form in and out); 0 -> 0.  Scalar::invert (circuit_lib.rs:273-275).
+// 8-limb helpers for the inversion below (one carry chain each)
+SC_INLINE uint32_t sc_sub8(uint32_t *r, const uint32_t *a, const uint32_t *b) {   // r = a - b, returns the borrow (0/1)
+    uint32_t bw;
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]), "=&r"(bw)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+          "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    return bw & 1u;
+}
+SC_INLINE void sc_add8_masked(uint32_t *r, const uint32_t *a, const uint32_t *b, uint32_t mask) {   // r = a + (b & mask)
+    asm("add.cc.u32 %0, %8, %16;\n\t"
+        "addc.cc.u32 %1, %9, %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32 %7, %15, %23;"
+        : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+          "r"(b[0] & mask), "r"(b[1] & mask), "r"(b[2] & mask), "r"(b[3] & mask), "r"(b[4] & mask), "r"(b[5] & mask),
+          "r"(b[6] & mask), "r"(b[7] & mask));
+}
+
+// r = a^-1 mod l (standard form in and out); 0 -> 0, like dalek's Scalar::invert (circuit_lib.rs:273-275), which
+// raises to l - 2: 253 squarings + 67 multiplications, one dependent chain (~270 us for a lone warp).  Inversion
+// sits on the critical path of every proof (y^-1 before the power chains, u_j^-1 in every inner-product round),
+// so it is done by a branch-free binary extended GCD instead: invariants a*x1 = u, a*x2 = v (mod l), v odd;
+// each step makes u even (subtracting v after a conditional swap) and halves it, x1 following mod l.
+// len(u) + len(v) <= 506 drops by at least one per step, so 508 steps always end with u = 0, v = gcd = 1 and
+// x2 = a^-1 (x2 = 0 for a = 0); ~100 plain integer instructions per step, no multiplications.
 __device__ __noinline__ void sc_invert(sc &r, const sc &a) {
-    // l - 2, little-endian limbs
-    const uint32_t e[8] = {0x5cf5d3ebu, 0x5812631au, 0xa2f79cd6u, 0x14def9deu, 0u, 0u, 0u, 0x10000000u};
-    sc am, acc;
-    sc_to_mont(am, a);
-    sc_const(acc, SC_R);  // 1 in Montgomery form
+    uint32_t u[8], v[8], x1[8], x2[8], t[8], lm[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { u[i] = a.v[i]; v[i] = SC_L[i]; lm[i] = SC_L[i]; x1[i] = 0; x2[i] = 0; }
+    x1[0] = 1;
 #pragma unroll 1
-    for (int bit = 252; bit >= 0; bit--) {
-        sc_mont_noinline(acc, acc, acc);
-        if ((e[bit >> 5] >> (bit & 31)) & 1u) sc_mont_noinline(acc, acc, am);
+    for (int it = 0; it < 508; it++) {
+        const uint32_t odd = 0u - (u[0] & 1u);
+        const uint32_t lt = 0u - sc_sub8(t, u, v);          // u < v
+        const uint32_t sw = odd & lt;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {                       // conditional swap (u, v), (x1, x2)
+            uint32_t d = (u[i] ^ v[i]) & sw;
+            u[i] ^= d; v[i] ^= d;
+            d = (x1[i] ^ x2[i]) & sw;
+            x1[i] ^= d; x2[i] ^= d;
+        }
+        uint32_t vm[8], xm[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) { vm[i] = v[i] & odd; xm[i] = x2[i] & odd; }
+        sc_sub8(u, u, vm);                                  // u >= v here when odd: no borrow; u is even now
+        const uint32_t neg = 0u - sc_sub8(t, x1, xm);       // x1 - x2 (mod l)
+        sc_add8_masked(x1, t, lm, neg);
+#pragma unroll
+        for (int i = 0; i < 7; i++) u[i] = (u[i] >> 1) | (u[i + 1] << 31);
+        u[7] >>= 1;
+        const uint32_t xo = 0u - (x1[0] & 1u);              // x1 / 2 mod l: add l first when odd (< 2^254, no carry out)
+        sc_add8_masked(t, x1, lm, xo);
+#pragma unroll
+        for (int i = 0; i < 7; i++) x1[i] = (t[i] >> 1) | (t[i + 1] << 31);
+        x1[7] = t[7] >> 1;
     }
-    sc_from_mont(r, acc);
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = x2[i];
 }

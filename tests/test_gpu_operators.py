@@ -87,6 +87,20 @@ def test_scalar_powers_exp_invert(ops):
     assert ops.invert_all(xs) == [R.sc_inv(v) for v in xs]   # 0 -> 0 like dalek's x^(l-2)
 
 
+def test_scalar_invert_binary_gcd_worst_cases(ops):
+    """Scalar::invert (circuit_lib.rs:273-275) is a fixed-length binary extended GCD on the device: powers of two,
+    their neighbours and negatives take the most steps (505 of the 508 performed); 0 -> 0 like dalek's x^(l-2)."""
+    import random
+    rnd = random.Random(77)
+    xs = [0, 1, 2, 3, L - 1, L - 2, (L - 1) // 2, (L + 1) // 2]
+    for k in range(1, 253):
+        xs += [pow(2, k, L), (pow(2, k, L) - 1) % L, (L - pow(2, k, L)) % L]
+    xs += [rnd.randrange(L) for _ in range(2000)]
+    got = ops.invert_all(xs)
+    for x, g in zip(xs, got):
+        assert g == (pow(x, L - 2, L)), hex(x)
+
+
 def test_wide_reduce_and_reduce(ops):
     rng = ChaChaRng(b"\x05" * 32)
     blobs = [rng.fill_bytes(64) for _ in range(200)] + [bytes(64), b"\xff" * 64, b"\x00" * 32 + b"\xff" * 32]
