@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(ACP_POW_THREADS) k_acp_pow(acp_layout lay, uin
 #pragma unroll 1
     for (uint32_t i = 0; i < cnt; i++) {
         ret = nxt;
-        sc_mont_noinline(nxt, nxt, base);
+        sc_mont(nxt, nxt, base);
         base = ret;
         sc_store(dst + 8 * (size_t)i, ret);
     }
