@@ -194,7 +194,7 @@ extern "C" int bpp_gens_create(bpp_ctx *ctx, const uint8_t g[32], const uint8_t 
     }
     const size_t half = (size_t)1 << (gs->c - 1);
     const size_t entries = (size_t)gs->n_gens * gs->Wn * half;
-    if (cudaMalloc((void **)&gs->d_table, entries * 96) != cudaSuccess) {
+    if (cudaMalloc((void **)&gs->d_table, entries * FB_ENTRY_U32 * 4) != cudaSuccess) {
         cudaGetLastError();
         cudaFree(gs->d_niels);
         delete gs;

@@ -97,6 +97,10 @@ __global__ void k_acp_put_wide(const uint32_t *__restrict__ wide /* B x per x 16
 }
 
 // ---- fixed-base tables ---------------------------------------------------------------------------
+// u32 per table entry.  Padding the 96-byte entries to 128 bytes (exactly two 64-byte DRAM atoms per gather instead
+// of two or three; ncu shows 2.5 GB read per launch for 1.3 GB of entries) was measured: 3 % SLOWER (1.185 vs
+// 1.155 ms per A_I-shaped launch) - the larger table costs more in L2/TLB reach than the atoms save.
+#define FB_ENTRY_U32 24
 // table[((gen * Wn + w) * half + (j - 1))] = j * 2^(c w) * P_gen as affine Niels (96 B).
 // Thread per (gen, window): 2^(c w) P by doublings, then j = 1..half by repeated addition, each
 // entry normalised with its own inversion (one-time cost at generator upload).
@@ -114,7 +118,7 @@ __global__ void __launch_bounds__(64) k_fb_build(const uint32_t *__restrict__ ge
 #pragma unroll 1
     for (uint32_t i = 0; i < w * (uint32_t)c; i++) ge_double_noinline(base, base);
     run = base;
-    uint32_t *dst = table + 24 * ((size_t)id * half);
+    uint32_t *dst = table + FB_ENTRY_U32 * ((size_t)id * half);
 #pragma unroll 1
     for (uint32_t j = 1; j <= half; j++) {
         fe zi, x, y;
@@ -123,7 +127,7 @@ __global__ void __launch_bounds__(64) k_fb_build(const uint32_t *__restrict__ ge
         fe_mul_noinline(y, run.Y, zi);
         ge_niels e;
         ge_affine_to_niels(e, x, y);
-        ge_niels_store(dst + 24 * (size_t)(j - 1), e);
+        ge_niels_store(dst + FB_ENTRY_U32 * (size_t)(j - 1), e);
         if (j < half) ge_add_noinline(run, run, base);
     }
 }
@@ -205,7 +209,7 @@ __global__ void __launch_bounds__(FB_THREADS) k_fb_msm(const uint32_t *__restric
             int d = (ww + 1 == (uint32_t)Wn) ? (int)u : (int)u - (int)half;
             if (d == 0) continue;
             uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-            ptr = table + 24 * (((size_t)gen * Wn + ww) * half + (mag - 1));
+            ptr = table + FB_ENTRY_U32 * (((size_t)gen * Wn + ww) * half + (mag - 1));
             neg = d < 0;
             return true;
         }
@@ -284,7 +288,7 @@ __global__ void __launch_bounds__(128) k_fb_msm_small(const uint32_t *__restrict
                 if (d == 0) continue;
                 uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
                 ge_niels q;
-                ge_niels_load(q, table + 24 * (((size_t)gen * Wn + w) * half + (mag - 1)));
+                ge_niels_load(q, table + FB_ENTRY_U32 * (((size_t)gen * Wn + w) * half + (mag - 1)));
                 ge_madd(acc, acc, q, d < 0);
             }
         }
