@@ -119,6 +119,10 @@ class Backend:
     def set_window_bits(self, c: int):
         self._check(self._lib.bpp_set_window_bits(self._ctx, c))
 
+    def set_msm_groups(self, groups: int):
+        """Window groups of the pipelined MSM (0 = automatic, 1 = in order on one stream)."""
+        self._check(self._lib.bpp_set_msm_groups(self._ctx, groups))
+
     def set_profiling(self, on: bool):
         self._check(self._lib.bpp_set_profiling(self._ctx, int(on)))
 

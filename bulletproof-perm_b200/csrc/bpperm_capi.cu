@@ -10,6 +10,9 @@
 #include "../../include/bpperm.h"
 #include "msm_kernels.cuh"
 
+#define BPP_MAX_GROUPS 8
+#define BPP_PIPELINE_MIN_POINTS (1u << 18)
+
 struct bpp_points {
     uint32_t *niels = nullptr;  // n x 24 u32 (96 B)
     size_t n = 0;
@@ -44,6 +47,12 @@ struct bpp_ctx {
     uint32_t *d_flag = nullptr;
     uint8_t *h_pinned = nullptr; size_t cap_pinned = 0;         // pinned staging for host scalars
     uint8_t *d_vec = nullptr; size_t cap_vec = 0;               // arena of the scalar-vector operators
+    // pipelined MSM: window groups on side streams (msm_pipeline_init)
+    bool pipe_ready = false;
+    int forced_groups = 0;
+    cudaStream_t s_sort = nullptr, s_tail[BPP_MAX_GROUPS] = {};
+    cudaEvent_t ev_fork = nullptr, ev_sorted[BPP_MAX_GROUPS] = {}, ev_acc[BPP_MAX_GROUPS] = {}, ev_tail[BPP_MAX_GROUPS] = {};
+    uint8_t *d_gparts = nullptr;                                // BPP_MAX_GROUPS x 128 B
 };
 
 #define CK(ctx, call)                                                                              \
@@ -139,6 +148,17 @@ extern "C" void bpp_free(bpp_ctx *ctx) {
     for (int i = 0; i <= BPP_PHASE_COUNT; i++)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->pipe_ready) {
+        cudaStreamDestroy(ctx->s_sort);
+        cudaEventDestroy(ctx->ev_fork);
+        for (int g = 0; g < BPP_MAX_GROUPS; g++) {
+            cudaStreamDestroy(ctx->s_tail[g]);
+            cudaEventDestroy(ctx->ev_sorted[g]);
+            cudaEventDestroy(ctx->ev_acc[g]);
+            cudaEventDestroy(ctx->ev_tail[g]);
+        }
+        cudaFree(ctx->d_gparts);
+    }
     delete ctx;
 }
 
@@ -177,6 +197,12 @@ extern "C" int bpp_set_window_bits(bpp_ctx *ctx, int c) {
     ctx->forced_c = c;
     return BPP_OK;
 }
+extern "C" int bpp_set_msm_groups(bpp_ctx *ctx, int groups) {
+    if (!ctx || groups < 0 || groups > BPP_MAX_GROUPS) return BPP_ERR_INVALID_ARG;
+    ctx->forced_groups = groups;
+    return BPP_OK;
+}
+
 extern "C" int bpp_set_profiling(bpp_ctx *ctx, int on) {
     if (!ctx) return BPP_ERR_INVALID_ARG;
     ctx->profiling = on != 0;
@@ -329,6 +355,35 @@ static int pick_window(size_t n) {
     return 16;
 }
 
+// Side streams and events of the pipelined MSM, created on first use.
+static int msm_pipeline_init(bpp_ctx *ctx) {
+    if (ctx->pipe_ready) return BPP_OK;
+    int lo = 0, hi = 0;
+    CK(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));  // hi = numerically lowest = most urgent
+    CK(ctx, cudaStreamCreateWithPriority(&ctx->s_sort, cudaStreamNonBlocking, hi));
+    for (int g = 0; g < BPP_MAX_GROUPS; g++) {
+        CK(ctx, cudaStreamCreateWithPriority(&ctx->s_tail[g], cudaStreamNonBlocking, hi));
+        CK(ctx, cudaEventCreateWithFlags(&ctx->ev_sorted[g], cudaEventDisableTiming));
+        CK(ctx, cudaEventCreateWithFlags(&ctx->ev_acc[g], cudaEventDisableTiming));
+        CK(ctx, cudaEventCreateWithFlags(&ctx->ev_tail[g], cudaEventDisableTiming));
+    }
+    CK(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    CK(ctx, cudaMalloc((void **)&ctx->d_gparts, 128 * BPP_MAX_GROUPS));
+    ctx->pipe_ready = true;
+    return BPP_OK;
+}
+
+// Number of window groups for an n-point MSM (1 = everything in order on the caller's stream).  Measured on
+// B200 (tools/msm_groups.py): the pipeline pays once the accumulate of one group is long enough to hide the
+// dependent tail (fix-up, node merges, Horner) of the previous one.
+static int pick_groups(const bpp_ctx *ctx, size_t n, int W) {
+    int G = ctx->forced_groups ? ctx->forced_groups : (n >= BPP_PIPELINE_MIN_POINTS ? 4 : 1);
+    if (G > W) G = W;
+    if (G > BPP_MAX_GROUPS) G = BPP_MAX_GROUPS;
+    if (ctx->profiling) G = 1;  // the per-phase events describe the in-order pipeline
+    return G < 1 ? 1 : G;
+}
+
 static int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points *pts, size_t off, size_t n,
                        uint8_t *d_out, int do_compress) {
     const int c = ctx->forced_c ? ctx->forced_c : pick_window(n);
@@ -341,8 +396,7 @@ static int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points
     struct level { int kind; uint32_t L, T_in, T_out, loglen; };   // kind 0 thread-serial, 1 quad-serial, 2 quad block merge
     level plan[10];
     int n_levels = 0;
-    uint32_t T = B, loglen = 0;
-    size_t node_elems = 0;  // u32 elements of node storage (S and A each), ping-pong halves
+    uint32_t T = B, loglen = 0, max_T_out = 0;
     while (T > 1) {
         level lv;
         if (n_levels == 0 && T >= 64) { lv.kind = 0; lv.L = 8; lv.T_out = T / 8; }
@@ -351,11 +405,16 @@ static int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points
         lv.T_in = T;
         lv.loglen = loglen;
         plan[n_levels++] = lv;
-        if ((size_t)W * lv.T_out * 32 > node_elems) node_elems = (size_t)W * lv.T_out * 32;
+        if (lv.T_out > max_T_out) max_T_out = lv.T_out;
         T = lv.T_out;
         loglen += lv.kind == 2 ? 5 : 3;
     }
+    // node storage (S and A each): two ping-pong halves; inside a half every window owns max_T_out nodes, so the
+    // window groups of the pipelined form (each at its own level at any moment) never share storage
+    const size_t node_elems = (size_t)W * max_T_out * 32;
+    const int G = pick_groups(ctx, n, W);
     int rc;
+    if (G > 1 && (rc = msm_pipeline_init(ctx))) return rc;
     if ((rc = grow(ctx, &ctx->d_counts, &ctx->cap_wb, WB))) return rc;
     if ((rc = grow(ctx, &ctx->d_offsets, &ctx->cap_offsets, WB))) return rc;
     if ((rc = grow(ctx, &ctx->d_cursor, &ctx->cap_cursor, WB))) return rc;
@@ -363,8 +422,7 @@ static int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points
     const uint32_t tpw = (uint32_t)((n + BPP_TILE - 1) / BPP_TILE);
     const size_t total_tiles = (size_t)W * tpw;
     if ((rc = grow(ctx, &ctx->d_partials, &ctx->cap_partials, total_tiles * 2 * 32))) return rc;
-    if ((rc = grow(ctx, &ctx->d_long, &ctx->cap_long, total_tiles / BPP_LONG_SPAN + 16))) return rc;
-    uint32_t *d_nlong = ctx->d_flag + 8;
+    if ((rc = grow(ctx, &ctx->d_long, &ctx->cap_long, total_tiles / BPP_LONG_SPAN + 16 * (BPP_MAX_GROUPS + 1)))) return rc;
     if ((rc = grow(ctx, &ctx->d_buckets, &ctx->cap_buckets, WB * 32))) return rc;
     if (node_elems) {
         size_t need = 2 * node_elems;  // two ping-pong buffers in each of segS / segR
@@ -380,63 +438,105 @@ static int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points
     }
 
     cudaStream_t s = ctx->stream;
-    const bool prof = ctx->profiling;
+    const bool prof = ctx->profiling && G == 1;
     const uint32_t *niels = pts->niels + 24 * off;
+    const unsigned sb = (unsigned)((n + 255) / 256);
+    uint64_t red_add = 0, red_dbl = 0;
     if (prof) cudaEventRecord(ctx->ev[0], s);
     CK(ctx, cudaMemsetAsync(ctx->d_counts, 0, WB * 4, s));
-    CK(ctx, cudaMemsetAsync(d_nlong, 0, 4, s));
-    unsigned sb = (unsigned)((n + 255) / 256);
-    k_digit_hist<<<sb, 256, 0, s>>>(d_scalars, (uint32_t)n, c, W, ctx->d_counts);
-    LAUNCH_CHECK(ctx);
-    if (prof) cudaEventRecord(ctx->ev[1], s);
-    k_window_scan<<<W, 1024, 0, s>>>(ctx->d_counts, B, ctx->d_offsets, ctx->d_cursor);
-    LAUNCH_CHECK(ctx);
-    if (prof) cudaEventRecord(ctx->ev[2], s);
-    k_digit_scatter<<<sb, 256, 0, s>>>(d_scalars, (uint32_t)n, c, W, ctx->d_cursor, ctx->d_entries);
-    LAUNCH_CHECK(ctx);
-    if (prof) cudaEventRecord(ctx->ev[3], s);
-    k_bucket_accum<<<(unsigned)((total_tiles + BPP_ACC_THREADS - 1) / BPP_ACC_THREADS), BPP_ACC_THREADS, 0, s>>>(
-        niels, ctx->d_entries, ctx->d_offsets, ctx->d_cursor, (uint32_t)n, B, tpw, (uint32_t)total_tiles,
-        ctx->d_buckets, ctx->d_partials);
-    LAUNCH_CHECK(ctx);
-    if (prof) cudaEventRecord(ctx->ev[4], s);
-    k_bucket_fixup<<<(unsigned)((WB + 127) / 128), 128, 0, s>>>(ctx->d_offsets, ctx->d_cursor, B, tpw, (uint32_t)WB,
-                                                               ctx->d_partials, ctx->d_buckets, ctx->d_long, d_nlong);
-    LAUNCH_CHECK(ctx);
-    k_bucket_fixup_long<<<ctx->sm_count * 2, 128, 0, s>>>(ctx->d_offsets, ctx->d_cursor, B, tpw, ctx->d_partials,
-                                                         ctx->d_buckets, ctx->d_long, d_nlong);
-    LAUNCH_CHECK(ctx);
-    const uint32_t *curS = ctx->d_buckets, *curA = nullptr;
-    uint64_t red_add = 0, red_dbl = 0;
-    for (int i = 0; i < n_levels; i++) {
-        const level &lv = plan[i];
-        uint32_t *oS = ctx->d_segS + (i & 1) * node_elems, *oA = ctx->d_segR + (i & 1) * node_elems;
-        const uint32_t n_out = (uint32_t)W * lv.T_out;
-        if (lv.kind == 0) {
-            k_node_merge_serial<<<(n_out + 127) / 128, 128, 0, s>>>(curS, curA, lv.L, lv.loglen, n_out, oS, oA);
-            red_add += (uint64_t)n_out * (2 * lv.L - 3 + (curA ? lv.L : 0));
-            red_dbl += (uint64_t)n_out * lv.loglen;
-        } else if (lv.kind == 1) {
-            k_node_merge_quad_serial<<<(4 * n_out + 127) / 128, 128, 0, s>>>(curS, curA, lv.L, lv.loglen, n_out, oS, oA);
-            red_add += (uint64_t)n_out * (3 * lv.L - 3);
-            red_dbl += (uint64_t)n_out * lv.loglen;
-        } else {
-            k_node_merge_quad_block<<<dim3(lv.T_out, W), 128, 0, s>>>(curS, curA, lv.T_in, lv.loglen, lv.T_out, oS, oA);
-            red_add += (uint64_t)W * lv.T_out * (2 * (uint64_t)lv.T_in / lv.T_out + 1);  // useful additions
-            red_dbl += (uint64_t)W * lv.T_out * lv.loglen;
-        }
-        LAUNCH_CHECK(ctx);
-        curS = oS;
-        curA = oA;
+    CK(ctx, cudaMemsetAsync(ctx->d_flag + 8, 0, 4 * BPP_MAX_GROUPS, s));
+    if (G > 1) {
+        CK(ctx, cudaEventRecord(ctx->ev_fork, s));
+        CK(ctx, cudaStreamWaitEvent(ctx->s_sort, ctx->ev_fork, 0));
     }
-    if (prof) cudaEventRecord(ctx->ev[5], s);
-    k_msm_finish<<<1, 32, 0, s>>>(curS, curA, c, W, do_compress, d_out);
-    LAUNCH_CHECK(ctx);
+    // Window groups from the top down: the top group's partial needs the most doublings to reach its weight, and
+    // they run beside the accumulate of the groups below.  With G == 1 every stream below is the caller's.
+    int w_hi = W;
+    for (int g = 0; g < G; g++) {
+        const int Wg = (W - (W / G) * G > g) ? W / G + 1 : W / G;
+        const int w0 = w_hi - Wg;
+        w_hi = w0;
+        cudaStream_t s_sort = G > 1 ? ctx->s_sort : s, s_tail = G > 1 ? ctx->s_tail[g] : s;
+        uint32_t *counts = ctx->d_counts + (size_t)w0 * B, *offsets = ctx->d_offsets + (size_t)w0 * B;
+        uint32_t *ends = ctx->d_cursor + (size_t)w0 * B, *entries = ctx->d_entries + (size_t)w0 * n;
+        uint32_t *buckets = ctx->d_buckets + (size_t)w0 * B * 32, *partials = ctx->d_partials + (size_t)w0 * tpw * 64;
+        uint32_t *long_list = ctx->d_long + ((size_t)w0 * tpw) / BPP_LONG_SPAN + 16 * g, *d_nlong = ctx->d_flag + 8 + g;
+        const uint32_t group_tiles = (uint32_t)Wg * tpw, group_buckets = (uint32_t)Wg * B;
+        // sort: recode + histogram, scan, counting-sort scatter (absolute window numbers: the recoding carry
+        // ripples up from window 0)
+        k_digit_hist<<<sb, 256, 0, s_sort>>>(d_scalars, (uint32_t)n, c, w0, w0 + Wg, ctx->d_counts);
+        LAUNCH_CHECK(ctx);
+        if (prof) cudaEventRecord(ctx->ev[1], s);
+        k_window_scan<<<Wg, 1024, 0, s_sort>>>(counts, B, offsets, ends);
+        LAUNCH_CHECK(ctx);
+        if (prof) cudaEventRecord(ctx->ev[2], s);
+        k_digit_scatter<<<sb, 256, 0, s_sort>>>(d_scalars, (uint32_t)n, c, w0, w0 + Wg, ctx->d_cursor, ctx->d_entries);
+        LAUNCH_CHECK(ctx);
+        if (prof) cudaEventRecord(ctx->ev[3], s);
+        if (G > 1) {
+            CK(ctx, cudaEventRecord(ctx->ev_sorted[g], s_sort));
+            CK(ctx, cudaStreamWaitEvent(s, ctx->ev_sorted[g], 0));
+        }
+        // accumulate: on the caller's stream, group after group - the work that fills the GPU
+        k_bucket_accum<<<(group_tiles + BPP_ACC_THREADS - 1) / BPP_ACC_THREADS, BPP_ACC_THREADS, 0, s>>>(
+            niels, entries, offsets, ends, (uint32_t)n, B, tpw, group_tiles, buckets, partials);
+        LAUNCH_CHECK(ctx);
+        if (prof) cudaEventRecord(ctx->ev[4], s);
+        if (G > 1) {
+            CK(ctx, cudaEventRecord(ctx->ev_acc[g], s));
+            CK(ctx, cudaStreamWaitEvent(s_tail, ctx->ev_acc[g], 0));
+        }
+        // tail: dependent chains on a high-priority stream of their own
+        k_bucket_fixup<<<(group_buckets + 127) / 128, 128, 0, s_tail>>>(offsets, ends, B, tpw, group_buckets, partials,
+                                                                       buckets, long_list, d_nlong);
+        LAUNCH_CHECK(ctx);
+        k_bucket_fixup_long<<<ctx->sm_count * 2, 128, 0, s_tail>>>(offsets, ends, B, tpw, partials, buckets, long_list,
+                                                                  d_nlong);
+        LAUNCH_CHECK(ctx);
+        const uint32_t *curS = buckets, *curA = nullptr;
+        for (int i = 0; i < n_levels; i++) {
+            const level &lv = plan[i];
+            uint32_t *oS = ctx->d_segS + (i & 1) * node_elems + (size_t)w0 * max_T_out * 32;
+            uint32_t *oA = ctx->d_segR + (i & 1) * node_elems + (size_t)w0 * max_T_out * 32;
+            const uint32_t n_out = (uint32_t)Wg * lv.T_out;
+            if (lv.kind == 0) {
+                k_node_merge_serial<<<(n_out + 127) / 128, 128, 0, s_tail>>>(curS, curA, lv.L, lv.loglen, n_out, oS, oA);
+                red_add += (uint64_t)n_out * (2 * lv.L - 3 + (curA ? lv.L : 0));
+                red_dbl += (uint64_t)n_out * lv.loglen;
+            } else if (lv.kind == 1) {
+                k_node_merge_quad_serial<<<(4 * n_out + 127) / 128, 128, 0, s_tail>>>(curS, curA, lv.L, lv.loglen, n_out, oS, oA);
+                red_add += (uint64_t)n_out * (3 * lv.L - 3);
+                red_dbl += (uint64_t)n_out * lv.loglen;
+            } else {
+                k_node_merge_quad_block<<<dim3(lv.T_out, Wg), 128, 0, s_tail>>>(curS, curA, lv.T_in, lv.loglen, lv.T_out, oS, oA);
+                red_add += (uint64_t)Wg * lv.T_out * (2 * (uint64_t)lv.T_in / lv.T_out + 1);  // useful additions
+                red_dbl += (uint64_t)Wg * lv.T_out * lv.loglen;
+            }
+            LAUNCH_CHECK(ctx);
+            curS = oS;
+            curA = oA;
+        }
+        if (prof) cudaEventRecord(ctx->ev[5], s);
+        if (G == 1) {
+            k_msm_finish<<<1, 32, 0, s>>>(curS, curA, c, W, 0, do_compress, d_out);
+            LAUNCH_CHECK(ctx);
+        } else {
+            // Horner inside the group, then c*w0 doublings to the group's weight; raw point to d_gparts[g]
+            k_msm_finish<<<1, 32, 0, s_tail>>>(curS, curA, c, Wg, c * w0, 0, ctx->d_gparts + 128 * g);
+            LAUNCH_CHECK(ctx);
+            CK(ctx, cudaEventRecord(ctx->ev_tail[g], s_tail));
+        }
+    }
+    if (G > 1) {
+        for (int g = 0; g < G; g++) CK(ctx, cudaStreamWaitEvent(s, ctx->ev_tail[g], 0));
+        k_points_sum_finish<<<1, 32, 0, s>>>((const uint32_t *)ctx->d_gparts, (uint32_t)G, do_compress, d_out);
+        LAUNCH_CHECK(ctx);
+    }
     if (prof) { cudaEventRecord(ctx->ev[6], s); ctx->events_pending = true; }
     ctx->n_madd = (uint64_t)W * n;
     ctx->n_add = (uint64_t)W * (B < tpw ? B : tpw) /* fix-up of buckets cut by tile boundaries (upper bound) */ +
-                 red_add + 2 * (uint64_t)W;
-    ctx->n_dbl = (uint64_t)c * (W - 1) + red_dbl;
+                 red_add + 2 * (uint64_t)W + (G > 1 ? G - 1 : 0);
+    ctx->n_dbl = (uint64_t)c * (W - 1) + red_dbl;  // the useful Horner doublings (the grouped form spends more, off the critical path)
     return BPP_OK;
 }
 

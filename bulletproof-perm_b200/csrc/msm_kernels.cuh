@@ -31,7 +31,9 @@ FE_INLINE uint32_t sc_window(const uint32_t s[8], int bit, int c) {
     return (uint32_t)(v >> sh) & ((1u << c) - 1u);
 }
 
-__global__ void k_digit_hist(const uint32_t *__restrict__ scalars, uint32_t n, int c, int W,
+// Windows [w_begin, w_end) are counted (a window group of the pipelined MSM); the recoding carry is
+// still rippled up from window 0.
+__global__ void k_digit_hist(const uint32_t *__restrict__ scalars, uint32_t n, int c, int w_begin, int w_end,
                              uint32_t *__restrict__ counts) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -41,11 +43,11 @@ __global__ void k_digit_hist(const uint32_t *__restrict__ scalars, uint32_t n, i
     s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w; s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
     const uint32_t half = 1u << (c - 1);
     uint32_t carry = 0;
-    for (int w = 0; w < W; w++) {
+    for (int w = 0; w < w_end; w++) {
         uint32_t raw = sc_window(s, w * c, c) + carry;
         carry = raw > half ? 1u : 0u;
         uint32_t mag = carry ? (1u << c) - raw : raw;
-        if (mag) atomicAdd(&counts[(size_t)w * half + (mag - 1)], 1u);
+        if (mag && w >= w_begin) atomicAdd(&counts[(size_t)w * half + (mag - 1)], 1u);
     }
 }
 
@@ -116,7 +118,7 @@ __global__ void __launch_bounds__(1024) k_window_scan(const uint32_t *__restrict
     }
 }
 
-__global__ void k_digit_scatter(const uint32_t *__restrict__ scalars, uint32_t n, int c, int W,
+__global__ void k_digit_scatter(const uint32_t *__restrict__ scalars, uint32_t n, int c, int w_begin, int w_end,
                                 uint32_t *__restrict__ cursor, uint32_t *__restrict__ entries) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -126,11 +128,11 @@ __global__ void k_digit_scatter(const uint32_t *__restrict__ scalars, uint32_t n
     s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w; s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
     const uint32_t half = 1u << (c - 1);
     uint32_t carry = 0;
-    for (int w = 0; w < W; w++) {
+    for (int w = 0; w < w_end; w++) {
         uint32_t raw = sc_window(s, w * c, c) + carry;
         carry = raw > half ? 1u : 0u;
         uint32_t mag = carry ? (1u << c) - raw : raw;
-        if (mag) {
+        if (mag && w >= w_begin) {
             uint32_t pos = atomicAdd(&cursor[(size_t)w * half + (mag - 1)], 1u);
             entries[(size_t)w * n + pos] = i | (carry << 31);
         }
@@ -539,8 +541,9 @@ __global__ void __launch_bounds__(128) k_node_merge_quad_block(const uint32_t *_
 // warp runs Horner over the windows in quad form (c doublings + 1 addition per window) and lane 0
 // compresses.  With `do_compress` the 32-byte encoding goes to out[0..32) and the raw extended
 // point to out[32..160); otherwise the raw extended point goes to out[0..128).
+// `shift` extra doublings at the end place a window group at its weight 2^shift (pipelined MSM).
 __global__ void __launch_bounds__(32) k_msm_finish(const uint32_t *__restrict__ inS,
-                                                   const uint32_t *__restrict__ inA, int c, int W,
+                                                   const uint32_t *__restrict__ inA, int c, int W, int shift,
                                                    int do_compress, uint8_t *__restrict__ out) {
     __shared__ __align__(16) uint32_t sh[64][32];
     const uint32_t lane = threadIdx.x;
@@ -572,6 +575,8 @@ __global__ void __launch_bounds__(32) k_msm_finish(const uint32_t *__restrict__ 
             for (int i = 0; i < c; i++) quad_double(v, lane & 3);
         }
     }
+#pragma unroll 1
+    for (int i = 0; i < shift; i++) quad_double(v, lane & 3);
     ge_ext acc;
     fe_shfl4(acc.X, v, 0);
     fe_shfl4(acc.Y, v, 1);
@@ -599,6 +604,25 @@ __global__ void __launch_bounds__(32) k_points_sum_compress(const uint32_t *__re
         ge_add(acc, acc, t);
     }
     ge_compress(out32, acc);
+}
+
+// sum of g window-group partials, written like k_msm_finish does (encoding + raw point, or raw point only)
+__global__ void __launch_bounds__(32) k_points_sum_finish(const uint32_t *__restrict__ parts, uint32_t g,
+                                                          int do_compress, uint8_t *__restrict__ out) {
+    if (threadIdx.x != 0) return;
+    ge_ext acc, t;
+    ge_load(acc, parts);
+#pragma unroll 1
+    for (uint32_t i = 1; i < g; i++) {
+        ge_load(t, parts + 32 * (size_t)i);
+        ge_add(acc, acc, t);
+    }
+    if (do_compress) {
+        ge_compress(out, acc);
+        ge_store(reinterpret_cast<uint32_t *>(out + 32), acc);
+    } else {
+        ge_store(reinterpret_cast<uint32_t *>(out), acc);
+    }
 }
 
 // ---- point ingestion ----------------------------------------------------------------------------

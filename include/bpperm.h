@@ -101,6 +101,12 @@ int bpp_msm_partial_dev(bpp_ctx *ctx, const void *d_scalars, const bpp_points *p
 int bpp_points_sum_compress_dev(bpp_ctx *ctx, const void *d_partials, size_t g, void *d_out32);
 /* Override the Pippenger window width (0 = automatic). */
 int bpp_set_window_bits(bpp_ctx *ctx, int c);
+/* Override the number of window groups of the pipelined MSM (0 = automatic, 1 = everything in order on the
+ * caller's stream, up to 8).  With more than one group the windows are processed group by group from the top:
+ * the sort of the next group and the dependent tail of the previous one (fix-up, bucket reduction, Horner, the
+ * doublings to the group's weight) run on internal high-priority streams beside the accumulate of the current
+ * group; the call still is stream-ordered on the caller's stream.  The result bytes do not depend on it. */
+int bpp_set_msm_groups(bpp_ctx *ctx, int groups);
 
 /* ---- scalar-vector operators mod l: the reference's util.rs / poly.rs -------------------------------
  * All vectors are arrays of 32-byte little-endian canonical scalars in host memory.  Where the Rust

@@ -171,3 +171,34 @@ def test_sweep_inputs_match_oracle(backend, log_n):
     got = backend.vartime_multiscalar_mul(sc.tobytes(), table)
     table.free()
     assert got == cref.msm(sc.tobytes(), cref.from_uniform(blobs.tobytes()))
+
+
+@pytest.mark.parametrize("groups,c", [(2, 16), (3, 11), (4, 16), (5, 13), (8, 8), (8, 16), (4, 0)])
+def test_window_groups_match_oracle(backend, groups, c):
+    """The pipelined form (window groups on side streams, bpp_set_msm_groups) against the C restatement: 2^14 random
+    terms plus a skewed tail (repeated and tiny scalars: hot buckets and the long-bucket queue inside every group,
+    zero scalars: empty windows).  The bytes must not depend on the grouping or on the window width."""
+    import numpy as np
+    from oracle import cref
+    n = (1 << 14) + 3000
+    rs = np.random.RandomState(900 + groups)
+    blobs = rs.randint(0, 256, size=(n, 64), dtype=np.uint8)
+    sc = rs.randint(0, 256, size=(n, 32), dtype=np.uint8)
+    sc[:, 31] &= 0x0F
+    sc[1 << 14:(1 << 14) + 2000] = sc[7]          # one scalar 2000 times: every window has a hot bucket
+    sc[(1 << 14) + 2000:(1 << 14) + 2500, 1:] = 0  # tiny scalars: only window 0 is populated
+    sc[(1 << 14) + 2500:] = 0                      # zero scalars
+    table = backend.points_from_uniform(blobs.tobytes())
+    backend.set_window_bits(c)
+    backend.set_msm_groups(groups)
+    try:
+        got = backend.vartime_multiscalar_mul(sc.tobytes(), table)
+        again = backend.vartime_multiscalar_mul(sc.tobytes(), table)   # scratch reuse across calls
+        backend.set_msm_groups(1)
+        in_order = backend.vartime_multiscalar_mul(sc.tobytes(), table)
+    finally:
+        backend.set_window_bits(0)
+        backend.set_msm_groups(0)
+        table.free()
+    assert got == again == in_order
+    assert got == cref.msm(sc.tobytes(), cref.from_uniform(blobs.tobytes()))
