@@ -123,6 +123,20 @@ class Backend:
         """Window groups of the pipelined MSM (0 = automatic, 1 = in order on one stream)."""
         self._check(self._lib.bpp_set_msm_groups(self._ctx, groups))
 
+    def set_msm_partition(self, sizes):
+        """Explicit window-group sizes, top group first (empty = clear)."""
+        arr = (ctypes.c_int * max(1, len(sizes)))(*sizes)
+        self._check(self._lib.bpp_set_msm_partition(self._ctx, arr, len(sizes)))
+
+    def set_msm_trace(self, on: bool):
+        self._check(self._lib.bpp_set_msm_trace(self._ctx, int(on)))
+
+    def msm_trace(self) -> str:
+        """Stage timeline of the last MSM (see bpp_msm_trace_dump)."""
+        buf = ctypes.create_string_buffer(1 << 16)
+        self._check(self._lib.bpp_msm_trace_dump(self._ctx, buf, len(buf)))
+        return buf.value.decode()
+
     def set_profiling(self, on: bool):
         self._check(self._lib.bpp_set_profiling(self._ctx, int(on)))
 
@@ -193,6 +207,14 @@ class Backend:
     def msm_dev(self, d_scalars: int, points: Points, off: int, n: int, d_out: int):
         self._check(self._lib.bpp_msm_vartime_dev(self._ctx, ctypes.c_void_p(d_scalars), points._h, off, n,
                                                   ctypes.c_void_p(d_out)))
+
+    def msm_submit_dev(self, d_scalars: int, points: Points, off: int, n: int, d_out: int):
+        """Throughput form: enqueue without making the caller's stream wait; the result is valid after msm_wait()."""
+        self._check(self._lib.bpp_msm_submit_dev(self._ctx, ctypes.c_void_p(d_scalars), points._h, off, n,
+                                                 ctypes.c_void_p(d_out)))
+
+    def msm_wait(self):
+        self._check(self._lib.bpp_msm_wait(self._ctx))
 
     def msm_partial_dev(self, d_scalars: int, points: Points, off: int, n: int, d_partial: int):
         self._check(self._lib.bpp_msm_partial_dev(self._ctx, ctypes.c_void_p(d_scalars), points._h, off, n,

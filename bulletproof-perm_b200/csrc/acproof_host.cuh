@@ -701,7 +701,7 @@ extern "C" int bpp_acp_batch_upload_proofs(bpp_acp_batch *b, const uint8_t *proo
 }
 
 static int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points *pts, size_t off, size_t n, uint8_t *d_out,
-                       int do_compress);
+                       int do_compress, bool join);
 
 // One MSM over the batch (see k_rlc_weights).  *decided = true when every proof's accept byte is final.
 static int acp_verify_rlc(bpp_acp_batch *b, uint32_t per, int check_t, bool *decided) {
@@ -720,7 +720,7 @@ static int acp_verify_rlc(bpp_acp_batch *b, uint32_t per, int check_t, bool *dec
     bpp_points view;
     view.niels = b->d_dyn;
     view.n = N;
-    int rc = msm_enqueue(ctx, b->d_rlc_sc, &view, 0, N, b->d_rlc_out, 1);
+    int rc = msm_enqueue(ctx, b->d_rlc_sc, &view, 0, N, b->d_rlc_out, 1, true);
     view.niels = nullptr;
     if (rc) return rc;
     k_rlc_accept<<<(B + 127) / 128, 128, 0, s>>>(b->d_rlc_out, L, B, L.rho, b->d_blk, b->d_accept, b->d_rlc_flag);

@@ -33,14 +33,22 @@ struct bpp_ctx {
     uint64_t n_madd = 0, n_add = 0, n_dbl = 0;
     // scratch (grown on demand)
     uint32_t *d_scalars = nullptr; size_t cap_scalars = 0;       // n x 8
-    uint32_t *d_counts = nullptr, *d_offsets = nullptr, *d_cursor = nullptr;  // W x B each
-    size_t cap_wb = 0, cap_offsets = 0, cap_cursor = 0;
-    uint32_t *d_entries = nullptr; size_t cap_entries = 0;      // W x n
-    uint32_t *d_partials = nullptr; size_t cap_partials = 0;    // 2 x tiles x 32
-    uint32_t *d_long = nullptr; size_t cap_long = 0;            // hot-bucket queue (+ counter at [0] of d_flag+1)
-    uint32_t *d_buckets = nullptr; size_t cap_buckets = 0;      // W x B x 32
-    uint32_t *d_segS = nullptr, *d_segR = nullptr; size_t cap_seg = 0;
-    uint32_t *d_blk = nullptr; size_t cap_blk = 0;              // 3 x W x nb x 32
+    // MSM scratch: two slots, so that a submitted MSM (bpp_msm_submit_dev) can still be in its tail while the
+    // next one sorts and accumulates
+    struct msm_scratch {
+        uint32_t *d_counts = nullptr, *d_offsets = nullptr, *d_cursor = nullptr;  // W x B each
+        size_t cap_wb = 0, cap_offsets = 0, cap_cursor = 0;
+        uint32_t *d_entries = nullptr; size_t cap_entries = 0;      // W x n
+        uint32_t *d_partials = nullptr; size_t cap_partials = 0;    // 2 x tiles x 32
+        uint32_t *d_long = nullptr; size_t cap_long = 0;            // hot-bucket queues (one region per window group)
+        uint32_t *d_nlong = nullptr;                                // their counters
+        uint32_t *d_buckets = nullptr; size_t cap_buckets = 0;      // W x B x 32
+        uint32_t *d_segS = nullptr, *d_segR = nullptr; size_t cap_seg = 0;
+        uint8_t *d_gparts = nullptr;                                // BPP_MAX_GROUPS x 128 B: window-group partials
+        cudaEvent_t ev_done = nullptr;                              // recorded when the slot's MSM has written its result
+        bool pending = false;                                       // the caller's stream has not waited for ev_done yet
+    } scr[2];
+    int slot = 0;
     uint8_t *d_out = nullptr;                                   // 160 B
     uint8_t *h_out = nullptr;                                   // pinned 160 B
     uint8_t *d_stage = nullptr; size_t cap_stage = 0;           // upload staging
@@ -50,10 +58,22 @@ struct bpp_ctx {
     // pipelined MSM: window groups on side streams (msm_pipeline_init)
     bool pipe_ready = false;
     int forced_groups = 0;
-    cudaStream_t s_sort = nullptr, s_tail[BPP_MAX_GROUPS] = {};
+    int forced_part[BPP_MAX_GROUPS] = {}, n_forced_part = 0;    // explicit group sizes, top window group first
+    cudaStream_t s_sort = nullptr, s_bulk[2] = {}, s_tail[BPP_MAX_GROUPS] = {};
     cudaEvent_t ev_fork = nullptr, ev_sorted[BPP_MAX_GROUPS] = {}, ev_acc[BPP_MAX_GROUPS] = {}, ev_tail[BPP_MAX_GROUPS] = {};
-    uint8_t *d_gparts = nullptr;                                // BPP_MAX_GROUPS x 128 B
+    cudaStream_t s_final = nullptr;
+    // stage timeline of the last MSM (bpp_set_msm_trace): timing events on whichever stream ran the stage
+    bool trace = false;
+    std::vector<std::pair<std::string, cudaEvent_t>> trace_ev;
 };
+
+static void trace_mark(bpp_ctx *ctx, cudaStream_t s, const char *what, int g) {
+    if (!ctx->trace) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, s);
+    ctx->trace_ev.emplace_back(std::string(what) + "[" + std::to_string(g) + "]", e);
+}
 
 #define CK(ctx, call)                                                                              \
     do {                                                                                           \
@@ -85,6 +105,8 @@ static int grow(bpp_ctx *ctx, T **p, size_t *cap, size_t need_elems) {
     *cap = want;
     return BPP_OK;
 }
+
+static int msm_wait_pending(bpp_ctx *ctx);
 
 extern "C" const char *bpp_strerror(int s) {
     switch (s) {
@@ -138,11 +160,16 @@ extern "C" void bpp_free(bpp_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    void *ptrs[] = {ctx->d_scalars, ctx->d_counts, ctx->d_offsets, ctx->d_cursor, ctx->d_entries, ctx->d_buckets,
-                    ctx->d_segS, ctx->d_segR, ctx->d_blk, ctx->d_out, ctx->d_stage, ctx->d_flag,
-                    ctx->d_partials, ctx->d_long, ctx->d_vec};
+    void *ptrs[] = {ctx->d_scalars, ctx->d_out, ctx->d_stage, ctx->d_flag, ctx->d_vec};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    for (auto &sc : ctx->scr) {
+        void *sp[] = {sc.d_counts, sc.d_offsets, sc.d_cursor, sc.d_entries, sc.d_partials, sc.d_long, sc.d_nlong,
+                      sc.d_buckets, sc.d_segS, sc.d_segR, sc.d_gparts};
+        for (void *p : sp)
+            if (p) cudaFree(p);
+        if (sc.ev_done) cudaEventDestroy(sc.ev_done);
+    }
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (int i = 0; i <= BPP_PHASE_COUNT; i++)
@@ -150,6 +177,9 @@ extern "C" void bpp_free(bpp_ctx *ctx) {
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->pipe_ready) {
         cudaStreamDestroy(ctx->s_sort);
+        cudaStreamDestroy(ctx->s_bulk[0]);
+        cudaStreamDestroy(ctx->s_bulk[1]);
+        cudaStreamDestroy(ctx->s_final);
         cudaEventDestroy(ctx->ev_fork);
         for (int g = 0; g < BPP_MAX_GROUPS; g++) {
             cudaStreamDestroy(ctx->s_tail[g]);
@@ -157,7 +187,6 @@ extern "C" void bpp_free(bpp_ctx *ctx) {
             cudaEventDestroy(ctx->ev_acc[g]);
             cudaEventDestroy(ctx->ev_tail[g]);
         }
-        cudaFree(ctx->d_gparts);
     }
     delete ctx;
 }
@@ -165,6 +194,8 @@ extern "C" void bpp_free(bpp_ctx *ctx) {
 extern "C" int bpp_set_stream(bpp_ctx *ctx, void *s) {
     if (!ctx) return BPP_ERR_INVALID_ARG;
     CK(ctx, cudaSetDevice(ctx->device));
+    int rc = msm_wait_pending(ctx);
+    if (rc) return rc;
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     ctx->stream = (cudaStream_t)s;
@@ -173,6 +204,7 @@ extern "C" int bpp_set_stream(bpp_ctx *ctx, void *s) {
 }
 extern "C" int bpp_synchronize(bpp_ctx *ctx) {
     if (!ctx) return BPP_ERR_INVALID_ARG;
+    if (int rc = msm_wait_pending(ctx)) return rc;
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     return BPP_OK;
 }
@@ -200,6 +232,38 @@ extern "C" int bpp_set_window_bits(bpp_ctx *ctx, int c) {
 extern "C" int bpp_set_msm_groups(bpp_ctx *ctx, int groups) {
     if (!ctx || groups < 0 || groups > BPP_MAX_GROUPS) return BPP_ERR_INVALID_ARG;
     ctx->forced_groups = groups;
+    ctx->n_forced_part = 0;
+    return BPP_OK;
+}
+
+extern "C" int bpp_set_msm_partition(bpp_ctx *ctx, const int *sizes, int count) {
+    if (!ctx || count < 0 || count > BPP_MAX_GROUPS || (count && !sizes)) return BPP_ERR_INVALID_ARG;
+    for (int i = 0; i < count; i++)
+        if (sizes[i] < 1) return BPP_ERR_INVALID_ARG;
+    for (int i = 0; i < count; i++) ctx->forced_part[i] = sizes[i];
+    ctx->n_forced_part = count;
+    return BPP_OK;
+}
+
+extern "C" int bpp_set_msm_trace(bpp_ctx *ctx, int on) {
+    if (!ctx) return BPP_ERR_INVALID_ARG;
+    ctx->trace = on != 0;
+    return BPP_OK;
+}
+
+extern "C" int bpp_msm_trace_dump(bpp_ctx *ctx, char *buf, size_t cap) {
+    if (!ctx || !buf || cap == 0) return BPP_ERR_INVALID_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaDeviceSynchronize());
+    std::string out;
+    for (size_t i = 0; i < ctx->trace_ev.size(); i++) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->trace_ev[0].second, ctx->trace_ev[i].second);
+        char line[96];
+        snprintf(line, sizeof line, "%s %.1f\n", ctx->trace_ev[i].first.c_str(), ms * 1000.f);
+        out += line;
+    }
+    snprintf(buf, cap, "%s", out.c_str());
     return BPP_OK;
 }
 
@@ -335,6 +399,7 @@ extern "C" void bpp_points_free(bpp_ctx *ctx, bpp_points *p) {
     if (!p) return;
     if (ctx) {
         cudaSetDevice(ctx->device);
+        msm_wait_pending(ctx);   // a submitted MSM may still be reading the table on the side streams
         cudaStreamSynchronize(ctx->stream);
     }
     if (p->niels) cudaFree(p->niels);
@@ -361,6 +426,9 @@ static int msm_pipeline_init(bpp_ctx *ctx) {
     int lo = 0, hi = 0;
     CK(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));  // hi = numerically lowest = most urgent
     CK(ctx, cudaStreamCreateWithPriority(&ctx->s_sort, cudaStreamNonBlocking, hi));
+    CK(ctx, cudaStreamCreateWithPriority(&ctx->s_bulk[0], cudaStreamNonBlocking, lo));
+    CK(ctx, cudaStreamCreateWithPriority(&ctx->s_bulk[1], cudaStreamNonBlocking, lo));
+    CK(ctx, cudaStreamCreateWithPriority(&ctx->s_final, cudaStreamNonBlocking, hi));
     for (int g = 0; g < BPP_MAX_GROUPS; g++) {
         CK(ctx, cudaStreamCreateWithPriority(&ctx->s_tail[g], cudaStreamNonBlocking, hi));
         CK(ctx, cudaEventCreateWithFlags(&ctx->ev_sorted[g], cudaEventDisableTiming));
@@ -368,24 +436,47 @@ static int msm_pipeline_init(bpp_ctx *ctx) {
         CK(ctx, cudaEventCreateWithFlags(&ctx->ev_tail[g], cudaEventDisableTiming));
     }
     CK(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-    CK(ctx, cudaMalloc((void **)&ctx->d_gparts, 128 * BPP_MAX_GROUPS));
     ctx->pipe_ready = true;
     return BPP_OK;
 }
 
-// Number of window groups for an n-point MSM (1 = everything in order on the caller's stream).  Measured on
-// B200 (tools/msm_groups.py): the pipeline pays once the accumulate of one group is long enough to hide the
-// dependent tail (fix-up, node merges, Horner) of the previous one.
-static int pick_groups(const bpp_ctx *ctx, size_t n, int W) {
+// Window groups of an n-point MSM, top group first (sizes sum to W; one group = everything in order on the
+// caller's stream).  Measured on B200 (tools/msm_groups.py, tools/msm_trace.py): the pipeline pays once the
+// accumulate of one group is long enough to hide the dependent tail (fix-up, node merges, Horner) of the previous
+// one; a small first group starts the accumulate early and a small last group leaves a short tail.
+static int pick_partition(const bpp_ctx *ctx, size_t n, int W, int part[BPP_MAX_GROUPS]) {
+    if (ctx->n_forced_part && !ctx->profiling) {
+        int sum = 0;
+        for (int i = 0; i < ctx->n_forced_part; i++) sum += ctx->forced_part[i];
+        if (sum == W) {
+            for (int i = 0; i < ctx->n_forced_part; i++) part[i] = ctx->forced_part[i];
+            return ctx->n_forced_part;
+        }
+    }
     int G = ctx->forced_groups ? ctx->forced_groups : (n >= BPP_PIPELINE_MIN_POINTS ? 4 : 1);
     if (G > W) G = W;
     if (G > BPP_MAX_GROUPS) G = BPP_MAX_GROUPS;
-    if (ctx->profiling) G = 1;  // the per-phase events describe the in-order pipeline
-    return G < 1 ? 1 : G;
+    if (ctx->profiling || G < 1) G = 1;  // the per-phase events describe the in-order pipeline
+    for (int g = 0; g < G; g++) part[g] = (W - (W / G) * G > g) ? W / G + 1 : W / G;
+    return G;
 }
 
+// The caller's stream waits for every MSM that was submitted and not yet waited for.
+static int msm_wait_pending(bpp_ctx *ctx) {
+    for (auto &sc : ctx->scr)
+        if (sc.pending) {
+            CK(ctx, cudaStreamWaitEvent(ctx->stream, sc.ev_done, 0));
+            sc.pending = false;
+        }
+    return BPP_OK;
+}
+
+// Enqueues one MSM.  join = true: the result is in d_out in stream order on the caller's stream when the call returns
+// (the classic contract).  join = false (bpp_msm_submit_dev): the caller's stream is not made to wait; the result is
+// valid after bpp_msm_wait, and up to two submitted MSMs are in flight (the tail of one beside the sort and
+// accumulate of the next).
 static int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points *pts, size_t off, size_t n,
-                       uint8_t *d_out, int do_compress) {
+                       uint8_t *d_out, int do_compress, bool join = true) {
     const int c = ctx->forced_c ? ctx->forced_c : pick_window(n);
     const int W = (256 + c - 1) / c;
     const uint32_t B = 1u << (c - 1);
@@ -412,92 +503,127 @@ static int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points
     // node storage (S and A each): two ping-pong halves; inside a half every window owns max_T_out nodes, so the
     // window groups of the pipelined form (each at its own level at any moment) never share storage
     const size_t node_elems = (size_t)W * max_T_out * 32;
-    const int G = pick_groups(ctx, n, W);
+    int part[BPP_MAX_GROUPS];
+    const int G = pick_partition(ctx, n, W, part);
     int rc;
     if (G > 1 && (rc = msm_pipeline_init(ctx))) return rc;
-    if ((rc = grow(ctx, &ctx->d_counts, &ctx->cap_wb, WB))) return rc;
-    if ((rc = grow(ctx, &ctx->d_offsets, &ctx->cap_offsets, WB))) return rc;
-    if ((rc = grow(ctx, &ctx->d_cursor, &ctx->cap_cursor, WB))) return rc;
-    if ((rc = grow(ctx, &ctx->d_entries, &ctx->cap_entries, (size_t)W * n))) return rc;
+    ctx->slot ^= 1;
+    bpp_ctx::msm_scratch &sc = ctx->scr[ctx->slot];
+    cudaStream_t s = ctx->stream;
+    if (!sc.ev_done) {
+        CK(ctx, cudaEventCreateWithFlags(&sc.ev_done, cudaEventDisableTiming));
+        CK(ctx, cudaMalloc((void **)&sc.d_gparts, 128 * BPP_MAX_GROUPS));
+        CK(ctx, cudaMalloc((void **)&sc.d_nlong, 4 * BPP_MAX_GROUPS));
+    }
+    // the slot's previous MSM (two submissions ago) must be done before its scratch is reused (or reallocated)
+    if (sc.pending) {
+        CK(ctx, cudaStreamWaitEvent(s, sc.ev_done, 0));
+        sc.pending = false;
+    }
     const uint32_t tpw = (uint32_t)((n + BPP_TILE - 1) / BPP_TILE);
     const size_t total_tiles = (size_t)W * tpw;
-    if ((rc = grow(ctx, &ctx->d_partials, &ctx->cap_partials, total_tiles * 2 * 32))) return rc;
-    if ((rc = grow(ctx, &ctx->d_long, &ctx->cap_long, total_tiles / BPP_LONG_SPAN + 16 * (BPP_MAX_GROUPS + 1)))) return rc;
-    if ((rc = grow(ctx, &ctx->d_buckets, &ctx->cap_buckets, WB * 32))) return rc;
+    const bool must_grow = WB > sc.cap_wb || WB > sc.cap_offsets || WB > sc.cap_cursor || (size_t)W * n > sc.cap_entries ||
+                           total_tiles * 64 > sc.cap_partials || WB * 32 > sc.cap_buckets || 2 * node_elems > sc.cap_seg ||
+                           total_tiles / BPP_LONG_SPAN + 16 * (BPP_MAX_GROUPS + 1) > sc.cap_long;
+    if (must_grow) CK(ctx, cudaDeviceSynchronize());  // cudaFree of scratch another in-flight MSM never touches, but be plain
+    if ((rc = grow(ctx, &sc.d_counts, &sc.cap_wb, WB))) return rc;
+    if ((rc = grow(ctx, &sc.d_offsets, &sc.cap_offsets, WB))) return rc;
+    if ((rc = grow(ctx, &sc.d_cursor, &sc.cap_cursor, WB))) return rc;
+    if ((rc = grow(ctx, &sc.d_entries, &sc.cap_entries, (size_t)W * n))) return rc;
+    if ((rc = grow(ctx, &sc.d_partials, &sc.cap_partials, total_tiles * 2 * 32))) return rc;
+    if ((rc = grow(ctx, &sc.d_long, &sc.cap_long, total_tiles / BPP_LONG_SPAN + 16 * (BPP_MAX_GROUPS + 1)))) return rc;
+    if ((rc = grow(ctx, &sc.d_buckets, &sc.cap_buckets, WB * 32))) return rc;
     if (node_elems) {
         size_t need = 2 * node_elems;  // two ping-pong buffers in each of segS / segR
-        if (need > ctx->cap_seg) {
-            if (ctx->d_segS) cudaFree(ctx->d_segS);
-            if (ctx->d_segR) cudaFree(ctx->d_segR);
-            ctx->d_segS = ctx->d_segR = nullptr;
-            ctx->cap_seg = 0;
-            CK(ctx, cudaMalloc((void **)&ctx->d_segS, need * 4));
-            CK(ctx, cudaMalloc((void **)&ctx->d_segR, need * 4));
-            ctx->cap_seg = need;
+        if (need > sc.cap_seg) {
+            if (sc.d_segS) cudaFree(sc.d_segS);
+            if (sc.d_segR) cudaFree(sc.d_segR);
+            sc.d_segS = sc.d_segR = nullptr;
+            sc.cap_seg = 0;
+            CK(ctx, cudaMalloc((void **)&sc.d_segS, need * 4));
+            CK(ctx, cudaMalloc((void **)&sc.d_segR, need * 4));
+            sc.cap_seg = need;
         }
     }
 
-    cudaStream_t s = ctx->stream;
     const bool prof = ctx->profiling && G == 1;
     const uint32_t *niels = pts->niels + 24 * off;
     const unsigned sb = (unsigned)((n + 255) / 256);
     uint64_t red_add = 0, red_dbl = 0;
     if (prof) cudaEventRecord(ctx->ev[0], s);
-    CK(ctx, cudaMemsetAsync(ctx->d_counts, 0, WB * 4, s));
-    CK(ctx, cudaMemsetAsync(ctx->d_flag + 8, 0, 4 * BPP_MAX_GROUPS, s));
+    if (ctx->trace) {
+        for (auto &pe : ctx->trace_ev) cudaEventDestroy(pe.second);
+        ctx->trace_ev.clear();
+    }
+    trace_mark(ctx, s, "start", 0);
+    // Pipelined form: nothing but the fork and (join) the final wait touches the caller's stream.
+    //   s_sort (urgent)     sort of group 0, 1, 2, ... in order: runs ahead of the accumulates
+    //   s_bulk[g & 1] (low) accumulate of group g: the work that fills the GPU; alternating streams let the last,
+    //                       partly filled wave of one group run beside the first wave of the next
+    //   s_tail[g] (urgent)  fix-up, bucket reduction, Horner and the doublings to the group's weight: dependent
+    //                       chains that take the SM slots they need as accumulate blocks retire
+    //   s_final (urgent)    sum of the group partials, compress
+    cudaStream_t s_sort = G > 1 ? ctx->s_sort : s;
     if (G > 1) {
         CK(ctx, cudaEventRecord(ctx->ev_fork, s));
-        CK(ctx, cudaStreamWaitEvent(ctx->s_sort, ctx->ev_fork, 0));
+        CK(ctx, cudaStreamWaitEvent(s_sort, ctx->ev_fork, 0));
     }
+    CK(ctx, cudaMemsetAsync(sc.d_counts, 0, WB * 4, s_sort));
+    CK(ctx, cudaMemsetAsync(sc.d_nlong, 0, 4 * BPP_MAX_GROUPS, s_sort));
     // Window groups from the top down: the top group's partial needs the most doublings to reach its weight, and
     // they run beside the accumulate of the groups below.  With G == 1 every stream below is the caller's.
     int w_hi = W;
     for (int g = 0; g < G; g++) {
-        const int Wg = (W - (W / G) * G > g) ? W / G + 1 : W / G;
+        const int Wg = part[g];
         const int w0 = w_hi - Wg;
         w_hi = w0;
-        cudaStream_t s_sort = G > 1 ? ctx->s_sort : s, s_tail = G > 1 ? ctx->s_tail[g] : s;
-        uint32_t *counts = ctx->d_counts + (size_t)w0 * B, *offsets = ctx->d_offsets + (size_t)w0 * B;
-        uint32_t *ends = ctx->d_cursor + (size_t)w0 * B, *entries = ctx->d_entries + (size_t)w0 * n;
-        uint32_t *buckets = ctx->d_buckets + (size_t)w0 * B * 32, *partials = ctx->d_partials + (size_t)w0 * tpw * 64;
-        uint32_t *long_list = ctx->d_long + ((size_t)w0 * tpw) / BPP_LONG_SPAN + 16 * g, *d_nlong = ctx->d_flag + 8 + g;
+        cudaStream_t s_tail = G > 1 ? ctx->s_tail[g] : s, s_acc = G > 1 ? ctx->s_bulk[g & 1] : s;
+        uint32_t *counts = sc.d_counts + (size_t)w0 * B, *offsets = sc.d_offsets + (size_t)w0 * B;
+        uint32_t *ends = sc.d_cursor + (size_t)w0 * B, *entries = sc.d_entries + (size_t)w0 * n;
+        uint32_t *buckets = sc.d_buckets + (size_t)w0 * B * 32, *partials = sc.d_partials + (size_t)w0 * tpw * 64;
+        uint32_t *long_list = sc.d_long + ((size_t)w0 * tpw) / BPP_LONG_SPAN + 16 * g, *d_nlong = sc.d_nlong + g;
         const uint32_t group_tiles = (uint32_t)Wg * tpw, group_buckets = (uint32_t)Wg * B;
         // sort: recode + histogram, scan, counting-sort scatter (absolute window numbers: the recoding carry
         // ripples up from window 0)
-        k_digit_hist<<<sb, 256, 0, s_sort>>>(d_scalars, (uint32_t)n, c, w0, w0 + Wg, ctx->d_counts);
+        trace_mark(ctx, s_sort, "sort>", g);
+        k_digit_hist<<<sb, 256, 0, s_sort>>>(d_scalars, (uint32_t)n, c, w0, w0 + Wg, sc.d_counts);
         LAUNCH_CHECK(ctx);
+        trace_mark(ctx, s_sort, "hist.", g);
         if (prof) cudaEventRecord(ctx->ev[1], s);
         k_window_scan<<<Wg, 1024, 0, s_sort>>>(counts, B, offsets, ends);
         LAUNCH_CHECK(ctx);
         if (prof) cudaEventRecord(ctx->ev[2], s);
-        k_digit_scatter<<<sb, 256, 0, s_sort>>>(d_scalars, (uint32_t)n, c, w0, w0 + Wg, ctx->d_cursor, ctx->d_entries);
+        k_digit_scatter<<<sb, 256, 0, s_sort>>>(d_scalars, (uint32_t)n, c, w0, w0 + Wg, sc.d_cursor, sc.d_entries);
         LAUNCH_CHECK(ctx);
         if (prof) cudaEventRecord(ctx->ev[3], s);
+        trace_mark(ctx, s_sort, "sort.", g);
         if (G > 1) {
             CK(ctx, cudaEventRecord(ctx->ev_sorted[g], s_sort));
-            CK(ctx, cudaStreamWaitEvent(s, ctx->ev_sorted[g], 0));
+            CK(ctx, cudaStreamWaitEvent(s_acc, ctx->ev_sorted[g], 0));
         }
-        // accumulate: on the caller's stream, group after group - the work that fills the GPU
-        k_bucket_accum<<<(group_tiles + BPP_ACC_THREADS - 1) / BPP_ACC_THREADS, BPP_ACC_THREADS, 0, s>>>(
+        trace_mark(ctx, s_acc, "accum>", g);
+        k_bucket_accum<<<(group_tiles + BPP_ACC_THREADS - 1) / BPP_ACC_THREADS, BPP_ACC_THREADS, 0, s_acc>>>(
             niels, entries, offsets, ends, (uint32_t)n, B, tpw, group_tiles, buckets, partials);
         LAUNCH_CHECK(ctx);
         if (prof) cudaEventRecord(ctx->ev[4], s);
+        trace_mark(ctx, s_acc, "accum.", g);
         if (G > 1) {
-            CK(ctx, cudaEventRecord(ctx->ev_acc[g], s));
+            CK(ctx, cudaEventRecord(ctx->ev_acc[g], s_acc));
             CK(ctx, cudaStreamWaitEvent(s_tail, ctx->ev_acc[g], 0));
         }
-        // tail: dependent chains on a high-priority stream of their own
+        trace_mark(ctx, s_tail, "tail>", g);
         k_bucket_fixup<<<(group_buckets + 127) / 128, 128, 0, s_tail>>>(offsets, ends, B, tpw, group_buckets, partials,
                                                                        buckets, long_list, d_nlong);
         LAUNCH_CHECK(ctx);
         k_bucket_fixup_long<<<ctx->sm_count * 2, 128, 0, s_tail>>>(offsets, ends, B, tpw, partials, buckets, long_list,
                                                                   d_nlong);
         LAUNCH_CHECK(ctx);
+        trace_mark(ctx, s_tail, "fixup.", g);
         const uint32_t *curS = buckets, *curA = nullptr;
         for (int i = 0; i < n_levels; i++) {
             const level &lv = plan[i];
-            uint32_t *oS = ctx->d_segS + (i & 1) * node_elems + (size_t)w0 * max_T_out * 32;
-            uint32_t *oA = ctx->d_segR + (i & 1) * node_elems + (size_t)w0 * max_T_out * 32;
+            uint32_t *oS = sc.d_segS + (i & 1) * node_elems + (size_t)w0 * max_T_out * 32;
+            uint32_t *oA = sc.d_segR + (i & 1) * node_elems + (size_t)w0 * max_T_out * 32;
             const uint32_t n_out = (uint32_t)Wg * lv.T_out;
             if (lv.kind == 0) {
                 k_node_merge_serial<<<(n_out + 127) / 128, 128, 0, s_tail>>>(curS, curA, lv.L, lv.loglen, n_out, oS, oA);
@@ -513,6 +639,7 @@ static int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points
                 red_dbl += (uint64_t)Wg * lv.T_out * lv.loglen;
             }
             LAUNCH_CHECK(ctx);
+            trace_mark(ctx, s_tail, i == 0 ? "merge0." : "merge.", g);
             curS = oS;
             curA = oA;
         }
@@ -522,15 +649,25 @@ static int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points
             LAUNCH_CHECK(ctx);
         } else {
             // Horner inside the group, then c*w0 doublings to the group's weight; raw point to d_gparts[g]
-            k_msm_finish<<<1, 32, 0, s_tail>>>(curS, curA, c, Wg, c * w0, 0, ctx->d_gparts + 128 * g);
+            k_msm_finish<<<1, 32, 0, s_tail>>>(curS, curA, c, Wg, c * w0, 0, sc.d_gparts + 128 * g);
             LAUNCH_CHECK(ctx);
             CK(ctx, cudaEventRecord(ctx->ev_tail[g], s_tail));
         }
+        trace_mark(ctx, s_tail, "finish.", g);
     }
     if (G > 1) {
-        for (int g = 0; g < G; g++) CK(ctx, cudaStreamWaitEvent(s, ctx->ev_tail[g], 0));
-        k_points_sum_finish<<<1, 32, 0, s>>>((const uint32_t *)ctx->d_gparts, (uint32_t)G, do_compress, d_out);
+        for (int g = 0; g < G; g++) CK(ctx, cudaStreamWaitEvent(ctx->s_final, ctx->ev_tail[g], 0));
+        k_points_sum_finish<<<1, 32, 0, ctx->s_final>>>((const uint32_t *)sc.d_gparts, (uint32_t)G, do_compress, d_out);
         LAUNCH_CHECK(ctx);
+        trace_mark(ctx, ctx->s_final, "end", 0);
+        CK(ctx, cudaEventRecord(sc.ev_done, ctx->s_final));
+        sc.pending = true;
+        if (join && (rc = msm_wait_pending(ctx))) return rc;
+    } else {
+        trace_mark(ctx, s, "end", 0);
+        if (!join) {   // in order on the caller's stream: nothing to wait for, but the slot's reuse rule stays uniform
+            CK(ctx, cudaEventRecord(sc.ev_done, s));
+        }
     }
     if (prof) { cudaEventRecord(ctx->ev[6], s); ctx->events_pending = true; }
     ctx->n_madd = (uint64_t)W * n;
@@ -564,6 +701,20 @@ extern "C" int bpp_msm_vartime_dev(bpp_ctx *ctx, const void *d_scalars, const bp
     CK(ctx, cudaSetDevice(ctx->device));
     int rc = msm_enqueue(ctx, (const uint32_t *)d_scalars, points, off, n, (uint8_t *)d_out, 1);
     return rc;
+}
+
+extern "C" int bpp_msm_submit_dev(bpp_ctx *ctx, const void *d_scalars, const bpp_points *points, size_t off, size_t n,
+                                  void *d_out) {
+    if (!ctx || !d_scalars || !points || !d_out || n == 0) return BPP_ERR_INVALID_ARG;
+    if (off + n > points->n) return BPP_ERR_LENGTH_MISMATCH;
+    CK(ctx, cudaSetDevice(ctx->device));
+    return msm_enqueue(ctx, (const uint32_t *)d_scalars, points, off, n, (uint8_t *)d_out, 1, false);
+}
+
+extern "C" int bpp_msm_wait(bpp_ctx *ctx) {
+    if (!ctx) return BPP_ERR_INVALID_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    return msm_wait_pending(ctx);
 }
 
 extern "C" int bpp_msm_partial_dev(bpp_ctx *ctx, const void *d_scalars, const bpp_points *points, size_t off, size_t n,

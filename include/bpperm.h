@@ -93,6 +93,16 @@ int bpp_msm_vartime_host(bpp_ctx *ctx, const uint8_t *scalars, size_t n_scalars,
  * X,Y,Z,T as raw 8x32-bit-limb field elements) written to d_out (160 B, device). Asynchronous. */
 int bpp_msm_vartime_dev(bpp_ctx *ctx, const void *d_scalars, const bpp_points *points, size_t off, size_t n,
                         void *d_out);
+/* Throughput form of bpp_msm_vartime_dev for a sequence of independent MSMs: submit enqueues the MSM without
+ * making the caller's stream wait for it; the result is valid (in stream order on the caller's stream) after
+ * bpp_msm_wait.  Up to two submitted MSMs are in flight on the library's internal streams - the dependent tail of
+ * one (bucket reduction, Horner, compress) runs beside the sort and accumulate of the next; a third submit first
+ * waits for the oldest.  d_scalars and d_out of a submitted MSM must stay untouched until bpp_msm_wait (or
+ * bpp_synchronize / bpp_points_free / bpp_set_stream, which wait too).  Inputs are taken in stream order: work
+ * queued on the caller's stream before the submit is complete before the MSM reads d_scalars. */
+int bpp_msm_submit_dev(bpp_ctx *ctx, const void *d_scalars, const bpp_points *points, size_t off, size_t n,
+                       void *d_out);
+int bpp_msm_wait(bpp_ctx *ctx);
 /* Partial (uncompressed) sum for multi-GPU sharding: writes the 128-byte extended point (raw limbs)
  * to d_partial and does not compress.  bpp_points_sum_compress_dev adds g such partials (e.g. after an
  * all-gather) and compresses: d_out32 receives the 32-byte encoding. */
@@ -107,6 +117,9 @@ int bpp_set_window_bits(bpp_ctx *ctx, int c);
  * doublings to the group's weight) run on internal high-priority streams beside the accumulate of the current
  * group; the call still is stream-ordered on the caller's stream.  The result bytes do not depend on it. */
 int bpp_set_msm_groups(bpp_ctx *ctx, int groups);
+/* Explicit window-group sizes, top group first (count <= 8; used when they sum to the number of windows of the
+ * MSM, ignored otherwise; count = 0 clears).  A tuning hook like bpp_set_window_bits. */
+int bpp_set_msm_partition(bpp_ctx *ctx, const int *sizes, int count);
 
 /* ---- scalar-vector operators mod l: the reference's util.rs / poly.rs -------------------------------
  * All vectors are arrays of 32-byte little-endian canonical scalars in host memory.  Where the Rust
@@ -226,6 +239,11 @@ int bpp_bench_pipe_probe(bpp_ctx *ctx, int mode, int iters, double *ops_per_sec)
 enum { BPP_PHASE_RECODE = 0, BPP_PHASE_SCAN, BPP_PHASE_SCATTER, BPP_PHASE_ACCUMULATE, BPP_PHASE_REDUCE,
        BPP_PHASE_FINISH, BPP_PHASE_COUNT };
 int bpp_set_profiling(bpp_ctx *ctx, int on);
+/* Stage timeline of the last bpp_msm_* call (pipelined or not): with tracing on, every stage boundary records a
+ * timing event on the stream that runs the stage; the dump synchronises the device and writes one line per mark,
+ * "<stage>[group] <microseconds since the start mark>" ('>' = stage begins, '.' = stage done). */
+int bpp_set_msm_trace(bpp_ctx *ctx, int on);
+int bpp_msm_trace_dump(bpp_ctx *ctx, char *buf, size_t cap);
 int bpp_last_phase_ms(bpp_ctx *ctx, float ms[BPP_PHASE_COUNT]);
 /* point-add count of the last MSM: accumulate (mixed) adds, reduction (full) adds, doublings */
 int bpp_last_op_counts(bpp_ctx *ctx, uint64_t *mixed_adds, uint64_t *full_adds, uint64_t *doublings);

@@ -202,3 +202,52 @@ def test_window_groups_match_oracle(backend, groups, c):
         table.free()
     assert got == again == in_order
     assert got == cref.msm(sc.tobytes(), cref.from_uniform(blobs.tobytes()))
+
+
+def test_submitted_msms_match_joined(backend):
+    """bpp_msm_submit_dev / bpp_msm_wait: six independent MSMs submitted back to back (two in flight on the internal
+    streams, scratch slots reused three times) give the bytes of the one-at-a-time calls and of the C restatement."""
+    import numpy as np
+    import torch
+    from oracle import cref
+    n = 1 << 14
+    rs = np.random.RandomState(4242)
+    blobs = rs.randint(0, 256, size=(n, 64), dtype=np.uint8)
+    table = backend.points_from_uniform(blobs.tobytes())
+    dev = torch.device("cuda:0")
+    sets = []
+    for i in range(6):
+        sc = rs.randint(0, 256, size=(n, 32), dtype=np.uint8)
+        sc[:, 31] &= 0x0F
+        if i == 3:
+            sc[:5000] = sc[0]     # a skewed one in the middle
+        sets.append(sc)
+    d_sets = [torch.from_numpy(s).to(dev) for s in sets]
+    outs = torch.zeros(6, 160, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    backend.set_msm_groups(4)
+    try:
+        for i in range(6):
+            backend.msm_submit_dev(d_sets[i].data_ptr(), table, 0, n, outs[i].data_ptr())
+        backend.msm_wait()
+        backend.synchronize()
+        got = [bytes(outs[i, :32].cpu().numpy().tobytes()) for i in range(6)]
+        outs.zero_()
+        # mixed: submitted, then a joined call, then a partial (uncompressed) one
+        backend.msm_submit_dev(d_sets[0].data_ptr(), table, 0, n, outs[0].data_ptr())
+        backend.msm_dev(d_sets[1].data_ptr(), table, 0, n, outs[1].data_ptr())
+        backend.synchronize()
+        assert bytes(outs[0, :32].cpu().numpy().tobytes()) == got[0]
+        assert bytes(outs[1, :32].cpu().numpy().tobytes()) == got[1]
+    finally:
+        backend.set_msm_groups(0)
+    pts = cref.from_uniform(blobs.tobytes())
+    for i in (0, 3, 5):
+        assert got[i] == cref.msm(sets[i].tobytes(), pts)
+    backend.set_msm_groups(1)
+    try:
+        for i in range(6):
+            assert backend.vartime_multiscalar_mul(sets[i].tobytes(), table) == got[i]
+    finally:
+        backend.set_msm_groups(0)
+        table.free()
