@@ -556,13 +556,34 @@ def run_ours(args):
             h_out.copy_(d_out[:32], non_blocking=True)
             stream.synchronize()
 
+        # throughput form (single GPU): every step is one bpp_msm_submit_dev, two MSMs in flight on the library's
+        # internal streams (the dependent tail of one beside the sort + accumulate of the next), one bpp_msm_wait
+        # before the closing event; results alternate between two output buffers
+        d_outs = [torch.zeros(160, dtype=torch.uint8, device=dev) for _ in range(2)]
+
+        def msm_submitted(cnt, first):
+            for i in range(cnt):
+                be.msm_submit_dev(d_sets[(first + i) % n_sets].data_ptr(), table, 0, n, d_outs[i & 1].data_ptr())
+            be.msm_wait()
+
         msm_steps = max(args.steps, 10)
         l0 = be.launch_count
         samp2 = ClockSampler(local)
         if rank == 0 and args.workload == "msm":
             samp2.start()
-        ms_res = timed(msm_resident, msm_steps, args.warmup)
+        ms_single = timed(msm_resident, msm_steps, args.warmup)
         launches = (be.launch_count - l0) * msm_steps // (msm_steps + args.warmup)
+        if world == 1:
+            ms_res = timed_block(msm_submitted, msm_steps, args.warmup)
+            # the submitted results are the single-call results
+            want = []
+            for i in range(2):
+                be.msm_dev(d_sets[(args.warmup + msm_steps - 2 + i) % n_sets].data_ptr(), table, 0, n, d_out.data_ptr())
+                want.append(bytes(d_out[:32].cpu().numpy().tobytes()))
+            got = [bytes(d_outs[(msm_steps - 2 + i) & 1][:32].cpu().numpy().tobytes()) for i in range(2)]
+            assert got == want, "submitted MSM results differ from the single-call results"
+        else:
+            ms_res = ms_single
         clocks2 = samp2.stop() if (rank == 0 and args.workload == "msm") else None
         ms_e2e_serial = timed(msm_e2e, msm_steps, args.warmup)
         # e2e, double buffered: the next step's scalars travel on a copy stream while this step's MSM runs
@@ -571,14 +592,44 @@ def run_ours(args):
         ready = [torch.cuda.Event() for _ in range(2)]
         free = [torch.cuda.Event() for _ in range(2)]
 
-        def msm_pipelined(n, first):
+        bufs3 = [torch.empty_like(d_sets[0]) for _ in range(3)]
+        ready3 = [torch.cuda.Event() for _ in range(3)]
+        free3 = [torch.cuda.Event() for _ in range(3)]
+
+        def msm_pipelined(cnt, first):
+            if world == 1:
+                # submit(i) / wait_previous / read result i-1: scalars of step i+1 travel on the copy stream meanwhile;
+                # three scalar buffers because two MSMs are in flight while the third buffer is being filled
+                used = [False] * 3
+                with torch.cuda.stream(copy_stream):
+                    bufs3[0].copy_(h_sets[first % n_sets], non_blocking=True)
+                    ready3[0].record(copy_stream)
+                for i in range(cnt):
+                    b, nb = i % 3, (i + 1) % 3
+                    if i + 1 < cnt:
+                        with torch.cuda.stream(copy_stream):
+                            if used[nb]:
+                                copy_stream.wait_event(free3[nb])
+                            bufs3[nb].copy_(h_sets[(first + i + 1) % n_sets], non_blocking=True)
+                            ready3[nb].record(copy_stream)
+                    stream.wait_event(ready3[b])
+                    be.msm_submit_dev(bufs3[b].data_ptr(), table, 0, n, d_outs[i & 1].data_ptr())
+                    be.msm_wait_previous()
+                    if i:
+                        pb = (i - 1) % 3
+                        free3[pb].record(stream)   # MSM i-1 is complete here in stream order: its scalars may be replaced
+                        used[pb] = True
+                        h_out.copy_(d_outs[(i - 1) & 1][:32], non_blocking=True)
+                be.msm_wait()
+                h_out.copy_(d_outs[(cnt - 1) & 1][:32], non_blocking=True)
+                return
             used = [False, False]
             with torch.cuda.stream(copy_stream):
                 bufs[0].copy_(h_sets[first % n_sets], non_blocking=True)
                 ready[0].record(copy_stream)
-            for i in range(n):
+            for i in range(cnt):
                 b = i & 1
-                if i + 1 < n:
+                if i + 1 < cnt:
                     with torch.cuda.stream(copy_stream):
                         if used[b ^ 1]:
                             copy_stream.wait_event(free[b ^ 1])
@@ -609,6 +660,11 @@ def run_ours(args):
             msm = {
                 "metric": "MSM points/sec at 2^20", "value": total_points * msm_steps / (ms_res * 1e-3), "unit": "points/s",
                 "n_gpus": world, "steps": msm_steps, "ms_per_step": ms_res / msm_steps, "scaling": "weak",
+                "mode": ("throughput: one bpp_msm_submit_dev per step, two MSMs in flight (the tail of one beside the sort "
+                         "and accumulate of the next), one bpp_msm_wait before the closing event; results checked against "
+                         "the single-call results") if world == 1 else "one bpp_msm_partial_dev + all-gather + sum per step",
+                "single_call": {"value": total_points * msm_steps / (ms_single * 1e-3), "ms_per_step": ms_single / msm_steps,
+                                "note": "bpp_msm_vartime_dev one call at a time: the caller's stream joins every MSM"},
                 "config": {"workload": f"ristretto255 vartime MSM, 2^{args.log_n} points per GPU (BASELINE configs[4])",
                            "points": "from_uniform_bytes(seeded bytes), resident as affine Niels (96 B/pt), no precomputed multiples",
                            "scalars": "uniform < 2^252, 4 rotating sets",
@@ -618,8 +674,9 @@ def run_ours(args):
                 "e2e": {"value": total_points * msm_steps / (ms_e2e * 1e-3), "unit": "points/s", "h2d_bytes_per_step": n * 32,
                         "d2h_bytes_per_step": 32, "ms_per_step": ms_e2e / msm_steps,
                         "serial": {"value": total_points * msm_steps / (ms_e2e_serial * 1e-3), "ms_per_step": ms_e2e_serial / msm_steps},
-                        "note": "scalars pinned-host->HBM and result HBM->host every step; generator table resident; double "
-                                "buffered (the next step's scalars are copied on a second stream during this step's MSM)"},
+                        "note": "scalars pinned-host->HBM and result HBM->host every step; generator table resident; the next "
+                                "step's scalars are copied on a second stream during this step's MSM; single GPU: submit(i), "
+                                "wait_previous, read result i-1 (two MSMs in flight)"},
                 "gpu_launches": launches,
                 "roofline": {"bound": "imad", "kernel": "k_bucket_accum", "achieved": ach / 1e12, "peak": imad_peak / 1e12,
                              "unit": "T IMAD.WIDE.U32/s", "frac": ach / imad_peak, "kernel_ms": float(phases[3]),

@@ -216,6 +216,10 @@ class Backend:
     def msm_wait(self):
         self._check(self._lib.bpp_msm_wait(self._ctx))
 
+    def msm_wait_previous(self):
+        """Wait for every submitted MSM except the one submitted last."""
+        self._check(self._lib.bpp_msm_wait_previous(self._ctx))
+
     def msm_partial_dev(self, d_scalars: int, points: Points, off: int, n: int, d_partial: int):
         self._check(self._lib.bpp_msm_partial_dev(self._ctx, ctypes.c_void_p(d_scalars), points._h, off, n,
                                                   ctypes.c_void_p(d_partial)))

@@ -12,6 +12,7 @@
 
 #define BPP_MAX_GROUPS 8
 #define BPP_PIPELINE_MIN_POINTS (1u << 18)
+#define BPP_PIPELINE_MIN_POINTS_SUBMIT (1u << 12)
 
 struct bpp_points {
     uint32_t *niels = nullptr;  // n x 24 u32 (96 B)
@@ -106,7 +107,7 @@ static int grow(bpp_ctx *ctx, T **p, size_t *cap, size_t need_elems) {
     return BPP_OK;
 }
 
-static int msm_wait_pending(bpp_ctx *ctx);
+static int msm_wait_pending(bpp_ctx *ctx, bool keep_latest = false);
 
 extern "C" const char *bpp_strerror(int s) {
     switch (s) {
@@ -444,7 +445,7 @@ static int msm_pipeline_init(bpp_ctx *ctx) {
 // caller's stream).  Measured on B200 (tools/msm_groups.py, tools/msm_trace.py): the pipeline pays once the
 // accumulate of one group is long enough to hide the dependent tail (fix-up, node merges, Horner) of the previous
 // one; a small first group starts the accumulate early and a small last group leaves a short tail.
-static int pick_partition(const bpp_ctx *ctx, size_t n, int W, int part[BPP_MAX_GROUPS]) {
+static int pick_partition(const bpp_ctx *ctx, size_t n, int W, bool join, int part[BPP_MAX_GROUPS]) {
     if (ctx->n_forced_part && !ctx->profiling) {
         int sum = 0;
         for (int i = 0; i < ctx->n_forced_part; i++) sum += ctx->forced_part[i];
@@ -453,7 +454,15 @@ static int pick_partition(const bpp_ctx *ctx, size_t n, int W, int part[BPP_MAX_
             return ctx->n_forced_part;
         }
     }
-    int G = ctx->forced_groups ? ctx->forced_groups : (n >= BPP_PIPELINE_MIN_POINTS ? 4 : 1);
+    if (!ctx->forced_groups && !ctx->profiling && W >= 8 &&
+        n >= (join ? BPP_PIPELINE_MIN_POINTS : BPP_PIPELINE_MIN_POINTS_SUBMIT)) {
+        // measured best of the partitions tried at 2^18..2^22 points (profiles/r1_msm_partitions.md): an eighth of the
+        // windows first and last, the rest in two halves (16 windows: 2, 6, 6, 2)
+        const int edge = W / 8, mid = W - 2 * edge;
+        part[0] = edge; part[1] = (mid + 1) / 2; part[2] = mid / 2; part[3] = edge;
+        return 4;
+    }
+    int G = ctx->forced_groups ? ctx->forced_groups : 1;
     if (G > W) G = W;
     if (G > BPP_MAX_GROUPS) G = BPP_MAX_GROUPS;
     if (ctx->profiling || G < 1) G = 1;  // the per-phase events describe the in-order pipeline
@@ -461,13 +470,16 @@ static int pick_partition(const bpp_ctx *ctx, size_t n, int W, int part[BPP_MAX_
     return G;
 }
 
-// The caller's stream waits for every MSM that was submitted and not yet waited for.
-static int msm_wait_pending(bpp_ctx *ctx) {
-    for (auto &sc : ctx->scr)
-        if (sc.pending) {
+// The caller's stream waits for every MSM that was submitted and not yet waited for (keep_latest: except the one
+// submitted last, which stays in flight).
+static int msm_wait_pending(bpp_ctx *ctx, bool keep_latest) {
+    for (int i = 0; i < 2; i++) {
+        bpp_ctx::msm_scratch &sc = ctx->scr[i];
+        if (sc.pending && !(keep_latest && i == ctx->slot)) {
             CK(ctx, cudaStreamWaitEvent(ctx->stream, sc.ev_done, 0));
             sc.pending = false;
         }
+    }
     return BPP_OK;
 }
 
@@ -504,7 +516,7 @@ static int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points
     // window groups of the pipelined form (each at its own level at any moment) never share storage
     const size_t node_elems = (size_t)W * max_T_out * 32;
     int part[BPP_MAX_GROUPS];
-    const int G = pick_partition(ctx, n, W, part);
+    const int G = pick_partition(ctx, n, W, join, part);
     int rc;
     if (G > 1 && (rc = msm_pipeline_init(ctx))) return rc;
     ctx->slot ^= 1;
@@ -715,6 +727,12 @@ extern "C" int bpp_msm_wait(bpp_ctx *ctx) {
     if (!ctx) return BPP_ERR_INVALID_ARG;
     CK(ctx, cudaSetDevice(ctx->device));
     return msm_wait_pending(ctx);
+}
+
+extern "C" int bpp_msm_wait_previous(bpp_ctx *ctx) {
+    if (!ctx) return BPP_ERR_INVALID_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    return msm_wait_pending(ctx, true);
 }
 
 extern "C" int bpp_msm_partial_dev(bpp_ctx *ctx, const void *d_scalars, const bpp_points *points, size_t off, size_t n,

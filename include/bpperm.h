@@ -103,6 +103,9 @@ int bpp_msm_vartime_dev(bpp_ctx *ctx, const void *d_scalars, const bpp_points *p
 int bpp_msm_submit_dev(bpp_ctx *ctx, const void *d_scalars, const bpp_points *points, size_t off, size_t n,
                        void *d_out);
 int bpp_msm_wait(bpp_ctx *ctx);
+/* Like bpp_msm_wait, but the MSM submitted last stays in flight: after submit(i), the results of every MSM up to
+ * i-1 are valid - the form a producer/consumer loop uses (submit i, wait_previous, consume i-1). */
+int bpp_msm_wait_previous(bpp_ctx *ctx);
 /* Partial (uncompressed) sum for multi-GPU sharding: writes the 128-byte extended point (raw limbs)
  * to d_partial and does not compress.  bpp_points_sum_compress_dev adds g such partials (e.g. after an
  * all-gather) and compresses: d_out32 receives the 32-byte encoding. */

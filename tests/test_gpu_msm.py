@@ -251,3 +251,42 @@ def test_submitted_msms_match_joined(backend):
     finally:
         backend.set_msm_groups(0)
         table.free()
+
+
+def test_wait_previous_producer_consumer_loop():
+    """submit(i); wait_previous(); consume(i-1) on the caller's (torch) stream: the consumer copies see final bytes."""
+    import numpy as np
+    import torch
+    import bpperm_b200
+    dev = torch.device("cuda:0")
+    be = bpperm_b200.Backend(0)
+    stream = torch.cuda.Stream(dev)
+    be.set_stream(stream.cuda_stream)
+    n = 1 << 13
+    rs = np.random.RandomState(77)
+    table = be.points_from_uniform(rs.randint(0, 256, size=(n, 64), dtype=np.uint8).tobytes())
+    sets = []
+    for i in range(5):
+        sc = rs.randint(0, 256, size=(n, 32), dtype=np.uint8)
+        sc[:, 31] &= 0x0F
+        sets.append(sc)
+    want = [be.vartime_multiscalar_mul(s.tobytes(), table) for s in sets]
+    d_sets = [torch.from_numpy(s).to(dev) for s in sets]
+    outs = torch.zeros(5, 160, dtype=torch.uint8, device=dev)
+    host = torch.zeros(5, 32, dtype=torch.uint8).pin_memory()
+    torch.cuda.synchronize()
+    be.set_msm_groups(3)
+    with torch.cuda.stream(stream):
+        for i in range(5):
+            be.msm_submit_dev(d_sets[i].data_ptr(), table, 0, n, outs[i].data_ptr())
+            be.msm_wait_previous()
+            if i:
+                host[i - 1].copy_(outs[i - 1, :32], non_blocking=True)
+        be.msm_wait()
+        host[4].copy_(outs[4, :32], non_blocking=True)
+    stream.synchronize()
+    be.set_msm_groups(0)
+    for i in range(5):
+        assert bytes(host[i].numpy().tobytes()) == want[i], i
+    table.free()
+    be.close()

@@ -53,7 +53,8 @@ def timed(submit):
 be.set_msm_groups(1)
 t_inorder = timed(False)
 want = outs[:, :32].cpu().numpy().copy()
-print(f"2^{log_n} in-order, joined: {t_inorder:.3f} ms/MSM", flush=True)
+t_inorder_sub = timed(True)
+print(f"2^{log_n} in-order, joined: {t_inorder:.3f} ms/MSM (submitted in order: {t_inorder_sub:.3f})", flush=True)
 rows.append({"log_n": log_n, "partition": "in-order", "joined_ms": t_inorder})
 be.set_msm_groups(0)
 for part in parts:
