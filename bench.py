@@ -451,6 +451,33 @@ def run_ours(args):
                           "proofs": torch.empty(B * plen, dtype=torch.uint8).pin_memory(),
                           "accept": torch.empty(B, dtype=torch.uint8).pin_memory(), "ok": True})
 
+        # resident, two lanes: the same two batches in flight with their inputs already in HBM (witness uploaded and
+        # committed once per lane); a step is one batch of B proofs proved and verified.  The small dependent kernels
+        # of one batch (transcripts, power chains, dot products) run beside the table-gather MSMs of the other.
+        for ln in lanes:
+            ln["batch"].upload_witness(aL, aR, aO, gamma, seeds)
+            ln["batch"].commit(v)
+            ln["be"].synchronize()
+
+        def lane_resident(lane, cnt):
+            for _ in range(cnt):
+                lane["batch"].prove()
+                lane["batch"].verify(b"\x5a" * 32)
+
+        def run_resident2(cnt, first):
+            split = [(cnt + 1) // 2, cnt // 2]
+            th = [threading.Thread(target=lane_resident, args=(lanes[k], split[k])) for k in range(2) if split[k]]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+
+        res2_steps = max(2, args.steps + (args.steps & 1))   # an even number of steps: both lanes do the same work
+        ms_res2 = timed_block(run_resident2, res2_steps, max(2, args.warmup), [ln["stream"] for ln in lanes])
+        for ln in lanes:
+            ln["batch"].download_accept_ptr(ln["accept"].data_ptr())
+            ln["ok"] = ln["ok"] and bytes(ln["accept"].numpy().tobytes()) == b"\x01" * B
+
         def lane_steps(lane, n):
             bt = lane["batch"]
             for _ in range(n):
@@ -483,14 +510,21 @@ def run_ours(args):
             all_ok = bool(okt.item())
         if rank == 0:
             total = B * world
-            value = total * args.steps / (ms_res * 1e-3)
+            value_single = total * args.steps / (ms_res * 1e-3)
+            value = max(value_single, total * res2_steps / (ms_res2 * 1e-3))
+            two_lanes = value > value_single
             e2e = total * args.steps / (ms_e2e * 1e-3)
             fb_imads = fb_madd * IMAD_MADD + fb_add * IMAD_ADD
             ach = fb_imads / (fb_ms * 1e-3)
             line = {
                 "metric": "shuffle proofs/sec prove+verify (52-card)", "value": value, "unit": "proofs/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True,
+                "steps": res2_steps if two_lanes else args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_res2 / res2_steps if two_lanes else ms_res / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u32 (8x32-bit limbs, IMAD.WIDE.U32)", "data": "synthetic",
+                "mode": ("two batches in flight on two streams (one host thread each), inputs resident" if two_lanes
+                         else "one batch at a time on one stream, inputs resident"),
+                "single_stream": {"value": value_single, "ms_per_step": ms_res / args.steps, "steps": args.steps},
+                "two_lanes": {"value": total * res2_steps / (ms_res2 * 1e-3), "ms_per_step": ms_res2 / res2_steps, "steps": res2_steps},
                 "config": {"workload": f"52-card shuffle prove+verify, batch of {B} independent proofs per GPU "
                                        f"(k=52, n={n}, Q={Q}, m={m}; BASELINE configs[1]/[3])",
                            "mode": "reference-fixed (SURVEY A.3: the reference's own flow never verifies)",

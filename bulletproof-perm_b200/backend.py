@@ -123,6 +123,10 @@ class Backend:
         """Window groups of the pipelined MSM (0 = automatic, 1 = in order on one stream)."""
         self._check(self._lib.bpp_set_msm_groups(self._ctx, groups))
 
+    def set_msm_sort(self, mode: int):
+        """Sort form: 0 automatic, 1 global atomics, 2 shared memory."""
+        self._check(self._lib.bpp_set_msm_sort(self._ctx, mode))
+
     def set_msm_partition(self, sizes):
         """Explicit window-group sizes, top group first (empty = clear)."""
         arr = (ctypes.c_int * max(1, len(sizes)))(*sizes)

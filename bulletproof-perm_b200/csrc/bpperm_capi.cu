@@ -11,6 +11,7 @@
 #include "msm_kernels.cuh"
 
 #define BPP_MAX_GROUPS 8
+#define BPP_SORT_SMEM_MAX (128 * 1024)
 #define BPP_PIPELINE_MIN_POINTS (1u << 18)
 #define BPP_PIPELINE_MIN_POINTS_SUBMIT (1u << 12)
 
@@ -44,6 +45,10 @@ struct bpp_ctx {
         uint32_t *d_long = nullptr; size_t cap_long = 0;            // hot-bucket queues (one region per window group)
         uint32_t *d_nlong = nullptr;                                // their counters
         uint32_t *d_buckets = nullptr; size_t cap_buckets = 0;      // W x B x 32
+        uint32_t *d_chunk = nullptr; size_t cap_chunk = 0;          // shared-memory sort: [window of the group][chunk][B]
+        uint32_t *d_dig = nullptr; size_t cap_dig = 0;              // shared-memory / two-pass sort: digits, W x n
+        uint32_t *d_tmp = nullptr; size_t cap_tmp = 0;              // two-pass sort: entries after pass A, W x n
+        uint32_t *d_binoff = nullptr;                               // two-pass sort: coarse-bin offsets, W x 257
         uint32_t *d_segS = nullptr, *d_segR = nullptr; size_t cap_seg = 0;
         uint8_t *d_gparts = nullptr;                                // BPP_MAX_GROUPS x 128 B: window-group partials
         cudaEvent_t ev_done = nullptr;                              // recorded when the slot's MSM has written its result
@@ -59,6 +64,8 @@ struct bpp_ctx {
     // pipelined MSM: window groups on side streams (msm_pipeline_init)
     bool pipe_ready = false;
     int forced_groups = 0;
+    int sort_mode = 0;                                          // 0 automatic, 1 global atomics, 2 shared memory, 3 two-pass
+    bool smem_sort_ready = false;
     int forced_part[BPP_MAX_GROUPS] = {}, n_forced_part = 0;    // explicit group sizes, top window group first
     cudaStream_t s_sort = nullptr, s_bulk[2] = {}, s_tail[BPP_MAX_GROUPS] = {};
     cudaEvent_t ev_fork = nullptr, ev_sorted[BPP_MAX_GROUPS] = {}, ev_acc[BPP_MAX_GROUPS] = {}, ev_tail[BPP_MAX_GROUPS] = {};
@@ -166,7 +173,7 @@ extern "C" void bpp_free(bpp_ctx *ctx) {
         if (p) cudaFree(p);
     for (auto &sc : ctx->scr) {
         void *sp[] = {sc.d_counts, sc.d_offsets, sc.d_cursor, sc.d_entries, sc.d_partials, sc.d_long, sc.d_nlong,
-                      sc.d_buckets, sc.d_segS, sc.d_segR, sc.d_gparts};
+                      sc.d_buckets, sc.d_segS, sc.d_segR, sc.d_gparts, sc.d_chunk, sc.d_dig, sc.d_tmp, sc.d_binoff};
         for (void *p : sp)
             if (p) cudaFree(p);
         if (sc.ev_done) cudaEventDestroy(sc.ev_done);
@@ -234,6 +241,12 @@ extern "C" int bpp_set_msm_groups(bpp_ctx *ctx, int groups) {
     if (!ctx || groups < 0 || groups > BPP_MAX_GROUPS) return BPP_ERR_INVALID_ARG;
     ctx->forced_groups = groups;
     ctx->n_forced_part = 0;
+    return BPP_OK;
+}
+
+extern "C" int bpp_set_msm_sort(bpp_ctx *ctx, int mode) {
+    if (!ctx || mode < 0 || mode > 3) return BPP_ERR_INVALID_ARG;
+    ctx->sort_mode = mode;
     return BPP_OK;
 }
 
@@ -534,7 +547,45 @@ static int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points
     }
     const uint32_t tpw = (uint32_t)((n + BPP_TILE - 1) / BPP_TILE);
     const size_t total_tiles = (size_t)W * tpw;
-    const bool must_grow = WB > sc.cap_wb || WB > sc.cap_offsets || WB > sc.cap_cursor || (size_t)W * n > sc.cap_entries ||
+    // sort form: through shared memory once the input is large enough to feed one block per (window, chunk)
+    const bool smem_sort = B * 4 <= BPP_SORT_SMEM_MAX &&
+                           ctx->sort_mode == 2;
+    // two passes with coalesced writes (msm_kernels.cuh): items carry a 23-bit point index
+    const bool sort2 = n <= (1u << 23) && ctx->sort_mode == 3;
+    const uint32_t nb = B >> SORT2_LOW ? B >> SORT2_LOW : 1u, chunks2 = (uint32_t)((n + SORT2_CHUNK - 1) / SORT2_CHUNK);
+    size_t chunk_elems = 0;
+    int chunks_of[BPP_MAX_GROUPS] = {};
+    if (sort2) {
+        if (!ctx->smem_sort_ready) {
+            CK(ctx, cudaFuncSetAttribute(k_sort_count, cudaFuncAttributeMaxDynamicSharedMemorySize, BPP_SORT_SMEM_MAX));
+            CK(ctx, cudaFuncSetAttribute(k_sort_place, cudaFuncAttributeMaxDynamicSharedMemorySize, BPP_SORT_SMEM_MAX));
+            CK(ctx, cudaFuncSetAttribute(k_sort2_fine, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * SORT2_CAP * 4));
+            ctx->smem_sort_ready = true;
+        }
+        int wmax = 0;
+        for (int g = 0; g < G; g++) wmax = part[g] > wmax ? part[g] : wmax;
+        chunk_elems = (size_t)wmax * nb * chunks2;
+    } else if (smem_sort) {
+        if (!ctx->smem_sort_ready) {
+            CK(ctx, cudaFuncSetAttribute(k_sort2_fine, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * SORT2_CAP * 4));
+            CK(ctx, cudaFuncSetAttribute(k_sort_count, cudaFuncAttributeMaxDynamicSharedMemorySize, BPP_SORT_SMEM_MAX));
+            CK(ctx, cudaFuncSetAttribute(k_sort_place, cudaFuncAttributeMaxDynamicSharedMemorySize, BPP_SORT_SMEM_MAX));
+            ctx->smem_sort_ready = true;
+        }
+        for (int g = 0; g < G; g++) {
+            // about one block per SM for the group, but no chunk shorter than 2048 scalars
+            int ch = (ctx->sm_count + part[g] - 1) / part[g];
+            const int by_len = (int)((n + 2047) / 2048);
+            if (ch > by_len) ch = by_len;
+            if (ch < 1) ch = 1;
+            chunks_of[g] = ch;
+            const size_t need = (size_t)part[g] * ch * B;
+            if (need > chunk_elems) chunk_elems = need;
+        }
+    }
+    const bool need_dig = smem_sort || sort2;
+    const bool must_grow = chunk_elems > sc.cap_chunk || (need_dig && (size_t)W * ((n + 3) & ~(size_t)3) > sc.cap_dig) ||
+                           (sort2 && (size_t)W * n > sc.cap_tmp) || WB > sc.cap_wb || WB > sc.cap_offsets || WB > sc.cap_cursor || (size_t)W * n > sc.cap_entries ||
                            total_tiles * 64 > sc.cap_partials || WB * 32 > sc.cap_buckets || 2 * node_elems > sc.cap_seg ||
                            total_tiles / BPP_LONG_SPAN + 16 * (BPP_MAX_GROUPS + 1) > sc.cap_long;
     if (must_grow) CK(ctx, cudaDeviceSynchronize());  // cudaFree of scratch another in-flight MSM never touches, but be plain
@@ -545,6 +596,10 @@ static int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points
     if ((rc = grow(ctx, &sc.d_partials, &sc.cap_partials, total_tiles * 2 * 32))) return rc;
     if ((rc = grow(ctx, &sc.d_long, &sc.cap_long, total_tiles / BPP_LONG_SPAN + 16 * (BPP_MAX_GROUPS + 1)))) return rc;
     if ((rc = grow(ctx, &sc.d_buckets, &sc.cap_buckets, WB * 32))) return rc;
+    if (chunk_elems && (rc = grow(ctx, &sc.d_chunk, &sc.cap_chunk, chunk_elems))) return rc;
+    if (need_dig && (rc = grow(ctx, &sc.d_dig, &sc.cap_dig, (size_t)W * ((n + 3) & ~(size_t)3)))) return rc;
+    if (sort2 && (rc = grow(ctx, &sc.d_tmp, &sc.cap_tmp, (size_t)W * n))) return rc;
+    if (sort2 && !sc.d_binoff) CK(ctx, cudaMalloc((void **)&sc.d_binoff, 64 * 257 * 4));
     if (node_elems) {
         size_t need = 2 * node_elems;  // two ping-pong buffers in each of segS / segR
         if (need > sc.cap_seg) {
@@ -559,6 +614,7 @@ static int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points
     }
 
     const bool prof = ctx->profiling && G == 1;
+    const uint32_t ld = (uint32_t)((n + 3) & ~(size_t)3);   // row stride of the digit array
     const uint32_t *niels = pts->niels + 24 * off;
     const unsigned sb = (unsigned)((n + 255) / 256);
     uint64_t red_add = 0, red_dbl = 0;
@@ -580,7 +636,12 @@ static int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points
         CK(ctx, cudaEventRecord(ctx->ev_fork, s));
         CK(ctx, cudaStreamWaitEvent(s_sort, ctx->ev_fork, 0));
     }
-    CK(ctx, cudaMemsetAsync(sc.d_counts, 0, WB * 4, s_sort));
+    if (!need_dig) {
+        CK(ctx, cudaMemsetAsync(sc.d_counts, 0, WB * 4, s_sort));
+    } else {
+        k_sort_digits<<<sb, 256, 0, s_sort>>>(d_scalars, (uint32_t)n, ld, c, W, sc.d_dig);
+        LAUNCH_CHECK(ctx);
+    }
     CK(ctx, cudaMemsetAsync(sc.d_nlong, 0, 4 * BPP_MAX_GROUPS, s_sort));
     // Window groups from the top down: the top group's partial needs the most doublings to reach its weight, and
     // they run beside the accumulate of the groups below.  With G == 1 every stream below is the caller's.
@@ -598,15 +659,50 @@ static int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points
         // sort: recode + histogram, scan, counting-sort scatter (absolute window numbers: the recoding carry
         // ripples up from window 0)
         trace_mark(ctx, s_sort, "sort>", g);
-        k_digit_hist<<<sb, 256, 0, s_sort>>>(d_scalars, (uint32_t)n, c, w0, w0 + Wg, sc.d_counts);
-        LAUNCH_CHECK(ctx);
-        trace_mark(ctx, s_sort, "hist.", g);
-        if (prof) cudaEventRecord(ctx->ev[1], s);
-        k_window_scan<<<Wg, 1024, 0, s_sort>>>(counts, B, offsets, ends);
-        LAUNCH_CHECK(ctx);
-        if (prof) cudaEventRecord(ctx->ev[2], s);
-        k_digit_scatter<<<sb, 256, 0, s_sort>>>(d_scalars, (uint32_t)n, c, w0, w0 + Wg, sc.d_cursor, sc.d_entries);
-        LAUNCH_CHECK(ctx);
+        if (sort2) {
+            const uint32_t *dig = sc.d_dig + (size_t)w0 * ld;
+            k_sort2_count<<<dim3(chunks2, Wg), 1024, 0, s_sort>>>(dig, (uint32_t)n, ld, nb, sc.d_chunk);
+            LAUNCH_CHECK(ctx);
+            trace_mark(ctx, s_sort, "count.", g);
+            k_sort2_prefix<<<dim3(nb, Wg), 1024, 0, s_sort>>>(sc.d_chunk, chunks2, counts);
+            LAUNCH_CHECK(ctx);
+            k_sort2_binscan<<<Wg, 256, 0, s_sort>>>(counts, nb, sc.d_binoff);
+            LAUNCH_CHECK(ctx);
+            trace_mark(ctx, s_sort, "hist.", g);
+            if (prof) cudaEventRecord(ctx->ev[1], s);
+            k_sort2_split<<<dim3(chunks2, Wg), 1024, 0, s_sort>>>(dig, (uint32_t)n, ld, nb, sc.d_chunk, sc.d_binoff,
+                                                                 sc.d_tmp);
+            LAUNCH_CHECK(ctx);
+            if (prof) cudaEventRecord(ctx->ev[2], s);
+            trace_mark(ctx, s_sort, "split.", g);
+            k_sort2_fine<<<dim3(nb, Wg), 1024, 2 * SORT2_CAP * 4, s_sort>>>(sc.d_tmp, (uint32_t)n, nb, B, sc.d_binoff, entries,
+                                                                           offsets, ends);
+            LAUNCH_CHECK(ctx);
+        } else if (smem_sort) {
+            const uint32_t ch = (uint32_t)chunks_of[g], chunk_len = (uint32_t)(((n + ch - 1) / ch + 7) & ~(size_t)7);
+            k_sort_count<<<dim3(ch, Wg), 1024, B * 4, s_sort>>>(sc.d_dig + (size_t)w0 * ld, (uint32_t)n, ld, chunk_len, B, sc.d_chunk);
+            LAUNCH_CHECK(ctx);
+            k_chunk_prefix<<<(group_buckets + 255) / 256, 256, 0, s_sort>>>(sc.d_chunk, ch, B, group_buckets, counts);
+            LAUNCH_CHECK(ctx);
+            trace_mark(ctx, s_sort, "hist.", g);
+            if (prof) cudaEventRecord(ctx->ev[1], s);
+            k_window_scan<<<Wg, 1024, 0, s_sort>>>(counts, B, offsets, ends, 1);
+            LAUNCH_CHECK(ctx);
+            if (prof) cudaEventRecord(ctx->ev[2], s);
+            k_sort_place<<<dim3(ch, Wg), 1024, B * 4, s_sort>>>(sc.d_dig + (size_t)w0 * ld, (uint32_t)n, ld, chunk_len, B,
+                                                               sc.d_chunk, offsets, entries);
+            LAUNCH_CHECK(ctx);
+        } else {
+            k_digit_hist<<<sb, 256, 0, s_sort>>>(d_scalars, (uint32_t)n, c, w0, w0 + Wg, sc.d_counts);
+            LAUNCH_CHECK(ctx);
+            trace_mark(ctx, s_sort, "hist.", g);
+            if (prof) cudaEventRecord(ctx->ev[1], s);
+            k_window_scan<<<Wg, 1024, 0, s_sort>>>(counts, B, offsets, ends, 0);
+            LAUNCH_CHECK(ctx);
+            if (prof) cudaEventRecord(ctx->ev[2], s);
+            k_digit_scatter<<<sb, 256, 0, s_sort>>>(d_scalars, (uint32_t)n, c, w0, w0 + Wg, sc.d_cursor, sc.d_entries);
+            LAUNCH_CHECK(ctx);
+        }
         if (prof) cudaEventRecord(ctx->ev[3], s);
         trace_mark(ctx, s_sort, "sort.", g);
         if (G > 1) {

@@ -120,6 +120,12 @@ int bpp_set_window_bits(bpp_ctx *ctx, int c);
  * doublings to the group's weight) run on internal high-priority streams beside the accumulate of the current
  * group; the call still is stream-ordered on the caller's stream.  The result bytes do not depend on it. */
 int bpp_set_msm_groups(bpp_ctx *ctx, int groups);
+/* Sort form of the MSM: 0 = automatic (by input size), 1 = global atomics (histogram + scatter on L2 atomics),
+ * 2 = through shared memory (one block per window and chunk of scalars keeps the window's counters in shared
+ * memory; measured, not faster: both are bound by the scattered 4-byte writes of the sorted list), 3 = two passes
+ * with coalesced writes (by the high bits of the bucket number, then by the low bits inside shared memory).  The
+ * result bytes do not depend on it.  A tuning hook. */
+int bpp_set_msm_sort(bpp_ctx *ctx, int mode);
 /* Explicit window-group sizes, top group first (count <= 8; used when they sum to the number of windows of the
  * MSM, ignored otherwise; count = 0 clears).  A tuning hook like bpp_set_window_bits. */
 int bpp_set_msm_partition(bpp_ctx *ctx, const int *sizes, int count);

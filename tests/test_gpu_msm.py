@@ -290,3 +290,45 @@ def test_wait_previous_producer_consumer_loop():
         assert bytes(host[i].numpy().tobytes()) == want[i], i
     table.free()
     be.close()
+
+
+@pytest.mark.parametrize("mode", [2, 3])
+@pytest.mark.parametrize("c,groups", [(16, 1), (16, 4), (15, 2), (13, 2), (12, 1), (11, 3), (8, 1), (5, 8), (4, 1), (0, 0)])
+def test_sort_forms_match_oracle(backend, c, groups, mode):
+    """bpp_set_msm_sort: the sort through shared memory (2: per-chunk histograms, chunk prefixes, shared-memory cursors)
+    and the two-pass sort with coalesced writes (3: coarse bins, then the low bits inside shared memory) against the C
+    restatement and against the global-atomic sort, on random + skewed + zero + extreme scalars (hot buckets overflow
+    the shared-memory capacity of a coarse bin; all-ones windows exercise the recoding carry across windows)."""
+    import numpy as np
+    from oracle import cref
+    n = 40000 + 1234
+    rs = np.random.RandomState(3100 + c)
+    blobs = rs.randint(0, 256, size=(n, 64), dtype=np.uint8)
+    sc = rs.randint(0, 256, size=(n, 32), dtype=np.uint8)
+    sc[:, 31] &= 0x0F
+    sc[100:1600] = sc[7]               # hot buckets in every window
+    sc[21000:36000] = sc[8]            # 15 000 equal scalars: a coarse bin larger than its shared-memory staging
+    sc[2000:2300, 2:] = 0              # only the lowest windows populated
+    sc[2300:2400] = 0                  # zero scalars
+    sc[2400:2500, :31] = 0xFF          # runs of ones: carries ripple through every window
+    sc[2500:2600, :16] = 0x80          # windows equal to `half` at c = 8 / 16: the carry look-back continues downwards
+    sc[2500:2600, 0] = 0x81
+    sc[2600:2700, :] = 0
+    sc[2600:2700, 1::2] = 0x80         # 0x8000 in every 16-bit window: digits exactly `half`, no carry
+    sc[2600:2700, 31] = 0x08
+    table = backend.points_from_uniform(blobs.tobytes())
+    backend.set_window_bits(c)
+    backend.set_msm_groups(groups)
+    try:
+        backend.set_msm_sort(mode)
+        got = backend.vartime_multiscalar_mul(sc.tobytes(), table)
+        again = backend.vartime_multiscalar_mul(sc.tobytes(), table)
+        backend.set_msm_sort(1)
+        atomics = backend.vartime_multiscalar_mul(sc.tobytes(), table)
+    finally:
+        backend.set_msm_sort(0)
+        backend.set_window_bits(0)
+        backend.set_msm_groups(0)
+        table.free()
+    assert got == again == atomics
+    assert got == cref.msm(sc.tobytes(), cref.from_uniform(blobs.tobytes()))
