@@ -21,7 +21,7 @@ SYMBOLS = [
     "bpp_inner_product", "bpp_hadamard_V", "bpp_vm_mult", "bpp_mv_mult", "bpp_exp_iter", "bpp_scalar_powers",
     "bpp_scalar_exp", "bpp_scalar_invert", "bpp_scalar_from_wide", "bpp_scalar_reduce",
     "bpp_vecpoly3_special_inner_product", "bpp_vecpoly3_eval", "bpp_poly6_eval",
-    "bpp_circuit_create", "bpp_circuit_free", "bpp_gens_create", "bpp_gens_free", "bpp_acproof_proof_len", "bpp_acproof_proof_len_mode",
+    "bpp_circuit_create", "bpp_circuit_free", "bpp_gens_create", "bpp_gens_free", "bpp_acproof_proof_len", "bpp_acproof_proof_len_mode", "bpp_acproof_wire_len", "bpp_acproof_to_wire", "bpp_acproof_from_wire",
     "bpp_acproof_prove_batch", "bpp_acproof_verify_batch", "bpp_acp_batch_create", "bpp_acp_batch_free",
     "bpp_acp_batch_upload_witness", "bpp_acp_batch_commit", "bpp_acp_batch_prove", "bpp_acp_batch_download_proofs",
     "bpp_acp_batch_upload_proofs", "bpp_acp_batch_verify", "bpp_acp_batch_download_accept",
@@ -109,6 +109,10 @@ def load() -> ctypes.CDLL:
     lib.bpp_gens_free.argtypes = [vp, vp]
     lib.bpp_gens_free.restype = None
     lib.bpp_acproof_proof_len.argtypes = [sz]
+    lib.bpp_acproof_wire_len.restype = sz
+    lib.bpp_acproof_wire_len.argtypes = [sz, c.c_int]
+    lib.bpp_acproof_to_wire.argtypes = [sz, c.c_int, sz, u8p, c.c_char_p]
+    lib.bpp_acproof_from_wire.argtypes = [sz, c.c_int, sz, u8p, sz, c.c_char_p, c.c_char_p]
     lib.bpp_acproof_proof_len.restype = sz
     lib.bpp_acproof_proof_len_mode.argtypes = [sz, c.c_int]
     lib.bpp_acproof_proof_len_mode.restype = sz

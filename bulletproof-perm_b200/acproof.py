@@ -197,3 +197,40 @@ def transcript_script(backend, records) -> bytes:
     out = ctypes.create_string_buffer(max(out_len, 1))
     backend._check(backend._lib.bpp_transcript_script(backend._ctx, script, len(script), out, out_len))
     return out.raw[:out_len]
+
+
+# ---- proof wire format: byte handling only, no device and no Backend needed ---------------
+WIRE_VERSION = {0: 0x80, 1: 0x81, 2: 0x00}   # mode 2 = bulletproofs 4.0.0 R1CSProof::to_bytes, one-phase
+
+
+def wire_len(n: int, mode="fixed") -> int:
+    from . import _lib
+    return _lib.load().bpp_acproof_wire_len(n, _MODES[mode])
+
+
+def to_wire(proofs: bytes, n: int, count: int, mode="fixed") -> bytes:
+    """count proofs (the library's proof bytes) -> count wire records (version byte + proof)."""
+    from . import _lib
+    lib = _lib.load()
+    if len(proofs) != count * proof_len(n, mode):
+        raise ValueError("proofs: wrong length for this circuit")
+    out = ctypes.create_string_buffer(count * wire_len(n, mode))
+    rc = lib.bpp_acproof_to_wire(n, _MODES[mode], count, proofs, out)
+    if rc:
+        raise _lib.BppError(rc, lib.bpp_strerror(rc).decode())
+    return out.raw
+
+
+def from_wire(wire: bytes, n: int, count: int, mode="fixed"):
+    """-> (proof bytes, status bytes): status 1 = ProofError::FormatError (wrong version byte or a non-canonical
+    scalar; that proof's bytes are zeroed).  Raises on a record length that does not match the circuit."""
+    from . import _lib
+    lib = _lib.load()
+    if count == 0 or len(wire) % count:
+        raise _lib.BppError(-4, lib.bpp_strerror(-4).decode())
+    out = ctypes.create_string_buffer(count * proof_len(n, mode))
+    status = ctypes.create_string_buffer(count)
+    rc = lib.bpp_acproof_from_wire(n, _MODES[mode], count, wire, len(wire) // count, out, status)
+    if rc:
+        raise _lib.BppError(rc, lib.bpp_strerror(rc).decode())
+    return out.raw, status.raw

@@ -231,6 +231,63 @@ extern "C" size_t bpp_acproof_proof_len_mode(size_t n, int mode) {
     return 32 * (13 + 2 * (size_t)acp_log2(acp_next_pow2((uint32_t)n)));
 }
 
+// ---- proof wire format -----------------------------------------------------------------
+// The reference defines no serialisation.  Mode 2 (`fixed`) adopts bulletproofs 4.0.0 R1CSProof::to_bytes for a
+// one-phase proof (r1cs/proof.rs): version byte 0 | A_I1 A_O1 S1 | T_1 T_3 T_4 T_5 T_6 | t_x t_x_blinding e_blinding |
+// L_0 R_0 .. | a b - i.e. the version byte followed by the library's own proof bytes.  Modes 0 and 1 (l, r in the
+// clear: no upstream format) use the version bytes 0x80 / 0x81 the same way.  from_wire is the parser a batch
+// verifier runs first: like R1CSProof::from_bytes it rejects (FormatError) a wrong version byte, a length that is
+// not 1 + 32k or does not match the circuit, and any scalar field that is not canonical (>= l); points stay
+// compressed - an invalid encoding is a VerificationError of the verifier, not a format error.  Pure byte handling:
+// no device work, callable without a context.
+static const uint8_t ACP_WIRE_VERSION[3] = {0x80, 0x81, 0x00};
+
+static bool acp_scalar_is_canonical(const uint8_t *s) {   // little-endian s < l = 2^252 + 27742317777372353535851937790883648493
+    static const uint8_t L[32] = {0xed, 0xd3, 0xf5, 0x5c, 0x1a, 0x63, 0x12, 0x58, 0xd6, 0x9c, 0xf7, 0xa2, 0xde, 0xf9, 0xde, 0x14,
+                                  0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0x10};
+    for (int i = 31; i >= 0; i--) {
+        if (s[i] < L[i]) return true;
+        if (s[i] > L[i]) return false;
+    }
+    return false;
+}
+
+extern "C" size_t bpp_acproof_wire_len(size_t n, int mode) { return 1 + bpp_acproof_proof_len_mode(n, mode); }
+
+extern "C" int bpp_acproof_to_wire(size_t n, int mode, size_t count, const uint8_t *proofs, uint8_t *wire_out) {
+    if (mode < 0 || mode > 2 || (count && (!proofs || !wire_out))) return BPP_ERR_INVALID_ARG;
+    const size_t plen = bpp_acproof_proof_len_mode(n, mode);
+    for (size_t p = 0; p < count; p++) {
+        wire_out[p * (plen + 1)] = ACP_WIRE_VERSION[mode];
+        memcpy(wire_out + p * (plen + 1) + 1, proofs + p * plen, plen);
+    }
+    return BPP_OK;
+}
+
+// wire: count records of wire_len bytes each.  status[p] = 0 ok, 1 format error (that proof's bytes in proofs_out are
+// zeroed, so a verifier fed with them rejects).  Returns BPP_ERR_LENGTH_MISMATCH if wire_len itself is not the
+// circuit's record length (nothing is parsed then).
+extern "C" int bpp_acproof_from_wire(size_t n, int mode, size_t count, const uint8_t *wire, size_t wire_len,
+                                     uint8_t *proofs_out, uint8_t *status) {
+    if (mode < 0 || mode > 2 || (count && (!wire || !proofs_out || !status))) return BPP_ERR_INVALID_ARG;
+    const size_t plen = bpp_acproof_proof_len_mode(n, mode);
+    if (wire_len != plen + 1) return BPP_ERR_LENGTH_MISMATCH;
+    const size_t words = plen / 32, lg = mode == 2 ? (words - 13) / 2 : 0;
+    for (size_t p = 0; p < count; p++) {
+        const uint8_t *rec = wire + p * wire_len, *body = rec + 1;
+        bool ok = rec[0] == ACP_WIRE_VERSION[mode];
+        for (size_t i = 8; ok && i < words; i++) {
+            // scalar fields: modes 0/1 everything after the 8 points; mode 2 t_x, t_x_blinding, e_blinding and a, b
+            const bool is_scalar = mode != 2 || i < 11 || i >= 11 + 2 * lg;
+            if (is_scalar && !acp_scalar_is_canonical(body + 32 * i)) ok = false;
+        }
+        status[p] = ok ? 0 : 1;
+        if (ok) memcpy(proofs_out + p * plen, body, plen);
+        else memset(proofs_out + p * plen, 0, plen);
+    }
+    return BPP_OK;
+}
+
 extern "C" void bpp_acp_batch_free(bpp_acp_batch *b) {
     if (!b) return;
     cudaSetDevice(b->ctx->device);

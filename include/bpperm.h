@@ -197,6 +197,17 @@ void bpp_circuit_free(bpp_ctx *ctx, bpp_circuit *c);
 int bpp_gens_create(bpp_ctx *ctx, const uint8_t g[32], const uint8_t h[32], const uint8_t *G, const uint8_t *H, size_t n,
                     int window_bits, bpp_gens **out);
 void bpp_gens_free(bpp_ctx *ctx, bpp_gens *g);
+/* Proof wire format (the reference defines none).  A record is one version byte followed by the
+ * proof bytes above.  Mode 2: version 0 - the layout of bulletproofs 4.0.0 R1CSProof::to_bytes for a one-phase proof
+ * (A_I1 A_O1 S1 | T_1 T_3 T_4 T_5 T_6 | t_x t_x_blinding e_blinding | L_0 R_0 .. | a b).  Modes 0 / 1: versions
+ * 0x80 / 0x81.  from_wire is the parser a verifier runs first: like R1CSProof::from_bytes it flags (status 1 =
+ * ProofError::FormatError) a wrong version byte and any non-canonical scalar field; points stay compressed, an
+ * invalid point encoding is the verifier's VerificationError.  A wire_len that does not match the circuit returns
+ * BPP_ERR_LENGTH_MISMATCH.  Byte handling only: no device work, no context. */
+size_t bpp_acproof_wire_len(size_t n, int mode);
+int bpp_acproof_to_wire(size_t n, int mode, size_t count, const uint8_t *proofs, uint8_t *wire_out);
+int bpp_acproof_from_wire(size_t n, int mode, size_t count, const uint8_t *wire, size_t wire_len, uint8_t *proofs_out,
+                          uint8_t *status);
 size_t bpp_acproof_proof_len(size_t n);                  /* modes 0 and 1: 32 * (11 + 2n) */
 size_t bpp_acproof_proof_len_mode(size_t n, int mode);    /* mode 2: 32 * (13 + 2 lg n') */
 /* One-call host forms: host buffers in, host buffers out (all copies included). */

@@ -33,6 +33,25 @@ extern "C" {
     pub fn bpp_msm_vartime_host(ctx: *mut bpp_ctx, scalars: *const u8, n_scalars: usize, fmt: c_int, pts: *const u8,
                                 n_points: usize, out_compressed: *mut u8) -> c_int;
 
+    // device-pointer forms: scalars / results already in HBM (pointers from the caller's CUDA allocator)
+    pub fn bpp_set_stream(ctx: *mut bpp_ctx, cuda_stream: *mut core::ffi::c_void) -> c_int;
+    pub fn bpp_msm_vartime_dev(ctx: *mut bpp_ctx, d_scalars: *const core::ffi::c_void, points: *const bpp_points, off: usize,
+                               n: usize, d_out: *mut core::ffi::c_void) -> c_int;
+    // throughput form: submit without joining, up to two MSMs in flight; results valid after bpp_msm_wait
+    pub fn bpp_msm_submit_dev(ctx: *mut bpp_ctx, d_scalars: *const core::ffi::c_void, points: *const bpp_points, off: usize,
+                              n: usize, d_out: *mut core::ffi::c_void) -> c_int;
+    pub fn bpp_msm_wait(ctx: *mut bpp_ctx) -> c_int;
+    pub fn bpp_msm_wait_previous(ctx: *mut bpp_ctx) -> c_int;
+    pub fn bpp_msm_partial_dev(ctx: *mut bpp_ctx, d_scalars: *const core::ffi::c_void, points: *const bpp_points, off: usize,
+                               n: usize, d_partial: *mut core::ffi::c_void) -> c_int;
+    pub fn bpp_points_sum_compress_dev(ctx: *mut bpp_ctx, d_partials: *const core::ffi::c_void, g: usize,
+                                       d_out32: *mut core::ffi::c_void) -> c_int;
+    // result-neutral tuning hooks
+    pub fn bpp_set_window_bits(ctx: *mut bpp_ctx, c: c_int) -> c_int;
+    pub fn bpp_set_msm_groups(ctx: *mut bpp_ctx, groups: c_int) -> c_int;
+    pub fn bpp_set_msm_partition(ctx: *mut bpp_ctx, sizes: *const c_int, count: c_int) -> c_int;
+    pub fn bpp_set_msm_sort(ctx: *mut bpp_ctx, mode: c_int) -> c_int;
+
     pub fn bpp_inner_product(ctx: *mut bpp_ctx, a: *const u8, la: usize, b: *const u8, lb: usize, out: *mut u8) -> c_int;
     pub fn bpp_hadamard_V(ctx: *mut bpp_ctx, a: *const u8, la: usize, b: *const u8, lb: usize, out: *mut u8) -> c_int;
     pub fn bpp_vm_mult(ctx: *mut bpp_ctx, a: *const u8, la: usize, b: *const u8, rows: usize, cols: usize, out: *mut u8) -> c_int;
