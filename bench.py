@@ -154,7 +154,7 @@ def synth_shuffle_batch(k: int, count: int, rank: int):
     return b"".join(aL), b"".join(aR), b"".join(aO), g.tobytes(), b"".join(vv), seeds.tobytes()
 
 
-FB_WINDOW_BITS = 16   # fixed-base table window: 16 windows x 32768 entries x 96 B = 50 MB per generator
+FB_WINDOW_BITS = int(os.environ.get("BPP_FB_WINDOW", "16"))   # fixed-base table window: 16 windows x 32768 entries x 96 B = 50 MB per generator
 
 
 def shuffle_setup(be, k: int, window_bits: int = FB_WINDOW_BITS):
@@ -472,7 +472,7 @@ def run_ours(args):
             for t in th:
                 t.join()
 
-        res2_steps = max(2, args.steps + (args.steps & 1))   # an even number of steps: both lanes do the same work
+        res2_steps = args.steps                  # exactly K steps, split over the two lanes (K odd: 1 more on lane 0)
         res2_warm = max(2, args.warmup)
         l2_0 = sum(ln["be"].launch_count for ln in lanes)
         ms_res2 = timed_block(run_resident2, res2_steps, res2_warm, [ln["stream"] for ln in lanes])
@@ -533,7 +533,7 @@ def run_ours(args):
                            "mode": "reference-fixed (SURVEY A.3: the reference's own flow never verifies)",
                            "inputs": "deck 1..52, random permutation and challenge value per proof, uniform blindings, "
                                      "generators = from_uniform_bytes(seeded bytes); prover RNG = ChaCha20 per proof",
-                           "tables": f"fixed-base window tables, c = {FB_WINDOW_BITS}: {(2 * n + 2) * 16 * 32768 * 96 / 2**30:.1f} GiB in HBM, "
+                           "tables": f"fixed-base window tables, c = {FB_WINDOW_BITS}: {(2 * n + 2) * ((256 + FB_WINDOW_BITS - 1) // FB_WINDOW_BITS) * 2 ** (FB_WINDOW_BITS - 1) * 96 / 2**30:.1f} GiB in HBM, "
                                      "built once per generator set (not timed)",
                            "verify": "one random-linear-combination MSM over the batch's decompressed points + shared generators "
                                      "(Pippenger), per-proof kernels only on failure; accept bytes are per proof",
@@ -744,7 +744,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="both", choices=["shuffle", "msm", "both"])

@@ -168,7 +168,7 @@ extern "C" int bpp_gens_create(bpp_ctx *ctx, const uint8_t g[32], const uint8_t 
                                size_t n, int window_bits, bpp_gens **out) {
     if (!ctx || !out || !g || !h || !G || !H || n == 0) return BPP_ERR_INVALID_ARG;
     if (window_bits == 0) window_bits = 8;
-    if (window_bits < 4 || window_bits > 16) return BPP_ERR_INVALID_ARG;
+    if (window_bits < 4 || window_bits > 20) return BPP_ERR_INVALID_ARG;   // 2^(c-1) entries x 96 B per (generator, window)
     *out = nullptr;
     std::vector<uint8_t> all(32 * (2 * n + 2));
     memcpy(&all[0], g, 32);

@@ -193,7 +193,8 @@ int bpp_circuit_create(bpp_ctx *ctx, size_t n, size_t Q, size_t m, const uint32_
                        const uint32_t *constraint, const uint8_t *coeff, const uint8_t *c_vec, bpp_circuit **out);
 void bpp_circuit_free(bpp_ctx *ctx, bpp_circuit *c);
 /* g_base, h_base, G_vec[n], H_vec[n] (circuit_lib.rs:59-65) as compressed points; builds the fixed-base
- * window tables (window_bits 4..16, 0 = default 8) used by every commitment of the protocol. */
+ * window tables (window_bits 4..20, 0 = default 8; 2^(c-1) entries x 96 B per generator and window: a memory/throughput
+ * dial - c = 16: 48 MiB per generator, c = 18: 180 MiB, c = 19: 336 MiB) used by every commitment of the protocol. */
 int bpp_gens_create(bpp_ctx *ctx, const uint8_t g[32], const uint8_t h[32], const uint8_t *G, const uint8_t *H, size_t n,
                     int window_bits, bpp_gens **out);
 void bpp_gens_free(bpp_ctx *ctx, bpp_gens *g);
