@@ -329,6 +329,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":   # keep NCCL's version banner off stdout (one JSON line)
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_version_%h_%p.log")
         dist.init_process_group("nccl", device_id=dev)
     be = bpperm_b200.Backend(local)
     stream = torch.cuda.current_stream(dev)
@@ -599,6 +601,15 @@ def run_ours(args):
         d_outs = [torch.zeros(160, dtype=torch.uint8, device=dev) for _ in range(2)]
 
         def msm_submitted(cnt, first):
+            if world > 1:   # sharded: the 128-byte all-gather + sum of step i-1 beside the MSM of step i
+                for i in range(cnt):
+                    smsm.submit(d_sets[(first + i) % n_sets], i & 1)
+                    smsm.wait_previous()
+                    if i:
+                        smsm.combine((i - 1) & 1)
+                smsm.wait()
+                smsm.combine((cnt - 1) & 1)
+                return
             for i in range(cnt):
                 be.msm_submit_dev(d_sets[(first + i) % n_sets].data_ptr(), table, 0, n, d_outs[i & 1].data_ptr())
             be.msm_wait()
@@ -610,17 +621,15 @@ def run_ours(args):
             samp2.start()
         ms_single = timed(msm_resident, msm_steps, args.warmup)
         launches = (be.launch_count - l0) * msm_steps // (msm_steps + args.warmup)
-        if world == 1:
-            ms_res = timed_block(msm_submitted, msm_steps, args.warmup)
-            # the submitted results are the single-call results
-            want = []
-            for i in range(2):
-                be.msm_dev(d_sets[(args.warmup + msm_steps - 2 + i) % n_sets].data_ptr(), table, 0, n, d_out.data_ptr())
-                want.append(bytes(d_out[:32].cpu().numpy().tobytes()))
-            got = [bytes(d_outs[(msm_steps - 2 + i) & 1][:32].cpu().numpy().tobytes()) for i in range(2)]
-            assert got == want, "submitted MSM results differ from the single-call results"
-        else:
-            ms_res = ms_single
+        ms_res = timed_block(msm_submitted, msm_steps, args.warmup)
+        # the submitted results are the single-call results
+        want = []
+        for i in range(2):
+            msm_once(d_sets[(args.warmup + msm_steps - 2 + i) % n_sets])
+            want.append(bytes(d_out[:32].cpu().numpy().tobytes()))
+        sub_outs = d_outs if world == 1 else [smsm._slots()[k][2] for k in range(2)]
+        got = [bytes(sub_outs[(msm_steps - 2 + i) & 1][:32].cpu().numpy().tobytes()) for i in range(2)]
+        assert got == want, "submitted MSM results differ from the single-call results"
         clocks2 = samp2.stop() if (rank == 0 and args.workload == "msm") else None
         ms_e2e_serial = timed(msm_e2e, msm_steps, args.warmup)
         # e2e, double buffered: the next step's scalars travel on a copy stream while this step's MSM runs
@@ -699,7 +708,9 @@ def run_ours(args):
                 "n_gpus": world, "steps": msm_steps, "ms_per_step": ms_res / msm_steps, "scaling": "weak",
                 "mode": ("throughput: one bpp_msm_submit_dev per step, two MSMs in flight (the tail of one beside the sort "
                          "and accumulate of the next), one bpp_msm_wait before the closing event; results checked against "
-                         "the single-call results") if world == 1 else "one bpp_msm_partial_dev + all-gather + sum per step",
+                         "the single-call results") if world == 1 else
+                        ("throughput, sharded: bpp_msm_submit_partial_dev per step on every rank (two in flight), the 128-byte "
+                         "all-gather + sum of step i-1 beside the MSM of step i; results checked against the single-call results"),
                 "single_call": {"value": total_points * msm_steps / (ms_single * 1e-3), "ms_per_step": ms_single / msm_steps,
                                 "note": "bpp_msm_vartime_dev one call at a time: the caller's stream joins every MSM"},
                 "config": {"workload": f"ristretto255 vartime MSM, 2^{args.log_n} points per GPU (BASELINE configs[4])",

@@ -217,6 +217,10 @@ class Backend:
         self._check(self._lib.bpp_msm_submit_dev(self._ctx, ctypes.c_void_p(d_scalars), points._h, off, n,
                                                  ctypes.c_void_p(d_out)))
 
+    def msm_submit_partial_dev(self, d_scalars: int, points: Points, off: int, n: int, d_partial: int):
+        self._check(self._lib.bpp_msm_submit_partial_dev(self._ctx, ctypes.c_void_p(d_scalars), points._h, off, n,
+                                                         ctypes.c_void_p(d_partial)))
+
     def msm_wait(self):
         self._check(self._lib.bpp_msm_wait(self._ctx))
 

@@ -821,6 +821,14 @@ extern "C" int bpp_msm_submit_dev(bpp_ctx *ctx, const void *d_scalars, const bpp
     return msm_enqueue(ctx, (const uint32_t *)d_scalars, points, off, n, (uint8_t *)d_out, 1, false);
 }
 
+extern "C" int bpp_msm_submit_partial_dev(bpp_ctx *ctx, const void *d_scalars, const bpp_points *points, size_t off,
+                                          size_t n, void *d_partial) {
+    if (!ctx || !d_scalars || !points || !d_partial || n == 0) return BPP_ERR_INVALID_ARG;
+    if (off + n > points->n) return BPP_ERR_LENGTH_MISMATCH;
+    CK(ctx, cudaSetDevice(ctx->device));
+    return msm_enqueue(ctx, (const uint32_t *)d_scalars, points, off, n, (uint8_t *)d_partial, 0, false);
+}
+
 extern "C" int bpp_msm_wait(bpp_ctx *ctx) {
     if (!ctx) return BPP_ERR_INVALID_ARG;
     CK(ctx, cudaSetDevice(ctx->device));

@@ -51,3 +51,38 @@ class ShardedMsm:
         dist.all_gather_into_tensor(self.d_all, self.d_part)
         self.be.points_sum_compress_dev(self.d_all.data_ptr(), self.world, self.d_out.data_ptr())
         return self.d_out
+
+    # Throughput form for a sequence of independent MSMs (two in flight per rank, bpp_msm_submit_*):
+    #     for i, sc in enumerate(sets): m.submit(sc, i & 1); m.wait_previous(); (i > 0) and m.combine((i - 1) & 1)
+    #     m.wait(); m.combine(last & 1)
+    # The all-gather of step i-1 runs on the caller's stream while step i's MSM runs on the library's streams.
+    def _slots(self):
+        if not hasattr(self, "_slot_bufs"):
+            dev = self.d_out.device
+            self._slot_bufs = [(torch.zeros(self.PARTIAL_BYTES, dtype=torch.uint8, device=dev),
+                                torch.zeros(self.world * self.PARTIAL_BYTES, dtype=torch.uint8, device=dev),
+                                torch.zeros(160, dtype=torch.uint8, device=dev)) for _ in range(2)]
+        return self._slot_bufs
+
+    def submit(self, d_scalars: torch.Tensor, slot: int):
+        part, _, out = self._slots()[slot]
+        n = len(self.table)
+        if self.world == 1:
+            self.be.msm_submit_dev(d_scalars.data_ptr(), self.table, 0, n, out.data_ptr())
+        else:
+            self.be.msm_submit_partial_dev(d_scalars.data_ptr(), self.table, 0, n, part.data_ptr())
+
+    def wait_previous(self):
+        self.be.msm_wait_previous()
+
+    def wait(self):
+        self.be.msm_wait()
+
+    def combine(self, slot: int) -> torch.Tensor:
+        """After the slot's MSM has been waited for: all-gather + sum (nothing to do on one GPU).  Returns the
+        slot's 160-byte output buffer (first 32 bytes = the compressed result)."""
+        part, allp, out = self._slots()[slot]
+        if self.world > 1:
+            dist.all_gather_into_tensor(allp, part)
+            self.be.points_sum_compress_dev(allp.data_ptr(), self.world, out.data_ptr())
+        return out

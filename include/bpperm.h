@@ -102,6 +102,10 @@ int bpp_msm_vartime_dev(bpp_ctx *ctx, const void *d_scalars, const bpp_points *p
  * queued on the caller's stream before the submit is complete before the MSM reads d_scalars. */
 int bpp_msm_submit_dev(bpp_ctx *ctx, const void *d_scalars, const bpp_points *points, size_t off, size_t n,
                        void *d_out);
+/* submitted form of bpp_msm_partial_dev (128-byte extended point, not compressed): the sharded multi-GPU MSM in
+ * throughput form - submit(i), wait_previous, all-gather + bpp_points_sum_compress_dev of step i-1. */
+int bpp_msm_submit_partial_dev(bpp_ctx *ctx, const void *d_scalars, const bpp_points *points, size_t off, size_t n,
+                               void *d_partial);
 int bpp_msm_wait(bpp_ctx *ctx);
 /* Like bpp_msm_wait, but the MSM submitted last stays in flight: after submit(i), the results of every MSM up to
  * i-1 are valid - the form a producer/consumer loop uses (submit i, wait_previous, consume i-1). */
