@@ -329,8 +329,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":   # keep NCCL's version banner off stdout (one JSON line)
-            os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_version_%h_%p.log")
+        # NCCL prints its version banner (and warnings) to stdout at NCCL_DEBUG=VERSION/WARN: keep stdout to the one
+        # JSON line; INFO/TRACE runs (someone looking for NVLS) are left alone
+        if os.environ.get("NCCL_DEBUG", "WARN").upper() in ("VERSION", "WARN"):
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_%h_%p.log")
         dist.init_process_group("nccl", device_id=dev)
     be = bpperm_b200.Backend(local)
     stream = torch.cuda.current_stream(dev)
