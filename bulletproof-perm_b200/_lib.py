@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbpperm_cuda.so")
+# BPPERM_LIB: another build of the same library (tuning variants, tools/build_variants.sh); never a fallback
+LIB_PATH = os.environ.get("BPPERM_LIB") or os.path.join(_HERE, "libbpperm_cuda.so")
 
 # every symbol include/bpperm.h declares (tests check that the .so exports all of them)
 SYMBOLS = [

@@ -150,8 +150,12 @@ struct fb_shape {
 struct fb_consts {
     uint32_t K[8];  // sum_{w < Wn-1} half * 2^(c w)
 };
+#ifndef FB_THREADS
 #define FB_THREADS 128
+#endif
+#ifndef FB_GROUP
 #define FB_GROUP 4  // windows handled per work item
+#endif
 
 __global__ void __launch_bounds__(FB_THREADS) k_fb_msm(const uint32_t *__restrict__ blk, acp_layout lay, fb_shape sh,
                                                        const uint32_t *__restrict__ table, int c, int Wn, fb_consts kc,

@@ -71,6 +71,11 @@ extern "C" {
                            window_bits: c_int, out: *mut *mut bpp_gens) -> c_int;
     pub fn bpp_gens_free(ctx: *mut bpp_ctx, g: *mut bpp_gens);
     pub fn bpp_acproof_proof_len_mode(n: usize, mode: c_int) -> usize;
+    // wire records: version byte + proof bytes (mode 2 = bulletproofs R1CSProof::to_bytes, one-phase); no context needed
+    pub fn bpp_acproof_wire_len(n: usize, mode: c_int) -> usize;
+    pub fn bpp_acproof_to_wire(n: usize, mode: c_int, count: usize, proofs: *const u8, wire_out: *mut u8) -> c_int;
+    pub fn bpp_acproof_from_wire(n: usize, mode: c_int, count: usize, wire: *const u8, wire_len: usize,
+                                 proofs_out: *mut u8, status: *mut u8) -> c_int;
     pub fn bpp_acproof_prove_batch(ctx: *mut bpp_ctx, cir: *const bpp_circuit, gens: *const bpp_gens, mode: c_int, count: usize,
                                    a_l: *const u8, a_r: *const u8, a_o: *const u8, gamma: *const u8, seeds: *const u8,
                                    label: *const u8, label_len: usize, proofs_out: *mut u8) -> c_int;

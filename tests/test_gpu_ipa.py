@@ -195,3 +195,33 @@ def test_batch_verification_with_one_percent_corrupted_proofs_matches_the_oracle
         batch.verify(b"\x21" * 32)
         assert list(batch.download_accept()) == want, rlc
     batch.free()
+
+
+def test_wire_records_parse_then_verify(backend):
+    """f-2 end to end: proofs -> wire records -> parser -> verifier.  A record with a non-canonical scalar is a format
+    error (flagged by from_wire, rejected by the verifier on its zeroed bytes); a record with an invalid point encoding
+    parses and is rejected by the verifier; a record with a wrong version byte is a format error; the others accept.
+    The decisions equal the oracle's (from_bytes + verify)."""
+    from bpperm_b200 import acproof as G
+    from oracle import wire as W
+    core, prover, V, cir, gens, inst = _setup(backend, 5, 91)
+    n = core["n"]
+    seeds = [bytes([40 + i]) * 32 for i in range(5)]
+    B = len(seeds)
+    proofs = G.prove_batch(backend, cir, gens, _sb(prover["a_L"]) * B, _sb(prover["a_R"]) * B, _sb(prover["a_O"]) * B,
+                           _sb(prover["gamma"]) * B, b"".join(seeds), B, "fixed")
+    plen, wlen = G.proof_len(n, "fixed"), G.wire_len(n, "fixed")
+    recs = bytearray(G.to_wire(proofs, n, B, "fixed"))
+    assert len(recs) == B * wlen and wlen == plen + 1
+    recs[1 * wlen + 1 + 32 * 9:1 * wlen + 1 + 32 * 10] = (L + 5).to_bytes(32, "little")   # proof 1: t_x_blinding >= l
+    recs[2 * wlen + 1:2 * wlen + 33] = b"\xff" * 32                                      # proof 2: A_I not a valid encoding
+    recs[3 * wlen] = 0x01                                                                 # proof 3: unknown version
+    back, status = G.from_wire(bytes(recs), n, B, "fixed")
+    assert list(status) == [0, 1, 0, 1, 0]
+    Vc = b"".join(R.compress(p) for p in V)
+    acc = list(G.verify_batch(backend, cir, gens, back, Vc * B, B, "fixed"))
+    assert acc == [1, 0, 0, 0, 1]
+    for i in range(B):
+        pb = W.from_bytes(bytes(recs[i * wlen:(i + 1) * wlen]), n, 2)
+        want = 0 if pb is None else int(bool(ipa.verify(core, V, pb)))
+        assert acc[i] == want, i

@@ -332,3 +332,32 @@ def test_sort_forms_match_oracle(backend, c, groups, mode):
         table.free()
     assert got == again == atomics
     assert got == cref.msm(sc.tobytes(), cref.from_uniform(blobs.tobytes()))
+
+
+def test_submitted_partials_sum_to_the_full_result(backend):
+    """bpp_msm_submit_partial_dev (the sharded multi-GPU form, here two shards on one GPU): the two submitted
+    partials of a split MSM, summed by bpp_points_sum_compress_dev, give the bytes of the one-call MSM."""
+    import numpy as np
+    import torch
+    n = 1 << 15
+    rs = np.random.RandomState(515)
+    table = backend.points_from_uniform(rs.randint(0, 256, size=(n, 64), dtype=np.uint8).tobytes())
+    sc = _np_scalars(n, 616)
+    want = backend.vartime_multiscalar_mul(sc.tobytes(), table)
+    dev = torch.device("cuda:0")
+    d_sc = torch.from_numpy(sc).to(dev)
+    parts = torch.zeros(2, 128, dtype=torch.uint8, device=dev)
+    out32 = torch.zeros(32, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    h = n // 2 + 37
+    backend.set_msm_groups(3)
+    try:
+        backend.msm_submit_partial_dev(d_sc.data_ptr(), table, 0, h, parts[0].data_ptr())
+        backend.msm_submit_partial_dev(d_sc[h:].data_ptr(), table, h, n - h, parts[1].data_ptr())
+        backend.msm_wait()
+        backend.points_sum_compress_dev(parts.data_ptr(), 2, out32.data_ptr())
+        backend.synchronize()
+    finally:
+        backend.set_msm_groups(0)
+    assert bytes(out32.cpu().numpy().tobytes()) == want
+    table.free()
