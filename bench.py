@@ -312,7 +312,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _emit(line)
     return 0
 
 
@@ -329,10 +329,6 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL prints its version banner (and warnings) to stdout at NCCL_DEBUG=VERSION/WARN: keep stdout to the one
-        # JSON line; INFO/TRACE runs (someone looking for NVLS) are left alone
-        if os.environ.get("NCCL_DEBUG", "WARN").upper() in ("VERSION", "WARN"):
-            os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_%h_%p.log")
         dist.init_process_group("nccl", device_id=dev)
     be = bpperm_b200.Backend(local)
     stream = torch.cuda.current_stream(dev)
@@ -748,10 +744,19 @@ def run_ours(args):
                              "dtype": "u32 (8x32-bit limbs, IMAD.WIDE.U32)", "data": "synthetic"})
 
     if rank == 0:
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+_REAL_STDOUT = None
+
+
+def _emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -767,6 +772,12 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    # The contract is ONE JSON line on stdout.  Libraries write to file descriptor 1 behind Python's back (NCCL prints
+    # its version banner there): keep the real stdout aside for the JSON line and point fd 1 at stderr meanwhile.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
