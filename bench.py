@@ -599,14 +599,8 @@ def run_ours(args):
         d_outs = [torch.zeros(160, dtype=torch.uint8, device=dev) for _ in range(2)]
 
         def msm_submitted(cnt, first):
-            if world > 1:   # sharded: the 128-byte all-gather + sum of step i-1 beside the MSM of step i
-                for i in range(cnt):
-                    smsm.submit(d_sets[(first + i) % n_sets], i & 1)
-                    smsm.wait_previous()
-                    if i:
-                        smsm.combine((i - 1) & 1)
-                smsm.wait()
-                smsm.combine((cnt - 1) & 1)
+            if world > 1:   # sharded: the 128-byte all-gather of step i-1 on a side stream beside the MSM of step i
+                smsm.run_many([d_sets[(first + i) % n_sets] for i in range(cnt)])
                 return
             for i in range(cnt):
                 be.msm_submit_dev(d_sets[(first + i) % n_sets].data_ptr(), table, 0, n, d_outs[i & 1].data_ptr())
@@ -625,8 +619,10 @@ def run_ours(args):
         for i in range(2):
             msm_once(d_sets[(args.warmup + msm_steps - 2 + i) % n_sets])
             want.append(bytes(d_out[:32].cpu().numpy().tobytes()))
-        sub_outs = d_outs if world == 1 else [smsm._slots()[k][2] for k in range(2)]
-        got = [bytes(sub_outs[(msm_steps - 2 + i) & 1][:32].cpu().numpy().tobytes()) for i in range(2)]
+        if world == 1:
+            got = [bytes(d_outs[(msm_steps - 2 + i) & 1][:32].cpu().numpy().tobytes()) for i in range(2)]
+        else:
+            got = [bytes(smsm._slots()[(msm_steps - 2 + i) % 3][2][:32].cpu().numpy().tobytes()) for i in range(2)]
         assert got == want, "submitted MSM results differ from the single-call results"
         clocks2 = samp2.stop() if (rank == 0 and args.workload == "msm") else None
         ms_e2e_serial = timed(msm_e2e, msm_steps, args.warmup)
@@ -708,7 +704,8 @@ def run_ours(args):
                          "and accumulate of the next), one bpp_msm_wait before the closing event; results checked against "
                          "the single-call results") if world == 1 else
                         ("throughput, sharded: bpp_msm_submit_partial_dev per step on every rank (two in flight), the 128-byte "
-                         "all-gather + sum of step i-1 beside the MSM of step i; results checked against the single-call results"),
+                         "all-gather of step i-1 on a side stream beside the MSM of step i, its sum one step later; results "
+                         "checked against the single-call results"),
                 "single_call": {"value": total_points * msm_steps / (ms_single * 1e-3), "ms_per_step": ms_single / msm_steps,
                                 "note": "bpp_msm_vartime_dev one call at a time: the caller's stream joins every MSM"},
                 "config": {"workload": f"ristretto255 vartime MSM, 2^{args.log_n} points per GPU (BASELINE configs[4])",

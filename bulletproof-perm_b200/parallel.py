@@ -52,16 +52,31 @@ class ShardedMsm:
         self.be.points_sum_compress_dev(self.d_all.data_ptr(), self.world, self.d_out.data_ptr())
         return self.d_out
 
-    # Throughput form for a sequence of independent MSMs (two in flight per rank, bpp_msm_submit_*):
-    #     for i, sc in enumerate(sets): m.submit(sc, i & 1); m.wait_previous(); (i > 0) and m.combine((i - 1) & 1)
-    #     m.wait(); m.combine(last & 1)
-    # The all-gather of step i-1 runs on the caller's stream while step i's MSM runs on the library's streams.
+    # Throughput form for a sequence of independent MSMs (two in flight per rank, bpp_msm_submit_*), three buffer
+    # slots (i % 3):
+    #     for i, sc in enumerate(sets):
+    #         m.submit(sc, i % 3); m.wait_previous()
+    #         if i >= 1: m.gather((i - 1) % 3)       # 128 B/rank all-gather + sum + compress on a side stream
+    #         if i >= 2: m.finish((i - 2) % 3)       # event wait only: that step's result is final
+    #     m.wait(); m.gather(last % 3); m.finish((last - 1) % 3); m.finish(last % 3)
+    # Nothing but event waits goes onto the caller's stream between two submits: a kernel there (even the one-warp
+    # sum) queues behind the accumulate blocks of the MSM in flight and would hold back the next submit's fork.  The
+    # gather of step i-1 and its sum + compress run on a side stream (the sum through a second context bound to it)
+    # beside the MSM of step i; finish() only makes the caller's stream wait for them.
+    SLOTS = 3
+
     def _slots(self):
         if not hasattr(self, "_slot_bufs"):
             dev = self.d_out.device
             self._slot_bufs = [(torch.zeros(self.PARTIAL_BYTES, dtype=torch.uint8, device=dev),
                                 torch.zeros(self.world * self.PARTIAL_BYTES, dtype=torch.uint8, device=dev),
-                                torch.zeros(160, dtype=torch.uint8, device=dev)) for _ in range(2)]
+                                torch.zeros(160, dtype=torch.uint8, device=dev)) for _ in range(self.SLOTS)]
+            self._gathered = [torch.cuda.Event() for _ in range(self.SLOTS)]
+            self._ready = torch.cuda.Event()
+            self._side = torch.cuda.Stream(dev)
+            if self.world > 1:
+                self._side_be = type(self.be)(dev.index if dev.index is not None else 0)
+                self._side_be.set_stream(self._side.cuda_stream)
         return self._slot_bufs
 
     def submit(self, d_scalars: torch.Tensor, slot: int):
@@ -78,11 +93,49 @@ class ShardedMsm:
     def wait(self):
         self.be.msm_wait()
 
-    def combine(self, slot: int) -> torch.Tensor:
-        """After the slot's MSM has been waited for: all-gather + sum (nothing to do on one GPU).  Returns the
-        slot's 160-byte output buffer (first 32 bytes = the compressed result)."""
-        part, allp, out = self._slots()[slot]
-        if self.world > 1:
+    def gather(self, slot: int):
+        """After the slot's MSM has been waited for on the caller's stream: all-gather of the partials on the side
+        stream (nothing to do on one GPU)."""
+        if self.world == 1:
+            return
+        part, allp, _ = self._slots()[slot]
+        cur = torch.cuda.current_stream(part.device)
+        self._ready.record(cur)
+        self._side.wait_event(self._ready)
+        _, _, out = self._slots()[slot]
+        with torch.cuda.stream(self._side):
             dist.all_gather_into_tensor(allp, part)
-            self.be.points_sum_compress_dev(allp.data_ptr(), self.world, out.data_ptr())
+            self._side_be.points_sum_compress_dev(allp.data_ptr(), self.world, out.data_ptr())
+            self._gathered[slot].record(self._side)
+
+    def finish(self, slot: int) -> torch.Tensor:
+        """The caller's stream waits for the slot's gather + sum.  Returns the slot's 160-byte output buffer (first
+        32 bytes = the compressed result, identical on every rank)."""
+        _, allp, out = self._slots()[slot]
+        if self.world > 1:
+            torch.cuda.current_stream(out.device).wait_event(self._gathered[slot])
         return out
+
+    def close(self):
+        """Release the side context of the throughput form (multi-GPU only)."""
+        be2 = getattr(self, "_side_be", None)
+        if be2 is not None:
+            torch.cuda.synchronize()
+            be2.close()
+            self._side_be = None
+
+    def run_many(self, scalar_sets):
+        """The loop above over a list of device scalar tensors; returns the output buffer of the last step."""
+        k = len(scalar_sets)
+        for i, sc in enumerate(scalar_sets):
+            self.submit(sc, i % 3)
+            self.wait_previous()
+            if i >= 1:
+                self.gather((i - 1) % 3)
+            if i >= 2:
+                self.finish((i - 2) % 3)
+        self.wait()
+        self.gather((k - 1) % 3)
+        if k >= 2:
+            self.finish((k - 2) % 3)
+        return self.finish((k - 1) % 3)
