@@ -154,6 +154,7 @@ def synth_shuffle_batch(k: int, count: int, rank: int):
     return b"".join(aL), b"".join(aR), b"".join(aO), g.tobytes(), b"".join(vv), seeds.tobytes()
 
 
+LANE_PRIORITY_SPLIT = os.environ.get("BPP_LANE_SPLIT", "1") != "0"
 FB_WINDOW_BITS = int(os.environ.get("BPP_FB_WINDOW", "16"))   # fixed-base table window: 16 windows x 32768 entries x 96 B = 50 MB per generator
 
 
@@ -443,10 +444,13 @@ def run_ours(args):
         # timed region; a step is still one batch of B proofs proved and verified through host buffers.
         lanes = []
         for _ in range(2):
-            st = torch.cuda.Stream(dev)
+            # urgent lane streams + priority split: the GPU-filling table-gather MSMs of a lane run at the lowest
+            # priority, its short dependent kernels win the SM slots against the other lane's bulk work
+            st = torch.cuda.Stream(dev, priority=-1) if LANE_PRIORITY_SPLIT else torch.cuda.Stream(dev)
             be_l = bpperm_b200.Backend(local)
             be_l.set_stream(st.cuda_stream)
             b_l = G.Batch(be_l, cir, gens, B, "reference-fixed", b"test")
+            b_l.set_priority_split(LANE_PRIORITY_SPLIT)
             lanes.append({"stream": st, "be": be_l, "batch": b_l,
                           "proofs": torch.empty(B * plen, dtype=torch.uint8).pin_memory(),
                           "accept": torch.empty(B, dtype=torch.uint8).pin_memory(), "ok": True})
@@ -473,7 +477,7 @@ def run_ours(args):
                 t.join()
 
         res2_steps = args.steps                  # exactly K steps, split over the two lanes (K odd: 1 more on lane 0)
-        res2_warm = max(2, args.warmup)
+        res2_warm = max(4, args.warmup + (args.warmup & 1))   # at least two warm-up steps per lane
         l2_0 = sum(ln["be"].launch_count for ln in lanes)
         ms_res2 = timed_block(run_resident2, res2_steps, res2_warm, [ln["stream"] for ln in lanes])
         launches2 = (sum(ln["be"].launch_count for ln in lanes) - l2_0) * res2_steps // (res2_steps + res2_warm)

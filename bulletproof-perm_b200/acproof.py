@@ -118,6 +118,10 @@ class Batch:
         """Verify with one random-linear-combination MSM over the batch first (default) or per proof only."""
         self.be._check(self.be._lib.bpp_acp_batch_set_batch_rlc(self._h, 1 if on else 0))
 
+    def set_priority_split(self, on: bool):
+        """Table-gather MSMs on an internal lowest-priority stream (for several batches in flight on urgent streams)."""
+        self.be._check(self.be._lib.bpp_acp_batch_set_priority_split(self._h, 1 if on else 0))
+
     def prove(self):
         self.be._check(self.be._lib.bpp_acp_batch_prove(self._h))
 

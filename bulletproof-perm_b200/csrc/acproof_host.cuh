@@ -49,6 +49,12 @@ struct bpp_acp_batch {
     // scalar chain (Fiat-Shamir replay, Fibonacci power chains, CSR products: serial, low occupancy)
     cudaStream_t aux = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // priority split (bpp_acp_batch_set_priority_split): the table-gather MSMs (k_fb_msm) run on `bulk`, a stream of
+    // the lowest priority, so that on an urgent caller's stream the short dependent kernels of this batch win the SM
+    // slots against the GPU-filling kernels of a second batch in flight on another stream
+    bool priority_split = false;
+    cudaStream_t bulk = nullptr;
+    cudaEvent_t ev_bfork = nullptr, ev_bjoin = nullptr;
     // batch verification by random linear combination (k_rlc_*): scalars of the one MSM over the batch's
     // dynamic points + the shared generators (appended to d_dyn), its compressed result, the fall-back flag
     bool batch_rlc = true;
@@ -303,6 +309,9 @@ extern "C" void bpp_acp_batch_free(bpp_acp_batch *b) {
     if (b->h_tx3) cudaFreeHost(b->h_tx3);
     if (b->h_rlc_flag) cudaFreeHost(b->h_rlc_flag);
     if (b->aux) cudaStreamDestroy(b->aux);
+    if (b->bulk) cudaStreamDestroy(b->bulk);
+    if (b->ev_bfork) cudaEventDestroy(b->ev_bfork);
+    if (b->ev_bjoin) cudaEventDestroy(b->ev_bjoin);
     if (b->ev_fork) cudaEventDestroy(b->ev_fork);
     if (b->ev_join) cudaEventDestroy(b->ev_join);
     delete b;
@@ -390,6 +399,21 @@ extern "C" int bpp_acp_batch_create(bpp_ctx *ctx, const bpp_circuit *cir, const 
 
 // Verification strategy: 1 (default) = one random-linear-combination MSM over the whole batch first, per-proof
 // kernels only if it fails (some proof is invalid); 0 = always per proof.  Decisions are identical.
+extern "C" int bpp_acp_batch_set_priority_split(bpp_acp_batch *b, int on) {
+    if (!b) return BPP_ERR_INVALID_ARG;
+    bpp_ctx *ctx = b->ctx;
+    if (on && !b->bulk) {
+        int lo = 0, hi = 0;
+        CK(ctx, cudaSetDevice(ctx->device));
+        CK(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(ctx, cudaStreamCreateWithPriority(&b->bulk, cudaStreamNonBlocking, lo));
+        CK(ctx, cudaEventCreateWithFlags(&b->ev_bfork, cudaEventDisableTiming));
+        CK(ctx, cudaEventCreateWithFlags(&b->ev_bjoin, cudaEventDisableTiming));
+    }
+    b->priority_split = on != 0;
+    return BPP_OK;
+}
+
 extern "C" int bpp_acp_batch_set_batch_rlc(bpp_acp_batch *b, int on) {
     if (!b) return BPP_ERR_INVALID_ARG;
     b->batch_rlc = on != 0;
@@ -446,22 +470,32 @@ static int acp_fb(bpp_acp_batch *b, const fb_shape &sh, uint32_t *dst, uint32_t 
         LAUNCH_CHECK(ctx);
         return BPP_OK;
     }
+    cudaStream_t st = ctx->stream;
+    if (b->priority_split) {   // the GPU-filling launch goes to the low-priority stream, bracketed by events
+        st = b->bulk;
+        CK(ctx, cudaEventRecord(b->ev_bfork, ctx->stream));
+        CK(ctx, cudaStreamWaitEvent(st, b->ev_bfork, 0));
+    }
     const uint64_t blocks = (uint64_t)b->B * sh.outs, want = 4ull * ctx->sm_count;
     const uint64_t items = (uint64_t)terms * ((b->gens->Wn + FB_GROUP - 1) / FB_GROUP);
     uint64_t sp = blocks >= want ? 1 : (want + blocks - 1) / blocks;
     if (sp > (items + FB_THREADS - 1) / FB_THREADS) sp = (items + FB_THREADS - 1) / FB_THREADS;
     if (sp > b->fb_splits || sh.outs > 8) sp = sh.outs > 8 ? 1 : b->fb_splits;
     if (sp > 1) {
-        k_fb_msm<<<dim3(b->B, sh.outs, (uint32_t)sp), FB_THREADS, 0, ctx->stream>>>(b->d_blk, b->lay, s, b->gens->d_table,
-                                                                                   b->gens->c, b->gens->Wn, b->gens->kc, b->d_part);
+        k_fb_msm<<<dim3(b->B, sh.outs, (uint32_t)sp), FB_THREADS, 0, st>>>(b->d_blk, b->lay, s, b->gens->d_table,
+                                                                          b->gens->c, b->gens->Wn, b->gens->kc, b->d_part);
         LAUNCH_CHECK(ctx);
-        k_fb_sum_splits<<<dim3(b->B, sh.outs), 32, 0, ctx->stream>>>(b->d_part, sh.outs, (uint32_t)sp, pitch, dst);
+        k_fb_sum_splits<<<dim3(b->B, sh.outs), 32, 0, st>>>(b->d_part, sh.outs, (uint32_t)sp, pitch, dst);
         LAUNCH_CHECK(ctx);
-        return BPP_OK;
+    } else {
+        k_fb_msm<<<dim3(b->B, sh.outs), FB_THREADS, 0, st>>>(b->d_blk, b->lay, s, b->gens->d_table, b->gens->c,
+                                                            b->gens->Wn, b->gens->kc, dst);
+        LAUNCH_CHECK(ctx);
     }
-    k_fb_msm<<<dim3(b->B, sh.outs), FB_THREADS, 0, ctx->stream>>>(b->d_blk, b->lay, s, b->gens->d_table, b->gens->c,
-                                                                  b->gens->Wn, b->gens->kc, dst);
-    LAUNCH_CHECK(ctx);
+    if (b->priority_split) {
+        CK(ctx, cudaEventRecord(b->ev_bjoin, st));
+        CK(ctx, cudaStreamWaitEvent(ctx->stream, b->ev_bjoin, 0));
+    }
     return BPP_OK;
 }
 

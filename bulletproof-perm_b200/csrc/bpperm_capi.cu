@@ -586,34 +586,42 @@ static int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points
         }
     }
     const bool need_dig = smem_sort || sort2;
-    const bool must_grow = chunk_elems > sc.cap_chunk || (need_dig && (size_t)W * ((n + 3) & ~(size_t)3) > sc.cap_dig) ||
-                           (sort2 && (size_t)W * n > sc.cap_tmp) || WB > sc.cap_wb || WB > sc.cap_offsets || WB > sc.cap_cursor || (size_t)W * n > sc.cap_entries ||
-                           total_tiles * 64 > sc.cap_partials || WB * 32 > sc.cap_buckets || 2 * node_elems > sc.cap_seg ||
-                           total_tiles / BPP_LONG_SPAN + 16 * (BPP_MAX_GROUPS + 1) > sc.cap_long;
-    if (must_grow) CK(ctx, cudaDeviceSynchronize());  // cudaFree of scratch another in-flight MSM never touches, but be plain
-    if ((rc = grow(ctx, &sc.d_counts, &sc.cap_wb, WB))) return rc;
-    if ((rc = grow(ctx, &sc.d_offsets, &sc.cap_offsets, WB))) return rc;
-    if ((rc = grow(ctx, &sc.d_cursor, &sc.cap_cursor, WB))) return rc;
-    if ((rc = grow(ctx, &sc.d_entries, &sc.cap_entries, (size_t)W * n))) return rc;
-    if ((rc = grow(ctx, &sc.d_partials, &sc.cap_partials, total_tiles * 2 * 32))) return rc;
-    if ((rc = grow(ctx, &sc.d_long, &sc.cap_long, total_tiles / BPP_LONG_SPAN + 16 * (BPP_MAX_GROUPS + 1)))) return rc;
-    if ((rc = grow(ctx, &sc.d_buckets, &sc.cap_buckets, WB * 32))) return rc;
-    if (chunk_elems && (rc = grow(ctx, &sc.d_chunk, &sc.cap_chunk, chunk_elems))) return rc;
-    if (need_dig && (rc = grow(ctx, &sc.d_dig, &sc.cap_dig, (size_t)W * ((n + 3) & ~(size_t)3)))) return rc;
-    if (sort2 && (rc = grow(ctx, &sc.d_tmp, &sc.cap_tmp, (size_t)W * n))) return rc;
-    if (sort2 && !sc.d_binoff) CK(ctx, cudaMalloc((void **)&sc.d_binoff, 64 * 257 * 4));
-    if (node_elems) {
-        size_t need = 2 * node_elems;  // two ping-pong buffers in each of segS / segR
-        if (need > sc.cap_seg) {
-            if (sc.d_segS) cudaFree(sc.d_segS);
-            if (sc.d_segR) cudaFree(sc.d_segR);
-            sc.d_segS = sc.d_segR = nullptr;
-            sc.cap_seg = 0;
-            CK(ctx, cudaMalloc((void **)&sc.d_segS, need * 4));
-            CK(ctx, cudaMalloc((void **)&sc.d_segR, need * 4));
-            sc.cap_seg = need;
+    // Scratch of BOTH slots is grown together (the next call uses the other slot: without this its first use would
+    // allocate - and synchronise the device - in the middle of somebody's pipeline).
+    auto grow_slot = [&](bpp_ctx::msm_scratch &x) -> int {
+        const bool must_grow = chunk_elems > x.cap_chunk || (need_dig && (size_t)W * ((n + 3) & ~(size_t)3) > x.cap_dig) ||
+                               (sort2 && (size_t)W * n > x.cap_tmp) || WB > x.cap_wb || WB > x.cap_offsets || WB > x.cap_cursor ||
+                               (size_t)W * n > x.cap_entries || total_tiles * 64 > x.cap_partials || WB * 32 > x.cap_buckets ||
+                               2 * node_elems > x.cap_seg || total_tiles / BPP_LONG_SPAN + 16 * (BPP_MAX_GROUPS + 1) > x.cap_long ||
+                               (sort2 && !x.d_binoff);
+        if (!must_grow) return BPP_OK;
+        CK(ctx, cudaDeviceSynchronize());   // nothing in flight may still use what is freed below
+        int r;
+        if ((r = grow(ctx, &x.d_counts, &x.cap_wb, WB))) return r;
+        if ((r = grow(ctx, &x.d_offsets, &x.cap_offsets, WB))) return r;
+        if ((r = grow(ctx, &x.d_cursor, &x.cap_cursor, WB))) return r;
+        if ((r = grow(ctx, &x.d_entries, &x.cap_entries, (size_t)W * n))) return r;
+        if ((r = grow(ctx, &x.d_partials, &x.cap_partials, total_tiles * 2 * 32))) return r;
+        if ((r = grow(ctx, &x.d_long, &x.cap_long, total_tiles / BPP_LONG_SPAN + 16 * (BPP_MAX_GROUPS + 1)))) return r;
+        if ((r = grow(ctx, &x.d_buckets, &x.cap_buckets, WB * 32))) return r;
+        if (chunk_elems && (r = grow(ctx, &x.d_chunk, &x.cap_chunk, chunk_elems))) return r;
+        if (need_dig && (r = grow(ctx, &x.d_dig, &x.cap_dig, (size_t)W * ((n + 3) & ~(size_t)3)))) return r;
+        if (sort2 && (r = grow(ctx, &x.d_tmp, &x.cap_tmp, (size_t)W * n))) return r;
+        if (sort2 && !x.d_binoff) CK(ctx, cudaMalloc((void **)&x.d_binoff, 64 * 257 * 4));
+        if (2 * node_elems > x.cap_seg) {   // two ping-pong buffers in each of segS / segR
+            const size_t need = 2 * node_elems;
+            if (x.d_segS) cudaFree(x.d_segS);
+            if (x.d_segR) cudaFree(x.d_segR);
+            x.d_segS = x.d_segR = nullptr;
+            x.cap_seg = 0;
+            CK(ctx, cudaMalloc((void **)&x.d_segS, need * 4));
+            CK(ctx, cudaMalloc((void **)&x.d_segR, need * 4));
+            x.cap_seg = need;
         }
-    }
+        return BPP_OK;
+    };
+    if ((rc = grow_slot(sc))) return rc;
+    if (n >= BPP_PIPELINE_MIN_POINTS_SUBMIT && (rc = grow_slot(ctx->scr[ctx->slot ^ 1]))) return rc;
 
     const bool prof = ctx->profiling && G == 1;
     const uint32_t ld = (uint32_t)((n + 3) & ~(size_t)3);   // row stride of the digit array

@@ -244,6 +244,12 @@ int bpp_acp_batch_download_accept(bpp_acp_batch *b, uint8_t *accept);
 int bpp_acp_batch_set_batch_rlc(bpp_acp_batch *b, int on);
 /* Fiat-Shamir location: 0 (default) per-proof Merlin transcripts on the device, 1 on host threads. */
 int bpp_acp_batch_set_host_transcripts(bpp_acp_batch *b, int on);
+/* Priority split for a caller that keeps several batches in flight on several streams: with on = 1 the table-gather
+ * MSMs of this batch (the launches that fill the GPU) run on an internal stream of the lowest priority, bracketed by
+ * events, so that when the caller's stream is an urgent one (cudaStreamCreateWithPriority) the short dependent
+ * kernels of this batch - transcripts, power chains, dot products - take SM slots ahead of the GPU-filling kernels of
+ * the other batches.  Result-neutral; no effect worth having on a default-priority stream. */
+int bpp_acp_batch_set_priority_split(bpp_acp_batch *b, int on);
 /* merlin::Transcript on the device, scripted (test hook for the Merlin KAT and framing edge cases): records
  * op (1 B: 0 append_message, 1 challenge_bytes) | label_len (1 B) | label | n (4 B LE) | message (op 0);
  * the transcript is Transcript::new(first record's message) when the first record is labelled "dom-sep";
