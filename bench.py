@@ -154,6 +154,7 @@ def synth_shuffle_batch(k: int, count: int, rank: int):
     return b"".join(aL), b"".join(aR), b"".join(aO), g.tobytes(), b"".join(vv), seeds.tobytes()
 
 
+N_LANES = int(os.environ.get("BPP_LANES", "3"))   # batches in flight in the pipelined legs
 LANE_PRIORITY_SPLIT = os.environ.get("BPP_LANE_SPLIT", "1") != "0"
 FB_WINDOW_BITS = int(os.environ.get("BPP_FB_WINDOW", "16"))   # fixed-base table window: 16 windows x 32768 entries x 96 B = 50 MB per generator
 
@@ -443,7 +444,7 @@ def run_ours(args):
         # batch overlap the kernels of the other.  Same public calls, same bytes per step, every copy inside the
         # timed region; a step is still one batch of B proofs proved and verified through host buffers.
         lanes = []
-        for _ in range(2):
+        for _ in range(N_LANES):
             # urgent lane streams + priority split: the GPU-filling table-gather MSMs of a lane run at the lowest
             # priority, its short dependent kernels win the SM slots against the other lane's bulk work
             st = torch.cuda.Stream(dev, priority=-1) if LANE_PRIORITY_SPLIT else torch.cuda.Stream(dev)
@@ -469,15 +470,15 @@ def run_ours(args):
                 lane["batch"].verify(b"\x5a" * 32)
 
         def run_resident2(cnt, first):
-            split = [(cnt + 1) // 2, cnt // 2]
-            th = [threading.Thread(target=lane_resident, args=(lanes[k], split[k])) for k in range(2) if split[k]]
+            split = [cnt // N_LANES + (1 if k < cnt % N_LANES else 0) for k in range(N_LANES)]
+            th = [threading.Thread(target=lane_resident, args=(lanes[k], split[k])) for k in range(N_LANES) if split[k]]
             for t in th:
                 t.start()
             for t in th:
                 t.join()
 
-        res2_steps = args.steps                  # exactly K steps, split over the two lanes (K odd: 1 more on lane 0)
-        res2_warm = max(4, args.warmup + (args.warmup & 1))   # at least two warm-up steps per lane
+        res2_steps = args.steps                  # exactly K steps, split over the lanes
+        res2_warm = max(2 * N_LANES, args.warmup)   # at least two warm-up steps per lane
         l2_0 = sum(ln["be"].launch_count for ln in lanes)
         ms_res2 = timed_block(run_resident2, res2_steps, res2_warm, [ln["stream"] for ln in lanes])
         launches2 = (sum(ln["be"].launch_count for ln in lanes) - l2_0) * res2_steps // (res2_steps + res2_warm)
@@ -497,8 +498,8 @@ def run_ours(args):
                 lane["ok"] = lane["ok"] and bytes(lane["accept"].numpy().tobytes()) == b"\x01" * B
 
         def run_pipelined(n, first):
-            split = [(n + 1) // 2, n // 2]
-            th = [threading.Thread(target=lane_steps, args=(lanes[k], split[k])) for k in range(2) if split[k]]
+            split = [n // N_LANES + (1 if k < n % N_LANES else 0) for k in range(N_LANES)]
+            th = [threading.Thread(target=lane_steps, args=(lanes[k], split[k])) for k in range(N_LANES) if split[k]]
             for t in th:
                 t.start()
             for t in th:
@@ -528,10 +529,12 @@ def run_ours(args):
                 "steps": res2_steps if two_lanes else args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_res2 / res2_steps if two_lanes else ms_res / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u32 (8x32-bit limbs, IMAD.WIDE.U32)", "data": "synthetic",
-                "mode": ("two batches in flight on two streams (one host thread each), inputs resident" if two_lanes
+                "mode": (f"{N_LANES} batches in flight on {N_LANES} urgent streams (one host thread each; table-gather MSMs on "
+                         "lowest-priority streams), inputs resident" if two_lanes
                          else "one batch at a time on one stream, inputs resident"),
                 "single_stream": {"value": value_single, "ms_per_step": ms_res / args.steps, "steps": args.steps},
-                "two_lanes": {"value": total * res2_steps / (ms_res2 * 1e-3), "ms_per_step": ms_res2 / res2_steps, "steps": res2_steps},
+                "multi_lane": {"lanes": N_LANES, "value": total * res2_steps / (ms_res2 * 1e-3), "ms_per_step": ms_res2 / res2_steps,
+                               "steps": res2_steps},
                 "config": {"workload": f"52-card shuffle prove+verify, batch of {B} independent proofs per GPU "
                                        f"(k=52, n={n}, Q={Q}, m={m}; BASELINE configs[1]/[3])",
                            "mode": "reference-fixed (SURVEY A.3: the reference's own flow never verifies)",
@@ -551,7 +554,7 @@ def run_ours(args):
                                    "note": "one batch at a time: every copy waits for the kernels before it"},
                         "proof_bytes_equal_serial_run": same_bytes,
                         "note": "witness H2D, proofs D2H, proofs+commitments H2D, accept bytes D2H inside the timed region; "
-                                "pinned host buffers; double buffered (two batches in flight on two streams, so copies of one "
+                                f"pinned host buffers; {N_LANES} batches in flight on {N_LANES} streams (so copies of one "
                                 "overlap kernels of the other); Fiat-Shamir transcripts on the device (one thread per proof)"},
                 "gpu_launches": launches2 if two_lanes else launches,
                 "roofline": {"bound": "imad", "kernel": f"k_fb_msm (A_I-shaped commitment MSM, 209 terms x {(256 + FB_WINDOW_BITS - 1) // FB_WINDOW_BITS} windows per proof)",
