@@ -16,7 +16,10 @@
  *   - compressed points are 32-byte RFC 9496 ristretto255 encodings.
  *   - "host" entry points take host pointers and include the host<->device copies;
  *     "_dev" entry points take device pointers and enqueue on the context's stream.
- *   - a context is bound to one GPU and one stream; use one context per thread.
+ *   - a context is bound to one GPU and one stream; use one context per thread.  Work is stream-ordered on that
+ *     stream: a large MSM internally forks onto the library's own streams (window groups, msm_kernels.cuh) and joins
+ *     back before the call's result is used, so the caller sees ordinary stream semantics; only the explicit
+ *     throughput form (bpp_msm_submit_dev / bpp_msm_wait) leaves work in flight across calls.
  *   - there is no CPU fallback: without a CUDA device bpp_init fails with BPP_ERR_NO_DEVICE.
  */
 #ifndef BPPERM_H
