@@ -35,19 +35,21 @@ FE_INLINE uint32_t sc_window(const uint32_t s[8], int bit, int c) {
 // still rippled up from window 0.
 __global__ void k_digit_hist(const uint32_t *__restrict__ scalars, uint32_t n, int c, int w_begin, int w_end,
                              uint32_t *__restrict__ counts) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t s[8];
-    const uint4 *p = reinterpret_cast<const uint4 *>(scalars + 8 * (size_t)i);
-    uint4 lo = __ldg(p), hi = __ldg(p + 1);
-    s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w; s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
     const uint32_t half = 1u << (c - 1);
-    uint32_t carry = 0;
-    for (int w = 0; w < w_end; w++) {
-        uint32_t raw = sc_window(s, w * c, c) + carry;
-        carry = raw > half ? 1u : 0u;
-        uint32_t mag = carry ? (1u << c) - raw : raw;
-        if (mag && w >= w_begin) atomicAdd(&counts[(size_t)w * half + (mag - 1)], 1u);
+    // grid-stride: the pipelined MSM launches this with a small grid (a block or two per SM) so that the sort keeps
+    // few SM slots while the accumulate of the previous group runs
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t s[8];
+        const uint4 *p = reinterpret_cast<const uint4 *>(scalars + 8 * (size_t)i);
+        uint4 lo = __ldg(p), hi = __ldg(p + 1);
+        s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w; s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
+        uint32_t carry = 0;
+        for (int w = 0; w < w_end; w++) {
+            uint32_t raw = sc_window(s, w * c, c) + carry;
+            carry = raw > half ? 1u : 0u;
+            uint32_t mag = carry ? (1u << c) - raw : raw;
+            if (mag && w >= w_begin) atomicAdd(&counts[(size_t)w * half + (mag - 1)], 1u);
+        }
     }
 }
 
@@ -125,23 +127,23 @@ __global__ void __launch_bounds__(1024) k_window_scan(const uint32_t *__restrict
 
 __global__ void k_digit_scatter(const uint32_t *__restrict__ scalars, uint32_t n, int c, int w_begin, int w_end,
                                 uint32_t *__restrict__ cursor, uint32_t *__restrict__ entries) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t s[8];
-    const uint4 *p = reinterpret_cast<const uint4 *>(scalars + 8 * (size_t)i);
-    uint4 lo = __ldg(p), hi = __ldg(p + 1);
-    s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w; s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
     const uint32_t half = 1u << (c - 1);
-    uint32_t carry = 0;
     // (issuing the position atomics eight windows at a time before the first write was measured: not faster, alone
     // or beside the accumulate - profiles/r1_msm_sort.md)
-    for (int w = 0; w < w_end; w++) {
-        uint32_t raw = sc_window(s, w * c, c) + carry;
-        carry = raw > half ? 1u : 0u;
-        uint32_t mag = carry ? (1u << c) - raw : raw;
-        if (mag && w >= w_begin) {
-            uint32_t pos = atomicAdd(&cursor[(size_t)w * half + (mag - 1)], 1u);
-            entries[(size_t)w * n + pos] = i | (carry << 31);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t s[8];
+        const uint4 *p = reinterpret_cast<const uint4 *>(scalars + 8 * (size_t)i);
+        uint4 lo = __ldg(p), hi = __ldg(p + 1);
+        s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w; s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
+        uint32_t carry = 0;
+        for (int w = 0; w < w_end; w++) {
+            uint32_t raw = sc_window(s, w * c, c) + carry;
+            carry = raw > half ? 1u : 0u;
+            uint32_t mag = carry ? (1u << c) - raw : raw;
+            if (mag && w >= w_begin) {
+                uint32_t pos = atomicAdd(&cursor[(size_t)w * half + (mag - 1)], 1u);
+                entries[(size_t)w * n + pos] = i | (carry << 31);
+            }
         }
     }
 }
