@@ -95,4 +95,5 @@ extern "C" {
     pub fn bpp_acp_batch_download_accept(b: *mut bpp_acp_batch, accept: *mut u8) -> c_int;
     pub fn bpp_acp_batch_set_host_transcripts(b: *mut bpp_acp_batch, on: c_int) -> c_int;
     pub fn bpp_acp_batch_set_batch_rlc(b: *mut bpp_acp_batch, on: c_int) -> c_int;
+    pub fn bpp_acp_batch_set_priority_split(b: *mut bpp_acp_batch, on: c_int) -> c_int;
 }

@@ -3,6 +3,8 @@ import numpy as np
 sys.path.insert(0, ".")
 import bpperm_b200
 be = bpperm_b200.Backend(0)
+import os
+be.set_msm_groups(int(os.environ.get("BPP_GROUPS", "0")))   # 1 = in-order kernels (whole-MSM launches) for ncu
 n = 1 << 20
 rs = np.random.RandomState(20)
 table = be.points_from_uniform(rs.randint(0, 256, size=(n, 64), dtype=np.uint8).tobytes())
