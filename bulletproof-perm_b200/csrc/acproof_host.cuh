@@ -52,6 +52,9 @@ struct bpp_acp_batch {
     // priority split (bpp_acp_batch_set_priority_split): the table-gather MSMs (k_fb_msm) run on `bulk`, a stream of
     // the lowest priority, so that on an urgent caller's stream the short dependent kernels of this batch win the SM
     // slots against the GPU-filling kernels of a second batch in flight on another stream
+    // large batches: one warp per output point (k_fb_msm_warp) instead of one block; same speed on the A_I shape,
+    // 5 % on the `fixed` mode's prover (two outputs per launch).  BPP_FB_WARP=0 keeps the block form (tuning hook).
+    bool fb_warp_per_output = true;
     bool priority_split = false;
     cudaStream_t bulk = nullptr;
     cudaEvent_t ev_bfork = nullptr, ev_bjoin = nullptr;
@@ -333,6 +336,7 @@ extern "C" int bpp_acp_batch_create(bpp_ctx *ctx, const bpp_circuit *cir, const 
     b->ctx = ctx; b->cir = cir; b->gens = gens; b->mode = mode; b->B = (uint32_t)count;
     b->lay = acp_make_layout(cir->n, cir->Q, cir->m, mode);
     b->proof_len = (uint32_t)bpp_acproof_proof_len_mode(cir->n, mode);
+    if (const char *e = getenv("BPP_FB_WARP")) b->fb_warp_per_output = e[0] != '0';
     b->label.assign(label, label + label_len);
     const size_t B = count, lg = b->lay.lg, per = cir->m + 8 + 2 * lg, nch = 4 + lg;
     {   // small batches of large circuits: split each fixed-base MSM over several blocks (k_fb_sum_splits adds them)
@@ -481,7 +485,13 @@ static int acp_fb(bpp_acp_batch *b, const fb_shape &sh, uint32_t *dst, uint32_t 
     uint64_t sp = blocks >= want ? 1 : (want + blocks - 1) / blocks;
     if (sp > (items + FB_THREADS - 1) / FB_THREADS) sp = (items + FB_THREADS - 1) / FB_THREADS;
     if (sp > b->fb_splits || sh.outs > 8) sp = sh.outs > 8 ? 1 : b->fb_splits;
-    if (sp > 1) {
+    if (sp == 1 && b->fb_warp_per_output && blocks >= 16ull * ctx->sm_count) {
+        // plenty of outputs: a warp per output (no block tree, no barrier)
+        const uint32_t n_out = b->B * sh.outs;
+        k_fb_msm_warp<<<(n_out + FB_THREADS / 32 - 1) / (FB_THREADS / 32), FB_THREADS, 0, st>>>(
+            b->d_blk, b->lay, s, b->gens->d_table, b->gens->c, b->gens->Wn, b->gens->kc, b->B, sh.outs, dst);
+        LAUNCH_CHECK(ctx);
+    } else if (sp > 1) {
         k_fb_msm<<<dim3(b->B, sh.outs, (uint32_t)sp), FB_THREADS, 0, st>>>(b->d_blk, b->lay, s, b->gens->d_table,
                                                                           b->gens->c, b->gens->Wn, b->gens->kc, b->d_part);
         LAUNCH_CHECK(ctx);
@@ -1021,7 +1031,8 @@ extern "C" int bpp_acp_batch_time_commit_msm(bpp_acp_batch *b, int reps, float *
     cudaEventDestroy(e1);
     *ms_avg = ms / reps;
     if (mixed_adds) *mixed_adds = (uint64_t)b->B * (1 + 2 * L.n) * b->gens->Wn;
-    if (full_adds) *full_adds = (uint64_t)b->B * (FB_THREADS - 1);
+    const bool warp_form = b->fb_warp_per_output && (uint64_t)b->B >= 16ull * ctx->sm_count;
+    if (full_adds) *full_adds = (uint64_t)b->B * (warp_form ? 31 : FB_THREADS - 1);
     return BPP_OK;
 }
 

@@ -255,6 +255,104 @@ __global__ void __launch_bounds__(FB_THREADS) k_fb_msm(const uint32_t *__restric
         dst[threadIdx.x] = red[0][threadIdx.x];
     }
 }
+// One WARP per output point (large batches: B x outs warps fill the GPU): no shared memory, no block barrier - the
+// 32 partial sums meet in five shuffle steps.  (ncu of the block-per-output form, profiles/r1_ncu_full_k_fb_msm.csv:
+// barrier stalls 1.7 per issue from the 7-level shared-memory tree.)
+__global__ void __launch_bounds__(FB_THREADS) k_fb_msm_warp(const uint32_t *__restrict__ blk, acp_layout lay, fb_shape sh,
+                                                            const uint32_t *__restrict__ table, int c, int Wn, fb_consts kc,
+                                                            uint32_t B, uint32_t outs /* per proof; sh.outs = pitch */,
+                                                            uint32_t *__restrict__ out_ext /* [p][pitch] x 32 */) {
+    const uint32_t wid = blockIdx.x * (FB_THREADS / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (wid >= B * outs) return;   // whole warps leave together
+    const uint32_t p = wid / outs, o = wid - p * outs;
+    const uint32_t half = 1u << (c - 1), mask = (1u << c) - 1u;
+    const uint32_t groups = (Wn + FB_GROUP - 1) / FB_GROUP;
+    uint32_t total_terms = 0;
+    for (uint32_t s = 0; s < sh.nseg; s++) total_terms += sh.cnt[s];
+    const uint32_t items = total_terms * groups;
+    ge_ext acc;
+    ge_identity(acc);
+    // Work items (term, group of FB_GROUP windows) are strided over the block; within this thread's items the
+    // non-zero digits form one stream of (table entry, sign) pairs.  The stream is software pipelined: the
+    // next entry's 96-byte gather (random access into a multi-GB table) is issued before the current mixed add.
+    const uint32_t stride = 32;
+    uint32_t it = lane;
+    uint32_t w = 0, w_end = 0, gen = 0;
+    uint32_t s[9];
+    bool first = true;
+    auto advance = [&](const uint32_t *&ptr, bool &neg) -> bool {
+        for (;;) {
+            if (w >= w_end) {
+                if (!first) it += stride;
+                first = false;
+                if (it >= items) return false;
+                uint32_t term = it / groups, grp = it - term * groups;
+                uint32_t seg = 0, k = term;
+                while (seg + 1 < sh.nseg && k >= sh.cnt[seg]) { k -= sh.cnt[seg]; seg++; }
+                w = grp * FB_GROUP;
+                w_end = min((uint32_t)Wn, (grp + 1) * FB_GROUP);
+                if (sh.sel_period && sh.sel[seg]) {
+                    const bool upper = (k & (sh.sel_period - 1)) >= (sh.sel_period >> 1);
+                    if ((upper == (o == 0)) != (sh.sel[seg] == 1)) { w = w_end; continue; }
+                }
+                const uint32_t *sp = ACP_PTR(blk, lay, p, sh.sc_off[seg] + o * sh.sc_ostride[seg] + k);
+                gen = sh.gen[seg] + k;
+                uint4 lo = *reinterpret_cast<const uint4 *>(sp), hi = *reinterpret_cast<const uint4 *>(sp + 4);
+                s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w; s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
+                unsigned long long carry = 0;   // s' = s + K
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    carry += (unsigned long long)s[i] + kc.K[i];
+                    s[i] = (uint32_t)carry;
+                    carry >>= 32;
+                }
+                s[8] = (uint32_t)carry;
+            }
+            const uint32_t ww = w++;
+            int bit = c * (int)ww, limb = bit >> 5, shf = bit & 31;
+            unsigned long long v = s[limb];
+            if (limb + 1 < 9) v |= (unsigned long long)s[limb + 1] << 32;
+            uint32_t u = (uint32_t)(v >> shf) & mask;
+            int d = (ww + 1 == (uint32_t)Wn) ? (int)u : (int)u - (int)half;
+            if (d == 0) continue;
+            uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+            ptr = table + FB_ENTRY_U32 * (((size_t)gen * Wn + ww) * half + (mag - 1));
+            neg = d < 0;
+            return true;
+        }
+    };
+    {
+        const uint32_t *ptr = nullptr, *ptr_n = nullptr;
+        bool neg = false, neg_n = false;
+        bool ok = advance(ptr, neg);
+        ge_niels q, qn;
+        if (ok) ge_niels_load(q, ptr);
+#pragma unroll 1
+        while (ok) {
+            bool ok_n = advance(ptr_n, neg_n);
+            qn = q;
+            if (ok_n) ge_niels_load(qn, ptr_n);
+            ge_madd(acc, acc, q, neg);
+            q = qn;
+            neg = neg_n;
+            ok = ok_n;
+        }
+    }
+    // warp reduction: five shuffle steps
+#pragma unroll 1
+    for (int d = 16; d >= 1; d >>= 1) {
+        ge_ext o2;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            o2.X.v[i] = __shfl_down_sync(0xffffffffu, acc.X.v[i], d);
+            o2.Y.v[i] = __shfl_down_sync(0xffffffffu, acc.Y.v[i], d);
+            o2.Z.v[i] = __shfl_down_sync(0xffffffffu, acc.Z.v[i], d);
+            o2.T.v[i] = __shfl_down_sync(0xffffffffu, acc.T.v[i], d);
+        }
+        ge_add(acc, acc, o2);
+    }
+    if (lane == 0) ge_store(out_ext + 32 * ((size_t)p * sh.outs + o), acc);
+}
 // Few-term shapes (T_i = t_i*g + tau_i*h, V_j = v_j*g + gamma_j*h: 2 terms): one THREAD per output point
 // walks its terms x windows serially - no block tree, no idle lanes.
 __global__ void __launch_bounds__(128) k_fb_msm_small(const uint32_t *__restrict__ blk, acp_layout lay, fb_shape sh,
