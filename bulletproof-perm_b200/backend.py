@@ -127,6 +127,10 @@ class Backend:
         """Sort form: 0 automatic, 1 global atomics, 2 shared memory."""
         self._check(self._lib.bpp_set_msm_sort(self._ctx, mode))
 
+    def set_msm_tile(self, tile_len: int):
+        """Entries per accumulate tile (0 = by input size)."""
+        self._check(self._lib.bpp_set_msm_tile(self._ctx, tile_len))
+
     def set_msm_partition(self, sizes):
         """Explicit window-group sizes, top group first (empty = clear)."""
         arr = (ctypes.c_int * max(1, len(sizes)))(*sizes)

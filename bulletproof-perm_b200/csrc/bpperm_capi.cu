@@ -14,6 +14,7 @@
 #define BPP_MAX_GROUPS 8
 #define BPP_SORT_SMEM_MAX (128 * 1024)
 #define BPP_SORT_BLOCKS_PER_SM 2u
+#define BPP_TILE64_MIN_POINTS (3u << 20)
 #define BPP_PIPELINE_MIN_POINTS (1u << 18)
 #define BPP_PIPELINE_MIN_POINTS_SUBMIT (1u << 12)
 
@@ -66,6 +67,7 @@ struct bpp_ctx {
     // pipelined MSM: window groups on side streams (msm_pipeline_init)
     bool pipe_ready = false;
     int forced_groups = 0;
+    int forced_tile = 0;                                        // tile length override (bpp_set_msm_tile), 0 = by input size
     int sort_mode = 0;                                          // 0 automatic, 1 global atomics, 2 shared memory, 3 two-pass
     bool smem_sort_ready = false;
     int forced_part[BPP_MAX_GROUPS] = {}, n_forced_part = 0;    // explicit group sizes, top window group first
@@ -243,6 +245,12 @@ extern "C" int bpp_set_msm_groups(bpp_ctx *ctx, int groups) {
     if (!ctx || groups < 0 || groups > BPP_MAX_GROUPS) return BPP_ERR_INVALID_ARG;
     ctx->forced_groups = groups;
     ctx->n_forced_part = 0;
+    return BPP_OK;
+}
+
+extern "C" int bpp_set_msm_tile(bpp_ctx *ctx, int tile_len) {
+    if (!ctx || (tile_len != 0 && (tile_len < 8 || tile_len > 256))) return BPP_ERR_INVALID_ARG;
+    ctx->forced_tile = tile_len;
     return BPP_OK;
 }
 
@@ -548,7 +556,8 @@ static int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points
         CK(ctx, cudaStreamWaitEvent(s, sc.ev_done, 0));
         sc.pending = false;
     }
-    const uint32_t tpw = (uint32_t)((n + BPP_TILE - 1) / BPP_TILE);
+    const uint32_t tile_len = ctx->forced_tile ? (uint32_t)ctx->forced_tile : (n >= BPP_TILE64_MIN_POINTS ? 64u : 32u);
+    const uint32_t tpw = (uint32_t)((n + tile_len - 1) / tile_len);
     const size_t total_tiles = (size_t)W * tpw;
     // sort form: through shared memory once the input is large enough to feed one block per (window, chunk)
     const bool smem_sort = B * 4 <= BPP_SORT_SMEM_MAX &&
@@ -727,7 +736,7 @@ static int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points
         }
         trace_mark(ctx, s_acc, "accum>", g);
         k_bucket_accum<<<(group_tiles + BPP_ACC_THREADS - 1) / BPP_ACC_THREADS, BPP_ACC_THREADS, 0, s_acc>>>(
-            niels, entries, offsets, ends, (uint32_t)n, B, tpw, group_tiles, buckets, partials);
+            niels, entries, offsets, ends, (uint32_t)n, B, tpw, group_tiles, tile_len, buckets, partials);
         LAUNCH_CHECK(ctx);
         if (prof) cudaEventRecord(ctx->ev[4], s);
         trace_mark(ctx, s_acc, "accum.", g);
@@ -736,10 +745,10 @@ static int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points
             CK(ctx, cudaStreamWaitEvent(s_tail, ctx->ev_acc[g], 0));
         }
         trace_mark(ctx, s_tail, "tail>", g);
-        k_bucket_fixup<<<(group_buckets + 127) / 128, 128, 0, s_tail>>>(offsets, ends, B, tpw, group_buckets, partials,
+        k_bucket_fixup<<<(group_buckets + 127) / 128, 128, 0, s_tail>>>(offsets, ends, B, tpw, group_buckets, tile_len, partials,
                                                                        buckets, long_list, d_nlong);
         LAUNCH_CHECK(ctx);
-        k_bucket_fixup_long<<<ctx->sm_count * 2, 128, 0, s_tail>>>(offsets, ends, B, tpw, partials, buckets, long_list,
+        k_bucket_fixup_long<<<ctx->sm_count * 2, 128, 0, s_tail>>>(offsets, ends, B, tpw, tile_len, partials, buckets, long_list,
                                                                   d_nlong);
         LAUNCH_CHECK(ctx);
         trace_mark(ctx, s_tail, "fixup.", g);

@@ -512,14 +512,16 @@ __global__ void __launch_bounds__(1024) k_sort2_fine(const uint32_t *__restrict_
 }
 
 // ---- bucket accumulation: the dominant kernel ------------------------------------------------
-// The bucket-sorted entry list of each window is cut into tiles of BPP_TILE entries; one thread
+// The bucket-sorted entry list of each window is cut into tiles of `tile_len` entries; one thread
 // owns one tile, so every thread performs the same number of mixed adds (extended += affine
 // Niels, 7M) whatever the bucket sizes are: no warp divergence from Poisson bucket sizes and no
 // serialisation on hot buckets (repeated / small scalars).  A bucket that lies inside one tile is
 // written directly; a bucket cut by a tile boundary leaves partial sums (at most two per tile:
 // `head` = the run touching the tile start, `tail` = the run touching the tile end) that
 // k_bucket_fixup adds up.  `niels` is the static point table (96 B per point, read-only path).
-#define BPP_TILE 32
+// The tile length is a launch parameter (`tile_len`): 32 entries, 64 from 3 M points (measured: half the partials
+// and half the cut buckets outweigh the coarser accumulate grid only once the input is large - 2^22 points 6.15 ->
+// 5.79 ms per submitted MSM, 2^21 3.12 -> 3.19 ms, 2^18 0.66 -> 0.73 ms; bpp_set_msm_tile overrides).
 
 FE_INLINE void bucket_flush(const ge_ext &acc, uint32_t w, uint32_t b, uint32_t rs, uint32_t re, uint32_t e0,
                             uint32_t B, size_t tile, const uint32_t *__restrict__ offsets,
@@ -534,15 +536,15 @@ FE_INLINE void bucket_flush(const ge_ext &acc, uint32_t w, uint32_t b, uint32_t 
 __global__ void __launch_bounds__(BPP_ACC_THREADS, 4) k_bucket_accum(
     const uint32_t *__restrict__ niels, const uint32_t *__restrict__ entries, const uint32_t *__restrict__ offsets,
     const uint32_t *__restrict__ ends, uint32_t n, uint32_t B, uint32_t tiles_per_window, uint32_t total_tiles,
-    uint32_t *__restrict__ buckets, uint32_t *__restrict__ partials) {
+    uint32_t tile_len, uint32_t *__restrict__ buckets, uint32_t *__restrict__ partials) {
     uint32_t tile = blockIdx.x * blockDim.x + threadIdx.x;
     if (tile >= total_tiles) return;
     const uint32_t w = tile / tiles_per_window, t = tile - w * tiles_per_window;
     const uint32_t *endw = ends + (size_t)w * B;
     const uint32_t cnt = endw[B - 1];  // entries in this window
-    const uint32_t e0 = t * BPP_TILE;
+    const uint32_t e0 = t * tile_len;
     if (e0 >= cnt) return;
-    const uint32_t e1 = min(e0 + BPP_TILE, cnt);
+    const uint32_t e1 = min(e0 + tile_len, cnt);
     const uint32_t *ew = entries + (size_t)w * n;
     // bucket of entry e0 = the first bucket whose end offset lies beyond e0 (the entry list carries no
     // bucket ids: the sorted order and the offsets determine them)
@@ -590,7 +592,7 @@ __global__ void __launch_bounds__(BPP_ACC_THREADS, 4) k_bucket_accum(
 #define BPP_LONG_SPAN 24
 __global__ void __launch_bounds__(128) k_bucket_fixup(const uint32_t *__restrict__ offsets,
                                                       const uint32_t *__restrict__ ends, uint32_t B,
-                                                      uint32_t tiles_per_window, uint32_t total_buckets,
+                                                      uint32_t tiles_per_window, uint32_t total_buckets, uint32_t tile_len,
                                                       const uint32_t *__restrict__ partials,
                                                       uint32_t *__restrict__ buckets, uint32_t *__restrict__ long_list,
                                                       uint32_t *__restrict__ n_long) {
@@ -603,7 +605,7 @@ __global__ void __launch_bounds__(128) k_bucket_fixup(const uint32_t *__restrict
         ge_store(buckets + 32 * (size_t)g, id);
         return;
     }
-    const uint32_t first = beg / BPP_TILE, last = (end - 1) / BPP_TILE;
+    const uint32_t first = beg / tile_len, last = (end - 1) / tile_len;
     if (first == last) return;  // complete inside one tile: already written
     if (last - first > BPP_LONG_SPAN) {
         long_list[atomicAdd(n_long, 1u)] = g;
@@ -611,7 +613,7 @@ __global__ void __launch_bounds__(128) k_bucket_fixup(const uint32_t *__restrict
     }
     const size_t tbase = (size_t)(g / B) * tiles_per_window;
     ge_ext acc, t;
-    ge_load(acc, partials + 32 * (2 * (tbase + first) + (beg > first * BPP_TILE ? 1 : 0)));
+    ge_load(acc, partials + 32 * (2 * (tbase + first) + (beg > first * tile_len ? 1 : 0)));
 #pragma unroll 1
     for (uint32_t k = first + 1; k <= last; k++) {
         ge_load(t, partials + 32 * (2 * (tbase + k)));
@@ -623,7 +625,7 @@ __global__ void __launch_bounds__(128) k_bucket_fixup(const uint32_t *__restrict
 // One block (128 threads) per hot bucket: strided partial sums, then a shared-memory tree.
 __global__ void __launch_bounds__(128) k_bucket_fixup_long(const uint32_t *__restrict__ offsets,
                                                            const uint32_t *__restrict__ ends, uint32_t B,
-                                                           uint32_t tiles_per_window,
+                                                           uint32_t tiles_per_window, uint32_t tile_len,
                                                            const uint32_t *__restrict__ partials,
                                                            uint32_t *__restrict__ buckets,
                                                            const uint32_t *__restrict__ long_list,
@@ -633,7 +635,7 @@ __global__ void __launch_bounds__(128) k_bucket_fixup_long(const uint32_t *__res
     for (uint32_t i = blockIdx.x; i < nl; i += gridDim.x) {
         const uint32_t g = long_list[i];
         const uint32_t beg = offsets[g], end = ends[g];
-        const uint32_t first = beg / BPP_TILE, last = (end - 1) / BPP_TILE;
+        const uint32_t first = beg / tile_len, last = (end - 1) / tile_len;
         const size_t tbase = (size_t)(g / B) * tiles_per_window;
         ge_ext acc, t;
         ge_identity(acc);
@@ -656,7 +658,7 @@ __global__ void __launch_bounds__(128) k_bucket_fixup_long(const uint32_t *__res
         }
         if (threadIdx.x == 0) {
             ge_load(acc, &sh[0][0]);
-            ge_load(t, partials + 32 * (2 * (tbase + first) + (beg > first * BPP_TILE ? 1 : 0)));
+            ge_load(t, partials + 32 * (2 * (tbase + first) + (beg > first * tile_len ? 1 : 0)));
             ge_add(acc, acc, t);
             ge_store(buckets + 32 * (size_t)g, acc);
         }

@@ -133,6 +133,9 @@ int bpp_set_msm_groups(bpp_ctx *ctx, int groups);
  * with coalesced writes (by the high bits of the bucket number, then by the low bits inside shared memory).  The
  * result bytes do not depend on it.  A tuning hook. */
 int bpp_set_msm_sort(bpp_ctx *ctx, int mode);
+/* Entries per accumulate tile (one thread adds one tile of the bucket-sorted entry list): 0 = by input size (32, and 64
+ * from 3 M points), else 8..256.  Result-neutral tuning hook. */
+int bpp_set_msm_tile(bpp_ctx *ctx, int tile_len);
 /* Explicit window-group sizes, top group first (count <= 8; used when they sum to the number of windows of the
  * MSM, ignored otherwise; count = 0 clears).  A tuning hook like bpp_set_window_bits. */
 int bpp_set_msm_partition(bpp_ctx *ctx, const int *sizes, int count);

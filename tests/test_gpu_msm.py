@@ -361,3 +361,30 @@ def test_submitted_partials_sum_to_the_full_result(backend):
         backend.set_msm_groups(0)
     assert bytes(out32.cpu().numpy().tobytes()) == want
     table.free()
+
+
+@pytest.mark.parametrize("tile,c,groups", [(8, 11, 1), (48, 16, 3), (64, 16, 4), (64, 8, 1), (256, 13, 2)])
+def test_tile_lengths_match_oracle(backend, tile, c, groups):
+    """bpp_set_msm_tile: the accumulate's tile length (32 by default, 64 for large inputs) with skewed scalars, so that
+    buckets span many tiles (the long-bucket queue at tile 8) or many buckets share one tile (tile 256)."""
+    import numpy as np
+    from oracle import cref
+    n = 12000 + 345
+    rs = np.random.RandomState(8200 + tile)
+    blobs = rs.randint(0, 256, size=(n, 64), dtype=np.uint8)
+    sc = rs.randint(0, 256, size=(n, 32), dtype=np.uint8)
+    sc[:, 31] &= 0x0F
+    sc[500:3000] = sc[1]
+    sc[4000:4200, 2:] = 0
+    table = backend.points_from_uniform(blobs.tobytes())
+    backend.set_window_bits(c)
+    backend.set_msm_groups(groups)
+    backend.set_msm_tile(tile)
+    try:
+        got = backend.vartime_multiscalar_mul(sc.tobytes(), table)
+    finally:
+        backend.set_msm_tile(0)
+        backend.set_msm_groups(0)
+        backend.set_window_bits(0)
+        table.free()
+    assert got == cref.msm(sc.tobytes(), cref.from_uniform(blobs.tobytes()))
