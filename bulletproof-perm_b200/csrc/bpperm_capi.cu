@@ -482,6 +482,10 @@ static int pick_partition(const bpp_ctx *ctx, size_t n, int W, bool join, int pa
         n >= (join ? BPP_PIPELINE_MIN_POINTS : BPP_PIPELINE_MIN_POINTS_SUBMIT)) {
         // measured best of the partitions tried at 2^18..2^22 points (profiles/r1_msm_partitions.md): an eighth of the
         // windows first and last, the rest in two halves (16 windows: 2, 6, 6, 2)
+        if (!join && n >= BPP_TILE64_MIN_POINTS) {   // very large submitted MSMs: two halves (2^22: 5.81 -> 5.62 ms)
+            part[0] = W / 2; part[1] = W - W / 2;
+            return 2;
+        }
         const int edge = W / 8, mid = W - 2 * edge;
         part[0] = edge; part[1] = (mid + 1) / 2; part[2] = mid / 2; part[3] = edge;
         return 4;
