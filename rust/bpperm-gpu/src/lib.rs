@@ -99,3 +99,39 @@ impl ShuffleBatch {
     }
 }
 impl Drop for ShuffleBatch { fn drop(&mut self) { unsafe { sys::bpp_acp_batch_free(self.b) } } }
+
+// ---- proof records on the wire (bpperm.h: bpp_acproof_to_wire / bpp_acproof_from_wire) ------------------------
+// mode 2 records are bulletproofs 4.0.0 `R1CSProof::to_bytes` of a one-phase proof (version byte 0).
+pub fn proofs_to_wire(n: usize, mode: i32, count: usize, proofs: &[u8]) -> Vec<u8> {
+    let wlen = unsafe { sys::bpp_acproof_wire_len(n, mode) };
+    let mut out = vec![0u8; count * wlen];
+    assert_eq!(unsafe { sys::bpp_acproof_to_wire(n, mode, count, proofs.as_ptr(), out.as_mut_ptr()) }, 0);
+    out
+}
+/// One `Result` per record: `Err(ProofError::FormatError)` for a wrong version byte or a non-canonical scalar
+/// (what `R1CSProof::from_bytes` rejects); the proof bytes of a rejected record are zeroed.
+pub fn proofs_from_wire(n: usize, mode: i32, count: usize, wire: &[u8]) -> Result<(Vec<u8>, Vec<Result<(), ProofError>>), ProofError> {
+    let plen = unsafe { sys::bpp_acproof_proof_len_mode(n, mode) };
+    let mut proofs = vec![0u8; count * plen];
+    let mut status = vec![0u8; count];
+    if count == 0 || wire.len() % count != 0 { return Err(ProofError::FormatError); }
+    let rc = unsafe { sys::bpp_acproof_from_wire(n, mode, count, wire.as_ptr(), wire.len() / count, proofs.as_mut_ptr(), status.as_mut_ptr()) };
+    if rc != 0 { return Err(ProofError::FormatError); }          // record length does not match the circuit
+    Ok((proofs, status.into_iter().map(|s| if s == 0 { Ok(()) } else { Err(ProofError::FormatError) }).collect()))
+}
+
+// ---- many independent large MSMs: two in flight (bpp_msm_submit_dev / bpp_msm_wait_previous / bpp_msm_wait) ---
+// `d_scalars[i]` / `d_out[i & 1]` are device pointers of the caller (e.g. from cust / cudarc); `consume(i, ptr)`
+// enqueues whatever reads result i on the context's stream.  Same bytes as one bpp_msm_vartime_dev call per MSM.
+pub unsafe fn msm_stream(points: *const sys::bpp_points, n: usize, d_scalars: &[*const core::ffi::c_void],
+                         d_out: [*mut core::ffi::c_void; 2], mut consume: impl FnMut(usize, *mut core::ffi::c_void)) {
+    with_ctx(|ctx| {
+        for (i, sc) in d_scalars.iter().enumerate() {
+            assert_eq!(sys::bpp_msm_submit_dev(ctx, *sc, points, 0, n, d_out[i & 1]), 0);
+            assert_eq!(sys::bpp_msm_wait_previous(ctx), 0);      // results up to i - 1 are valid in stream order
+            if i > 0 { consume(i - 1, d_out[(i - 1) & 1]); }
+        }
+        assert_eq!(sys::bpp_msm_wait(ctx), 0);
+        if !d_scalars.is_empty() { consume(d_scalars.len() - 1, d_out[(d_scalars.len() - 1) & 1]); }
+    })
+}
