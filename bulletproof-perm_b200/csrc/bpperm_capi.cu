@@ -439,7 +439,7 @@ static int pick_window(size_t n) {
     // c = 15 below ~2^20 points, c = 16 from there (equal at 2^20; 16 keeps W*n exact for 252-bit scalars).  (Odd widths win over their even neighbours because
     // W = ceil(256/c) drops at 11, 13, 15.)
     if (n <= 1500) return 8;
-    if (n <= 180000) return 11;
+    if (n <= 96000) return 11;   // crossover between 2^16 (c = 11: 0.638 vs 0.654 ms) and 2^17 (c = 15: 0.764 vs 0.795 ms)
     if (n < 1000000) return 15;
     return 16;
 }
