@@ -1,9 +1,10 @@
-// acproof_host.cuh - host driver + C ABI of the batched shuffle prover / verifier.
-// Included by bpperm_capi.cu.  The driver re-expresses the seven-step state machine of
+// capi_acproof.cu - host driver + C ABI of the batched shuffle prover / verifier.
+// The driver re-expresses the seven-step state machine of
 // /root/reference/bp-perm/src/circuit_lib.rs (call order lib.rs:219-231) for B proofs in lock-step:
 // one kernel launch per protocol step for the whole batch, Fiat-Shamir transcripts on host threads.
-#pragma once
 #include <thread>
+
+#include "bpperm_internal.hpp"
 
 #include "acproof_kernels.cuh"
 #include "ipa_kernels.cuh"
@@ -800,9 +801,6 @@ extern "C" int bpp_acp_batch_upload_proofs(bpp_acp_batch *b, const uint8_t *proo
     if (V) CK(ctx, cudaMemcpyAsync(b->d_V, V, (size_t)b->B * b->lay.m * 32, cudaMemcpyHostToDevice, ctx->stream));
     return BPP_OK;
 }
-
-static int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points *pts, size_t off, size_t n, uint8_t *d_out,
-                       int do_compress, bool join);
 
 // One MSM over the batch (see k_rlc_weights).  *decided = true when every proof's accept byte is final.
 static int acp_verify_rlc(bpp_acp_batch *b, uint32_t per, int check_t, bool *decided) {

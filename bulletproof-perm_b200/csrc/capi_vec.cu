@@ -1,5 +1,5 @@
-// vec_capi.cuh - host entry points (C ABI) of the scalar-vector operators.  Included by bpperm_capi.cu.
-#pragma once
+// capi_vec.cu - host entry points (C ABI) of the scalar-vector operators.
+#include "bpperm_internal.hpp"
 #include "vec_kernels.cuh"
 
 // Stages host buffers into one device arena: [in0 | in1 | ... | out]; returns device pointers.

@@ -329,17 +329,17 @@ FE_INLINE void fe_tobytes(uint8_t *s, const fe &a) {
 }
 
 // n squarings, rolled (keeps code size small; the loop body is one fe_mul)
-__device__ __noinline__ void fe_sqr_n(fe &r, const fe &a, int n) {
+static __device__ __noinline__ void fe_sqr_n(fe &r, const fe &a, int n) {
     fe t;
     fe_copy(t, a);
 #pragma unroll 1
     for (int i = 0; i < n; i++) fe_sqr(t, t);
     fe_copy(r, t);
 }
-__device__ __noinline__ void fe_mul_noinline(fe &r, const fe &a, const fe &b) { fe_mul(r, a, b); }
+static __device__ __noinline__ void fe_mul_noinline(fe &r, const fe &a, const fe &b) { fe_mul(r, a, b); }
 
 // z^(2^250-1) and z^11, the shared prefix of inversion and pow((p-5)/8).
-__device__ __noinline__ void fe_pow_2_250_1(fe &t250, fe &z11, const fe &z) {
+static __device__ __noinline__ void fe_pow_2_250_1(fe &t250, fe &z11, const fe &z) {
     fe z2, z9, t, u;
     fe_sqr_n(z2, z, 1);                      // 2
     fe_sqr_n(t, z2, 2);                      // 8
@@ -372,14 +372,14 @@ __device__ __noinline__ void fe_pow_2_250_1(fe &t250, fe &z11, const fe &z) {
 }
 
 // r = z^(p-2) = 1/z (0 -> 0)
-__device__ __noinline__ void fe_invert(fe &r, const fe &z) {
+static __device__ __noinline__ void fe_invert(fe &r, const fe &z) {
     fe t250, z11, t;
     fe_pow_2_250_1(t250, z11, z);
     fe_sqr_n(t, t250, 5);                    // 2^255-2^5
     fe_mul_noinline(r, t, z11);              // 2^255-21
 }
 // r = z^((p-5)/8) = z^(2^252-3)
-__device__ __noinline__ void fe_pow_p58(fe &r, const fe &z) {
+static __device__ __noinline__ void fe_pow_p58(fe &r, const fe &z) {
     fe t250, z11, t;
     fe_pow_2_250_1(t250, z11, z);
     fe_sqr_n(t, t250, 2);                    // 2^252-4

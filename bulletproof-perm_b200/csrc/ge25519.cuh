@@ -137,8 +137,8 @@ FE_INLINE void ge_double_p2(ge_ext &r, const ge_ext &p) {
     fe_mul(r.Z, f, g);
 }
 
-__device__ __noinline__ void ge_add_noinline(ge_ext &r, const ge_ext &p, const ge_ext &q) { ge_add(r, p, q); }
-__device__ __noinline__ void ge_double_noinline(ge_ext &r, const ge_ext &p) { ge_double(r, p); }
+static __device__ __noinline__ void ge_add_noinline(ge_ext &r, const ge_ext &p, const ge_ext &q) { ge_add(r, p, q); }
+static __device__ __noinline__ void ge_double_noinline(ge_ext &r, const ge_ext &p) { ge_double(r, p); }
 
 FE_INLINE void ge_neg(ge_ext &r, const ge_ext &p) {
     fe_neg(r.X, p.X);
@@ -158,7 +158,7 @@ FE_INLINE void ge_affine_to_niels(ge_niels &r, const fe &x, const fe &y) {
 }
 
 // RFC 9496 4.2: (was_square, r) with r = |sqrt(u/v)| or |sqrt(i*u/v)|
-__device__ __noinline__ bool fe_sqrt_ratio_i(fe &r, const fe &u, const fe &v) {
+static __device__ __noinline__ bool fe_sqrt_ratio_i(fe &r, const fe &u, const fe &v) {
     fe v3, v7, t, rr, check, i, nu, nui;
     fe_mul_noinline(t, v, v);
     fe_mul_noinline(v3, t, v);
@@ -182,7 +182,7 @@ __device__ __noinline__ bool fe_sqrt_ratio_i(fe &r, const fe &u, const fe &v) {
 }
 
 // RFC 9496 4.3.2 Encode
-__device__ __noinline__ void ge_compress(uint8_t *out32, const ge_ext &p) {
+static __device__ __noinline__ void ge_compress(uint8_t *out32, const ge_ext &p) {
     fe u1, u2, t, inv, i1, i2, zinv, den, X, Y, one, c;
     fe_add(u1, p.Z, p.Y);
     fe_sub(t, p.Z, p.Y);
@@ -216,7 +216,7 @@ __device__ __noinline__ void ge_compress(uint8_t *out32, const ge_ext &p) {
 }
 
 // RFC 9496 4.3.1 Decode -> affine (x, y); returns false for invalid encodings
-__device__ __noinline__ bool ge_decompress(fe &x, fe &y, const uint8_t *in32) {
+static __device__ __noinline__ bool ge_decompress(fe &x, fe &y, const uint8_t *in32) {
     fe s, c, ss, u1, u2, u2s, v, t, inv, dx, dy, one, d;
     fe_frombytes(s, in32);
     fe_canon(c, s);
@@ -249,7 +249,7 @@ __device__ __noinline__ bool ge_decompress(fe &x, fe &y, const uint8_t *in32) {
 }
 
 // RFC 9496 4.3.4 MAP (dalek RistrettoPoint::elligator_ristretto_flavor)
-__device__ __noinline__ void ge_elligator(ge_ext &out, const fe &r0) {
+static __device__ __noinline__ void ge_elligator(ge_ext &out, const fe &r0) {
     fe i, d, one, r, u, v, t, t2, s, sp, c, N, w0, w1, w2, w3, k;
     fe_const(i, GE_SQRTM1);
     fe_const(d, GE_D);
@@ -292,7 +292,7 @@ __device__ __noinline__ void ge_elligator(ge_ext &out, const fe &r0) {
 }
 
 // dalek RistrettoPoint::from_uniform_bytes (RFC 9496 one-way map): 64 bytes -> point
-__device__ __noinline__ void ge_from_uniform(ge_ext &out, const uint8_t *b64) {
+static __device__ __noinline__ void ge_from_uniform(ge_ext &out, const uint8_t *b64) {
     fe r1, r2;
     fe_frombytes(r1, b64);
     fe_frombytes(r2, b64 + 32);
@@ -305,7 +305,7 @@ __device__ __noinline__ void ge_from_uniform(ge_ext &out, const uint8_t *b64) {
 }
 
 // Ristretto equality: X1*Y2 == Y1*X2 or X1*X2 == Y1*Y2
-__device__ __noinline__ bool ge_ristretto_eq(const ge_ext &p, const ge_ext &q) {
+static __device__ __noinline__ bool ge_ristretto_eq(const ge_ext &p, const ge_ext &q) {
     fe a, b;
     fe_mul_noinline(a, p.X, q.Y);
     fe_mul_noinline(b, p.Y, q.X);

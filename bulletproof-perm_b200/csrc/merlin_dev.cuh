@@ -26,7 +26,7 @@ __device__ __constant__ const uint64_t KECCAK_RC[24] = {
 __device__ __forceinline__ uint64_t keccak_rol(uint64_t v, int n) { return (v << n) | (v >> (64 - n)); }
 
 // Keccak-f[1600], lanes in registers, fully unrolled rounds' inner structure (rho/pi written out)
-__device__ __noinline__ void keccak_f1600_dev(uint64_t *st) {
+static __device__ __noinline__ void keccak_f1600_dev(uint64_t *st) {
     uint64_t a00 = st[0], a01 = st[1], a02 = st[2], a03 = st[3], a04 = st[4];
     uint64_t a05 = st[5], a06 = st[6], a07 = st[7], a08 = st[8], a09 = st[9];
     uint64_t a10 = st[10], a11 = st[11], a12 = st[12], a13 = st[13], a14 = st[14];

@@ -746,7 +746,7 @@ FE_INLINE void quad_finish(fe &v, const fe &E, const fe &F, const fe &G, const f
     fe_pick(q, F, t, ql == 0);
     fe_mul(v, p, q);
 }
-__device__ __noinline__ void quad_double(fe &v, uint32_t ql) {
+static __device__ __noinline__ void quad_double(fe &v, uint32_t ql) {
     fe x, y, s, in, sq, A, B, Zs, D, E, F, G, H;
     fe_shfl4(x, v, 0);
     fe_shfl4(y, v, 1);
@@ -765,7 +765,7 @@ __device__ __noinline__ void quad_double(fe &v, uint32_t ql) {
     quad_finish(v, E, F, G, H, ql);
 }
 // v += the point cached at c (8 limbs each of Y+X, Y-X, Z, 2d*T; same address in every lane): two stages
-__device__ __noinline__ void quad_add_cached(fe &v, const uint32_t *c, uint32_t ql) {
+static __device__ __noinline__ void quad_add_cached(fe &v, const uint32_t *c, uint32_t ql) {
     fe x, y, z, t, p, q, m, a, b, cc, d, E, F, G, H;
     fe_shfl4(x, v, 0);
     fe_shfl4(y, v, 1);
@@ -791,7 +791,7 @@ __device__ __noinline__ void quad_add_cached(fe &v, const uint32_t *c, uint32_t 
 }
 // v += w, both in quad form: (Y1-X1)(Y2-X2) | (Y1+X1)(Y2+X2) | T1*T2 | Z1*Z2, then 2d*(T1*T2) in lane 2,
 // then the four products of the last stage.
-__device__ __noinline__ void quad_add(fe &v, const fe &w, uint32_t ql) {
+static __device__ __noinline__ void quad_add(fe &v, const fe &w, uint32_t ql) {
     fe x1, y1, x2, y2, p1, p2, a, b, m, k, cc, d, E, F, G, H;
     fe_shfl4(x1, v, 0);
     fe_shfl4(y1, v, 1);

@@ -191,8 +191,8 @@ SC_INLINE void sc_mul(sc &r, const sc &a, const sc &b) {
     sc_const(k, SC_R2);
     sc_mont(r, t, k);
 }
-__device__ __noinline__ void sc_mul_noinline(sc &r, const sc &a, const sc &b) { sc_mul(r, a, b); }
-__device__ __noinline__ void sc_mont_noinline(sc &r, const sc &a, const sc &b) { sc_mont(r, a, b); }
+static __device__ __noinline__ void sc_mul_noinline(sc &r, const sc &a, const sc &b) { sc_mul(r, a, b); }
+static __device__ __noinline__ void sc_mont_noinline(sc &r, const sc &a, const sc &b) { sc_mont(r, a, b); }
 
 // Scalar::from_bytes_mod_order_wide: 512-bit little-endian value mod l
 SC_INLINE void sc_from_wide(sc &r, const uint32_t w[16]) {
@@ -254,7 +254,7 @@ SC_INLINE void sc_add8_masked(uint32_t *r, const uint32_t *a, const uint32_t *b,
 // each step makes u even (subtracting v after a conditional swap) and halves it, x1 following mod l.
 // len(u) + len(v) <= 506 drops by at least one per step, so 508 steps always end with u = 0, v = gcd = 1 and
 // x2 = a^-1 (x2 = 0 for a = 0); ~100 plain integer instructions per step, no multiplications.
-__device__ __noinline__ void sc_invert(sc &r, const sc &a) {
+static __device__ __noinline__ void sc_invert(sc &r, const sc &a) {
     uint32_t u[8], v[8], x1[8], x2[8], t[8], lm[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) { u[i] = a.v[i]; v[i] = SC_L[i]; lm[i] = SC_L[i]; x1[i] = 0; x2[i] = 0; }

@@ -55,7 +55,7 @@ SC_INLINE void dot_partial(sc &acc, const uint32_t *__restrict__ a, size_t sa, c
 
 // out[row] = <a, b[row]> for `rows` rows of length n (vm_mult); rows == 1 is inner_product.
 // Inputs canonical; one block per row.
-__global__ void __launch_bounds__(256) k_rows_dot(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b,
+static __global__ void __launch_bounds__(256) k_rows_dot(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b,
                                                   uint32_t n, uint32_t *__restrict__ out) {
     __shared__ __align__(16) uint32_t sh[32 * 8];
     const uint32_t row = blockIdx.x;
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) k_rows_dot(const uint32_t *__restrict__ a
 }
 
 // out[col] = sum_i a[i][col] * b[i]  (mv_mult: a is rows x cols, row-major); one block per column.
-__global__ void __launch_bounds__(256) k_cols_dot(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b,
+static __global__ void __launch_bounds__(256) k_cols_dot(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b,
                                                   uint32_t rows, uint32_t cols, uint32_t *__restrict__ out) {
     __shared__ __align__(16) uint32_t sh[32 * 8];
     const uint32_t col = blockIdx.x;
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256) k_cols_dot(const uint32_t *__restrict__ a
     }
 }
 
-__global__ void k_hadamard(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b, uint32_t n,
+static __global__ void k_hadamard(const uint32_t *__restrict__ a, const uint32_t *__restrict__ b, uint32_t n,
                            uint32_t *__restrict__ out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -97,7 +97,7 @@ __global__ void k_hadamard(const uint32_t *__restrict__ a, const uint32_t *__res
 
 // util.rs exp_iter as coded: state (x = 1, next = x0); each step returns next, then next *= x; x = returned.
 // A serial chain by construction (x^F(i) = x^F(i-1) * x^F(i-2)); one thread.
-__global__ void k_exp_iter_fib(const uint32_t *__restrict__ x0, uint32_t count, uint32_t *__restrict__ out) {
+static __global__ void k_exp_iter_fib(const uint32_t *__restrict__ x0, uint32_t count, uint32_t *__restrict__ out) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     sc base, nxt, ret;
     sc_const(base, SC_R);  // 1 in Montgomery form
@@ -115,7 +115,7 @@ __global__ void k_exp_iter_fib(const uint32_t *__restrict__ x0, uint32_t count, 
 }
 
 // out[i] = x^(i + first) by square-and-multiply, one thread per power (standard powers 1, x, x^2, ...)
-__global__ void k_scalar_powers(const uint32_t *__restrict__ x0, uint32_t first, uint32_t count,
+static __global__ void k_scalar_powers(const uint32_t *__restrict__ x0, uint32_t first, uint32_t count,
                                 uint32_t *__restrict__ out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
@@ -133,7 +133,7 @@ __global__ void k_scalar_powers(const uint32_t *__restrict__ x0, uint32_t first,
     sc_store(out + 8 * (size_t)i, acc);
 }
 
-__global__ void k_scalar_invert(const uint32_t *__restrict__ a, uint32_t n, uint32_t *__restrict__ out) {
+static __global__ void k_scalar_invert(const uint32_t *__restrict__ a, uint32_t n, uint32_t *__restrict__ out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     sc x, r;
@@ -142,7 +142,7 @@ __global__ void k_scalar_invert(const uint32_t *__restrict__ a, uint32_t n, uint
     sc_store(out + 8 * (size_t)i, r);
 }
 
-__global__ void k_scalar_reduce(const uint32_t *__restrict__ a, uint32_t n, uint32_t *__restrict__ out) {
+static __global__ void k_scalar_reduce(const uint32_t *__restrict__ a, uint32_t n, uint32_t *__restrict__ out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     sc x;
@@ -151,7 +151,7 @@ __global__ void k_scalar_reduce(const uint32_t *__restrict__ a, uint32_t n, uint
     sc_store(out + 8 * (size_t)i, x);
 }
 
-__global__ void k_scalar_from_wide(const uint32_t *__restrict__ in, uint32_t n, uint32_t *__restrict__ out) {
+static __global__ void k_scalar_from_wide(const uint32_t *__restrict__ in, uint32_t n, uint32_t *__restrict__ out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t w[16];
@@ -163,7 +163,7 @@ __global__ void k_scalar_from_wide(const uint32_t *__restrict__ in, uint32_t n, 
 }
 
 // VecPoly3::eval: out[i] = c0[i] + x*(c1[i] + x*(c2[i] + x*c3[i])); c is 4 x n
-__global__ void k_vecpoly3_eval(const uint32_t *__restrict__ c, const uint32_t *__restrict__ x0, uint32_t n,
+static __global__ void k_vecpoly3_eval(const uint32_t *__restrict__ c, const uint32_t *__restrict__ x0, uint32_t n,
                                 uint32_t *__restrict__ out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -185,7 +185,7 @@ __global__ void k_vecpoly3_eval(const uint32_t *__restrict__ c, const uint32_t *
 // VecPoly3::special_inner_product: the 9 inner products -> t1..t6 (poly.rs:39-55).  One block per
 // inner product (blockIdx.x = 0..8), then block 0's thread 0 of a second launch combines - here the
 // combination is done by a tiny second kernel to keep this one race-free.
-__global__ void __launch_bounds__(256) k_vecpoly3_nine_dots(const uint32_t *__restrict__ l, const uint32_t *__restrict__ r,
+static __global__ void __launch_bounds__(256) k_vecpoly3_nine_dots(const uint32_t *__restrict__ l, const uint32_t *__restrict__ r,
                                                             uint32_t n, uint32_t *__restrict__ dots /* 9 x 8 */) {
     __shared__ __align__(16) uint32_t sh[32 * 8];
     // (lhs index, rhs index) per poly.rs:40-45
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(256) k_vecpoly3_nine_dots(const uint32_t *__re
         sc_store(dots + 8 * k, tot);
     }
 }
-__global__ void k_vecpoly3_combine(const uint32_t *__restrict__ dots, uint32_t *__restrict__ t6) {
+static __global__ void k_vecpoly3_combine(const uint32_t *__restrict__ dots, uint32_t *__restrict__ t6) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     sc d[9], t;
 #pragma unroll
@@ -218,7 +218,7 @@ __global__ void k_vecpoly3_combine(const uint32_t *__restrict__ dots, uint32_t *
 }
 
 // Poly6::eval (poly.rs:14-18): x*(t1 + x*(t2 + ... + x*t6)); scalar_exp(x, pow) (util.rs:75-82)
-__global__ void k_poly6_eval(const uint32_t *__restrict__ t6, const uint32_t *__restrict__ x0, uint32_t *__restrict__ out) {
+static __global__ void k_poly6_eval(const uint32_t *__restrict__ t6, const uint32_t *__restrict__ x0, uint32_t *__restrict__ out) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     sc x, acc, c;
     sc_load(x, x0);
@@ -232,7 +232,7 @@ __global__ void k_poly6_eval(const uint32_t *__restrict__ t6, const uint32_t *__
     sc_mul_noinline(acc, x, acc);
     sc_store(out, acc);
 }
-__global__ void k_scalar_exp(const uint32_t *__restrict__ x0, uint32_t pow, uint32_t *__restrict__ out) {
+static __global__ void k_scalar_exp(const uint32_t *__restrict__ x0, uint32_t pow, uint32_t *__restrict__ out) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     sc x, acc;
     sc_load(x, x0);
