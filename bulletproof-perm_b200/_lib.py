@@ -17,7 +17,7 @@ SYMBOLS = [
     "bpp_init", "bpp_free", "bpp_set_stream", "bpp_synchronize", "bpp_strerror", "bpp_last_error",
     "bpp_launch_count", "bpp_device_info", "bpp_points_upload", "bpp_points_from_uniform", "bpp_points_compress", "bpp_points_free", "bpp_points_len",
     "bpp_msm_vartime", "bpp_msm_vartime_host", "bpp_msm_vartime_dev", "bpp_msm_partial_dev", "bpp_msm_submit_dev", "bpp_msm_submit_partial_dev", "bpp_msm_wait", "bpp_msm_wait_previous",
-    "bpp_points_sum_compress_dev", "bpp_set_window_bits", "bpp_set_msm_groups", "bpp_set_msm_partition", "bpp_set_msm_sort", "bpp_set_msm_tile", "bpp_set_msm_trace", "bpp_msm_trace_dump", "bpp_bench_imad_peak", "bpp_device_clock_khz", "bpp_bench_pipe_probe", "bpp_set_profiling",
+    "bpp_points_sum_compress_dev", "bpp_set_window_bits", "bpp_set_msm_groups", "bpp_set_msm_partition", "bpp_set_msm_tile", "bpp_set_msm_trace", "bpp_msm_trace_dump", "bpp_bench_imad_peak", "bpp_device_clock_khz", "bpp_bench_pipe_probe", "bpp_set_profiling",
     "bpp_last_phase_ms", "bpp_last_op_counts", "bpp_test_op",
     "bpp_inner_product", "bpp_hadamard_V", "bpp_vm_mult", "bpp_mv_mult", "bpp_exp_iter", "bpp_scalar_powers",
     "bpp_scalar_exp", "bpp_scalar_invert", "bpp_scalar_from_wide", "bpp_scalar_reduce",
@@ -79,7 +79,6 @@ def load() -> ctypes.CDLL:
     lib.bpp_points_sum_compress_dev.argtypes = [vp, vp, sz, vp]
     lib.bpp_set_window_bits.argtypes = [vp, c.c_int]
     lib.bpp_set_msm_groups.argtypes = [vp, c.c_int]
-    lib.bpp_set_msm_sort.argtypes = [vp, c.c_int]
     lib.bpp_set_msm_tile.argtypes = [vp, c.c_int]
     lib.bpp_set_msm_partition.argtypes = [vp, c.POINTER(c.c_int), c.c_int]
     lib.bpp_set_msm_trace.argtypes = [vp, c.c_int]

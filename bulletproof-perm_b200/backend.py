@@ -123,10 +123,6 @@ class Backend:
         """Window groups of the pipelined MSM (0 = automatic, 1 = in order on one stream)."""
         self._check(self._lib.bpp_set_msm_groups(self._ctx, groups))
 
-    def set_msm_sort(self, mode: int):
-        """Sort form: 0 automatic, 1 global atomics, 2 shared memory."""
-        self._check(self._lib.bpp_set_msm_sort(self._ctx, mode))
-
     def set_msm_tile(self, tile_len: int):
         """Entries per accumulate tile (0 = by input size)."""
         self._check(self._lib.bpp_set_msm_tile(self._ctx, tile_len))

@@ -13,7 +13,6 @@
 #include "../../include/bpperm.h"
 
 #define BPP_MAX_GROUPS 8
-#define BPP_SORT_SMEM_MAX (128 * 1024)
 #define BPP_SORT_BLOCKS_PER_SM 2u
 #define BPP_TILE64_MIN_POINTS (3u << 20)
 #define BPP_PIPELINE_MIN_POINTS (1u << 18)
@@ -49,10 +48,6 @@ struct bpp_ctx {
         uint32_t *d_long = nullptr; size_t cap_long = 0;            // hot-bucket queues (one region per window group)
         uint32_t *d_nlong = nullptr;                                // their counters
         uint32_t *d_buckets = nullptr; size_t cap_buckets = 0;      // W x B x 32
-        uint32_t *d_chunk = nullptr; size_t cap_chunk = 0;          // shared-memory sort: [window of the group][chunk][B]
-        uint32_t *d_dig = nullptr; size_t cap_dig = 0;              // shared-memory / two-pass sort: digits, W x n
-        uint32_t *d_tmp = nullptr; size_t cap_tmp = 0;              // two-pass sort: entries after pass A, W x n
-        uint32_t *d_binoff = nullptr;                               // two-pass sort: coarse-bin offsets, W x 257
         uint32_t *d_segS = nullptr, *d_segR = nullptr; size_t cap_seg = 0;
         uint8_t *d_gparts = nullptr;                                // BPP_MAX_GROUPS x 128 B: window-group partials
         cudaEvent_t ev_done = nullptr;                              // recorded when the slot's MSM has written its result
@@ -69,8 +64,6 @@ struct bpp_ctx {
     bool pipe_ready = false;
     int forced_groups = 0;
     int forced_tile = 0;                                        // tile length override (bpp_set_msm_tile), 0 = by input size
-    int sort_mode = 0;                                          // 0 automatic, 1 global atomics, 2 shared memory, 3 two-pass
-    bool smem_sort_ready = false;
     int forced_part[BPP_MAX_GROUPS] = {}, n_forced_part = 0;    // explicit group sizes, top window group first
     cudaStream_t s_sort = nullptr, s_bulk[2] = {}, s_tail[BPP_MAX_GROUPS] = {};
     cudaEvent_t ev_fork = nullptr, ev_sorted[BPP_MAX_GROUPS] = {}, ev_acc[BPP_MAX_GROUPS] = {}, ev_tail[BPP_MAX_GROUPS] = {};

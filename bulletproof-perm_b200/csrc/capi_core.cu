@@ -60,7 +60,7 @@ extern "C" void bpp_free(bpp_ctx *ctx) {
         if (p) cudaFree(p);
     for (auto &sc : ctx->scr) {
         void *sp[] = {sc.d_counts, sc.d_offsets, sc.d_cursor, sc.d_entries, sc.d_partials, sc.d_long, sc.d_nlong,
-                      sc.d_buckets, sc.d_segS, sc.d_segR, sc.d_gparts, sc.d_chunk, sc.d_dig, sc.d_tmp, sc.d_binoff};
+                      sc.d_buckets, sc.d_segS, sc.d_segR, sc.d_gparts};
         for (void *p : sp)
             if (p) cudaFree(p);
         if (sc.ev_done) cudaEventDestroy(sc.ev_done);
@@ -134,12 +134,6 @@ extern "C" int bpp_set_msm_groups(bpp_ctx *ctx, int groups) {
 extern "C" int bpp_set_msm_tile(bpp_ctx *ctx, int tile_len) {
     if (!ctx || (tile_len != 0 && (tile_len < 8 || tile_len > 256))) return BPP_ERR_INVALID_ARG;
     ctx->forced_tile = tile_len;
-    return BPP_OK;
-}
-
-extern "C" int bpp_set_msm_sort(bpp_ctx *ctx, int mode) {
-    if (!ctx || mode < 0 || mode > 3) return BPP_ERR_INVALID_ARG;
-    ctx->sort_mode = mode;
     return BPP_OK;
 }
 
@@ -446,51 +440,16 @@ int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points *pts, 
     const uint32_t tile_len = ctx->forced_tile ? (uint32_t)ctx->forced_tile : (n >= BPP_TILE64_MIN_POINTS ? 64u : 32u);
     const uint32_t tpw = (uint32_t)((n + tile_len - 1) / tile_len);
     const size_t total_tiles = (size_t)W * tpw;
-    // sort form: through shared memory once the input is large enough to feed one block per (window, chunk)
-    const bool smem_sort = B * 4 <= BPP_SORT_SMEM_MAX &&
-                           ctx->sort_mode == 2;
-    // two passes with coalesced writes (msm_kernels.cuh): items carry a 23-bit point index
-    const bool sort2 = n <= (1u << 23) && ctx->sort_mode == 3;
-    const uint32_t nb = B >> SORT2_LOW ? B >> SORT2_LOW : 1u, chunks2 = (uint32_t)((n + SORT2_CHUNK - 1) / SORT2_CHUNK);
-    size_t chunk_elems = 0;
-    int chunks_of[BPP_MAX_GROUPS] = {};
-    if (sort2) {
-        if (!ctx->smem_sort_ready) {
-            CK(ctx, cudaFuncSetAttribute(k_sort_count, cudaFuncAttributeMaxDynamicSharedMemorySize, BPP_SORT_SMEM_MAX));
-            CK(ctx, cudaFuncSetAttribute(k_sort_place, cudaFuncAttributeMaxDynamicSharedMemorySize, BPP_SORT_SMEM_MAX));
-            CK(ctx, cudaFuncSetAttribute(k_sort2_fine, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * SORT2_CAP * 4));
-            ctx->smem_sort_ready = true;
-        }
-        int wmax = 0;
-        for (int g = 0; g < G; g++) wmax = part[g] > wmax ? part[g] : wmax;
-        chunk_elems = (size_t)wmax * nb * chunks2;
-    } else if (smem_sort) {
-        if (!ctx->smem_sort_ready) {
-            CK(ctx, cudaFuncSetAttribute(k_sort2_fine, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * SORT2_CAP * 4));
-            CK(ctx, cudaFuncSetAttribute(k_sort_count, cudaFuncAttributeMaxDynamicSharedMemorySize, BPP_SORT_SMEM_MAX));
-            CK(ctx, cudaFuncSetAttribute(k_sort_place, cudaFuncAttributeMaxDynamicSharedMemorySize, BPP_SORT_SMEM_MAX));
-            ctx->smem_sort_ready = true;
-        }
-        for (int g = 0; g < G; g++) {
-            // about one block per SM for the group, but no chunk shorter than 2048 scalars
-            int ch = (ctx->sm_count + part[g] - 1) / part[g];
-            const int by_len = (int)((n + 2047) / 2048);
-            if (ch > by_len) ch = by_len;
-            if (ch < 1) ch = 1;
-            chunks_of[g] = ch;
-            const size_t need = (size_t)part[g] * ch * B;
-            if (need > chunk_elems) chunk_elems = need;
-        }
-    }
-    const bool need_dig = smem_sort || sort2;
+    // Hot-bucket queue: a bucket is queued when it spans more than BPP_LONG_SPAN tiles, so one window holds at most
+    // tpw / BPP_LONG_SPAN + 1 of them.  Every window group owns a DISJOINT region sized for that worst case (the groups'
+    // fix-up kernels run concurrently on different streams).
+    const size_t long_per_window = tpw / BPP_LONG_SPAN + 1, long_total = (size_t)W * long_per_window;
     // Scratch of BOTH slots is grown together (the next call uses the other slot: without this its first use would
     // allocate - and synchronise the device - in the middle of somebody's pipeline).
     auto grow_slot = [&](bpp_ctx::msm_scratch &x) -> int {
-        const bool must_grow = chunk_elems > x.cap_chunk || (need_dig && (size_t)W * ((n + 3) & ~(size_t)3) > x.cap_dig) ||
-                               (sort2 && (size_t)W * n > x.cap_tmp) || WB > x.cap_wb || WB > x.cap_offsets || WB > x.cap_cursor ||
-                               (size_t)W * n > x.cap_entries || total_tiles * 64 > x.cap_partials || WB * 32 > x.cap_buckets ||
-                               2 * node_elems > x.cap_seg || total_tiles / BPP_LONG_SPAN + 16 * (BPP_MAX_GROUPS + 1) > x.cap_long ||
-                               (sort2 && !x.d_binoff);
+        const bool must_grow = WB > x.cap_wb || WB > x.cap_offsets || WB > x.cap_cursor || (size_t)W * n > x.cap_entries ||
+                               total_tiles * 64 > x.cap_partials || WB * 32 > x.cap_buckets || 2 * node_elems > x.cap_seg ||
+                               long_total > x.cap_long;
         if (!must_grow) return BPP_OK;
         CK(ctx, cudaDeviceSynchronize());   // nothing in flight may still use what is freed below
         int r;
@@ -499,12 +458,8 @@ int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points *pts, 
         if ((r = grow(ctx, &x.d_cursor, &x.cap_cursor, WB))) return r;
         if ((r = grow(ctx, &x.d_entries, &x.cap_entries, (size_t)W * n))) return r;
         if ((r = grow(ctx, &x.d_partials, &x.cap_partials, total_tiles * 2 * 32))) return r;
-        if ((r = grow(ctx, &x.d_long, &x.cap_long, total_tiles / BPP_LONG_SPAN + 16 * (BPP_MAX_GROUPS + 1)))) return r;
+        if ((r = grow(ctx, &x.d_long, &x.cap_long, long_total))) return r;
         if ((r = grow(ctx, &x.d_buckets, &x.cap_buckets, WB * 32))) return r;
-        if (chunk_elems && (r = grow(ctx, &x.d_chunk, &x.cap_chunk, chunk_elems))) return r;
-        if (need_dig && (r = grow(ctx, &x.d_dig, &x.cap_dig, (size_t)W * ((n + 3) & ~(size_t)3)))) return r;
-        if (sort2 && (r = grow(ctx, &x.d_tmp, &x.cap_tmp, (size_t)W * n))) return r;
-        if (sort2 && !x.d_binoff) CK(ctx, cudaMalloc((void **)&x.d_binoff, 64 * 257 * 4));
         if (2 * node_elems > x.cap_seg) {   // two ping-pong buffers in each of segS / segR
             const size_t need = 2 * node_elems;
             if (x.d_segS) cudaFree(x.d_segS);
@@ -521,7 +476,6 @@ int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points *pts, 
     if (n >= BPP_PIPELINE_MIN_POINTS_SUBMIT && (rc = grow_slot(ctx->scr[ctx->slot ^ 1]))) return rc;
 
     const bool prof = ctx->profiling && G == 1;
-    const uint32_t ld = (uint32_t)((n + 3) & ~(size_t)3);   // row stride of the digit array
     const uint32_t *niels = pts->niels + 24 * off;
     unsigned sb = (unsigned)((n + 255) / 256);
     // Pipelined form: the sort kernels run grid-stride on two blocks per SM.  Their threads mostly wait on the L2, and
@@ -548,12 +502,7 @@ int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points *pts, 
         CK(ctx, cudaEventRecord(ctx->ev_fork, s));
         CK(ctx, cudaStreamWaitEvent(s_sort, ctx->ev_fork, 0));
     }
-    if (!need_dig) {
-        CK(ctx, cudaMemsetAsync(sc.d_counts, 0, WB * 4, s_sort));
-    } else {
-        k_sort_digits<<<sb, 256, 0, s_sort>>>(d_scalars, (uint32_t)n, ld, c, W, sc.d_dig);
-        LAUNCH_CHECK(ctx);
-    }
+    CK(ctx, cudaMemsetAsync(sc.d_counts, 0, WB * 4, s_sort));
     CK(ctx, cudaMemsetAsync(sc.d_nlong, 0, 4 * BPP_MAX_GROUPS, s_sort));
     // Window groups from the top down: the top group's partial needs the most doublings to reach its weight, and
     // they run beside the accumulate of the groups below.  With G == 1 every stream below is the caller's.
@@ -566,45 +515,12 @@ int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points *pts, 
         uint32_t *counts = sc.d_counts + (size_t)w0 * B, *offsets = sc.d_offsets + (size_t)w0 * B;
         uint32_t *ends = sc.d_cursor + (size_t)w0 * B, *entries = sc.d_entries + (size_t)w0 * n;
         uint32_t *buckets = sc.d_buckets + (size_t)w0 * B * 32, *partials = sc.d_partials + (size_t)w0 * tpw * 64;
-        uint32_t *long_list = sc.d_long + ((size_t)w0 * tpw) / BPP_LONG_SPAN + 16 * g, *d_nlong = sc.d_nlong + g;
+        uint32_t *long_list = sc.d_long + (size_t)w0 * long_per_window, *d_nlong = sc.d_nlong + g;
         const uint32_t group_tiles = (uint32_t)Wg * tpw, group_buckets = (uint32_t)Wg * B;
         // sort: recode + histogram, scan, counting-sort scatter (absolute window numbers: the recoding carry
         // ripples up from window 0)
         trace_mark(ctx, s_sort, "sort>", g);
-        if (sort2) {
-            const uint32_t *dig = sc.d_dig + (size_t)w0 * ld;
-            k_sort2_count<<<dim3(chunks2, Wg), 1024, 0, s_sort>>>(dig, (uint32_t)n, ld, nb, sc.d_chunk);
-            LAUNCH_CHECK(ctx);
-            trace_mark(ctx, s_sort, "count.", g);
-            k_sort2_prefix<<<dim3(nb, Wg), 1024, 0, s_sort>>>(sc.d_chunk, chunks2, counts);
-            LAUNCH_CHECK(ctx);
-            k_sort2_binscan<<<Wg, 256, 0, s_sort>>>(counts, nb, sc.d_binoff);
-            LAUNCH_CHECK(ctx);
-            trace_mark(ctx, s_sort, "hist.", g);
-            if (prof) cudaEventRecord(ctx->ev[1], s);
-            k_sort2_split<<<dim3(chunks2, Wg), 1024, 0, s_sort>>>(dig, (uint32_t)n, ld, nb, sc.d_chunk, sc.d_binoff,
-                                                                 sc.d_tmp);
-            LAUNCH_CHECK(ctx);
-            if (prof) cudaEventRecord(ctx->ev[2], s);
-            trace_mark(ctx, s_sort, "split.", g);
-            k_sort2_fine<<<dim3(nb, Wg), 1024, 2 * SORT2_CAP * 4, s_sort>>>(sc.d_tmp, (uint32_t)n, nb, B, sc.d_binoff, entries,
-                                                                           offsets, ends);
-            LAUNCH_CHECK(ctx);
-        } else if (smem_sort) {
-            const uint32_t ch = (uint32_t)chunks_of[g], chunk_len = (uint32_t)(((n + ch - 1) / ch + 7) & ~(size_t)7);
-            k_sort_count<<<dim3(ch, Wg), 1024, B * 4, s_sort>>>(sc.d_dig + (size_t)w0 * ld, (uint32_t)n, ld, chunk_len, B, sc.d_chunk);
-            LAUNCH_CHECK(ctx);
-            k_chunk_prefix<<<(group_buckets + 255) / 256, 256, 0, s_sort>>>(sc.d_chunk, ch, B, group_buckets, counts);
-            LAUNCH_CHECK(ctx);
-            trace_mark(ctx, s_sort, "hist.", g);
-            if (prof) cudaEventRecord(ctx->ev[1], s);
-            k_window_scan<<<Wg, 1024, 0, s_sort>>>(counts, B, offsets, ends, 1);
-            LAUNCH_CHECK(ctx);
-            if (prof) cudaEventRecord(ctx->ev[2], s);
-            k_sort_place<<<dim3(ch, Wg), 1024, B * 4, s_sort>>>(sc.d_dig + (size_t)w0 * ld, (uint32_t)n, ld, chunk_len, B,
-                                                               sc.d_chunk, offsets, entries);
-            LAUNCH_CHECK(ctx);
-        } else {
+        {
             k_digit_hist<<<sb, 256, 0, s_sort>>>(d_scalars, (uint32_t)n, c, w0, w0 + Wg, sc.d_counts);
             LAUNCH_CHECK(ctx);
             trace_mark(ctx, s_sort, "hist.", g);

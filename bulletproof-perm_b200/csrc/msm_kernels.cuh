@@ -148,368 +148,9 @@ __global__ void k_digit_scatter(const uint32_t *__restrict__ scalars, uint32_t n
     }
 }
 
-// ---- sort through shared memory (the form used from ~2^15 points) -----------------------------------
-// The global-atomic sort above is bound by the L2 atomic units (2 x 16.8 M random atomics at 2^20 points, c = 16:
-// 99 + 210 us) and, beside the accumulate, its blocks take the SM slots the accumulate needs.  Here one block owns
-// (window, chunk of the scalars) and keeps that window's whole counter array in shared memory (2^(c-1) x 4 B =
-// 128 KiB at c = 16):
-//   k_sort_digits  one pass over the scalars: every window's signed digit as a 4-byte word, dig[window][scalar]
-//                  (the per-window blocks below read 4 bytes per scalar instead of the 32-byte scalar)
-//   k_sort_count   per-chunk histogram with shared-memory atomics, written out as chunk_counts[window][chunk][bucket]
-//   k_chunk_prefix exclusive prefix over the chunks of every bucket (in place) + the bucket totals
-//   k_window_scan  (ends_mode) bucket offsets and ends from the totals
-//   k_sort_place   cursor = offset + chunk prefix in shared memory; position by shared-memory atomic; 4-byte store
-// all digits of every scalar in one pass over the scalars: dig[w][i] = magnitude | sign << 31 (0 = skip)
-// (row stride ld = n rounded up to a multiple of 4, so that every row can be read as uint4)
-__global__ void __launch_bounds__(256) k_sort_digits(const uint32_t *__restrict__ scalars, uint32_t n, uint32_t ld, int c,
-                                                     int W, uint32_t *__restrict__ dig) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t s[8];
-    const uint4 *p = reinterpret_cast<const uint4 *>(scalars + 8 * (size_t)i);
-    uint4 lo = __ldg(p), hi = __ldg(p + 1);
-    s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w; s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
-    const uint32_t half = 1u << (c - 1);
-    uint32_t carry = 0;
-    for (int w = 0; w < W; w++) {
-        uint32_t raw = sc_window(s, w * c, c) + carry;
-        carry = raw > half ? 1u : 0u;
-        uint32_t mag = carry ? (1u << c) - raw : raw;
-        dig[(size_t)w * ld + i] = mag ? (mag | (carry << 31)) : 0u;
-    }
-}
-
-// grid (chunks, windows of the group), dynamic shared memory B x 4 bytes; dig points at the group's first window.
-// chunk_len is a multiple of 8: a thread takes 8 consecutive digits per trip (two 16-byte loads in flight).
-__global__ void __launch_bounds__(1024) k_sort_count(const uint32_t *__restrict__ dig, uint32_t n, uint32_t ld,
-                                                     uint32_t chunk_len, uint32_t B,
-                                                     uint32_t *__restrict__ chunk_counts) {
-    extern __shared__ uint32_t sh_cnt[];
-    const uint32_t j = blockIdx.x, wl = blockIdx.y;
-    for (uint32_t b = threadIdx.x; b < B; b += blockDim.x) sh_cnt[b] = 0;
-    __syncthreads();
-    const uint32_t *dw = dig + (size_t)wl * ld;
-    const uint32_t beg = j * chunk_len, end = min(n, beg + chunk_len);
-    for (uint32_t i = beg + 8 * threadIdx.x; i < end; i += 8 * blockDim.x) {
-        uint32_t d[8];
-        if (i + 8 <= end) {
-            uint4 lo = __ldg(reinterpret_cast<const uint4 *>(dw + i)), hi = __ldg(reinterpret_cast<const uint4 *>(dw + i + 4));
-            d[0] = lo.x; d[1] = lo.y; d[2] = lo.z; d[3] = lo.w; d[4] = hi.x; d[5] = hi.y; d[6] = hi.z; d[7] = hi.w;
-        } else {
-#pragma unroll
-            for (int k = 0; k < 8; k++) d[k] = i + k < end ? dw[i + k] : 0u;
-        }
-#pragma unroll
-        for (int k = 0; k < 8; k++)
-            if (d[k]) atomicAdd(&sh_cnt[(d[k] & 0x7fffffffu) - 1], 1u);
-    }
-    __syncthreads();
-    uint32_t *out = chunk_counts + ((size_t)wl * gridDim.x + j) * B;
-    for (uint32_t b = threadIdx.x; b < B; b += blockDim.x) out[b] = sh_cnt[b];
-}
-
-// one thread per (window, bucket): chunk_counts[w][j][b] <- sum_{j' < j} counts, totals[w][b] <- sum_j counts
-__global__ void __launch_bounds__(256) k_chunk_prefix(uint32_t *__restrict__ chunk_counts, uint32_t chunks, uint32_t B,
-                                                      uint32_t total_buckets, uint32_t *__restrict__ totals) {
-    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= total_buckets) return;
-    const uint32_t wl = g / B, b = g - wl * B;
-    uint32_t *p = chunk_counts + (size_t)wl * chunks * B + b;
-    uint32_t run = 0;
-    uint32_t j = 0;
-    for (; j + 4 <= chunks; j += 4) {   // four independent loads in flight
-        uint32_t v0 = p[(size_t)j * B], v1 = p[(size_t)(j + 1) * B], v2 = p[(size_t)(j + 2) * B], v3 = p[(size_t)(j + 3) * B];
-        p[(size_t)j * B] = run;
-        p[(size_t)(j + 1) * B] = run + v0;
-        p[(size_t)(j + 2) * B] = run + v0 + v1;
-        p[(size_t)(j + 3) * B] = run + v0 + v1 + v2;
-        run += v0 + v1 + v2 + v3;
-    }
-    for (; j < chunks; j++) {
-        uint32_t v = p[(size_t)j * B];
-        p[(size_t)j * B] = run;
-        run += v;
-    }
-    totals[g] = run;
-}
-
-__global__ void __launch_bounds__(1024) k_sort_place(const uint32_t *__restrict__ dig, uint32_t n, uint32_t ld,
-                                                     uint32_t chunk_len, uint32_t B,
-                                                     const uint32_t *__restrict__ chunk_prefix,
-                                                     const uint32_t *__restrict__ offsets,
-                                                     uint32_t *__restrict__ entries) {
-    extern __shared__ uint32_t sh_cur[];
-    const uint32_t j = blockIdx.x, wl = blockIdx.y;
-    const uint32_t *pre = chunk_prefix + ((size_t)wl * gridDim.x + j) * B, *off = offsets + (size_t)wl * B;
-    for (uint32_t b = threadIdx.x; b < B; b += blockDim.x) sh_cur[b] = off[b] + pre[b];
-    __syncthreads();
-    uint32_t *ew = entries + (size_t)wl * n;
-    const uint32_t *dw = dig + (size_t)wl * ld;
-    const uint32_t beg = j * chunk_len, end = min(n, beg + chunk_len);
-    for (uint32_t i = beg + 8 * threadIdx.x; i < end; i += 8 * blockDim.x) {
-        uint32_t d[8];
-        if (i + 8 <= end) {
-            uint4 lo = __ldg(reinterpret_cast<const uint4 *>(dw + i)), hi = __ldg(reinterpret_cast<const uint4 *>(dw + i + 4));
-            d[0] = lo.x; d[1] = lo.y; d[2] = lo.z; d[3] = lo.w; d[4] = hi.x; d[5] = hi.y; d[6] = hi.z; d[7] = hi.w;
-        } else {
-#pragma unroll
-            for (int k = 0; k < 8; k++) d[k] = i + k < end ? dw[i + k] : 0u;
-        }
-#pragma unroll
-        for (int k = 0; k < 8; k++)
-            if (d[k]) {
-                uint32_t pos = atomicAdd(&sh_cur[(d[k] & 0x7fffffffu) - 1], 1u);
-                ew[pos] = (i + k) | (d[k] & 0x80000000u);
-            }
-    }
-}
-
-// ---- two-pass sort with coalesced writes (the form used for large inputs) ----------------------------
-// Measured (profiles/r1_msm_sort.md): what bounds both sorts above is not the atomics but the 16.8 M scattered 4-byte
-// writes of the sorted entry list (~210 us at 2^20 points, c = 16, whether the position comes from an L2 atomic or
-// from shared memory, and whether the write is a store or a RED).  So the entries are moved twice, both times in
-// runs that consecutive threads write:
-//   pass A  by the high bits of the bucket number (coarse bins of 2^SORT2_LOW buckets): a block takes a chunk of
-//           SORT2_CHUNK digits of one window, ranks them per coarse bin in shared memory, stages the chunk in bin
-//           order and writes every bin's run to its place in `tmp` (k_sort2_count, k_sort2_prefix, k_sort2_binscan,
-//           k_sort2_split); an item is fine bits << 24 | sign << 23 | point index (hence n <= 2^23)
-//   pass B  one block per (window, coarse bin): the bin (about SORT2_CHUNK items) is sorted by its low bits inside
-//           shared memory and written out linearly as the final entry list, together with the offsets and ends of
-//           its buckets (k_sort2_fine); a bin too large for shared memory (hot buckets) is counted and placed tile by
-//           tile with direct writes.
-#define SORT2_LOW 8
-#define SORT2_CHUNK 8192
-#define SORT2_CAP 12288          // items of one coarse bin held in shared memory (2 x 48 KiB)
-
-FE_INLINE void sort2_load8(uint32_t d[8], const uint32_t *__restrict__ dw, uint32_t i, uint32_t end) {
-    if (i + 8 <= end) {
-        uint4 lo = __ldg(reinterpret_cast<const uint4 *>(dw + i)), hi = __ldg(reinterpret_cast<const uint4 *>(dw + i + 4));
-        d[0] = lo.x; d[1] = lo.y; d[2] = lo.z; d[3] = lo.w; d[4] = hi.x; d[5] = hi.y; d[6] = hi.z; d[7] = hi.w;
-    } else {
-#pragma unroll
-        for (int k = 0; k < 8; k++) d[k] = i + k < end ? dw[i + k] : 0u;
-    }
-}
-
-// exclusive scan of cnt[0..len) (len <= 256) into out[0..len], by warp 0 (8 entries per lane); callers sync around it
-FE_INLINE void sort2_scan256(const uint32_t *cnt, uint32_t *out, uint32_t len) {
-    if (threadIdx.x >= 32) return;
-    const uint32_t lane = threadIdx.x;
-    uint32_t v[8], sum = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        v[k] = 8 * lane + k < len ? cnt[8 * lane + k] : 0u;
-        sum += v[k];
-    }
-    uint32_t incl = sum;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= (uint32_t)d) incl += o;
-    }
-    uint32_t run = incl - sum;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        if (8 * lane + k < len) out[8 * lane + k] = run;
-        run += v[k];
-    }
-    if (lane == 31) out[len] = incl;
-}
-
-// grid (chunks, windows of the group), 1024 threads: coarse-bin histogram of one chunk -> chunk_counts[wl][bin][chunk]
-__global__ void __launch_bounds__(1024) k_sort2_count(const uint32_t *__restrict__ dig, uint32_t n, uint32_t ld, uint32_t nb,
-                                                      uint32_t *__restrict__ chunk_counts) {
-    __shared__ uint32_t cnt[256];
-    const uint32_t j = blockIdx.x, wl = blockIdx.y, chunks = gridDim.x;
-    if (threadIdx.x < 256) cnt[threadIdx.x] = 0;
-    __syncthreads();
-    const uint32_t *dw = dig + (size_t)wl * ld;
-    const uint32_t beg = j * SORT2_CHUNK, end = min(n, beg + SORT2_CHUNK);
-    uint32_t d[8];
-    const uint32_t i = beg + 8 * threadIdx.x;
-    if (i < end) {
-        sort2_load8(d, dw, i, end);
-#pragma unroll
-        for (int k = 0; k < 8; k++)
-            if (d[k]) atomicAdd(&cnt[((d[k] & 0x7fffffffu) - 1) >> SORT2_LOW], 1u);
-    }
-    __syncthreads();
-    if (threadIdx.x < nb) chunk_counts[((size_t)wl * nb + threadIdx.x) * chunks + j] = cnt[threadIdx.x];
-}
-
-// grid (coarse bins, windows), 1024 threads: exclusive prefix over the chunks of one (window, bin), in place; total out
-__global__ void __launch_bounds__(1024) k_sort2_prefix(uint32_t *__restrict__ chunk_counts, uint32_t chunks,
-                                                       uint32_t *__restrict__ totals) {
-    __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t carry_sh;
-    uint32_t *row = chunk_counts + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * chunks;
-    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry_sh = 0;
-    __syncthreads();
-    for (uint32_t base = 0; base < chunks; base += 1024) {
-        const uint32_t t = base + threadIdx.x;
-        const uint32_t v = t < chunks ? row[t] : 0u;
-        uint32_t incl = v;
-#pragma unroll
-        for (int dlt = 1; dlt < 32; dlt <<= 1) {
-            uint32_t o = __shfl_up_sync(0xffffffffu, incl, dlt);
-            if (lane >= (uint32_t)dlt) incl += o;
-        }
-        if (lane == 31) warp_sums[wid] = incl;
-        __syncthreads();
-        if (wid == 0) {
-            uint32_t ws = warp_sums[lane], iv = ws;
-#pragma unroll
-            for (int dlt = 1; dlt < 32; dlt <<= 1) {
-                uint32_t o = __shfl_up_sync(0xffffffffu, iv, dlt);
-                if (lane >= (uint32_t)dlt) iv += o;
-            }
-            warp_sums[lane] = iv - ws;
-        }
-        __syncthreads();
-        const uint32_t carry = carry_sh;
-        if (t < chunks) row[t] = carry + warp_sums[wid] + incl - v;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry_sh = carry + warp_sums[wid] + incl;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) totals[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = carry_sh;
-}
-
-// grid (windows), 256 threads: exclusive scan of the nb bin totals of a window -> bin_off[wl][0..nb] (nb <= 256)
-__global__ void __launch_bounds__(256) k_sort2_binscan(const uint32_t *__restrict__ totals, uint32_t nb,
-                                                       uint32_t *__restrict__ bin_off) {
-    __shared__ uint32_t sh[257];
-    const uint32_t wl = blockIdx.x;
-    if (threadIdx.x < nb) sh[threadIdx.x + 1] = totals[(size_t)wl * nb + threadIdx.x];
-    if (threadIdx.x == 0) sh[0] = 0;
-    __syncthreads();
-    if (threadIdx.x == 0)
-        for (uint32_t b = 1; b <= nb; b++) sh[b] += sh[b - 1];
-    __syncthreads();
-    if (threadIdx.x <= nb) bin_off[(size_t)wl * (nb + 1) + threadIdx.x] = sh[threadIdx.x];
-    if (threadIdx.x == 0 && nb == 256) bin_off[(size_t)wl * (nb + 1) + 256] = sh[256];
-}
-
-// grid (chunks, windows), 1024 threads: rank the chunk's items per coarse bin, stage them in bin order, write the runs
-__global__ void __launch_bounds__(1024) k_sort2_split(const uint32_t *__restrict__ dig, uint32_t n, uint32_t ld, uint32_t nb,
-                                                      const uint32_t *__restrict__ chunk_prefix,
-                                                      const uint32_t *__restrict__ bin_off, uint32_t *__restrict__ tmp) {
-    __shared__ uint32_t cnt[256], start[257], gbase[256];
-    __shared__ uint32_t staged[SORT2_CHUNK];
-    const uint32_t j = blockIdx.x, wl = blockIdx.y, chunks = gridDim.x;
-    if (threadIdx.x < 256) cnt[threadIdx.x] = 0;
-    __syncthreads();
-    const uint32_t *dw = dig + (size_t)wl * ld;
-    const uint32_t beg = j * SORT2_CHUNK, end = min(n, beg + SORT2_CHUNK);
-    uint32_t d[8], rank[8];
-    const uint32_t i = beg + 8 * threadIdx.x;
-#pragma unroll
-    for (int k = 0; k < 8; k++) d[k] = 0;
-    if (i < end) {
-        sort2_load8(d, dw, i, end);
-#pragma unroll
-        for (int k = 0; k < 8; k++)
-            if (d[k]) rank[k] = atomicAdd(&cnt[((d[k] & 0x7fffffffu) - 1) >> SORT2_LOW], 1u);
-    }
-    __syncthreads();
-    sort2_scan256(cnt, start, nb);
-    if (threadIdx.x < nb)
-        gbase[threadIdx.x] = bin_off[(size_t)wl * (nb + 1) + threadIdx.x] +
-                             chunk_prefix[((size_t)wl * nb + threadIdx.x) * chunks + j];
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 8; k++)
-        if (d[k]) {
-            const uint32_t bkt = (d[k] & 0x7fffffffu) - 1;
-            staged[start[bkt >> SORT2_LOW] + rank[k]] = ((bkt & ((1u << SORT2_LOW) - 1u)) << 24) | ((d[k] >> 31) << 23) | (i + k);
-        }
-    __syncthreads();
-    const uint32_t total = start[nb];
-    uint32_t *tw = tmp + (size_t)wl * n;
-    for (uint32_t k = threadIdx.x; k < total; k += blockDim.x) {
-        uint32_t lo = 0, hi = nb - 1;     // the bin of staged position k: last b with start[b] <= k
-        while (lo < hi) {
-            uint32_t mid = (lo + hi + 1) >> 1;
-            if (start[mid] <= k) lo = mid;
-            else hi = mid - 1;
-        }
-        tw[gbase[lo] + (k - start[lo])] = staged[k];
-    }
-}
-
-// grid (coarse bins, windows), 1024 threads, dynamic shared memory 2 x SORT2_CAP x 4 bytes
-__global__ void __launch_bounds__(1024) k_sort2_fine(const uint32_t *__restrict__ tmp, uint32_t n, uint32_t nb, uint32_t B,
-                                                     const uint32_t *__restrict__ bin_off, uint32_t *__restrict__ entries,
-                                                     uint32_t *__restrict__ offsets, uint32_t *__restrict__ ends) {
-    extern __shared__ uint32_t sh_items[];          // [SORT2_CAP] items, then [SORT2_CAP] sorted output
-    __shared__ uint32_t cnt[1u << SORT2_LOW], pre[(1u << SORT2_LOW) + 1];
-    const uint32_t bin = blockIdx.x, wl = blockIdx.y;
-    const uint32_t FINE = min(B, 1u << SORT2_LOW);
-    const uint32_t off = bin_off[(size_t)wl * (nb + 1) + bin], m = bin_off[(size_t)wl * (nb + 1) + bin + 1] - off;
-    const uint32_t *src = tmp + (size_t)wl * n + off;
-    uint32_t *dst = entries + (size_t)wl * n + off;
-    if (threadIdx.x < FINE) cnt[threadIdx.x] = 0;
-    __syncthreads();
-    const bool fits = m <= SORT2_CAP;
-    uint32_t *sh_out = sh_items + SORT2_CAP;
-    constexpr int PER = SORT2_CAP / 1024;   // 12 items per thread when the bin fits
-    uint32_t it[PER], rk[PER];
-    if (fits) {
-#pragma unroll
-        for (int k = 0; k < PER; k++) {
-            const uint32_t p = threadIdx.x + 1024 * k;
-            it[k] = p < m ? src[p] : 0xffffffffu;
-        }
-#pragma unroll
-        for (int k = 0; k < PER; k++)
-            if (threadIdx.x + 1024 * k < m) rk[k] = atomicAdd(&cnt[it[k] >> 24], 1u);
-    } else {
-        for (uint32_t p0 = 0; p0 < m; p0 += 8 * 1024) {   // 8 loads in flight per thread
-            uint32_t v[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const uint32_t p = p0 + threadIdx.x + 1024 * k;
-                v[k] = p < m ? src[p] : 0xffffffffu;
-            }
-#pragma unroll
-            for (int k = 0; k < 8; k++)
-                if (p0 + threadIdx.x + 1024 * k < m) atomicAdd(&cnt[v[k] >> 24], 1u);
-        }
-    }
-    __syncthreads();
-    sort2_scan256(cnt, pre, FINE);
-    __syncthreads();
-    if (threadIdx.x < FINE) {
-        const size_t g = (size_t)wl * B + (size_t)bin * FINE + threadIdx.x;
-        offsets[g] = off + pre[threadIdx.x];
-        ends[g] = off + pre[threadIdx.x + 1];
-    }
-    if (fits) {
-#pragma unroll
-        for (int k = 0; k < PER; k++)
-            if (threadIdx.x + 1024 * k < m)
-                sh_out[pre[it[k] >> 24] + rk[k]] = (it[k] & 0x7fffffu) | (((it[k] >> 23) & 1u) << 31);
-        __syncthreads();
-        for (uint32_t p = threadIdx.x; p < m; p += blockDim.x) dst[p] = sh_out[p];
-    } else {
-        __syncthreads();
-        if (threadIdx.x < FINE) cnt[threadIdx.x] = pre[threadIdx.x];   // cursors
-        __syncthreads();
-        for (uint32_t p0 = 0; p0 < m; p0 += 8 * 1024) {
-            uint32_t v[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const uint32_t p = p0 + threadIdx.x + 1024 * k;
-                v[k] = p < m ? src[p] : 0xffffffffu;
-            }
-#pragma unroll
-            for (int k = 0; k < 8; k++)
-                if (p0 + threadIdx.x + 1024 * k < m)
-                    dst[atomicAdd(&cnt[v[k] >> 24], 1u)] = (v[k] & 0x7fffffu) | (((v[k] >> 23) & 1u) << 31);
-        }
-    }
-}
+// (Two other sort forms were built and measured in round 1 - per-window counters in shared memory, and a two-pass sort
+// with coalesced writes.  Neither beat the global-atomic form beside the accumulate; they were removed from the product
+// in round 2.  Record: profiles/r1_msm_sort.md, code: tools/experiments/msm_sort_forms_2_3.patch.)
 
 // ---- bucket accumulation: the dominant kernel ------------------------------------------------
 // The bucket-sorted entry list of each window is cut into tiles of `tile_len` entries; one thread

@@ -127,12 +127,6 @@ int bpp_set_window_bits(bpp_ctx *ctx, int c);
  * doublings to the group's weight) run on internal high-priority streams beside the accumulate of the current
  * group; the call still is stream-ordered on the caller's stream.  The result bytes do not depend on it. */
 int bpp_set_msm_groups(bpp_ctx *ctx, int groups);
-/* Sort form of the MSM: 0 = automatic (by input size), 1 = global atomics (histogram + scatter on L2 atomics),
- * 2 = through shared memory (one block per window and chunk of scalars keeps the window's counters in shared
- * memory; measured, not faster: both are bound by the scattered 4-byte writes of the sorted list), 3 = two passes
- * with coalesced writes (by the high bits of the bucket number, then by the low bits inside shared memory).  The
- * result bytes do not depend on it.  A tuning hook. */
-int bpp_set_msm_sort(bpp_ctx *ctx, int mode);
 /* Entries per accumulate tile (one thread adds one tile of the bucket-sorted entry list): 0 = by input size (32, and 64
  * from 3 M points), else 8..256.  Result-neutral tuning hook. */
 int bpp_set_msm_tile(bpp_ctx *ctx, int tile_len);

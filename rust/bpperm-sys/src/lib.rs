@@ -50,7 +50,6 @@ extern "C" {
     pub fn bpp_set_window_bits(ctx: *mut bpp_ctx, c: c_int) -> c_int;
     pub fn bpp_set_msm_groups(ctx: *mut bpp_ctx, groups: c_int) -> c_int;
     pub fn bpp_set_msm_partition(ctx: *mut bpp_ctx, sizes: *const c_int, count: c_int) -> c_int;
-    pub fn bpp_set_msm_sort(ctx: *mut bpp_ctx, mode: c_int) -> c_int;
 
     pub fn bpp_inner_product(ctx: *mut bpp_ctx, a: *const u8, la: usize, b: *const u8, lb: usize, out: *mut u8) -> c_int;
     pub fn bpp_hadamard_V(ctx: *mut bpp_ctx, a: *const u8, la: usize, b: *const u8, lb: usize, out: *mut u8) -> c_int;

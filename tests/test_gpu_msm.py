@@ -292,13 +292,10 @@ def test_wait_previous_producer_consumer_loop():
     be.close()
 
 
-@pytest.mark.parametrize("mode", [2, 3])
 @pytest.mark.parametrize("c,groups", [(16, 1), (16, 4), (15, 2), (13, 2), (12, 1), (11, 3), (8, 1), (5, 8), (4, 1), (0, 0)])
-def test_sort_forms_match_oracle(backend, c, groups, mode):
-    """bpp_set_msm_sort: the sort through shared memory (2: per-chunk histograms, chunk prefixes, shared-memory cursors)
-    and the two-pass sort with coalesced writes (3: coarse bins, then the low bits inside shared memory) against the C
-    restatement and against the global-atomic sort, on random + skewed + zero + extreme scalars (hot buckets overflow
-    the shared-memory capacity of a coarse bin; all-ones windows exercise the recoding carry across windows)."""
+def test_skewed_scalars_match_oracle(backend, c, groups):
+    """random + skewed + zero + extreme scalars against the C restatement: hot buckets (one scalar repeated 1 500 and
+    15 000 times) go through the hot-bucket queue, all-ones windows exercise the recoding carry across windows."""
     import numpy as np
     from oracle import cref
     n = 40000 + 1234
@@ -307,11 +304,11 @@ def test_sort_forms_match_oracle(backend, c, groups, mode):
     sc = rs.randint(0, 256, size=(n, 32), dtype=np.uint8)
     sc[:, 31] &= 0x0F
     sc[100:1600] = sc[7]               # hot buckets in every window
-    sc[21000:36000] = sc[8]            # 15 000 equal scalars: a coarse bin larger than its shared-memory staging
+    sc[21000:36000] = sc[8]            # 15 000 equal scalars
     sc[2000:2300, 2:] = 0              # only the lowest windows populated
     sc[2300:2400] = 0                  # zero scalars
     sc[2400:2500, :31] = 0xFF          # runs of ones: carries ripple through every window
-    sc[2500:2600, :16] = 0x80          # windows equal to `half` at c = 8 / 16: the carry look-back continues downwards
+    sc[2500:2600, :16] = 0x80          # windows equal to `half` at c = 8 / 16
     sc[2500:2600, 0] = 0x81
     sc[2600:2700, :] = 0
     sc[2600:2700, 1::2] = 0x80         # 0x8000 in every 16-bit window: digits exactly `half`, no carry
@@ -320,18 +317,61 @@ def test_sort_forms_match_oracle(backend, c, groups, mode):
     backend.set_window_bits(c)
     backend.set_msm_groups(groups)
     try:
-        backend.set_msm_sort(mode)
         got = backend.vartime_multiscalar_mul(sc.tobytes(), table)
         again = backend.vartime_multiscalar_mul(sc.tobytes(), table)
-        backend.set_msm_sort(1)
-        atomics = backend.vartime_multiscalar_mul(sc.tobytes(), table)
     finally:
-        backend.set_msm_sort(0)
         backend.set_window_bits(0)
         backend.set_msm_groups(0)
         table.free()
-    assert got == again == atomics
+    assert got == again
     assert got == cref.msm(sc.tobytes(), cref.from_uniform(blobs.tobytes()))
+
+
+@pytest.mark.parametrize("log_n", [12, 13])
+@pytest.mark.parametrize("groups,tile", [(0, 0), (4, 0), (8, 8), (3, 16)])
+def test_hot_buckets_in_every_window_group(backend, log_n, groups, tile):
+    """Small inputs in the pipelined / submitted form with hot buckets in EVERY window: each window group queues its own
+    hot buckets and the groups' fix-up kernels run concurrently on different streams, so the queues must not share
+    memory (at n = 2^12 the per-group regions overlapped).  Several equal scalars repeated ~800 times
+    each give every window of every group several hot buckets; submitted twice in flight + joined vs the C restatement."""
+    import numpy as np
+    import torch
+    from oracle import cref
+    n = 1 << log_n
+    dev = torch.device("cuda:0")
+    rs = np.random.RandomState(5200 + log_n)
+    blobs = rs.randint(0, 256, size=(n, 64), dtype=np.uint8)
+    sets = []
+    for k in range(3):
+        sc = rs.randint(0, 256, size=(n, 32), dtype=np.uint8)
+        sc[:, 31] &= 0x0F
+        reps = 3 + k
+        span = (n - 64) // reps
+        for r in range(reps):          # `reps` different scalars, each repeated span times: hot buckets in all windows
+            sc[r * span:(r + 1) * span] = sc[n - 1 - r]
+        sets.append(sc)
+    table = backend.points_from_uniform(blobs.tobytes())
+    pts = cref.from_uniform(blobs.tobytes())
+    want = [cref.msm(s.tobytes(), pts) for s in sets]
+    d_sets = [torch.from_numpy(s).to(dev) for s in sets]
+    outs = torch.zeros(3, 160, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    backend.set_msm_groups(groups)
+    backend.set_msm_tile(tile)
+    try:
+        for rep in range(2):
+            for i in range(3):
+                backend.msm_submit_dev(d_sets[i].data_ptr(), table, 0, n, outs[i].data_ptr())
+            backend.msm_wait()
+            backend.synchronize()
+            for i in range(3):
+                assert bytes(outs[i, :32].cpu().numpy().tobytes()) == want[i], (rep, i)
+        for i in range(3):
+            assert backend.vartime_multiscalar_mul(sets[i].tobytes(), table) == want[i]
+    finally:
+        backend.set_msm_groups(0)
+        backend.set_msm_tile(0)
+        table.free()
 
 
 def test_submitted_partials_sum_to_the_full_result(backend):

@@ -12,7 +12,6 @@ dev = torch.device("cuda", 0)
 stream = torch.cuda.current_stream(dev)
 be.set_stream(stream.cuda_stream)
 import os
-be.set_msm_sort(int(os.environ.get("BPP_SORT", "0")))
 be.set_msm_tile(int(os.environ.get("BPP_TILE", "0")))
 log_n = int(sys.argv[1])
 parts = [[int(x) for x in p.split(",")] for p in sys.argv[2].split(";")]
