@@ -154,6 +154,32 @@ def synth_shuffle_batch(k: int, count: int, rank: int):
     return b"".join(aL), b"".join(aR), b"".join(aO), g.tobytes(), b"".join(vv), seeds.tobytes()
 
 
+def synth_shuffle_inputs(k: int, count: int, rank: int, salt: int):
+    """What defines `count` independent k-card shuffles (the inputs of bpp_acp_batch_gen_shuffle_witness): the deck
+    1..k (weights.rs:38-56 create_variables), one permutation and one challenge value X per proof, uniform blindings
+    gamma (count x m) and prover RNG seeds.  numpy arrays: deck (k,32) u8, perm (count,k) u32, x (count,32) u8,
+    gamma (count*m,32) u8, seeds (count,32) u8."""
+    rs = np.random.RandomState(777 + 1000 * salt + rank)
+    deck = np.zeros((k, 32), dtype=np.uint8)
+    for i in range(k):
+        deck[i, :4] = np.frombuffer((i + 1).to_bytes(4, "little"), dtype=np.uint8)
+    perm = np.stack([rs.permutation(k) for _ in range(count)]).astype(np.uint32)
+    x = rs.randint(0, 256, size=(count, 32), dtype=np.uint8)
+    x[:, 31] = 0
+    m = 2 * k + 1
+    gamma = rs.randint(0, 256, size=(count * m, 32), dtype=np.uint8)
+    gamma[:, 31] &= 0x0F
+    seeds = rs.randint(0, 256, size=(count, 32), dtype=np.uint8)
+    return deck, perm, x, gamma, seeds
+
+
+def shuffle_witness_bytes(k, deck, perm_row, x_row):
+    """a_L, a_R, a_O, v of one shuffle on the host (bulletproof-perm_b200/weights.py), for the CPU arm."""
+    import bpperm_b200
+    v, a_L, a_R, a_O = bpperm_b200.weights.shuffle_witness(k, [int(j) for j in perm_row], int.from_bytes(bytes(x_row), "little"))
+    return _sc_bytes(a_L), _sc_bytes(a_R), _sc_bytes(a_O), _sc_bytes(v)
+
+
 N_LANES = int(os.environ.get("BPP_LANES", "3"))   # batches in flight in the pipelined legs
 LANE_PRIORITY_SPLIT = os.environ.get("BPP_LANE_SPLIT", "1") != "0"
 FB_WINDOW_BITS = int(os.environ.get("BPP_FB_WINDOW", "16"))   # fixed-base table window: 16 windows x 32768 entries x 96 B = 50 MB per generator
@@ -318,6 +344,509 @@ def run_reference(args):
     return 0
 
 
+# ---------------------------------------------------------------------------------- algorithmic work
+DECOMP_IMAD = 275 * 72   # one Ristretto (de)compression: an inverse square root (254 squarings + 11 multiplications) and
+                         # ~10 more multiplications at 72 IMAD.WIDE.U32 per field multiplication (madd = 7 x 72)
+SC_MUL_IMAD = 136        # one scalar product mod l: 64 (product) + 64 (Montgomery reduction) + 8 (final subtraction)
+
+
+def _next_pow2(n):
+    p = 1
+    while p < n:
+        p *= 2
+    return p
+
+
+def shuffle_imad_per_proof(n, Q, m, mode, table_windows, rlc_windows):
+    """Algorithmic IMAD.WIDE.U32 per proof of one prove + verify: fixed-base mixed adds of the
+    prover's commitments (and, in `fixed` mode, of the lg n' rounds of L_j, R_j over 2 n' + 2 generators), the
+    verifier's share of the batch MSM, point (de)compressions and the scalar products of the vector work."""
+    fixed = mode == "fixed"
+    np_ = _next_pow2(n) if fixed else n
+    lg = np_.bit_length() - 1 if fixed else 0
+    terms = (2 * n + 1) + (n + 1) + (2 * n + 1) + 5 * 2 + lg * (2 * np_ + 2)
+    dyn = m + 8 + 2 * lg
+    madds = terms * table_windows + dyn * rlc_windows
+    points = (8 + 2 * lg) + dyn
+    sc_mults = 25 * n + (12 * n + 3 * m + Q) + (dyn + 2 * np_ + 2) + (lg * 3 * np_ + 6 * np_ if fixed else 0)
+    return {"mixed_adds": madds, "compress_decompress": points, "scalar_products": sc_mults,
+            "imad": madds * IMAD_MADD + points * DECOMP_IMAD + sc_mults * SC_MUL_IMAD}
+
+
+# ---------------------------------------------------------------------------------- GPU arm: shuffle proofs
+def _pin(arr):
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
+    return t
+
+
+def shuffle_setup_mode(be, k, mode, window_bits):
+    """Generators as RistrettoPoint::random (lib.rs:164-167,179-180) from a seeded byte stream (the first 2 n + 2 are
+    the stream of the `reference-fixed` runs; `fixed` needs next_pow2(n) per vector), the library-built k-card shuffle
+    circuit, fixed-base tables.  Returns (circuit, generators, encodings g | h | G | H, (n, Q, m, ng), table build s)."""
+    import bpperm_b200
+    G = bpperm_b200.acproof
+    n, Q, m = 2 * k, 4 * k, 2 * k + 1
+    ng = _next_pow2(n) if mode == "fixed" else n
+    rs = np.random.RandomState(4242)
+    blobs = rs.randint(0, 256, size=(2 * n + 2, 64), dtype=np.uint8)
+    if ng > n:   # g, h, G[0..n), H[0..n) as before, then the padding generators
+        extra = np.random.RandomState(4243).randint(0, 256, size=(2 * (ng - n), 64), dtype=np.uint8)
+        blobs = np.concatenate([blobs[:2 + n], extra[:ng - n], blobs[2 + n:], extra[ng - n:]])
+    pts = be.points_from_uniform(blobs.tobytes())
+    enc = be.compress_points(pts)
+    pts.free()
+    cir = G.Circuit.shuffle(be, k)
+    t0 = time.time()
+    gens = G.Generators(be, enc[:32], enc[32:64], [enc[64 + 32 * i: 96 + 32 * i] for i in range(ng)],
+                        [enc[64 + 32 * (ng + i): 96 + 32 * (ng + i)] for i in range(ng)], window_bits)
+    be.synchronize()
+    return cir, gens, enc, (n, Q, m, ng), time.time() - t0
+
+
+def bench_shuffle(E, mode, steps, warmup, want_cpu):
+    """prove + verify of `--batch` independent 52-card proofs per GPU and step, inputs resident (value) and through
+    host buffers (e2e).  Every step works on the next of N_SETS input sets (permutations, challenge values, blindings,
+    prover seeds); the witness is generated on the device from them (bpp_acp_batch_gen_shuffle_witness)."""
+    import torch
+    import bpperm_b200
+    G = bpperm_b200.acproof
+    be, dev, stream, world, rank, args, dist = E["be"], E["dev"], E["stream"], E["world"], E["rank"], E["args"], E["dist"]
+    timed, timed_block, imad_peak = E["timed"], E["timed_block"], E["imad_peak"]
+    k, B = K_CARDS, args.batch
+    cir, gens, enc, (n, Q, m, ng), table_s = shuffle_setup_mode(be, k, mode, FB_WINDOW_BITS)
+    Wn = (256 + FB_WINDOW_BITS - 1) // FB_WINDOW_BITS
+    N_SETS = 4
+    sets = [synth_shuffle_inputs(k, B, rank, s) for s in range(N_SETS)]
+    h_deck = _pin(sets[0][0])
+    d_deck = h_deck.to(dev)
+    hs = [dict(perm=_pin(p), x=_pin(x), gamma=_pin(g), seeds=_pin(sd)) for (_, p, x, g, sd) in sets]
+    ds = [{kk: v.to(dev) for kk, v in h.items()} for h in hs]
+    batch = G.Batch(be, cir, gens, B, mode, b"test")
+    plen = batch.proof_len
+    # commit_variables for every input set: input generation, not timed
+    for s_i in range(N_SETS):
+        batch.gen_shuffle_witness(d_deck.data_ptr(), ds[s_i]["perm"].data_ptr(), ds[s_i]["x"].data_ptr(), ds[s_i]["gamma"].data_ptr(),
+                                  ds[s_i]["seeds"].data_ptr())
+        Vc = batch.commit(None)
+        hs[s_i]["V"] = _pin(np.frombuffer(Vc, dtype=np.uint8))
+        ds[s_i]["V"] = hs[s_i]["V"].to(dev)
+
+    def resident_step(bt, i):
+        d = ds[i % N_SETS]
+        bt.gen_shuffle_witness(d_deck.data_ptr(), d["perm"].data_ptr(), d["x"].data_ptr(), d["gamma"].data_ptr(), d["seeds"].data_ptr())
+        bt.upload_commitments(d["V"].data_ptr())
+        bt.prove()
+        bt.verify(None)          # verifier weights from the OS RNG, bound to each proof's transcript
+
+    def e2e_step(bt, i, h_proofs, h_accept):
+        h = hs[i % N_SETS]
+        bt.gen_shuffle_witness(h_deck.data_ptr(), h["perm"].data_ptr(), h["x"].data_ptr(), h["gamma"].data_ptr(), h["seeds"].data_ptr())
+        bt.upload_commitments(h["V"].data_ptr())                 # the prover binds V to its transcript
+        bt.prove()
+        bt.download_proofs_ptr(h_proofs.data_ptr())              # proofs leave the device ...
+        bt.upload_proofs_ptr(h_proofs.data_ptr(), h["V"].data_ptr())   # ... and come back with the commitments
+        bt.verify(None)
+        bt.download_accept_ptr(h_accept.data_ptr())
+
+    h_proofs = torch.empty(B * plen, dtype=torch.uint8).pin_memory()
+    h_accept = torch.empty(B, dtype=torch.uint8).pin_memory()
+    state = {"ok": True}
+
+    def step_resident(i):
+        resident_step(batch, i)
+
+    def step_e2e(i):
+        e2e_step(batch, i, h_proofs, h_accept)
+        state["ok"] = state["ok"] and bytes(h_accept.numpy().tobytes()) == b"\x01" * B
+
+    l0 = be.launch_count
+    ms_res = timed(step_resident, steps, warmup)
+    launches = (be.launch_count - l0) * steps // (steps + warmup)
+    batch.download_accept_ptr(h_accept.data_ptr())
+    be.synchronize()
+    state["ok"] = bytes(h_accept.numpy().tobytes()) == b"\x01" * B
+    ms_e2e_serial = timed(step_e2e, steps, warmup)
+    serial_last = (warmup + steps - 1) % N_SETS
+    serial_proofs = bytes(h_proofs.numpy().tobytes())
+    # several batches in flight on several streams, one host thread each, so that the copies and the short dependent
+    # kernels of one batch overlap the GPU-filling kernels of another.  Same public calls, same bytes per step; a step
+    # is still one batch of B proofs proved and verified.
+    lanes = []
+    for _ in range(N_LANES):
+        st = torch.cuda.Stream(dev, priority=-1) if LANE_PRIORITY_SPLIT else torch.cuda.Stream(dev)
+        be_l = bpperm_b200.Backend(E["local"])
+        be_l.set_stream(st.cuda_stream)
+        b_l = G.Batch(be_l, cir, gens, B, mode, b"test")
+        b_l.set_priority_split(LANE_PRIORITY_SPLIT)
+        lanes.append({"stream": st, "be": be_l, "batch": b_l, "proofs": torch.empty(B * plen, dtype=torch.uint8).pin_memory(),
+                      "accept": torch.empty(B, dtype=torch.uint8).pin_memory(), "ok": True, "last": None})
+
+    def run_lanes(body):
+        def run(cnt, first):
+            idx = [[first + j for j in range(cnt) if j % N_LANES == kk] for kk in range(N_LANES)]
+            th = [threading.Thread(target=body, args=(lanes[kk], idx[kk])) for kk in range(N_LANES) if idx[kk]]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+        return run
+
+    def lane_resident(lane, idx):
+        for i in idx:
+            resident_step(lane["batch"], i)
+
+    def lane_e2e(lane, idx):
+        for i in idx:
+            e2e_step(lane["batch"], i, lane["proofs"], lane["accept"])
+            lane["ok"] = lane["ok"] and bytes(lane["accept"].numpy().tobytes()) == b"\x01" * B
+            lane["last"] = i
+
+    lane_warm = max(2 * N_LANES, warmup)
+    l2_0 = sum(ln["be"].launch_count for ln in lanes)
+    ms_res2 = timed_block(run_lanes(lane_resident), steps, lane_warm, [ln["stream"] for ln in lanes])
+    launches2 = (sum(ln["be"].launch_count for ln in lanes) - l2_0) * steps // (steps + lane_warm)
+    for ln in lanes:
+        ln["batch"].download_accept_ptr(ln["accept"].data_ptr())
+        ln["be"].synchronize()
+        ln["ok"] = ln["ok"] and bytes(ln["accept"].numpy().tobytes()) == b"\x01" * B
+    ms_e2e = timed_block(run_lanes(lane_e2e), steps, lane_warm, [ln["stream"] for ln in lanes])
+    all_ok = state["ok"] and all(ln["ok"] for ln in lanes)
+    # the same input set gives the same proof bytes on a lane as in the serial run
+    same_bytes = None
+    for ln in lanes:
+        if ln["last"] is not None and ln["last"] % N_SETS == serial_last:
+            same_bytes = bytes(ln["proofs"].numpy().tobytes()) == serial_proofs
+    for ln in lanes:
+        ln["batch"].free()
+        ln["be"].close()
+    fb_ms, fb_madd, fb_add = batch.time_commit_msm(5)
+    if world > 1:
+        okt = torch.tensor([1 if all_ok else 0], device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        all_ok = bool(okt.item())
+    out = None
+    if rank == 0:
+        total = B * world
+        value_single = total * steps / (ms_res * 1e-3)
+        value_lanes = total * steps / (ms_res2 * 1e-3)
+        two = value_lanes > value_single
+        value, ms_step = (value_lanes, ms_res2 / steps) if two else (value_single, ms_res / steps)
+        e2e = total * steps / (ms_e2e * 1e-3)
+        fb_imads = fb_madd * IMAD_MADD + fb_add * IMAD_ADD
+        ach = fb_imads / (fb_ms * 1e-3)
+        alg = shuffle_imad_per_proof(n, Q, m, mode, Wn, 16)
+        lg = (ng.bit_length() - 1) if mode == "fixed" else 0
+        h2d = k * 32 + B * (4 * k + 32 + 32 * m + 32) + B * 32 * m + B * plen + B * 32 * m
+        fb_kernel = "k_fb_msm_warp" if B >= 16 * 148 else "k_fb_msm"
+        traffic_file = "r2_ncu_full_k_fb_msm_warp.csv" if fb_kernel == "k_fb_msm_warp" else "r1_ncu_full_k_fb_msm.csv"
+        gens_n = 2 * ng + 2
+        table_gib = gens_n * Wn * 2 ** (FB_WINDOW_BITS - 1) * 96 / 2**30
+        out = {
+            "metric": "shuffle proofs/sec prove+verify (52-card)", "value": value, "unit": "proofs/s", "n_gpus": world,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32 (8x32-bit limbs, IMAD.WIDE.U32)", "data": "synthetic",
+            "mode": (f"{N_LANES} batches in flight on {N_LANES} urgent streams (one host thread each; table-gather MSMs on "
+                     "lowest-priority streams), inputs resident" if two else "one batch at a time on one stream, inputs resident"),
+            "single_stream": {"value": value_single, "ms_per_step": ms_res / steps, "steps": steps},
+            "multi_lane": {"lanes": N_LANES, "value": value_lanes, "ms_per_step": ms_res2 / steps, "steps": steps},
+            "config": {"workload": f"52-card shuffle prove+verify, batch of {B} independent proofs per GPU "
+                                   f"(k=52, n={n}, Q={Q}, m={m}; BASELINE configs[1])",
+                       "mode": ("reference-fixed (SURVEY A.3: the reference's own flow never verifies); l, r in the clear, "
+                                f"{plen}-byte proofs" if mode != "fixed" else
+                                f"fixed: l, r replaced by the inner-product argument (n' = {ng}, {lg} rounds), {plen}-byte proofs"),
+                       "inputs": f"{N_SETS} rotating input sets per GPU (a different one every step): deck 1..52, a random permutation and "
+                                 "challenge value per proof, uniform blindings, prover RNG = ChaCha20 per proof and seed; witness "
+                                 "a_L, a_R, a_O generated on the device from them; generators = from_uniform_bytes(seeded bytes); "
+                                 "value commitments bound to every transcript; verifier weights from the OS RNG",
+                       "tables": f"fixed-base window tables, c = {FB_WINDOW_BITS}: {table_gib:.1f} GiB in HBM for {gens_n} generators, "
+                                 f"built once per generator set in {table_s:.2f} s (not timed) = the time of "
+                                 f"{table_s / (ms_step * 1e-3) * B:.0f} proofs at this rate",
+                       "verify": "one random-linear-combination MSM over the batch's decompressed points + shared generators "
+                                 "(Pippenger), per-proof kernels only on failure; accept bytes are per proof",
+                       "l2": f"per-step working set {B * plen / 2**20:.0f} MiB proofs + {B * batch_stride_bytes(n, Q, m, ng, lg) / 2**20:.0f} MiB "
+                             f"scalar blocks + randomly gathered {table_gib:.0f} GiB tables + {B * (m + 8 + 2 * lg) * 96 / 2**20:.0f} MiB decompressed points > 126 MB L2",
+                       "parallelism": f"proofs sharded over {world} GPU(s), no data-path collective" if world > 1 else "single GPU",
+                       "all_accepted": all_ok},
+            "e2e": {"value": e2e, "unit": "proofs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * plen + B,
+                    "ms_per_step": ms_e2e / steps,
+                    "serial": {"value": total * steps / (ms_e2e_serial * 1e-3), "ms_per_step": ms_e2e_serial / steps,
+                               "note": "one batch at a time: every copy waits for the kernels before it"},
+                    "proof_bytes_equal_serial_run": same_bytes,
+                    "note": "every step, inside the timed region: permutations + challenge values + blindings + seeds H2D (the witness is "
+                            "generated on the device: round 1 sent a_L, a_R, a_O, 3 n x 32 more bytes per proof), commitments H2D, "
+                            "proofs D2H, proofs + commitments H2D, accept bytes D2H; pinned host buffers; "
+                            f"{N_LANES} batches in flight on {N_LANES} streams; Fiat-Shamir transcripts on the device"},
+            "gpu_launches": launches2 if two else launches,
+            "roofline": {"bound": "imad", "kernel": f"{fb_kernel} (A_I-shaped commitment MSM, {2 * n + 1} terms x {Wn} windows per proof)",
+                         "achieved": ach / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD.WIDE.U32/s",
+                         "frac": ach / imad_peak, "kernel_ms": fb_ms, "point_adds_per_s": (fb_madd + fb_add) / (fb_ms * 1e-3),
+                         "peak_source": E["peak_src"], "imad_probes": E["imad_probes"],
+                         "traffic": _ncu_traffic(traffic_file),
+                         "traffic_source": f"profiles/{traffic_file} (dram read+write of one A_I-shaped launch; algorithmic gathers = "
+                                           f"mixed adds x 96 B = {fb_madd * 96 / 1e9:.2f} GB)",
+                         "whole_step": {"imad_per_proof": alg["imad"], "breakdown": alg,
+                                        "frac_of_peak": alg["imad"] * B / (ms_step * 1e-3) / imad_peak,
+                                        "note": "algorithmic IMAD.WIDE.U32 of one prove + verify (DESIGN.md section 6) x batch / ms_per_step / peak"},
+                         "hbm_peak_gbs": E["peaks"].get("hbm_gbs"), "hbm_peak_source": E["peaks_src"]},
+        }
+        if want_cpu:
+            out["cpu_baseline"] = cpu_shuffle_baseline_mode(k, mode, enc, ng, sets[serial_last], serial_proofs, plen)
+    batch.free()
+    gens.free()
+    cir.free()
+    return out
+
+
+def _event_ms(stream, fn, reps):
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(reps):
+        fn()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def bench_large_deck(E, k=4096, window_bits=8):
+    """BASELINE configs[2]: one proof of a k = 4096-card shuffle (n = 8192 multipliers, 2^14 + 2 generators, 13
+    inner-product rounds) on one GPU: prover and verifier latency, device events around each call."""
+    import bpperm_b200
+    G = bpperm_b200.acproof
+    be, stream = E["be"], E["stream"]
+    if E["rank"] != 0:
+        return None
+    cir, gens, enc, (n, Q, m, ng), table_s = shuffle_setup_mode(be, k, "fixed", window_bits)
+    deck, perm, x, gamma, seeds = synth_shuffle_inputs(k, 1, 0, 99)
+    batch = G.Batch(be, cir, gens, 1, "fixed", b"test")
+    batch.gen_shuffle_witness(deck.tobytes(), perm.tobytes(), x.tobytes(), gamma.tobytes(), seeds.tobytes())
+    batch.commit(None, want=False)
+    for _ in range(3):
+        batch.prove()
+        batch.verify(None)
+    l0 = be.launch_count
+    tp = _event_ms(stream, batch.prove, 5)
+    lp = (be.launch_count - l0) // 5
+    tv = _event_ms(stream, lambda: batch.verify(None), 5)
+    ok = batch.download_accept() == b"\x01"
+    Wn = (256 + window_bits - 1) // window_bits
+    alg = shuffle_imad_per_proof(n, Q, m, "fixed", Wn, 16)
+    out = {"workload": f"large-deck shuffle, k = {k} committed card values, single proof, `fixed` mode (BASELINE configs[2])",
+           "n": n, "generators": 2 * ng + 2, "ipa_rounds": ng.bit_length() - 1, "proof_bytes": batch.proof_len,
+           "prove_ms": tp, "verify_ms": tv, "proofs_per_s": 1e3 / (tp + tv), "accepted": ok, "prover_launches": lp,
+           "tables": f"fixed-base window tables, c = {window_bits}: {(2 * ng + 2) * Wn * 2 ** (window_bits - 1) * 96 / 2**30:.1f} GiB, built in {table_s:.2f} s",
+           "whole_step": {"imad_per_proof": alg["imad"], "frac_of_peak": alg["imad"] / ((tp + tv) * 1e-3) / E["imad_peak"],
+                          "note": "one proof cannot fill the GPU: the 13 rounds are a chain of dependent launches (latency, not throughput)"}}
+    batch.free()
+    gens.free()
+    cir.free()
+    return out
+
+
+def bench_batch_verify(E, total=4096, corrupt_every=97):
+    """BASELINE configs[3]: batch verification of 4096 independent 52-card proofs IN TOTAL (strong scaling), `fixed`
+    mode, sharded over the ranks (bulletproof-perm_b200.parallel.shard_bounds), >= 1 % of them corrupted; every rank
+    verifies its slice (one random-linear-combination MSM, bisection on failure), the accept bytes are gathered to
+    every rank through NCCL and compared with the expected decisions."""
+    import torch
+    import bpperm_b200
+    G = bpperm_b200.acproof
+    par = bpperm_b200.parallel
+    be, dev, stream, world, rank, args, dist = E["be"], E["dev"], E["stream"], E["world"], E["rank"], E["args"], E["dist"]
+    k, mode = K_CARDS, "fixed"
+    cir, gens, enc, (n, Q, m, ng), _ = shuffle_setup_mode(be, k, mode, FB_WINDOW_BITS)
+    off, cnt = par.shard_bounds(total, world, rank)
+    # proofs are produced where they are verified (synthetic input generation, not timed): the same global set for any N
+    deck, perm, x, gamma, seeds = synth_shuffle_inputs(k, total, 0, 7)
+    sl = slice(off, off + cnt)
+    batch = G.Batch(be, cir, gens, cnt, mode, b"test")
+    plen = batch.proof_len
+    batch.gen_shuffle_witness(deck.tobytes(), perm[sl].tobytes(), x[sl].tobytes(), gamma[m * off:m * (off + cnt)].tobytes(),
+                              seeds[sl].tobytes())
+    Vc = batch.commit(None)
+    batch.prove()
+    good = batch.download_proofs()
+    bad = bytearray(good)
+    expect = bytearray(b"\x01" * cnt)
+    fields = [0, 5, 8, 11, 12, plen // 32 - 1]         # A_I, T_4, t_x, L_0, R_0, b
+    j = 0
+    for g in range(total):
+        if g % corrupt_every == 3 and off <= g < off + cnt:
+            i, f = g - off, fields[j % len(fields)]
+            bad[i * plen + 32 * f + 1] ^= 0x20
+            expect[i] = 0
+        if g % corrupt_every == 3:
+            j += 1
+    n_bad_total = len([g for g in range(total) if g % corrupt_every == 3])
+    d_good = torch.frombuffer(bytearray(good), dtype=torch.uint8).to(dev)
+    d_bad = torch.frombuffer(bad, dtype=torch.uint8).to(dev)
+    d_V = torch.frombuffer(bytearray(Vc), dtype=torch.uint8).to(dev)
+    per = (total + world - 1) // world
+    d_acc = torch.zeros(per, dtype=torch.uint8, device=dev)
+    res = {}
+
+    def run(d_proofs, key):
+        def step(i):
+            batch.upload_proofs_ptr(d_proofs.data_ptr(), d_V.data_ptr())      # D2D: proofs + commitments resident in HBM
+            batch.verify(None)
+            batch.download_accept_ptr(d_acc.data_ptr())
+            res[key] = par.gather_bytes(d_acc, world)                         # NCCL all-gather of the accept bytes
+        return step
+
+    steps, warm = max(5, args.steps), max(3, args.warmup)
+    ms_good = E["timed"](run(d_good, "good"), steps, warm)
+    ms_bad = E["timed"](run(d_bad, "bad"), steps, warm)
+    acc_all = bytes(res["bad"].cpu().numpy().tobytes())
+    mine = acc_all[per * rank: per * rank + cnt]
+    ok = mine == bytes(expect)
+    okg = bytes(res["good"].cpu().numpy().tobytes())[per * rank: per * rank + cnt] == b"\x01" * cnt
+    if world > 1:
+        t = torch.tensor([1 if (ok and okg) else 0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        ok = okg = bool(t.item())
+    out = None
+    if rank == 0:
+        rebuilt = b"".join(acc_all[per * r: per * r + par.shard_bounds(total, world, r)[1]] for r in range(world))
+        out = {"metric": "batch verification proofs/sec (52-card, `fixed` mode)", "unit": "proofs/s", "scaling": "strong",
+               "workload": f"{total} independent 52-card proofs in total, sharded over {world} GPU(s) ({cnt} on rank 0), "
+                           f"{n_bad_total} of them ({100.0 * n_bad_total / total:.1f} %) corrupted in different fields; verify only; "
+                           "accept bytes all-gathered over NCCL (BASELINE configs[3])",
+               "n_gpus": world, "steps": steps,
+               "value": total / (ms_bad / steps * 1e-3), "ms_per_step": ms_bad / steps,
+               "all_valid": {"value": total / (ms_good / steps * 1e-3), "ms_per_step": ms_good / steps},
+               "corrupted_over_all_valid": ms_bad / ms_good,
+               "rejected": rebuilt.count(b"\x00"), "decisions_match_expected": bool(ok and okg),
+               "note": "value = the batch with corrupted proofs (the combined check fails and is bisected); all_valid = the same "
+                       "batch untouched (one combined check)"}
+    batch.free()
+    gens.free()
+    cir.free()
+    return out
+
+
+def bench_small_msm(E):
+    """The reference's own call sites (circuit_lib.rs:187-575: 2, 105, 209 points) through the trait-level host call
+    bpp_msm_vartime_host (scalars + compressed points in, compressed point out), and `count` of them per launch through
+    bpp_msm_vartime_batch; CPU restatement beside it."""
+    import bpperm_b200
+    from oracle import cref
+    be = E["be"]
+    if E["rank"] != 0:
+        return None
+    rs = np.random.RandomState(31)
+    rows = []
+    for npts in (2, 105, 209):
+        blobs = rs.randint(0, 256, size=(npts, 64), dtype=np.uint8).tobytes()
+        pts = be.points_from_uniform(blobs)
+        enc = be.compress_points(pts)
+        sc = rs.randint(0, 256, size=(npts, 32), dtype=np.uint8)
+        sc[:, 31] &= 0x0F
+        scb = sc.tobytes()
+        want = cref.msm(scb, cref.decompress(enc))
+        for _ in range(3):
+            got = be.msm_host(scb, enc)
+        R = 20
+        t0 = time.time()
+        for _ in range(R):
+            got = be.msm_host(scb, enc)
+        t_host = (time.time() - t0) / R
+        t0 = time.time()
+        for _ in range(R):
+            got_res = be.vartime_multiscalar_mul(scb, pts)
+        t_res = (time.time() - t0) / R
+        cp = cref.decompress(enc)
+        t0 = time.time()
+        for _ in range(R):
+            cref.msm(scb, cp)
+        t_cpu = (time.time() - t0) / R
+        row = {"points": npts, "host_call_us": t_host * 1e6, "resident_points_call_us": t_res * 1e6, "cpu_restatement_us": t_cpu * 1e6,
+               "matches_cpu": got == want and got_res == want}
+        cnt = 4096
+        scs = rs.randint(0, 256, size=(cnt * npts, 32), dtype=np.uint8)
+        scs[:, 31] &= 0x0F
+        for _ in range(2):
+            outs = be.msm_batch(scs.tobytes(), pts, npts, cnt)
+        t0 = time.time()
+        for _ in range(5):
+            outs = be.msm_batch(scs.tobytes(), pts, npts, cnt)
+        t_b = (time.time() - t0) / 5
+        row["batch_4096_shared_points_us_per_msm"] = t_b / cnt * 1e6
+        row["batch_first_matches_cpu"] = outs[:32] == cref.msm(scs[:npts].tobytes(), cp)
+        rows.append(row)
+        pts.free()
+    return {"note": "wall clock around the public call (host buffers in and out, one synchronisation per call); batch = "
+                    "bpp_msm_vartime_batch: 4096 MSMs over the same points with different scalars in one launch",
+            "cpu_cores": 1, "rows": rows}
+
+
+def batch_stride_bytes(n, Q, m, ng, lg):
+    """Approximate bytes of one proof's scalar block (acp_make_layout)."""
+    return 32 * (8 * n + 3 * m + Q + 12 * n + 6 * ng + 2 * lg + 90 + (2 * ng + 60 if lg else 0))
+
+
+def cpu_shuffle_baseline_mode(k, mode, enc, ng, input_set, gpu_proofs, plen, n_single=6):
+    """The CPU restatement (oracle/c) on the first proofs of the step the GPU's serial e2e run ended on: single core
+    (the reference is single-threaded) and all cores over independent proofs; proof bytes compared with the GPU's."""
+    global _CPU_INST
+    import multiprocessing as mp
+    from oracle import cref
+    import bpperm_b200
+    n, m = 2 * k, 2 * k + 1
+    deck, perm, x, gamma, seeds = input_set
+    if mode == "fixed":
+        _n, Q, _m, WL, WR, WO, WV, c = bpperm_b200.weights.shuffle_circuit(k)
+        _CPU_INST = cref.AcpFixedInstance(n, Q, m, WL, WR, WO, WV, _sc_bytes(c), enc[:32], enc[32:64], enc[64:64 + 32 * ng],
+                                          enc[64 + 32 * ng:64 + 64 * ng])
+    else:
+        _CPU_INST = _cpu_instance(k, enc)
+    cores = os.cpu_count() or 1
+
+    def job(i):
+        aL, aR, aO, v = shuffle_witness_bytes(k, deck, perm[i], x[i])
+        return (aL, aR, aO, gamma[m * i:m * (i + 1)].tobytes(), v, seeds[i].tobytes(), mode)
+
+    jobs1 = [job(i) for i in range(n_single)]
+    res = [_cpu_one_mode(j) for j in jobs1]
+    t1 = sum(r[0] for r in res)
+    out = {"value": n_single / t1, "unit": "proofs/s", "cores": 1, "kind": "port",
+           "sample": f"the first {n_single} proofs of one GPU step, prove+verify each, one core ({t1 / n_single * 1e3:.1f} ms/proof)",
+           "impl": ("C restatement of circuit_lib.rs over curve25519-dalek-ng 4.1.1's serial u64 algorithms (oracle/c), dense W matrices"
+                    if mode != "fixed" else
+                    "C restatement of the `fixed` flow (oracle/c: sparse weights, bulletproofs 4.0.0 inner-product argument with "
+                    "explicit generator folding) over dalek-ng 4.1.1's serial algorithms"),
+           "accepted": all(r[1] == 1 for r in res),
+           "proof_bytes_equal_gpu": [r[2] for r in res] == [gpu_proofs[i * plen:(i + 1) * plen] for i in range(n_single)]}
+    try:
+        ctx = mp.get_context("fork")
+        jobs = [jobs1[i % n_single] for i in range(cores * 2)]
+        with ctx.Pool(cores) as pool:
+            pool.map(_cpu_one_mode, jobs[:cores])  # warm the workers
+            t0 = time.time()
+            pool.map(_cpu_one_mode, jobs)
+            tall = time.time() - t0
+        out["all_cores"] = {"value": len(jobs) / tall, "cores": cores}
+    except Exception as e:  # pragma: no cover
+        out["all_cores"] = {"error": str(e)}
+    return out
+
+
+def _cpu_one_mode(args):
+    aL, aR, aO, gamma, v, seed, mode = args
+    from oracle import cref
+    Vp = _CPU_INST.commit(v, gamma)
+    if mode == "fixed":
+        Ve = cref.compress(Vp)
+        t0 = time.time()
+        pb = _CPU_INST.prove(aL, aR, aO, gamma, Vp, seed, V_enc=Ve)
+        rc = 1 if _CPU_INST.verify(pb, Vp, V_enc=Ve) else 0
+        return time.time() - t0, rc, pb
+    t0 = time.time()
+    pb, rc = _CPU_INST.prove_verify(aL, aR, aO, gamma, Vp, seed, 1)
+    return time.time() - t0, rc, pb
+
+
 # ---------------------------------------------------------------------------------- GPU arm
 def run_ours(args):
     import torch
@@ -395,185 +924,31 @@ def run_ours(args):
     line = {}
     sampler = ClockSampler(local)
 
+    E = dict(be=be, dev=dev, stream=stream, world=world, rank=rank, local=local, timed=timed, timed_block=timed_block,
+             imad_peak=imad_peak, imad_probes=imad_probes, peak_src=peak_src, peaks=peaks, peaks_src=peaks_src, args=args, dist=dist)
     # ------------------------------------------------------------------ shuffle proofs (headline)
     if args.workload in ("shuffle", "both"):
-        G = bpperm_b200.acproof
-        k, B = K_CARDS, args.batch
-        cir, gens, enc, (n, Q, m) = shuffle_setup(be, k)
-        data = synth_shuffle_batch(k, B, rank)
-        aL, aR, aO, gamma, v, seeds = data
-        batch = G.Batch(be, cir, gens, B, "reference-fixed", b"test")
-        batch.upload_witness(aL, aR, aO, gamma, seeds)
-        Vc = batch.commit(v)               # commit_variables: input generation, not timed
-        plen = batch.proof_len
-
-        def step_resident(i):
-            batch.prove()
-            batch.verify(b"\x5a" * 32)
-
-        # e2e: every host buffer of the step lives in pinned memory (the caller's side of the C ABI)
-        def pinned(b):
-            t = torch.frombuffer(bytearray(b), dtype=torch.uint8).pin_memory()
-            return t
-
-        h_in = [pinned(x) for x in (aL, aR, aO, gamma, seeds)]
-        h_V = pinned(Vc)
-        h_proofs = torch.empty(B * plen, dtype=torch.uint8).pin_memory()
-        h_accept = torch.empty(B, dtype=torch.uint8).pin_memory()
-        state = {}
-
-        def step_e2e(i):
-            batch.upload_witness_ptr(*[t.data_ptr() for t in h_in])
-            batch.prove()
-            batch.download_proofs_ptr(h_proofs.data_ptr())      # proofs leave the device ...
-            batch.upload_proofs_ptr(h_proofs.data_ptr(), h_V.data_ptr())   # ... and come back with the commitments
-            batch.verify(b"\x5a" * 32)
-            batch.download_accept_ptr(h_accept.data_ptr())
-            state["accept"] = bytes(h_accept.numpy().tobytes())
-            state["proofs"] = h_proofs
-
         if rank == 0:
             sampler.start()
-        l0 = be.launch_count
-        ms_res = timed(step_resident, args.steps, args.warmup)
-        launches = (be.launch_count - l0) * args.steps // (args.steps + args.warmup)
+        line = bench_shuffle(E, "reference-fixed", args.steps, args.warmup, want_cpu=(world == 1 and not args.no_cpu))
         clocks = sampler.stop() if rank == 0 else None
-        ms_e2e_serial = timed(step_e2e, args.steps, args.warmup)
-        all_ok = state["accept"] == b"\x01" * B
-        # e2e, double buffered: two batches in flight on two streams, one host thread each, so that the copies of one
-        # batch overlap the kernels of the other.  Same public calls, same bytes per step, every copy inside the
-        # timed region; a step is still one batch of B proofs proved and verified through host buffers.
-        lanes = []
-        for _ in range(N_LANES):
-            # urgent lane streams + priority split: the GPU-filling table-gather MSMs of a lane run at the lowest
-            # priority, its short dependent kernels win the SM slots against the other lane's bulk work
-            st = torch.cuda.Stream(dev, priority=-1) if LANE_PRIORITY_SPLIT else torch.cuda.Stream(dev)
-            be_l = bpperm_b200.Backend(local)
-            be_l.set_stream(st.cuda_stream)
-            b_l = G.Batch(be_l, cir, gens, B, "reference-fixed", b"test")
-            b_l.set_priority_split(LANE_PRIORITY_SPLIT)
-            lanes.append({"stream": st, "be": be_l, "batch": b_l,
-                          "proofs": torch.empty(B * plen, dtype=torch.uint8).pin_memory(),
-                          "accept": torch.empty(B, dtype=torch.uint8).pin_memory(), "ok": True})
-
-        # resident, two lanes: the same two batches in flight with their inputs already in HBM (witness uploaded and
-        # committed once per lane); a step is one batch of B proofs proved and verified.  The small dependent kernels
-        # of one batch (transcripts, power chains, dot products) run beside the table-gather MSMs of the other.
-        for ln in lanes:
-            ln["batch"].upload_witness(aL, aR, aO, gamma, seeds)
-            ln["batch"].commit(v)
-            ln["be"].synchronize()
-
-        def lane_resident(lane, cnt):
-            for _ in range(cnt):
-                lane["batch"].prove()
-                lane["batch"].verify(b"\x5a" * 32)
-
-        def run_resident2(cnt, first):
-            split = [cnt // N_LANES + (1 if k < cnt % N_LANES else 0) for k in range(N_LANES)]
-            th = [threading.Thread(target=lane_resident, args=(lanes[k], split[k])) for k in range(N_LANES) if split[k]]
-            for t in th:
-                t.start()
-            for t in th:
-                t.join()
-
-        res2_steps = args.steps                  # exactly K steps, split over the lanes
-        res2_warm = max(2 * N_LANES, args.warmup)   # at least two warm-up steps per lane
-        l2_0 = sum(ln["be"].launch_count for ln in lanes)
-        ms_res2 = timed_block(run_resident2, res2_steps, res2_warm, [ln["stream"] for ln in lanes])
-        launches2 = (sum(ln["be"].launch_count for ln in lanes) - l2_0) * res2_steps // (res2_steps + res2_warm)
-        for ln in lanes:
-            ln["batch"].download_accept_ptr(ln["accept"].data_ptr())
-            ln["ok"] = ln["ok"] and bytes(ln["accept"].numpy().tobytes()) == b"\x01" * B
-
-        def lane_steps(lane, n):
-            bt = lane["batch"]
-            for _ in range(n):
-                bt.upload_witness_ptr(*[t.data_ptr() for t in h_in])
-                bt.prove()
-                bt.download_proofs_ptr(lane["proofs"].data_ptr())
-                bt.upload_proofs_ptr(lane["proofs"].data_ptr(), h_V.data_ptr())
-                bt.verify(b"\x5a" * 32)
-                bt.download_accept_ptr(lane["accept"].data_ptr())
-                lane["ok"] = lane["ok"] and bytes(lane["accept"].numpy().tobytes()) == b"\x01" * B
-
-        def run_pipelined(n, first):
-            split = [n // N_LANES + (1 if k < n % N_LANES else 0) for k in range(N_LANES)]
-            th = [threading.Thread(target=lane_steps, args=(lanes[k], split[k])) for k in range(N_LANES) if split[k]]
-            for t in th:
-                t.start()
-            for t in th:
-                t.join()
-
-        ms_e2e = timed_block(run_pipelined, args.steps, args.warmup, [ln["stream"] for ln in lanes])
-        all_ok = all_ok and all(ln["ok"] for ln in lanes)
-        same_bytes = bytes(lanes[0]["proofs"].numpy().tobytes()) == bytes(h_proofs.numpy().tobytes())
-        for ln in lanes:
-            ln["batch"].free()
-            ln["be"].close()
-        fb_ms, fb_madd, fb_add = batch.time_commit_msm(5)
-        if world > 1:
-            okt = torch.tensor([1 if all_ok else 0], device=dev)
-            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
-            all_ok = bool(okt.item())
         if rank == 0:
-            total = B * world
-            value_single = total * args.steps / (ms_res * 1e-3)
-            value = max(value_single, total * res2_steps / (ms_res2 * 1e-3))
-            two_lanes = value > value_single
-            e2e = total * args.steps / (ms_e2e * 1e-3)
-            fb_imads = fb_madd * IMAD_MADD + fb_add * IMAD_ADD
-            ach = fb_imads / (fb_ms * 1e-3)
-            line = {
-                "metric": "shuffle proofs/sec prove+verify (52-card)", "value": value, "unit": "proofs/s", "n_gpus": world,
-                "steps": res2_steps if two_lanes else args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_res2 / res2_steps if two_lanes else ms_res / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "u32 (8x32-bit limbs, IMAD.WIDE.U32)", "data": "synthetic",
-                "mode": (f"{N_LANES} batches in flight on {N_LANES} urgent streams (one host thread each; table-gather MSMs on "
-                         "lowest-priority streams), inputs resident" if two_lanes
-                         else "one batch at a time on one stream, inputs resident"),
-                "single_stream": {"value": value_single, "ms_per_step": ms_res / args.steps, "steps": args.steps},
-                "multi_lane": {"lanes": N_LANES, "value": total * res2_steps / (ms_res2 * 1e-3), "ms_per_step": ms_res2 / res2_steps,
-                               "steps": res2_steps},
-                "config": {"workload": f"52-card shuffle prove+verify, batch of {B} independent proofs per GPU "
-                                       f"(k=52, n={n}, Q={Q}, m={m}; BASELINE configs[1]/[3])",
-                           "mode": "reference-fixed (SURVEY A.3: the reference's own flow never verifies)",
-                           "inputs": "deck 1..52, random permutation and challenge value per proof, uniform blindings, "
-                                     "generators = from_uniform_bytes(seeded bytes); prover RNG = ChaCha20 per proof",
-                           "tables": f"fixed-base window tables, c = {FB_WINDOW_BITS}: {(2 * n + 2) * ((256 + FB_WINDOW_BITS - 1) // FB_WINDOW_BITS) * 2 ** (FB_WINDOW_BITS - 1) * 96 / 2**30:.1f} GiB in HBM, "
-                                     "built once per generator set (not timed)",
-                           "verify": "one random-linear-combination MSM over the batch's decompressed points + shared generators "
-                                     "(Pippenger), per-proof kernels only on failure; accept bytes are per proof",
-                           "l2": f"per-step working set {B * batch.proof_len / 2**20:.0f} MiB proofs + {B * 2548 * 32 / 2**20:.0f} MiB "
-                                 "scalar blocks + randomly gathered 10 GiB tables + 43 MiB decompressed points > 126 MB L2",
-                           "parallelism": f"proofs sharded over {world} GPU(s), no data-path collective" if world > 1 else "single GPU",
-                           "all_accepted": all_ok},
-                "e2e": {"value": e2e, "unit": "proofs/s", "h2d_bytes_per_step": B * (3 * n + m) * 32 + B * 32 + B * plen + B * m * 32,
-                        "d2h_bytes_per_step": B * plen + B, "ms_per_step": ms_e2e / args.steps,
-                        "serial": {"value": total * args.steps / (ms_e2e_serial * 1e-3), "ms_per_step": ms_e2e_serial / args.steps,
-                                   "note": "one batch at a time: every copy waits for the kernels before it"},
-                        "proof_bytes_equal_serial_run": same_bytes,
-                        "note": "witness H2D, proofs D2H, proofs+commitments H2D, accept bytes D2H inside the timed region; "
-                                f"pinned host buffers; {N_LANES} batches in flight on {N_LANES} streams (so copies of one "
-                                "overlap kernels of the other); Fiat-Shamir transcripts on the device (one thread per proof)"},
-                "gpu_launches": launches2 if two_lanes else launches,
-                "roofline": {"bound": "imad", "kernel": f"k_fb_msm (A_I-shaped commitment MSM, 209 terms x {(256 + FB_WINDOW_BITS - 1) // FB_WINDOW_BITS} windows per proof)",
-                             "achieved": ach / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD.WIDE.U32/s",
-                             "frac": ach / imad_peak, "kernel_ms": fb_ms, "point_adds_per_s": (fb_madd + fb_add) / (fb_ms * 1e-3),
-                             "peak_source": peak_src, "imad_probes": imad_probes,
-                             "traffic": _ncu_traffic("r1_ncu_full_k_fb_msm.csv"),
-                             "traffic_source": "profiles/r1_ncu_full_k_fb_msm.csv (dram read+write of one A_I-shaped launch; "
-                                               "algorithmic gathers = mixed adds x 96 B)",
-                             "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_peak_source": peaks_src},
-                "clocks": clocks,
-            }
-            if world == 1 and not args.no_cpu:
-                cb = cpu_shuffle_baseline(k, enc, data)
-                pb_all = bytes(state["proofs"].numpy().tobytes())
-                gpu_first = [pb_all[i * plen:(i + 1) * plen] for i in range(len(cb["proofs"]))]
-                cb["proof_bytes_equal_gpu"] = gpu_first == cb.pop("proofs")
-                line["cpu_baseline"] = cb
-        batch.free()
+            line["clocks"] = clocks
+        if not args.no_fixed:
+            # the north_star's own protocol: l, r replaced by the inner-product argument
+            fx = bench_shuffle(E, "fixed", max(3, args.steps // 2), args.warmup, want_cpu=(world == 1 and not args.no_cpu))
+            if rank == 0:
+                line["fixed"] = fx
+        if not args.no_extra:
+            bv = bench_batch_verify(E)          # BASELINE configs[3]: 4096 proofs in total, sharded, >= 1 % corrupted
+            ld = bench_large_deck(E) if world == 1 else None   # BASELINE configs[2]: single-GPU by definition
+            sm = bench_small_msm(E) if world == 1 else None    # the reference's 15 call sites through the trait-level call
+            if rank == 0:
+                line["batch_verify"] = bv
+                if ld:
+                    line["large_deck"] = ld
+                if sm:
+                    line["trait_call_msm"] = sm
 
     # ------------------------------------------------------------------ MSM at 2^20 (second metric)
     if args.workload in ("msm", "both"):
@@ -773,6 +1148,8 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="independent 52-card proofs per GPU per step")
     ap.add_argument("--log-n", type=int, default=20)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs")
+    ap.add_argument("--no-fixed", action="store_true", help="skip the `fixed` (inner-product) mode leg of the shuffle workload")
+    ap.add_argument("--no-extra", action="store_true", help="skip batch_verify / large_deck / trait_call_msm")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

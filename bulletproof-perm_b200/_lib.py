@@ -16,15 +16,15 @@ LIB_PATH = os.environ.get("BPPERM_LIB") or os.path.join(_HERE, "libbpperm_cuda.s
 SYMBOLS = [
     "bpp_init", "bpp_free", "bpp_set_stream", "bpp_synchronize", "bpp_strerror", "bpp_last_error",
     "bpp_launch_count", "bpp_device_info", "bpp_points_upload", "bpp_points_from_uniform", "bpp_points_compress", "bpp_points_free", "bpp_points_len",
-    "bpp_msm_vartime", "bpp_msm_vartime_host", "bpp_msm_vartime_dev", "bpp_msm_partial_dev", "bpp_msm_submit_dev", "bpp_msm_submit_partial_dev", "bpp_msm_wait", "bpp_msm_wait_previous",
+    "bpp_msm_vartime", "bpp_msm_vartime_host", "bpp_points_precompute", "bpp_msm_vartime_batch", "bpp_msm_vartime_batch_dev", "bpp_msm_vartime_dev", "bpp_msm_partial_dev", "bpp_msm_submit_dev", "bpp_msm_submit_partial_dev", "bpp_msm_wait", "bpp_msm_wait_previous",
     "bpp_points_sum_compress_dev", "bpp_set_window_bits", "bpp_set_msm_groups", "bpp_set_msm_partition", "bpp_set_msm_tile", "bpp_set_msm_trace", "bpp_msm_trace_dump", "bpp_bench_imad_peak", "bpp_device_clock_khz", "bpp_bench_pipe_probe", "bpp_set_profiling",
     "bpp_last_phase_ms", "bpp_last_op_counts", "bpp_test_op",
     "bpp_inner_product", "bpp_hadamard_V", "bpp_vm_mult", "bpp_mv_mult", "bpp_exp_iter", "bpp_scalar_powers",
     "bpp_scalar_exp", "bpp_scalar_invert", "bpp_scalar_from_wide", "bpp_scalar_reduce",
     "bpp_vecpoly3_special_inner_product", "bpp_vecpoly3_eval", "bpp_poly6_eval",
-    "bpp_circuit_create", "bpp_circuit_free", "bpp_gens_create", "bpp_gens_free", "bpp_acproof_proof_len", "bpp_acproof_proof_len_mode", "bpp_acproof_wire_len", "bpp_acproof_to_wire", "bpp_acproof_from_wire",
+    "bpp_circuit_create", "bpp_circuit_create_shuffle", "bpp_circuit_free", "bpp_gens_create", "bpp_gens_free", "bpp_acproof_proof_len", "bpp_acproof_proof_len_mode", "bpp_acproof_wire_len", "bpp_acproof_to_wire", "bpp_acproof_from_wire",
     "bpp_acproof_prove_batch", "bpp_acproof_verify_batch", "bpp_acp_batch_create", "bpp_acp_batch_free",
-    "bpp_acp_batch_upload_witness", "bpp_acp_batch_commit", "bpp_acp_batch_prove", "bpp_acp_batch_download_proofs",
+    "bpp_acp_batch_upload_witness", "bpp_acp_batch_commit", "bpp_acp_batch_upload_commitments", "bpp_acp_batch_gen_shuffle_witness", "bpp_acp_batch_prove", "bpp_acp_batch_download_proofs",
     "bpp_acp_batch_upload_proofs", "bpp_acp_batch_verify", "bpp_acp_batch_download_accept",
     "bpp_acp_batch_time_commit_msm", "bpp_acp_batch_set_host_transcripts", "bpp_transcript_script", "bpp_acp_batch_set_batch_rlc", "bpp_acp_batch_set_priority_split",
 ]
@@ -70,6 +70,9 @@ def load() -> ctypes.CDLL:
     lib.bpp_points_len.restype = sz
     lib.bpp_msm_vartime.argtypes = [vp, u8p, sz, vp, sz, sz, c.c_char_p, c.c_char_p]
     lib.bpp_msm_vartime_host.argtypes = [vp, u8p, sz, c.c_int, u8p, sz, c.c_char_p]
+    lib.bpp_points_precompute.argtypes = [vp, vp, c.c_int]
+    lib.bpp_msm_vartime_batch.argtypes = [vp, u8p, sz, vp, sz, sz, c.c_char_p]
+    lib.bpp_msm_vartime_batch_dev.argtypes = [vp, vp, sz, vp, sz, sz, vp]
     lib.bpp_msm_vartime_dev.argtypes = [vp, vp, vp, sz, sz, vp]
     lib.bpp_msm_partial_dev.argtypes = [vp, vp, vp, sz, sz, vp]
     lib.bpp_msm_submit_dev.argtypes = [vp, vp, vp, sz, sz, vp]
@@ -105,6 +108,8 @@ def load() -> ctypes.CDLL:
     lib.bpp_poly6_eval.argtypes = [vp, u8p, u8p, c.c_char_p]
     u32p = c.POINTER(c.c_uint32)
     lib.bpp_circuit_create.argtypes = [vp, sz, sz, sz, u32p, u32p, u32p, u8p, u8p, c.POINTER(vp)]
+    lib.bpp_circuit_create_shuffle.argtypes = [vp, sz, c.POINTER(vp)]
+    lib.bpp_acp_batch_gen_shuffle_witness.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.bpp_circuit_free.argtypes = [vp, vp]
     lib.bpp_circuit_free.restype = None
     lib.bpp_gens_create.argtypes = [vp, u8p, u8p, u8p, u8p, sz, c.c_int, c.POINTER(vp)]
@@ -118,7 +123,7 @@ def load() -> ctypes.CDLL:
     lib.bpp_acproof_proof_len.restype = sz
     lib.bpp_acproof_proof_len_mode.argtypes = [sz, c.c_int]
     lib.bpp_acproof_proof_len_mode.restype = sz
-    lib.bpp_acproof_prove_batch.argtypes = [vp, vp, vp, c.c_int, sz, u8p, u8p, u8p, u8p, u8p, u8p, sz, c.c_char_p]
+    lib.bpp_acproof_prove_batch.argtypes = [vp, vp, vp, c.c_int, sz, u8p, u8p, u8p, u8p, u8p, u8p, u8p, sz, c.c_char_p]
     lib.bpp_acproof_verify_batch.argtypes = [vp, vp, vp, c.c_int, sz, u8p, u8p, u8p, sz, u8p, c.c_char_p]
     lib.bpp_acp_batch_create.argtypes = [vp, vp, vp, c.c_int, sz, u8p, sz, c.POINTER(vp)]
     lib.bpp_acp_batch_free.argtypes = [vp]
@@ -126,6 +131,7 @@ def load() -> ctypes.CDLL:
     # host buffers as void*: bytes objects or raw addresses of pinned memory
     lib.bpp_acp_batch_upload_witness.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.bpp_acp_batch_commit.argtypes = [vp, vp, vp]
+    lib.bpp_acp_batch_upload_commitments.argtypes = [vp, vp]
     lib.bpp_acp_batch_prove.argtypes = [vp]
     lib.bpp_acp_batch_download_proofs.argtypes = [vp, vp]
     lib.bpp_acp_batch_upload_proofs.argtypes = [vp, vp, vp]

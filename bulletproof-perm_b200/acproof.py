@@ -40,6 +40,17 @@ class Circuit:
         backend._adopt(self)
 
     @classmethod
+    def shuffle(cls, backend: Backend, k: int):
+        """The corrected k-card shuffle circuit, built inside the library (bpp_circuit_create_shuffle)."""
+        self = cls.__new__(cls)
+        self.be, self.n, self.Q, self.m = backend, 2 * k, 4 * k, 2 * k + 1
+        h = ctypes.c_void_p()
+        backend._check(backend._lib.bpp_circuit_create_shuffle(backend._ctx, k, ctypes.byref(h)))
+        self._h = h
+        backend._adopt(self)
+        return self
+
+    @classmethod
     def from_dense(cls, backend, W_L, W_R, W_O, W_V, c_vec):
         """From the reference's dense matrices (rows = wires, columns = constraints)."""
         def trip(M):
@@ -105,10 +116,22 @@ class Batch:
             raise ValueError("witness shape mismatch (circuit_lib.rs:160-167 assert_eq!)")
         self.be._check(self.be._lib.bpp_acp_batch_upload_witness(self._h, aL, aR, aO, gamma, seeds))
 
-    def commit(self, v: bytes, want: bool = True) -> bytes:
+    def gen_shuffle_witness(self, deck, perm, x, gamma, seeds):
+        """Witness of `count` k-card shuffles computed on the device: deck (k x 32 bytes), perm (count x k uint32 indices),
+        x (count x 32), gamma (count x m x 32), seeds (count x 32); bytes or addresses of pinned buffers."""
+        self.be._check(self.be._lib.bpp_acp_batch_gen_shuffle_witness(self._h, deck, perm, x, gamma, seeds))
+
+    def commit(self, v: bytes = None, want: bool = True) -> bytes:
         out = ctypes.create_string_buffer(32 * self.cir.m * self.count) if want else None
         self.be._check(self.be._lib.bpp_acp_batch_commit(self._h, v, out))
         return out.raw if want else b""
+
+    def upload_commitments(self, V):
+        """The value commitments (count x m x 32 compressed; bytes or the address of a pinned buffer): modes
+        "reference-fixed" and "fixed" bind them to every proof's transcript, so the prover needs them before prove()."""
+        if not isinstance(V, int) and len(V) != 32 * self.cir.m * self.count:
+            raise ValueError("V: count x m x 32 bytes")
+        self.be._check(self.be._lib.bpp_acp_batch_upload_commitments(self._h, V))
 
     def set_host_transcripts(self, on: bool):
         """Fiat-Shamir on host threads (True) instead of one device thread per proof (default)."""
@@ -146,7 +169,11 @@ class Batch:
     def upload_proofs(self, proofs: bytes, V: bytes = None):
         self.be._check(self.be._lib.bpp_acp_batch_upload_proofs(self._h, proofs, V))
 
-    def verify(self, verifier_seed: bytes = bytes(32)):
+    def verify(self, verifier_seed: bytes = None):
+        """verifier_seed: 32 bytes of secret, fresh randomness; None = the library draws them from the OS.  The
+        per-proof and batch weights are challenge scalars of each proof's transcript rekeyed with it."""
+        if verifier_seed is not None and len(verifier_seed) != 32:
+            raise ValueError("verifier_seed: 32 bytes or None")
         self.be._check(self.be._lib.bpp_acp_batch_verify(self._h, verifier_seed))
 
     def download_accept(self) -> bytes:
@@ -172,15 +199,19 @@ class Batch:
             pass
 
 
-def prove_batch(backend, circuit, gens, aL, aR, aO, gamma, seeds, count, mode="reference-fixed", label=b"test") -> bytes:
+def prove_batch(backend, circuit, gens, aL, aR, aO, gamma, seeds, count, mode="reference-fixed", label=b"test",
+                V: bytes = None) -> bytes:
+    """V: the value commitments (count x m x 32 compressed) - required in every mode but "reference"."""
+    if _MODES[mode] != 0 and V is None:
+        raise ValueError("modes reference-fixed and fixed bind the commitments V to the transcript: pass V")
     out = ctypes.create_string_buffer(proof_len(circuit.n, mode) * count)
     backend._check(backend._lib.bpp_acproof_prove_batch(backend._ctx, circuit._h, gens._h, _MODES[mode], count, aL, aR, aO,
-                                                         gamma, seeds, label, len(label), out))
+                                                         gamma, seeds, V, label, len(label), out))
     return out.raw
 
 
 def verify_batch(backend, circuit, gens, proofs, V, count, mode="reference-fixed", label=b"test",
-                 verifier_seed=bytes(32)) -> bytes:
+                 verifier_seed=None) -> bytes:
     out = ctypes.create_string_buffer(count)
     backend._check(backend._lib.bpp_acproof_verify_batch(backend._ctx, circuit._h, gens._h, _MODES[mode], count, proofs, V,
                                                           label, len(label), verifier_seed, out))

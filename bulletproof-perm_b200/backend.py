@@ -207,6 +207,23 @@ class Backend:
                                                    out))
         return out.raw
 
+    def msm_host(self, scalars: bytes, points_enc: bytes) -> bytes:
+        """The trait-level call: scalars and compressed points in host memory -> compressed result
+        (bpp_msm_vartime_host: decompress, multiply, compress; one call, nothing stays resident)."""
+        return self.vartime_multiscalar_mul(scalars, bytes(points_enc))
+
+    def precompute(self, points: Points, window_bits: int = 0):
+        """Attach a fixed-base window table to a long-lived point set (bpp_points_precompute)."""
+        self._check(self._lib.bpp_points_precompute(self._ctx, points._h, window_bits))
+
+    def msm_batch(self, scalars: bytes, points: Points, n: int, count: int, off: int = 0) -> bytes:
+        """`count` MSMs over the same points[off:off+n] with count x n scalars, one launch -> count x 32 bytes."""
+        if len(scalars) != 32 * n * count:
+            raise ValueError("scalars: count x n x 32 bytes")
+        out = ctypes.create_string_buffer(32 * count)
+        self._check(self._lib.bpp_msm_vartime_batch(self._ctx, bytes(scalars), count, points._h, off, n, out))
+        return out.raw
+
     # device-pointer forms (pointers are ints, e.g. torch.Tensor.data_ptr())
     def msm_dev(self, d_scalars: int, points: Points, off: int, n: int, d_out: int):
         self._check(self._lib.bpp_msm_vartime_dev(self._ctx, ctypes.c_void_p(d_scalars), points._h, off, n,

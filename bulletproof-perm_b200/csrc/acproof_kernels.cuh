@@ -28,9 +28,10 @@ struct acp_layout {
     uint32_t tc, tsel, sigma;                      // t1..t6, the five committed values, delta(y,z)
     uint32_t l, r, that, taux, mu;                 // proof scalars
     uint32_t vg, vh, vG, vH, vd;                   // verifier MSM scalars: static (contiguous g,h,G,H), dynamic (m+8)
-    uint32_t rho;                                  // batch verification weight (k_rlc_weights)
+    uint32_t rho, rho0;                            // batch verification weight: as drawn (k_tr_weights), as used (k_rlc_weights)
     uint32_t wq, u, uinv, cl, pa, pb, ptab;        // `fixed` mode: challenge w, u_j / u_j^-1 (lg each), w*c_L, w*c_R,
                                                    // the proof's a and b, 3 x IPA_MAX_LG squarings for the power tables
+    uint32_t stab;                                 // `fixed` mode: 2 x n' table of the s_t (ipa_kernels.cuh)
 };
 
 #define ACP_PTR(base, lay, p, off) ((base) + 8 * ((size_t)(p) * (lay).stride + (off)))
@@ -78,6 +79,105 @@ __global__ void __launch_bounds__(128) k_acp_place_witness(const uint32_t *__res
     const uint32_t off = which == 0 ? lay.aL : which == 1 ? lay.aR : which == 2 ? lay.aO : lay.gamma;
     uint4 lo = *reinterpret_cast<const uint4 *>(src), hi = *reinterpret_cast<const uint4 *>(src + 4);
     uint32_t *dst = ACP_PTR(blk, lay, p, off + k);
+    *reinterpret_cast<uint4 *>(dst) = lo;
+    *reinterpret_cast<uint4 *>(dst + 4) = hi;
+}
+
+// ---- shuffle witness on the device (replaces weights.rs:38-113 create_variables / create_a for the corrected k-card
+// circuit of bpp_circuit_create_shuffle; CPU restatement: shuffle_witness in the test tree) ----------------------
+// v = deck | deck[perm] | x (m = 2k + 1 committed values).  Chain c (0: input deck, 1: output deck), base multiplier
+// gb = c (k - 1), base value vb = c k:  a_R[gb + i] = v[vb + i + 1] - x,  a_L[gb] = v[vb] - x,  a_L[gb + i] = a_O[gb + i - 1],
+// a_O[gb + i] = a_L[gb + i] a_R[gb + i]  (i < k - 1): a_O is the running product of (v[vb + t] - x), t <= i + 1.  The two
+// padding multipliers 2k - 2, 2k - 1 are zero.  Block per (chain, proof): each thread multiplies up a run of consecutive
+// factors, the run totals are scanned through shared memory (Hillis-Steele), so a 4096-card chain is 8 + 9 + 8
+// dependent multiplications deep instead of 4095.  Products in Montgomery form until the final store.
+#define WIT_THREADS 256
+__global__ void __launch_bounds__(WIT_THREADS) k_shuffle_witness(const uint32_t *__restrict__ deck /* k x 8 */,
+                                                                 const uint32_t *__restrict__ perm /* B x k */,
+                                                                 const uint32_t *__restrict__ xs /* B x 8 */, uint32_t k,
+                                                                 acp_layout lay, uint32_t *__restrict__ blk,
+                                                                 uint32_t *__restrict__ vout /* B x m x 8 */) {
+    __shared__ __align__(16) uint32_t sh[2][WIT_THREADS * 8];
+    const uint32_t c = blockIdx.x, p = blockIdx.y, tid = threadIdx.x;
+    const uint32_t gb = c * (k - 1), vb = c * k, len = k - 1;      // factors f_i = v[vb + i + 1] - x, i < len
+    const uint32_t run = (len + WIT_THREADS - 1) / WIT_THREADS, i0 = tid * run, i1 = min(len, i0 + run);
+    const uint32_t *pp = perm + (size_t)p * k;
+    uint32_t *vp = vout + 8 * (size_t)p * lay.m;
+    sc x, one, r2;
+    sc_load(x, xs + 8 * (size_t)p);
+    sc_const(one, SC_R);
+    sc_const(r2, SC_R2);
+    auto value = [&](uint32_t j) {      // v[vb + j], also written out
+        sc v;
+        sc_load(v, deck + 8 * (size_t)(c ? pp[j] : j));
+        sc_store(vp + 8 * (size_t)(vb + j), v);
+        return v;
+    };
+    // pass 1: this thread's run product (Montgomery)
+    sc acc = one, f, t;
+    for (uint32_t i = i0; i < i1; i++) {
+        f = value(i + 1);
+        sc_sub(f, f, x);
+        sc_store(ACP_PTR(blk, lay, p, lay.aR + gb + i), f);
+        sc_mont(t, f, r2);
+        sc_mont(acc, acc, t);
+    }
+    if (tid == 0) {                     // the chain's first value joins the first run
+        f = value(0);
+        sc_sub(f, f, x);
+        sc_store(ACP_PTR(blk, lay, p, lay.aL + gb), f);
+        sc_mont(t, f, r2);
+        sc_mont(acc, acc, t);
+        if (c == 0) {
+            sc_store(vp + 8 * (size_t)(2 * k), x);
+            sc z;
+            sc_set0(z);
+            for (uint32_t q = 2 * k - 2; q < 2 * k; q++) {
+                sc_store(ACP_PTR(blk, lay, p, lay.aL + q), z);
+                sc_store(ACP_PTR(blk, lay, p, lay.aR + q), z);
+                sc_store(ACP_PTR(blk, lay, p, lay.aO + q), z);
+            }
+        }
+    }
+    // inclusive scan of the run products
+    int cur = 0;
+    sc_store(sh[0] + 8 * tid, acc);
+    __syncthreads();
+    for (uint32_t d = 1; d < WIT_THREADS; d <<= 1) {
+        sc a, b2;
+        sc_load(a, sh[cur] + 8 * tid);
+        if (tid >= d) {
+            sc_load(b2, sh[cur] + 8 * (tid - d));
+            sc_mont(a, a, b2);
+        }
+        sc_store(sh[cur ^ 1] + 8 * tid, a);
+        cur ^= 1;
+        __syncthreads();
+    }
+    // pass 2: exclusive prefix of the earlier runs, then the run again
+    if (tid) sc_load(acc, sh[cur] + 8 * (tid - 1));
+    else {                              // thread 0 restarts from the first value
+        sc_load(f, ACP_PTR(blk, lay, p, lay.aL + gb));
+        sc_mont(acc, f, r2);
+    }
+    for (uint32_t i = i0; i < i1; i++) {
+        sc prev;
+        sc_from_mont(prev, acc);
+        if (i) sc_store(ACP_PTR(blk, lay, p, lay.aL + gb + i), prev);
+        sc_load(f, ACP_PTR(blk, lay, p, lay.aR + gb + i));
+        sc_mont(t, f, r2);
+        sc_mont(acc, acc, t);
+        sc_from_mont(prev, acc);
+        sc_store(ACP_PTR(blk, lay, p, lay.aO + gb + i), prev);
+    }
+}
+// gamma (B x m, staged contiguously) -> the proofs' scalar blocks
+__global__ void __launch_bounds__(128) k_acp_place_gamma(const uint32_t *__restrict__ st, acp_layout lay, uint32_t *__restrict__ blk) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
+    if (i >= lay.m) return;
+    const uint32_t *src = st + 8 * ((size_t)p * lay.m + i);
+    uint4 lo = *reinterpret_cast<const uint4 *>(src), hi = *reinterpret_cast<const uint4 *>(src + 4);
+    uint32_t *dst = ACP_PTR(blk, lay, p, lay.gamma + i);
     *reinterpret_cast<uint4 *>(dst) = lo;
     *reinterpret_cast<uint4 *>(dst + 4) = hi;
 }
@@ -485,24 +585,43 @@ struct acp_csr {
     const uint32_t *coeff;    // nnz x 8 (used when kind == 0)
     uint32_t rows;
 };
+// rows of more than ACP_CSR_LONG entries (the shuffle circuit has one: the challenge value's row of W_V, 2k - 2
+// entries) are left to k_acp_csr_long, a block per (row, proof) - one thread walking 8190 entries is 2.5 ms of a
+// single-proof 4096-card prover and of its verifier (profiles/r2a_launches_large_deck.csv)
+#define ACP_CSR_LONG 64
+SC_INLINE void acp_csr_term(sc &acc, const acp_csr &W, const uint32_t *zq, uint32_t e) {
+    sc z, t, cf;
+    sc_load(z, zq + 8 * (size_t)W.col[e]);
+    const uint8_t k = W.kind[e];
+    if (k == 1) sc_add(acc, acc, z);
+    else if (k == 2) sc_sub(acc, acc, z);
+    else {
+        sc_load(cf, W.coeff + 8 * (size_t)e);
+        sc_mul(t, cf, z);
+        sc_add(acc, acc, t);
+    }
+}
 __global__ void __launch_bounds__(128) k_acp_csr(acp_csr W, acp_layout lay, uint32_t *__restrict__ blk) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
     if (r >= W.rows) return;
+    const uint32_t e0 = W.rowptr[r], e1 = W.rowptr[r + 1];
+    if (e1 - e0 > ACP_CSR_LONG) return;
     const uint32_t *zq = ACP_PTR(blk, lay, p, lay.zq);
-    sc acc, z, t, cf;
+    sc acc;
     sc_set0(acc);
-    for (uint32_t e = W.rowptr[r]; e < W.rowptr[r + 1]; e++) {
-        sc_load(z, zq + 8 * (size_t)W.col[e]);
-        uint8_t k = W.kind[e];
-        if (k == 1) sc_add(acc, acc, z);
-        else if (k == 2) sc_sub(acc, acc, z);
-        else {
-            sc_load(cf, W.coeff + 8 * (size_t)e);
-            sc_mul(t, cf, z);
-            sc_add(acc, acc, t);
-        }
-    }
+    for (uint32_t e = e0; e < e1; e++) acp_csr_term(acc, W, zq, e);
     sc_store(ACP_PTR(blk, lay, p, lay.zWL + r), acc);
+}
+__global__ void __launch_bounds__(128) k_acp_csr_long(acp_csr W, const uint32_t *__restrict__ long_rows, acp_layout lay,
+                                                      uint32_t *__restrict__ blk) {
+    __shared__ __align__(16) uint32_t sh[32 * 8];
+    const uint32_t r = long_rows[blockIdx.x], p = blockIdx.y;
+    const uint32_t *zq = ACP_PTR(blk, lay, p, lay.zq);
+    sc acc, tot;
+    sc_set0(acc);
+    for (uint32_t e = W.rowptr[r] + threadIdx.x; e < W.rowptr[r + 1]; e += blockDim.x) acp_csr_term(acc, W, zq, e);
+    block_sum_sc(tot, acc, sh);
+    if (threadIdx.x == 0) sc_store(ACP_PTR(blk, lay, p, lay.zWL + r), tot);
 }
 
 // thread per (proof, i < n): l_in, l1, r0, r1, r3 (circuit_lib.rs:286,313-339)
@@ -901,27 +1020,14 @@ __global__ void __launch_bounds__(64) k_dyn_horner_accept(acp_layout lay, uint32
 // windows instead of per-proof 4-bit windows, i.e. 16 mixed adds per point instead of ~64.  It is the
 // identity for an all-valid batch and, for any invalid proof, a non-identity except with probability
 // ~2^-252; on failure the caller falls back to the per-proof kernels, so per-proof decisions are unchanged.
-// rho_p = Scalar::random from the verifier's ChaCha20 stream (key = verifier seed, block p, stream word 1);
+// rho_p comes from the proof's own transcript rekeyed with the verifier seed (k_tr_weights, transcript_kernels.cuh);
 // proofs that already failed a cheap check (bad encoding, t != <l, r>) get rho_p = 0 and are rejected here.
-__global__ void k_rlc_weights(const uint32_t *__restrict__ seed8, acp_layout lay, uint32_t B, int check_t,
-                              const uint32_t *__restrict__ bad, uint32_t rho_off, uint32_t *__restrict__ blk) {
+__global__ void k_rlc_weights(acp_layout lay, uint32_t B, int check_t, const uint32_t *__restrict__ bad,
+                              uint32_t *__restrict__ blk) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= B) return;
-    uint32_t s[16], x[16];
-    s[0] = 0x61707865u; s[1] = 0x3320646eu; s[2] = 0x79622d32u; s[3] = 0x6b206574u;
-    for (int i = 0; i < 8; i++) s[4 + i] = seed8[i];
-    s[12] = p; s[13] = 0; s[14] = 1; s[15] = 0;
-    for (int i = 0; i < 16; i++) x[i] = s[i];
-#pragma unroll 1
-    for (int rd = 0; rd < 10; rd++) {
-        CHACHA_QR(x[0], x[4], x[8], x[12]) CHACHA_QR(x[1], x[5], x[9], x[13])
-        CHACHA_QR(x[2], x[6], x[10], x[14]) CHACHA_QR(x[3], x[7], x[11], x[15])
-        CHACHA_QR(x[0], x[5], x[10], x[15]) CHACHA_QR(x[1], x[6], x[11], x[12])
-        CHACHA_QR(x[2], x[7], x[8], x[13]) CHACHA_QR(x[3], x[4], x[9], x[14])
-    }
-    for (int i = 0; i < 16; i++) x[i] += s[i];
     sc r;
-    sc_from_wide(r, x);
+    sc_load(r, ACP_PTR(blk, lay, p, lay.rho0));
     bool ok = bad[p] == 0;
     if (check_t) {
         sc that, lr;
@@ -930,7 +1036,7 @@ __global__ void k_rlc_weights(const uint32_t *__restrict__ seed8, acp_layout lay
         ok = ok && sc_eq(that, lr);
     }
     if (!ok) sc_set0(r);
-    sc_store(ACP_PTR(blk, lay, p, rho_off), r);
+    sc_store(ACP_PTR(blk, lay, p, lay.rho), r);
 }
 // out[p * per + k] = rho_p * vd_p[k]
 __global__ void __launch_bounds__(128) k_rlc_dyn_scalars(acp_layout lay, uint32_t per, uint32_t B, uint32_t rho_off,

@@ -17,10 +17,15 @@
 #define BPP_TILE64_MIN_POINTS (3u << 20)
 #define BPP_PIPELINE_MIN_POINTS (1u << 18)
 #define BPP_PIPELINE_MIN_POINTS_SUBMIT (1u << 12)
+#define BPP_TABLE_MSM_MAX_POINTS (1u << 13)   // single MSMs over precomputed points go through the table up to here
 
 struct bpp_points {
     uint32_t *niels = nullptr;  // n x 24 u32 (96 B)
     size_t n = 0;
+    // bpp_points_precompute: fixed-base window table over all n points (entry layout of acproof_kernels.cuh k_fb_build)
+    uint32_t *fb_table = nullptr;
+    int fb_c = 0, fb_Wn = 0;
+    uint32_t fb_K[8] = {};
 };
 
 struct bpp_ctx {
@@ -60,6 +65,7 @@ struct bpp_ctx {
     uint32_t *d_flag = nullptr;
     uint8_t *h_pinned = nullptr; size_t cap_pinned = 0;         // pinned staging for host scalars
     uint8_t *d_vec = nullptr; size_t cap_vec = 0;               // arena of the scalar-vector operators
+    uint8_t *d_small = nullptr; size_t cap_small = 0;           // arena of bpp_msm_vartime_batch
     // pipelined MSM: window groups on side streams (msm_pipeline_init)
     bool pipe_ready = false;
     int forced_groups = 0;

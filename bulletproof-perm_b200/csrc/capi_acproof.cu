@@ -15,6 +15,7 @@ struct bpp_circuit {
     uint32_t n = 0, Q = 0, m = 0, rows = 0, nnz = 0;
     uint32_t *d_rowptr = nullptr, *d_col = nullptr, *d_coeff = nullptr;
     uint8_t *d_kind = nullptr;
+    uint32_t n_long = 0, *d_long = nullptr;   // rows of more than ACP_CSR_LONG entries (k_acp_csr_long)
 };
 
 struct bpp_gens {
@@ -44,12 +45,21 @@ struct bpp_acp_batch {
     // host threads (host_transcripts: the same bytes, kept as the cross-check and for hosts that want the
     // transcript in their own process)
     bool host_transcripts = false;
-    uint64_t *d_tr = nullptr, *d_proto = nullptr;
+    uint64_t *d_tr = nullptr, *d_proto = nullptr;   // d_proto: 2 states - the proof transcripts' common prefix, Transcript::new("acp-V")
+    uint8_t *d_vdig = nullptr;                      // chunk digests of the commitments (k_tr_vchunks), B x chunks x 32
     uint32_t *d_wstage = nullptr;   // witness staging (contiguous upload), allocated on first use
     // verifier fork: point decompression (IMAD-bound, fills the GPU) runs on `aux` beside the challenge-dependent
     // scalar chain (Fiat-Shamir replay, Fibonacci power chains, CSR products: serial, low occupancy)
     cudaStream_t aux = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // second side stream: the prover's absorption of the commitments (beside the commitment MSMs) and the verifier's
+    // weight derivation (k_tr_weights: hashes the rest of the proof; beside the challenge-dependent scalar chain)
+    cudaStream_t aux2 = nullptr;
+    cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr;
+    uint32_t *d_vwit = nullptr, *d_wgen = nullptr;   // bpp_acp_batch_gen_shuffle_witness: v (B x m), staging of its inputs
+    bool have_vwit = false;
+    bool have_V = false;            // commitments resident (bpp_acp_batch_commit / _upload_commitments / _upload_proofs)
+    uint8_t *h_V = nullptr;         // host transcripts only: pinned copy of the commitments
     // priority split (bpp_acp_batch_set_priority_split): the table-gather MSMs (k_fb_msm) run on `bulk`, a stream of
     // the lowest priority, so that on an urgent caller's stream the short dependent kernels of this batch win the SM
     // slots against the GPU-filling kernels of a second batch in flight on another stream
@@ -81,7 +91,7 @@ static acp_layout acp_make_layout(uint32_t n_, uint32_t Q, uint32_t m, int mode)
     const uint32_t n = L.n, np = L.np;   // only y^n, y^-n, l, r and the verifier's G/H scalars have the padded length
     L.aL = take(n); L.aR = take(n); L.aO = take(n); L.gamma = take(m);
     L.alpha = take(1); L.beta = take(1); L.ro = take(1); L.sl = take(n); L.sr = take(n); L.tau = take(5);
-    L.y = take(1); L.z = take(1); L.x = take(1); L.w = take(1);
+    L.y = take(1); L.z = take(1); L.x = take(1); L.w = take(1); L.rho0 = take(1);   // contiguous: host transcripts place them in one go
     L.yn = take(np); L.yninv = take(np); L.zq = take(Q);
     L.zWL = take(n); L.zWR = take(n); L.zWO = take(n); L.zWV = take(m); L.zc = take(1);
     L.lin = take(n); L.l1 = take(n); L.r0 = take(n); L.r1 = take(n); L.r3 = take(n);
@@ -91,6 +101,7 @@ static acp_layout acp_make_layout(uint32_t n_, uint32_t Q, uint32_t m, int mode)
     L.vg = take(1); L.vh = take(1); L.vG = take(np); L.vH = take(np); L.vd = take(m + 8 + 2 * L.lg);
     L.wq = take(1); L.u = take(L.lg); L.uinv = take(L.lg); L.cl = take(2); L.pa = take(1); L.pb = take(1);
     L.ptab = take(mode == 2 ? 3 * IPA_MAX_LG : 0);
+    L.stab = take(mode == 2 ? 2 * np : 0);
     L.rho = take(1);
     L.stride = (o + 3) & ~3u;
     return L;
@@ -157,6 +168,12 @@ extern "C" int bpp_circuit_create(bpp_ctx *ctx, size_t n, size_t Q, size_t m, co
     if (err == cudaSuccess) err = cudaMemcpy(c->d_col, col.data(), col.size() * 4, cudaMemcpyHostToDevice);
     if (err == cudaSuccess) err = cudaMemcpy(c->d_coeff, cf.data(), cf.size() * 4, cudaMemcpyHostToDevice);
     if (err == cudaSuccess) err = cudaMemcpy(c->d_kind, kind.data(), kind.size(), cudaMemcpyHostToDevice);
+    std::vector<uint32_t> long_rows;
+    for (uint32_t r = 0; r < rows; r++)
+        if (rowptr[r + 1] - rowptr[r] > ACP_CSR_LONG) long_rows.push_back(r);
+    c->n_long = (uint32_t)long_rows.size();
+    if (err == cudaSuccess && c->n_long) err = cudaMalloc((void **)&c->d_long, long_rows.size() * 4);
+    if (err == cudaSuccess && c->n_long) err = cudaMemcpy(c->d_long, long_rows.data(), long_rows.size() * 4, cudaMemcpyHostToDevice);
     if (err != cudaSuccess) {
         ctx->last_error = cudaGetErrorString(err);
         delete c;
@@ -165,10 +182,50 @@ extern "C" int bpp_circuit_create(bpp_ctx *ctx, size_t n, size_t Q, size_t m, co
     *out = c;
     return BPP_OK;
 }
+// The corrected k-card shuffle circuit (CPU restatement: shuffle_circuit in the test tree; the shape of weights.rs:130-204
+// create_weights, which as coded only makes sense for 2-3 cards): prod_i (v_i - X) == prod_i (v_{k+i} - X), X = v[2k] -
+// two product chains of k - 1 multipliers, one equality, two padding multipliers.  n = 2k, Q = 4k, m = 2k + 1, c = 0.
+extern "C" int bpp_circuit_create_shuffle(bpp_ctx *ctx, size_t k_, bpp_circuit **out) {
+    if (!ctx || !out || k_ < 2 || k_ > (1u << 24)) return BPP_ERR_INVALID_ARG;
+    const uint32_t k = (uint32_t)k_;
+    struct trip { uint32_t wire, q; bool minus; };
+    std::vector<trip> W[4];   // W_L, W_R, W_O, W_V
+    uint32_t q = 0;
+    for (uint32_t c = 0; c < 2; c++) {
+        const uint32_t gb = c * (k - 1), vb = c * k;
+        W[0].push_back({gb, q, false}); W[3].push_back({vb, q, false}); W[3].push_back({2 * k, q, true}); q++;
+        for (uint32_t i = 0; i + 1 < k; i++) {
+            W[1].push_back({gb + i, q, false}); W[3].push_back({vb + i + 1, q, false}); W[3].push_back({2 * k, q, true}); q++;
+        }
+        for (uint32_t i = 1; i + 1 < k; i++) {
+            W[0].push_back({gb + i, q, false}); W[2].push_back({gb + i - 1, q, true}); q++;
+        }
+    }
+    W[2].push_back({k - 2, q, false}); W[2].push_back({2 * k - 3, q, true}); q++;
+    W[0].push_back({2 * k - 2, q, false}); q++;
+    W[0].push_back({2 * k - 1, q, false}); q++;
+    static const uint8_t ONE[32] = {1};
+    static const uint8_t MINUS_ONE[32] = {0xec, 0xd3, 0xf5, 0x5c, 0x1a, 0x63, 0x12, 0x58, 0xd6, 0x9c, 0xf7, 0xa2, 0xde, 0xf9, 0xde, 0x14,
+                                          0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0x10};
+    uint32_t nnz[4];
+    std::vector<uint32_t> wire, cons;
+    std::vector<uint8_t> coeff;
+    for (int m = 0; m < 4; m++) {
+        nnz[m] = (uint32_t)W[m].size();
+        for (const trip &t : W[m]) {
+            wire.push_back(t.wire);
+            cons.push_back(t.q);
+            coeff.insert(coeff.end(), t.minus ? MINUS_ONE : ONE, (t.minus ? MINUS_ONE : ONE) + 32);
+        }
+    }
+    std::vector<uint8_t> cvec((size_t)4 * k * 32, 0);
+    return bpp_circuit_create(ctx, 2 * (size_t)k, 4 * (size_t)k, 2 * (size_t)k + 1, nnz, wire.data(), cons.data(), coeff.data(),
+                              cvec.data(), out);
+}
 extern "C" void bpp_circuit_free(bpp_ctx *ctx, bpp_circuit *c) {
     if (!c) return;
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
-    cudaFree(c->d_rowptr); cudaFree(c->d_col); cudaFree(c->d_coeff); cudaFree(c->d_kind);
+    cudaFree(c->d_rowptr); cudaFree(c->d_col); cudaFree(c->d_coeff); cudaFree(c->d_kind); cudaFree(c->d_long);
     delete c;
 }
 
@@ -231,6 +288,119 @@ extern "C" void bpp_gens_free(bpp_ctx *ctx, bpp_gens *g) {
     cudaFree(g->d_niels);
     cudaFree(g->d_table);
     delete g;
+}
+
+__global__ void k_compress_strided(const uint32_t *__restrict__ ext, uint32_t pitch, uint32_t first, uint32_t cnt, uint32_t B,
+                                   uint8_t *__restrict__ out32);
+// ---- small and batched variable-base MSMs over a long-lived point set ---------------------
+// The reference's 15 vartime_multiscalar_mul call sites (circuit_lib.rs:187-575) have 2..209 points, always drawn from
+// the same generator set, with fresh scalars per proof.  For such a set the window table of bpp_points_precompute turns
+// every MSM into table look-ups and mixed adds - no buckets, no doublings, so no 253-step dependent chain - and
+// bpp_msm_vartime_batch evaluates `count` of them per launch.
+static void fb_make_K(int c, int Wn, uint32_t K[8]) {   // sum_{w < Wn-1} 2^(c w + c - 1)
+    memset(K, 0, 32);
+    for (int w = 0; w < Wn - 1; w++) {
+        int bit = c * w + c - 1;
+        K[bit >> 5] |= 1u << (bit & 31);
+    }
+}
+extern "C" int bpp_points_precompute(bpp_ctx *ctx, bpp_points *p, int window_bits) {
+    if (!ctx || !p || p->n == 0) return BPP_ERR_INVALID_ARG;
+    if (window_bits == 0) window_bits = 8;
+    if (window_bits < 4 || window_bits > 20) return BPP_ERR_INVALID_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (p->fb_table && p->fb_c == window_bits) return BPP_OK;
+    if (p->fb_table) {
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(p->fb_table);
+        p->fb_table = nullptr;
+    }
+    const int Wn = (256 + window_bits - 1) / window_bits;
+    const size_t half = (size_t)1 << (window_bits - 1), entries = p->n * Wn * half;
+    if (p->n * (size_t)Wn >= (1ull << 31)) return BPP_ERR_INVALID_ARG;
+    if (cudaMalloc((void **)&p->fb_table, entries * FB_ENTRY_U32 * 4) != cudaSuccess) {
+        cudaGetLastError();
+        p->fb_table = nullptr;
+        return BPP_ERR_OOM;
+    }
+    const uint32_t threads = (uint32_t)(p->n * Wn);
+    k_fb_build<<<(threads + 63) / 64, 64, 0, ctx->stream>>>(p->niels, (uint32_t)p->n, window_bits, Wn, p->fb_table);
+    LAUNCH_CHECK(ctx);
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    p->fb_c = window_bits;
+    p->fb_Wn = Wn;
+    fb_make_K(window_bits, Wn, p->fb_K);
+    return BPP_OK;
+}
+// d_sc: count x n scalars; d_out32: count x 32.  Stream-ordered, no synchronisation.
+static int msm_table_run(bpp_ctx *ctx, const uint32_t *d_sc, const bpp_points *P, size_t off, size_t n, size_t count, uint8_t *d_out32,
+                         uint32_t *d_ext, uint32_t *d_part, uint32_t sp) {
+    acp_layout lay;
+    memset(&lay, 0, sizeof(lay));
+    lay.stride = (uint32_t)n;          // one "proof block" per MSM: its n scalars
+    fb_shape sh;
+    memset(&sh, 0, sizeof(sh));
+    sh.nseg = 1; sh.cnt[0] = (uint32_t)n; sh.gen[0] = (uint32_t)off; sh.outs = 1;
+    fb_consts kc;
+    memcpy(kc.K, P->fb_K, 32);
+    cudaStream_t st = ctx->stream;
+    if (count >= 16ull * ctx->sm_count) {
+        k_fb_msm_warp<<<(unsigned)((count + FB_THREADS / 32 - 1) / (FB_THREADS / 32)), FB_THREADS, 0, st>>>(
+            d_sc, lay, sh, P->fb_table, P->fb_c, P->fb_Wn, kc, (uint32_t)count, 1, d_ext);
+        LAUNCH_CHECK(ctx);
+    } else if (sp > 1) {
+        k_fb_msm<<<dim3((unsigned)count, 1, sp), FB_THREADS, 0, st>>>(d_sc, lay, sh, P->fb_table, P->fb_c, P->fb_Wn, kc, d_part);
+        LAUNCH_CHECK(ctx);
+        k_fb_sum_splits<<<dim3((unsigned)count, 1), 32, 0, st>>>(d_part, 1, sp, 1, d_ext);
+        LAUNCH_CHECK(ctx);
+    } else {
+        k_fb_msm<<<dim3((unsigned)count, 1), FB_THREADS, 0, st>>>(d_sc, lay, sh, P->fb_table, P->fb_c, P->fb_Wn, kc, d_ext);
+        LAUNCH_CHECK(ctx);
+    }
+    k_compress_strided<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(d_ext, 1, 0, 1, (uint32_t)count, d_out32);
+    LAUNCH_CHECK(ctx);
+    return BPP_OK;
+}
+static uint32_t msm_table_splits(const bpp_ctx *ctx, const bpp_points *P, size_t n, size_t count) {
+    const uint64_t want = 4ull * ctx->sm_count, items = (uint64_t)n * ((P->fb_Wn + FB_GROUP - 1) / FB_GROUP);
+    uint64_t sp = count >= want ? 1 : (want + count - 1) / count;
+    if (sp > (items + FB_THREADS - 1) / FB_THREADS) sp = (items + FB_THREADS - 1) / FB_THREADS;
+    if (sp > 256) sp = 256;
+    return (uint32_t)(sp ? sp : 1);
+}
+extern "C" int bpp_msm_vartime_batch_dev(bpp_ctx *ctx, const void *d_scalars, size_t count, bpp_points *points, size_t off, size_t n,
+                                         void *d_out32) {
+    if (!ctx || !d_scalars || !points || !d_out32 || count == 0 || n == 0) return BPP_ERR_INVALID_ARG;
+    if (off + n > points->n || count >= (1ull << 31)) return BPP_ERR_LENGTH_MISMATCH;
+    CK(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if (!points->fb_table && (rc = bpp_points_precompute(ctx, points, 8))) return rc;
+    const uint32_t sp = msm_table_splits(ctx, points, n, count);
+    const size_t ext_b = count * 128, part_b = sp > 1 ? count * sp * 128 : 0;
+    if ((rc = grow(ctx, &ctx->d_small, &ctx->cap_small, ext_b + part_b))) return rc;
+    return msm_table_run(ctx, (const uint32_t *)d_scalars, points, off, n, count, (uint8_t *)d_out32, (uint32_t *)ctx->d_small,
+                         (uint32_t *)(ctx->d_small + ext_b), sp);
+}
+extern "C" int bpp_msm_vartime_batch(bpp_ctx *ctx, const uint8_t *scalars, size_t count, bpp_points *points, size_t off, size_t n,
+                                     uint8_t *out32) {
+    if (!ctx || !scalars || !points || !out32 || count == 0 || n == 0) return BPP_ERR_INVALID_ARG;
+    if (off + n > points->n || count >= (1ull << 31)) return BPP_ERR_LENGTH_MISMATCH;
+    for (size_t i = 0; i < count * n; i++)
+        if (scalars[32 * i + 31] & 0x80) return BPP_ERR_SCALAR_RANGE;
+    CK(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if (!points->fb_table && (rc = bpp_points_precompute(ctx, points, 8))) return rc;
+    const uint32_t sp = msm_table_splits(ctx, points, n, count);
+    const size_t sc_b = count * n * 32, ext_b = count * 128, part_b = sp > 1 ? count * sp * 128 : 0, out_b = count * 32;
+    if ((rc = grow(ctx, &ctx->d_small, &ctx->cap_small, sc_b + ext_b + part_b + out_b))) return rc;
+    uint8_t *d = ctx->d_small;
+    CK(ctx, cudaMemcpyAsync(d, scalars, sc_b, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = msm_table_run(ctx, (const uint32_t *)d, points, off, n, count, d + sc_b + ext_b + part_b, (uint32_t *)(d + sc_b),
+                            (uint32_t *)(d + sc_b + ext_b), sp)))
+        return rc;
+    CK(ctx, cudaMemcpyAsync(out32, d + sc_b + ext_b + part_b, out_b, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return BPP_OK;
 }
 
 // ---- batch object ----------------------------------------------------------------------------------
@@ -303,7 +473,7 @@ extern "C" void bpp_acp_batch_free(bpp_acp_batch *b) {
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
     void *dev[] = {b->d_blk, b->d_seeds, b->d_wide, b->d_ext8, b->d_dyn, b->d_wsum, b->d_stat, b->d_bad, b->d_vext, b->d_vseed,
-                   b->d_pts8, b->d_proofs, b->d_V, b->d_accept, b->d_lr, b->d_tx3, b->d_lrext, b->d_part, b->d_tr, b->d_proto, b->d_rlc_sc, b->d_rlc_flag, b->d_rlc_out, b->d_wstage};
+                   b->d_pts8, b->d_proofs, b->d_V, b->d_accept, b->d_lr, b->d_tx3, b->d_lrext, b->d_part, b->d_tr, b->d_proto, b->d_vdig, b->d_vwit, b->d_wgen, b->d_rlc_sc, b->d_rlc_flag, b->d_rlc_out, b->d_wstage};
     for (void *p : dev)
         if (p) cudaFree(p);
     if (b->h_pts8) cudaFreeHost(b->h_pts8);
@@ -312,6 +482,10 @@ extern "C" void bpp_acp_batch_free(bpp_acp_batch *b) {
     if (b->h_lr) cudaFreeHost(b->h_lr);
     if (b->h_tx3) cudaFreeHost(b->h_tx3);
     if (b->h_rlc_flag) cudaFreeHost(b->h_rlc_flag);
+    if (b->h_V) cudaFreeHost(b->h_V);
+    if (b->aux2) cudaStreamDestroy(b->aux2);
+    if (b->ev_fork2) cudaEventDestroy(b->ev_fork2);
+    if (b->ev_join2) cudaEventDestroy(b->ev_join2);
     if (b->aux) cudaStreamDestroy(b->aux);
     if (b->bulk) cudaStreamDestroy(b->bulk);
     if (b->ev_bfork) cudaEventDestroy(b->ev_bfork);
@@ -339,7 +513,7 @@ extern "C" int bpp_acp_batch_create(bpp_ctx *ctx, const bpp_circuit *cir, const 
     b->proof_len = (uint32_t)bpp_acproof_proof_len_mode(cir->n, mode);
     if (const char *e = getenv("BPP_FB_WARP")) b->fb_warp_per_output = e[0] != '0';
     b->label.assign(label, label + label_len);
-    const size_t B = count, lg = b->lay.lg, per = cir->m + 8 + 2 * lg, nch = 4 + lg;
+    const size_t B = count, lg = b->lay.lg, per = cir->m + 8 + 2 * lg, nch = 6 + lg;   // challenges per proof + the two weights
     {   // small batches of large circuits: split each fixed-base MSM over several blocks (k_fb_sum_splits adds them)
         const size_t terms = 2 * (size_t)b->lay.np + 2, want = 4 * (size_t)ctx->sm_count;
         size_t sp = B >= want ? 1 : (want + B - 1) / B;
@@ -354,13 +528,19 @@ extern "C" int bpp_acp_batch_create(bpp_ctx *ctx, const bpp_circuit *cir, const 
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->aux, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->aux2, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_fork2, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_join2, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_tr, B * MERLIN_STATE_WORDS * 8);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_proto, MERLIN_STATE_WORDS * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_proto, 2 * MERLIN_STATE_WORDS * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_vdig, B * TR_V_CHUNKS(cir->m) * 32);
     if (e == cudaSuccess) {   // Transcript::new(label) + arithmetic_domain_sep(n): identical for every proof, hashed once
         bpp_host::Transcript proto(b->label.data(), b->label.size());
         proto.arithmetic_domain_sep(cir->n);
-        uint64_t st[MERLIN_STATE_WORDS];
+        uint64_t st[2 * MERLIN_STATE_WORDS];
         proto.export_state(st);
+        bpp_host::Transcript vproto((const uint8_t *)"acp-V", 5);
+        vproto.export_state(st + MERLIN_STATE_WORDS);
         e = cudaMemcpyAsync(b->d_proto, st, sizeof(st), cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     }
@@ -520,31 +700,6 @@ __global__ void __launch_bounds__(128) k_compress_strided(const uint32_t *__rest
     ge_compress(out32 + 32 * ((size_t)p * pitch + k), pt);
 }
 
-// per-proof verifier weights: Scalar::random from ChaCha20(verifier_seed), block p (mode 1); 0 in mode 0
-__global__ void k_acp_weights(const uint32_t *__restrict__ seed8, acp_layout lay, uint32_t B, int mode,
-                              uint32_t *__restrict__ blk) {
-    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= B) return;
-    sc r;
-    sc_set0(r);
-    if (mode != 0) {
-        uint32_t s[16], x[16];
-        s[0] = 0x61707865u; s[1] = 0x3320646eu; s[2] = 0x79622d32u; s[3] = 0x6b206574u;
-        for (int i = 0; i < 8; i++) s[4 + i] = seed8[i];
-        s[12] = p; s[13] = 0; s[14] = 0; s[15] = 0;
-        for (int i = 0; i < 16; i++) x[i] = s[i];
-        for (int rd = 0; rd < 10; rd++) {
-            CHACHA_QR(x[0], x[4], x[8], x[12]) CHACHA_QR(x[1], x[5], x[9], x[13])
-            CHACHA_QR(x[2], x[6], x[10], x[14]) CHACHA_QR(x[3], x[7], x[11], x[15])
-            CHACHA_QR(x[0], x[5], x[10], x[15]) CHACHA_QR(x[1], x[6], x[11], x[12])
-            CHACHA_QR(x[2], x[7], x[8], x[13]) CHACHA_QR(x[3], x[4], x[9], x[14])
-        }
-        for (int i = 0; i < 16; i++) x[i] += s[i];
-        sc_from_wide(r, x);
-    }
-    sc_store(ACP_PTR(blk, lay, p, lay.w), r);
-}
-
 // witness: a_L, a_R, a_O (count x n), gamma (count x m), prover RNG seeds (count x 32)
 extern "C" int bpp_acp_batch_upload_witness(bpp_acp_batch *b, const uint8_t *aL, const uint8_t *aR, const uint8_t *aO,
                                             const uint8_t *gamma, const uint8_t *seeds) {
@@ -569,17 +724,53 @@ extern "C" int bpp_acp_batch_upload_witness(bpp_acp_batch *b, const uint8_t *aL,
     return BPP_OK;
 }
 
-// commit_variables (weights.rs:58-61): V_j = v_j * g + gamma_j * h for the uploaded gamma; the compressed
-// commitments are returned (count x m x 32) and also stay resident as this batch's V.
-extern "C" int bpp_acp_batch_commit(bpp_acp_batch *b, const uint8_t *v, uint8_t *V_out) {
-    if (!b || !v) return BPP_ERR_INVALID_ARG;
+// The k-card shuffle witness generated on the device (weights.rs:38-113 create_variables + create_a for the circuit of
+// bpp_circuit_create_shuffle): the caller sends what defines the shuffles - the deck, one permutation and one challenge
+// value per proof - plus the blindings and RNG seeds, 4 k + 32 (m + 2) bytes per proof instead of the 32 (3 n + m + 1) of
+// bpp_acp_batch_upload_witness (52 cards: 3.6 KB instead of 13.4 KB).  v = deck | deck[perm] | x stays resident for
+// bpp_acp_batch_commit(b, NULL, ..).
+extern "C" int bpp_acp_batch_gen_shuffle_witness(bpp_acp_batch *b, const uint8_t *deck, const uint32_t *perm, const uint8_t *x,
+                                                 const uint8_t *gamma, const uint8_t *seeds) {
+    if (!b || !deck || !perm || !x || !gamma || !seeds) return BPP_ERR_INVALID_ARG;
     bpp_ctx *ctx = b->ctx;
     CK(ctx, cudaSetDevice(ctx->device));
     const acp_layout &L = b->lay;
-    // v is staged in the (not yet used) zWV..; use vd area? keep it simple: stage into the l/r area (2n >= m)
+    if (L.n < 4 || (L.n & 1u) || L.m != L.n + 1) {
+        ctx->last_error = "gen_shuffle_witness: not a shuffle circuit (n = 2k, m = 2k + 1)";
+        return BPP_ERR_INVALID_ARG;
+    }
+    const uint32_t k = L.n / 2, B = b->B;
+    const size_t m32 = (size_t)L.m * 32 * B, dk = (size_t)k * 32, pk = (size_t)B * k * 4, xb = (size_t)B * 32;
+    if (!b->d_vwit) CK(ctx, cudaMalloc((void **)&b->d_vwit, m32));
+    if (!b->d_wgen) CK(ctx, cudaMalloc((void **)&b->d_wgen, m32 + dk + pk + xb));
+    uint8_t *st = (uint8_t *)b->d_wgen;   // gamma | deck | x | perm
+    CK(ctx, cudaMemcpyAsync(st, gamma, m32, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(st + m32, deck, dk, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(st + m32 + dk, x, xb, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(st + m32 + dk + xb, perm, pk, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(b->d_seeds, seeds, (size_t)B * 32, cudaMemcpyHostToDevice, ctx->stream));
+    k_acp_place_gamma<<<dim3((L.m + 127) / 128, B), 128, 0, ctx->stream>>>((const uint32_t *)st, L, b->d_blk);
+    LAUNCH_CHECK(ctx);
+    k_shuffle_witness<<<dim3(2, B), WIT_THREADS, 0, ctx->stream>>>((const uint32_t *)(st + m32), (const uint32_t *)(st + m32 + dk + xb),
+                                                                  (const uint32_t *)(st + m32 + dk), k, L, b->d_blk, b->d_vwit);
+    LAUNCH_CHECK(ctx);
+    b->have_vwit = true;
+    return BPP_OK;
+}
+
+// commit_variables (weights.rs:58-61): V_j = v_j * g + gamma_j * h for the uploaded gamma; the compressed
+// commitments are returned (count x m x 32) and also stay resident as this batch's V.  v = NULL: the values generated
+// by bpp_acp_batch_gen_shuffle_witness.
+extern "C" int bpp_acp_batch_commit(bpp_acp_batch *b, const uint8_t *v, uint8_t *V_out) {
+    if (!b || (!v && !b->have_vwit)) return BPP_ERR_INVALID_ARG;
+    bpp_ctx *ctx = b->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    const acp_layout &L = b->lay;
+    // v is staged in the l/r area of the proof block (not yet used at this point; 2n >= m)
     if (2 * L.n < L.m) return BPP_ERR_INVALID_ARG;
     const size_t pitch = (size_t)L.stride * 32, m32 = (size_t)L.m * 32;
-    CK(ctx, cudaMemcpy2DAsync((uint8_t *)b->d_blk + 32 * (size_t)L.l, pitch, v, m32, m32, b->B, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaMemcpy2DAsync((uint8_t *)b->d_blk + 32 * (size_t)L.l, pitch, v ? (const void *)v : (const void *)b->d_vwit, m32, m32, b->B,
+                              v ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ctx->stream));
     fb_shape sh = acp_shape(L.m);
     acp_seg(sh, L.l, 1, 0, 1);
     acp_seg(sh, L.gamma, 1, 1, 1);
@@ -589,15 +780,104 @@ extern "C" int bpp_acp_batch_commit(bpp_acp_batch *b, const uint8_t *v, uint8_t 
     LAUNCH_CHECK(ctx);
     if (V_out) CK(ctx, cudaMemcpyAsync(V_out, b->d_V, (size_t)b->B * L.m * 32, cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
+    b->have_V = true;
     return BPP_OK;
 }
 
-static int acp_put_challenges(bpp_acp_batch *b, uint32_t off, uint32_t per) {
+// The value commitments of the batch (count x m x 32 compressed): the prover binds them to its transcript (modes 1, 2),
+// the verifier needs them for check 2.
+extern "C" int bpp_acp_batch_upload_commitments(bpp_acp_batch *b, const uint8_t *V) {
+    if (!b || !V) return BPP_ERR_INVALID_ARG;
     bpp_ctx *ctx = b->ctx;
-    CK(ctx, cudaMemcpyAsync(b->d_wide, b->h_wide, (size_t)b->B * per * 64, cudaMemcpyHostToDevice, ctx->stream));
-    k_acp_put_wide<<<(b->B * per + 127) / 128, 128, 0, ctx->stream>>>(b->d_wide, b->lay, off, per, b->B, b->d_blk);
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaMemcpyAsync(b->d_V, V, (size_t)b->B * b->lay.m * 32, cudaMemcpyHostToDevice, ctx->stream));
+    b->have_V = true;
+    return BPP_OK;
+}
+
+// host transcripts: the commitments on the host (pinned), fetched from the resident copy
+static int acp_fetch_commitments(bpp_acp_batch *b) {
+    bpp_ctx *ctx = b->ctx;
+    const size_t bytes = (size_t)b->B * b->lay.m * 32;
+    if (!b->h_V) CK(ctx, cudaMallocHost((void **)&b->h_V, bytes));
+    CK(ctx, cudaMemcpyAsync(b->h_V, b->d_V, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return BPP_OK;
+}
+static void acp_host_append_commitments(bpp_host::Transcript &t, const uint8_t *V, uint32_t m) {
+    t.append_u64("m", m);
+    for (uint32_t c = 0; c < m; c += TR_V_CHUNK) {   // two levels, see k_tr_vchunks
+        bpp_host::Transcript ch((const uint8_t *)"acp-V", 5);
+        ch.append_u64("chunk", c / TR_V_CHUNK);
+        for (uint32_t j = c; j < m && j < c + TR_V_CHUNK; j++) ch.append_point("V", V + 32 * (size_t)j);
+        uint8_t d[32];
+        ch.challenge_bytes("d", d, 32);
+        t.append_message("Vd", d, 32);
+    }
+}
+// device transcripts: the chunk digests of the resident commitments, on the second side stream
+static int acp_fork_vchunks(bpp_acp_batch *b) {
+    bpp_ctx *ctx = b->ctx;
+    CK(ctx, cudaEventRecord(b->ev_fork2, ctx->stream));
+    CK(ctx, cudaStreamWaitEvent(b->aux2, b->ev_fork2, 0));
+    TR_LAUNCH(k_tr_vchunks, b->B * TR_V_CHUNKS(b->lay.m), b->aux2, b->d_proto + MERLIN_STATE_WORDS, b->d_V, b->lay.m,
+                                                                                      b->B, b->d_vdig);
+    LAUNCH_CHECK(ctx);
+    CK(ctx, cudaEventRecord(b->ev_join2, b->aux2));
+    return BPP_OK;
+}
+
+// h_wide[byte_off ..): B x per wide (64-byte) values -> scalars at layout offset `off` of every proof
+static int acp_put_challenges(bpp_acp_batch *b, uint32_t off, uint32_t per, size_t byte_off = 0) {
+    bpp_ctx *ctx = b->ctx;
+    CK(ctx, cudaMemcpyAsync((uint8_t *)b->d_wide + byte_off, b->h_wide + byte_off, (size_t)b->B * per * 64, cudaMemcpyHostToDevice,
+                            ctx->stream));
+    k_acp_put_wide<<<(b->B * per + 127) / 128, 128, 0, ctx->stream>>>(b->d_wide + byte_off / 4, b->lay, off, per, b->B, b->d_blk);
     LAUNCH_CHECK(ctx);
     return BPP_OK;
+}
+
+// The verifier's secret randomness (k_tr_weights): the caller's 32 bytes, or 32 bytes from the operating system when the
+// caller passes NULL.  Soundness of the fused per-proof check and of the batch combination needs weights the prover
+// cannot predict; they are additionally bound to every byte of each proof through its transcript.
+#include <sys/random.h>
+static int acp_set_verifier_seed(bpp_acp_batch *b, const uint8_t *seed, uint8_t host_copy[32]) {
+    bpp_ctx *ctx = b->ctx;
+    if (seed) {
+        memcpy(host_copy, seed, 32);
+    } else {
+        size_t got = 0;
+        while (got < 32) {
+            ssize_t r = getrandom(host_copy + got, 32 - got, 0);
+            if (r <= 0) {
+                ctx->last_error = "getrandom failed: no verifier seed";
+                return BPP_ERR_INVALID_ARG;
+            }
+            got += (size_t)r;
+        }
+    }
+    CK(ctx, cudaMemcpyAsync(b->d_vseed, host_copy, 32, cudaMemcpyHostToDevice, ctx->stream));   // pageable: staged before return
+    return BPP_OK;
+}
+// device transcripts: continue every proof's final verifier state into its weights, on the second side stream
+static int acp_fork_weights(bpp_acp_batch *b) {
+    bpp_ctx *ctx = b->ctx;
+    CK(ctx, cudaEventRecord(b->ev_fork2, ctx->stream));
+    CK(ctx, cudaStreamWaitEvent(b->aux2, b->ev_fork2, 0));
+    TR_LAUNCH(k_tr_weights, b->B, b->aux2, b->d_tr, b->d_proofs, b->proof_len, (const uint8_t *)b->d_vseed, b->lay,
+                                                              b->B, b->mode, b->d_blk);
+    LAUNCH_CHECK(ctx);
+    CK(ctx, cudaEventRecord(b->ev_join2, b->aux2));
+    return BPP_OK;
+}
+// host transcripts: the same continuation on the host; writes the wide values of w and rho to out128
+static void acp_host_weights(bpp_host::Transcript &t, const uint8_t *proof, uint32_t proof_len, const uint8_t seed[32],
+                             uint32_t p, int mode, uint8_t *out128) {
+    if (mode == 0) { memset(out128, 0, 128); return; }
+    t.append_message("proof-tail", proof + 256, proof_len - 256);
+    t.append_message("verifier-seed", seed, 32);
+    t.append_u64("proof-index", p);
+    t.challenge_wide("w", out128);
+    t.challenge_wide("rho", out128 + 64);
 }
 
 static int acp_challenge_dependent_scalars(bpp_acp_batch *b) {
@@ -617,6 +897,10 @@ static int acp_challenge_dependent_scalars(bpp_acp_batch *b) {
     acp_csr W{b->cir->d_rowptr, b->cir->d_col, b->cir->d_kind, b->cir->d_coeff, b->cir->rows};
     k_acp_csr<<<dim3((W.rows + 127) / 128, b->B), 128, 0, ctx->stream>>>(W, L, b->d_blk);
     LAUNCH_CHECK(ctx);
+    if (b->cir->n_long) {
+        k_acp_csr_long<<<dim3(b->cir->n_long, b->B), 128, 0, ctx->stream>>>(W, b->cir->d_long, L, b->d_blk);
+        LAUNCH_CHECK(ctx);
+    }
     k_acp_vec1<<<dim3((L.n + 127) / 128, b->B), 128, 0, ctx->stream>>>(L, b->d_blk);
     LAUNCH_CHECK(ctx);
     return BPP_OK;
@@ -630,13 +914,13 @@ static int acp_prove_ipa(bpp_acp_batch *b) {
     const uint32_t B = b->B, np = L.np, lg = L.lg;
     cudaStream_t s = ctx->stream;
     int rc;
+    const unsigned rt = np >= IPA_ROUND_THREADS ? IPA_ROUND_THREADS : (np < 128 ? 128 : np);   // k_ipa_round block
     if (!b->host_transcripts) {
-        k_tr_prove_w<<<(B + TR_THREADS - 1) / TR_THREADS, TR_THREADS, 0, s>>>(L, B, b->d_tr, b->d_blk);
+        TR_LAUNCH(k_ipa_challenge, B, s, nullptr, L, B, -1, b->d_tr, b->d_blk);
         LAUNCH_CHECK(ctx);
     } else {
         // t_hat, tau_x, mu are contiguous in the proof block
-        CK(ctx, cudaMemcpy2DAsync(b->h_tx3, 96, (const uint8_t *)b->d_blk + 32 * (size_t)L.that, (size_t)L.stride * 32, 96, B,
-                                  cudaMemcpyDeviceToHost, s));
+        CK(ctx, cudaMemcpy2DAsync(b->h_tx3, 96, ACP_PTR(b->d_blk, L, 0, L.that), (size_t)L.stride * 32, 96, B, cudaMemcpyDeviceToHost, s));
         CK(ctx, cudaStreamSynchronize(s));
         acp_parallel_for(B, [&](uint32_t p) {
             bpp_host::Transcript &t = b->tr[p];
@@ -650,13 +934,11 @@ static int acp_prove_ipa(bpp_acp_batch *b) {
         });
         if ((rc = acp_put_challenges(b, L.wq, 1))) return rc;
     }
+    k_ipa_round<<<B, rt, 0, s>>>(L, -1, b->d_blk);   // s table = {1}, c_L, c_R and the MSM scalars of round 0
+    LAUNCH_CHECK(ctx);
     const uint32_t gH = 2 + b->gens->n;
     for (uint32_t j = 0; j < lg; j++) {
-        const uint32_t nj = np >> j, h = nj >> 1;
-        k_ipa_dots<<<dim3(2, B), 128, 0, s>>>(L, h, b->d_blk);
-        LAUNCH_CHECK(ctx);
-        k_ipa_prep<<<dim3((np + 127) / 128, B), 128, 0, s>>>(L, j, b->d_blk);
-        LAUNCH_CHECK(ctx);
+        const uint32_t nj = np >> j;
         fb_shape sh = acp_shape(2);
         sh.sel_period = nj;
         acp_seg(sh, L.vG, 0, 2, np);  sh.sel[0] = 1;    // <a_L s, G_R> for L, <a_R s, G_L> for R
@@ -666,7 +948,7 @@ static int acp_prove_ipa(bpp_acp_batch *b) {
         k_compress_strided<<<(2 * B + 127) / 128, 128, 0, s>>>(b->d_lrext, 2 * lg, 2 * j, 2, B, b->d_lr);
         LAUNCH_CHECK(ctx);
         if (!b->host_transcripts) {
-            k_tr_prove_u<<<(B + TR_THREADS - 1) / TR_THREADS, TR_THREADS, 0, s>>>(b->d_lr, L, B, j, b->d_tr, b->d_blk);
+            TR_LAUNCH(k_ipa_challenge, B, s, b->d_lr, L, B, (int)j, b->d_tr, b->d_blk);
             LAUNCH_CHECK(ctx);
         } else {
             CK(ctx, cudaMemcpy2DAsync(b->h_pts8, 64, b->d_lr + 64 * (size_t)j, 64 * (size_t)lg, 64, B, cudaMemcpyDeviceToHost, s));
@@ -678,10 +960,10 @@ static int acp_prove_ipa(bpp_acp_batch *b) {
                 t.challenge_wide("u", b->h_wide + 64 * (size_t)p);
             });
             if ((rc = acp_put_challenges(b, L.u + j, 1))) return rc;
+            k_ipa_uinv<<<(B + 63) / 64, 64, 0, s>>>(L, B, j, b->d_blk);
+            LAUNCH_CHECK(ctx);
         }
-        k_ipa_uinv<<<(B + 63) / 64, 64, 0, s>>>(L, B, j, b->d_blk);
-        LAUNCH_CHECK(ctx);
-        k_ipa_fold<<<dim3((h + 127) / 128, B), 128, 0, s>>>(L, j, b->d_blk);
+        k_ipa_round<<<B, rt, 0, s>>>(L, (int)j, b->d_blk);   // fold a, b; s table; next round's c_L, c_R and MSM scalars
         LAUNCH_CHECK(ctx);
     }
     k_acp_pack_fixed<<<dim3((b->proof_len / 32 + 127) / 128, B), 128, 0, s>>>(L, b->d_pts8, b->d_lr, b->d_blk, b->d_proofs,
@@ -699,6 +981,12 @@ extern "C" int bpp_acp_batch_prove(bpp_acp_batch *b) {
     const uint32_t B = b->B, n = L.n;
     cudaStream_t s = ctx->stream;
     int rc;
+    const bool bind_V = b->mode != 0;   // `reference` mode: the reference never appends V (SURVEY A.3 defect 12)
+    if (bind_V && !b->have_V) {
+        ctx->last_error = "prove: the value commitments are not resident (bpp_acp_batch_commit / _upload_commitments)";
+        return BPP_ERR_INVALID_ARG;
+    }
+    if (bind_V && !b->host_transcripts && (rc = acp_fork_vchunks(b))) return rc;   // beside the commitment MSMs
     // create(): randomness alpha,beta,ro,s_l,s_r (+ the five tau drawn later from the same stream)
     const uint32_t nrand = 3 + 2 * n + 5;
     k_acp_rng<<<dim3((nrand + 127) / 128, B), 128, 0, s>>>(b->d_seeds, L, nrand, b->d_blk);
@@ -719,10 +1007,12 @@ extern "C" int bpp_acp_batch_prove(bpp_acp_batch *b) {
     LAUNCH_CHECK(ctx);
     // transcripts: dom-sep, A_I, A_O, S -> y, z
     if (!b->host_transcripts) {
-        k_tr_prove_yz<<<(B + TR_THREADS - 1) / TR_THREADS, TR_THREADS, 0, s>>>(b->d_proto, b->d_pts8, L, B, b->d_tr, b->d_blk);
+        if (bind_V) CK(ctx, cudaStreamWaitEvent(s, b->ev_join2, 0));
+        TR_LAUNCH(k_tr_prove_yz, B, s, b->d_proto, bind_V ? b->d_vdig : nullptr, b->d_pts8, L, B, b->d_tr, b->d_blk);
         LAUNCH_CHECK(ctx);
     } else {
         CK(ctx, cudaMemcpyAsync(b->h_pts8, b->d_pts8, (size_t)B * 256, cudaMemcpyDeviceToHost, s));
+        if (bind_V && (rc = acp_fetch_commitments(b))) return rc;
         CK(ctx, cudaStreamSynchronize(s));
         {   // Transcript::new(label) + arithmetic_domain_sep(n) are identical for every proof: hash once, copy
             bpp_host::Transcript proto(b->label.data(), b->label.size());
@@ -732,6 +1022,7 @@ extern "C" int bpp_acp_batch_prove(bpp_acp_batch *b) {
         acp_parallel_for(B, [&](uint32_t p) {
             bpp_host::Transcript &t = b->tr[p];
             const uint8_t *pt = b->h_pts8 + 256 * (size_t)p;
+            if (bind_V) acp_host_append_commitments(t, b->h_V + 32 * (size_t)p * L.m, L.m);
             t.append_point("A_I", pt);
             t.append_point("A_O", pt + 32);
             t.append_point("S", pt + 64);
@@ -754,7 +1045,7 @@ extern "C" int bpp_acp_batch_prove(bpp_acp_batch *b) {
     LAUNCH_CHECK(ctx);
     const int mode = b->mode;
     if (!b->host_transcripts) {
-        k_tr_prove_x<<<(B + TR_THREADS - 1) / TR_THREADS, TR_THREADS, 0, s>>>(b->d_pts8, L, B, mode, b->d_tr, b->d_blk);
+        TR_LAUNCH(k_tr_prove_x, B, s, b->d_pts8, L, B, mode, b->d_tr, b->d_blk);
         LAUNCH_CHECK(ctx);
     } else {
         CK(ctx, cudaMemcpyAsync(b->h_pts8, b->d_pts8, (size_t)B * 256, cudaMemcpyDeviceToHost, s));
@@ -798,7 +1089,10 @@ extern "C" int bpp_acp_batch_upload_proofs(bpp_acp_batch *b, const uint8_t *proo
     bpp_ctx *ctx = b->ctx;
     CK(ctx, cudaSetDevice(ctx->device));
     CK(ctx, cudaMemcpyAsync(b->d_proofs, proofs, (size_t)b->B * b->proof_len, cudaMemcpyHostToDevice, ctx->stream));
-    if (V) CK(ctx, cudaMemcpyAsync(b->d_V, V, (size_t)b->B * b->lay.m * 32, cudaMemcpyHostToDevice, ctx->stream));
+    if (V) {
+        CK(ctx, cudaMemcpyAsync(b->d_V, V, (size_t)b->B * b->lay.m * 32, cudaMemcpyHostToDevice, ctx->stream));
+        b->have_V = true;
+    }
     return BPP_OK;
 }
 
@@ -810,7 +1104,7 @@ static int acp_verify_rlc(bpp_acp_batch *b, uint32_t per, int check_t, bool *dec
     cudaStream_t s = ctx->stream;
     *decided = false;
     const size_t N = (size_t)B * per + nstat;
-    k_rlc_weights<<<(B + 127) / 128, 128, 0, s>>>(b->d_vseed, L, B, check_t, b->d_bad, L.rho, b->d_blk);
+    k_rlc_weights<<<(B + 127) / 128, 128, 0, s>>>(L, B, check_t, b->d_bad, b->d_blk);
     LAUNCH_CHECK(ctx);
     k_rlc_dyn_scalars<<<dim3((per + 127) / 128, B), 128, 0, s>>>(L, per, B, L.rho, b->d_blk, b->d_rlc_sc);
     LAUNCH_CHECK(ctx);
@@ -833,12 +1127,13 @@ static int acp_verify_rlc(bpp_acp_batch *b, uint32_t per, int check_t, bool *dec
 // `fixed` mode verifier (bulletproofs 4.0.0 verification_scalars + the mega-check of dalek's R1CS verifier): replays the transcript including the inner-product rounds,
 // then evaluates rho * check 2 + check 3 with the inner-product verification substituted for <l,G> + <r,h'>
 // as ONE MSM per proof (2 n' + 2 fixed-base terms, m + 8 + 2 lg decompressed points) that must be the identity.
-static int acp_verify_fixed(bpp_acp_batch *b, const uint8_t verifier_seed[32]) {
+static int acp_verify_fixed(bpp_acp_batch *b, const uint8_t *verifier_seed) {
     bpp_ctx *ctx = b->ctx;
     const acp_layout &L = b->lay;
     const uint32_t B = b->B, n = L.n, np = L.np, m = L.m, lg = L.lg, per = m + 8 + 2 * lg, nch = 4 + lg;
     cudaStream_t s = ctx->stream;
     int rc;
+    uint8_t seed[32];
     k_acp_unpack_fixed<<<dim3((b->proof_len / 32 + 127) / 128, B), 128, 0, s>>>(L, b->d_proofs, b->proof_len, b->d_blk, b->d_pts8,
                                                                                b->d_lr, b->d_tx3);
     LAUNCH_CHECK(ctx);
@@ -850,22 +1145,29 @@ static int acp_verify_fixed(bpp_acp_batch *b, const uint8_t verifier_seed[32]) {
     k_acp_decompress_lr<<<(B * 2 * lg + 127) / 128, 128, 0, b->aux>>>(b->d_lr, m, lg, B, b->d_dyn, b->d_bad);
     LAUNCH_CHECK(ctx);
     CK(ctx, cudaEventRecord(b->ev_join, b->aux));
-    CK(ctx, cudaMemcpyAsync(b->d_vseed, verifier_seed, 32, cudaMemcpyHostToDevice, s));
+    if ((rc = acp_set_verifier_seed(b, verifier_seed, seed))) return rc;
     if (!b->host_transcripts) {
-        k_tr_verify<<<(B + TR_THREADS - 1) / TR_THREADS, TR_THREADS, 0, s>>>(b->d_proto, b->d_pts8, (const uint8_t *)b->d_tx3, b->d_lr,
-                                                                             L, B, 2, b->d_blk);
+        if ((rc = acp_fork_vchunks(b))) return rc;
+        CK(ctx, cudaStreamWaitEvent(s, b->ev_join2, 0));
+        TR_LAUNCH(k_tr_verify, B, s, b->d_proto, b->d_vdig, b->d_pts8, (const uint8_t *)b->d_tx3, b->d_lr, L, B, 2,
+                                                        b->d_blk, b->d_tr);
         LAUNCH_CHECK(ctx);
+        if ((rc = acp_fork_weights(b))) return rc;
     } else {
         CK(ctx, cudaMemcpyAsync(b->h_pts8, b->d_pts8, (size_t)B * 256, cudaMemcpyDeviceToHost, s));
         CK(ctx, cudaMemcpyAsync(b->h_tx3, b->d_tx3, (size_t)B * 96, cudaMemcpyDeviceToHost, s));
         CK(ctx, cudaMemcpyAsync(b->h_lr, b->d_lr, (size_t)B * 64 * lg, cudaMemcpyDeviceToHost, s));
+        CK(ctx, cudaMemcpyAsync(b->h_proofs, b->d_proofs, (size_t)B * b->proof_len, cudaMemcpyDeviceToHost, s));
+        if ((rc = acp_fetch_commitments(b))) return rc;
         CK(ctx, cudaStreamSynchronize(s));
         bpp_host::Transcript proto(b->label.data(), b->label.size());
         proto.arithmetic_domain_sep(n);
+        const size_t w_off = (size_t)B * nch * 64;   // the two weights follow the challenges in h_wide
         acp_parallel_for(B, [&](uint32_t p) {
             bpp_host::Transcript t = proto;
             const uint8_t *pt = b->h_pts8 + 256 * (size_t)p, *sc3 = b->h_tx3 + 96 * (size_t)p, *lr = b->h_lr + 64 * (size_t)lg * p;
             uint8_t *wide = b->h_wide + 64 * (size_t)nch * p;
+            acp_host_append_commitments(t, b->h_V + 32 * (size_t)p * m, m);
             t.append_point("A_I", pt);
             t.append_point("A_O", pt + 32);
             t.append_point("S", pt + 64);
@@ -888,19 +1190,22 @@ static int acp_verify_fixed(bpp_acp_batch *b, const uint8_t verifier_seed[32]) {
                 t.append_point("R", lr + 64 * (size_t)j + 32);
                 t.challenge_wide("u", wide + 256 + 64 * (size_t)j);
             }
+            acp_host_weights(t, b->h_proofs + (size_t)p * b->proof_len, b->proof_len, seed, p, 2, b->h_wide + w_off + 128 * (size_t)p);
         });
-        // challenges land at y, z, x, (w = verifier weight, overwritten below), then wq and u_j are placed explicitly
+        // challenges land at y, z, x, wq and u_j; the verifier weights at w, rho0
         CK(ctx, cudaMemcpyAsync(b->d_wide, b->h_wide, (size_t)B * nch * 64, cudaMemcpyHostToDevice, s));
         k_acp_put_wide_strided<<<(B * nch + 127) / 128, 128, 0, s>>>(b->d_wide, L, nch, B, b->d_blk);
         LAUNCH_CHECK(ctx);
+        if ((rc = acp_put_challenges(b, L.w, 2, w_off))) return rc;
     }
-    k_acp_weights<<<(B + 127) / 128, 128, 0, s>>>(b->d_vseed, L, B, 1, b->d_blk);
-    LAUNCH_CHECK(ctx);
     if ((rc = acp_challenge_dependent_scalars(b))) return rc;
     k_acp_dots<<<dim3(1, B), 128, 0, s>>>(L, 9, b->d_blk);   // sigma
     LAUNCH_CHECK(ctx);
     k_ipa_vprep<<<(B + 63) / 64, 64, 0, s>>>(L, B, b->d_blk);
     LAUNCH_CHECK(ctx);
+    k_ipa_stable_full<<<B, np >= IPA_ROUND_THREADS ? IPA_ROUND_THREADS : (np < 128 ? 128 : np), 0, s>>>(L, b->d_blk);
+    LAUNCH_CHECK(ctx);
+    if (!b->host_transcripts) CK(ctx, cudaStreamWaitEvent(s, b->ev_join2, 0));   // w, rho0 (k_tr_weights)
     k_acp_vscal_fixed<<<dim3((np + m + 1 + 127) / 128, B), 128, 0, s>>>(L, b->d_blk);
     LAUNCH_CHECK(ctx);
     CK(ctx, cudaStreamWaitEvent(s, b->ev_join, 0));   // decompressed points + bad flags (forked after the unpack)
@@ -924,15 +1229,20 @@ static int acp_verify_fixed(bpp_acp_batch *b, const uint8_t verifier_seed[32]) {
 // Verifier: proofs + V resident -> accept bytes resident.  Replays the transcript (A_I,A_O,S -> y,z;
 // T's -> x), recomputes the challenge-dependent scalars and evaluates the checks of
 // circuit_lib.rs:518 (t == <l,r>), :541 and (mode 1) :577-582 as one MSM per proof.
-extern "C" int bpp_acp_batch_verify(bpp_acp_batch *b, const uint8_t verifier_seed[32]) {
-    if (!b || !verifier_seed) return BPP_ERR_INVALID_ARG;
+extern "C" int bpp_acp_batch_verify(bpp_acp_batch *b, const uint8_t *verifier_seed) {
+    if (!b) return BPP_ERR_INVALID_ARG;
     bpp_ctx *ctx = b->ctx;
     CK(ctx, cudaSetDevice(ctx->device));
+    if (!b->have_V) {
+        ctx->last_error = "verify: the value commitments are not resident (bpp_acp_batch_upload_proofs with V / _upload_commitments)";
+        return BPP_ERR_INVALID_ARG;
+    }
     if (b->mode == 2) return acp_verify_fixed(b, verifier_seed);
     const acp_layout &L = b->lay;
     const uint32_t B = b->B, n = L.n, m = L.m, per = m + 8;
     cudaStream_t s = ctx->stream;
     int rc;
+    uint8_t seed[32];
     k_acp_unpack<<<dim3((b->proof_len / 32 + 127) / 128, B), 128, 0, s>>>(L, B, b->d_proofs, b->proof_len, b->d_blk, b->d_pts8);
     LAUNCH_CHECK(ctx);
     CK(ctx, cudaEventRecord(b->ev_fork, s));
@@ -941,39 +1251,47 @@ extern "C" int bpp_acp_batch_verify(bpp_acp_batch *b, const uint8_t verifier_see
     k_acp_decompress<<<(B * per + 127) / 128, 128, 0, b->aux>>>(b->d_V, b->d_pts8, m, B, per, b->d_dyn, b->d_bad);
     LAUNCH_CHECK(ctx);
     CK(ctx, cudaEventRecord(b->ev_join, b->aux));
-    CK(ctx, cudaMemcpyAsync(b->d_vseed, verifier_seed, 32, cudaMemcpyHostToDevice, s));
+    if ((rc = acp_set_verifier_seed(b, verifier_seed, seed))) return rc;
     const int mode = b->mode;
     if (!b->host_transcripts) {
-        k_tr_verify<<<(B + TR_THREADS - 1) / TR_THREADS, TR_THREADS, 0, s>>>(b->d_proto, b->d_pts8, nullptr, nullptr, L, B, mode,
-                                                                             b->d_blk);
+        if (mode != 0) {
+            if ((rc = acp_fork_vchunks(b))) return rc;
+            CK(ctx, cudaStreamWaitEvent(s, b->ev_join2, 0));
+        }
+        TR_LAUNCH(k_tr_verify, B, s, b->d_proto, b->d_vdig, b->d_pts8, nullptr, nullptr, L, B, mode, b->d_blk, b->d_tr);
         LAUNCH_CHECK(ctx);
+        if ((rc = acp_fork_weights(b))) return rc;
     } else {
         CK(ctx, cudaMemcpyAsync(b->h_pts8, b->d_pts8, (size_t)B * 256, cudaMemcpyDeviceToHost, s));
+        CK(ctx, cudaMemcpyAsync(b->h_proofs, b->d_proofs, (size_t)B * b->proof_len, cudaMemcpyDeviceToHost, s));
+        if (mode != 0 && (rc = acp_fetch_commitments(b))) return rc;
         CK(ctx, cudaStreamSynchronize(s));
         bpp_host::Transcript proto(b->label.data(), b->label.size());
         proto.arithmetic_domain_sep(n);
         acp_parallel_for(B, [&](uint32_t p) {
             bpp_host::Transcript t = proto;
             const uint8_t *pt = b->h_pts8 + 256 * (size_t)p;
+            uint8_t *wide = b->h_wide + 320 * (size_t)p;   // y, z, x, w, rho0
+            if (mode != 0) acp_host_append_commitments(t, b->h_V + 32 * (size_t)p * m, m);
             t.append_point("A_I", pt);
             t.append_point("A_O", pt + 32);
             t.append_point("S", pt + 64);
-            t.challenge_wide("y", b->h_wide + 192 * (size_t)p);
-            t.challenge_wide("z", b->h_wide + 192 * (size_t)p + 64);
+            t.challenge_wide("y", wide);
+            t.challenge_wide("z", wide + 64);
             t.append_point("T1", pt + 96);
             t.append_point("T3", pt + 128);
             t.append_point("T4", mode == 0 ? pt + 128 : pt + 160);
             t.append_point("T5", pt + 192);
             t.append_point("T6", pt + 224);
-            t.challenge_wide("x", b->h_wide + 192 * (size_t)p + 128);
+            t.challenge_wide("x", wide + 128);
+            acp_host_weights(t, b->h_proofs + (size_t)p * b->proof_len, b->proof_len, seed, p, mode, wide + 192);
         });
-        if ((rc = acp_put_challenges(b, L.y, 3))) return rc;
+        if ((rc = acp_put_challenges(b, L.y, 5))) return rc;
     }
-    k_acp_weights<<<(B + 127) / 128, 128, 0, s>>>(b->d_vseed, L, B, mode, b->d_blk);
-    LAUNCH_CHECK(ctx);
     if ((rc = acp_challenge_dependent_scalars(b))) return rc;
     k_acp_dots<<<dim3(2, B), 128, 0, s>>>(L, 9, b->d_blk);  // sigma, <l, r>
     LAUNCH_CHECK(ctx);
+    if (!b->host_transcripts) CK(ctx, cudaStreamWaitEvent(s, b->ev_join2, 0));   // w, rho0 (k_tr_weights)
     k_acp_vscal<<<dim3((n + m + 1 + 127) / 128, B), 128, 0, s>>>(L, b->d_blk);
     LAUNCH_CHECK(ctx);
     CK(ctx, cudaStreamWaitEvent(s, b->ev_join, 0));   // decompressed points + bad flags (forked after the unpack)
@@ -1037,11 +1355,14 @@ extern "C" int bpp_acp_batch_time_commit_msm(bpp_acp_batch *b, int reps, float *
 // ---- one-call host forms (what a drop-in for create..blinding_values / verify binds) -------------------
 extern "C" int bpp_acproof_prove_batch(bpp_ctx *ctx, const bpp_circuit *cir, const bpp_gens *gens, int mode, size_t count,
                                        const uint8_t *aL, const uint8_t *aR, const uint8_t *aO, const uint8_t *gamma,
-                                       const uint8_t *seeds, const uint8_t *label, size_t label_len, uint8_t *proofs_out) {
+                                       const uint8_t *seeds, const uint8_t *V, const uint8_t *label, size_t label_len,
+                                       uint8_t *proofs_out) {
+    if (mode != 0 && !V) return BPP_ERR_INVALID_ARG;   // modes 1 and 2 bind the commitments to the transcript
     bpp_acp_batch *b = nullptr;
     int rc = bpp_acp_batch_create(ctx, cir, gens, mode, count, label, label_len, &b);
     if (rc) return rc;
     rc = bpp_acp_batch_upload_witness(b, aL, aR, aO, gamma, seeds);
+    if (!rc && V) rc = bpp_acp_batch_upload_commitments(b, V);
     if (!rc) rc = bpp_acp_batch_prove(b);
     if (!rc) rc = bpp_acp_batch_download_proofs(b, proofs_out);
     bpp_acp_batch_free(b);
@@ -1050,7 +1371,7 @@ extern "C" int bpp_acproof_prove_batch(bpp_ctx *ctx, const bpp_circuit *cir, con
 
 extern "C" int bpp_acproof_verify_batch(bpp_ctx *ctx, const bpp_circuit *cir, const bpp_gens *gens, int mode, size_t count,
                                         const uint8_t *proofs, const uint8_t *V, const uint8_t *label, size_t label_len,
-                                        const uint8_t verifier_seed[32], uint8_t *accept) {
+                                        const uint8_t *verifier_seed, uint8_t *accept) {
     if (!V) return BPP_ERR_INVALID_ARG;
     bpp_acp_batch *b = nullptr;
     int rc = bpp_acp_batch_create(ctx, cir, gens, mode, count, label, label_len, &b);

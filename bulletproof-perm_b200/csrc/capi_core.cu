@@ -55,7 +55,7 @@ extern "C" void bpp_free(bpp_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    void *ptrs[] = {ctx->d_scalars, ctx->d_out, ctx->d_stage, ctx->d_flag, ctx->d_vec};
+    void *ptrs[] = {ctx->d_scalars, ctx->d_out, ctx->d_stage, ctx->d_flag, ctx->d_vec, ctx->d_small};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto &sc : ctx->scr) {
@@ -304,6 +304,7 @@ extern "C" void bpp_points_free(bpp_ctx *ctx, bpp_points *p) {
         cudaStreamSynchronize(ctx->stream);
     }
     if (p->niels) cudaFree(p->niels);
+    if (p->fb_table) cudaFree(p->fb_table);
     delete p;
 }
 extern "C" size_t bpp_points_len(const bpp_points *p) { return p ? p->n : 0; }
@@ -691,6 +692,8 @@ extern "C" int bpp_msm_vartime(bpp_ctx *ctx, const uint8_t *scalars, size_t n_sc
     int rc = check_scalars_host(scalars, n);
     if (rc) return rc;
     CK(ctx, cudaSetDevice(ctx->device));
+    if (points->fb_table && !out_ext && n <= BPP_TABLE_MSM_MAX_POINTS)   // precomputed points: no buckets, no doublings
+        return bpp_msm_vartime_batch(ctx, scalars, 1, const_cast<bpp_points *>(points), off, n, out32);
     if ((rc = grow(ctx, &ctx->d_scalars, &ctx->cap_scalars, n * 8))) return rc;
     CK(ctx, cudaMemcpyAsync(ctx->d_scalars, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
     if ((rc = msm_enqueue(ctx, ctx->d_scalars, points, off, n, ctx->d_out, 1))) return rc;

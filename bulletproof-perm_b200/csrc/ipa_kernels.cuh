@@ -61,57 +61,94 @@ __global__ void __launch_bounds__(128) k_pow_fill(acp_layout lay, uint32_t *__re
 }
 
 // ---- prover rounds -----------------------------------------------------------------------------------
-// block per (proof, which): cl[0] = w <a_L, b_R>, cl[1] = w <a_R, b_L> over the current halves (the Q = w*g term)
-__global__ void __launch_bounds__(128) k_ipa_dots(acp_layout lay, uint32_t h, uint32_t *__restrict__ blk) {
+// A round is: [MSM over the original generators -> L_j, R_j] -> compress -> k_ipa_challenge (transcript_kernels.cuh: one
+// warp per proof appends L_j, R_j, draws u_j and inverts it) -> k_ipa_round (below: everything that is parallel over the
+// vector - fold a and b, extend the table of the s_t, the next round's two inner products and its MSM scalars).
+//
+// s table (lay.stab, 2 x n' scalars per proof, Montgomery form, double buffered by the parity of the rounds done):
+// after r rounds buffer r & 1 holds s_t = prod_{k<r} (bit (r-1-k) of t ? u_k : u_k^-1) for t < 2^r, built by doubling,
+// s'_{2t+b} = s_t * (b ? u_r : u_r^-1): one multiplication per entry and round instead of r per generator and round.
+// The inverse is the complemented index: s_t^-1 = s_{2^r - 1 - t}.
+#define IPA_ROUND_THREADS 512
+SC_INLINE uint32_t *ipa_stab(uint32_t *blk, const acp_layout &lay, uint32_t p, uint32_t rounds_done) {
+    return ACP_PTR(blk, lay, p, lay.stab + (rounds_done & 1u) * lay.np);
+}
+// block per proof.  round = index of the challenge just drawn (u[round], uinv[round] in Montgomery form), -1 before the
+// first round (w at lay.wq drawn).  Leaves a, b folded (lay.l, lay.r), cl[0..1] = w <a_lo, b_hi>, w <a_hi, b_lo> and
+// vG, vH = the next round's MSM scalars; after the last round only the fold happens (a, b are l[0], r[0]).
+__global__ void __launch_bounds__(IPA_ROUND_THREADS) k_ipa_round(acp_layout lay, int round, uint32_t *__restrict__ blk) {
     __shared__ __align__(16) uint32_t sh[32 * 8];
-    const uint32_t which = blockIdx.x, p = blockIdx.y;
-    const uint32_t *a = ACP_PTR(blk, lay, p, lay.l + (which ? h : 0));
-    const uint32_t *b = ACP_PTR(blk, lay, p, lay.r + (which ? 0 : h));
-    sc acc, tot, w;
-    dot_partial(acc, a, 1, b, 1, h);
-    block_sum_sc(tot, acc, sh);
-    if (threadIdx.x == 0) {
-        sc r2;
-        sc_const(r2, SC_R2);
-        sc_mont(tot, tot, r2);
+    const uint32_t p = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const uint32_t done = (uint32_t)(round + 1);
+    uint32_t *st_new = ipa_stab(blk, lay, p, done);
+    if (round < 0) {
+        if (tid == 0) {
+            sc one;
+            sc_const(one, SC_R);
+            sc_store(st_new, one);
+        }
+    } else {
+        const uint32_t h = lay.np >> done;
+        sc u, ui, lo, hi, t1, t2;
+        sc_load(u, ACP_PTR(blk, lay, p, lay.u + round));
+        sc_load(ui, ACP_PTR(blk, lay, p, lay.uinv + round));
+        for (uint32_t i = tid; i < h; i += nt) {       // a[i] = a[i] u + u^-1 a[h+i],  b[i] = b[i] u^-1 + u b[h+i]
+            sc_load(lo, ACP_PTR(blk, lay, p, lay.l + i));
+            sc_load(hi, ACP_PTR(blk, lay, p, lay.l + h + i));
+            sc_mont(t1, lo, u);
+            sc_mont(t2, hi, ui);
+            sc_add(t1, t1, t2);
+            sc_store(ACP_PTR(blk, lay, p, lay.l + i), t1);
+            sc_load(lo, ACP_PTR(blk, lay, p, lay.r + i));
+            sc_load(hi, ACP_PTR(blk, lay, p, lay.r + h + i));
+            sc_mont(t1, lo, ui);
+            sc_mont(t2, hi, u);
+            sc_add(t1, t1, t2);
+            sc_store(ACP_PTR(blk, lay, p, lay.r + i), t1);
+        }
+        if (done < lay.lg) {                           // the last round's table is never read
+            const uint32_t *st_old = ipa_stab(blk, lay, p, (uint32_t)round);
+            for (uint32_t t = tid; t < (1u << done); t += nt) {
+                sc_load(lo, st_old + 8 * (size_t)(t >> 1));
+                sc_mont(t1, lo, (t & 1u) ? u : ui);
+                sc_store(st_new + 8 * (size_t)t, t1);
+            }
+        }
+    }
+    if (done >= lay.lg) return;
+    __syncthreads();                                   // a, b, s table of this block: visible to the whole block
+    const uint32_t nj = lay.np >> done, h = nj >> 1;
+    {
+        sc acc, tot, w, r2;
         sc_load(w, ACP_PTR(blk, lay, p, lay.wq));
-        sc_mul(tot, tot, w);
-        sc_store(ACP_PTR(blk, lay, p, lay.cl + which), tot);
+        sc_const(r2, SC_R2);
+        for (uint32_t which = 0; which < 2; which++) {
+            dot_partial(acc, ACP_PTR(blk, lay, p, lay.l + (which ? h : 0)), 1, ACP_PTR(blk, lay, p, lay.r + (which ? 0 : h)), 1, h);
+            block_sum_sc(tot, acc, sh);
+            if (tid == 0) {
+                sc_mont(tot, tot, r2);
+                sc_mul(tot, tot, w);
+                sc_store(ACP_PTR(blk, lay, p, lay.cl + which), tot);
+            }
+        }
+    }
+    const uint32_t tmask = (1u << done) - 1u;
+    for (uint32_t g = tid; g < lay.np; g += nt) {      // the round's MSM scalars over the original generators
+        const uint32_t i = g & (nj - 1), t = g >> (lay.lg - done), ip = i ^ h;
+        sc s, sinv, a, b, yi, r;
+        sc_load(s, st_new + 8 * (size_t)t);
+        sc_load(sinv, st_new + 8 * (size_t)(tmask - t));
+        sc_load(a, ACP_PTR(blk, lay, p, lay.l + ip));
+        sc_load(b, ACP_PTR(blk, lay, p, lay.r + ip));
+        sc_load(yi, ACP_PTR(blk, lay, p, lay.yninv + g));
+        sc_mont(r, a, s);                              // a * s_t (s in Montgomery form -> standard result)
+        sc_store(ACP_PTR(blk, lay, p, lay.vG + g), r);
+        sc_mont(r, b, sinv);
+        sc_mul(r, r, yi);
+        sc_store(ACP_PTR(blk, lay, p, lay.vH + g), r);
     }
 }
-// s_t (or its inverse) for the first `rounds` challenges: prod_k (bit (rounds-1-k) of t ? u_k : u_k^-1)
-SC_INLINE void ipa_s_mont(sc &s, sc &sinv, const uint32_t *__restrict__ u, const uint32_t *__restrict__ ui, uint32_t rounds,
-                          uint32_t t) {
-    sc a, b;
-    sc_const(s, SC_R);
-    sinv = s;
-#pragma unroll 1
-    for (uint32_t k = 0; k < rounds; k++) {
-        sc_load(a, u + 8 * (size_t)k);      // Montgomery form
-        sc_load(b, ui + 8 * (size_t)k);
-        const bool bit = (t >> (rounds - 1 - k)) & 1u;
-        sc_mont_noinline(s, s, bit ? a : b);
-        sc_mont_noinline(sinv, sinv, bit ? b : a);
-    }
-}
-// thread per (proof, g < n'): the round's MSM scalars over the original generators
-__global__ void __launch_bounds__(128) k_ipa_prep(acp_layout lay, uint32_t round, uint32_t *__restrict__ blk) {
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
-    if (g >= lay.np) return;
-    const uint32_t nj = lay.np >> round, h = nj >> 1;
-    const uint32_t i = g & (nj - 1), t = g >> (lay.lg - round), ip = i ^ h;
-    sc s, sinv, a, b, yi, r;
-    ipa_s_mont(s, sinv, ACP_PTR(blk, lay, p, lay.u), ACP_PTR(blk, lay, p, lay.uinv), round, t);
-    sc_load(a, ACP_PTR(blk, lay, p, lay.l + ip));
-    sc_load(b, ACP_PTR(blk, lay, p, lay.r + ip));
-    sc_load(yi, ACP_PTR(blk, lay, p, lay.yninv + g));
-    sc_mont(r, a, s);                       // a * s_t (s in Montgomery form -> standard result)
-    sc_store(ACP_PTR(blk, lay, p, lay.vG + g), r);
-    sc_mont(r, b, sinv);
-    sc_mul(r, r, yi);
-    sc_store(ACP_PTR(blk, lay, p, lay.vH + g), r);
-}
-// thread per proof: u_round^-1; both kept in Montgomery form at u[round], uinv[round]
+// host-transcript path: thread per proof: u_round^-1; both kept in Montgomery form at u[round], uinv[round]
 __global__ void __launch_bounds__(64) k_ipa_uinv(acp_layout lay, uint32_t B, uint32_t round, uint32_t *__restrict__ blk) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= B) return;
@@ -123,26 +160,27 @@ __global__ void __launch_bounds__(64) k_ipa_uinv(acp_layout lay, uint32_t B, uin
     sc_store(ACP_PTR(blk, lay, p, lay.u + round), u);
     sc_store(ACP_PTR(blk, lay, p, lay.uinv + round), ui);
 }
-// thread per (proof, i < h): a[i] = a[i] u + u^-1 a[h+i],  b[i] = b[i] u^-1 + u b[h+i]   (in place)
-__global__ void __launch_bounds__(128) k_ipa_fold(acp_layout lay, uint32_t round, uint32_t *__restrict__ blk) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
-    const uint32_t h = lay.np >> (round + 1);
-    if (i >= h) return;
-    sc u, ui, lo, hi, t1, t2;
-    sc_load(u, ACP_PTR(blk, lay, p, lay.u + round));
-    sc_load(ui, ACP_PTR(blk, lay, p, lay.uinv + round));
-    sc_load(lo, ACP_PTR(blk, lay, p, lay.l + i));
-    sc_load(hi, ACP_PTR(blk, lay, p, lay.l + h + i));
-    sc_mont(t1, lo, u);
-    sc_mont(t2, hi, ui);
-    sc_add(t1, t1, t2);
-    sc_store(ACP_PTR(blk, lay, p, lay.l + i), t1);
-    sc_load(lo, ACP_PTR(blk, lay, p, lay.r + i));
-    sc_load(hi, ACP_PTR(blk, lay, p, lay.r + h + i));
-    sc_mont(t1, lo, ui);
-    sc_mont(t2, hi, u);
-    sc_add(t1, t1, t2);
-    sc_store(ACP_PTR(blk, lay, p, lay.r + i), t1);
+// verifier: the complete table s_i, i < n' (all lg challenges known) into buffer lg & 1 of lay.stab; block per proof
+__global__ void __launch_bounds__(IPA_ROUND_THREADS) k_ipa_stable_full(acp_layout lay, uint32_t *__restrict__ blk) {
+    const uint32_t p = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    if (tid == 0) {
+        sc one;
+        sc_const(one, SC_R);
+        sc_store(ipa_stab(blk, lay, p, 0), one);
+    }
+    for (uint32_t r = 0; r < lay.lg; r++) {
+        __syncthreads();
+        sc u, ui, v, o;
+        sc_load(u, ACP_PTR(blk, lay, p, lay.u + r));
+        sc_load(ui, ACP_PTR(blk, lay, p, lay.uinv + r));
+        const uint32_t *st_old = ipa_stab(blk, lay, p, r);
+        uint32_t *st_new = ipa_stab(blk, lay, p, r + 1);
+        for (uint32_t t = tid; t < (2u << r); t += nt) {
+            sc_load(v, st_old + 8 * (size_t)(t >> 1));
+            sc_mont(o, v, (t & 1u) ? u : ui);
+            sc_store(st_new + 8 * (size_t)t, o);
+        }
+    }
 }
 
 // ---- proof (de)serialisation, `fixed` mode: 8 points | t_hat, tau_x, mu | (L_j, R_j) x lg | a, b -----------
@@ -250,7 +288,9 @@ __global__ void __launch_bounds__(128) k_acp_vscal_fixed(acp_layout lay, uint32_
     sc_load(rho, ACP_PTR(blk, lay, p, lay.w));
     if (i < lay.np) {
         sc s, sinv, pa, pb, yi, yn;
-        ipa_s_mont(s, sinv, ACP_PTR(blk, lay, p, lay.u), ACP_PTR(blk, lay, p, lay.uinv), lay.lg, i);
+        const uint32_t *st = ipa_stab(blk, lay, p, lay.lg);   // k_ipa_stable_full
+        sc_load(s, st + 8 * (size_t)i);
+        sc_load(sinv, st + 8 * (size_t)(lay.np - 1 - i));
         sc_load(pa, ACP_PTR(blk, lay, p, lay.pa));
         sc_load(pb, ACP_PTR(blk, lay, p, lay.pb));
         sc_load(yi, ACP_PTR(blk, lay, p, lay.yninv + i));

@@ -78,6 +78,8 @@ static __device__ __noinline__ void keccak_f1600_dev(uint64_t *st) {
 struct merlin_tr {
     uint64_t st[25];
     uint32_t pos, pos_begin, cur_flags;
+    static const uint32_t GROUP = 1;   // threads per transcript (merlin_warp: 32)
+    static const uint32_t lane = 0;    // every thread is its transcript's leader
 
     static const uint32_t R = 166;
     static const uint32_t F_I = 1, F_A = 2, F_C = 4, F_M = 16, F_K = 32;

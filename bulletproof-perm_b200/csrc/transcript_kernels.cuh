@@ -8,37 +8,102 @@
 #pragma once
 #include "acproof_kernels.cuh"
 #include "merlin_dev.cuh"
+#include "merlin_warp.cuh"
 
-#define TR_THREADS 32
+// Every transcript kernel exists in two forms, selected by the number of independent sponges of the launch:
+//   merlin_warp  one WARP per sponge (merlin_warp.cuh): lowest latency per permutation (~2.5 us), nine 64-bit shuffles
+//                per round - the form for small batches, where the sponge is the critical path;
+//   merlin_tr    one THREAD per sponge (merlin_dev.cuh): ~6 us per permutation but 32 sponges per warp and no shuffles,
+//                2-3 x less issue work per permutation - it only pays once the launch has enough sponges for more than
+//                a warp per SM sub-partition (measured, profiles/r2c_launches_*.csv: 4096 sponges - k_tr_weights 0.94 ms
+//                against 0.40 ms in the warp form, k_tr_verify 0.43 against 0.27; 8192 sponges - k_tr_vchunks 0.35
+//                against 0.48).
+// TR_LAUNCH picks by count (tr_warp_max sponges and below: warp form; BPP_TR_WARP_MAX overrides).
+#define TR_THREADS 128
+template <class T>
+__device__ __forceinline__ uint32_t tr_index() { return (blockIdx.x * blockDim.x + threadIdx.x) / T::GROUP; }
+template <class T>
+__device__ __forceinline__ bool tr_leader() { return (threadIdx.x % T::GROUP) == 0; }
+static inline uint32_t tr_warp_max() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("BPP_TR_WARP_MAX");
+        v = e ? atoi(e) : 6143;
+    }
+    return (uint32_t)v;
+}
+#define TR_LAUNCH(kern, count, stream, ...)                                                                        \
+    do {                                                                                                           \
+        const uint32_t tr_cnt_ = (uint32_t)(count);                                                                \
+        if (tr_cnt_ <= tr_warp_max()) kern<merlin_warp><<<(tr_cnt_ + TR_THREADS / 32 - 1) / (TR_THREADS / 32), TR_THREADS, 0, stream>>>(__VA_ARGS__); \
+        else kern<merlin_tr><<<(tr_cnt_ + 31) / 32, 32, 0, stream>>>(__VA_ARGS__);                                 \
+    } while (0)
 
-// proto: the transcript after Transcript::new(label) + arithmetic_domain_sep(n), identical for every
-// proof (hashed once on the host).  pts8: B x 8 x 32 compressed (A_I, A_O, S, T1, T3, T4, T5, T6).
-__global__ void __launch_bounds__(TR_THREADS) k_tr_prove_yz(const uint64_t *__restrict__ proto,
+// The value commitments, bound to the transcript right after the domain separator (modes 1 and 2; the reference never
+// appends them - SURVEY A.3 defect 12, weak Fiat-Shamir: the prover of a shuffle chooses the output-deck commitments).
+// Two levels (CPU restatements: commitment_digests / append_commitments in the test tree): every chunk of TR_V_CHUNK commitments is a
+// sponge of its own - Transcript::new("acp-V"), append_u64("chunk", index), append_point("V", V_j) in order,
+// challenge_bytes("d", 32) - and the proof's transcript absorbs m under "m" and the chunk digests under "Vd".  One
+// serial sponge over the m = 8193 commitments of a 4096-card deck is ~2000 permutations in a row on the critical path
+// of prover and verifier; the chunks run as independent warps.
+#define TR_V_CHUNK 64
+#define TR_V_CHUNKS(m) (((m) + TR_V_CHUNK - 1) / TR_V_CHUNK)
+// vproto: the transcript after Transcript::new("acp-V").  One warp per (proof, chunk); vdig: B x chunks x 32.
+template <class T>
+__global__ void __launch_bounds__(TR_THREADS) k_tr_vchunks(const uint64_t *__restrict__ vproto, const uint8_t *__restrict__ V,
+                                                           uint32_t m, uint32_t B, uint8_t *__restrict__ vdig) {
+    const uint32_t nch = TR_V_CHUNKS(m), w = tr_index<T>();
+    if (w >= B * nch) return;
+    const uint32_t p = w / nch, c = w % nch;
+    T t;
+    t.load(vproto);
+    t.append_u64(MERLIN_LABEL("chunk"), c);
+    const uint8_t *v = V + 32 * ((size_t)p * m + (size_t)c * TR_V_CHUNK);
+    const uint32_t cnt = min((uint32_t)TR_V_CHUNK, m - c * TR_V_CHUNK);
+#pragma unroll 1
+    for (uint32_t j = 0; j < cnt; j++) t.append_message(MERLIN_LABEL("V"), v + 32 * (size_t)j, 32);
+    t.challenge_bytes(MERLIN_LABEL("d"), vdig + 32 * (size_t)w, 32);
+}
+template <class T>
+__device__ __forceinline__ void tr_append_commitments(T &t, const uint8_t *vdig, uint32_t m) {
+    t.append_u64(MERLIN_LABEL("m"), m);
+    const uint32_t nch = TR_V_CHUNKS(m);
+#pragma unroll 1
+    for (uint32_t c = 0; c < nch; c++) t.append_message(MERLIN_LABEL("Vd"), vdig + 32 * (size_t)c, 32);
+}
+
+// proto: the transcript after Transcript::new(label) + arithmetic_domain_sep(n), identical for every proof (hashed
+// once on the host).  pts8: B x 8 x 32 compressed (A_I, A_O, S, T1, T3, T4, T5, T6).  vdig: the chunk digests of the
+// commitments (k_tr_vchunks), null in mode 0.
+template <class T>
+__global__ void __launch_bounds__(TR_THREADS) k_tr_prove_yz(const uint64_t *__restrict__ proto, const uint8_t *__restrict__ vdig,
                                                             const uint8_t *__restrict__ pts8, acp_layout lay,
                                                             uint32_t B, uint64_t *__restrict__ states,
                                                             uint32_t *__restrict__ blk) {
-    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t p = tr_index<T>();
     if (p >= B) return;
-    merlin_tr t;
+    T t;
     t.load(proto);
+    if (vdig) tr_append_commitments(t, vdig + 32 * (size_t)p * TR_V_CHUNKS(lay.m), lay.m);
     const uint8_t *pt = pts8 + 256 * (size_t)p;
     t.append_message(MERLIN_LABEL("A_I"), pt, 32);
     t.append_message(MERLIN_LABEL("A_O"), pt + 32, 32);
     t.append_message(MERLIN_LABEL("S"), pt + 64, 32);
     sc c;
     t.challenge_scalar(MERLIN_LABEL("y"), c);
-    sc_store(ACP_PTR(blk, lay, p, lay.y), c);
+    if (t.lane == 0) sc_store(ACP_PTR(blk, lay, p, lay.y), c);
     t.challenge_scalar(MERLIN_LABEL("z"), c);
-    sc_store(ACP_PTR(blk, lay, p, lay.z), c);
+    if (t.lane == 0) sc_store(ACP_PTR(blk, lay, p, lay.z), c);
     t.store(states + MERLIN_STATE_WORDS * (size_t)p);
 }
 
+template <class T>
 __global__ void __launch_bounds__(TR_THREADS) k_tr_prove_x(const uint8_t *__restrict__ pts8, acp_layout lay, uint32_t B,
                                                            int mode, uint64_t *__restrict__ states,
                                                            uint32_t *__restrict__ blk) {
-    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t p = tr_index<T>();
     if (p >= B) return;
-    merlin_tr t;
+    T t;
     t.load(states + MERLIN_STATE_WORDS * (size_t)p);
     const uint8_t *pt = pts8 + 256 * (size_t)p + 96;
     t.append_message(MERLIN_LABEL("T1"), pt, 32);
@@ -48,99 +113,130 @@ __global__ void __launch_bounds__(TR_THREADS) k_tr_prove_x(const uint8_t *__rest
     t.append_message(MERLIN_LABEL("T6"), pt + 128, 32);
     sc c;
     t.challenge_scalar(MERLIN_LABEL("x"), c);
-    sc_store(ACP_PTR(blk, lay, p, lay.x), c);
+    if (t.lane == 0) sc_store(ACP_PTR(blk, lay, p, lay.x), c);
     t.store(states + MERLIN_STATE_WORDS * (size_t)p);
 }
 
-FE_INLINE void tr_scalar_bytes(uint8_t out[32], const uint32_t *src) {
-    for (int i = 0; i < 8; i++) {
-        uint32_t v = src[i];
-        out[4 * i] = (uint8_t)v; out[4 * i + 1] = (uint8_t)(v >> 8); out[4 * i + 2] = (uint8_t)(v >> 16);
-        out[4 * i + 3] = (uint8_t)(v >> 24);
+// `fixed` mode: t_x, t_x_blinding, e_blinding (contiguous canonical scalars at lay.that: in memory they ARE their
+// 32-byte little-endian encodings) -> w; inner-product domain separator
+template <class T>
+__device__ __forceinline__ void tr_fixed_w(T &t, const uint8_t *s3, uint32_t np, sc &w) {
+    t.append_message(MERLIN_LABEL("t_x"), s3, 32);
+    t.append_message(MERLIN_LABEL("t_x_blinding"), s3 + 32, 32);
+    t.append_message(MERLIN_LABEL("e_blinding"), s3 + 64, 32);
+    t.challenge_scalar(MERLIN_LABEL("w"), w);
+    t.append_message(MERLIN_LABEL("dom-sep"), (const uint8_t *)"ipp v1", 6);
+    t.append_u64(MERLIN_LABEL("n"), np);
+}
+// Inner-product rounds of the prover, one warp per proof.  round < 0: t_x, t_x_blinding, e_blinding -> w and the
+// inner-product domain separator.  round >= 0: append L_round, R_round, draw u_round and invert it (lane 0; the
+// branch-free GCD of sc_invert) - u and u^-1 are left in Montgomery form at lay.u / lay.uinv for k_ipa_round.
+template <class T>
+__global__ void __launch_bounds__(TR_THREADS) k_ipa_challenge(const uint8_t *__restrict__ lr, acp_layout lay, uint32_t B,
+                                                              int round, uint64_t *__restrict__ states,
+                                                              uint32_t *__restrict__ blk) {
+    const uint32_t p = tr_index<T>();
+    if (p >= B) return;
+    T t;
+    t.load(states + MERLIN_STATE_WORDS * (size_t)p);
+    sc c;
+    if (round < 0) {
+        tr_fixed_w(t, (const uint8_t *)ACP_PTR(blk, lay, p, lay.that), lay.np, c);
+        if (t.lane == 0) sc_store(ACP_PTR(blk, lay, p, lay.wq), c);
+    } else {
+        const uint8_t *q = lr + 64 * ((size_t)lay.lg * p + round);
+        t.append_message(MERLIN_LABEL("L"), q, 32);
+        t.append_message(MERLIN_LABEL("R"), q + 32, 32);
+        t.challenge_scalar(MERLIN_LABEL("u"), c);
+    }
+    t.store(states + MERLIN_STATE_WORDS * (size_t)p);
+    if (round >= 0 && t.lane == 0) {
+        sc ci;
+        sc_invert(ci, c);
+        sc_to_mont(c, c);
+        sc_to_mont(ci, ci);
+        sc_store(ACP_PTR(blk, lay, p, lay.u + round), c);
+        sc_store(ACP_PTR(blk, lay, p, lay.uinv + round), ci);
     }
 }
 
-// `fixed` mode: t_x, t_x_blinding, e_blinding (contiguous at lay.that) -> w; inner-product domain separator
-__global__ void __launch_bounds__(TR_THREADS) k_tr_prove_w(acp_layout lay, uint32_t B, uint64_t *__restrict__ states,
-                                                           uint32_t *__restrict__ blk) {
-    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= B) return;
-    merlin_tr t;
-    t.load(states + MERLIN_STATE_WORDS * (size_t)p);
-    uint8_t s[32];
-    tr_scalar_bytes(s, ACP_PTR(blk, lay, p, lay.that));
-    t.append_message(MERLIN_LABEL("t_x"), s, 32);
-    tr_scalar_bytes(s, ACP_PTR(blk, lay, p, lay.that + 1));
-    t.append_message(MERLIN_LABEL("t_x_blinding"), s, 32);
-    tr_scalar_bytes(s, ACP_PTR(blk, lay, p, lay.that + 2));
-    t.append_message(MERLIN_LABEL("e_blinding"), s, 32);
-    sc c;
-    t.challenge_scalar(MERLIN_LABEL("w"), c);
-    sc_store(ACP_PTR(blk, lay, p, lay.wq), c);
-    t.append_message(MERLIN_LABEL("dom-sep"), (const uint8_t *)"ipp v1", 6);
-    t.append_u64(MERLIN_LABEL("n"), lay.np);
-    t.store(states + MERLIN_STATE_WORDS * (size_t)p);
-}
-
-// `fixed` mode, round j: L_j, R_j (B x 2 lg x 32 compressed) -> u_j
-__global__ void __launch_bounds__(TR_THREADS) k_tr_prove_u(const uint8_t *__restrict__ lr, acp_layout lay, uint32_t B,
-                                                           uint32_t j, uint64_t *__restrict__ states,
-                                                           uint32_t *__restrict__ blk) {
-    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= B) return;
-    merlin_tr t;
-    t.load(states + MERLIN_STATE_WORDS * (size_t)p);
-    const uint8_t *q = lr + 64 * ((size_t)lay.lg * p + j);
-    t.append_message(MERLIN_LABEL("L"), q, 32);
-    t.append_message(MERLIN_LABEL("R"), q + 32, 32);
-    sc c;
-    t.challenge_scalar(MERLIN_LABEL("u"), c);
-    sc_store(ACP_PTR(blk, lay, p, lay.u + j), c);
-    t.store(states + MERLIN_STATE_WORDS * (size_t)p);
-}
-
-// Verifier: replays the whole transcript of one proof.  tx3 (B x 3 x 32: t_x, t_x_blinding, e_blinding)
-// and lr are used in `fixed` mode only (lay.lg > 0).
-__global__ void __launch_bounds__(TR_THREADS) k_tr_verify(const uint64_t *__restrict__ proto,
+// Verifier: replays the whole transcript of one proof and leaves its final state in `states` (k_tr_weights continues
+// it).  tx3 (B x 3 x 32: t_x, t_x_blinding, e_blinding, reduced) and lr are used in `fixed` mode only (lay.lg > 0).
+template <class T>
+__global__ void __launch_bounds__(TR_THREADS) k_tr_verify(const uint64_t *__restrict__ proto, const uint8_t *__restrict__ vdig,
                                                           const uint8_t *__restrict__ pts8,
                                                           const uint8_t *__restrict__ tx3,
                                                           const uint8_t *__restrict__ lr, acp_layout lay, uint32_t B,
-                                                          int mode, uint32_t *__restrict__ blk) {
-    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+                                                          int mode, uint32_t *__restrict__ blk,
+                                                          uint64_t *__restrict__ states) {
+    const uint32_t p = tr_index<T>();
     if (p >= B) return;
-    merlin_tr t;
+    T t;
     t.load(proto);
+    if (mode != 0) tr_append_commitments(t, vdig + 32 * (size_t)p * TR_V_CHUNKS(lay.m), lay.m);
     const uint8_t *pt = pts8 + 256 * (size_t)p;
     t.append_message(MERLIN_LABEL("A_I"), pt, 32);
     t.append_message(MERLIN_LABEL("A_O"), pt + 32, 32);
     t.append_message(MERLIN_LABEL("S"), pt + 64, 32);
     sc c;
     t.challenge_scalar(MERLIN_LABEL("y"), c);
-    sc_store(ACP_PTR(blk, lay, p, lay.y), c);
+    if (t.lane == 0) sc_store(ACP_PTR(blk, lay, p, lay.y), c);
     t.challenge_scalar(MERLIN_LABEL("z"), c);
-    sc_store(ACP_PTR(blk, lay, p, lay.z), c);
+    if (t.lane == 0) sc_store(ACP_PTR(blk, lay, p, lay.z), c);
     t.append_message(MERLIN_LABEL("T1"), pt + 96, 32);
     t.append_message(MERLIN_LABEL("T3"), pt + 128, 32);
     t.append_message(MERLIN_LABEL("T4"), mode == 0 ? pt + 128 : pt + 160, 32);
     t.append_message(MERLIN_LABEL("T5"), pt + 192, 32);
     t.append_message(MERLIN_LABEL("T6"), pt + 224, 32);
     t.challenge_scalar(MERLIN_LABEL("x"), c);
-    sc_store(ACP_PTR(blk, lay, p, lay.x), c);
-    if (mode != 2) return;
-    const uint8_t *s3 = tx3 + 96 * (size_t)p;
-    t.append_message(MERLIN_LABEL("t_x"), s3, 32);
-    t.append_message(MERLIN_LABEL("t_x_blinding"), s3 + 32, 32);
-    t.append_message(MERLIN_LABEL("e_blinding"), s3 + 64, 32);
-    t.challenge_scalar(MERLIN_LABEL("w"), c);
-    sc_store(ACP_PTR(blk, lay, p, lay.wq), c);
-    t.append_message(MERLIN_LABEL("dom-sep"), (const uint8_t *)"ipp v1", 6);
-    t.append_u64(MERLIN_LABEL("n"), lay.np);
-    for (uint32_t j = 0; j < lay.lg; j++) {   // an identity encoding is rejected in k_acp_decompress_lr
-        const uint8_t *q = lr + 64 * ((size_t)lay.lg * p + j);
-        t.append_message(MERLIN_LABEL("L"), q, 32);
-        t.append_message(MERLIN_LABEL("R"), q + 32, 32);
-        t.challenge_scalar(MERLIN_LABEL("u"), c);
-        sc_store(ACP_PTR(blk, lay, p, lay.u + j), c);
+    if (t.lane == 0) sc_store(ACP_PTR(blk, lay, p, lay.x), c);
+    if (mode == 2) {
+        tr_fixed_w(t, tx3 + 96 * (size_t)p, lay.np, c);
+        if (t.lane == 0) sc_store(ACP_PTR(blk, lay, p, lay.wq), c);
+#pragma unroll 1
+        for (uint32_t j = 0; j < lay.lg; j++) {   // an identity encoding is rejected in k_acp_decompress_lr
+            const uint8_t *q = lr + 64 * ((size_t)lay.lg * p + j);
+            t.append_message(MERLIN_LABEL("L"), q, 32);
+            t.append_message(MERLIN_LABEL("R"), q + 32, 32);
+            t.challenge_scalar(MERLIN_LABEL("u"), c);
+            if (t.lane == 0) sc_store(ACP_PTR(blk, lay, p, lay.u + j), c);
+        }
+    }
+    t.store(states + MERLIN_STATE_WORDS * (size_t)p);
+}
+
+// Verifier weights.  The per-proof weight w (check 2 + w * check 3 as ONE multiscalar multiplication) and
+// the batch weight rho (random linear combination over the batch) must be unpredictable to whoever made the proofs:
+// with a known w a prover cancels an error of check 3 against tau_x in check 2, with known rho two proofs of one batch
+// carry cancelling offsets.  They are drawn like dalek's verifier draws its weights - from the proof's own transcript,
+// which has absorbed the commitments and every proof message, rekeyed with the verifier's secret randomness: the final
+// verifier state continues with the rest of the proof bytes (the scalars after the eight points), the verifier seed
+// and the proof's index, then "w" and "rho" are challenge scalars.  So even a caller that reuses or leaks its seed
+// gets weights that depend on every byte of the proof.  (bpp_acp_batch_verify draws the seed from the OS when the
+// caller passes none.)  mode 0 (`reference`): w = 0, only checks 1 and 2 are live (circuit_lib.rs:577-582).
+template <class T>
+__global__ void __launch_bounds__(TR_THREADS) k_tr_weights(const uint64_t *__restrict__ states,
+                                                           const uint8_t *__restrict__ proofs, uint32_t proof_len,
+                                                           const uint8_t *__restrict__ vseed, acp_layout lay, uint32_t B,
+                                                           int mode, uint32_t *__restrict__ blk) {
+    const uint32_t p = tr_index<T>();
+    if (p >= B) return;
+    sc w, rho;
+    if (mode == 0) {
+        sc_set0(w);
+        sc_set0(rho);
+    } else {
+        T t;
+        t.load(states + MERLIN_STATE_WORDS * (size_t)p);
+        t.append_message(MERLIN_LABEL("proof-tail"), proofs + (size_t)p * proof_len + 256, proof_len - 256);
+        t.append_message(MERLIN_LABEL("verifier-seed"), vseed, 32);
+        t.append_u64(MERLIN_LABEL("proof-index"), p);
+        t.challenge_scalar(MERLIN_LABEL("w"), w);
+        t.challenge_scalar(MERLIN_LABEL("rho"), rho);
+    }
+    if (tr_leader<T>()) {
+        sc_store(ACP_PTR(blk, lay, p, lay.w), w);
+        sc_store(ACP_PTR(blk, lay, p, lay.rho0), rho);
     }
 }
 

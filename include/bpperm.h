@@ -166,6 +166,21 @@ int bpp_vecpoly3_eval(bpp_ctx *ctx, const uint8_t *coeffs, size_t n, const uint8
 /* poly.rs:14-18  Poly6::eval */
 int bpp_poly6_eval(bpp_ctx *ctx, const uint8_t t1_t6[192], const uint8_t x[32], uint8_t out[32]);
 
+/* ---- small and batched MSMs over a long-lived point set ---------------------------------
+ * The reference's 15 call sites (circuit_lib.rs:187-575) multiply 2..209 points that always come from the same
+ * generator set (g, h, G_vec, H_vec, lib.rs:164-180) by fresh scalars.  bpp_points_precompute attaches a fixed-base
+ * window table to a point set (window_bits 4..20, 0 = 8: 2^(c-1) x ceil(256/c) entries of 96 B per point, built once);
+ * from then on bpp_msm_vartime over any sub-range of up to 8192 of its points is table look-ups + mixed adds (no
+ * buckets, no doublings: three short launches), and bpp_msm_vartime_batch evaluates `count` MSMs over the same
+ * points[off..off+n) with count x n scalars in one launch (out32: count x 32 compressed results).  The table is built
+ * on first use (c = 8) if bpp_points_precompute was not called.  _dev: scalars and results in device memory,
+ * stream-ordered, no synchronisation. */
+int bpp_points_precompute(bpp_ctx *ctx, bpp_points *points, int window_bits);
+int bpp_msm_vartime_batch(bpp_ctx *ctx, const uint8_t *scalars, size_t count, bpp_points *points, size_t off, size_t n,
+                          uint8_t *out32);
+int bpp_msm_vartime_batch_dev(bpp_ctx *ctx, const void *d_scalars, size_t count, bpp_points *points, size_t off, size_t n,
+                              void *d_out32);
+
 /* ---- the arithmetic-circuit (shuffle) proof, batched ------------------------------------------------
  * Replaces the group/scalar arithmetic of ACProof::ArithmeticCircuitProof (circuit_lib.rs:133-585) for
  * `count` independent proofs that share one circuit and one generator set, driven in the reference's
@@ -195,6 +210,10 @@ typedef struct bpp_acp_batch bpp_acp_batch;
  * c_vec is the dense constant vector (Q x 32).  Constraint q: W_L a_L + W_R a_R + W_O a_O = W_V v + c. */
 int bpp_circuit_create(bpp_ctx *ctx, size_t n, size_t Q, size_t m, const uint32_t nnz[4], const uint32_t *wire,
                        const uint32_t *constraint, const uint8_t *coeff, const uint8_t *c_vec, bpp_circuit **out);
+/* The corrected k-card shuffle circuit, built inside the library (replaces weights.rs:130-204 create_weights, which as
+ * coded only makes sense for 2-3 cards - SURVEY A.3 defects 6-9): prod_i (v_i - X) == prod_i (v_{k+i} - X) with
+ * X = v[2k]; n = 2k multipliers, Q = 4k constraints, m = 2k + 1 committed values, c = 0. */
+int bpp_circuit_create_shuffle(bpp_ctx *ctx, size_t k, bpp_circuit **out);
 void bpp_circuit_free(bpp_ctx *ctx, bpp_circuit *c);
 /* g_base, h_base, G_vec[n], H_vec[n] (circuit_lib.rs:59-65) as compressed points; builds the fixed-base
  * window tables (window_bits 4..20, 0 = default 8; 2^(c-1) entries x 96 B per generator and window: a memory/throughput
@@ -219,10 +238,12 @@ size_t bpp_acproof_proof_len_mode(size_t n, int mode);    /* mode 2: 32 * (13 + 
 int bpp_acproof_prove_batch(bpp_ctx *ctx, const bpp_circuit *cir, const bpp_gens *gens, int mode, size_t count,
                             const uint8_t *aL, const uint8_t *aR, const uint8_t *aO /* count x n x 32 */,
                             const uint8_t *gamma /* count x m x 32 */, const uint8_t *seeds /* count x 32 */,
+                            const uint8_t *V /* count x m x 32 compressed; modes 1, 2 (bound to the transcript) */,
                             const uint8_t *label, size_t label_len, uint8_t *proofs_out /* count x proof_len */);
 int bpp_acproof_verify_batch(bpp_ctx *ctx, const bpp_circuit *cir, const bpp_gens *gens, int mode, size_t count,
                              const uint8_t *proofs, const uint8_t *V /* count x m x 32 compressed */,
-                             const uint8_t *label, size_t label_len, const uint8_t verifier_seed[32],
+                             const uint8_t *label, size_t label_len,
+                             const uint8_t *verifier_seed /* 32 secret bytes, or NULL: drawn from the OS */,
                              uint8_t *accept /* count bytes: 1 = Ok(()), 0 = Err(VerificationError) */);
 /* Staged forms (device-resident batches; used for the resident-input timing and by long-lived provers). */
 int bpp_acp_batch_create(bpp_ctx *ctx, const bpp_circuit *cir, const bpp_gens *gens, int mode, size_t count,
@@ -230,12 +251,32 @@ int bpp_acp_batch_create(bpp_ctx *ctx, const bpp_circuit *cir, const bpp_gens *g
 void bpp_acp_batch_free(bpp_acp_batch *b);
 int bpp_acp_batch_upload_witness(bpp_acp_batch *b, const uint8_t *aL, const uint8_t *aR, const uint8_t *aO,
                                  const uint8_t *gamma, const uint8_t *seeds);
-/* commit_variables (weights.rs:58-61): V_j = v_j*g + gamma_j*h with the uploaded gamma; V_out nullable. */
-int bpp_acp_batch_commit(bpp_acp_batch *b, const uint8_t *v /* count x m x 32 */, uint8_t *V_out);
+/* The shuffle witness generated on the device (replaces weights.rs:38-113 create_variables + create_a for the circuit
+ * of bpp_circuit_create_shuffle): deck = k card values (k x 32, shared by the batch), perm = count x k indices into the
+ * deck (proof p's output deck is deck[perm[p][i]]), x = count x 32 challenge values, gamma = count x m x 32 blindings,
+ * seeds = count x 32 prover RNG seeds.  Leaves a_L, a_R, a_O, gamma and v = deck | deck[perm] | x resident
+ * (bpp_acp_batch_commit with v = NULL commits to that v). */
+int bpp_acp_batch_gen_shuffle_witness(bpp_acp_batch *b, const uint8_t *deck, const uint32_t *perm, const uint8_t *x,
+                                      const uint8_t *gamma, const uint8_t *seeds);
+/* commit_variables (weights.rs:58-61): V_j = v_j*g + gamma_j*h with the uploaded gamma; V_out nullable; v = NULL: the
+ * values left by bpp_acp_batch_gen_shuffle_witness. */
+int bpp_acp_batch_commit(bpp_acp_batch *b, const uint8_t *v /* count x m x 32, nullable */, uint8_t *V_out);
+/* The value commitments as the caller holds them (count x m x 32 compressed).  Modes 1 and 2 bind them to every
+ * proof's transcript right after the domain separator (append_u64("m"), append_point("V") per commitment - what
+ * bulletproofs 4.0.0's R1CS prover/verifier do at commit time), so the prover needs them resident before
+ * bpp_acp_batch_prove: through this call or bpp_acp_batch_commit.  Mode 0 reproduces the reference, which never
+ * appends them (circuit_lib.rs:178-200; SURVEY A.3 defect 12). */
+int bpp_acp_batch_upload_commitments(bpp_acp_batch *b, const uint8_t *V);
 int bpp_acp_batch_prove(bpp_acp_batch *b);
 int bpp_acp_batch_download_proofs(bpp_acp_batch *b, uint8_t *proofs_out);
 int bpp_acp_batch_upload_proofs(bpp_acp_batch *b, const uint8_t *proofs, const uint8_t *V /* nullable */);
-int bpp_acp_batch_verify(bpp_acp_batch *b, const uint8_t verifier_seed[32]);
+/* verifier_seed: 32 bytes of SECRET, FRESH randomness of the verifier, or NULL to have the library draw them from
+ * the operating system (getrandom).  The per-proof weight w (check 2 + w * check 3 as one MSM) and the batch weight rho
+ * are challenge scalars of each proof's own transcript - which has absorbed V and every proof message - continued with
+ * the remaining proof bytes, this seed and the proof's index (dalek draws its verifier weights the same way, from a
+ * transcript RNG rekeyed with thread_rng).  A seed known to the prover before it fixes its proofs would still leave the
+ * weights bound to every proof byte, but pass NULL or fresh randomness; a constant is for reproducible tests only. */
+int bpp_acp_batch_verify(bpp_acp_batch *b, const uint8_t *verifier_seed);
 int bpp_acp_batch_download_accept(bpp_acp_batch *b, uint8_t *accept);
 /* Verification strategy: 1 (default) = first ONE random-linear-combination MSM over the whole batch (weights from
  * the verifier seed; Pippenger over count x (m + 8) decompressed points + the shared generators), the per-proof

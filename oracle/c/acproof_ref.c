@@ -241,6 +241,12 @@ static void tr_challenge_scalar(strobe *s, const char *label, sc *out) { /* tran
     strobe_prf(s, buf, 64);
     sc_from_wide(out, buf);
 }
+static void tr_challenge_bytes(strobe *s, const char *label, u8 *out, size_t n) {
+    u8 len[4] = {(u8)n, (u8)(n >> 8), (u8)(n >> 16), (u8)(n >> 24)};
+    strobe_meta_ad(s, (const u8 *)label, strlen(label), 0);
+    strobe_meta_ad(s, len, 4, 1);
+    strobe_prf(s, out, n);
+}
 static void tr_append_scalar(strobe *s, const char *label, const sc *x) { u8 b[32]; sc_tobytes(b, x); tr_append(s, label, b, 32); }
 /* append_vec_scalar (transcript_protocol.rs:36-43): decimal strings + bytevec framing; no challenge is
  * drawn afterwards in the reference flow, so only its cost matters here */
@@ -313,14 +319,35 @@ static int ge_ristretto_eq(const ge_ext *p, const ge_ext *q) {
 }
 
 /* ------------------------------------------------------------------ the 7-step flow ------------ */
+/* m as a u64 under "m", then every value commitment's encoding under "V" (oracle/acproof.py append_commitments;
+ * bulletproofs 4.0.0 r1cs prover: append_point(b"V", ..) per commit(), append_u64(b"m", m)).  V_enc (m x 32 compressed
+ * encodings, what a verifier is handed) is used when given, else the points are compressed here. */
+#define V_CHUNK 64
+static void tr_append_commitments(strobe *tr, const ge_ext *V, const u8 *V_enc, size_t m) {
+    u8 mb[8], enc[32], dig[32];
+    for (int i = 0; i < 8; i++) mb[i] = (u8)((u64)m >> (8 * i));
+    tr_append(tr, "m", mb, 8);
+    for (size_t c = 0; c < m; c += V_CHUNK) {   /* one sponge per chunk of 64 commitments, its digest under "Vd" */
+        strobe ch; tr_new(&ch, (const u8 *)"acp-V", 5);
+        for (int i = 0; i < 8; i++) mb[i] = (u8)((u64)(c / V_CHUNK) >> (8 * i));
+        tr_append(&ch, "chunk", mb, 8);
+        for (size_t j = c; j < m && j < c + V_CHUNK; j++) {
+            if (V_enc) tr_append(&ch, "V", V_enc + 32 * j, 32);
+            else { ristretto_compress(enc, &V[j]); tr_append(&ch, "V", enc, 32); }
+        }
+        tr_challenge_bytes(&ch, "d", dig, 32);
+        tr_append(tr, "Vd", dig, 32);
+    }
+}
+
 /* lib.rs:219-231 / circuit_lib.rs:133-585.  W_* dense, row-major: W_L,W_R,W_O n x Q, W_V m x Q.
  * mode 0 = reference (defects included), 1 = reference-fixed.  Writes the proof bytes
  * (A_I,A_O,S,T1,T3,T4,T5,T6,tau_x,mu,t,l,r) and returns 1 for Ok(()), 0 for Err(VerificationError),
  * -5 for an undecodable T (the reference panics). */
 int orc_acp_prove_verify(int mode, size_t n, size_t Q, size_t m, const u8 *WLb, const u8 *WRb, const u8 *WOb,
                          const u8 *WVb, const u8 *cb, const u8 *g_pt, const u8 *h_pt, const u8 *G_pts, const u8 *H_pts,
-                         const u8 *aLb, const u8 *aRb, const u8 *aOb, const u8 *gammab, const u8 *V_pts, const u8 *seed32,
-                         const u8 *label, size_t label_len, u8 *proof_out, int do_verify) {
+                         const u8 *aLb, const u8 *aRb, const u8 *aOb, const u8 *gammab, const u8 *V_pts, const u8 *V_enc,
+                         const u8 *seed32, const u8 *label, size_t label_len, u8 *proof_out, int do_verify) {
     orc_init();
     const sc *W_L = (const sc *)WLb, *W_R = (const sc *)WRb, *W_O = (const sc *)WOb, *W_V = (const sc *)WVb;
     const sc *cv = (const sc *)cb, *a_L = (const sc *)aLb, *a_R = (const sc *)aRb, *a_O = (const sc *)aOb;
@@ -333,6 +360,7 @@ int orc_acp_prove_verify(int mode, size_t n, size_t Q, size_t m, const u8 *WLb, 
     sc *sv = malloc(big * sizeof(sc)); ge_ext *pv = malloc(big * sizeof(ge_ext));
     /* ---- create :139-253 ---- */
     { u8 nb[8]; for (int i = 0; i < 8; i++) nb[i] = (u8)((u64)n >> (8 * i)); tr_append(&tr, "dom-sep", (const u8 *)"acp v1", 6); tr_append(&tr, "n", nb, 8); }
+    if (mode != 0) tr_append_commitments(&tr, V, V_enc, m);   /* the reference never binds V (defect 12) */
     sc alpha, beta, ro; rng_scalar(&rng, &alpha); rng_scalar(&rng, &beta); rng_scalar(&rng, &ro);
     ge_ext A_I, A_O, S;
     sv[0] = alpha; pv[0] = *h; memcpy(sv + 1, a_L, n * 32); memcpy(pv + 1, G, n * sizeof(ge_ext));
@@ -518,8 +546,8 @@ size_t orc_acp_fixed_proof_len(size_t n) {
 int orc_acp_fixed_prove_verify(size_t n, size_t Q, size_t m, const u32 nnz[4], const u32 *wire, const u32 *cons,
                                const u8 *coeffb, const u8 *cb, const u8 *g_pt, const u8 *h_pt, const u8 *G_pts,
                                const u8 *H_pts, const u8 *aLb, const u8 *aRb, const u8 *aOb, const u8 *gammab,
-                               const u8 *V_pts, const u8 *seed32, const u8 *label, size_t label_len, u8 *proof,
-                               int do_prove, int do_verify) {
+                               const u8 *V_pts, const u8 *V_enc, const u8 *seed32, const u8 *label, size_t label_len,
+                               u8 *proof, int do_prove, int do_verify) {
     orc_init();
     const size_t np = next_pow2_sz(n);
     size_t lg = 0; while (((size_t)1 << lg) < np) lg++;
@@ -543,6 +571,7 @@ int orc_acp_fixed_prove_verify(size_t n, size_t Q, size_t m, const u32 nnz[4], c
         rng_t rng; memcpy(rng.key, seed32, 32); rng.ctr = 0;
         strobe tr; tr_new(&tr, label, label_len);
         { u8 nb[8]; for (int i = 0; i < 8; i++) nb[i] = (u8)((u64)n >> (8 * i)); tr_append(&tr, "dom-sep", (const u8 *)"acp v1", 6); tr_append(&tr, "n", nb, 8); }
+        tr_append_commitments(&tr, V, V_enc, m);
         sc alpha, beta, ro; rng_scalar(&rng, &alpha); rng_scalar(&rng, &beta); rng_scalar(&rng, &ro);
         ge_ext A_I, A_O, S;
         sv[0] = alpha; pv[0] = *h; memcpy(sv + 1, a_L, n * 32); memcpy(pv + 1, G, n * sizeof(ge_ext));
@@ -659,6 +688,7 @@ int orc_acp_fixed_prove_verify(size_t n, size_t Q, size_t m, const u32 nnz[4], c
         sc_from_bytes_mod_order(&pa, po + 352 + 64 * lg); sc_from_bytes_mod_order(&pb, po + 384 + 64 * lg);
         strobe tr; tr_new(&tr, label, label_len);
         { u8 nb[8]; for (int i = 0; i < 8; i++) nb[i] = (u8)((u64)n >> (8 * i)); tr_append(&tr, "dom-sep", (const u8 *)"acp v1", 6); tr_append(&tr, "n", nb, 8); }
+        tr_append_commitments(&tr, V, V_enc, m);
         tr_append(&tr, "A_I", po, 32); tr_append(&tr, "A_O", po + 32, 32); tr_append(&tr, "S", po + 64, 32);
         sc y, z, x, w, y_inv; tr_challenge_scalar(&tr, "y", &y); tr_challenge_scalar(&tr, "z", &z);
         for (int k = 0; k < 5; k++) tr_append(&tr, TL[k], po + 96 + 32 * k, 32);

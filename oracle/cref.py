@@ -45,12 +45,12 @@ def lib():
         l.orc_scalar_mul.restype = None
         l.orc_msm_vartime_mt.argtypes = [c.c_char_p, c.c_char_p, c.c_size_t, c.c_int, c.c_char_p]
         l.orc_msm_vartime_mt.restype = None
-        l.orc_acp_prove_verify.argtypes = [c.c_int, c.c_size_t, c.c_size_t, c.c_size_t] + [c.c_char_p] * 16 + [
+        l.orc_acp_prove_verify.argtypes = [c.c_int, c.c_size_t, c.c_size_t, c.c_size_t] + [c.c_char_p] * 17 + [
             c.c_size_t, c.c_char_p, c.c_int]
         l.orc_acp_fixed_proof_len.argtypes = [c.c_size_t]
         l.orc_acp_fixed_proof_len.restype = c.c_size_t
         l.orc_acp_fixed_prove_verify.argtypes = [c.c_size_t, c.c_size_t, c.c_size_t, c.c_char_p, c.c_char_p, c.c_char_p] + [
-            c.c_char_p] * 12 + [c.c_char_p, c.c_size_t, c.c_char_p, c.c_int, c.c_int]
+            c.c_char_p] * 13 + [c.c_char_p, c.c_size_t, c.c_char_p, c.c_int, c.c_int]
         l.orc_commit_variables.argtypes = [c.c_char_p] * 4 + [c.c_size_t, c.c_char_p]
         l.orc_commit_variables.restype = None
         l.orc_scalar_ops_selftest.argtypes = [c.c_char_p] * 4
@@ -123,12 +123,13 @@ class AcpInstance:
         lib().orc_commit_variables(self.g, self.h, v, gamma, self.m, out)
         return out.raw
 
-    def prove_verify(self, aL, aR, aO, gamma, V_pts, seed, mode=1, label=b"test", do_verify=True):
-        """-> (proof_bytes, result) with result 1 = Ok(()), 0 = Err(VerificationError)."""
+    def prove_verify(self, aL, aR, aO, gamma, V_pts, seed, mode=1, label=b"test", do_verify=True, V_enc=None):
+        """-> (proof_bytes, result) with result 1 = Ok(()), 0 = Err(VerificationError).  V_pts: the commitments as
+        points (orc layout); V_enc: their 32-byte encodings when the caller has them (else compressed inside)."""
         out = ctypes.create_string_buffer(32 * (11 + 2 * self.n))
         rc = lib().orc_acp_prove_verify(mode, self.n, self.Q, self.m, self.W[0], self.W[1], self.W[2], self.W[3], self.c,
-                                        self.g, self.h, self.G, self.H, aL, aR, aO, gamma, V_pts, seed, label, len(label),
-                                        out, 1 if do_verify else 0)
+                                        self.g, self.h, self.G, self.H, aL, aR, aO, gamma, V_pts, V_enc, seed, label,
+                                        len(label), out, 1 if do_verify else 0)
         return out.raw, rc
 
 
@@ -163,16 +164,17 @@ class AcpFixedInstance:
         lib().orc_commit_variables(self.g, self.h, v, gamma, self.m, out)
         return out.raw
 
-    def _call(self, aL, aR, aO, gamma, V_pts, seed, label, buf, do_prove, do_verify):
+    def _call(self, aL, aR, aO, gamma, V_pts, V_enc, seed, label, buf, do_prove, do_verify):
         return lib().orc_acp_fixed_prove_verify(self.n, self.Q, self.m, self.nnz, self.wire, self.cons, self.coeff, self.c,
-                                                self.g, self.h, self.G, self.H, aL, aR, aO, gamma, V_pts, seed, label,
+                                                self.g, self.h, self.G, self.H, aL, aR, aO, gamma, V_pts, V_enc, seed, label,
                                                 len(label), buf, do_prove, do_verify)
 
-    def prove(self, aL, aR, aO, gamma, seed, label=b"test") -> bytes:
+    def prove(self, aL, aR, aO, gamma, V_pts, seed, label=b"test", V_enc=None) -> bytes:
+        """V_pts: the value commitments as points (bound to the transcript); V_enc: their encodings, if at hand."""
         buf = ctypes.create_string_buffer(self.proof_len)
-        self._call(aL, aR, aO, gamma, None, seed, label, buf, 1, 0)
+        self._call(aL, aR, aO, gamma, V_pts, V_enc, seed, label, buf, 1, 0)
         return buf.raw
 
-    def verify(self, proof: bytes, V_pts: bytes, label=b"test") -> bool:
+    def verify(self, proof: bytes, V_pts: bytes, label=b"test", V_enc=None) -> bool:
         buf = ctypes.create_string_buffer(proof, len(proof))
-        return self._call(None, None, None, None, V_pts, None, label, buf, 0, 1) == 1
+        return self._call(None, None, None, None, V_pts, V_enc, None, label, buf, 0, 1) == 1

@@ -22,7 +22,7 @@ from __future__ import annotations
 
 from . import ristretto255 as R
 from .merlin import Transcript
-from .acproof import (VecPoly3, commit_variables, hadamard_V, inner_product, mv_mult, scalar_exp,  # noqa: F401
+from .acproof import (VecPoly3, append_commitments, commit_variables, hadamard_V, inner_product, mv_mult, scalar_exp,  # noqa: F401
                       vm_mult)
 
 L = R.L
@@ -132,8 +132,9 @@ def proof_len(n: int) -> int:
     return 32 * (13 + 2 * lg)
 
 
-def prove(core, prover, rng, label=b"test", msm=None):
-    """`fixed`-mode prover.  core["G_vec"], core["H_vec"] must hold at least next_pow2(n) generators.
+def prove(core, prover, V, rng, label=b"test", msm=None):
+    """`fixed`-mode prover.  core["G_vec"], core["H_vec"] must hold at least next_pow2(n) generators; V = the value
+    commitments (bound to the transcript right after the domain separator, oracle.acproof.append_commitments).
     Returns (proof_bytes, state) - state carries the intermediate values tests look at."""
     msm = msm or R.vartime_multiscalar_mul
     n, Q, m = core["n"], core["Q"], core["m"]
@@ -144,6 +145,7 @@ def prove(core, prover, rng, label=b"test", msm=None):
     a_L, a_R, a_O, gamma = prover["a_L"], prover["a_R"], prover["a_O"], prover["gamma"]
     trans = Transcript(label)
     trans.arithmetic_domain_sep(n)
+    append_commitments(trans, V, m)
     alpha, beta, ro = rng.scalar(), rng.scalar(), rng.scalar()
     A_I = msm([alpha] + a_L + a_R, [h] + G[:n] + H[:n])
     A_O = msm([beta] + a_O, [h] + G[:n])
@@ -219,6 +221,9 @@ def verify(core, V, proof: bytes, label=b"test", msm=None) -> bool:
                             R.sc_from_bytes_mod_order(w32[11 + 2 * lg]), R.sc_from_bytes_mod_order(w32[12 + 2 * lg]))
     trans = Transcript(label)
     trans.arithmetic_domain_sep(n)
+    if len(V) != m:
+        return False
+    append_commitments(trans, V, m)
     for lab, b in zip((b"A_I", b"A_O", b"S"), w32[:3]):
         trans.append_point(lab, b)
     y = trans.challenge_scalar(b"y")

@@ -72,6 +72,7 @@ def test_null_arguments_are_rejected_without_a_device():
     assert lib.bpp_transcript_script(None, b"x", 1, None, 0) == -3
     assert lib.bpp_acp_batch_prove(None) == -3
     assert lib.bpp_acp_batch_verify(None, bytes(32)) == -3
+    assert lib.bpp_acp_batch_verify(None, None) == -3
     assert lib.bpp_msm_vartime(None, b"", 0, None, 0, 0, None, None) == -3
     assert lib.bpp_strerror(-3).decode() == "invalid argument"
     assert lib.bpp_acproof_proof_len_mode(104, 2) == 32 * (13 + 2 * 7)

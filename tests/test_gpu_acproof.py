@@ -37,10 +37,10 @@ def test_small_decks_proof_bytes_and_decisions(backend, k, mode):
     seeds = [bytes([i + 1]) * 32 for i in range(3)]
     B = len(seeds)
     n, m = core["n"], core["m"]
-    proofs = G.prove_batch(backend, cir, gens, _sb(prover["a_L"]) * B, _sb(prover["a_R"]) * B, _sb(prover["a_O"]) * B,
-                           _sb(prover["gamma"]) * B, b"".join(seeds), B, mode)
-    plen = G.proof_len(n)
     Vc = b"".join(R.compress(p) for p in V)
+    proofs = G.prove_batch(backend, cir, gens, _sb(prover["a_L"]) * B, _sb(prover["a_R"]) * B, _sb(prover["a_O"]) * B,
+                           _sb(prover["gamma"]) * B, b"".join(seeds), B, mode, V=Vc * B)
+    plen = G.proof_len(n)
     want_ok = []
     for i, sd in enumerate(seeds):
         pb, ok, _, _ = _oracle(core, prover, V, sd, mode)
@@ -65,14 +65,14 @@ def test_52_card_shuffle_proof_is_byte_identical(backend):
 
     seeds = [b"\x77" * 32, b"\x78" * 32]
     B = len(seeds)
+    Vc = b"".join(R.compress(p) for p in V)
     proofs = G.prove_batch(backend, cir, gens, _sb(prover["a_L"]) * B, _sb(prover["a_R"]) * B, _sb(prover["a_O"]) * B,
-                           _sb(prover["gamma"]) * B, b"".join(seeds), B, "reference-fixed")
+                           _sb(prover["gamma"]) * B, b"".join(seeds), B, "reference-fixed", V=Vc * B)
     plen = G.proof_len(104)
     for i, sd in enumerate(seeds):
         pb, ok, _, _ = _oracle(core, prover, V, sd, "reference-fixed", fast_msm)
         assert ok
         assert proofs[i * plen:(i + 1) * plen] == pb
-    Vc = b"".join(R.compress(p) for p in V)
     assert list(G.verify_batch(backend, cir, gens, proofs, Vc * B, B)) == [1, 1]
 
 
@@ -82,10 +82,10 @@ def test_tampered_proofs_and_commitments_are_rejected(backend):
     n, m = core["n"], core["m"]
     B = 12
     seeds = b"".join(bytes([100 + i]) * 32 for i in range(B))
-    proofs = bytearray(G.prove_batch(backend, cir, gens, _sb(prover["a_L"]) * B, _sb(prover["a_R"]) * B,
-                                     _sb(prover["a_O"]) * B, _sb(prover["gamma"]) * B, seeds, B))
-    plen = G.proof_len(n)
     Vc = bytearray(b"".join(R.compress(p) for p in V) * B)
+    proofs = bytearray(G.prove_batch(backend, cir, gens, _sb(prover["a_L"]) * B, _sb(prover["a_R"]) * B,
+                                     _sb(prover["a_O"]) * B, _sb(prover["gamma"]) * B, seeds, B, V=bytes(Vc)))
+    plen = G.proof_len(n)
     good = bytes(proofs)
     assert list(G.verify_batch(backend, cir, gens, good, bytes(Vc), B)) == [1] * B
     # one corruption per proof, each in a different field
@@ -105,7 +105,7 @@ def test_tampered_proofs_and_commitments_are_rejected(backend):
     bad_aO = list(prover["a_O"])
     bad_aO[0] = (bad_aO[0] + 1) % L
     p2 = G.prove_batch(backend, cir, gens, _sb(prover["a_L"]), _sb(prover["a_R"]), _sb(bad_aO), _sb(prover["gamma"]),
-                       seeds[:32], 1)
+                       seeds[:32], 1, V=bytes(Vc[:32 * m]))
     _, ok, _, _ = _oracle(core, dict(prover, a_O=bad_aO), V, seeds[:32], "reference-fixed")
     assert not ok and list(G.verify_batch(backend, cir, gens, p2, bytes(Vc[:32 * m]), 1)) == [0]
 
@@ -132,6 +132,59 @@ def test_commit_variables_and_staged_batch(backend):
         g2 = G.Generators(backend, R.compress(core["g_base"]), R.compress(core["h_base"]),
                           [R.compress(p) for p in core["G_vec"]], [R.compress(p) for p in core["H_vec"]], c)
         p2 = G.prove_batch(backend, cir, g2, _sb(prover["a_L"]), _sb(prover["a_R"]), _sb(prover["a_O"]), _sb(prover["gamma"]),
-                           bytes([69]) * 32, 1)
+                           bytes([69]) * 32, 1, V=want)
         assert p2 == pb
         g2.free()
+
+
+@pytest.mark.parametrize("k", [2, 5, 52, 300])
+def test_device_shuffle_witness_and_library_circuit_equal_the_oracle(backend, k):
+    """SURVEY 8 row f-1 behind the C ABI: bpp_circuit_create_shuffle + bpp_acp_batch_gen_shuffle_witness against
+    oracle/acproof.py shuffle_circuit / shuffle_witness - same commitments and byte-identical proofs as the uploaded
+    witness over the Python-built circuit."""
+    import numpy as np
+    from bpperm_b200 import acproof as G
+    from oracle import cref
+    n, Q, m, WL, WR, WO, WV, c = A.shuffle_circuit(k)
+    rs = np.random.RandomState(900 + k)
+    enc = cref.compress(cref.from_uniform(rs.randint(0, 256, size=(2 * n + 2, 64), dtype=np.uint8).tobytes()))
+    pts = [enc[32 * i:32 * i + 32] for i in range(2 * n + 2)]
+    cir_py = G.Circuit(backend, n, Q, m, WL, WR, WO, WV, c)
+    cir_lib = G.Circuit.shuffle(backend, k)
+    assert (cir_lib.n, cir_lib.Q, cir_lib.m) == (n, Q, m)
+    gens = G.Generators(backend, pts[0], pts[1], pts[2:2 + n], pts[2 + n:], 6)
+    B = 3
+    deck = [(7 * i + 3) % L for i in range(1, k + 1)]
+    perms, xs, wit = [], [], []
+    for p in range(B):
+        perm = rs.permutation(k)
+        x = int.from_bytes(rs.bytes(32), "little") % L
+        v = deck + [deck[j] for j in perm] + [x]
+        aL, aR, aO = [0] * n, [0] * n, [0] * n
+        for gb, vb in ((0, 0), (k - 1, k)):               # oracle.acproof.shuffle_witness, with this deck and permutation
+            for i in range(k - 1):
+                aL[gb + i] = (v[vb] - x) % L if i == 0 else aO[gb + i - 1]
+                aR[gb + i] = (v[vb + i + 1] - x) % L
+                aO[gb + i] = aL[gb + i] * aR[gb + i] % L
+        perms.append(perm.astype(np.uint32).tobytes()); xs.append(x); wit.append((v, aL, aR, aO))
+    gamma = [[int.from_bytes(rs.bytes(32), "little") % L for _ in range(m)] for _ in range(B)]
+    seeds = b"".join(bytes([p + 1]) * 32 for p in range(B))
+    gam_b = b"".join(_sb(g) for g in gamma)
+    # uploaded witness, Python-built circuit
+    b1 = G.Batch(backend, cir_py, gens, B)
+    b1.upload_witness(b"".join(_sb(w[1]) for w in wit), b"".join(_sb(w[2]) for w in wit), b"".join(_sb(w[3]) for w in wit), gam_b, seeds)
+    V1 = b1.commit(b"".join(_sb(w[0]) for w in wit))
+    b1.prove()
+    p1 = b1.download_proofs()
+    # generated witness, library-built circuit
+    b2 = G.Batch(backend, cir_lib, gens, B)
+    b2.gen_shuffle_witness(_sb(deck), b"".join(perms), _sb(xs), gam_b, seeds)
+    V2 = b2.commit(None)
+    b2.prove()
+    p2 = b2.download_proofs()
+    assert V1 == V2 and p1 == p2
+    b2.upload_proofs(p2, V2)
+    b2.verify()
+    assert b2.download_accept() == b"\x01" * B
+    for o in (b1, b2, gens, cir_py, cir_lib):
+        o.free()

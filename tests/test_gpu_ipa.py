@@ -32,13 +32,13 @@ def test_small_decks_fixed_mode_bytes_and_decisions(backend, k):
     seeds = [bytes([i + 1]) * 32 for i in range(3)]
     B = len(seeds)
     n = core["n"]
+    Vc = b"".join(R.compress(p) for p in V)
     proofs = G.prove_batch(backend, cir, gens, _sb(prover["a_L"]) * B, _sb(prover["a_R"]) * B, _sb(prover["a_O"]) * B,
-                           _sb(prover["gamma"]) * B, b"".join(seeds), B, "fixed")
+                           _sb(prover["gamma"]) * B, b"".join(seeds), B, "fixed", V=Vc * B)
     plen = G.proof_len(n, "fixed")
     assert plen == ipa.proof_len(n) and len(proofs) == B * plen
-    Vc = b"".join(R.compress(p) for p in V)
     for i, sd in enumerate(seeds):
-        pb, _ = ipa.prove(core, prover, ChaChaRng(sd))
+        pb, _ = ipa.prove(core, prover, V, ChaChaRng(sd))
         assert proofs[i * plen:(i + 1) * plen] == pb, (k, i)
         assert ipa.verify(core, V, pb)
     assert list(G.verify_batch(backend, cir, gens, proofs, Vc * B, B, "fixed")) == [1] * B
@@ -50,16 +50,16 @@ def test_52_card_fixed_mode_proof_is_byte_identical_to_the_c_restatement(backend
     core, prover, V, cir, gens, inst = _setup(backend, 52, 53)
     seeds = [b"\x77" * 32, b"\x78" * 32, b"\x79" * 32]
     B = len(seeds)
+    Vp = inst.commit(_sb(prover["v"]), _sb(prover["gamma"]))
+    Vc = cref.compress(Vp)
     proofs = G.prove_batch(backend, cir, gens, _sb(prover["a_L"]) * B, _sb(prover["a_R"]) * B, _sb(prover["a_O"]) * B,
-                           _sb(prover["gamma"]) * B, b"".join(seeds), B, "fixed")
+                           _sb(prover["gamma"]) * B, b"".join(seeds), B, "fixed", V=Vc * B)
     plen = G.proof_len(104, "fixed")
     assert plen == 864
-    Vp = inst.commit(_sb(prover["v"]), _sb(prover["gamma"]))
     for i, sd in enumerate(seeds):
-        want = inst.prove(_sb(prover["a_L"]), _sb(prover["a_R"]), _sb(prover["a_O"]), _sb(prover["gamma"]), sd)
+        want = inst.prove(_sb(prover["a_L"]), _sb(prover["a_R"]), _sb(prover["a_O"]), _sb(prover["gamma"]), Vp, sd)
         assert proofs[i * plen:(i + 1) * plen] == want
         assert inst.verify(want, Vp)
-    Vc = cref.compress(Vp)
     assert list(G.verify_batch(backend, cir, gens, proofs, Vc * B, B, "fixed")) == [1] * B
 
 
@@ -71,10 +71,10 @@ def test_fixed_mode_tampering_matches_the_oracle_decision_per_proof(backend):
     words = plen // 32
     B = words + 3
     seeds = b"".join(bytes([50 + i]) * 32 for i in range(B))
-    proofs = bytearray(G.prove_batch(backend, cir, gens, _sb(prover["a_L"]) * B, _sb(prover["a_R"]) * B, _sb(prover["a_O"]) * B,
-                                     _sb(prover["gamma"]) * B, seeds, B, "fixed"))
     Vp = inst.commit(_sb(prover["v"]), _sb(prover["gamma"]))
     Vc = bytearray(cref.compress(Vp) * B)
+    proofs = bytearray(G.prove_batch(backend, cir, gens, _sb(prover["a_L"]) * B, _sb(prover["a_R"]) * B, _sb(prover["a_O"]) * B,
+                                     _sb(prover["gamma"]) * B, seeds, B, "fixed", V=bytes(Vc)))
     assert list(G.verify_batch(backend, cir, gens, bytes(proofs), bytes(Vc), B, "fixed")) == [1] * B
     for f in range(words):                   # proof f: one bit flipped in field f
         proofs[f * plen + 32 * f + 5] ^= 0x04
@@ -84,8 +84,8 @@ def test_fixed_mode_tampering_matches_the_oracle_decision_per_proof(backend):
     acc = list(G.verify_batch(backend, cir, gens, bytes(proofs), bytes(Vc), B, "fixed"))
     want = []
     for i in range(B):
-        Vi = cref.decompress(bytes(Vc[i * 32 * m:(i + 1) * 32 * m]))
-        want.append(1 if inst.verify(bytes(proofs[i * plen:(i + 1) * plen]), Vi) else 0)
+        Ve = bytes(Vc[i * 32 * m:(i + 1) * 32 * m])
+        want.append(1 if inst.verify(bytes(proofs[i * plen:(i + 1) * plen]), cref.decompress(Ve), V_enc=Ve) else 0)
     assert acc == want
     assert sum(acc) <= 1     # a flipped high bit of a scalar field may stay the same value mod l; everything else rejects
 
@@ -97,11 +97,11 @@ def test_larger_deck_single_proof_uses_split_msm_and_matches_c(backend, k, windo
     from bpperm_b200 import acproof as G
     core, prover, V, cir, gens, inst = _setup(backend, k, 77, window_bits)
     sd = b"\x42" * 32
-    proof = G.prove_batch(backend, cir, gens, _sb(prover["a_L"]), _sb(prover["a_R"]), _sb(prover["a_O"]), _sb(prover["gamma"]),
-                          sd, 1, "fixed")
-    want = inst.prove(_sb(prover["a_L"]), _sb(prover["a_R"]), _sb(prover["a_O"]), _sb(prover["gamma"]), sd)
-    assert proof == want
     Vp = inst.commit(_sb(prover["v"]), _sb(prover["gamma"]))
+    proof = G.prove_batch(backend, cir, gens, _sb(prover["a_L"]), _sb(prover["a_R"]), _sb(prover["a_O"]), _sb(prover["gamma"]),
+                          sd, 1, "fixed", V=cref.compress(Vp))
+    want = inst.prove(_sb(prover["a_L"]), _sb(prover["a_R"]), _sb(prover["a_O"]), _sb(prover["gamma"]), Vp, sd)
+    assert proof == want
     assert inst.verify(want, Vp)
     assert list(G.verify_batch(backend, cir, gens, proof, cref.compress(Vp), 1, "fixed")) == [1]
     # the same circuit in the other modes still needs exactly n generators
@@ -137,13 +137,13 @@ def test_large_deck_4096_cards_single_proof_is_byte_identical(backend):
     cir = G.Circuit(backend, n, Q, m, WL, WR, WO, WV, c)
     gens = G.Generators(backend, g, h, [Gb[32 * i:32 * i + 32] for i in range(npad)], [Hb[32 * i:32 * i + 32] for i in range(npad)], 8)
     sd = b"\x42" * 32
-    proof = G.prove_batch(backend, cir, gens, _sb(aL), _sb(aR), _sb(aO), _sb(gamma), sd, 1, "fixed")
-    assert len(proof) == 32 * (13 + 2 * 13)
-    want = inst.prove(_sb(aL), _sb(aR), _sb(aO), _sb(gamma), sd)
-    assert proof == want
     Vp = inst.commit(_sb(v), _sb(gamma))
-    assert inst.verify(want, Vp)
     Vc = cref.compress(Vp)
+    proof = G.prove_batch(backend, cir, gens, _sb(aL), _sb(aR), _sb(aO), _sb(gamma), sd, 1, "fixed", V=Vc)
+    assert len(proof) == 32 * (13 + 2 * 13)
+    want = inst.prove(_sb(aL), _sb(aR), _sb(aO), _sb(gamma), Vp, sd, V_enc=Vc)
+    assert proof == want
+    assert inst.verify(want, Vp, V_enc=Vc)
     assert list(G.verify_batch(backend, cir, gens, proof, Vc, 1, "fixed")) == [1]
     bad = bytearray(proof)
     bad[32 * 20 + 3] ^= 2      # one of the L_j
@@ -164,10 +164,11 @@ def test_batch_verification_with_one_percent_corrupted_proofs_matches_the_oracle
     seeds = b"".join((1000 + i).to_bytes(4, "little") * 8 for i in range(B))
     batch = G.Batch(backend, cir, gens, B, "fixed", b"test")
     batch.upload_witness(_sb(prover["a_L"]) * B, _sb(prover["a_R"]) * B, _sb(prover["a_O"]) * B, _sb(prover["gamma"]) * B, seeds)
-    batch.prove()
-    good = batch.download_proofs()
     Vp = inst.commit(_sb(prover["v"]), _sb(prover["gamma"]))
     Vc1 = cref.compress(Vp)
+    batch.upload_commitments(Vc1 * B)
+    batch.prove()
+    good = batch.download_proofs()
     # all valid: the combined check decides
     batch.upload_proofs(good, Vc1 * B)
     batch.verify(b"\x21" * 32)
@@ -184,8 +185,8 @@ def test_batch_verification_with_one_percent_corrupted_proofs_matches_the_oracle
     want = []
     for i in range(B):
         if i in victims or i == 222 or i % 64 == 0:      # every corrupted proof + a sample of the valid ones
-            Vi = cref.decompress(bytes(Vc[i * 32 * m:(i + 1) * 32 * m]))
-            want.append(1 if inst.verify(bytes(proofs[i * plen:(i + 1) * plen]), Vi) else 0)
+            Ve = bytes(Vc[i * 32 * m:(i + 1) * 32 * m])
+            want.append(1 if inst.verify(bytes(proofs[i * plen:(i + 1) * plen]), cref.decompress(Ve), V_enc=Ve) else 0)
         else:
             want.append(1)
     assert sum(want) == B - 7
@@ -208,8 +209,9 @@ def test_wire_records_parse_then_verify(backend):
     n = core["n"]
     seeds = [bytes([40 + i]) * 32 for i in range(5)]
     B = len(seeds)
+    Vc = b"".join(R.compress(p) for p in V)
     proofs = G.prove_batch(backend, cir, gens, _sb(prover["a_L"]) * B, _sb(prover["a_R"]) * B, _sb(prover["a_O"]) * B,
-                           _sb(prover["gamma"]) * B, b"".join(seeds), B, "fixed")
+                           _sb(prover["gamma"]) * B, b"".join(seeds), B, "fixed", V=Vc * B)
     plen, wlen = G.proof_len(n, "fixed"), G.wire_len(n, "fixed")
     recs = bytearray(G.to_wire(proofs, n, B, "fixed"))
     assert len(recs) == B * wlen and wlen == plen + 1
@@ -218,7 +220,6 @@ def test_wire_records_parse_then_verify(backend):
     recs[3 * wlen] = 0x01                                                                 # proof 3: unknown version
     back, status = G.from_wire(bytes(recs), n, B, "fixed")
     assert list(status) == [0, 1, 0, 1, 0]
-    Vc = b"".join(R.compress(p) for p in V)
     acc = list(G.verify_batch(backend, cir, gens, back, Vc * B, B, "fixed"))
     assert acc == [1, 0, 0, 0, 1]
     for i in range(B):

@@ -428,3 +428,50 @@ def test_tile_lengths_match_oracle(backend, tile, c, groups):
         backend.set_window_bits(0)
         table.free()
     assert got == cref.msm(sc.tobytes(), cref.from_uniform(blobs.tobytes()))
+
+
+# ---- small and batched MSMs over a precomputed point set (the reference's call-site sizes) -----------
+@pytest.mark.parametrize("n", [2, 105, 209])
+@pytest.mark.parametrize("window_bits", [0, 5, 11])
+def test_precomputed_points_single_msm_matches_the_bucket_path_and_the_oracle(backend, n, window_bits):
+    import numpy as np
+    from oracle import cref
+    rs = np.random.RandomState(1000 + n + window_bits)
+    blobs = rs.randint(0, 256, size=(n + 3, 64), dtype=np.uint8).tobytes()
+    pts_c = cref.from_uniform(blobs)
+    sc = rs.randint(0, 256, size=(n, 32), dtype=np.uint8)
+    sc[:, 31] &= 0x1F                    # up to 2^253: non-canonical values allowed below 2^255
+    sc[0] = 0
+    scb = sc.tobytes()
+    table = backend.points_from_uniform(blobs)
+    want = cref.msm(scb, pts_c[160 * 3:160 * (3 + n)])          # a sub-range of the set: points 3 .. 3 + n
+    plain = backend.vartime_multiscalar_mul(scb, table, 3, n)
+    backend.precompute(table, window_bits)
+    l0 = backend.launch_count
+    fast = backend.vartime_multiscalar_mul(scb, table, 3, n)
+    assert backend.launch_count - l0 <= 3                     # table look-ups + sum + compress: no bucket pipeline
+    assert plain == want and fast == want
+    table.free()
+
+
+@pytest.mark.parametrize("n,count", [(2, 1), (2, 5000), (105, 7), (209, 300), (209, 2500), (33, 1)])
+def test_batched_msm_over_shared_points_matches_the_c_restatement(backend, n, count):
+    import numpy as np
+    from oracle import cref
+    rs = np.random.RandomState(7 * n + count)
+    blobs = rs.randint(0, 256, size=(n, 64), dtype=np.uint8).tobytes()
+    pts_c = cref.from_uniform(blobs)
+    sc = rs.randint(0, 256, size=(count * n, 32), dtype=np.uint8)
+    sc[:, 31] &= 0x0F
+    sc[n - 1] = 0
+    sc[0, :] = np.frombuffer((R.L - 1).to_bytes(32, "little"), dtype=np.uint8)
+    table = backend.points_from_uniform(blobs)
+    out = backend.msm_batch(sc.tobytes(), table, n, count)
+    assert len(out) == 32 * count
+    for i in sorted(set([0, 1 % count, count // 2, count - 1])):
+        assert out[32 * i:32 * i + 32] == cref.msm(sc[i * n:(i + 1) * n].tobytes(), pts_c), i
+    with pytest.raises(Exception):
+        bad = bytearray(sc[:n].tobytes())
+        bad[31] |= 0x80                                        # bit 255 set: BPP_ERR_SCALAR_RANGE like the single call
+        backend.msm_batch(bytes(bad), table, n, 1)
+    table.free()

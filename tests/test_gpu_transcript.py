@@ -76,6 +76,7 @@ def test_device_and_host_transcripts_agree(backend, mode):
         batch = G.Batch(backend, cir, gens, B, mode, b"test")
         batch.set_host_transcripts(host)
         batch.upload_witness(sb(prover["a_L"]) * B, sb(prover["a_R"]) * B, sb(prover["a_O"]) * B, sb(prover["gamma"]) * B, seeds)
+        batch.upload_commitments(Vc)
         batch.prove()
         proofs = batch.download_proofs()
         bad = bytearray(proofs)
@@ -113,6 +114,7 @@ def test_batch_rlc_verification_matches_per_proof_decisions(backend, mode):
     Vc = b"".join(R.compress(p) for p in V) * B
     batch = G.Batch(backend, cir, gens, B, mode, b"test")
     batch.upload_witness(sb(prover["a_L"]) * B, sb(prover["a_R"]) * B, sb(prover["a_O"]) * B, sb(prover["gamma"]) * B, seeds)
+    batch.upload_commitments(Vc)
     batch.prove()
     proofs = batch.download_proofs()
     plen = batch.proof_len

@@ -53,9 +53,9 @@ def test_fixed_mode_python_equals_c_and_is_complete_and_sound(k):
     Vp = inst.commit(_sb(prover["v"]), _sb(prover["gamma"]))
     assert cref.compress(Vp) == b"".join(R.compress(p) for p in V)
     seed = bytes([k + 1]) * 32
-    proof, st = ipa.prove(core, prover, ChaChaRng(seed))
+    proof, st = ipa.prove(core, prover, V, ChaChaRng(seed))
     assert len(proof) == ipa.proof_len(core["n"]) == inst.proof_len
-    assert inst.prove(_sb(prover["a_L"]), _sb(prover["a_R"]), _sb(prover["a_O"]), _sb(prover["gamma"]), seed) == proof
+    assert inst.prove(_sb(prover["a_L"]), _sb(prover["a_R"]), _sb(prover["a_O"]), _sb(prover["gamma"]), Vp, seed) == proof
     assert ipa.verify(core, V, proof) and inst.verify(proof, Vp)
     assert st["t_hat"] == ipa.inner_product(st["l"], st["r"])
     npad = ipa.next_pow2(core["n"])
@@ -89,5 +89,5 @@ def test_fixed_mode_rejects_a_non_permutation():
             a_R[gb + i] = (bad_v[vb + i + 1] - x) % L
             a_O[gb + i] = a_L[gb + i] * a_R[gb + i] % L
     V2 = A.commit_variables(bad_v, prover["gamma"], core["g_base"], core["h_base"])
-    proof, _ = ipa.prove(core, dict(prover, a_L=a_L, a_R=a_R, a_O=a_O, v=bad_v), ChaChaRng(b"\x01" * 32))
+    proof, _ = ipa.prove(core, dict(prover, a_L=a_L, a_R=a_R, a_O=a_O, v=bad_v), V2, ChaChaRng(b"\x01" * 32))
     assert not ipa.verify(core, V2, proof)
