@@ -282,16 +282,17 @@ def cpu_msm_baseline():
         import ctypes
         per = n // cores
         ctx = mp.get_context("fork")
-        t0 = time.time()
+        jobs = [(scb[32 * i * per:32 * (i + 1) * per], pts[160 * i * per:160 * (i + 1) * per]) for i in range(cores)]
         with ctx.Pool(cores) as pool:
-            parts = pool.starmap(cref.msm_raw, [(scb[32 * i * per:32 * (i + 1) * per], pts[160 * i * per:160 * (i + 1) * per])
-                                                for i in range(cores)])
-        acc = parts[0]
-        for p in parts[1:]:
-            o = ctypes.create_string_buffer(160)
-            cref.lib().orc_point_add(acc, p, o)
-            acc = o.raw
-        tall = time.time() - t0
+            pool.starmap(cref.msm_raw, [(j[0][:32 * 64], j[1][:160 * 64]) for j in jobs])   # workers forked and warm
+            t0 = time.time()                                                              # the clock starts with a warm pool
+            parts = pool.starmap(cref.msm_raw, jobs)
+            acc = parts[0]
+            for p in parts[1:]:
+                o = ctypes.create_string_buffer(160)
+                cref.lib().orc_point_add(acc, p, o)
+                acc = o.raw
+            tall = time.time() - t0
         out["all_cores"] = {"value": n / tall, "cores": cores,
                             "matches_1core": (cref.compress(acc) == r1) if per * cores == n else None}
     except Exception as e:  # pragma: no cover
@@ -864,6 +865,7 @@ def run_ours(args):
     be = bpperm_b200.Backend(local)
     stream = torch.cuda.current_stream(dev)
     be.set_stream(stream.cuda_stream)
+    bpperm_b200.parallel.init_comm(be, world, rank, dev)   # the library's own NCCL communicator (bpp_comm_init)
 
     def barrier():
         if world > 1:
@@ -1004,16 +1006,12 @@ def run_ours(args):
         if world == 1:
             got = [bytes(d_outs[(msm_steps - 2 + i) & 1][:32].cpu().numpy().tobytes()) for i in range(2)]
         else:
-            got = [bytes(smsm._slots()[(msm_steps - 2 + i) % 3][2][:32].cpu().numpy().tobytes()) for i in range(2)]
+            got = [bytes(smsm.d_outs[(msm_steps - 2 + i) % 3][:32].cpu().numpy().tobytes()) for i in range(2)]
         assert got == want, "submitted MSM results differ from the single-call results"
         clocks2 = samp2.stop() if (rank == 0 and args.workload == "msm") else None
         ms_e2e_serial = timed(msm_e2e, msm_steps, args.warmup)
         # e2e, double buffered: the next step's scalars travel on a copy stream while this step's MSM runs
         copy_stream = torch.cuda.Stream(dev)
-        bufs = [torch.empty_like(d_sets[0]) for _ in range(2)]
-        ready = [torch.cuda.Event() for _ in range(2)]
-        free = [torch.cuda.Event() for _ in range(2)]
-
         bufs3 = [torch.empty_like(d_sets[0]) for _ in range(3)]
         ready3 = [torch.cuda.Event() for _ in range(3)]
         free3 = [torch.cuda.Event() for _ in range(3)]
@@ -1045,23 +1043,32 @@ def run_ours(args):
                 be.msm_wait()
                 h_out.copy_(d_outs[(cnt - 1) & 1][:32], non_blocking=True)
                 return
-            used = [False, False]
+            # sharded: bpp_msm_sharded_submit_dev(i) leaves the caller's stream behind MSM i - 1 (its scalars may be
+            # replaced) and behind the gathered result of MSM i - 2 (it may be read); scalars of step i + 1 travel on
+            # the copy stream meanwhile
+            used = [False] * 3
             with torch.cuda.stream(copy_stream):
-                bufs[0].copy_(h_sets[first % n_sets], non_blocking=True)
-                ready[0].record(copy_stream)
+                bufs3[0].copy_(h_sets[first % n_sets], non_blocking=True)
+                ready3[0].record(copy_stream)
             for i in range(cnt):
-                b = i & 1
+                b, nb = i % 3, (i + 1) % 3
                 if i + 1 < cnt:
                     with torch.cuda.stream(copy_stream):
-                        if used[b ^ 1]:
-                            copy_stream.wait_event(free[b ^ 1])
-                        bufs[b ^ 1].copy_(h_sets[(first + i + 1) % n_sets], non_blocking=True)
-                        ready[b ^ 1].record(copy_stream)
-                stream.wait_event(ready[b])
-                msm_once(bufs[b])
-                free[b].record(stream)
-                used[b] = True
-                h_out.copy_(d_out[:32], non_blocking=True)
+                        if used[nb]:
+                            copy_stream.wait_event(free3[nb])
+                        bufs3[nb].copy_(h_sets[(first + i + 1) % n_sets], non_blocking=True)
+                        ready3[nb].record(copy_stream)
+                stream.wait_event(ready3[b])
+                be.msm_sharded_submit_dev(bufs3[b].data_ptr(), table, 0, n, smsm.d_outs[i % 3].data_ptr())
+                if i >= 1:
+                    free3[(i - 1) % 3].record(stream)
+                    used[(i - 1) % 3] = True
+                if i >= 2:
+                    h_out.copy_(smsm.d_outs[(i - 2) % 3][:32], non_blocking=True)
+            be.msm_sharded_wait()
+            if cnt >= 2:
+                h_out.copy_(smsm.d_outs[(cnt - 2) % 3][:32], non_blocking=True)
+            h_out.copy_(smsm.d_outs[(cnt - 1) % 3][:32], non_blocking=True)
 
         ms_e2e = timed_block(msm_pipelined, msm_steps, args.warmup, [copy_stream])
         be.set_profiling(True)
@@ -1078,6 +1085,9 @@ def run_ours(args):
             acc_t = float(phases[3]) * 1e-3
             imads_acc = ops["mixed_adds"] * IMAD_MADD
             imads_all = imads_acc + ops["full_adds"] * IMAD_ADD + ops["doublings"] * IMAD_DBL
+            c_win = 8 if n <= 1500 else 11 if n <= 96000 else 15 if n < 1000000 else 16      # pick_window (capi_core.cu)
+            W_win = (253 + c_win - 1) // c_win
+            imads_alg = IMAD_MADD * n * W_win + IMAD_ADD * 2 * (2 ** (c_win - 1) - 1) * W_win + IMAD_DBL * c_win * (W_win - 1)
             ach = imads_acc / acc_t
             msm = {
                 "metric": "MSM points/sec at 2^20", "value": total_points * msm_steps / (ms_res * 1e-3), "unit": "points/s",
@@ -1100,15 +1110,19 @@ def run_ours(args):
                         "d2h_bytes_per_step": 32, "ms_per_step": ms_e2e / msm_steps,
                         "serial": {"value": total_points * msm_steps / (ms_e2e_serial * 1e-3), "ms_per_step": ms_e2e_serial / msm_steps},
                         "note": "scalars pinned-host->HBM and result HBM->host every step; generator table resident; the next "
-                                "step's scalars are copied on a second stream during this step's MSM; single GPU: submit(i), "
-                                "wait_previous, read result i-1 (two MSMs in flight)"},
+                                "step's scalars are copied on a second stream during this step's MSM; submitted form (two MSMs "
+                                "in flight per GPU; sharded: bpp_msm_sharded_submit_dev, the 128-byte gather of step i-1 beside step i)"},
                 "gpu_launches": launches,
                 "roofline": {"bound": "imad", "kernel": "k_bucket_accum", "achieved": ach / 1e12, "peak": imad_peak / 1e12,
                              "unit": "T IMAD.WIDE.U32/s", "frac": ach / imad_peak, "kernel_ms": float(phases[3]),
                              "point_adds_per_s": ops["mixed_adds"] / acc_t, "peak_source": peak_src,
                              "traffic": _ncu_traffic("r1_ncu_full_k_bucket_accum.csv") if args.log_n == 20 else None,
                              "traffic_source": "profiles/r1_ncu_full_k_bucket_accum.csv (dram read+write per launch)",
-                             "whole_msm": {"imad_equiv": imads_all, "frac_of_peak": imads_all / (ms_res / msm_steps * 1e-3) / imad_peak},
+                             "whole_msm": {"imad_algorithmic": imads_alg, "formula": "SURVEY 8(d): 504 N W + 648 * 2 (2^(c-1) - 1) W + 464 c (W - 1), "
+                                                                                     f"c = {c_win}, W = {W_win}",
+                                           "frac_of_peak": imads_alg / (ms_res / msm_steps * 1e-3) / imad_peak,
+                                           "frac_of_peak_single_call": imads_alg / (ms_single / msm_steps * 1e-3) / imad_peak,
+                                           "imad_executed": imads_all},
                              "phases_ms": dict(zip(bpperm_b200.backend.PHASES, [float(x) for x in phases]))},
             }
             if clocks2:

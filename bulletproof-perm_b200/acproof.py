@@ -181,6 +181,14 @@ class Batch:
         self.be._check(self.be._lib.bpp_acp_batch_download_accept(self._h, out))
         return out.raw
 
+    def gather_accept(self, per: int) -> bytes:
+        """Sharded batch verification: all ranks' accept bytes (nranks x per, rank r's at r * per), through the
+        library's NCCL communicator (Backend.comm_init)."""
+        nr, _ = self.be.comm_info()
+        out = ctypes.create_string_buffer(per * nr)
+        self.be._check(self.be._lib.bpp_acp_batch_gather_accept(self._h, per, out))
+        return out.raw
+
     def time_commit_msm(self, reps: int = 5):
         ms, madd, add = ctypes.c_float(), ctypes.c_uint64(), ctypes.c_uint64()
         self.be._check(self.be._lib.bpp_acp_batch_time_commit_msm(self._h, reps, ctypes.byref(ms), ctypes.byref(madd),

@@ -253,6 +253,42 @@ class Backend:
         self._check(self._lib.bpp_points_sum_compress_dev(self._ctx, ctypes.c_void_p(d_partials), g,
                                                           ctypes.c_void_p(d_out32)))
 
+    # -- multi-GPU: the library's own NCCL communicator (one process per GPU) -----------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """128-byte id made on rank 0; the host program hands it to every rank (bpp_comm_unique_id)."""
+        from . import _lib
+        out = ctypes.create_string_buffer(128)
+        rc = _lib.load().bpp_comm_unique_id(out)
+        if rc:
+            raise _lib.BppError(rc, "bpp_comm_unique_id")
+        return out.raw
+
+    def comm_init(self, nranks: int, rank: int, uid: bytes):
+        self._check(self._lib.bpp_comm_init(self._ctx, nranks, rank, bytes(uid)))
+
+    def comm_free(self):
+        self._check(self._lib.bpp_comm_free(self._ctx))
+
+    def comm_info(self):
+        nr, r = ctypes.c_int(), ctypes.c_int()
+        self._check(self._lib.bpp_comm_info(self._ctx, ctypes.byref(nr), ctypes.byref(r)))
+        return nr.value, r.value
+
+    def all_gather_dev(self, d_send: int, bytes_per_rank: int, d_recv: int):
+        self._check(self._lib.bpp_comm_all_gather_dev(self._ctx, ctypes.c_void_p(d_send), bytes_per_rank, ctypes.c_void_p(d_recv)))
+
+    def msm_sharded_dev(self, d_scalars: int, points: Points, off: int, n: int, d_out32: int):
+        """This rank's slice -> the full MSM's encoding on every rank (partial, 128-byte all-gather, sum, compress)."""
+        self._check(self._lib.bpp_msm_sharded_dev(self._ctx, ctypes.c_void_p(d_scalars), points._h, off, n, ctypes.c_void_p(d_out32)))
+
+    def msm_sharded_submit_dev(self, d_scalars: int, points: Points, off: int, n: int, d_out32: int):
+        self._check(self._lib.bpp_msm_sharded_submit_dev(self._ctx, ctypes.c_void_p(d_scalars), points._h, off, n,
+                                                         ctypes.c_void_p(d_out32)))
+
+    def msm_sharded_wait(self):
+        self._check(self._lib.bpp_msm_sharded_wait(self._ctx))
+
     # -- element-wise self-test hook ------------------------------------------------------------------
     def test_op(self, op: int, a: bytes, b: bytes) -> bytes:
         n = len(a) // 32

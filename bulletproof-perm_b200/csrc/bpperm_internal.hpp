@@ -74,6 +74,15 @@ struct bpp_ctx {
     cudaStream_t s_sort = nullptr, s_bulk[2] = {}, s_tail[BPP_MAX_GROUPS] = {};
     cudaEvent_t ev_fork = nullptr, ev_sorted[BPP_MAX_GROUPS] = {}, ev_acc[BPP_MAX_GROUPS] = {}, ev_tail[BPP_MAX_GROUPS] = {};
     cudaStream_t s_final = nullptr;
+    // multi-GPU (bpp_comm_init): one NCCL communicator per context, created once; collectives run on s_comm or on the
+    // caller's stream.  Payloads are tiny (128 B partial points, accept bytes): latency, not bandwidth.
+    void *comm = nullptr;                                       // ncclComm_t
+    int comm_rank = 0, comm_nranks = 1;
+    cudaStream_t s_comm = nullptr;
+    uint8_t *d_comm = nullptr;                                  // 3 slots x (128 B partial + nranks x 128 B gathered)
+    uint8_t *d_comm_out[3] = {};                                // where each slot's result goes (caller's buffers)
+    cudaEvent_t ev_comm_ready = nullptr, ev_comm_done[3] = {};
+    uint64_t comm_seq = 0;                                      // sharded MSMs submitted so far
     // stage timeline of the last MSM (bpp_set_msm_trace): timing events on whichever stream ran the stage
     bool trace = false;
     std::vector<std::pair<std::string, cudaEvent_t>> trace_ev;
@@ -119,6 +128,7 @@ static int grow(bpp_ctx *ctx, T **p, size_t *cap, size_t need_elems) {
 }
 
 // defined in capi_core.cu
+int comm_all_gather(bpp_ctx *ctx, const void *d_send, void *d_recv, size_t bytes_per_rank, cudaStream_t stream);
 int msm_wait_pending(bpp_ctx *ctx, bool keep_latest = false);
 int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points *pts, size_t off, size_t n, uint8_t *d_out,
                 int do_compress, bool join = true);

@@ -914,9 +914,8 @@ static int acp_prove_ipa(bpp_acp_batch *b) {
     const uint32_t B = b->B, np = L.np, lg = L.lg;
     cudaStream_t s = ctx->stream;
     int rc;
-    const unsigned rt = np >= IPA_ROUND_THREADS ? IPA_ROUND_THREADS : (np < 128 ? 128 : np);   // k_ipa_round block
     if (!b->host_transcripts) {
-        TR_LAUNCH(k_ipa_challenge, B, s, nullptr, L, B, -1, b->d_tr, b->d_blk);
+        TR_LAUNCH_AT(tr_warp_max() < 1023 ? tr_warp_max() : 1023, k_ipa_challenge, B, s, nullptr, L, B, -1, b->d_tr, b->d_blk);
         LAUNCH_CHECK(ctx);
     } else {
         // t_hat, tau_x, mu are contiguous in the proof block
@@ -934,8 +933,8 @@ static int acp_prove_ipa(bpp_acp_batch *b) {
         });
         if ((rc = acp_put_challenges(b, L.wq, 1))) return rc;
     }
-    k_ipa_round<<<B, rt, 0, s>>>(L, -1, b->d_blk);   // s table = {1}, c_L, c_R and the MSM scalars of round 0
-    LAUNCH_CHECK(ctx);
+    CK(ctx, ipa_round_launch(L, -1, b->d_blk, B, s));   // s table = {1}, c_L, c_R and the MSM scalars of round 0
+    ctx->launches++;
     const uint32_t gH = 2 + b->gens->n;
     for (uint32_t j = 0; j < lg; j++) {
         const uint32_t nj = np >> j;
@@ -948,7 +947,7 @@ static int acp_prove_ipa(bpp_acp_batch *b) {
         k_compress_strided<<<(2 * B + 127) / 128, 128, 0, s>>>(b->d_lrext, 2 * lg, 2 * j, 2, B, b->d_lr);
         LAUNCH_CHECK(ctx);
         if (!b->host_transcripts) {
-            TR_LAUNCH(k_ipa_challenge, B, s, b->d_lr, L, B, (int)j, b->d_tr, b->d_blk);
+            TR_LAUNCH_AT(tr_warp_max() < 1023 ? tr_warp_max() : 1023, k_ipa_challenge, B, s, b->d_lr, L, B, (int)j, b->d_tr, b->d_blk);
             LAUNCH_CHECK(ctx);
         } else {
             CK(ctx, cudaMemcpy2DAsync(b->h_pts8, 64, b->d_lr + 64 * (size_t)j, 64 * (size_t)lg, 64, B, cudaMemcpyDeviceToHost, s));
@@ -963,8 +962,8 @@ static int acp_prove_ipa(bpp_acp_batch *b) {
             k_ipa_uinv<<<(B + 63) / 64, 64, 0, s>>>(L, B, j, b->d_blk);
             LAUNCH_CHECK(ctx);
         }
-        k_ipa_round<<<B, rt, 0, s>>>(L, (int)j, b->d_blk);   // fold a, b; s table; next round's c_L, c_R and MSM scalars
-        LAUNCH_CHECK(ctx);
+        CK(ctx, ipa_round_launch(L, (int)j, b->d_blk, B, s));   // fold a, b; s table; next round's c_L, c_R and MSM scalars
+        ctx->launches++;
     }
     k_acp_pack_fixed<<<dim3((b->proof_len / 32 + 127) / 128, B), 128, 0, s>>>(L, b->d_pts8, b->d_lr, b->d_blk, b->d_proofs,
                                                                              b->proof_len);
@@ -1349,6 +1348,22 @@ extern "C" int bpp_acp_batch_time_commit_msm(bpp_acp_batch *b, int reps, float *
     if (mixed_adds) *mixed_adds = (uint64_t)b->B * (1 + 2 * L.n) * b->gens->Wn;
     const bool warp_form = b->fb_warp_per_output && (uint64_t)b->B >= 16ull * ctx->sm_count;
     if (full_adds) *full_adds = (uint64_t)b->B * (warp_form ? 31 : FB_THREADS - 1);
+    return BPP_OK;
+}
+
+extern "C" int bpp_acp_batch_gather_accept(bpp_acp_batch *b, size_t per, uint8_t *accept_all) {
+    if (!b || !accept_all || per < b->B) return BPP_ERR_INVALID_ARG;
+    bpp_ctx *ctx = b->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    const size_t nr = (size_t)ctx->comm_nranks;
+    int rc;
+    if ((rc = grow(ctx, &ctx->d_small, &ctx->cap_small, per * (nr + 1)))) return rc;
+    uint8_t *mine = ctx->d_small, *all = ctx->d_small + per;
+    CK(ctx, cudaMemsetAsync(mine, 0, per, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(mine, b->d_accept, b->B, cudaMemcpyDeviceToDevice, ctx->stream));
+    if ((rc = comm_all_gather(ctx, mine, all, per, ctx->stream))) return rc;
+    CK(ctx, cudaMemcpyAsync(accept_all, all, per * nr, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
     return BPP_OK;
 }
 

@@ -65,6 +65,7 @@ extern "C" void bpp_free(bpp_ctx *ctx) {
             if (p) cudaFree(p);
         if (sc.ev_done) cudaEventDestroy(sc.ev_done);
     }
+    if (ctx->comm) bpp_comm_free(ctx);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (int i = 0; i <= BPP_PHASE_COUNT; i++)
@@ -735,6 +736,179 @@ extern "C" int bpp_msm_vartime_host(bpp_ctx *ctx, const uint8_t *scalars, size_t
     rc = bpp_msm_vartime(ctx, scalars, n_scalars, p, 0, n_points, out32, nullptr);
     bpp_points_free(ctx, p);
     return rc;
+}
+
+// ---- multi-GPU: NCCL inside the library (SURVEY 8b / D.3 "NCCL communicator created once") --------------------
+// One process per GPU; rank 0 makes a 128-byte id (bpp_comm_unique_id), the host program hands it to every rank by
+// whatever channel it has, every rank calls bpp_comm_init.  libnccl.so.2 is resolved at run time (dlopen), so a
+// single-GPU host needs no NCCL installed; a process that already loaded NCCL (e.g. through PyTorch) shares that copy.
+#include <dlfcn.h>
+#include <nccl.h>
+namespace {
+struct nccl_api {
+    void *h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+nccl_api &nccl() {
+    static nccl_api a;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *nm : names)
+            if ((a.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL))) break;
+        if (!a.h) return;
+        a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(a.h, "ncclGetUniqueId");
+        a.CommInitRank = (decltype(a.CommInitRank))dlsym(a.h, "ncclCommInitRank");
+        a.AllGather = (decltype(a.AllGather))dlsym(a.h, "ncclAllGather");
+        a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.h, "ncclCommDestroy");
+        a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.h, "ncclGetErrorString");
+        a.ok = a.GetUniqueId && a.CommInitRank && a.AllGather && a.CommDestroy && a.GetErrorString;
+    });
+    return a;
+}
+}  // namespace
+#define NCCL_CK(ctx, call)                                                                  \
+    do {                                                                                    \
+        ncclResult_t r_ = (call);                                                           \
+        if (r_ != ncclSuccess) {                                                            \
+            (ctx)->last_error = std::string(#call) + ": " + nccl().GetErrorString(r_);      \
+            return BPP_ERR_CUDA;                                                            \
+        }                                                                                   \
+    } while (0)
+
+extern "C" int bpp_comm_unique_id(uint8_t id[BPP_COMM_ID_BYTES]) {
+    if (!id) return BPP_ERR_INVALID_ARG;
+    static_assert(sizeof(ncclUniqueId) == BPP_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
+    if (!nccl().ok) return BPP_ERR_NO_DEVICE;
+    ncclUniqueId u;
+    if (nccl().GetUniqueId(&u) != ncclSuccess) return BPP_ERR_CUDA;
+    memcpy(id, &u, sizeof(u));
+    return BPP_OK;
+}
+extern "C" int bpp_comm_free(bpp_ctx *ctx) {
+    if (!ctx) return BPP_ERR_INVALID_ARG;
+    if (!ctx->comm) return BPP_OK;
+    cudaSetDevice(ctx->device);
+    msm_wait_pending(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->s_comm);
+    nccl().CommDestroy((ncclComm_t)ctx->comm);
+    ctx->comm = nullptr;
+    cudaStreamDestroy(ctx->s_comm);
+    cudaEventDestroy(ctx->ev_comm_ready);
+    for (int i = 0; i < 3; i++) cudaEventDestroy(ctx->ev_comm_done[i]);
+    cudaFree(ctx->d_comm);
+    ctx->d_comm = nullptr;
+    ctx->comm_nranks = 1;
+    ctx->comm_rank = 0;
+    return BPP_OK;
+}
+extern "C" int bpp_comm_init(bpp_ctx *ctx, int nranks, int rank, const uint8_t id[BPP_COMM_ID_BYTES]) {
+    if (!ctx || !id || nranks < 1 || rank < 0 || rank >= nranks) return BPP_ERR_INVALID_ARG;
+    if (ctx->comm) return BPP_ERR_INVALID_ARG;   // once per context
+    if (!nccl().ok) {
+        ctx->last_error = "libnccl.so.2 not found (dlopen)";
+        return BPP_ERR_NO_DEVICE;
+    }
+    CK(ctx, cudaSetDevice(ctx->device));
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof(u));
+    ncclComm_t c = nullptr;
+    NCCL_CK(ctx, nccl().CommInitRank(&c, nranks, u, rank));
+    ctx->comm = c;
+    ctx->comm_rank = rank;
+    ctx->comm_nranks = nranks;
+    CK(ctx, cudaStreamCreateWithFlags(&ctx->s_comm, cudaStreamNonBlocking));
+    CK(ctx, cudaEventCreateWithFlags(&ctx->ev_comm_ready, cudaEventDisableTiming));
+    for (int i = 0; i < 3; i++) CK(ctx, cudaEventCreateWithFlags(&ctx->ev_comm_done[i], cudaEventDisableTiming));
+    CK(ctx, cudaMalloc((void **)&ctx->d_comm, 3 * (size_t)(1 + nranks) * 128));
+    return BPP_OK;
+}
+extern "C" int bpp_comm_info(bpp_ctx *ctx, int *nranks, int *rank) {
+    if (!ctx) return BPP_ERR_INVALID_ARG;
+    if (nranks) *nranks = ctx->comm_nranks;
+    if (rank) *rank = ctx->comm_rank;
+    return BPP_OK;
+}
+int comm_all_gather(bpp_ctx *ctx, const void *d_send, void *d_recv, size_t bytes_per_rank, cudaStream_t stream) {
+    if (!ctx->comm) {   // a single rank: the gather is a copy
+        if (d_send != d_recv) CK(ctx, cudaMemcpyAsync(d_recv, d_send, bytes_per_rank, cudaMemcpyDeviceToDevice, stream));
+        return BPP_OK;
+    }
+    NCCL_CK(ctx, nccl().AllGather(d_send, d_recv, bytes_per_rank, ncclUint8, (ncclComm_t)ctx->comm, stream));
+    return BPP_OK;
+}
+extern "C" int bpp_comm_all_gather_dev(bpp_ctx *ctx, const void *d_send, size_t bytes_per_rank, void *d_recv) {
+    if (!ctx || !d_send || !d_recv || bytes_per_rank == 0) return BPP_ERR_INVALID_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    return comm_all_gather(ctx, d_send, d_recv, bytes_per_rank, ctx->stream);
+}
+static inline uint8_t *comm_part(bpp_ctx *ctx, int slot) { return ctx->d_comm + (size_t)slot * (1 + ctx->comm_nranks) * 128; }
+// Sharded MSM: this rank holds a slice of the points and the matching scalars; every rank reduces its
+// slice to one extended point (128 B), one all-gather of those partials, every rank adds them and compresses - the
+// result (32 B encoding at d_out32) is identical on all ranks.  Joined form: in stream order on the caller's stream.
+extern "C" int bpp_msm_sharded_dev(bpp_ctx *ctx, const void *d_scalars, const bpp_points *points, size_t off, size_t n,
+                                   void *d_out32) {
+    if (!ctx || !d_scalars || !points || !d_out32 || n == 0) return BPP_ERR_INVALID_ARG;
+    if (off + n > points->n) return BPP_ERR_LENGTH_MISMATCH;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->comm) return msm_enqueue(ctx, (const uint32_t *)d_scalars, points, off, n, (uint8_t *)d_out32, 1);
+    int rc;
+    uint8_t *part = comm_part(ctx, 0);
+    if ((rc = msm_enqueue(ctx, (const uint32_t *)d_scalars, points, off, n, part, 0))) return rc;
+    if ((rc = comm_all_gather(ctx, part, part + 128, 128, ctx->stream))) return rc;
+    k_points_sum_compress<<<1, 32, 0, ctx->stream>>>((const uint32_t *)(part + 128), (uint32_t)ctx->comm_nranks, (uint8_t *)d_out32);
+    LAUNCH_CHECK(ctx);
+    return BPP_OK;
+}
+// Throughput form for a sequence of independent sharded MSMs: two MSMs in flight per rank (bpp_msm_submit_partial_dev),
+// the 128-byte all-gather + sum + compress of MSM i - 1 on the communication stream beside MSM i; d_out32 of MSM i is
+// final once the caller's stream has passed the submit of MSM i + 2, or after bpp_msm_sharded_wait.  Nothing but event
+// waits goes onto the caller's stream between two submits.
+static int comm_gather_slot(bpp_ctx *ctx, int slot) {
+    uint8_t *part = comm_part(ctx, slot);
+    CK(ctx, cudaEventRecord(ctx->ev_comm_ready, ctx->stream));
+    CK(ctx, cudaStreamWaitEvent(ctx->s_comm, ctx->ev_comm_ready, 0));
+    int rc = comm_all_gather(ctx, part, part + 128, 128, ctx->s_comm);
+    if (rc) return rc;
+    k_points_sum_compress<<<1, 32, 0, ctx->s_comm>>>((const uint32_t *)(part + 128), (uint32_t)ctx->comm_nranks, ctx->d_comm_out[slot]);
+    LAUNCH_CHECK(ctx);
+    CK(ctx, cudaEventRecord(ctx->ev_comm_done[slot], ctx->s_comm));
+    return BPP_OK;
+}
+extern "C" int bpp_msm_sharded_submit_dev(bpp_ctx *ctx, const void *d_scalars, const bpp_points *points, size_t off, size_t n,
+                                          void *d_out32) {
+    if (!ctx || !d_scalars || !points || !d_out32 || n == 0) return BPP_ERR_INVALID_ARG;
+    if (off + n > points->n) return BPP_ERR_LENGTH_MISMATCH;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->comm) return msm_enqueue(ctx, (const uint32_t *)d_scalars, points, off, n, (uint8_t *)d_out32, 1, false);
+    int rc;
+    const uint64_t i = ctx->comm_seq++;
+    const int slot = (int)(i % 3);
+    ctx->d_comm_out[slot] = (uint8_t *)d_out32;
+    if ((rc = msm_enqueue(ctx, (const uint32_t *)d_scalars, points, off, n, comm_part(ctx, slot), 0, false))) return rc;
+    if ((rc = msm_wait_pending(ctx, true))) return rc;                       // MSM i - 1 is complete on the caller's stream
+    if (i >= 1 && (rc = comm_gather_slot(ctx, (int)((i - 1) % 3)))) return rc;
+    if (i >= 2) CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_comm_done[(i - 2) % 3], 0));
+    return BPP_OK;
+}
+extern "C" int bpp_msm_sharded_wait(bpp_ctx *ctx) {
+    if (!ctx) return BPP_ERR_INVALID_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = msm_wait_pending(ctx))) return rc;
+    if (!ctx->comm || ctx->comm_seq == 0) return BPP_OK;
+    const uint64_t k = ctx->comm_seq;
+    if ((rc = comm_gather_slot(ctx, (int)((k - 1) % 3)))) return rc;
+    if (k >= 2) CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_comm_done[(k - 2) % 3], 0));
+    CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_comm_done[(k - 1) % 3], 0));
+    ctx->comm_seq = 0;
+    return BPP_OK;
 }
 
 // ---- measurement / tests -------------------------------------------------------------------------

@@ -11,6 +11,8 @@
 // b[i^h] s_t^-1 y^-g (H side), h = n_j / 2: they run through the same fixed-base tables as the
 // commitments (k_fb_msm) and no generator is ever folded.  a and b fold in place in the proof block.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "acproof_kernels.cuh"
 
 #define IPA_MAX_LG 20
@@ -73,12 +75,20 @@ __global__ void __launch_bounds__(128) k_pow_fill(acp_layout lay, uint32_t *__re
 SC_INLINE uint32_t *ipa_stab(uint32_t *blk, const acp_layout &lay, uint32_t p, uint32_t rounds_done) {
     return ACP_PTR(blk, lay, p, lay.stab + (rounds_done & 1u) * lay.np);
 }
-// block per proof.  round = index of the challenge just drawn (u[round], uinv[round] in Montgomery form), -1 before the
-// first round (w at lay.wq drawn).  Leaves a, b folded (lay.l, lay.r), cl[0..1] = w <a_lo, b_hi>, w <a_hi, b_lo> and
-// vG, vH = the next round's MSM scalars; after the last round only the fold happens (a, b are l[0], r[0]).
+// One thread-block CLUSTER per proof (1 CTA up to n' = 1024, then n' / 1024 CTAs up to 8: a single 4096-card proof has
+// n' = 8192 and would otherwise run each round on one SM).  round = index of the challenge just drawn (u[round],
+// uinv[round] in Montgomery form), -1 before the first round (w at lay.wq drawn).  Leaves a, b folded (lay.l, lay.r),
+// cl[0..1] = w <a_lo, b_hi>, w <a_hi, b_lo> and vG, vH = the next round's MSM scalars; after the last round only the
+// fold happens (a, b are l[0], r[0]).  The two barriers are cluster barriers (release/acquire at cluster scope: the
+// folded vectors and the table written by one CTA are read by the others); the CTAs' partial inner products meet in
+// rank 0 through distributed shared memory.
 __global__ void __launch_bounds__(IPA_ROUND_THREADS) k_ipa_round(acp_layout lay, int round, uint32_t *__restrict__ blk) {
+    namespace cg = cooperative_groups;
     __shared__ __align__(16) uint32_t sh[32 * 8];
-    const uint32_t p = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    __shared__ __align__(16) uint32_t part[2 * 8];     // this CTA's share of the two inner products (Montgomery sums)
+    cg::cluster_group cluster = cg::this_cluster();
+    const uint32_t C = cluster.num_blocks(), rank = cluster.block_rank();
+    const uint32_t p = blockIdx.x / C, tid = rank * blockDim.x + threadIdx.x, nt = C * blockDim.x;
     const uint32_t done = (uint32_t)(round + 1);
     uint32_t *st_new = ipa_stab(blk, lay, p, done);
     if (round < 0) {
@@ -115,22 +125,21 @@ __global__ void __launch_bounds__(IPA_ROUND_THREADS) k_ipa_round(acp_layout lay,
             }
         }
     }
-    if (done >= lay.lg) return;
-    __syncthreads();                                   // a, b, s table of this block: visible to the whole block
+    if (done >= lay.lg) return;                        // uniform over the cluster
+    cluster.sync();                                    // a, b, s table: visible to every CTA of the proof
     const uint32_t nj = lay.np >> done, h = nj >> 1;
-    {
-        sc acc, tot, w, r2;
-        sc_load(w, ACP_PTR(blk, lay, p, lay.wq));
-        sc_const(r2, SC_R2);
-        for (uint32_t which = 0; which < 2; which++) {
-            dot_partial(acc, ACP_PTR(blk, lay, p, lay.l + (which ? h : 0)), 1, ACP_PTR(blk, lay, p, lay.r + (which ? 0 : h)), 1, h);
-            block_sum_sc(tot, acc, sh);
-            if (tid == 0) {
-                sc_mont(tot, tot, r2);
-                sc_mul(tot, tot, w);
-                sc_store(ACP_PTR(blk, lay, p, lay.cl + which), tot);
-            }
+    for (uint32_t which = 0; which < 2; which++) {
+        const uint32_t *a = ACP_PTR(blk, lay, p, lay.l + (which ? h : 0)), *b = ACP_PTR(blk, lay, p, lay.r + (which ? 0 : h));
+        sc acc, tot, x, y, pr;
+        sc_set0(acc);
+        for (uint32_t i = tid; i < h; i += nt) {
+            sc_load(x, a + 8 * (size_t)i);
+            sc_load(y, b + 8 * (size_t)i);
+            sc_mont(pr, x, y);
+            sc_add(acc, acc, pr);
         }
+        block_sum_sc(tot, acc, sh);
+        if (threadIdx.x == 0) sc_store(part + 8 * which, tot);
     }
     const uint32_t tmask = (1u << done) - 1u;
     for (uint32_t g = tid; g < lay.np; g += nt) {      // the round's MSM scalars over the original generators
@@ -147,6 +156,46 @@ __global__ void __launch_bounds__(IPA_ROUND_THREADS) k_ipa_round(acp_layout lay,
         sc_mul(r, r, yi);
         sc_store(ACP_PTR(blk, lay, p, lay.vH + g), r);
     }
+    cluster.sync();                                    // every CTA's partial sums are in its shared memory
+    if (rank == 0 && threadIdx.x < 2) {
+        const uint32_t which = threadIdx.x;
+        sc tot, o, w, r2;
+        sc_set0(tot);
+        for (uint32_t r = 0; r < C; r++) {
+            const uint32_t *remote = cluster.map_shared_rank(part, r);
+            sc_load(o, remote + 8 * which);
+            sc_add(tot, tot, o);
+        }
+        sc_load(w, ACP_PTR(blk, lay, p, lay.wq));
+        sc_const(r2, SC_R2);
+        sc_mont(tot, tot, r2);
+        sc_mul(tot, tot, w);
+        sc_store(ACP_PTR(blk, lay, p, lay.cl + which), tot);
+    }
+    cluster.sync();                                    // no CTA leaves while rank 0 reads its shared memory
+}
+// launch: cluster of `C` CTAs per proof
+static inline cudaError_t ipa_round_launch(acp_layout lay, int round, uint32_t *blk, uint32_t B, cudaStream_t s) {
+    const uint32_t np = lay.np;
+    const unsigned threads = np >= IPA_ROUND_THREADS ? IPA_ROUND_THREADS : (np < 128 ? 128 : np);
+    unsigned C = 1;
+    while (C < 8 && (size_t)C * 1024 < np) C <<= 1;
+    if (C == 1) {
+        k_ipa_round<<<B, threads, 0, s>>>(lay, round, blk);
+        return cudaGetLastError();
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(B * C);
+    cfg.blockDim = dim3(threads);
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = C;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k_ipa_round, lay, round, blk);
 }
 // host-transcript path: thread per proof: u_round^-1; both kept in Montgomery form at u[round], uinv[round]
 __global__ void __launch_bounds__(64) k_ipa_uinv(acp_layout lay, uint32_t B, uint32_t round, uint32_t *__restrict__ blk) {

@@ -32,10 +32,14 @@ static inline uint32_t tr_warp_max() {
     }
     return (uint32_t)v;
 }
-#define TR_LAUNCH(kern, count, stream, ...)                                                                        \
+// TR_LAUNCH_AT: the same with an explicit limit (k_ipa_challenge ends in a one-lane inversion per sponge, which a warp
+// per sponge spreads over 32 x more warps: thread form from 1024 proofs - measured 17.8 against 20.2 ms per 4096-proof
+// `fixed` prover).
+#define TR_LAUNCH(kern, count, stream, ...) TR_LAUNCH_AT(tr_warp_max(), kern, count, stream, __VA_ARGS__)
+#define TR_LAUNCH_AT(limit, kern, count, stream, ...)                                                              \
     do {                                                                                                           \
         const uint32_t tr_cnt_ = (uint32_t)(count);                                                                \
-        if (tr_cnt_ <= tr_warp_max()) kern<merlin_warp><<<(tr_cnt_ + TR_THREADS / 32 - 1) / (TR_THREADS / 32), TR_THREADS, 0, stream>>>(__VA_ARGS__); \
+        if (tr_cnt_ <= (limit)) kern<merlin_warp><<<(tr_cnt_ + TR_THREADS / 32 - 1) / (TR_THREADS / 32), TR_THREADS, 0, stream>>>(__VA_ARGS__); \
         else kern<merlin_tr><<<(tr_cnt_ + 31) / 32, 32, 0, stream>>>(__VA_ARGS__);                                 \
     } while (0)
 

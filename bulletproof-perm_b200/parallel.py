@@ -1,10 +1,12 @@
-"""Multi-GPU plumbing (one process per GPU, torch.distributed): only what SURVEY 8(e) shards.
+"""Multi-GPU plumbing (one process per GPU): only what SURVEY 8(e) shards, and all of it behind the C ABI.
 
-* proofs are independent units  -> contiguous slices per rank, no data-path collective; accept bytes can be
-  gathered with `gather_bytes` when one rank needs all decisions;
-* a large MSM shards its points  -> every rank reduces its slice to one extended point (128 B), a single
-  all-gather of those partials, then every rank adds them and compresses.
-The collective payloads are tiny (128 B per rank): latency, not bandwidth, is what matters.
+* proofs are independent units  -> contiguous slices per rank (`shard_bounds`), no data-path collective; the accept
+  bytes are all-gathered by the library (bpp_acp_batch_gather_accept) when one rank needs all decisions;
+* a large MSM shards its points  -> every rank reduces its slice to one extended point (128 B), the library all-gathers
+  those partials over NCCL, every rank adds them and compresses (bpp_msm_sharded_dev / _submit_dev / _wait).
+The communicator lives in the library (bpp_comm_init, created once per context); this module only carries the 128-byte
+id from rank 0 to the others over whatever channel the host program has - here torch.distributed, which the
+benchmark and the tests use for their barriers anyway.  Payloads are tiny (128 B per rank): latency, not bandwidth.
 """
 from __future__ import annotations
 
@@ -20,8 +22,22 @@ def shard_bounds(n: int, world: int, rank: int):
     return off, cnt
 
 
+def init_comm(backend, world: int, rank: int, device=None):
+    """Create the library's NCCL communicator on `backend`: rank 0 makes the id, torch.distributed broadcasts it."""
+    if world == 1:
+        return
+    uid = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        uid = torch.frombuffer(bytearray(type(backend).comm_unique_id()), dtype=torch.uint8).clone()
+    if dist.get_backend() == "nccl":
+        uid = uid.to(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
+    dist.broadcast(uid, src=0)
+    backend.comm_init(world, rank, bytes(uid.cpu().numpy().tobytes()))
+
+
 def gather_bytes(local: torch.Tensor, world: int) -> torch.Tensor:
-    """All-gather a fixed-size uint8 tensor; result is [world * len(local)] in rank order."""
+    """All-gather a fixed-size uint8 tensor through torch.distributed (host-side tests on gloo); result is
+    [world * len(local)] in rank order.  The GPU path uses the library: Backend.all_gather_dev / Batch.gather_accept."""
     if world == 1:
         return local.clone()
     out = torch.empty(world * local.numel(), dtype=torch.uint8, device=local.device)
@@ -30,112 +46,29 @@ def gather_bytes(local: torch.Tensor, world: int) -> torch.Tensor:
 
 
 class ShardedMsm:
-    """MSM over a point set sharded across ranks.  `table` holds this rank's slice on its GPU."""
-
-    PARTIAL_BYTES = 128
+    """MSM over a point set sharded across ranks.  `table` holds this rank's slice on its GPU; the backend carries the
+    communicator (init_comm).  With world == 1 the same calls are the single-GPU MSM."""
 
     def __init__(self, backend, table, world: int, device):
         self.be, self.table, self.world = backend, table, world
-        self.d_part = torch.zeros(self.PARTIAL_BYTES, dtype=torch.uint8, device=device)
-        self.d_all = torch.zeros(world * self.PARTIAL_BYTES, dtype=torch.uint8, device=device)
         self.d_out = torch.zeros(160, dtype=torch.uint8, device=device)
+        self.d_outs = [torch.zeros(160, dtype=torch.uint8, device=device) for _ in range(3)]
 
     def run(self, d_scalars: torch.Tensor) -> torch.Tensor:
         """d_scalars: this rank's scalars (n_local x 32, uint8, on the GPU).  Returns the device buffer whose
         first 32 bytes are the compressed result (identical on every rank)."""
-        n = len(self.table)
-        if self.world == 1:
-            self.be.msm_dev(d_scalars.data_ptr(), self.table, 0, n, self.d_out.data_ptr())
-            return self.d_out
-        self.be.msm_partial_dev(d_scalars.data_ptr(), self.table, 0, n, self.d_part.data_ptr())
-        dist.all_gather_into_tensor(self.d_all, self.d_part)
-        self.be.points_sum_compress_dev(self.d_all.data_ptr(), self.world, self.d_out.data_ptr())
+        self.be.msm_sharded_dev(d_scalars.data_ptr(), self.table, 0, len(self.table), self.d_out.data_ptr())
         return self.d_out
 
-    # Throughput form for a sequence of independent MSMs (two in flight per rank, bpp_msm_submit_*), three buffer
-    # slots (i % 3):
-    #     for i, sc in enumerate(sets):
-    #         m.submit(sc, i % 3); m.wait_previous()
-    #         if i >= 1: m.gather((i - 1) % 3)       # 128 B/rank all-gather + sum + compress on a side stream
-    #         if i >= 2: m.finish((i - 2) % 3)       # event wait only: that step's result is final
-    #     m.wait(); m.gather(last % 3); m.finish((last - 1) % 3); m.finish(last % 3)
-    # Nothing but event waits goes onto the caller's stream between two submits: a kernel there (even the one-warp
-    # sum) queues behind the accumulate blocks of the MSM in flight and would hold back the next submit's fork.  The
-    # gather of step i-1 and its sum + compress run on a side stream (the sum through a second context bound to it)
-    # beside the MSM of step i; finish() only makes the caller's stream wait for them.
-    SLOTS = 3
-
-    def _slots(self):
-        if not hasattr(self, "_slot_bufs"):
-            dev = self.d_out.device
-            self._slot_bufs = [(torch.zeros(self.PARTIAL_BYTES, dtype=torch.uint8, device=dev),
-                                torch.zeros(self.world * self.PARTIAL_BYTES, dtype=torch.uint8, device=dev),
-                                torch.zeros(160, dtype=torch.uint8, device=dev)) for _ in range(self.SLOTS)]
-            self._gathered = [torch.cuda.Event() for _ in range(self.SLOTS)]
-            self._ready = torch.cuda.Event()
-            self._side = torch.cuda.Stream(dev)
-            if self.world > 1:
-                self._side_be = type(self.be)(dev.index if dev.index is not None else 0)
-                self._side_be.set_stream(self._side.cuda_stream)
-        return self._slot_bufs
-
-    def submit(self, d_scalars: torch.Tensor, slot: int):
-        part, _, out = self._slots()[slot]
+    def run_many(self, scalar_sets):
+        """Throughput form over a list of device scalar tensors: two MSMs in flight per rank, the 128-byte all-gather
+        + sum of step i - 1 on the library's communication stream beside the MSM of step i.  Returns the output buffer
+        of the last step (results rotate over three buffers: self.d_outs[i % 3])."""
         n = len(self.table)
-        if self.world == 1:
-            self.be.msm_submit_dev(d_scalars.data_ptr(), self.table, 0, n, out.data_ptr())
-        else:
-            self.be.msm_submit_partial_dev(d_scalars.data_ptr(), self.table, 0, n, part.data_ptr())
-
-    def wait_previous(self):
-        self.be.msm_wait_previous()
-
-    def wait(self):
-        self.be.msm_wait()
-
-    def gather(self, slot: int):
-        """After the slot's MSM has been waited for on the caller's stream: all-gather of the partials on the side
-        stream (nothing to do on one GPU)."""
-        if self.world == 1:
-            return
-        part, allp, _ = self._slots()[slot]
-        cur = torch.cuda.current_stream(part.device)
-        self._ready.record(cur)
-        self._side.wait_event(self._ready)
-        _, _, out = self._slots()[slot]
-        with torch.cuda.stream(self._side):
-            dist.all_gather_into_tensor(allp, part)
-            self._side_be.points_sum_compress_dev(allp.data_ptr(), self.world, out.data_ptr())
-            self._gathered[slot].record(self._side)
-
-    def finish(self, slot: int) -> torch.Tensor:
-        """The caller's stream waits for the slot's gather + sum.  Returns the slot's 160-byte output buffer (first
-        32 bytes = the compressed result, identical on every rank)."""
-        _, allp, out = self._slots()[slot]
-        if self.world > 1:
-            torch.cuda.current_stream(out.device).wait_event(self._gathered[slot])
-        return out
+        for i, sc in enumerate(scalar_sets):
+            self.be.msm_sharded_submit_dev(sc.data_ptr(), self.table, 0, n, self.d_outs[i % 3].data_ptr())
+        self.be.msm_sharded_wait()
+        return self.d_outs[(len(scalar_sets) - 1) % 3]
 
     def close(self):
-        """Release the side context of the throughput form (multi-GPU only)."""
-        be2 = getattr(self, "_side_be", None)
-        if be2 is not None:
-            torch.cuda.synchronize()
-            be2.close()
-            self._side_be = None
-
-    def run_many(self, scalar_sets):
-        """The loop above over a list of device scalar tensors; returns the output buffer of the last step."""
-        k = len(scalar_sets)
-        for i, sc in enumerate(scalar_sets):
-            self.submit(sc, i % 3)
-            self.wait_previous()
-            if i >= 1:
-                self.gather((i - 1) % 3)
-            if i >= 2:
-                self.finish((i - 2) % 3)
-        self.wait()
-        self.gather((k - 1) % 3)
-        if k >= 2:
-            self.finish((k - 2) % 3)
-        return self.finish((k - 1) % 3)
+        pass

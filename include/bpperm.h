@@ -166,6 +166,26 @@ int bpp_vecpoly3_eval(bpp_ctx *ctx, const uint8_t *coeffs, size_t n, const uint8
 /* poly.rs:14-18  Poly6::eval */
 int bpp_poly6_eval(bpp_ctx *ctx, const uint8_t t1_t6[192], const uint8_t x[32], uint8_t out[32]);
 
+/* ---- multi-GPU: one process per GPU, NCCL inside the library -----------------------------
+ * Only what the path shards: a large MSM (points partitioned, 128-byte partial results all-gathered, summed and
+ * compressed on every rank) and batch verification (proofs partitioned, accept bytes all-gathered).  Rank 0 makes the
+ * id, the host program distributes it (any channel), every rank calls bpp_comm_init once; libnccl.so.2 is resolved
+ * at run time.  Without a communicator every call below degrades to its single-GPU meaning. */
+#define BPP_COMM_ID_BYTES 128
+int bpp_comm_unique_id(uint8_t id[BPP_COMM_ID_BYTES]);
+int bpp_comm_init(bpp_ctx *ctx, int nranks, int rank, const uint8_t id[BPP_COMM_ID_BYTES]);
+int bpp_comm_free(bpp_ctx *ctx);
+int bpp_comm_info(bpp_ctx *ctx, int *nranks, int *rank);
+/* all-gather of bytes_per_rank device bytes per rank into d_recv (nranks x bytes_per_rank), on the context's stream */
+int bpp_comm_all_gather_dev(bpp_ctx *ctx, const void *d_send, size_t bytes_per_rank, void *d_recv);
+/* sharded vartime_multiscalar_mul: this rank's slice of scalars and points -> the full result's encoding (32 B at
+ * d_out32, identical on every rank).  _submit/_wait: the throughput form (two MSMs in flight, the gather of MSM i-1
+ * beside MSM i; results valid after bpp_msm_sharded_wait). */
+int bpp_msm_sharded_dev(bpp_ctx *ctx, const void *d_scalars, const bpp_points *points, size_t off, size_t n, void *d_out32);
+int bpp_msm_sharded_submit_dev(bpp_ctx *ctx, const void *d_scalars, const bpp_points *points, size_t off, size_t n,
+                               void *d_out32);
+int bpp_msm_sharded_wait(bpp_ctx *ctx);
+
 /* ---- small and batched MSMs over a long-lived point set ---------------------------------
  * The reference's 15 call sites (circuit_lib.rs:187-575) multiply 2..209 points that always come from the same
  * generator set (g, h, G_vec, H_vec, lib.rs:164-180) by fresh scalars.  bpp_points_precompute attaches a fixed-base
@@ -278,6 +298,10 @@ int bpp_acp_batch_upload_proofs(bpp_acp_batch *b, const uint8_t *proofs, const u
  * weights bound to every proof byte, but pass NULL or fresh randomness; a constant is for reproducible tests only. */
 int bpp_acp_batch_verify(bpp_acp_batch *b, const uint8_t *verifier_seed);
 int bpp_acp_batch_download_accept(bpp_acp_batch *b, uint8_t *accept);
+/* Sharded batch verification (BASELINE configs[3]): every rank verified its own slice of the batch; all ranks' accept
+ * bytes are all-gathered (NCCL, bpp_comm_init) into accept_all = nranks x per bytes, rank r's count bytes at r * per
+ * (per >= every rank's count; the rest is zero padding).  Host buffer; synchronises. */
+int bpp_acp_batch_gather_accept(bpp_acp_batch *b, size_t per, uint8_t *accept_all);
 /* Verification strategy: 1 (default) = first ONE random-linear-combination MSM over the whole batch (weights from
  * the verifier seed; Pippenger over count x (m + 8) decompressed points + the shared generators), the per-proof
  * kernels only when it is not the identity, i.e. some proof is invalid; 0 = always per proof.  The accept bytes
