@@ -300,10 +300,49 @@ def cpu_msm_baseline():
     return out
 
 
+def run_reference_msm_sweep(args):
+    """--impl reference --workload msm: the CPU restatement of dalek's vartime_multiscalar_mul on the inputs of
+    tools/msm_sweep.py (same seeds), one core and all cores (orc_msm_vartime_mt: points split over threads, partial
+    results added), at every N of the sweep up to 2^20 (BASELINE configs[4] "vs dalek ... on host cores")."""
+    from oracle import cref
+    cores = os.cpu_count() or 1
+    rows = []
+    for log_n in range(10, 21, 2):
+        n = 1 << log_n
+        rs = np.random.RandomState(5000 + log_n)
+        blobs = rs.randint(0, 256, size=(n, 64), dtype=np.uint8)
+        sc = rs.randint(0, 256, size=(n, 32), dtype=np.uint8)
+        sc[:, 31] &= 0x0F
+        pts = cref.from_uniform(blobs.tobytes())
+        scb = sc.tobytes()
+        reps = 3 if log_n <= 16 else 1
+        t0 = time.time()
+        for _ in range(reps):
+            r1 = cref.msm(scb, pts)
+        t1 = (time.time() - t0) / reps
+        cref.msm(scb[:32 * 1024], pts[:160 * 1024], threads=cores)   # thread pool warm
+        t0 = time.time()
+        for _ in range(reps):
+            rN = cref.msm(scb, pts, threads=cores)
+        tN = (time.time() - t0) / reps
+        rows.append({"log_n": log_n, "n": n, "cpu_1core_ms": t1 * 1e3, "cpu_all_cores_ms": tN * 1e3, "cores": cores,
+                     "points_per_s_1core": n / t1, "points_per_s_all_cores": n / tN, "result": r1.hex(), "mt_equal": rN == r1})
+    line = {"impl": "reference", "metric": "MSM points/sec (sweep 2^10..2^20)", "unit": "points/s", "n_gpus": args.gpus,
+            "value": rows[-1]["points_per_s_all_cores"], "higher_is_better": True, "data": "synthetic", "dtype": "u64 (5x51-bit limbs)",
+            "config": {"workload": "ristretto255 vartime MSM sweep, inputs of tools/msm_sweep.py (seed 5000 + log2 N)"},
+            "cpu_baseline": {"kind": "port", "cores": cores, "value": rows[-1]["points_per_s_all_cores"], "unit": "points/s",
+                             "sample": "one MSM per size (three up to 2^16): C restatement of dalek-ng 4.1.1 Straus / Pippenger"},
+            "sweep": rows}
+    _emit(line)
+    return 0
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path on all host cores, bounded sample per step."""
     if int(os.environ.get("RANK", "0")) != 0:
         return 0
+    if args.workload == "msm":
+        return run_reference_msm_sweep(args)
     global _CPU_INST
     import multiprocessing as mp
     from oracle import cref
@@ -686,6 +725,7 @@ def bench_batch_verify(E, total=4096, corrupt_every=97):
     d_V = torch.frombuffer(bytearray(Vc), dtype=torch.uint8).to(dev)
     per = (total + world - 1) // world
     d_acc = torch.zeros(per, dtype=torch.uint8, device=dev)
+    d_all = {"good": torch.zeros(per * world, dtype=torch.uint8, device=dev), "bad": torch.zeros(per * world, dtype=torch.uint8, device=dev)}
     res = {}
 
     def run(d_proofs, key):
@@ -693,7 +733,8 @@ def bench_batch_verify(E, total=4096, corrupt_every=97):
             batch.upload_proofs_ptr(d_proofs.data_ptr(), d_V.data_ptr())      # D2D: proofs + commitments resident in HBM
             batch.verify(None)
             batch.download_accept_ptr(d_acc.data_ptr())
-            res[key] = par.gather_bytes(d_acc, world)                         # NCCL all-gather of the accept bytes
+            be.all_gather_dev(d_acc.data_ptr(), per, d_all[key].data_ptr())   # the library's NCCL communicator (bpp_comm_all_gather_dev)
+            res[key] = d_all[key]
         return step
 
     steps, warm = max(5, args.steps), max(3, args.warmup)
@@ -719,8 +760,8 @@ def bench_batch_verify(E, total=4096, corrupt_every=97):
                "all_valid": {"value": total / (ms_good / steps * 1e-3), "ms_per_step": ms_good / steps},
                "corrupted_over_all_valid": ms_bad / ms_good,
                "rejected": rebuilt.count(b"\x00"), "decisions_match_expected": bool(ok and okg),
-               "note": "value = the batch with corrupted proofs (the combined check fails and is bisected); all_valid = the same "
-                       "batch untouched (one combined check)"}
+               "note": "value = the batch with corrupted proofs (the combined check fails, then every proof is checked on its own: "
+                       "DESIGN.md section 3.2 on why group testing does not pay at 1 %); all_valid = the same batch untouched (one combined check)"}
     batch.free()
     gens.free()
     cir.free()
@@ -862,6 +903,14 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        # one slice of the host cores per rank (round 1: every rank's lane threads roamed over all cores of one NUMA
+        # node and the end-to-end legs lost 22 % at 8 GPUs): the rank's threads and its pinned buffers stay together
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            os.sched_setaffinity(0, set(cores[local * per:(local + 1) * per]) or set(cores))
+        except Exception:
+            pass
     be = bpperm_b200.Backend(local)
     stream = torch.cuda.current_stream(dev)
     be.set_stream(stream.cuda_stream)

@@ -27,7 +27,7 @@ SYMBOLS = [
     "bpp_acproof_prove_batch", "bpp_acproof_verify_batch", "bpp_acp_batch_create", "bpp_acp_batch_free",
     "bpp_acp_batch_upload_witness", "bpp_acp_batch_commit", "bpp_acp_batch_upload_commitments", "bpp_acp_batch_gen_shuffle_witness", "bpp_acp_batch_prove", "bpp_acp_batch_download_proofs",
     "bpp_acp_batch_upload_proofs", "bpp_acp_batch_verify", "bpp_acp_batch_download_accept",
-    "bpp_acp_batch_time_commit_msm", "bpp_acp_batch_set_host_transcripts", "bpp_transcript_script", "bpp_acp_batch_set_batch_rlc", "bpp_acp_batch_set_priority_split",
+    "bpp_acp_batch_time_commit_msm", "bpp_acp_batch_set_host_transcripts", "bpp_transcript_script", "bpp_ipa_fold_generators", "bpp_acp_batch_set_batch_rlc", "bpp_acp_batch_set_priority_split",
 ]
 
 _lib = None
@@ -150,6 +150,7 @@ def load() -> ctypes.CDLL:
     lib.bpp_acp_batch_set_host_transcripts.argtypes = [vp, c.c_int]
     lib.bpp_acp_batch_set_batch_rlc.argtypes = [vp, c.c_int]
     lib.bpp_acp_batch_set_priority_split.argtypes = [vp, c.c_int]
+    lib.bpp_ipa_fold_generators.argtypes = [vp, vp, sz, sz, u8p, u8p, sz, c.c_char_p, c.POINTER(c.c_float)]
     lib.bpp_transcript_script.argtypes = [vp, u8p, sz, c.c_char_p, sz]
     lib.bpp_acp_batch_time_commit_msm.argtypes = [vp, c.c_int, c.POINTER(c.c_float), c.POINTER(c.c_uint64),
                                                   c.POINTER(c.c_uint64)]

@@ -253,6 +253,14 @@ class Backend:
         self._check(self._lib.bpp_points_sum_compress_dev(self._ctx, ctypes.c_void_p(d_partials), g,
                                                           ctypes.c_void_p(d_out32)))
 
+    def ipa_fold_generators(self, points: Points, n: int, u: bytes, uinv: bytes, off: int = 0, want: bool = True):
+        """K7: `folds` foldings G'_i = u^-1 P_i + u P_{i+n/2} of points[off:off+n]; returns (encodings or b"", kernel ms)."""
+        folds = len(u) // 32
+        out = ctypes.create_string_buffer(32 * folds * (n // 2)) if want else None
+        ms = ctypes.c_float()
+        self._check(self._lib.bpp_ipa_fold_generators(self._ctx, points._h, off, n, bytes(u), bytes(uinv), folds, out, ctypes.byref(ms)))
+        return (out.raw if want else b""), ms.value
+
     # -- multi-GPU: the library's own NCCL communicator (one process per GPU) -----------------------------------
     @staticmethod
     def comm_unique_id() -> bytes:

@@ -358,10 +358,19 @@ __global__ void __launch_bounds__(FB_THREADS) k_fb_msm(const uint32_t *__restric
 // One WARP per output point (large batches: B x outs warps fill the GPU): no shared memory, no block barrier - the
 // 32 partial sums meet in five shuffle steps.  (ncu of the block-per-output form, profiles/r1_ncu_full_k_fb_msm.csv:
 // barrier stalls 1.7 per issue from the 7-level shared-memory tree.)
-__global__ void __launch_bounds__(FB_THREADS) k_fb_msm_warp(const uint32_t *__restrict__ blk, acp_layout lay, fb_shape sh,
+// STAGE: the warp first copies the scalars of all its terms into shared memory (coalesced 32-byte loads, one pass), so
+// that the per-item scalar fetch - every FB_GROUP mixed adds, an un-prefetched global load on which the digit extraction
+// waits: 12 % of the warp stall samples in profiles/r2_ncu_full_k_fb_msm_warp.csv - becomes a shared-memory read.
+// Dynamic shared memory: (FB_THREADS / 32) x total_terms x 32 B (the host picks STAGE when that fits 48 KB).
+#ifndef FB_WARP_MINBLOCKS
+#define FB_WARP_MINBLOCKS 4
+#endif
+template <bool STAGE>
+__global__ void __launch_bounds__(FB_THREADS, FB_WARP_MINBLOCKS) k_fb_msm_warp(const uint32_t *__restrict__ blk, acp_layout lay, fb_shape sh,
                                                             const uint32_t *__restrict__ table, int c, int Wn, fb_consts kc,
                                                             uint32_t B, uint32_t outs /* per proof; sh.outs = pitch */,
                                                             uint32_t *__restrict__ out_ext /* [p][pitch] x 32 */) {
+    extern __shared__ __align__(16) uint32_t fb_stage[];
     const uint32_t wid = blockIdx.x * (FB_THREADS / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (wid >= B * outs) return;   // whole warps leave together
     const uint32_t p = wid / outs, o = wid - p * outs;
@@ -370,6 +379,18 @@ __global__ void __launch_bounds__(FB_THREADS) k_fb_msm_warp(const uint32_t *__re
     uint32_t total_terms = 0;
     for (uint32_t s = 0; s < sh.nseg; s++) total_terms += sh.cnt[s];
     const uint32_t items = total_terms * groups;
+    uint32_t *stage = fb_stage + 8 * (size_t)(threadIdx.x >> 5) * total_terms;
+    if (STAGE) {
+        for (uint32_t t = lane; t < total_terms; t += 32) {
+            uint32_t seg = 0, k = t;
+            while (seg + 1 < sh.nseg && k >= sh.cnt[seg]) { k -= sh.cnt[seg]; seg++; }
+            const uint32_t *sp = ACP_PTR(blk, lay, p, sh.sc_off[seg] + o * sh.sc_ostride[seg] + k);
+            const uint4 lo = *reinterpret_cast<const uint4 *>(sp), hi = *reinterpret_cast<const uint4 *>(sp + 4);
+            *reinterpret_cast<uint4 *>(stage + 8 * (size_t)t) = lo;
+            *reinterpret_cast<uint4 *>(stage + 8 * (size_t)t + 4) = hi;
+        }
+        __syncwarp();
+    }
     ge_ext acc;
     ge_identity(acc);
     // Work items (term, group of FB_GROUP windows) are strided over the block; within this thread's items the
@@ -395,7 +416,7 @@ __global__ void __launch_bounds__(FB_THREADS) k_fb_msm_warp(const uint32_t *__re
                     const bool upper = (k & (sh.sel_period - 1)) >= (sh.sel_period >> 1);
                     if ((upper == (o == 0)) != (sh.sel[seg] == 1)) { w = w_end; continue; }
                 }
-                const uint32_t *sp = ACP_PTR(blk, lay, p, sh.sc_off[seg] + o * sh.sc_ostride[seg] + k);
+                const uint32_t *sp = STAGE ? stage + 8 * (size_t)term : ACP_PTR(blk, lay, p, sh.sc_off[seg] + o * sh.sc_ostride[seg] + k);
                 gen = sh.gen[seg] + k;
                 uint4 lo = *reinterpret_cast<const uint4 *>(sp), hi = *reinterpret_cast<const uint4 *>(sp + 4);
                 s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w; s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;

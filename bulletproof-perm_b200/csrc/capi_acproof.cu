@@ -11,6 +11,8 @@
 #include "transcript_kernels.cuh"
 #include "host_merlin.hpp"
 
+#define FB_STAGE_MAX_BYTES (48u * 1024u)   // dynamic shared memory of k_fb_msm_warp<true> without an opt-in attribute
+
 struct bpp_circuit {
     uint32_t n = 0, Q = 0, m = 0, rows = 0, nnz = 0;
     uint32_t *d_rowptr = nullptr, *d_col = nullptr, *d_coeff = nullptr;
@@ -72,6 +74,7 @@ struct bpp_acp_batch {
     // batch verification by random linear combination (k_rlc_*): scalars of the one MSM over the batch's
     // dynamic points + the shared generators (appended to d_dyn), its compressed result, the fall-back flag
     bool batch_rlc = true;
+    bool fb_stage_scalars = true;   // k_fb_msm_warp<true>: the warp's scalars staged in shared memory (BPP_FB_STAGE=0: off)
     uint32_t *d_rlc_sc = nullptr, *d_rlc_flag = nullptr;
     uint8_t *d_rlc_out = nullptr;
     uint32_t *h_rlc_flag = nullptr;
@@ -345,8 +348,12 @@ static int msm_table_run(bpp_ctx *ctx, const uint32_t *d_sc, const bpp_points *P
     memcpy(kc.K, P->fb_K, 32);
     cudaStream_t st = ctx->stream;
     if (count >= 16ull * ctx->sm_count) {
-        k_fb_msm_warp<<<(unsigned)((count + FB_THREADS / 32 - 1) / (FB_THREADS / 32)), FB_THREADS, 0, st>>>(
-            d_sc, lay, sh, P->fb_table, P->fb_c, P->fb_Wn, kc, (uint32_t)count, 1, d_ext);
+        const size_t stage_b = (size_t)(FB_THREADS / 32) * n * 32;
+        const unsigned grid = (unsigned)((count + FB_THREADS / 32 - 1) / (FB_THREADS / 32));
+        if (stage_b <= FB_STAGE_MAX_BYTES)
+            k_fb_msm_warp<true><<<grid, FB_THREADS, stage_b, st>>>(d_sc, lay, sh, P->fb_table, P->fb_c, P->fb_Wn, kc, (uint32_t)count, 1, d_ext);
+        else
+            k_fb_msm_warp<false><<<grid, FB_THREADS, 0, st>>>(d_sc, lay, sh, P->fb_table, P->fb_c, P->fb_Wn, kc, (uint32_t)count, 1, d_ext);
         LAUNCH_CHECK(ctx);
     } else if (sp > 1) {
         k_fb_msm<<<dim3((unsigned)count, 1, sp), FB_THREADS, 0, st>>>(d_sc, lay, sh, P->fb_table, P->fb_c, P->fb_Wn, kc, d_part);
@@ -512,6 +519,7 @@ extern "C" int bpp_acp_batch_create(bpp_ctx *ctx, const bpp_circuit *cir, const 
     b->lay = acp_make_layout(cir->n, cir->Q, cir->m, mode);
     b->proof_len = (uint32_t)bpp_acproof_proof_len_mode(cir->n, mode);
     if (const char *e = getenv("BPP_FB_WARP")) b->fb_warp_per_output = e[0] != '0';
+    if (const char *e = getenv("BPP_FB_STAGE")) b->fb_stage_scalars = e[0] != '0';
     b->label.assign(label, label + label_len);
     const size_t B = count, lg = b->lay.lg, per = cir->m + 8 + 2 * lg, nch = 6 + lg;   // challenges per proof + the two weights
     {   // small batches of large circuits: split each fixed-base MSM over several blocks (k_fb_sum_splits adds them)
@@ -669,8 +677,14 @@ static int acp_fb(bpp_acp_batch *b, const fb_shape &sh, uint32_t *dst, uint32_t 
     if (sp == 1 && b->fb_warp_per_output && blocks >= 16ull * ctx->sm_count) {
         // plenty of outputs: a warp per output (no block tree, no barrier)
         const uint32_t n_out = b->B * sh.outs;
-        k_fb_msm_warp<<<(n_out + FB_THREADS / 32 - 1) / (FB_THREADS / 32), FB_THREADS, 0, st>>>(
-            b->d_blk, b->lay, s, b->gens->d_table, b->gens->c, b->gens->Wn, b->gens->kc, b->B, sh.outs, dst);
+        const size_t stage_b = (size_t)(FB_THREADS / 32) * terms * 32;
+        const unsigned grid = (n_out + FB_THREADS / 32 - 1) / (FB_THREADS / 32);
+        if (stage_b <= FB_STAGE_MAX_BYTES && b->fb_stage_scalars)
+            k_fb_msm_warp<true><<<grid, FB_THREADS, stage_b, st>>>(b->d_blk, b->lay, s, b->gens->d_table, b->gens->c, b->gens->Wn,
+                                                                   b->gens->kc, b->B, sh.outs, dst);
+        else
+            k_fb_msm_warp<false><<<grid, FB_THREADS, 0, st>>>(b->d_blk, b->lay, s, b->gens->d_table, b->gens->c, b->gens->Wn,
+                                                              b->gens->kc, b->B, sh.outs, dst);
         LAUNCH_CHECK(ctx);
     } else if (sp > 1) {
         k_fb_msm<<<dim3(b->B, sh.outs, (uint32_t)sp), FB_THREADS, 0, st>>>(b->d_blk, b->lay, s, b->gens->d_table,
@@ -1348,6 +1362,43 @@ extern "C" int bpp_acp_batch_time_commit_msm(bpp_acp_batch *b, int reps, float *
     if (mixed_adds) *mixed_adds = (uint64_t)b->B * (1 + 2 * L.n) * b->gens->Wn;
     const bool warp_form = b->fb_warp_per_output && (uint64_t)b->B >= 16ull * ctx->sm_count;
     if (full_adds) *full_adds = (uint64_t)b->B * (warp_form ? 31 : FB_THREADS - 1);
+    return BPP_OK;
+}
+
+// K7 as an operator (measurement + parity; see k_ipa_fold_gens): `folds` independent foldings of points[off..off+n)
+// with (u_f, u_f^-1): out[f][i] = u_f^-1 P_i + u_f P_{i + n/2}.  out_enc (host, folds x n/2 x 32, nullable): compressed
+// results; ms (nullable): device time of the folding kernel alone (CUDA events).
+extern "C" int bpp_ipa_fold_generators(bpp_ctx *ctx, const bpp_points *points, size_t off, size_t n, const uint8_t *u,
+                                       const uint8_t *uinv, size_t folds, uint8_t *out_enc, float *ms) {
+    if (!ctx || !points || !u || !uinv || n < 2 || (n & 1) || folds == 0) return BPP_ERR_INVALID_ARG;
+    if (off + n > points->n) return BPP_ERR_LENGTH_MISMATCH;
+    for (size_t i = 0; i < folds; i++)
+        if ((u[32 * i + 31] | uinv[32 * i + 31]) & 0xe0) return BPP_ERR_SCALAR_RANGE;   // reduced scalars (< 2^253)
+    CK(ctx, cudaSetDevice(ctx->device));
+    const size_t half = n / 2, outs = folds * half;
+    if (outs >= (1ull << 31)) return BPP_ERR_INVALID_ARG;
+    int rc;
+    if ((rc = grow(ctx, &ctx->d_small, &ctx->cap_small, folds * 64 + outs * 128 + outs * 32))) return rc;
+    uint8_t *d_u = ctx->d_small, *d_ui = d_u + folds * 32, *d_ext = d_ui + folds * 32, *d_enc = d_ext + outs * 128;
+    CK(ctx, cudaMemcpyAsync(d_u, u, folds * 32, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(d_ui, uinv, folds * 32, cudaMemcpyHostToDevice, ctx->stream));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, ctx->stream);
+    k_ipa_fold_gens<<<(unsigned)((outs + 63) / 64), 64, 0, ctx->stream>>>(points->niels + 24 * off, (uint32_t)half, (const uint32_t *)d_u,
+                                                                         (const uint32_t *)d_ui, (uint32_t)folds, (uint32_t *)d_ext);
+    cudaEventRecord(e1, ctx->stream);
+    LAUNCH_CHECK(ctx);
+    if (out_enc) {
+        k_compress_strided<<<(unsigned)((outs + 127) / 128), 128, 0, ctx->stream>>>((const uint32_t *)d_ext, 1, 0, 1, (uint32_t)outs, d_enc);
+        LAUNCH_CHECK(ctx);
+        CK(ctx, cudaMemcpyAsync(out_enc, d_enc, outs * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ms) cudaEventElapsedTime(ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
     return BPP_OK;
 }
 

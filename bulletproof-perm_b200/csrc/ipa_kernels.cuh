@@ -197,6 +197,69 @@ static inline cudaError_t ipa_round_launch(acp_layout lay, int round, uint32_t *
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, k_ipa_round, lay, round, blk);
 }
+// ---- K7: explicit generator folding (bulletproofs 4.0.0 inner_product_proof.rs create():
+// G'_i = u^-1 G_i + u G_{i + n/2}).  NOT on the prover's path - the rounds above fold the scalars and keep the original
+// generators, whose window tables exist - but built as an operator so that the two forms can be measured against each
+// other per round (tools/ipa_fold_compare.py, profiles/r2_ipa_fold_compare.json) and checked for equality.
+// Thread per (fold f, i < half): a two-scalar Straus multiplication with signed 4-bit digits: tables of 1..8 multiples
+// of both points (extended coordinates, local memory), then 64 windows of 4 doublings + up to 2 additions:
+// 256 doublings + ~134 additions per folded point, against 16 (c = 16) or 32 (c = 8) mixed adds per generator and
+// round in the scalar-folding form.
+SC_INLINE void ipa_signed_digits4(int8_t d[64], const uint32_t s[8]) {   // s < 2^253: 64 digits in [-8, 8)
+    uint32_t carry = 0;
+#pragma unroll 1
+    for (int i = 0; i < 64; i++) {
+        uint32_t v = ((s[i >> 3] >> (4 * (i & 7))) & 15u) + carry;
+        carry = v >= 8u;
+        d[i] = (int8_t)((int)v - (int)(carry << 4));
+    }   // the top nibble of a scalar below 2^253 is at most 1: no carry out
+}
+__global__ void __launch_bounds__(64) k_ipa_fold_gens(const uint32_t *__restrict__ niels /* n x 24: affine Niels */, uint32_t half,
+                                                      const uint32_t *__restrict__ u /* folds x 8 */,
+                                                      const uint32_t *__restrict__ uinv, uint32_t folds,
+                                                      uint32_t *__restrict__ out_ext /* folds x half x 32 */) {
+    const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= folds * half) return;
+    const uint32_t f = id / half, i = id - f * half;
+    ge_ext tab[2][8];
+#pragma unroll 1
+    for (int s = 0; s < 2; s++) {
+        ge_niels q;
+        ge_niels_load(q, niels + 24 * (size_t)(i + s * half));
+        ge_identity(tab[s][0]);
+        ge_madd(tab[s][0], tab[s][0], q, false);
+#pragma unroll 1
+        for (int k = 1; k < 8; k++) ge_madd(tab[s][k], tab[s][k - 1], q, false);
+    }
+    int8_t d_lo[64], d_hi[64];
+    uint32_t sc8[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) sc8[k] = uinv[8 * (size_t)f + k];
+    ipa_signed_digits4(d_lo, sc8);
+#pragma unroll
+    for (int k = 0; k < 8; k++) sc8[k] = u[8 * (size_t)f + k];
+    ipa_signed_digits4(d_hi, sc8);
+    ge_ext acc, t;
+    ge_identity(acc);
+#pragma unroll 1
+    for (int w = 63; w >= 0; w--) {
+        if (w != 63)
+            for (int k = 0; k < 4; k++) ge_double_noinline(acc, acc);
+        const int a = d_lo[w], b = d_hi[w];
+        if (a) {
+            t = tab[0][(a < 0 ? -a : a) - 1];
+            if (a < 0) ge_neg(t, t);
+            ge_add_noinline(acc, acc, t);
+        }
+        if (b) {
+            t = tab[1][(b < 0 ? -b : b) - 1];
+            if (b < 0) ge_neg(t, t);
+            ge_add_noinline(acc, acc, t);
+        }
+    }
+    ge_store(out_ext + 32 * (size_t)id, acc);
+}
+
 // host-transcript path: thread per proof: u_round^-1; both kept in Montgomery form at u[round], uinv[round]
 __global__ void __launch_bounds__(64) k_ipa_uinv(acp_layout lay, uint32_t B, uint32_t round, uint32_t *__restrict__ blk) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;

@@ -315,6 +315,13 @@ int bpp_acp_batch_set_host_transcripts(bpp_acp_batch *b, int on);
  * kernels of this batch - transcripts, power chains, dot products - take SM slots ahead of the GPU-filling kernels of
  * the other batches.  Result-neutral; no effect worth having on a default-priority stream. */
 int bpp_acp_batch_set_priority_split(bpp_acp_batch *b, int on);
+/* K7 (bulletproofs 4.0.0 inner_product_proof.rs create(): G'_i = u^-1 G_i + u G_{i+n/2}) as an operator:
+ * `folds` independent foldings of points[off..off+n) (n even) with scalars u_f, u_f^-1 (folds x 32 each, reduced):
+ * out_enc[f][i] = compress(u_f^-1 P_i + u_f P_{i+n/2}) (host, folds x n/2 x 32, nullable); ms (nullable) = device time of
+ * the folding kernel.  The prover does not use it - it folds the scalars and keeps the tabled generators
+ *  - it exists so the two forms can be measured against each other and checked for equality. */
+int bpp_ipa_fold_generators(bpp_ctx *ctx, const bpp_points *points, size_t off, size_t n, const uint8_t *u, const uint8_t *uinv,
+                            size_t folds, uint8_t *out_enc, float *ms);
 /* merlin::Transcript on the device, scripted (test hook for the Merlin KAT and framing edge cases): records
  * op (1 B: 0 append_message, 1 challenge_bytes) | label_len (1 B) | label | n (4 B LE) | message (op 0);
  * the transcript is Transcript::new(first record's message) when the first record is labelled "dom-sep";

@@ -30,16 +30,54 @@ impl VartimeMultiscalarMul for GpuRistretto {
         let s: Vec<u8> = scalars.into_iter().flat_map(|s| s.borrow().to_bytes().to_vec()).collect();
         let p: Vec<RistrettoPoint> = points.into_iter().collect::<Option<Vec<_>>>()?;
         assert_eq!(s.len() / 32, p.len()); // dalek asserts on the iterators' size hints
-        // RistrettoPoint is a transparent wrapper of EdwardsPoint { X, Y, Z, T: FieldElement51([u64; 5]) }: 160 B
-        let raw = unsafe { std::slice::from_raw_parts(p.as_ptr() as *const u8, p.len() * 160) };
+        // Points cross the boundary as their 32-byte encodings: dalek gives no layout guarantee for RistrettoPoint
+        // (BPP_FMT_DALEK_XYZT exists for builds that pin curve25519-dalek-ng 4.1.1's u64 backend and accept that).
+        // Long-lived generator sets should not come through here at all: see `GeneratorSet` below.
+        let enc: Vec<u8> = p.iter().flat_map(|q| q.compress().to_bytes().to_vec()).collect();
         let mut out = [0u8; 32];
         let rc = with_ctx(|c| unsafe {
-            sys::bpp_msm_vartime_host(c, s.as_ptr(), p.len(), sys::BPP_FMT_DALEK_XYZT, raw.as_ptr(), p.len(), out.as_mut_ptr())
+            sys::bpp_msm_vartime_host(c, s.as_ptr(), p.len(), sys::BPP_FMT_COMPRESSED, enc.as_ptr(), p.len(), out.as_mut_ptr())
         });
         assert_eq!(rc, 0);
         CompressedRistretto(out).decompress()
     }
 }
+
+/// The reference's 15 call sites always multiply sub-ranges of the same generators (g, h, G_vec, H_vec: lib.rs:164-180).
+/// Upload them once, attach the window table once; every later MSM is table look-ups + mixed adds, and
+/// `msm_batch` runs `count` of them (one per proof) in a single launch.
+pub struct GeneratorSet { pts: *mut sys::bpp_points, n: usize }
+unsafe impl Send for GeneratorSet {}
+impl GeneratorSet {
+    pub fn new(points: &[RistrettoPoint], window_bits: i32) -> Self {
+        let enc: Vec<u8> = points.iter().flat_map(|q| q.compress().to_bytes().to_vec()).collect();
+        let mut pts = std::ptr::null_mut();
+        with_ctx(|c| unsafe {
+            assert_eq!(sys::bpp_points_upload(c, sys::BPP_FMT_COMPRESSED, enc.as_ptr(), points.len(), &mut pts), 0);
+            assert_eq!(sys::bpp_points_precompute(c, pts, window_bits), 0);
+        });
+        GeneratorSet { pts, n: points.len() }
+    }
+    /// sum_i scalars[i] * points[off + i]
+    pub fn msm(&self, scalars: &[Scalar], off: usize) -> RistrettoPoint {
+        assert!(off + scalars.len() <= self.n);
+        let mut out = [0u8; 32];
+        let rc = with_ctx(|c| unsafe {
+            sys::bpp_msm_vartime(c, bytes_of(scalars).as_ptr(), scalars.len(), self.pts, off, scalars.len(), out.as_mut_ptr(), std::ptr::null_mut())
+        });
+        assert_eq!(rc, 0);
+        CompressedRistretto(out).decompress().expect("library returns valid encodings")
+    }
+    /// `count` MSMs over points[off..off + n) with count x n scalars (row-major), one launch
+    pub fn msm_batch(&self, scalars: &[Scalar], count: usize, off: usize, n: usize) -> Vec<CompressedRistretto> {
+        assert_eq!(scalars.len(), count * n);
+        let mut out = vec![0u8; 32 * count];
+        let rc = with_ctx(|c| unsafe { sys::bpp_msm_vartime_batch(c, bytes_of(scalars).as_ptr(), count, self.pts, off, n, out.as_mut_ptr()) });
+        assert_eq!(rc, 0);
+        out.chunks_exact(32).map(|c| CompressedRistretto(<[u8; 32]>::try_from(c).unwrap())).collect()
+    }
+}
+impl Drop for GeneratorSet { fn drop(&mut self) { with_ctx(|c| unsafe { sys::bpp_points_free(c, self.pts) }) } }
 
 fn bytes_of(v: &[Scalar]) -> &[u8] { unsafe { std::slice::from_raw_parts(v.as_ptr() as *const u8, v.len() * 32) } }
 
@@ -67,6 +105,78 @@ pub fn exp_iter_take(x: Scalar, n: usize) -> Vec<Scalar> {
     out
 }
 
+fn flatten(m: &Vec<Vec<Scalar>>) -> Vec<u8> { m.iter().flat_map(|r| bytes_of(r).to_vec()).collect() }
+/// util.rs:22-38: out[i] = <a, b[i]> (b: rows of length a.len())
+pub fn vm_mult(a: &Vec<Scalar>, b: &Vec<Vec<Scalar>>) -> Vec<Scalar> {
+    if a.len() != b[0].len() { panic!("vm_mult(a,b): a -> 1x{}, b -> {}x{} needs to be", a.len(), b[0].len(), b.len()); }
+    let mut out = vec![Scalar::zero(); b.len()];
+    let flat = flatten(b);
+    let rc = with_ctx(|c| unsafe { sys::bpp_vm_mult(c, bytes_of(a).as_ptr(), a.len(), flat.as_ptr(), b.len(), b[0].len(), out.as_mut_ptr() as *mut u8) });
+    assert_eq!(rc, 0);
+    out
+}
+/// util.rs:58-61
+pub fn lm_mult(a: &[Scalar], b: &Vec<Vec<Scalar>>) -> Vec<Scalar> { vm_mult(&Vec::from(a), b) }
+/// util.rs:40-56: out[i] = sum_j a[j][i] * b[j]
+pub fn mv_mult(a: &Vec<Vec<Scalar>>, b: &Vec<Scalar>) -> Vec<Scalar> {
+    if a.len() != b.len() { panic!("mv_mult(a,b): a->{}x{}, b->{}x1 needs to be", a.len(), a[0].len(), b.len()); }
+    let mut out = vec![Scalar::zero(); a[0].len()];
+    let flat = flatten(a);
+    let rc = with_ctx(|c| unsafe { sys::bpp_mv_mult(c, flat.as_ptr(), a.len(), a[0].len(), bytes_of(b).as_ptr(), b.len(), out.as_mut_ptr() as *mut u8) });
+    assert_eq!(rc, 0);
+    out
+}
+/// util.rs:67-82 (scalar_exp and scalar_exp_u): x^pow by repeated multiplication; pow <= 0 gives one
+pub fn scalar_exp(x: &Scalar, pow: i32) -> Scalar {
+    let mut out = [0u8; 32];
+    let rc = with_ctx(|c| unsafe { sys::bpp_scalar_exp(c, x.as_bytes().as_ptr(), pow.max(0) as u32, out.as_mut_ptr()) });
+    assert_eq!(rc, 0);
+    Scalar::from_canonical_bytes(out).unwrap()
+}
+pub fn scalar_exp_u(x: &Scalar, pow: usize) -> Scalar { scalar_exp(x, pow as i32) }
+/// circuit_lib.rs:273-275: y_n.iter().map(|k| k.invert()) - all inversions in one launch (0 -> 0 like Scalar::invert)
+pub fn invert_all(v: &[Scalar]) -> Vec<Scalar> {
+    let mut out = vec![Scalar::zero(); v.len()];
+    let rc = with_ctx(|c| unsafe { sys::bpp_scalar_invert(c, bytes_of(v).as_ptr(), v.len(), out.as_mut_ptr() as *mut u8) });
+    assert_eq!(rc, 0);
+    out
+}
+/// poly.rs:5-18
+pub struct Poly6 { pub t1: Scalar, pub t2: Scalar, pub t3: Scalar, pub t4: Scalar, pub t5: Scalar, pub t6: Scalar }
+impl Poly6 {
+    pub fn eval(&self, x: Scalar) -> Scalar {
+        let t = [self.t1, self.t2, self.t3, self.t4, self.t5, self.t6];
+        let mut out = [0u8; 32];
+        let rc = with_ctx(|c| unsafe { sys::bpp_poly6_eval(c, bytes_of(&t).as_ptr(), x.as_bytes().as_ptr(), out.as_mut_ptr()) });
+        assert_eq!(rc, 0);
+        Scalar::from_canonical_bytes(out).unwrap()
+    }
+}
+/// poly.rs:21-76
+#[derive(Clone, Debug, Default)]
+pub struct VecPoly3(pub Vec<Scalar>, pub Vec<Scalar>, pub Vec<Scalar>, pub Vec<Scalar>);
+impl VecPoly3 {
+    pub fn zero(n: usize) -> Self { VecPoly3(vec![Scalar::zero(); n], vec![Scalar::zero(); n], vec![Scalar::zero(); n], vec![Scalar::zero(); n]) }
+    fn flat(&self) -> Vec<u8> { [&self.0, &self.1, &self.2, &self.3].iter().flat_map(|v| bytes_of(v).to_vec()).collect() }
+    /// poly.rs:39-55 (the six sums as the reference codes them)
+    pub fn special_inner_product(lhs: &Self, rhs: &Self) -> Poly6 {
+        let (l, r) = (lhs.flat(), rhs.flat());
+        let mut t = [Scalar::zero(); 6];
+        let rc = with_ctx(|c| unsafe { sys::bpp_vecpoly3_special_inner_product(c, l.as_ptr(), r.as_ptr(), lhs.0.len(), t.as_mut_ptr() as *mut u8) });
+        assert_eq!(rc, 0);
+        Poly6 { t1: t[0], t2: t[1], t3: t[2], t4: t[3], t5: t[4], t6: t[5] }
+    }
+    /// poly.rs:57-76 (eval and eval_ref)
+    pub fn eval(&self, x: Scalar) -> Vec<Scalar> { self.eval_ref(&x) }
+    pub fn eval_ref(&self, x: &Scalar) -> Vec<Scalar> {
+        let mut out = vec![Scalar::zero(); self.0.len()];
+        let f = self.flat();
+        let rc = with_ctx(|c| unsafe { sys::bpp_vecpoly3_eval(c, f.as_ptr(), self.0.len(), x.as_bytes().as_ptr(), out.as_mut_ptr() as *mut u8) });
+        assert_eq!(rc, 0);
+        out
+    }
+}
+
 /// `count` ACProvers sharing one ACEssentials (circuit_lib.rs:58-88), proved and verified in lock-step.
 pub struct ShuffleBatch { b: *mut sys::bpp_acp_batch, count: usize, proof_len: usize }
 impl ShuffleBatch {
@@ -76,23 +186,48 @@ impl ShuffleBatch {
         assert_eq!(rc, 0);
         ShuffleBatch { b, count, proof_len: unsafe { sys::bpp_acproof_proof_len_mode(n, mode) } }
     }
-    /// create .. blinding_values (lib.rs:219-228); seeds: ChaCha20Rng::from_seed per proof instead of thread_rng()
-    pub fn prove(&mut self, a_l: &[Scalar], a_r: &[Scalar], a_o: &[Scalar], gamma: &[Scalar], seeds: &[[u8; 32]]) -> Vec<u8> {
+    /// weights.rs:38-113 on the device: the witness of `count` shuffles from the deck, one permutation and one challenge
+    /// value per proof; returns the value commitments V (commit_variables, weights.rs:58-61), which stay resident.
+    pub fn witness_from_shuffles(&mut self, deck: &[Scalar], perm: &[u32], x: &[Scalar], gamma: &[Scalar], seeds: &[[u8; 32]],
+                                 m: usize) -> Vec<CompressedRistretto> {
+        let mut v = vec![0u8; 32 * m * self.count];
+        unsafe {
+            assert_eq!(sys::bpp_acp_batch_gen_shuffle_witness(self.b, bytes_of(deck).as_ptr(), perm.as_ptr(), bytes_of(x).as_ptr(),
+                                                              bytes_of(gamma).as_ptr(), seeds.as_ptr() as *const u8), 0);
+            assert_eq!(sys::bpp_acp_batch_commit(self.b, std::ptr::null(), v.as_mut_ptr()), 0);
+        }
+        v.chunks_exact(32).map(|c| CompressedRistretto(<[u8; 32]>::try_from(c).unwrap())).collect()
+    }
+    /// prove the witness left by `witness_from_shuffles`
+    pub fn prove_resident(&mut self) -> Vec<u8> {
         let mut proofs = vec![0u8; self.count * self.proof_len];
         unsafe {
-            assert_eq!(sys::bpp_acp_batch_upload_witness(self.b, bytes_of(a_l).as_ptr(), bytes_of(a_r).as_ptr(), bytes_of(a_o).as_ptr(),
-                                                         bytes_of(gamma).as_ptr(), seeds.as_ptr() as *const u8), 0);
             assert_eq!(sys::bpp_acp_batch_prove(self.b), 0);
             assert_eq!(sys::bpp_acp_batch_download_proofs(self.b, proofs.as_mut_ptr()), 0);
         }
         proofs
     }
-    /// verify (lib.rs:230): one Result per proof
-    pub fn verify(&mut self, proofs: &[u8], v: &[CompressedRistretto], verifier_seed: &[u8; 32]) -> Vec<Result<(), ProofError>> {
+    /// create .. blinding_values (lib.rs:219-228); seeds: ChaCha20Rng::from_seed per proof instead of thread_rng();
+    /// v: the value commitments (count x m), bound to every transcript in modes 1 and 2
+    pub fn prove(&mut self, a_l: &[Scalar], a_r: &[Scalar], a_o: &[Scalar], gamma: &[Scalar], seeds: &[[u8; 32]],
+                 v: &[CompressedRistretto]) -> Vec<u8> {
+        let mut proofs = vec![0u8; self.count * self.proof_len];
+        unsafe {
+            assert_eq!(sys::bpp_acp_batch_upload_witness(self.b, bytes_of(a_l).as_ptr(), bytes_of(a_r).as_ptr(), bytes_of(a_o).as_ptr(),
+                                                         bytes_of(gamma).as_ptr(), seeds.as_ptr() as *const u8), 0);
+            assert_eq!(sys::bpp_acp_batch_upload_commitments(self.b, v.as_ptr() as *const u8), 0);
+            assert_eq!(sys::bpp_acp_batch_prove(self.b), 0);
+            assert_eq!(sys::bpp_acp_batch_download_proofs(self.b, proofs.as_mut_ptr()), 0);
+        }
+        proofs
+    }
+    /// verify (lib.rs:230): one Result per proof.  verifier_seed: 32 bytes of SECRET, FRESH randomness (e.g. from
+    /// `thread_rng()`), or None to have the library draw them from the operating system; never a constant.
+    pub fn verify(&mut self, proofs: &[u8], v: &[CompressedRistretto], verifier_seed: Option<&[u8; 32]>) -> Vec<Result<(), ProofError>> {
         let mut acc = vec![0u8; self.count];
         unsafe {
             assert_eq!(sys::bpp_acp_batch_upload_proofs(self.b, proofs.as_ptr(), v.as_ptr() as *const u8), 0);
-            assert_eq!(sys::bpp_acp_batch_verify(self.b, verifier_seed.as_ptr()), 0);
+            assert_eq!(sys::bpp_acp_batch_verify(self.b, verifier_seed.map_or(std::ptr::null(), |s| s.as_ptr())), 0);
             assert_eq!(sys::bpp_acp_batch_download_accept(self.b, acc.as_mut_ptr()), 0);
         }
         acc.into_iter().map(|a| if a == 1 { Ok(()) } else { Err(ProofError::VerificationError) }).collect()

@@ -46,6 +46,24 @@ extern "C" {
                                n: usize, d_partial: *mut core::ffi::c_void) -> c_int;
     pub fn bpp_points_sum_compress_dev(ctx: *mut bpp_ctx, d_partials: *const core::ffi::c_void, g: usize,
                                        d_out32: *mut core::ffi::c_void) -> c_int;
+    // long-lived point sets: window table once, then small MSMs and `count` MSMs per launch without buckets or doublings
+    pub fn bpp_points_precompute(ctx: *mut bpp_ctx, points: *mut bpp_points, window_bits: c_int) -> c_int;
+    pub fn bpp_msm_vartime_batch(ctx: *mut bpp_ctx, scalars: *const u8, count: usize, points: *mut bpp_points, off: usize, n: usize,
+                                 out32: *mut u8) -> c_int;
+    pub fn bpp_msm_vartime_batch_dev(ctx: *mut bpp_ctx, d_scalars: *const core::ffi::c_void, count: usize, points: *mut bpp_points,
+                                     off: usize, n: usize, d_out32: *mut core::ffi::c_void) -> c_int;
+    // multi-GPU: one process per GPU, NCCL inside the library
+    pub fn bpp_comm_unique_id(id: *mut u8) -> c_int;                      // 128 bytes, made on rank 0
+    pub fn bpp_comm_init(ctx: *mut bpp_ctx, nranks: c_int, rank: c_int, id: *const u8) -> c_int;
+    pub fn bpp_comm_free(ctx: *mut bpp_ctx) -> c_int;
+    pub fn bpp_comm_info(ctx: *mut bpp_ctx, nranks: *mut c_int, rank: *mut c_int) -> c_int;
+    pub fn bpp_comm_all_gather_dev(ctx: *mut bpp_ctx, d_send: *const core::ffi::c_void, bytes_per_rank: usize,
+                                   d_recv: *mut core::ffi::c_void) -> c_int;
+    pub fn bpp_msm_sharded_dev(ctx: *mut bpp_ctx, d_scalars: *const core::ffi::c_void, points: *const bpp_points, off: usize,
+                               n: usize, d_out32: *mut core::ffi::c_void) -> c_int;
+    pub fn bpp_msm_sharded_submit_dev(ctx: *mut bpp_ctx, d_scalars: *const core::ffi::c_void, points: *const bpp_points, off: usize,
+                                      n: usize, d_out32: *mut core::ffi::c_void) -> c_int;
+    pub fn bpp_msm_sharded_wait(ctx: *mut bpp_ctx) -> c_int;
     // result-neutral tuning hooks
     pub fn bpp_set_window_bits(ctx: *mut bpp_ctx, c: c_int) -> c_int;
     pub fn bpp_set_msm_groups(ctx: *mut bpp_ctx, groups: c_int) -> c_int;
@@ -58,6 +76,8 @@ extern "C" {
     pub fn bpp_exp_iter(ctx: *mut bpp_ctx, x: *const u8, count: usize, out: *mut u8) -> c_int;
     pub fn bpp_scalar_exp(ctx: *mut bpp_ctx, x: *const u8, pow: u32, out: *mut u8) -> c_int;
     pub fn bpp_scalar_invert(ctx: *mut bpp_ctx, a: *const u8, n: usize, out: *mut u8) -> c_int;
+    pub fn bpp_scalar_powers(ctx: *mut bpp_ctx, x: *const u8, first: usize, count: usize, out: *mut u8) -> c_int;
+    pub fn bpp_scalar_reduce(ctx: *mut bpp_ctx, in32: *const u8, n: usize, out: *mut u8) -> c_int;
     pub fn bpp_scalar_from_wide(ctx: *mut bpp_ctx, in64: *const u8, n: usize, out: *mut u8) -> c_int;
     pub fn bpp_vecpoly3_special_inner_product(ctx: *mut bpp_ctx, lhs: *const u8, rhs: *const u8, n: usize, out: *mut u8) -> c_int;
     pub fn bpp_vecpoly3_eval(ctx: *mut bpp_ctx, coeffs: *const u8, n: usize, x: *const u8, out: *mut u8) -> c_int;
@@ -65,6 +85,8 @@ extern "C" {
 
     pub fn bpp_circuit_create(ctx: *mut bpp_ctx, n: usize, q: usize, m: usize, nnz: *const u32, wire: *const u32,
                               constraint: *const u32, coeff: *const u8, c_vec: *const u8, out: *mut *mut bpp_circuit) -> c_int;
+    /// weights.rs:130-204 replaced: the corrected k-card shuffle circuit built inside the library
+    pub fn bpp_circuit_create_shuffle(ctx: *mut bpp_ctx, k: usize, out: *mut *mut bpp_circuit) -> c_int;
     pub fn bpp_circuit_free(ctx: *mut bpp_ctx, c: *mut bpp_circuit);
     pub fn bpp_gens_create(ctx: *mut bpp_ctx, g: *const u8, h: *const u8, g_vec: *const u8, h_vec: *const u8, n: usize,
                            window_bits: c_int, out: *mut *mut bpp_gens) -> c_int;
@@ -75,9 +97,10 @@ extern "C" {
     pub fn bpp_acproof_to_wire(n: usize, mode: c_int, count: usize, proofs: *const u8, wire_out: *mut u8) -> c_int;
     pub fn bpp_acproof_from_wire(n: usize, mode: c_int, count: usize, wire: *const u8, wire_len: usize,
                                  proofs_out: *mut u8, status: *mut u8) -> c_int;
+    /// v: count x m x 32 compressed commitments - required in modes 1 and 2 (bound to every transcript), null in mode 0
     pub fn bpp_acproof_prove_batch(ctx: *mut bpp_ctx, cir: *const bpp_circuit, gens: *const bpp_gens, mode: c_int, count: usize,
                                    a_l: *const u8, a_r: *const u8, a_o: *const u8, gamma: *const u8, seeds: *const u8,
-                                   label: *const u8, label_len: usize, proofs_out: *mut u8) -> c_int;
+                                   v: *const u8, label: *const u8, label_len: usize, proofs_out: *mut u8) -> c_int;
     pub fn bpp_acproof_verify_batch(ctx: *mut bpp_ctx, cir: *const bpp_circuit, gens: *const bpp_gens, mode: c_int, count: usize,
                                     proofs: *const u8, v: *const u8, label: *const u8, label_len: usize,
                                     verifier_seed: *const u8, accept: *mut u8) -> c_int;
@@ -86,7 +109,14 @@ extern "C" {
     pub fn bpp_acp_batch_free(b: *mut bpp_acp_batch);
     pub fn bpp_acp_batch_upload_witness(b: *mut bpp_acp_batch, a_l: *const u8, a_r: *const u8, a_o: *const u8,
                                         gamma: *const u8, seeds: *const u8) -> c_int;
+    /// weights.rs:38-113 replaced: a_L, a_R, a_O and v = deck | deck[perm] | x computed on the device
+    pub fn bpp_acp_batch_gen_shuffle_witness(b: *mut bpp_acp_batch, deck: *const u8, perm: *const u32, x: *const u8,
+                                             gamma: *const u8, seeds: *const u8) -> c_int;
+    /// v nullable: commit to the values left by bpp_acp_batch_gen_shuffle_witness
     pub fn bpp_acp_batch_commit(b: *mut bpp_acp_batch, v: *const u8, v_out: *mut u8) -> c_int;
+    pub fn bpp_acp_batch_upload_commitments(b: *mut bpp_acp_batch, v: *const u8) -> c_int;
+    /// sharded batch verification: all ranks' accept bytes (nranks x per) through the library's communicator
+    pub fn bpp_acp_batch_gather_accept(b: *mut bpp_acp_batch, per: usize, accept_all: *mut u8) -> c_int;
     pub fn bpp_acp_batch_prove(b: *mut bpp_acp_batch) -> c_int;
     pub fn bpp_acp_batch_download_proofs(b: *mut bpp_acp_batch, proofs_out: *mut u8) -> c_int;
     pub fn bpp_acp_batch_upload_proofs(b: *mut bpp_acp_batch, proofs: *const u8, v: *const u8) -> c_int;

@@ -77,3 +77,41 @@ def test_null_arguments_are_rejected_without_a_device():
     assert lib.bpp_strerror(-3).decode() == "invalid argument"
     assert lib.bpp_acproof_proof_len_mode(104, 2) == 32 * (13 + 2 * 7)
     assert lib.bpp_acproof_proof_len_mode(104, 1) == 32 * (11 + 208)
+
+
+def _header_functions():
+    """name -> parameter count, parsed from include/bpperm.h (comments stripped)."""
+    import re
+    txt = open(os.path.join(ROOT, "include", "bpperm.h")).read()
+    txt = re.sub(r"/\*.*?\*/", " ", txt, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(bpp_\w+)\s*\(([^;{]*?)\)\s*;", txt, flags=re.S):
+        args = m.group(2).strip()
+        out[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    return out
+
+
+def test_every_header_function_is_exported_and_listed():
+    import bpperm_b200
+    lib = bpperm_b200.load()
+    fns = _header_functions()
+    assert len(fns) > 80
+    missing = [f for f in fns if not hasattr(lib, f)]
+    assert not missing, missing
+    unlisted = [f for f in fns if f not in bpperm_b200.SYMBOLS]
+    assert not unlisted, unlisted
+
+
+def test_rust_extern_block_agrees_with_the_header():
+    """rust/bpperm-sys is never compiled here; at least every `pub fn` it declares exists in the header with the same
+    number of parameters."""
+    import re
+    fns = _header_functions()
+    src = open(os.path.join(ROOT, "rust", "bpperm-sys", "src", "lib.rs")).read()
+    src = re.sub(r"//[^\n]*", "", src)
+    decl = re.findall(r"pub fn (bpp_\w+)\s*\(([^)]*)\)", src, flags=re.S)
+    assert len(decl) > 60
+    for name, args in decl:
+        assert name in fns, name
+        n = 0 if not args.strip() else len([a for a in args.split(",") if a.strip()])
+        assert n == fns[name], (name, n, fns[name])

@@ -226,3 +226,28 @@ def test_wire_records_parse_then_verify(backend):
         pb = W.from_bytes(bytes(recs[i * wlen:(i + 1) * wlen]), n, 2)
         want = 0 if pb is None else int(bool(ipa.verify(core, V, pb)))
         assert acc[i] == want, i
+
+
+def test_generator_fold_operator_matches_the_oracle_and_the_scalar_fold_form(backend):
+    """K7 (G'_i = u^-1 G_i + u G_{i+n/2}) against big-int arithmetic, and - the equivalence the prover relies on - an MSM
+    over the folded generators against the MSM over the ORIGINAL generators with the folded scalars (a_i u^-1 | a_i u)."""
+    n = 16
+    rng = ChaChaRng(b"\x5c" * 32)
+    pts = [rng.point() for _ in range(n)]
+    enc = [R.compress(p) for p in pts]
+    us = [rng.scalar() for _ in range(3)] + [1, L - 1]
+    uis = [R.sc_inv(u) for u in us]
+    table = backend.upload_points(enc)
+    out, ms = backend.ipa_fold_generators(table, n, _sb(us), _sb(uis))
+    half = n // 2
+    assert ms > 0 and len(out) == 32 * len(us) * half
+    for f, (u, ui) in enumerate(zip(us, uis)):
+        for i in range(half):
+            want = R.compress(R.pt_add(R.pt_mul(ui, pts[i]), R.pt_mul(u, pts[i + half])))
+            assert out[32 * (f * half + i):32 * (f * half + i + 1)] == want, (f, i)
+    a = [rng.scalar() for _ in range(half)]
+    folded = [out[32 * i:32 * i + 32] for i in range(half)]                       # fold 0
+    lhs = backend.vartime_multiscalar_mul(_sb(a), folded)
+    rhs = backend.vartime_multiscalar_mul(_sb([x * uis[0] % L for x in a] + [x * us[0] % L for x in a]), enc)
+    assert lhs == rhs
+    table.free()

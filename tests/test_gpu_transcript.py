@@ -149,3 +149,47 @@ def test_batch_rlc_verification_matches_per_proof_decisions(backend, mode):
         if needs_msm:   # (a flipped byte of r already fails t == <l, r>: weight 0, no fall-back needed)
             assert n1 > n_rlc     # the combined check failed and the per-proof kernels ran
     batch.free()
+
+
+def test_offsets_that_cancelled_under_the_round_1_weights_are_rejected(backend):
+    """the round-1 verifier drew its per-proof weight w_p and batch weight rho_p from
+    ChaCha20(verifier_seed, block p) alone.  Whoever knew the seed could give two proofs of one batch tau_x offsets
+    d_0, d_1 with rho_0 w_0 d_0 + rho_1 w_1 d_1 = 0 - the h-coefficient of the combined check is sum_p rho_p (w_p tau_x_p
+    - mu_p) - and both were accepted.  The weights are now challenge scalars of each proof's own transcript (which has
+    absorbed V and every proof byte) rekeyed with the seed: the same crafted pair, under the same publicly known seed,
+    must be rejected, with the combined check and per proof."""
+    from bpperm_b200 import acproof as G
+    from oracle.chacha import chacha20_block
+    k = 4
+    core, prover, V = A.make_instance(k, ChaChaRng(bytes([123]) * 32))
+    n, m = core["n"], core["m"]
+    WL, WR, WO, WV = core["sparse"]
+    cir = G.Circuit(backend, n, core["Q"], m, WL, WR, WO, WV, core["c_vec"])
+    gens = G.Generators(backend, R.compress(core["g_base"]), R.compress(core["h_base"]),
+                        [R.compress(p) for p in core["G_vec"]], [R.compress(p) for p in core["H_vec"]])
+    B = 64
+    sb = lambda v: b"".join(R.sc_bytes(s) for s in v)
+    seeds = b"".join(bytes([i + 1]) * 32 for i in range(B))
+    Vc = b"".join(R.compress(p) for p in V) * B
+    batch = G.Batch(backend, cir, gens, B, "reference-fixed", b"test")
+    batch.upload_witness(sb(prover["a_L"]) * B, sb(prover["a_R"]) * B, sb(prover["a_O"]) * B, sb(prover["gamma"]) * B, seeds)
+    batch.upload_commitments(Vc)
+    batch.prove()
+    proofs = bytearray(batch.download_proofs())
+    plen = batch.proof_len
+    seed = b"\x33" * 32                      # known to the attacker
+    old_w = [R.sc_from_wide(chacha20_block(seed, p, 0)) for p in range(2)]      # round-1 k_acp_weights: stream word 0
+    old_rho = [R.sc_from_wide(chacha20_block(seed, p, 1)) for p in range(2)]    # round-1 k_rlc_weights: stream word 1
+    d0 = 0x1234567
+    d1 = (-old_rho[0] * old_w[0] * d0) * R.sc_inv(old_rho[1] * old_w[1] % R.L) % R.L
+    for p, d in ((0, d0), (1, d1)):
+        off = p * plen + 32 * 8             # tau_x: field 8 of a mode-1 proof
+        t = (int.from_bytes(proofs[off:off + 32], "little") + d) % R.L
+        proofs[off:off + 32] = R.sc_bytes(t)
+    for rlc in (True, False):
+        batch.set_batch_rlc(rlc)
+        batch.upload_proofs(bytes(proofs), Vc)
+        batch.verify(seed)
+        acc = batch.download_accept()
+        assert list(acc[:2]) == [0, 0] and acc[2:] == b"\x01" * (B - 2), rlc
+    batch.free()
