@@ -803,8 +803,18 @@ def bench_small_msm(E):
         for _ in range(R):
             cref.msm(scb, cp)
         t_cpu = (time.time() - t0) / R
-        row = {"points": npts, "host_call_us": t_host * 1e6, "resident_points_call_us": t_res * 1e6, "cpu_restatement_us": t_cpu * 1e6,
-               "matches_cpu": got == want and got_res == want}
+        t0 = time.time()
+        be.precompute(pts, 8)                 # window table of the point set, once (c = 8)
+        t_table = time.time() - t0
+        for _ in range(3):
+            got_tab = be.vartime_multiscalar_mul(scb, pts)
+        t0 = time.time()
+        for _ in range(R):
+            got_tab = be.vartime_multiscalar_mul(scb, pts)
+        t_tab = (time.time() - t0) / R
+        row = {"points": npts, "host_call_us": t_host * 1e6, "resident_points_call_us": t_res * 1e6,
+               "precomputed_points_call_us": t_tab * 1e6, "precompute_once_ms": t_table * 1e3, "cpu_restatement_us": t_cpu * 1e6,
+               "matches_cpu": got == want and got_res == want and got_tab == want}
         cnt = 4096
         scs = rs.randint(0, 256, size=(cnt * npts, 32), dtype=np.uint8)
         scs[:, 31] &= 0x0F
@@ -818,8 +828,11 @@ def bench_small_msm(E):
         row["batch_first_matches_cpu"] = outs[:32] == cref.msm(scs[:npts].tobytes(), cp)
         rows.append(row)
         pts.free()
-    return {"note": "wall clock around the public call (host buffers in and out, one synchronisation per call); batch = "
-                    "bpp_msm_vartime_batch: 4096 MSMs over the same points with different scalars in one launch",
+    return {"note": "wall clock around the public call (host buffers in and out, one synchronisation per call): host_call = "
+                    "bpp_msm_vartime_host (points sent, decompressed and bucket-sorted every call, 253 dependent doublings); "
+                    "resident_points = bpp_msm_vartime over uploaded points; precomputed_points = the same after "
+                    "bpp_points_precompute (table look-ups + mixed adds, no doublings); batch = bpp_msm_vartime_batch: 4096 MSMs "
+                    "over the same points with different scalars in one launch",
             "cpu_cores": 1, "rows": rows}
 
 
@@ -1057,6 +1070,21 @@ def run_ours(args):
         else:
             got = [bytes(smsm.d_outs[(msm_steps - 2 + i) % 3][:32].cpu().numpy().tobytes()) for i in range(2)]
         assert got == want, "submitted MSM results differ from the single-call results"
+        sharded_check = None
+        if world > 1:
+            # independent of the library's communicator: every rank's partial point (bpp_msm_partial_dev) all-gathered by
+            # torch.distributed, summed and compressed by one rank-local kernel - must be the sharded call's result
+            d_part = torch.zeros(128, dtype=torch.uint8, device=dev)
+            d_allp = torch.zeros(128 * world, dtype=torch.uint8, device=dev)
+            d_chk = torch.zeros(32, dtype=torch.uint8, device=dev)
+            last = d_sets[(args.warmup + msm_steps - 1) % n_sets]
+            be.msm_partial_dev(last.data_ptr(), table, 0, n, d_part.data_ptr())
+            stream.synchronize()
+            dist.all_gather_into_tensor(d_allp, d_part)
+            torch.cuda.synchronize()
+            be.points_sum_compress_dev(d_allp.data_ptr(), world, d_chk.data_ptr())
+            sharded_check = bytes(d_chk.cpu().numpy().tobytes()) == want[1]
+            assert sharded_check, "sharded MSM (library NCCL) differs from partials gathered by torch.distributed"
         clocks2 = samp2.stop() if (rank == 0 and args.workload == "msm") else None
         ms_e2e_serial = timed(msm_e2e, msm_steps, args.warmup)
         # e2e, double buffered: the next step's scalars travel on a copy stream while this step's MSM runs
@@ -1154,7 +1182,8 @@ def run_ours(args):
                            "scalars": "uniform < 2^252, 4 rotating sets",
                            "l2": "96 MiB table + 32 MiB scalars + 100 MiB sort scratch + 64 MiB buckets > 126 MB L2",
                            "parallelism": f"points sharded over {world} GPUs, one NCCL all-gather of 128 B/rank" if world > 1 else "single GPU",
-                           "result": bytes(d_out[:32].cpu().numpy().tobytes()).hex()},
+                           "result": bytes(d_out[:32].cpu().numpy().tobytes()).hex(),
+                           "sharded_result_equals_partials_gathered_by_torch": sharded_check},
                 "e2e": {"value": total_points * msm_steps / (ms_e2e * 1e-3), "unit": "points/s", "h2d_bytes_per_step": n * 32,
                         "d2h_bytes_per_step": 32, "ms_per_step": ms_e2e / msm_steps,
                         "serial": {"value": total_points * msm_steps / (ms_e2e_serial * 1e-3), "ms_per_step": ms_e2e_serial / msm_steps},

@@ -100,7 +100,8 @@ __global__ void __launch_bounds__(WIT_THREADS) k_shuffle_witness(const uint32_t 
     __shared__ __align__(16) uint32_t sh[2][WIT_THREADS * 8];
     const uint32_t c = blockIdx.x, p = blockIdx.y, tid = threadIdx.x;
     const uint32_t gb = c * (k - 1), vb = c * k, len = k - 1;      // factors f_i = v[vb + i + 1] - x, i < len
-    const uint32_t run = (len + WIT_THREADS - 1) / WIT_THREADS, i0 = tid * run, i1 = min(len, i0 + run);
+    const uint32_t T = blockDim.x;   // a power of two <= WIT_THREADS: 64 threads for a 52-card chain, 256 for long ones
+    const uint32_t run = (len + T - 1) / T, i0 = tid * run, i1 = min(len, i0 + run);
     const uint32_t *pp = perm + (size_t)p * k;
     uint32_t *vp = vout + 8 * (size_t)p * lay.m;
     sc x, one, r2;
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(WIT_THREADS) k_shuffle_witness(const uint32_t 
     sc_const(r2, SC_R2);
     auto value = [&](uint32_t j) {      // v[vb + j], also written out
         sc v;
+        BPP_ASSERT(j < k && (!c || pp[j] < k));
         sc_load(v, deck + 8 * (size_t)(c ? pp[j] : j));
         sc_store(vp + 8 * (size_t)(vb + j), v);
         return v;
@@ -143,7 +145,7 @@ __global__ void __launch_bounds__(WIT_THREADS) k_shuffle_witness(const uint32_t 
     int cur = 0;
     sc_store(sh[0] + 8 * tid, acc);
     __syncthreads();
-    for (uint32_t d = 1; d < WIT_THREADS; d <<= 1) {
+    for (uint32_t d = 1; d < T; d <<= 1) {
         sc a, b2;
         sc_load(a, sh[cur] + 8 * tid);
         if (tid >= d) {
@@ -437,6 +439,7 @@ __global__ void __launch_bounds__(FB_THREADS, FB_WARP_MINBLOCKS) k_fb_msm_warp(c
             int d = (ww + 1 == (uint32_t)Wn) ? (int)u : (int)u - (int)half;
             if (d == 0) continue;
             uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+            BPP_ASSERT(mag >= 1 && mag <= half && ww < (uint32_t)Wn && it < items);
             ptr = table + FB_ENTRY_U32 * (((size_t)gen * Wn + ww) * half + (mag - 1));
             neg = d < 0;
             return true;
@@ -612,6 +615,7 @@ struct acp_csr {
 #define ACP_CSR_LONG 64
 SC_INLINE void acp_csr_term(sc &acc, const acp_csr &W, const uint32_t *zq, uint32_t e) {
     sc z, t, cf;
+    BPP_ASSERT(e < W.rowptr[W.rows]);
     sc_load(z, zq + 8 * (size_t)W.col[e]);
     const uint8_t k = W.kind[e];
     if (k == 1) sc_add(acc, acc, z);
@@ -637,6 +641,7 @@ __global__ void __launch_bounds__(128) k_acp_csr_long(acp_csr W, const uint32_t 
                                                       uint32_t *__restrict__ blk) {
     __shared__ __align__(16) uint32_t sh[32 * 8];
     const uint32_t r = long_rows[blockIdx.x], p = blockIdx.y;
+    BPP_ASSERT(r < W.rows);
     const uint32_t *zq = ACP_PTR(blk, lay, p, lay.zq);
     sc acc, tot;
     sc_set0(acc);

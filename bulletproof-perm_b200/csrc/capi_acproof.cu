@@ -765,7 +765,9 @@ extern "C" int bpp_acp_batch_gen_shuffle_witness(bpp_acp_batch *b, const uint8_t
     CK(ctx, cudaMemcpyAsync(b->d_seeds, seeds, (size_t)B * 32, cudaMemcpyHostToDevice, ctx->stream));
     k_acp_place_gamma<<<dim3((L.m + 127) / 128, B), 128, 0, ctx->stream>>>((const uint32_t *)st, L, b->d_blk);
     LAUNCH_CHECK(ctx);
-    k_shuffle_witness<<<dim3(2, B), WIT_THREADS, 0, ctx->stream>>>((const uint32_t *)(st + m32), (const uint32_t *)(st + m32 + dk + xb),
+    unsigned wit_threads = 32;
+    while (wit_threads < WIT_THREADS && wit_threads < k - 1) wit_threads <<= 1;
+    k_shuffle_witness<<<dim3(2, B), wit_threads, 0, ctx->stream>>>((const uint32_t *)(st + m32), (const uint32_t *)(st + m32 + dk + xb),
                                                                   (const uint32_t *)(st + m32 + dk), k, L, b->d_blk, b->d_vwit);
     LAUNCH_CHECK(ctx);
     b->have_vwit = true;
@@ -822,7 +824,7 @@ static void acp_host_append_commitments(bpp_host::Transcript &t, const uint8_t *
     for (uint32_t c = 0; c < m; c += TR_V_CHUNK) {   // two levels, see k_tr_vchunks
         bpp_host::Transcript ch((const uint8_t *)"acp-V", 5);
         ch.append_u64("chunk", c / TR_V_CHUNK);
-        for (uint32_t j = c; j < m && j < c + TR_V_CHUNK; j++) ch.append_point("V", V + 32 * (size_t)j);
+        ch.append_message("V", V + 32 * (size_t)c, 32 * (size_t)((m - c) < TR_V_CHUNK ? (m - c) : TR_V_CHUNK));
         uint8_t d[32];
         ch.challenge_bytes("d", d, 32);
         t.append_message("Vd", d, 32);

@@ -7,6 +7,15 @@
 // :532 (decompress), :541 (equality).  Formulas: add-2008-hwcd-3 / dbl-2008-hwcd;
 // encodings: RFC 9496 sections 4.3.1-4.3.3.
 #pragma once
+// Bounds checks of the debug variant (tools/build_variants.sh dbg "-DBPP_DEBUG_BOUNDS"; compute-sanitizer is closed on
+// this pool): every index computed from device data is asserted against the extent the host allocated before it is
+// used.  A violated assertion traps and the next CUDA call of the library reports it.  Off in the product build.
+#ifdef BPP_DEBUG_BOUNDS
+#include <assert.h>
+#define BPP_ASSERT(cond) assert(cond)
+#else
+#define BPP_ASSERT(cond) ((void)0)
+#endif
 #include "fe25519.cuh"
 
 struct ge_ext {  // extended coordinates: x = X/Z, y = Y/Z, T = XY/Z

@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(IPA_ROUND_THREADS) k_ipa_round(acp_layout lay,
     const uint32_t tmask = (1u << done) - 1u;
     for (uint32_t g = tid; g < lay.np; g += nt) {      // the round's MSM scalars over the original generators
         const uint32_t i = g & (nj - 1), t = g >> (lay.lg - done), ip = i ^ h;
+        BPP_ASSERT(t <= tmask && ip < nj && done < lay.lg);
         sc s, sinv, a, b, yi, r;
         sc_load(s, st_new + 8 * (size_t)t);
         sc_load(sinv, st_new + 8 * (size_t)(tmask - t));

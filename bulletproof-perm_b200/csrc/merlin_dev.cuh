@@ -92,6 +92,7 @@ struct merlin_tr {
         return v;
     }
     __device__ void run_f() {
+        BPP_ASSERT(pos <= R && pos_begin <= R + 1);
         xor_byte(pos, pos_begin);
         xor_byte(pos + 1, 0x04);
         xor_byte(R + 1, 0x80);
@@ -99,10 +100,32 @@ struct merlin_tr {
         pos = 0;
         pos_begin = 0;
     }
+    // Whole Keccak lanes at a time where the sponge position allows it: one read-modify-write of the state (which lives in
+    // local memory: it is indexed by the position) per 8 message bytes instead of per byte.  A 4-byte aligned message
+    // is read as two 32-bit words per lane.
     __device__ void absorb(const uint8_t *d, uint32_t n) {
-        for (uint32_t i = 0; i < n; i++) {
-            xor_byte(pos, d[i]);
-            if (++pos == R) run_f();
+        while (n) {
+            const uint32_t take = min(n, R - pos);
+            uint32_t i = 0;
+            while (i < take && ((pos + i) & 7u)) { xor_byte(pos + i, d[i]); i++; }
+            if (((uintptr_t)(d + i) & 3u) == 0) {
+                for (; i + 8 <= take; i += 8) {
+                    const uint32_t *w = reinterpret_cast<const uint32_t *>(d + i);
+                    st[(pos + i) >> 3] ^= (uint64_t)w[0] | ((uint64_t)w[1] << 32);
+                }
+            } else {
+                for (; i + 8 <= take; i += 8) {
+                    uint64_t v = 0;
+#pragma unroll
+                    for (int b = 0; b < 8; b++) v |= (uint64_t)d[i + b] << (8 * b);
+                    st[(pos + i) >> 3] ^= v;
+                }
+            }
+            for (; i < take; i++) xor_byte(pos + i, d[i]);
+            pos += take;
+            d += take;
+            n -= take;
+            if (pos == R) run_f();
         }
     }
     __device__ void begin_op(uint32_t flags, bool more) {
@@ -143,13 +166,21 @@ struct merlin_tr {
     }
     // ---- TranscriptProtocol ----
     // challenge_scalar (transcript_protocol.rs:62-67): 64 bytes, Scalar::from_bytes_mod_order_wide
+    // The PRF operation always starts on a fresh block (its C flag forces the permutation unless pos == 0 already), so
+    // the 64 bytes are lanes 0..7 of the sponge, read and zeroed whole.
     __device__ void challenge_scalar(const char *label, uint32_t label_len, sc &out) {
-        uint8_t buf[64];
-        challenge_bytes(label, label_len, buf, 64);
+        const uint8_t len[4] = {64, 0, 0, 0};
+        meta_ad((const uint8_t *)label, label_len, false);
+        meta_ad(len, 4, true);
+        begin_op(F_I | F_A | F_C, false);   // pos == 0 afterwards
         uint32_t w[16];
-        for (int i = 0; i < 16; i++)
-            w[i] = (uint32_t)buf[4 * i] | ((uint32_t)buf[4 * i + 1] << 8) | ((uint32_t)buf[4 * i + 2] << 16) |
-                   ((uint32_t)buf[4 * i + 3] << 24);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            w[2 * i] = (uint32_t)st[i];
+            w[2 * i + 1] = (uint32_t)(st[i] >> 32);
+            st[i] = 0;
+        }
+        pos = 64;
         sc_from_wide(out, w);
     }
     // ---- state in global memory ----

@@ -71,6 +71,7 @@ struct merlin_warp {
         if (lane == (j >> 3)) s ^= (uint64_t)(v & 0xffu) << (8 * (j & 7));
     }
     __device__ void run_f() {
+        BPP_ASSERT(pos <= R && pos_begin <= R + 1);
         xor_byte(pos, pos_begin);
         xor_byte(pos + 1, 0x04);
         xor_byte(R + 1, 0x80);

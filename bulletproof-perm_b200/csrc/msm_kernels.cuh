@@ -141,7 +141,9 @@ __global__ void k_digit_scatter(const uint32_t *__restrict__ scalars, uint32_t n
             carry = raw > half ? 1u : 0u;
             uint32_t mag = carry ? (1u << c) - raw : raw;
             if (mag && w >= w_begin) {
+                BPP_ASSERT(mag <= half);
                 uint32_t pos = atomicAdd(&cursor[(size_t)w * half + (mag - 1)], 1u);
+                BPP_ASSERT(pos < n);
                 entries[(size_t)w * n + pos] = i | (carry << 31);
             }
         }
@@ -169,6 +171,7 @@ FE_INLINE void bucket_flush(const ge_ext &acc, uint32_t w, uint32_t b, uint32_t 
                             const uint32_t *__restrict__ ends, uint32_t *__restrict__ buckets,
                             uint32_t *__restrict__ partials) {
     size_t g = (size_t)w * B + b;
+    BPP_ASSERT(b < B && rs < re);
     bool complete = (offsets[g] == rs) && (ends[g] == re);
     uint32_t *dst = complete ? buckets + 32 * g : partials + 32 * (2 * tile + (rs == e0 ? 0 : 1));
     ge_store(dst, acc);
@@ -199,6 +202,7 @@ __global__ void __launch_bounds__(BPP_ACC_THREADS, 4) k_bucket_accum(
     ge_ext acc;
     ge_identity(acc);
     uint32_t idx = ew[e0];
+    BPP_ASSERT((idx & 0x7fffffffu) < n && cnt <= n && lo < B);
     ge_niels q;
     ge_niels_load(q, niels + 24 * (size_t)(idx & 0x7fffffffu));
 #pragma unroll 1
@@ -208,6 +212,7 @@ __global__ void __launch_bounds__(BPP_ACC_THREADS, 4) k_bucket_accum(
         ge_niels qn = q;
         if (e + 1 < e1) {
             idx_n = ew[e + 1];
+            BPP_ASSERT((idx_n & 0x7fffffffu) < n);
             ge_niels_load(qn, niels + 24 * (size_t)(idx_n & 0x7fffffffu));
         }
         ge_madd(acc, acc, q, (idx >> 31) != 0);
@@ -218,6 +223,7 @@ __global__ void __launch_bounds__(BPP_ACC_THREADS, 4) k_bucket_accum(
             if (e + 1 < e1) {   // next non-empty bucket
                 do {
                     cur++;
+                    BPP_ASSERT(cur < B);
                     cur_end = endw[cur];
                 } while (cur_end <= e + 1);
             }
@@ -247,6 +253,7 @@ __global__ void __launch_bounds__(128) k_bucket_fixup(const uint32_t *__restrict
         return;
     }
     const uint32_t first = beg / tile_len, last = (end - 1) / tile_len;
+    BPP_ASSERT(beg < end && last < tiles_per_window);
     if (first == last) return;  // complete inside one tile: already written
     if (last - first > BPP_LONG_SPAN) {
         long_list[atomicAdd(n_long, 1u)] = g;

@@ -28,7 +28,7 @@ static inline uint32_t tr_warp_max() {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("BPP_TR_WARP_MAX");
-        v = e ? atoi(e) : 6143;
+        v = e ? atoi(e) : 2047;
     }
     return (uint32_t)v;
 }
@@ -46,8 +46,8 @@ static inline uint32_t tr_warp_max() {
 // The value commitments, bound to the transcript right after the domain separator (modes 1 and 2; the reference never
 // appends them - SURVEY A.3 defect 12, weak Fiat-Shamir: the prover of a shuffle chooses the output-deck commitments).
 // Two levels (CPU restatements: commitment_digests / append_commitments in the test tree): every chunk of TR_V_CHUNK commitments is a
-// sponge of its own - Transcript::new("acp-V"), append_u64("chunk", index), append_point("V", V_j) in order,
-// challenge_bytes("d", 32) - and the proof's transcript absorbs m under "m" and the chunk digests under "Vd".  One
+// sponge of its own - Transcript::new("acp-V"), append_u64("chunk", index), append_message("V", the chunk's encodings
+// concatenated), challenge_bytes("d", 32) - and the proof's transcript absorbs m under "m" and the chunk digests under "Vd".  One
 // serial sponge over the m = 8193 commitments of a 4096-card deck is ~2000 permutations in a row on the critical path
 // of prover and verifier; the chunks run as independent warps.
 #define TR_V_CHUNK 64
@@ -64,8 +64,7 @@ __global__ void __launch_bounds__(TR_THREADS) k_tr_vchunks(const uint64_t *__res
     t.append_u64(MERLIN_LABEL("chunk"), c);
     const uint8_t *v = V + 32 * ((size_t)p * m + (size_t)c * TR_V_CHUNK);
     const uint32_t cnt = min((uint32_t)TR_V_CHUNK, m - c * TR_V_CHUNK);
-#pragma unroll 1
-    for (uint32_t j = 0; j < cnt; j++) t.append_message(MERLIN_LABEL("V"), v + 32 * (size_t)j, 32);
+    t.append_message(MERLIN_LABEL("V"), v, 32 * cnt);   // the chunk's encodings as one message
     t.challenge_bytes(MERLIN_LABEL("d"), vdig + 32 * (size_t)w, 32);
 }
 template <class T>

@@ -51,6 +51,8 @@ class ShardedMsm:
 
     def __init__(self, backend, table, world: int, device):
         self.be, self.table, self.world = backend, table, world
+        if backend.comm_info()[0] != world:
+            raise RuntimeError(f"ShardedMsm over {world} ranks needs the library communicator: call init_comm(backend, world, rank) first")
         self.d_out = torch.zeros(160, dtype=torch.uint8, device=device)
         self.d_outs = [torch.zeros(160, dtype=torch.uint8, device=device) for _ in range(3)]
 

@@ -236,7 +236,8 @@ V_CHUNK = 64
 
 def commitment_digests(V):
     """One 32-byte digest per chunk of V_CHUNK commitments: a Merlin transcript of its own, Transcript::new(b"acp-V"),
-    append_u64(b"chunk", index), append_point(b"V", V_j) for the chunk's commitments in order, challenge_bytes(b"d", 32).
+    append_u64(b"chunk", index), append_message(b"V", the chunk's encodings concatenated in order),
+    challenge_bytes(b"d", 32).  (Fixed-size items whose count is bound by "m" need no framing of their own.)
     The chunks are independent sponges, so a deck of thousands of commitments is hashed in parallel (one serial sponge
     over m = 8193 commitments is ~2000 Keccak permutations in a row on the critical path of every prover and verifier)."""
     enc = [Vj if isinstance(Vj, (bytes, bytearray)) else R.compress(Vj) for Vj in V]
@@ -244,8 +245,7 @@ def commitment_digests(V):
     for c in range(0, len(enc), V_CHUNK):
         t = Transcript(b"acp-V")
         t.append_u64(b"chunk", c // V_CHUNK)
-        for e in enc[c:c + V_CHUNK]:
-            t.append_point(b"V", bytes(e))
+        t.append_message(b"V", b"".join(bytes(e) for e in enc[c:c + V_CHUNK]))
         out.append(t.challenge_bytes(b"d", 32))
     return out
 

@@ -324,17 +324,19 @@ static int ge_ristretto_eq(const ge_ext *p, const ge_ext *q) {
  * encodings, what a verifier is handed) is used when given, else the points are compressed here. */
 #define V_CHUNK 64
 static void tr_append_commitments(strobe *tr, const ge_ext *V, const u8 *V_enc, size_t m) {
-    u8 mb[8], enc[32], dig[32];
+    u8 mb[8], dig[32], buf[32 * V_CHUNK];
     for (int i = 0; i < 8; i++) mb[i] = (u8)((u64)m >> (8 * i));
     tr_append(tr, "m", mb, 8);
     for (size_t c = 0; c < m; c += V_CHUNK) {   /* one sponge per chunk of 64 commitments, its digest under "Vd" */
         strobe ch; tr_new(&ch, (const u8 *)"acp-V", 5);
         for (int i = 0; i < 8; i++) mb[i] = (u8)((u64)(c / V_CHUNK) >> (8 * i));
         tr_append(&ch, "chunk", mb, 8);
-        for (size_t j = c; j < m && j < c + V_CHUNK; j++) {
-            if (V_enc) tr_append(&ch, "V", V_enc + 32 * j, 32);
-            else { ristretto_compress(enc, &V[j]); tr_append(&ch, "V", enc, 32); }
+        size_t cnt = 0;
+        for (size_t j = c; j < m && j < c + V_CHUNK; j++, cnt++) {
+            if (V_enc) memcpy(buf + 32 * cnt, V_enc + 32 * j, 32);
+            else ristretto_compress(buf + 32 * cnt, &V[j]);
         }
+        tr_append(&ch, "V", buf, 32 * cnt);   /* the chunk's encodings as one message */
         tr_challenge_bytes(&ch, "d", dig, 32);
         tr_append(tr, "Vd", dig, 32);
     }

@@ -41,6 +41,7 @@ def main():
     be = bpperm_b200.Backend(local)
     stream = torch.cuda.current_stream(dev)
     be.set_stream(stream.cuda_stream)
+    bpperm_b200.parallel.init_comm(be, world, rank, dev)   # the library's NCCL communicator (bpp_comm_init)
     rows = []
     for log_n in range(args.min, args.max + 1, args.step):
         n = 1 << log_n
