@@ -477,6 +477,144 @@ __global__ void __launch_bounds__(FB_THREADS, FB_WARP_MINBLOCKS) k_fb_msm_warp(c
     }
     if (lane == 0) ge_store(out_ext + 32 * ((size_t)p * sh.outs + o), acc);
 }
+// Digit-staged form of k_fb_msm_warp for the window widths whose window count is a power of two (c = 16: 16 windows,
+// c = 8: 32).  The source page of the form above (profiles/r2_ncu_source_fb_msm_warp.csv.gz) shows where its issue slots
+// go besides the mixed adds: ~200 of ~1200 warp instructions per add are the work-item bookkeeping (term / segment walk,
+// an 8-limb s + K, a local-memory array indexed by the window, 64-bit table index arithmetic on the multiplier pipe), and
+// every long-scoreboard stall (9.8 % of the samples) sits on that bookkeeping, none on the prefetched table gathers.
+// Here the warp does the bookkeeping ONCE while staging: the terms selected for this output are compacted (ballot +
+// popc), s' = s + K is written to shared memory - for these widths the digits of s' ARE its 16-bit / 8-bit fields - with
+// the generator index beside it.  The main loop then is: one LDS.U16 (digit), one LDS (generator), a shift/or for the
+// table entry - and, since the lane stride 32 is a multiple of the window count, a lane keeps the same window for its
+// whole life (ww = lane mod Wn): items are single (term, window) pairs, so lanes differ by at most one mixed add
+// (the 4-window items above: by four).  Dynamic shared memory: (FB_THREADS / 32) x total_terms x 36 B.
+#ifndef FB_STAGE_MAX_BYTES
+#define FB_STAGE_MAX_BYTES (48u * 1024u)   // dynamic shared memory without an opt-in attribute
+#endif
+template <int C>
+__global__ void __launch_bounds__(FB_THREADS, FB_WARP_MINBLOCKS) k_fb_msm_warp_d(const uint32_t *__restrict__ blk, acp_layout lay, fb_shape sh,
+                                                              const uint32_t *__restrict__ table, fb_consts kc,
+                                                              uint32_t B, uint32_t outs /* per proof; sh.outs = pitch */,
+                                                              uint32_t *__restrict__ out_ext /* [p][pitch] x 32 */) {
+    constexpr uint32_t WN = (256 + C - 1) / C, LOG_WN = WN == 32 ? 5 : 4, HALF = 1u << (C - 1);
+    static_assert((C == 16 && WN == 16) || (C == 8 && WN == 32), "window count must be a power of two dividing 32");
+    extern __shared__ __align__(16) uint32_t fb_stage[];
+    const uint32_t wid = blockIdx.x * (FB_THREADS / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (wid >= B * outs) return;   // whole warps leave together
+    const uint32_t p = wid / outs, o = wid - p * outs;
+    uint32_t total_terms = 0;
+    for (uint32_t s = 0; s < sh.nseg; s++) total_terms += sh.cnt[s];
+    // per warp: total_terms x 8 words of s', then the generator indices (region rounded up to 16 bytes)
+    uint32_t *stage = fb_stage + (size_t)(threadIdx.x >> 5) * ((9 * total_terms + 3) & ~3u);
+    uint32_t *sgen = stage + 8 * (size_t)total_terms;
+    uint32_t n_act = 0;
+    for (uint32_t t0 = 0; t0 < total_terms; t0 += 32) {
+        const uint32_t t = t0 + lane;
+        bool act = t < total_terms;
+        uint32_t seg = 0, k = t;
+        if (act) {
+            while (seg + 1 < sh.nseg && k >= sh.cnt[seg]) { k -= sh.cnt[seg]; seg++; }
+            if (sh.sel_period && sh.sel[seg]) {
+                const bool upper = (k & (sh.sel_period - 1)) >= (sh.sel_period >> 1);
+                act = (upper == (o == 0)) == (sh.sel[seg] == 1);
+            }
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, act);
+        if (act) {
+            const uint32_t idx = n_act + __popc(bal & ((1u << lane) - 1u));
+            const uint32_t *sp = ACP_PTR(blk, lay, p, sh.sc_off[seg] + o * sh.sc_ostride[seg] + k);
+            const uint4 lo = *reinterpret_cast<const uint4 *>(sp), hi = *reinterpret_cast<const uint4 *>(sp + 4);
+            uint32_t s[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+            unsigned long long carry = 0;   // s' = s + K < 2^256 (s < 2^255, K < 2^(C (WN - 1)))
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                carry += (unsigned long long)s[i] + kc.K[i];
+                s[i] = (uint32_t)carry;
+                carry >>= 32;
+            }
+            BPP_ASSERT(carry == 0 && idx < total_terms);
+            *reinterpret_cast<uint4 *>(stage + 8 * (size_t)idx) = make_uint4(s[0], s[1], s[2], s[3]);
+            *reinterpret_cast<uint4 *>(stage + 8 * (size_t)idx + 4) = make_uint4(s[4], s[5], s[6], s[7]);
+            sgen[idx] = sh.gen[seg] + k;
+        }
+        n_act += __popc(bal);
+    }
+    __syncwarp();
+    const uint32_t items = n_act << LOG_WN;
+    const uint32_t ww = lane & (WN - 1);
+    const bool top = ww == WN - 1;                      // the top window's digit is unsigned
+    const uint32_t lane_entry = ww << (C - 1);          // entry = (gen * WN + ww) * HALF + mag - 1
+    ge_ext acc;
+    ge_identity(acc);
+    uint32_t it = lane;
+    auto advance = [&](const uint32_t *&ptr, bool &neg) -> bool {
+        for (;;) {
+            if (it >= items) return false;
+            const uint32_t term = it >> LOG_WN;
+            it += 32;
+            uint32_t u;
+            if (C == 16) u = reinterpret_cast<const uint16_t *>(stage)[(term << 4) + ww];
+            else u = reinterpret_cast<const uint8_t *>(stage)[(term << 5) + ww];
+            const int d = top ? (int)u : (int)u - (int)HALF;
+            if (d == 0) continue;
+            const uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+            const uint32_t entry = ((sgen[term] << LOG_WN) << (C - 1)) + lane_entry + (mag - 1);
+            BPP_ASSERT(mag >= 1 && mag <= HALF && term < n_act);
+            ptr = table + (size_t)entry * FB_ENTRY_U32;
+            neg = d < 0;
+            return true;
+        }
+    };
+    {
+        const uint32_t *ptr = nullptr, *ptr_n = nullptr;
+        bool neg = false, neg_n = false;
+        bool ok = advance(ptr, neg);
+        ge_niels q, qn;
+        if (ok) ge_niels_load(q, ptr);
+#pragma unroll 1
+        while (ok) {
+            bool ok_n = advance(ptr_n, neg_n);
+            qn = q;
+            if (ok_n) ge_niels_load(qn, ptr_n);
+            ge_madd(acc, acc, q, neg);
+            q = qn;
+            neg = neg_n;
+            ok = ok_n;
+        }
+    }
+#pragma unroll 1
+    for (int d = 16; d >= 1; d >>= 1) {   // warp reduction: five shuffle steps
+        ge_ext o2;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            o2.X.v[i] = __shfl_down_sync(0xffffffffu, acc.X.v[i], d);
+            o2.Y.v[i] = __shfl_down_sync(0xffffffffu, acc.Y.v[i], d);
+            o2.Z.v[i] = __shfl_down_sync(0xffffffffu, acc.Z.v[i], d);
+            o2.T.v[i] = __shfl_down_sync(0xffffffffu, acc.T.v[i], d);
+        }
+        ge_add(acc, acc, o2);
+    }
+    if (lane == 0) ge_store(out_ext + 32 * ((size_t)p * sh.outs + o), acc);
+}
+// host side: the warp-per-output launch (digit-staged form when the table's window width has one and the stage fits)
+static inline void fb_warp_launch(const uint32_t *d_sc, const acp_layout &lay, const fb_shape &sh, const uint32_t *table, int c, int Wn,
+                                  const fb_consts &kc, uint32_t B, uint32_t outs, uint32_t terms, uint32_t *d_ext, bool stage_ok,
+                                  bool digits_ok, cudaStream_t st) {
+    const uint32_t n_out = B * outs;
+    const unsigned grid = (n_out + FB_THREADS / 32 - 1) / (FB_THREADS / 32);
+    const size_t stage_d = (size_t)(FB_THREADS / 32) * ((9 * terms + 3) & ~3u) * 4, stage_b = (size_t)(FB_THREADS / 32) * terms * 32;
+    uint64_t gen_end = 0;   // entry indices are 32-bit in the digit-staged form
+    for (uint32_t k = 0; k < sh.nseg; k++) gen_end = gen_end > (uint64_t)sh.gen[k] + sh.cnt[k] ? gen_end : (uint64_t)sh.gen[k] + sh.cnt[k];
+    const bool fits32 = ((gen_end * Wn) << (c - 1)) < (1ull << 32);
+    if (digits_ok && stage_ok && fits32 && stage_d <= FB_STAGE_MAX_BYTES && (c == 16 || c == 8)) {
+        if (c == 16) k_fb_msm_warp_d<16><<<grid, FB_THREADS, stage_d, st>>>(d_sc, lay, sh, table, kc, B, outs, d_ext);
+        else k_fb_msm_warp_d<8><<<grid, FB_THREADS, stage_d, st>>>(d_sc, lay, sh, table, kc, B, outs, d_ext);
+    } else if (stage_ok && stage_b <= FB_STAGE_MAX_BYTES) {
+        k_fb_msm_warp<true><<<grid, FB_THREADS, stage_b, st>>>(d_sc, lay, sh, table, c, Wn, kc, B, outs, d_ext);
+    } else {
+        k_fb_msm_warp<false><<<grid, FB_THREADS, 0, st>>>(d_sc, lay, sh, table, c, Wn, kc, B, outs, d_ext);
+    }
+}
 // Few-term shapes (T_i = t_i*g + tau_i*h, V_j = v_j*g + gamma_j*h: 2 terms): one THREAD per output point
 // walks its terms x windows serially - no block tree, no idle lanes.
 __global__ void __launch_bounds__(128) k_fb_msm_small(const uint32_t *__restrict__ blk, acp_layout lay, fb_shape sh,

@@ -11,7 +11,6 @@
 #include "transcript_kernels.cuh"
 #include "host_merlin.hpp"
 
-#define FB_STAGE_MAX_BYTES (48u * 1024u)   // dynamic shared memory of k_fb_msm_warp<true> without an opt-in attribute
 
 struct bpp_circuit {
     uint32_t n = 0, Q = 0, m = 0, rows = 0, nnz = 0;
@@ -58,6 +57,8 @@ struct bpp_acp_batch {
     // weight derivation (k_tr_weights: hashes the rest of the proof; beside the challenge-dependent scalar chain)
     cudaStream_t aux2 = nullptr;
     cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr;
+    cudaStream_t aux3 = nullptr;      // small batches: the third commitment of A_I / A_O / S side by side
+    cudaEvent_t ev_join3 = nullptr;
     uint32_t *d_vwit = nullptr, *d_wgen = nullptr;   // bpp_acp_batch_gen_shuffle_witness: v (B x m), staging of its inputs
     bool have_vwit = false;
     bool have_V = false;            // commitments resident (bpp_acp_batch_commit / _upload_commitments / _upload_proofs)
@@ -75,6 +76,8 @@ struct bpp_acp_batch {
     // dynamic points + the shared generators (appended to d_dyn), its compressed result, the fall-back flag
     bool batch_rlc = true;
     bool fb_stage_scalars = true;   // k_fb_msm_warp<true>: the warp's scalars staged in shared memory (BPP_FB_STAGE=0: off)
+    bool ipa_fused_tail = true;     // k_ipa_lr_tail for split launches (BPP_IPA_TAIL=0: the three separate launches)
+    bool fb_digits = true;          // k_fb_msm_warp_d: digits staged, c = 16 / 8 (BPP_FB_DIGITS=0: the form above; tuning hook)
     uint32_t *d_rlc_sc = nullptr, *d_rlc_flag = nullptr;
     uint8_t *d_rlc_out = nullptr;
     uint32_t *h_rlc_flag = nullptr;
@@ -300,6 +303,10 @@ __global__ void k_compress_strided(const uint32_t *__restrict__ ext, uint32_t pi
 // the same generator set, with fresh scalars per proof.  For such a set the window table of bpp_points_precompute turns
 // every MSM into table look-ups and mixed adds - no buckets, no doublings, so no 253-step dependent chain - and
 // bpp_msm_vartime_batch evaluates `count` of them per launch.
+static bool fb_digits_default() {
+    const char *e = getenv("BPP_FB_DIGITS");
+    return !e || e[0] != '0';
+}
 static void fb_make_K(int c, int Wn, uint32_t K[8]) {   // sum_{w < Wn-1} 2^(c w + c - 1)
     memset(K, 0, 32);
     for (int w = 0; w < Wn - 1; w++) {
@@ -348,12 +355,7 @@ static int msm_table_run(bpp_ctx *ctx, const uint32_t *d_sc, const bpp_points *P
     memcpy(kc.K, P->fb_K, 32);
     cudaStream_t st = ctx->stream;
     if (count >= 16ull * ctx->sm_count) {
-        const size_t stage_b = (size_t)(FB_THREADS / 32) * n * 32;
-        const unsigned grid = (unsigned)((count + FB_THREADS / 32 - 1) / (FB_THREADS / 32));
-        if (stage_b <= FB_STAGE_MAX_BYTES)
-            k_fb_msm_warp<true><<<grid, FB_THREADS, stage_b, st>>>(d_sc, lay, sh, P->fb_table, P->fb_c, P->fb_Wn, kc, (uint32_t)count, 1, d_ext);
-        else
-            k_fb_msm_warp<false><<<grid, FB_THREADS, 0, st>>>(d_sc, lay, sh, P->fb_table, P->fb_c, P->fb_Wn, kc, (uint32_t)count, 1, d_ext);
+        fb_warp_launch(d_sc, lay, sh, P->fb_table, P->fb_c, P->fb_Wn, kc, (uint32_t)count, 1, (uint32_t)n, d_ext, true, fb_digits_default(), st);
         LAUNCH_CHECK(ctx);
     } else if (sp > 1) {
         k_fb_msm<<<dim3((unsigned)count, 1, sp), FB_THREADS, 0, st>>>(d_sc, lay, sh, P->fb_table, P->fb_c, P->fb_Wn, kc, d_part);
@@ -491,6 +493,8 @@ extern "C" void bpp_acp_batch_free(bpp_acp_batch *b) {
     if (b->h_rlc_flag) cudaFreeHost(b->h_rlc_flag);
     if (b->h_V) cudaFreeHost(b->h_V);
     if (b->aux2) cudaStreamDestroy(b->aux2);
+    if (b->aux3) cudaStreamDestroy(b->aux3);
+    if (b->ev_join3) cudaEventDestroy(b->ev_join3);
     if (b->ev_fork2) cudaEventDestroy(b->ev_fork2);
     if (b->ev_join2) cudaEventDestroy(b->ev_join2);
     if (b->aux) cudaStreamDestroy(b->aux);
@@ -520,6 +524,8 @@ extern "C" int bpp_acp_batch_create(bpp_ctx *ctx, const bpp_circuit *cir, const 
     b->proof_len = (uint32_t)bpp_acproof_proof_len_mode(cir->n, mode);
     if (const char *e = getenv("BPP_FB_WARP")) b->fb_warp_per_output = e[0] != '0';
     if (const char *e = getenv("BPP_FB_STAGE")) b->fb_stage_scalars = e[0] != '0';
+    b->fb_digits = fb_digits_default();
+    if (const char *e = getenv("BPP_IPA_TAIL")) b->ipa_fused_tail = e[0] != '0';
     b->label.assign(label, label + label_len);
     const size_t B = count, lg = b->lay.lg, per = cir->m + 8 + 2 * lg, nch = 6 + lg;   // challenges per proof + the two weights
     {   // small batches of large circuits: split each fixed-base MSM over several blocks (k_fb_sum_splits adds them)
@@ -539,6 +545,8 @@ extern "C" int bpp_acp_batch_create(bpp_ctx *ctx, const bpp_circuit *cir, const 
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->aux2, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_fork2, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_join2, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->aux3, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_join3, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_tr, B * MERLIN_STATE_WORDS * 8);
     if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_proto, 2 * MERLIN_STATE_WORDS * 8);
     if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_vdig, B * TR_V_CHUNKS(cir->m) * 32);
@@ -648,8 +656,14 @@ static void acp_seg(fb_shape &s, uint32_t off, uint32_t ostride, uint32_t gen, u
     s.nseg++;
 }
 // launches the fixed-base MSM; results land in dst[(p * pitch + o)] (raw extended points)
-static int acp_fb(bpp_acp_batch *b, const fb_shape &sh, uint32_t *dst, uint32_t pitch) {
+// on: run on this stream instead of the context's (small batches: independent commitments side by side); part_region:
+// which eighth of the split scratch to use (concurrent split launches must not share it); deferred_splits: when given
+// and the launch is split, the partial sums are left in the scratch for the caller's own tail kernel (their count is
+// written there; 1 = the result is complete in dst).
+static int acp_fb(bpp_acp_batch *b, const fb_shape &sh, uint32_t *dst, uint32_t pitch, cudaStream_t on = nullptr,
+                  uint32_t part_region = 0, uint32_t *deferred_splits = nullptr) {
     bpp_ctx *ctx = b->ctx;
+    if (deferred_splits) *deferred_splits = 1;
     fb_shape s = sh;
     s.outs = pitch;  // k_fb_msm addresses out_ext + 32 * (p * outs + o)
     // few (proof, output) pairs: split the terms of each MSM over several blocks so the launch fills the GPU
@@ -663,8 +677,8 @@ static int acp_fb(bpp_acp_batch *b, const fb_shape &sh, uint32_t *dst, uint32_t 
         LAUNCH_CHECK(ctx);
         return BPP_OK;
     }
-    cudaStream_t st = ctx->stream;
-    if (b->priority_split) {   // the GPU-filling launch goes to the low-priority stream, bracketed by events
+    cudaStream_t st = on ? on : ctx->stream;
+    if (b->priority_split && !on) {   // the GPU-filling launch goes to the low-priority stream, bracketed by events
         st = b->bulk;
         CK(ctx, cudaEventRecord(b->ev_bfork, ctx->stream));
         CK(ctx, cudaStreamWaitEvent(st, b->ev_bfork, 0));
@@ -676,28 +690,26 @@ static int acp_fb(bpp_acp_batch *b, const fb_shape &sh, uint32_t *dst, uint32_t 
     if (sp > b->fb_splits || sh.outs > 8) sp = sh.outs > 8 ? 1 : b->fb_splits;
     if (sp == 1 && b->fb_warp_per_output && blocks >= 16ull * ctx->sm_count) {
         // plenty of outputs: a warp per output (no block tree, no barrier)
-        const uint32_t n_out = b->B * sh.outs;
-        const size_t stage_b = (size_t)(FB_THREADS / 32) * terms * 32;
-        const unsigned grid = (n_out + FB_THREADS / 32 - 1) / (FB_THREADS / 32);
-        if (stage_b <= FB_STAGE_MAX_BYTES && b->fb_stage_scalars)
-            k_fb_msm_warp<true><<<grid, FB_THREADS, stage_b, st>>>(b->d_blk, b->lay, s, b->gens->d_table, b->gens->c, b->gens->Wn,
-                                                                   b->gens->kc, b->B, sh.outs, dst);
-        else
-            k_fb_msm_warp<false><<<grid, FB_THREADS, 0, st>>>(b->d_blk, b->lay, s, b->gens->d_table, b->gens->c, b->gens->Wn,
-                                                              b->gens->kc, b->B, sh.outs, dst);
+        fb_warp_launch(b->d_blk, b->lay, s, b->gens->d_table, b->gens->c, b->gens->Wn, b->gens->kc, b->B, sh.outs, terms, dst,
+                       b->fb_stage_scalars, b->fb_digits, st);
         LAUNCH_CHECK(ctx);
     } else if (sp > 1) {
+        uint32_t *part = b->d_part + 32 * (size_t)part_region * b->B * b->fb_splits;
         k_fb_msm<<<dim3(b->B, sh.outs, (uint32_t)sp), FB_THREADS, 0, st>>>(b->d_blk, b->lay, s, b->gens->d_table,
-                                                                          b->gens->c, b->gens->Wn, b->gens->kc, b->d_part);
+                                                                          b->gens->c, b->gens->Wn, b->gens->kc, part);
         LAUNCH_CHECK(ctx);
-        k_fb_sum_splits<<<dim3(b->B, sh.outs), 32, 0, st>>>(b->d_part, sh.outs, (uint32_t)sp, pitch, dst);
-        LAUNCH_CHECK(ctx);
+        if (deferred_splits) {
+            *deferred_splits = (uint32_t)sp;
+        } else {
+            k_fb_sum_splits<<<dim3(b->B, sh.outs), 32, 0, st>>>(part, sh.outs, (uint32_t)sp, pitch, dst);
+            LAUNCH_CHECK(ctx);
+        }
     } else {
         k_fb_msm<<<dim3(b->B, sh.outs), FB_THREADS, 0, st>>>(b->d_blk, b->lay, s, b->gens->d_table, b->gens->c,
                                                             b->gens->Wn, b->gens->kc, dst);
         LAUNCH_CHECK(ctx);
     }
-    if (b->priority_split) {
+    if (b->priority_split && !on) {
         CK(ctx, cudaEventRecord(b->ev_bjoin, st));
         CK(ctx, cudaStreamWaitEvent(ctx->stream, b->ev_bjoin, 0));
     }
@@ -959,7 +971,17 @@ static int acp_prove_ipa(bpp_acp_batch *b) {
         acp_seg(sh, L.vG, 0, 2, np);  sh.sel[0] = 1;    // <a_L s, G_R> for L, <a_R s, G_L> for R
         acp_seg(sh, L.vH, 0, gH, np); sh.sel[1] = 2;    // <b_R s^-1 y^-n, H_L> for L, <b_L .., H_R> for R
         acp_seg(sh, L.cl, 1, 0, 1);   sh.sel[2] = 0;    // c_L Q, c_R Q with Q = w g
-        if ((rc = acp_fb(b, sh, b->d_lrext + 32 * 2 * (size_t)j, 2 * lg))) return rc;
+        // small batches with device transcripts: split sums, compression, transcript and u^-1 in one launch
+        const bool fuse_tail = !b->host_transcripts && B <= 1023 && b->ipa_fused_tail;
+        uint32_t split_n = 1;
+        if ((rc = acp_fb(b, sh, b->d_lrext + 32 * 2 * (size_t)j, 2 * lg, nullptr, 0, fuse_tail ? &split_n : nullptr))) return rc;
+        if (split_n > 1) {
+            k_ipa_lr_tail<<<B, 64, 0, s>>>(b->d_part, split_n, b->d_lrext, b->d_lr, L, (int)j, b->d_tr, b->d_blk);
+            LAUNCH_CHECK(ctx);
+            CK(ctx, ipa_round_launch(L, (int)j, b->d_blk, B, s));
+            ctx->launches++;
+            continue;
+        }
         k_compress_strided<<<(2 * B + 127) / 128, 128, 0, s>>>(b->d_lrext, 2 * lg, 2 * j, 2, B, b->d_lr);
         LAUNCH_CHECK(ctx);
         if (!b->host_transcripts) {
@@ -1007,16 +1029,30 @@ extern "C" int bpp_acp_batch_prove(bpp_acp_batch *b) {
     k_acp_rng<<<dim3((nrand + 127) / 128, B), 128, 0, s>>>(b->d_seeds, L, nrand, b->d_blk);
     LAUNCH_CHECK(ctx);
     {   // A_I = alpha*h + <a_L,G> + <a_R,H>; A_O = beta*h + <a_O,G>; S = ro*h + <s_l,G> + <s_r,H>
+        // small batches (split launches that do not fill the GPU for long): the three commitments side by side on
+        // three streams, each with its own part of the split scratch
+        const bool side = b->fb_splits > 1 && !b->priority_split && b->aux3;
+        if (side) {
+            CK(ctx, cudaEventRecord(b->ev_fork, s));
+            CK(ctx, cudaStreamWaitEvent(b->aux, b->ev_fork, 0));
+            CK(ctx, cudaStreamWaitEvent(b->aux3, b->ev_fork, 0));
+        }
         fb_shape sh = acp_shape(1);
         const uint32_t gH = 2 + b->gens->n;   // first H generator (gens order g, h, G[..], H[..])
         acp_seg(sh, L.alpha, 0, 1, 1); acp_seg(sh, L.aL, 0, 2, n); acp_seg(sh, L.aR, 0, gH, n);
         if ((rc = acp_fb(b, sh, b->d_ext8 + 0, 8))) return rc;
         sh = acp_shape(1);
         acp_seg(sh, L.beta, 0, 1, 1); acp_seg(sh, L.aO, 0, 2, n);
-        if ((rc = acp_fb(b, sh, b->d_ext8 + 32, 8))) return rc;
+        if ((rc = acp_fb(b, sh, b->d_ext8 + 32, 8, side ? b->aux : nullptr, side ? 1 : 0))) return rc;
         sh = acp_shape(1);
         acp_seg(sh, L.ro, 0, 1, 1); acp_seg(sh, L.sl, 0, 2, n); acp_seg(sh, L.sr, 0, gH, n);
-        if ((rc = acp_fb(b, sh, b->d_ext8 + 64, 8))) return rc;
+        if ((rc = acp_fb(b, sh, b->d_ext8 + 64, 8, side ? b->aux3 : nullptr, side ? 2 : 0))) return rc;
+        if (side) {
+            CK(ctx, cudaEventRecord(b->ev_join, b->aux));
+            CK(ctx, cudaEventRecord(b->ev_join3, b->aux3));
+            CK(ctx, cudaStreamWaitEvent(s, b->ev_join, 0));
+            CK(ctx, cudaStreamWaitEvent(s, b->ev_join3, 0));
+        }
     }
     k_compress_strided<<<(B * 3 + 127) / 128, 128, 0, s>>>(b->d_ext8, 8, 0, 3, B, b->d_pts8);
     LAUNCH_CHECK(ctx);

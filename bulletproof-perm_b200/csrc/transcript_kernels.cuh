@@ -163,6 +163,63 @@ __global__ void __launch_bounds__(TR_THREADS) k_ipa_challenge(const uint8_t *__r
     }
 }
 
+// Small batches (a single large-deck proof: every inner-product round is a chain of short dependent launches): the tail
+// of a round in ONE launch instead of three (k_fb_sum_splits -> k_compress_strided -> k_ipa_challenge).  Block per proof,
+// two warps: warp 0 sums the split partial sums of L_round (lane-strided additions, then five shuffle steps), warp 1
+// those of R_round; lane 0 of each compresses its point (the two inverse square roots run side by side); after the
+// barrier warp 0 appends both encodings to the proof's transcript, draws u_round and inverts it.
+__global__ void __launch_bounds__(64) k_ipa_lr_tail(const uint32_t *__restrict__ part /* [p][2][splits] x 32 */, uint32_t splits,
+                                                    uint32_t *__restrict__ lrext /* [p][2 lg] x 32 */, uint8_t *__restrict__ lr,
+                                                    acp_layout lay, int round, uint64_t *__restrict__ states,
+                                                    uint32_t *__restrict__ blk) {
+    const uint32_t p = blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    {
+        const uint32_t *src = part + 32 * ((size_t)p * 2 + w) * splits;
+        ge_ext acc, t;
+        ge_identity(acc);
+#pragma unroll 1
+        for (uint32_t z = lane; z < splits; z += 32) {
+            ge_load(t, src + 32 * (size_t)z);
+            ge_add_noinline(acc, acc, t);
+        }
+#pragma unroll 1
+        for (int d = 16; d >= 1; d >>= 1) {
+            ge_ext o2;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                o2.X.v[i] = __shfl_down_sync(0xffffffffu, acc.X.v[i], d);
+                o2.Y.v[i] = __shfl_down_sync(0xffffffffu, acc.Y.v[i], d);
+                o2.Z.v[i] = __shfl_down_sync(0xffffffffu, acc.Z.v[i], d);
+                o2.T.v[i] = __shfl_down_sync(0xffffffffu, acc.T.v[i], d);
+            }
+            ge_add_noinline(acc, acc, o2);
+        }
+        if (lane == 0) {
+            const size_t k = (size_t)p * 2 * lay.lg + 2 * (uint32_t)round + w;
+            ge_store(lrext + 32 * k, acc);
+            ge_compress(lr + 32 * k, acc);
+        }
+    }
+    __syncthreads();   // both encodings are in global memory, written by this block
+    if (w != 0) return;
+    merlin_warp t;
+    t.load(states + MERLIN_STATE_WORDS * (size_t)p);
+    const uint8_t *q = lr + 64 * ((size_t)lay.lg * p + (uint32_t)round);
+    t.append_message(MERLIN_LABEL("L"), q, 32);
+    t.append_message(MERLIN_LABEL("R"), q + 32, 32);
+    sc c;
+    t.challenge_scalar(MERLIN_LABEL("u"), c);
+    t.store(states + MERLIN_STATE_WORDS * (size_t)p);
+    if (lane == 0) {
+        sc ci;
+        sc_invert(ci, c);
+        sc_to_mont(c, c);
+        sc_to_mont(ci, ci);
+        sc_store(ACP_PTR(blk, lay, p, lay.u + round), c);
+        sc_store(ACP_PTR(blk, lay, p, lay.uinv + round), ci);
+    }
+}
+
 // Verifier: replays the whole transcript of one proof and leaves its final state in `states` (k_tr_weights continues
 // it).  tx3 (B x 3 x 32: t_x, t_x_blinding, e_blinding, reduced) and lr are used in `fixed` mode only (lay.lg > 0).
 template <class T>

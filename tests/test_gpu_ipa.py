@@ -251,3 +251,31 @@ def test_generator_fold_operator_matches_the_oracle_and_the_scalar_fold_form(bac
     rhs = backend.vartime_multiscalar_mul(_sb([x * uis[0] % L for x in a] + [x * us[0] % L for x in a]), enc)
     assert lhs == rhs
     table.free()
+
+
+@pytest.mark.parametrize("window_bits,digits", [(16, "1"), (8, "1"), (16, "0")])
+def test_large_batch_uses_the_warp_per_output_msm_and_stays_byte_identical(backend, monkeypatch, window_bits, digits):
+    """From 16 outputs per SM the commitments go through the warp-per-output fixed-base kernels (k_fb_msm_warp_d: digits
+    staged in shared memory, the inner-product rounds' L / R selection compacted while staging; BPP_FB_DIGITS=0: the
+    scalar-staged form).  A 5-card `fixed` batch of 2400 proofs with different prover seeds: a sample of proofs must equal
+    the CPU restatement byte for byte, and every proof must verify."""
+    from bpperm_b200 import acproof as G
+    monkeypatch.setenv("BPP_FB_DIGITS", digits)
+    core, prover, V, cir, gens, inst = _setup(backend, 5, 71, window_bits)
+    B = 2400
+    seeds = [(7000 + i).to_bytes(4, "little") * 8 for i in range(B)]
+    Vc = b"".join(R.compress(p) for p in V)
+    batch = G.Batch(backend, cir, gens, B, "fixed", b"test")
+    batch.upload_witness(_sb(prover["a_L"]) * B, _sb(prover["a_R"]) * B, _sb(prover["a_O"]) * B, _sb(prover["gamma"]) * B,
+                         b"".join(seeds))
+    batch.upload_commitments(Vc * B)
+    batch.prove()
+    proofs = batch.download_proofs()
+    plen = G.proof_len(core["n"], "fixed")
+    for i in (0, 1, 31, 32, 1199, 2399):
+        pb, _ = ipa.prove(core, prover, V, ChaChaRng(seeds[i]))
+        assert proofs[i * plen:(i + 1) * plen] == pb, i
+    batch.upload_proofs(proofs, Vc * B)
+    batch.verify(b"\x05" * 32)
+    assert batch.download_accept() == b"\x01" * B
+    batch.free()
