@@ -52,18 +52,30 @@ def _peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
 
 
-def _ncu_traffic(name):
-    """dram read + write bytes per launch from a committed `ncu --set full` summary (profiles/<name>), or None."""
+def _ncu_traffic(names, kernel):
+    """dram read + write bytes of one launch of `kernel` from a committed `ncu --set full` summary (the first of
+    profiles/<names> that exists; one column per captured launch) -> (bytes, file) or (None, None)."""
     import csv
-    path = os.path.join(ROOT, "profiles", name)
-    if not os.path.exists(path):
-        return None
     mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    tot = 0.0
-    for row in csv.reader(open(path)):
-        if len(row) >= 3 and row[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-            tot += float(row[2]) * mult.get(row[1], 1.0)
-    return tot or None
+    for name in names:
+        path = os.path.join(ROOT, "profiles", name)
+        if not os.path.exists(path):
+            continue
+        rows = list(csv.reader(open(path)))
+        col = None
+        for row in rows:
+            if row and row[0] == "Kernel Name":
+                col = next((i for i in range(2, len(row)) if kernel in row[i]), None)
+        if col is None:
+            continue
+        tot, seen = 0.0, set()
+        for row in rows:
+            if len(row) > col and row[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and row[0] not in seen:
+                seen.add(row[0])
+                tot += float(row[col]) * mult.get(row[1], 1.0)
+        if tot:
+            return tot, name
+    return None, None
 
 
 class ClockSampler:
@@ -578,8 +590,8 @@ def bench_shuffle(E, mode, steps, warmup, want_cpu):
         alg = shuffle_imad_per_proof(n, Q, m, mode, Wn, 16)
         lg = (ng.bit_length() - 1) if mode == "fixed" else 0
         h2d = k * 32 + B * (4 * k + 32 + 32 * m + 32) + B * 32 * m + B * plen + B * 32 * m
-        fb_kernel = "k_fb_msm_warp" if B >= 16 * 148 else "k_fb_msm"
-        traffic_file = "r2_ncu_full_k_fb_msm_warp.csv" if fb_kernel == "k_fb_msm_warp" else "r1_ncu_full_k_fb_msm.csv"
+        fb_kernel = "k_fb_msm_warp_d" if B >= 16 * 148 and FB_WINDOW_BITS in (8, 16) else ("k_fb_msm_warp" if B >= 16 * 148 else "k_fb_msm")
+        traffic, traffic_file = _ncu_traffic(["r2f_ncu_full_fb_msm_warp.csv", "r2f_ncu_full_fb_msm_warp_d.csv"], fb_kernel)
         gens_n = 2 * ng + 2
         table_gib = gens_n * Wn * 2 ** (FB_WINDOW_BITS - 1) * 96 / 2**30
         out = {
@@ -622,9 +634,10 @@ def bench_shuffle(E, mode, steps, warmup, want_cpu):
                          "achieved": ach / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD.WIDE.U32/s",
                          "frac": ach / imad_peak, "kernel_ms": fb_ms, "point_adds_per_s": (fb_madd + fb_add) / (fb_ms * 1e-3),
                          "peak_source": E["peak_src"], "imad_probes": E["imad_probes"],
-                         "traffic": _ncu_traffic(traffic_file),
+                         "traffic": traffic,
                          "traffic_source": f"profiles/{traffic_file} (dram read+write of one A_I-shaped launch; algorithmic gathers = "
-                                           f"mixed adds x 96 B = {fb_madd * 96 / 1e9:.2f} GB)",
+                                           f"mixed adds x 96 B = {fb_madd * 96 / 1e9:.2f} GB; a 96-byte entry lies in one or two 128-byte "
+                                           "lines, 1.5 on average, and the L2 fills whole lines: 192 B per gather - DESIGN.md section 3.2)",
                          "whole_step": {"imad_per_proof": alg["imad"], "breakdown": alg,
                                         "frac_of_peak": alg["imad"] * B / (ms_step * 1e-3) / imad_peak,
                                         "note": "algorithmic IMAD.WIDE.U32 of one prove + verify (DESIGN.md section 6) x batch / ms_per_step / peak"},
@@ -912,6 +925,13 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if os.environ.get("BPP_BLOCKING_SYNC") == "1":
+        # tuning hook: host threads sleep in cudaStreamSynchronize instead of spinning (cudaDeviceScheduleBlockingSync);
+        # must precede the creation of the device's primary context
+        import ctypes
+        rt = ctypes.CDLL("libcudart.so.12")
+        rt.cudaSetDevice(local)
+        rt.cudaSetDeviceFlags(4)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -1166,6 +1186,7 @@ def run_ours(args):
             W_win = (253 + c_win - 1) // c_win
             imads_alg = IMAD_MADD * n * W_win + IMAD_ADD * 2 * (2 ** (c_win - 1) - 1) * W_win + IMAD_DBL * c_win * (W_win - 1)
             ach = imads_acc / acc_t
+            acc_traffic, acc_traffic_file = _ncu_traffic(["r2f_ncu_full_msm2p20.csv", "r2_ncu_full_msm2p20.csv"], "k_bucket_accum")
             msm = {
                 "metric": "MSM points/sec at 2^20", "value": total_points * msm_steps / (ms_res * 1e-3), "unit": "points/s",
                 "n_gpus": world, "steps": msm_steps, "ms_per_step": ms_res / msm_steps, "scaling": "weak",
@@ -1194,8 +1215,8 @@ def run_ours(args):
                 "roofline": {"bound": "imad", "kernel": "k_bucket_accum", "achieved": ach / 1e12, "peak": imad_peak / 1e12,
                              "unit": "T IMAD.WIDE.U32/s", "frac": ach / imad_peak, "kernel_ms": float(phases[3]),
                              "point_adds_per_s": ops["mixed_adds"] / acc_t, "peak_source": peak_src,
-                             "traffic": _ncu_traffic("r1_ncu_full_k_bucket_accum.csv") if args.log_n == 20 else None,
-                             "traffic_source": "profiles/r1_ncu_full_k_bucket_accum.csv (dram read+write per launch)",
+                             "traffic": acc_traffic if args.log_n == 20 else None,
+                             "traffic_source": f"profiles/{acc_traffic_file} (dram read+write of one k_bucket_accum launch, 2^20 points, one window group)",
                              "whole_msm": {"imad_algorithmic": imads_alg, "formula": "SURVEY 8(d): 504 N W + 648 * 2 (2^(c-1) - 1) W + 464 c (W - 1), "
                                                                                      f"c = {c_win}, W = {W_win}",
                                            "frac_of_peak": imads_alg / (ms_res / msm_steps * 1e-3) / imad_peak,

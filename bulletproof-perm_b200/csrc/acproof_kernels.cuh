@@ -173,6 +173,52 @@ __global__ void __launch_bounds__(WIT_THREADS) k_shuffle_witness(const uint32_t 
         sc_store(ACP_PTR(blk, lay, p, lay.aO + gb + i), prev);
     }
 }
+// Short chains, many proofs (the 52-card batch): one THREAD per (chain, proof) walks its chain serially - 2 multiplications
+// per factor (f -> f R, then P <- P f R / R: the running product stays in standard form) instead of the ~13 per thread of
+// the block scan above, whose log-depth only pays when a single chain has to fill the GPU (k_shuffle_witness on the
+// 4096-proof 52-card batch: 510 us = 7 % of a prove + verify step; this form: 8192 threads, ~100 multiplications deep).
+__global__ void __launch_bounds__(64) k_shuffle_witness_serial(const uint32_t *__restrict__ deck /* k x 8 */,
+                                                               const uint32_t *__restrict__ perm /* B x k */,
+                                                               const uint32_t *__restrict__ xs /* B x 8 */, uint32_t k, uint32_t B,
+                                                               acp_layout lay, uint32_t *__restrict__ blk,
+                                                               uint32_t *__restrict__ vout /* B x m x 8 */) {
+    const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= 2 * B) return;
+    const uint32_t c = id & 1u, p = id >> 1;
+    const uint32_t gb = c * (k - 1), vb = c * k, len = k - 1;
+    const uint32_t *pp = perm + (size_t)p * k;
+    uint32_t *vp = vout + 8 * (size_t)p * lay.m;
+    sc x, r2, v, f, fm, P;
+    sc_load(x, xs + 8 * (size_t)p);
+    sc_const(r2, SC_R2);
+    BPP_ASSERT(!c || pp[0] < k);
+    sc_load(v, deck + 8 * (size_t)(c ? pp[0] : 0));
+    sc_store(vp + 8 * (size_t)vb, v);
+    sc_sub(P, v, x);
+    sc_store(ACP_PTR(blk, lay, p, lay.aL + gb), P);
+#pragma unroll 1
+    for (uint32_t i = 0; i < len; i++) {
+        BPP_ASSERT(!c || pp[i + 1] < k);
+        sc_load(v, deck + 8 * (size_t)(c ? pp[i + 1] : i + 1));
+        sc_store(vp + 8 * (size_t)(vb + i + 1), v);
+        sc_sub(f, v, x);
+        sc_store(ACP_PTR(blk, lay, p, lay.aR + gb + i), f);
+        if (i) sc_store(ACP_PTR(blk, lay, p, lay.aL + gb + i), P);   // a_L[gb + i] = a_O[gb + i - 1]
+        sc_mont_noinline(fm, f, r2);
+        sc_mont_noinline(P, P, fm);
+        sc_store(ACP_PTR(blk, lay, p, lay.aO + gb + i), P);
+    }
+    if (c == 0) {
+        sc_store(vp + 8 * (size_t)(2 * k), x);
+        sc z;
+        sc_set0(z);
+        for (uint32_t q = 2 * k - 2; q < 2 * k; q++) {
+            sc_store(ACP_PTR(blk, lay, p, lay.aL + q), z);
+            sc_store(ACP_PTR(blk, lay, p, lay.aR + q), z);
+            sc_store(ACP_PTR(blk, lay, p, lay.aO + q), z);
+        }
+    }
+}
 // gamma (B x m, staged contiguously) -> the proofs' scalar blocks
 __global__ void __launch_bounds__(128) k_acp_place_gamma(const uint32_t *__restrict__ st, acp_layout lay, uint32_t *__restrict__ blk) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
@@ -565,7 +611,26 @@ __global__ void __launch_bounds__(FB_THREADS, FB_WARP_MINBLOCKS) k_fb_msm_warp_d
             return true;
         }
     };
-    {
+#if defined(FB_PINGPONG) && FB_PINGPONG
+    {   // variant (measured, not faster): two entry buffers used in turn, unrolled by two, so that no buffer is copied
+        const uint32_t *ptr0 = nullptr, *ptr1 = nullptr;
+        bool neg0 = false, neg1 = false;
+        ge_niels q0, q1;
+        bool ok0 = advance(ptr0, neg0);
+        if (ok0) ge_niels_load(q0, ptr0);
+#pragma unroll 1
+        while (ok0) {
+            const bool ok1 = advance(ptr1, neg1);
+            if (ok1) ge_niels_load(q1, ptr1);
+            ge_madd(acc, acc, q0, neg0);
+            if (!ok1) break;
+            ok0 = advance(ptr0, neg0);
+            if (ok0) ge_niels_load(q0, ptr0);
+            ge_madd(acc, acc, q1, neg1);
+        }
+    }
+#else
+    {   // software pipelined: the gather of the next entry is issued before the current mixed add
         const uint32_t *ptr = nullptr, *ptr_n = nullptr;
         bool neg = false, neg_n = false;
         bool ok = advance(ptr, neg);
@@ -582,6 +647,7 @@ __global__ void __launch_bounds__(FB_THREADS, FB_WARP_MINBLOCKS) k_fb_msm_warp_d
             ok = ok_n;
         }
     }
+#endif
 #pragma unroll 1
     for (int d = 16; d >= 1; d >>= 1) {   // warp reduction: five shuffle steps
         ge_ext o2;

@@ -82,11 +82,36 @@ struct bpp_acp_batch {
     uint8_t *d_rlc_out = nullptr;
     uint32_t *h_rlc_flag = nullptr;
     std::vector<bpp_host::Transcript> tr;
+    // BPP_ACP_TRACE=1: stage timeline of prove / verify (timing events on the caller's stream, printed to stderr)
+    bool trace = false;
+    std::vector<std::pair<const char *, cudaEvent_t>> marks;
 };
 
 static uint32_t acp_next_pow2(uint32_t n) { uint32_t p = 1; while (p < n) p <<= 1; return p; }
 static uint32_t acp_log2(uint32_t p) { uint32_t l = 0; while ((1u << l) < p) l++; return l; }
 
+static void acp_mark(bpp_acp_batch *b, const char *name) {
+    if (!b->trace) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, b->ctx->stream);
+    b->marks.emplace_back(name, e);
+}
+static void acp_marks_dump(bpp_acp_batch *b, const char *what) {
+    if (!b->trace || b->marks.empty()) return;
+    cudaStreamSynchronize(b->ctx->stream);
+    fprintf(stderr, "[acp trace] %s:", what);
+    for (size_t i = 1; i < b->marks.size(); i++) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, b->marks[i - 1].second, b->marks[i].second);
+        fprintf(stderr, " %s %.0f us |", b->marks[i].first, ms * 1e3f);
+    }
+    float tot = 0;
+    cudaEventElapsedTime(&tot, b->marks.front().second, b->marks.back().second);
+    fprintf(stderr, " total %.0f us\n", tot * 1e3f);
+    for (auto &m : b->marks) cudaEventDestroy(m.second);
+    b->marks.clear();
+}
 static acp_layout acp_make_layout(uint32_t n_, uint32_t Q, uint32_t m, int mode) {
     acp_layout L;
     uint32_t o = 0;
@@ -525,6 +550,7 @@ extern "C" int bpp_acp_batch_create(bpp_ctx *ctx, const bpp_circuit *cir, const 
     if (const char *e = getenv("BPP_FB_WARP")) b->fb_warp_per_output = e[0] != '0';
     if (const char *e = getenv("BPP_FB_STAGE")) b->fb_stage_scalars = e[0] != '0';
     b->fb_digits = fb_digits_default();
+    if (const char *e = getenv("BPP_ACP_TRACE")) b->trace = e[0] == '1';
     if (const char *e = getenv("BPP_IPA_TAIL")) b->ipa_fused_tail = e[0] != '0';
     b->label.assign(label, label + label_len);
     const size_t B = count, lg = b->lay.lg, per = cir->m + 8 + 2 * lg, nch = 6 + lg;   // challenges per proof + the two weights
@@ -777,10 +803,16 @@ extern "C" int bpp_acp_batch_gen_shuffle_witness(bpp_acp_batch *b, const uint8_t
     CK(ctx, cudaMemcpyAsync(b->d_seeds, seeds, (size_t)B * 32, cudaMemcpyHostToDevice, ctx->stream));
     k_acp_place_gamma<<<dim3((L.m + 127) / 128, B), 128, 0, ctx->stream>>>((const uint32_t *)st, L, b->d_blk);
     LAUNCH_CHECK(ctx);
-    unsigned wit_threads = 32;
-    while (wit_threads < WIT_THREADS && wit_threads < k - 1) wit_threads <<= 1;
-    k_shuffle_witness<<<dim3(2, B), wit_threads, 0, ctx->stream>>>((const uint32_t *)(st + m32), (const uint32_t *)(st + m32 + dk + xb),
-                                                                  (const uint32_t *)(st + m32 + dk), k, L, b->d_blk, b->d_vwit);
+    if (k <= 64 || (k <= 1024 && 2ull * B >= 2048)) {
+        // short chains or enough of them: a thread per chain
+        k_shuffle_witness_serial<<<(2 * B + 63) / 64, 64, 0, ctx->stream>>>((const uint32_t *)(st + m32), (const uint32_t *)(st + m32 + dk + xb),
+                                                                           (const uint32_t *)(st + m32 + dk), k, B, L, b->d_blk, b->d_vwit);
+    } else {
+        unsigned wit_threads = 32;
+        while (wit_threads < WIT_THREADS && wit_threads < k - 1) wit_threads <<= 1;
+        k_shuffle_witness<<<dim3(2, B), wit_threads, 0, ctx->stream>>>((const uint32_t *)(st + m32), (const uint32_t *)(st + m32 + dk + xb),
+                                                                      (const uint32_t *)(st + m32 + dk), k, L, b->d_blk, b->d_vwit);
+    }
     LAUNCH_CHECK(ctx);
     b->have_vwit = true;
     return BPP_OK;
@@ -833,14 +865,14 @@ static int acp_fetch_commitments(bpp_acp_batch *b) {
 }
 static void acp_host_append_commitments(bpp_host::Transcript &t, const uint8_t *V, uint32_t m) {
     t.append_u64("m", m);
+    std::vector<uint8_t> digs(32 * (size_t)TR_V_CHUNKS(m));
     for (uint32_t c = 0; c < m; c += TR_V_CHUNK) {   // two levels, see k_tr_vchunks
         bpp_host::Transcript ch((const uint8_t *)"acp-V", 5);
         ch.append_u64("chunk", c / TR_V_CHUNK);
         ch.append_message("V", V + 32 * (size_t)c, 32 * (size_t)((m - c) < TR_V_CHUNK ? (m - c) : TR_V_CHUNK));
-        uint8_t d[32];
-        ch.challenge_bytes("d", d, 32);
-        t.append_message("Vd", d, 32);
+        ch.challenge_bytes("d", digs.data() + 32 * (size_t)(c / TR_V_CHUNK), 32);
     }
+    t.append_message("Vd", digs.data(), digs.size());   // the chunk digests, concatenated, as one message
 }
 // device transcripts: the chunk digests of the resident commitments, on the second side stream
 static int acp_fork_vchunks(bpp_acp_batch *b) {
@@ -1025,6 +1057,7 @@ extern "C" int bpp_acp_batch_prove(bpp_acp_batch *b) {
     }
     if (bind_V && !b->host_transcripts && (rc = acp_fork_vchunks(b))) return rc;   // beside the commitment MSMs
     // create(): randomness alpha,beta,ro,s_l,s_r (+ the five tau drawn later from the same stream)
+    acp_mark(b, "start");
     const uint32_t nrand = 3 + 2 * n + 5;
     k_acp_rng<<<dim3((nrand + 127) / 128, B), 128, 0, s>>>(b->d_seeds, L, nrand, b->d_blk);
     LAUNCH_CHECK(ctx);
@@ -1054,8 +1087,10 @@ extern "C" int bpp_acp_batch_prove(bpp_acp_batch *b) {
             CK(ctx, cudaStreamWaitEvent(s, b->ev_join3, 0));
         }
     }
+    acp_mark(b, "rng+A_I,A_O,S");
     k_compress_strided<<<(B * 3 + 127) / 128, 128, 0, s>>>(b->d_ext8, 8, 0, 3, B, b->d_pts8);
     LAUNCH_CHECK(ctx);
+    acp_mark(b, "compress");
     // transcripts: dom-sep, A_I, A_O, S -> y, z
     if (!b->host_transcripts) {
         if (bind_V) CK(ctx, cudaStreamWaitEvent(s, b->ev_join2, 0));
@@ -1082,11 +1117,14 @@ extern "C" int bpp_acp_batch_prove(bpp_acp_batch *b) {
         });
         if ((rc = acp_put_challenges(b, L.y, 2))) return rc;
     }
+    acp_mark(b, "y,z");
     if ((rc = acp_challenge_dependent_scalars(b))) return rc;
+    acp_mark(b, "scalars");
     k_acp_dots<<<dim3(10, B), 128, 0, s>>>(L, 0, b->d_blk);
     LAUNCH_CHECK(ctx);
     k_acp_tcoef<<<(B + 63) / 64, 64, 0, s>>>(L, B, b->mode, b->d_blk);
     LAUNCH_CHECK(ctx);
+    acp_mark(b, "dots");
     {   // T_i = t_i*g + tau_i*h for i in (1,3,4,5,6)
         fb_shape sh = acp_shape(5);
         acp_seg(sh, L.tsel, 1, 0, 1); acp_seg(sh, L.tau, 1, 1, 1);
@@ -1094,6 +1132,7 @@ extern "C" int bpp_acp_batch_prove(bpp_acp_batch *b) {
     }
     k_compress_strided<<<(B * 5 + 127) / 128, 128, 0, s>>>(b->d_ext8, 8, 3, 5, B, b->d_pts8);
     LAUNCH_CHECK(ctx);
+    acp_mark(b, "T_i");
     const int mode = b->mode;
     if (!b->host_transcripts) {
         TR_LAUNCH(k_tr_prove_x, B, s, b->d_pts8, L, B, mode, b->d_tr, b->d_blk);
@@ -1113,15 +1152,24 @@ extern "C" int bpp_acp_batch_prove(bpp_acp_batch *b) {
         });
         if ((rc = acp_put_challenges(b, L.x, 1))) return rc;
     }
+    acp_mark(b, "x");
     k_acp_final<<<dim3((L.np + 127) / 128, B), 128, 0, s>>>(L, b->d_blk);
     LAUNCH_CHECK(ctx);
     k_acp_dots<<<dim3(2, B), 128, 0, s>>>(L, 10, b->d_blk);
     LAUNCH_CHECK(ctx);
     k_acp_final2<<<(B + 63) / 64, 64, 0, s>>>(L, B, b->mode, b->d_blk);
     LAUNCH_CHECK(ctx);
-    if (b->mode == 2) return acp_prove_ipa(b);
+    acp_mark(b, "l,r,t,tau_x,mu");
+    if (b->mode == 2) {
+        rc = acp_prove_ipa(b);
+        acp_mark(b, "inner-product rounds");
+        acp_marks_dump(b, "prove");
+        return rc;
+    }
     k_acp_pack<<<dim3((b->proof_len / 32 + 127) / 128, B), 128, 0, s>>>(L, B, b->d_pts8, b->d_blk, b->d_proofs, b->proof_len);
     LAUNCH_CHECK(ctx);
+    acp_mark(b, "pack");
+    acp_marks_dump(b, "prove");
     return BPP_OK;
 }
 
@@ -1164,13 +1212,17 @@ static int acp_verify_rlc(bpp_acp_batch *b, uint32_t per, int check_t, bool *dec
     bpp_points view;
     view.niels = b->d_dyn;
     view.n = N;
+    acp_mark(b, "rlc-scalars");
     int rc = msm_enqueue(ctx, b->d_rlc_sc, &view, 0, N, b->d_rlc_out, 1, true);
     view.niels = nullptr;
     if (rc) return rc;
+    acp_mark(b, "rlc-msm");
     k_rlc_accept<<<(B + 127) / 128, 128, 0, s>>>(b->d_rlc_out, L, B, L.rho, b->d_blk, b->d_accept, b->d_rlc_flag);
     LAUNCH_CHECK(ctx);
     CK(ctx, cudaMemcpyAsync(b->h_rlc_flag, b->d_rlc_flag, 4, cudaMemcpyDeviceToHost, s));
+    acp_mark(b, "accept");
     CK(ctx, cudaStreamSynchronize(s));
+    acp_marks_dump(b, "verify");
     *decided = b->h_rlc_flag[0] == 0;
     return BPP_OK;
 }
@@ -1294,6 +1346,7 @@ extern "C" int bpp_acp_batch_verify(bpp_acp_batch *b, const uint8_t *verifier_se
     cudaStream_t s = ctx->stream;
     int rc;
     uint8_t seed[32];
+    acp_mark(b, "start");
     k_acp_unpack<<<dim3((b->proof_len / 32 + 127) / 128, B), 128, 0, s>>>(L, B, b->d_proofs, b->proof_len, b->d_blk, b->d_pts8);
     LAUNCH_CHECK(ctx);
     CK(ctx, cudaEventRecord(b->ev_fork, s));
@@ -1339,13 +1392,18 @@ extern "C" int bpp_acp_batch_verify(bpp_acp_batch *b, const uint8_t *verifier_se
         });
         if ((rc = acp_put_challenges(b, L.y, 5))) return rc;
     }
+    acp_mark(b, "transcript");
     if ((rc = acp_challenge_dependent_scalars(b))) return rc;
     k_acp_dots<<<dim3(2, B), 128, 0, s>>>(L, 9, b->d_blk);  // sigma, <l, r>
     LAUNCH_CHECK(ctx);
+    acp_mark(b, "scalars");
     if (!b->host_transcripts) CK(ctx, cudaStreamWaitEvent(s, b->ev_join2, 0));   // w, rho0 (k_tr_weights)
+    acp_mark(b, "wait-weights");
     k_acp_vscal<<<dim3((n + m + 1 + 127) / 128, B), 128, 0, s>>>(L, b->d_blk);
     LAUNCH_CHECK(ctx);
+    acp_mark(b, "vscal");
     CK(ctx, cudaStreamWaitEvent(s, b->ev_join, 0));   // decompressed points + bad flags (forked after the unpack)
+    acp_mark(b, "wait-decompress");
     if (b->batch_rlc && mode != 0 && (size_t)B * per >= 1024) {   // `reference` mode never accepts: nothing to gain from the combined check
         bool decided = false;
         if ((rc = acp_verify_rlc(b, per, 1, &decided))) return rc;

@@ -390,6 +390,18 @@ int msm_wait_pending(bpp_ctx *ctx, bool keep_latest) {
     return BPP_OK;
 }
 
+// Tuning hook (BPP_ACC_SMEM=<bytes>): unused dynamic shared memory requested by the accumulate launch, which caps its
+// resident blocks per SM below the four its 128 registers allow (e.g. 60000 -> three) and so leaves register-file room
+// for the sort blocks of the next window group / the next submitted MSM.  0 (default) = no cap.
+static size_t msm_acc_pad_smem() {
+    static long v = -1;
+    if (v < 0) {
+        const char *e = getenv("BPP_ACC_SMEM");
+        v = e ? atol(e) : 0;
+        if (v > 48 * 1024) cudaFuncSetAttribute(k_bucket_accum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v);
+    }
+    return (size_t)v;
+}
 // Enqueues one MSM.  join = true: the result is in d_out in stream order on the caller's stream when the call returns
 // (the classic contract).  join = false (bpp_msm_submit_dev): the caller's stream is not made to wait; the result is
 // valid after bpp_msm_wait, and up to two submitted MSMs are in flight (the tail of one beside the sort and
@@ -540,7 +552,7 @@ int msm_enqueue(bpp_ctx *ctx, const uint32_t *d_scalars, const bpp_points *pts, 
             CK(ctx, cudaStreamWaitEvent(s_acc, ctx->ev_sorted[g], 0));
         }
         trace_mark(ctx, s_acc, "accum>", g);
-        k_bucket_accum<<<(group_tiles + BPP_ACC_THREADS - 1) / BPP_ACC_THREADS, BPP_ACC_THREADS, 0, s_acc>>>(
+        k_bucket_accum<<<(group_tiles + BPP_ACC_THREADS - 1) / BPP_ACC_THREADS, BPP_ACC_THREADS, msm_acc_pad_smem(), s_acc>>>(
             niels, entries, offsets, ends, (uint32_t)n, B, tpw, group_tiles, tile_len, buckets, partials);
         LAUNCH_CHECK(ctx);
         if (prof) cudaEventRecord(ctx->ev[4], s);

@@ -252,12 +252,11 @@ def commitment_digests(V):
 
 def append_commitments(trans: Transcript, V, m: int):
     """Binds the value commitments to the transcript: m as a u64 under the label "m", then the chunk digests of
-    commitment_digests under "Vd".  (bulletproofs 4.0.0's R1CS prover appends every V_j to the one transcript at commit
+    commitment_digests, concatenated, as one message under "Vd".  (bulletproofs 4.0.0's R1CS prover appends every V_j to the one transcript at commit
     time; the two-level form binds the same bytes and keeps the hashing off the critical path.)  V: points or encodings."""
     assert V is not None and len(V) == m
     trans.append_u64(b"m", m)
-    for d in commitment_digests(V):
-        trans.append_message(b"Vd", d)
+    trans.append_message(b"Vd", b"".join(commitment_digests(V)))
 
 
 # ------------------------------------------------------------------ circuit_lib.rs --------

@@ -324,10 +324,12 @@ static int ge_ristretto_eq(const ge_ext *p, const ge_ext *q) {
  * encodings, what a verifier is handed) is used when given, else the points are compressed here. */
 #define V_CHUNK 64
 static void tr_append_commitments(strobe *tr, const ge_ext *V, const u8 *V_enc, size_t m) {
-    u8 mb[8], dig[32], buf[32 * V_CHUNK];
+    u8 mb[8], buf[32 * V_CHUNK];
+    const size_t nch = (m + V_CHUNK - 1) / V_CHUNK;
+    u8 *digs = (u8 *)malloc(32 * nch);
     for (int i = 0; i < 8; i++) mb[i] = (u8)((u64)m >> (8 * i));
     tr_append(tr, "m", mb, 8);
-    for (size_t c = 0; c < m; c += V_CHUNK) {   /* one sponge per chunk of 64 commitments, its digest under "Vd" */
+    for (size_t c = 0; c < m; c += V_CHUNK) {   /* one sponge per chunk of 64 commitments */
         strobe ch; tr_new(&ch, (const u8 *)"acp-V", 5);
         for (int i = 0; i < 8; i++) mb[i] = (u8)((u64)(c / V_CHUNK) >> (8 * i));
         tr_append(&ch, "chunk", mb, 8);
@@ -337,9 +339,10 @@ static void tr_append_commitments(strobe *tr, const ge_ext *V, const u8 *V_enc, 
             else ristretto_compress(buf + 32 * cnt, &V[j]);
         }
         tr_append(&ch, "V", buf, 32 * cnt);   /* the chunk's encodings as one message */
-        tr_challenge_bytes(&ch, "d", dig, 32);
-        tr_append(tr, "Vd", dig, 32);
+        tr_challenge_bytes(&ch, "d", digs + 32 * (c / V_CHUNK), 32);
     }
+    tr_append(tr, "Vd", digs, 32 * nch);        /* the chunk digests, concatenated, as one message */
+    free(digs);
 }
 
 /* lib.rs:219-231 / circuit_lib.rs:133-585.  W_* dense, row-major: W_L,W_R,W_O n x Q, W_V m x Q.

@@ -20,6 +20,9 @@ import torch
 be = bpperm_b200.Backend(0)
 stream = torch.cuda.current_stream()
 be.set_stream(stream.cuda_stream)
+import os
+if os.environ.get("BPP_GROUPS"):
+    be.set_msm_groups(int(os.environ["BPP_GROUPS"]))
 G = bpperm_b200.acproof
 n, Q, m, WL, WR, WO, WV, c = bpperm_b200.weights.shuffle_circuit(k)
 ng = G.next_pow2(n) if mode == "fixed" else n
