@@ -192,7 +192,11 @@ def shuffle_witness_bytes(k, deck, perm_row, x_row):
     return _sc_bytes(a_L), _sc_bytes(a_R), _sc_bytes(a_O), _sc_bytes(v)
 
 
-N_LANES = int(os.environ.get("BPP_LANES", "3"))   # batches in flight in the pipelined legs
+# batches in flight in the pipelined legs.  Six since round 2: on an 8-GPU host the per-GPU copy bandwidth halves (the
+# one-batch-at-a-time e2e step goes from 9.5 to 11.2 ms), a lane's prove -> copy out -> copy in -> verify chain gets longer,
+# and three lanes no longer cover it (8 GPUs, e2e: 3 lanes 3.56 M proofs/s, 4: 3.78 M, 6: 4.23 M, 8: 4.04 M;
+# profiles/r2f_shuffle_8gpu_lanes*.json); on one GPU six are no worse than three (586 K against 570-582 K e2e).
+N_LANES = int(os.environ.get("BPP_LANES", "6"))
 LANE_PRIORITY_SPLIT = os.environ.get("BPP_LANE_SPLIT", "1") != "0"
 FB_WINDOW_BITS = int(os.environ.get("BPP_FB_WINDOW", "16"))   # fixed-base table window: 16 windows x 32768 entries x 96 B = 50 MB per generator
 

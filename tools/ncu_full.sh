@@ -21,5 +21,6 @@ cap() {   # name, keep(0/1), regex, launch-skip, launch-count, command...
 cap fb_msm_warp 1 'k_fb_msm_warp' 30 1 python tools/prof_round.py 52 fixed 4096 16
 cap ipa_round 0 'k_ipa_round|k_ipa_challenge' 20 4 python tools/prof_round.py 52 fixed 4096 16
 cap acp_misc 0 'k_acp_decompress$|k_acp_dots|k_acp_vscal_fixed|k_compress_strided|k_pow_fill|k_acp_csr$|k_tr_verify|k_tr_vchunks|k_tr_weights' 30 12 python tools/prof_round.py 52 fixed 4096 16
+cap large_deck_round 0 'k_ipa_lr_tail|k_ipa_round' 20 4 python tools/prof_round.py 4096 fixed 1 8
 BPP_GROUPS=1 cap msm2p20 0 'k_bucket_accum|k_digit_scatter|k_digit_hist|k_bucket_fixup|k_msm_finish|k_node_merge' 20 14 python tools/prof_msm.py
 du -sh gpurun_out
