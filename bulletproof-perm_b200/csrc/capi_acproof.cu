@@ -76,6 +76,7 @@ struct bpp_acp_batch {
     // dynamic points + the shared generators (appended to d_dyn), its compressed result, the fall-back flag
     bool batch_rlc = true;
     bool fb_stage_scalars = true;   // k_fb_msm_warp<true>: the warp's scalars staged in shared memory (BPP_FB_STAGE=0: off)
+    bool decompress_late = false;   // verifier: fork the point decompression after the transcript replay (BPP_DECOMPRESS_LATE=1)
     bool ipa_fused_tail = true;     // k_ipa_lr_tail for split launches (BPP_IPA_TAIL=0: the three separate launches)
     bool fb_digits = true;          // k_fb_msm_warp_d: digits staged, c = 16 / 8 (BPP_FB_DIGITS=0: the form above; tuning hook)
     uint32_t *d_rlc_sc = nullptr, *d_rlc_flag = nullptr;
@@ -552,6 +553,7 @@ extern "C" int bpp_acp_batch_create(bpp_ctx *ctx, const bpp_circuit *cir, const 
     b->fb_digits = fb_digits_default();
     if (const char *e = getenv("BPP_ACP_TRACE")) b->trace = e[0] == '1';
     if (const char *e = getenv("BPP_IPA_TAIL")) b->ipa_fused_tail = e[0] != '0';
+    if (const char *e = getenv("BPP_DECOMPRESS_LATE")) b->decompress_late = e[0] == '1';
     b->label.assign(label, label + label_len);
     const size_t B = count, lg = b->lay.lg, per = cir->m + 8 + 2 * lg, nch = 6 + lg;   // challenges per proof + the two weights
     {   // small batches of large circuits: split each fixed-base MSM over several blocks (k_fb_sum_splits adds them)
@@ -1240,14 +1242,22 @@ static int acp_verify_fixed(bpp_acp_batch *b, const uint8_t *verifier_seed) {
     k_acp_unpack_fixed<<<dim3((b->proof_len / 32 + 127) / 128, B), 128, 0, s>>>(L, b->d_proofs, b->proof_len, b->d_blk, b->d_pts8,
                                                                                b->d_lr, b->d_tx3);
     LAUNCH_CHECK(ctx);
-    CK(ctx, cudaEventRecord(b->ev_fork, s));
-    CK(ctx, cudaStreamWaitEvent(b->aux, b->ev_fork, 0));
-    CK(ctx, cudaMemsetAsync(b->d_bad, 0, (size_t)B * 4, b->aux));
-    k_acp_decompress<<<(B * (m + 8) + 127) / 128, 128, 0, b->aux>>>(b->d_V, b->d_pts8, m, B, per, b->d_dyn, b->d_bad);
-    LAUNCH_CHECK(ctx);
-    k_acp_decompress_lr<<<(B * 2 * lg + 127) / 128, 128, 0, b->aux>>>(b->d_lr, m, lg, B, b->d_dyn, b->d_bad);
-    LAUNCH_CHECK(ctx);
-    CK(ctx, cudaEventRecord(b->ev_join, b->aux));
+    // point decompression (IMAD-bound, fills the GPU) on `aux`, beside the dependent chain.  decompress_late: forked
+    // only after the transcript replay - the few warps of the hashing kernels otherwise share every SM with it and take
+    // three times as long (stage timeline)
+    auto fork_decompress = [&]() -> int {
+        CK(ctx, cudaEventRecord(b->ev_fork, s));
+        CK(ctx, cudaStreamWaitEvent(b->aux, b->ev_fork, 0));
+        CK(ctx, cudaMemsetAsync(b->d_bad, 0, (size_t)B * 4, b->aux));
+        k_acp_decompress<<<(B * (m + 8) + 127) / 128, 128, 0, b->aux>>>(b->d_V, b->d_pts8, m, B, per, b->d_dyn, b->d_bad);
+        LAUNCH_CHECK(ctx);
+        k_acp_decompress_lr<<<(B * 2 * lg + 127) / 128, 128, 0, b->aux>>>(b->d_lr, m, lg, B, b->d_dyn, b->d_bad);
+        LAUNCH_CHECK(ctx);
+        CK(ctx, cudaEventRecord(b->ev_join, b->aux));
+        return BPP_OK;
+    };
+    const bool late = b->decompress_late && !b->host_transcripts;
+    if (!late && (rc = fork_decompress())) return rc;
     if ((rc = acp_set_verifier_seed(b, verifier_seed, seed))) return rc;
     if (!b->host_transcripts) {
         if ((rc = acp_fork_vchunks(b))) return rc;
@@ -1255,6 +1265,7 @@ static int acp_verify_fixed(bpp_acp_batch *b, const uint8_t *verifier_seed) {
         TR_LAUNCH(k_tr_verify, B, s, b->d_proto, b->d_vdig, b->d_pts8, (const uint8_t *)b->d_tx3, b->d_lr, L, B, 2,
                                                         b->d_blk, b->d_tr);
         LAUNCH_CHECK(ctx);
+        if (late && (rc = fork_decompress())) return rc;
         if ((rc = acp_fork_weights(b))) return rc;
     } else {
         CK(ctx, cudaMemcpyAsync(b->h_pts8, b->d_pts8, (size_t)B * 256, cudaMemcpyDeviceToHost, s));
@@ -1349,12 +1360,17 @@ extern "C" int bpp_acp_batch_verify(bpp_acp_batch *b, const uint8_t *verifier_se
     acp_mark(b, "start");
     k_acp_unpack<<<dim3((b->proof_len / 32 + 127) / 128, B), 128, 0, s>>>(L, B, b->d_proofs, b->proof_len, b->d_blk, b->d_pts8);
     LAUNCH_CHECK(ctx);
-    CK(ctx, cudaEventRecord(b->ev_fork, s));
-    CK(ctx, cudaStreamWaitEvent(b->aux, b->ev_fork, 0));
-    CK(ctx, cudaMemsetAsync(b->d_bad, 0, (size_t)B * 4, b->aux));
-    k_acp_decompress<<<(B * per + 127) / 128, 128, 0, b->aux>>>(b->d_V, b->d_pts8, m, B, per, b->d_dyn, b->d_bad);
-    LAUNCH_CHECK(ctx);
-    CK(ctx, cudaEventRecord(b->ev_join, b->aux));
+    auto fork_decompress = [&]() -> int {   // see acp_verify_fixed
+        CK(ctx, cudaEventRecord(b->ev_fork, s));
+        CK(ctx, cudaStreamWaitEvent(b->aux, b->ev_fork, 0));
+        CK(ctx, cudaMemsetAsync(b->d_bad, 0, (size_t)B * 4, b->aux));
+        k_acp_decompress<<<(B * per + 127) / 128, 128, 0, b->aux>>>(b->d_V, b->d_pts8, m, B, per, b->d_dyn, b->d_bad);
+        LAUNCH_CHECK(ctx);
+        CK(ctx, cudaEventRecord(b->ev_join, b->aux));
+        return BPP_OK;
+    };
+    const bool late = b->decompress_late && !b->host_transcripts;
+    if (!late && (rc = fork_decompress())) return rc;
     if ((rc = acp_set_verifier_seed(b, verifier_seed, seed))) return rc;
     const int mode = b->mode;
     if (!b->host_transcripts) {
@@ -1364,6 +1380,7 @@ extern "C" int bpp_acp_batch_verify(bpp_acp_batch *b, const uint8_t *verifier_se
         }
         TR_LAUNCH(k_tr_verify, B, s, b->d_proto, b->d_vdig, b->d_pts8, nullptr, nullptr, L, B, mode, b->d_blk, b->d_tr);
         LAUNCH_CHECK(ctx);
+        if (late && (rc = fork_decompress())) return rc;
         if ((rc = acp_fork_weights(b))) return rc;
     } else {
         CK(ctx, cudaMemcpyAsync(b->h_pts8, b->d_pts8, (size_t)B * 256, cudaMemcpyDeviceToHost, s));

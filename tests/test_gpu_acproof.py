@@ -137,8 +137,8 @@ def test_commit_variables_and_staged_batch(backend):
         g2.free()
 
 
-@pytest.mark.parametrize("k", [2, 5, 52, 300])
-def test_device_shuffle_witness_and_library_circuit_equal_the_oracle(backend, k):
+@pytest.mark.parametrize("k,B", [(2, 3), (5, 3), (52, 3), (300, 3), (70, 1030)])
+def test_device_shuffle_witness_and_library_circuit_equal_the_oracle(backend, k, B):
     """SURVEY 8 row f-1 behind the C ABI: bpp_circuit_create_shuffle + bpp_acp_batch_gen_shuffle_witness against
     oracle/acproof.py shuffle_circuit / shuffle_witness - same commitments and byte-identical proofs as the uploaded
     witness over the Python-built circuit."""
@@ -153,7 +153,8 @@ def test_device_shuffle_witness_and_library_circuit_equal_the_oracle(backend, k)
     cir_lib = G.Circuit.shuffle(backend, k)
     assert (cir_lib.n, cir_lib.Q, cir_lib.m) == (n, Q, m)
     gens = G.Generators(backend, pts[0], pts[1], pts[2:2 + n], pts[2 + n:], 6)
-    B = 3
+    # B = 3: short chains go thread-per-chain (k <= 64), k = 300 through the block scan; (70, 1030): the thread-per-chain
+    # form for medium chains once there are enough of them (k <= 1024 and 2 B >= 2048)
     deck = [(7 * i + 3) % L for i in range(1, k + 1)]
     perms, xs, wit = [], [], []
     for p in range(B):
@@ -168,7 +169,7 @@ def test_device_shuffle_witness_and_library_circuit_equal_the_oracle(backend, k)
                 aO[gb + i] = aL[gb + i] * aR[gb + i] % L
         perms.append(perm.astype(np.uint32).tobytes()); xs.append(x); wit.append((v, aL, aR, aO))
     gamma = [[int.from_bytes(rs.bytes(32), "little") % L for _ in range(m)] for _ in range(B)]
-    seeds = b"".join(bytes([p + 1]) * 32 for p in range(B))
+    seeds = b"".join((p + 1).to_bytes(4, "little") * 8 for p in range(B))
     gam_b = b"".join(_sb(g) for g in gamma)
     # uploaded witness, Python-built circuit
     b1 = G.Batch(backend, cir_py, gens, B)
