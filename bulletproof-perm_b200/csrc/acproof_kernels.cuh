@@ -611,25 +611,6 @@ __global__ void __launch_bounds__(FB_THREADS, FB_WARP_MINBLOCKS) k_fb_msm_warp_d
             return true;
         }
     };
-#if defined(FB_PINGPONG) && FB_PINGPONG
-    {   // variant (measured, not faster): two entry buffers used in turn, unrolled by two, so that no buffer is copied
-        const uint32_t *ptr0 = nullptr, *ptr1 = nullptr;
-        bool neg0 = false, neg1 = false;
-        ge_niels q0, q1;
-        bool ok0 = advance(ptr0, neg0);
-        if (ok0) ge_niels_load(q0, ptr0);
-#pragma unroll 1
-        while (ok0) {
-            const bool ok1 = advance(ptr1, neg1);
-            if (ok1) ge_niels_load(q1, ptr1);
-            ge_madd(acc, acc, q0, neg0);
-            if (!ok1) break;
-            ok0 = advance(ptr0, neg0);
-            if (ok0) ge_niels_load(q0, ptr0);
-            ge_madd(acc, acc, q1, neg1);
-        }
-    }
-#else
     {   // software pipelined: the gather of the next entry is issued before the current mixed add
         const uint32_t *ptr = nullptr, *ptr_n = nullptr;
         bool neg = false, neg_n = false;
@@ -647,7 +628,6 @@ __global__ void __launch_bounds__(FB_THREADS, FB_WARP_MINBLOCKS) k_fb_msm_warp_d
             ok = ok_n;
         }
     }
-#endif
 #pragma unroll 1
     for (int d = 16; d >= 1; d >>= 1) {   // warp reduction: five shuffle steps
         ge_ext o2;
