@@ -891,6 +891,63 @@ __global__ void __launch_bounds__(128) k_acp_dots(acp_layout lay, uint32_t first
     }
 }
 
+// The same dot products for large batches: block per proof, one WARP per dot product (blockDim = 32 x count, dot
+// first + warp): one barrier, a proof's vectors are read by the warps of one block (L1).  The
+// block-per-dot form above launches 10 x B blocks of one multiplication per thread - at B = 4096 its time is block
+// dispatch, not arithmetic (261 us for 4.3 M multiplications) - and stays for small batches, where a single proof's
+// n = 8192 needs the blocks.
+__global__ void __launch_bounds__(320) k_acp_dots_warp(acp_layout lay, uint32_t first, uint32_t *__restrict__ blk) {
+    const uint32_t k = first + (threadIdx.x >> 5), p = blockIdx.x, lane = threadIdx.x & 31;
+    uint32_t ua, vb, len = lay.n;
+    switch (k) {
+        case 0: ua = lay.l1; vb = lay.r0; break;
+        case 1: ua = lay.l1; vb = lay.r1; break;
+        case 2: ua = lay.aO; vb = lay.r0; break;
+        case 3: ua = lay.aO; vb = lay.r1; break;
+        case 4: ua = lay.sl; vb = lay.r0; break;
+        case 5: ua = lay.l1; vb = lay.r3; break;
+        case 6: ua = lay.sl; vb = lay.r1; break;
+        case 7: ua = lay.aO; vb = lay.r3; break;
+        case 8: ua = lay.sl; vb = lay.r3; break;
+        case 9: ua = lay.lin; vb = lay.zWL; break;
+        case 10: ua = lay.l; vb = lay.r; len = lay.np; break;
+        default: ua = lay.zWV; vb = lay.gamma; len = lay.m; break;
+    }
+    const uint32_t *a = ACP_PTR(blk, lay, p, ua), *b = ACP_PTR(blk, lay, p, vb);
+    sc acc, x, y, pr, tot;
+    sc_set0(acc);
+    for (uint32_t i = lane; i < len; i += 32) {
+        sc_load(x, a + 8 * (size_t)i);
+        sc_load(y, b + 8 * (size_t)i);
+        sc_mont(pr, x, y);
+        sc_add(acc, acc, pr);
+    }
+    // the warps leave their integer sums in shared memory; the reductions mod l and out of Montgomery form (three
+    // multiplications each) then run side by side in the first lanes of warp 0 instead of once per warp
+    __shared__ uint32_t sums[10 * 9];
+    uint32_t s9[9];
+    warp_sum9(s9, acc);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) sums[9 * (threadIdx.x >> 5) + i] = s9[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < (blockDim.x >> 5)) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) s9[i] = sums[9 * threadIdx.x + i];
+        sc r2;
+        sc_from9(tot, s9);
+        sc_const(r2, SC_R2);
+        sc_mont(tot, tot, r2);
+        sc_store(ACP_PTR(blk, lay, p, lay.dots + first + threadIdx.x), tot);
+    }
+}
+// host side: the form by batch size
+static inline void acp_dots_launch(const acp_layout &lay, uint32_t first, uint32_t count, uint32_t B, uint32_t *blk, cudaStream_t s) {
+    if (B >= 256 && count <= 10) k_acp_dots_warp<<<B, 32 * count, 0, s>>>(lay, first, blk);
+    else k_acp_dots<<<dim3(count, B), 128, 0, s>>>(lay, first, blk);
+}
+
 // thread per proof: t1..t6, sigma, and the five values committed in T_1,T_3,T_4,T_5,T_6:
 // mode 0 ("reference", circuit_lib.rs:362-406): t(X) evaluated at the integers 1,3,4,5,6;
 // mode 1 ("reference-fixed"): the coefficients t_1,t_3,t_4,t_5,t_6.

@@ -1122,7 +1122,7 @@ extern "C" int bpp_acp_batch_prove(bpp_acp_batch *b) {
     acp_mark(b, "y,z");
     if ((rc = acp_challenge_dependent_scalars(b))) return rc;
     acp_mark(b, "scalars");
-    k_acp_dots<<<dim3(10, B), 128, 0, s>>>(L, 0, b->d_blk);
+    acp_dots_launch(L, 0, 10, B, b->d_blk, s);
     LAUNCH_CHECK(ctx);
     k_acp_tcoef<<<(B + 63) / 64, 64, 0, s>>>(L, B, b->mode, b->d_blk);
     LAUNCH_CHECK(ctx);
@@ -1157,7 +1157,7 @@ extern "C" int bpp_acp_batch_prove(bpp_acp_batch *b) {
     acp_mark(b, "x");
     k_acp_final<<<dim3((L.np + 127) / 128, B), 128, 0, s>>>(L, b->d_blk);
     LAUNCH_CHECK(ctx);
-    k_acp_dots<<<dim3(2, B), 128, 0, s>>>(L, 10, b->d_blk);
+    acp_dots_launch(L, 10, 2, B, b->d_blk, s);
     LAUNCH_CHECK(ctx);
     k_acp_final2<<<(B + 63) / 64, 64, 0, s>>>(L, B, b->mode, b->d_blk);
     LAUNCH_CHECK(ctx);
@@ -1313,7 +1313,7 @@ static int acp_verify_fixed(bpp_acp_batch *b, const uint8_t *verifier_seed) {
         if ((rc = acp_put_challenges(b, L.w, 2, w_off))) return rc;
     }
     if ((rc = acp_challenge_dependent_scalars(b))) return rc;
-    k_acp_dots<<<dim3(1, B), 128, 0, s>>>(L, 9, b->d_blk);   // sigma
+    acp_dots_launch(L, 9, 1, B, b->d_blk, s);   // sigma
     LAUNCH_CHECK(ctx);
     k_ipa_vprep<<<(B + 63) / 64, 64, 0, s>>>(L, B, b->d_blk);
     LAUNCH_CHECK(ctx);
@@ -1411,7 +1411,7 @@ extern "C" int bpp_acp_batch_verify(bpp_acp_batch *b, const uint8_t *verifier_se
     }
     acp_mark(b, "transcript");
     if ((rc = acp_challenge_dependent_scalars(b))) return rc;
-    k_acp_dots<<<dim3(2, B), 128, 0, s>>>(L, 9, b->d_blk);  // sigma, <l, r>
+    acp_dots_launch(L, 9, 2, B, b->d_blk, s);  // sigma, <l, r>
     LAUNCH_CHECK(ctx);
     acp_mark(b, "scalars");
     if (!b->host_transcripts) CK(ctx, cudaStreamWaitEvent(s, b->ev_join2, 0));   // w, rho0 (k_tr_weights)
